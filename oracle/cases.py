@@ -1,0 +1,105 @@
+"""Named parity cases: configs + seeded inputs, shared by the golden generator and the
+tests (so fixtures hold reference OUTPUTS only).  TEST INFRASTRUCTURE ONLY."""
+import torch
+
+from . import synth
+
+# name -> kwargs overriding video_model_and_diffusion_defaults() (script_util.py:40-57).
+# rp_alpha/beta/gamma must be set even with use_rpe_net=True.
+_CFG = {
+    'tiny':      dict(image_size=32, num_channels=64, num_res_blocks=1, T=30),
+    'tiny_nrb2': dict(image_size=32, num_channels=64, num_res_blocks=2, T=30),
+    'c2':        dict(image_size=64, num_channels=128, num_res_blocks=2, T=500),
+    'c4':        dict(image_size=128, num_channels=128, num_res_blocks=2, T=1000),
+}
+
+
+def ref_config(name):
+    c = dict(_CFG[name])
+    c.update(rp_alpha=c['T'], rp_beta=c['T'], rp_gamma=c['T'])
+    return c
+
+
+# (mode, video_length, obs_length, max_frames, step_size)
+STRATEGY_GRID = [
+    ('autoreg', 30, 5, 10, 5), ('autoreg', 500, 36, 20, 7), ('autoreg', 300, 36, 20, 10), ('autoreg', 33, 0, 10, 4),
+    ('independent', 30, 5, 10, 5), ('independent', 300, 36, 20, 7), ('independent', 100, 10, 20, 10),
+    ('exp-past', 300, 36, 20, 8), ('exp-past', 100, 4, 10, 4), ('exp-past', 500, 36, 20, 4),
+    ('really-independent', 50, 5, 10, 3), ('mixed-autoreg-independent', 300, 36, 20, 7),
+    ('hierarchy-2', 300, 36, 20, 10), ('hierarchy-2', 100, 10, 10, 5), ('hierarchy-3', 300, 36, 20, 10),
+    ('hierarchy-2', 64, 0, 16, 8),
+]
+
+UNET_CASES = [
+    # sampling-style window: observed prefix, everything else latent
+    dict(name='tiny_window', cfg='tiny', B=1, F=10, n_obs=[5], n_lat=[5], t=[500],
+         frame_indices=[[0, 1, 2, 3, 4, 5, 6, 7, 8, 9]]),
+    # video_nll-style ragged rows with padding frames (neither observed nor latent)
+    dict(name='tiny_ragged', cfg='tiny', B=2, F=10, n_obs=[3, 6], n_lat=[5, 4], t=[17, 803],
+         frame_indices=[[0, 1, 2, 10, 11, 12, 13, 14, 0, 0], [3, 7, 9, 11, 12, 13, 20, 21, 22, 23]]),
+    dict(name='tiny_nrb2_window', cfg='tiny_nrb2', B=1, F=7, n_obs=[2], n_lat=[5], t=[999],
+         frame_indices=[[4, 29, 10, 11, 12, 13, 14]]),
+]
+
+
+def unet_case_inputs(case):
+    B, F = case['B'], case['F']
+    size = _CFG[case['cfg']]['image_size']
+    x0 = synth.make_video((B, F, 3, size, size), seed=21)
+    x = synth.make_noise((B, F, 3, size, size), seed=22)
+    obs = torch.zeros(B, F, 1, 1, 1)
+    lat = torch.zeros(B, F, 1, 1, 1)
+    for b in range(B):
+        obs[b, :case['n_obs'][b]] = 1
+        lat[b, case['n_obs'][b]:case['n_obs'][b] + case['n_lat'][b]] = 1
+    return dict(x=x, x0=x0, obs_mask=obs, latent_mask=lat, kinda_marg_mask=torch.zeros_like(obs),
+                frame_indices=torch.tensor(case['frame_indices'], dtype=torch.long),
+                t_model=torch.tensor(case['t'], dtype=torch.float32))
+
+
+def model_kwargs_for(inp):
+    return dict(x0=inp['x0'], obs_mask=inp['obs_mask'], latent_mask=inp['latent_mask'],
+                kinda_marg_mask=inp['kinda_marg_mask'], frame_indices=inp['frame_indices'],
+                x_t_minus_1=inp['x0'], observed_frames='x_0')
+
+
+def fake_eps(x, t):
+    """Stand-in network for the sampler-maths fixtures: depends on x and on the (rescaled) t."""
+    return 0.5 * torch.tanh(x) + t.float().view(-1, *([1] * (x.dim() - 1))) / 2000.0
+
+
+DIFFUSION_CASES = [
+    dict(name='full1000', schedule='linear', respacing='', shape=(2, 4, 3, 8, 8),
+         ts=dict(t0=[0, 0], tmid=[1, 517], tend=[999, 998]), t_seq=[999, 500, 1, 0]),
+    dict(name='ddim10', schedule='linear', respacing='ddim10', shape=(2, 4, 3, 8, 8),
+         ts=dict(t0=[0, 0], tmid=[3, 7], tend=[9, 9]), t_seq=None),
+    dict(name='ddim50', schedule='linear', respacing='ddim50', shape=(3, 2, 3, 4, 4),
+         ts=dict(tmid=[0, 25, 49]), t_seq=[49, 10, 0]),
+    dict(name='sections', schedule='cosine', respacing='10,15,20', shape=(2, 2, 3, 4, 4),
+         ts=dict(tmid=[0, 44]), t_seq=[44, 20, 0]),
+]
+
+CHAIN_CASE = dict(cfg='tiny', image_size=32, respacing='ddim10', bpd_respacing='ddim4', batch=1, video_length=30,
+                  obs_length=5, max_frames=10, step_size=5, mode='independent', video_seed=31, noise_seed=5000,
+                  bpd_obs=[[0, 1, 2], [3, 7, 9, 11, 12, 13]], bpd_lat=[[10, 11, 12, 13, 14], [20, 21, 22, 23]])
+
+
+def bpd_case_inputs(c):
+    """run_bpd_evaluation's packing (scripts/video_nll.py:149-164) for ragged index lists."""
+    obs_l, lat_l = c['bpd_obs'], c['bpd_lat']
+    B = len(obs_l)
+    video = synth.make_video((B, c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'] + 1)
+    mf = max(len(o) + len(l) for o, l in zip(obs_l, lat_l))
+    x0 = torch.zeros(B, mf, 3, c['image_size'], c['image_size'])
+    obs = torch.zeros(B, mf, 1, 1, 1)
+    lat = torch.zeros(B, mf, 1, 1, 1)
+    fi = torch.zeros(B, mf, dtype=torch.long)
+    for i, (o, l) in enumerate(zip(obs_l, lat_l)):
+        x0[i, :len(o)] = video[i, o]
+        obs[i, :len(o)] = 1
+        fi[i, :len(o)] = torch.tensor(o)
+        x0[i, len(o):len(o) + len(l)] = video[i, l]
+        lat[i, len(o):len(o) + len(l)] = 1
+        fi[i, len(o):len(o) + len(l)] = torch.tensor(l)
+    return dict(x0=x0, obs_mask=obs, latent_mask=lat, kinda_marg_mask=torch.zeros_like(obs), frame_indices=fi,
+                max_frames=mf)

@@ -1,0 +1,229 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported from
+/root/reference) on the CPU.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed as small
+fixtures; every input is regenerated from seeds by oracle/synth.py, so fixtures
+hold outputs only.  TEST INFRASTRUCTURE ONLY.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+
+# `inference_util` imports lpips at module scope (inference_util.py:3); stub it.
+_lp = types.ModuleType('lpips')
+_lp.LPIPS = type('LPIPS', (), {'__init__': lambda s, *a, **k: None})
+_lp.normalize_tensor = lambda x: x
+sys.modules['lpips'] = _lp
+
+from improved_diffusion import gaussian_diffusion as gd                      # noqa: E402
+from improved_diffusion import inference_util                                 # noqa: E402
+from improved_diffusion.script_util import (create_gaussian_diffusion,       # noqa: E402
+                                            create_video_model_and_diffusion,
+                                            video_model_and_diffusion_defaults)
+
+from oracle import synth                                                      # noqa: E402
+from oracle.cases import (CHAIN_CASE, DIFFUSION_CASES, STRATEGY_GRID, UNET_CASES, bpd_case_inputs,  # noqa: E402
+                          fake_eps, model_kwargs_for, ref_config, unet_case_inputs)
+
+
+class NoiseReplay:
+    """Replace th.randn_like inside the reference by a seeded, regenerable stream."""
+
+    def __init__(self, base_seed):
+        self.i, self.base = 0, base_seed
+
+    def __call__(self, like):
+        z = synth.make_noise(tuple(like.shape), seed=self.base + self.i)
+        self.i += 1
+        return z
+
+
+def build(cfg_name, respacing='', device='cpu'):
+    kw = video_model_and_diffusion_defaults()
+    kw.update(ref_config(cfg_name))
+    kw['timestep_respacing'] = respacing
+    with torch.device(device):
+        model, diffusion = create_video_model_and_diffusion(**kw)
+    return model.eval(), diffusion
+
+
+def dump_specs():
+    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):
+        model, _ = build(name, device='meta')
+        spec = {k: list(v.shape) for k, v in model.state_dict().items()}
+        with open(os.path.join(GOLD, f'spec_{name}.json'), 'w') as f:
+            json.dump(spec, f, indent=0, sort_keys=True)
+        print('spec', name, len(spec), sum(int(np.prod(s)) for s in spec.values()))
+
+
+def dump_strategies():
+    out = []
+    for mode, T, obs, mf, step in STRATEGY_GRID:
+        it = inference_util.inference_strategies[mode](video_length=T, num_obs=obs, max_frames=mf, step_size=step)
+        steps = [[[int(i) for i in o], [int(i) for i in l]] for o, l in it]
+        out.append(dict(mode=mode, T=T, obs=obs, max_frames=mf, step_size=step, steps=steps))
+    with open(os.path.join(GOLD, 'frame_indices.json'), 'w') as f:
+        json.dump(out, f)
+    print('strategies', len(out))
+
+
+def load_ref_model(cfg_name, respacing=''):
+    model, diffusion = build(cfg_name, respacing)
+    spec = json.load(open(os.path.join(GOLD, f'spec_{cfg_name}.json')))
+    model.load_state_dict(synth.make_state_dict(spec, seed=1))
+    return model, diffusion
+
+
+def dump_unet():
+    arrays = {}
+    for case in UNET_CASES:
+        model, _ = load_ref_model(case['cfg'])
+        inp = unet_case_inputs(case)
+        taps = {}
+        hooks = []
+        for grp in ('input_blocks', 'output_blocks'):
+            for i, seq in enumerate(getattr(model, grp)):
+                for j, mod in enumerate(seq):
+                    hooks.append(mod.register_forward_hook(
+                        lambda m, a, o, key=f'{grp}.{i}.{j}': taps.__setitem__(key, o)))
+        for j, mod in enumerate(model.middle_block):
+            hooks.append(mod.register_forward_hook(lambda m, a, o, key=f'middle_block.{j}': taps.__setitem__(key, o)))
+        hooks.append(model.time_embed.register_forward_hook(lambda m, a, o: taps.__setitem__('emb', o)))
+        with torch.no_grad():
+            out, _ = model(inp['x'], timesteps=inp['t_model'], **model_kwargs_for(inp))
+        for h in hooks:
+            h.remove()
+        arrays[f"{case['name']}/eps"] = out.numpy()
+        for k, v in taps.items():
+            arrays[f"{case['name']}/tap/{k}"] = synth.fingerprint(v)
+        print('unet', case['name'], float(out.abs().max()), float(out.std()))
+    np.savez_compressed(os.path.join(GOLD, 'unet.npz'), **arrays)
+
+
+def dump_diffusion():
+    arrays = {}
+    for case in DIFFUSION_CASES:
+        name, resp = case['name'], case['respacing']
+        d = create_gaussian_diffusion(steps=1000, noise_schedule=case['schedule'], timestep_respacing=resp,
+                                      rescale_timesteps=True, rescale_learned_sigmas=True)
+        for attr in ('betas', 'alphas_cumprod', 'alphas_cumprod_prev', 'sqrt_alphas_cumprod',
+                     'sqrt_one_minus_alphas_cumprod', 'log_one_minus_alphas_cumprod', 'sqrt_recip_alphas_cumprod',
+                     'sqrt_recipm1_alphas_cumprod', 'posterior_variance', 'posterior_log_variance_clipped',
+                     'posterior_mean_coef1', 'posterior_mean_coef2'):
+            arrays[f'{name}/{attr}'] = getattr(d, attr)
+        arrays[f'{name}/timestep_map'] = np.array(d.timestep_map, dtype=np.int64)
+        shape = case['shape']
+        x = synth.make_noise(shape, seed=11)
+        x0 = synth.make_video(shape, seed=12)
+        noise = synth.make_noise(shape, seed=13)
+        lat = torch.zeros(shape[0], shape[1], 1, 1, 1)
+        lat[:, shape[1] // 2:] = 1
+        model = lambda xx, timesteps, **kw: (fake_eps(xx, timesteps), None)
+        for tag, t in case['ts'].items():
+            t = torch.tensor(t)
+            gd.th.randn_like = lambda like: noise
+            ps = d.p_sample(model, x, t, clip_denoised=True, model_kwargs={})
+            arrays[f'{name}/{tag}/p_sample'] = ps['sample'].numpy()
+            arrays[f'{name}/{tag}/pred_xstart'] = ps['pred_xstart'].numpy()
+            pm = d.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs={})
+            arrays[f'{name}/{tag}/mean_noclip'] = pm['mean'].numpy()
+            arrays[f'{name}/{tag}/log_variance'] = pm['log_variance'].numpy()
+            for eta in (0.0, 0.7):
+                ds = d.ddim_sample(model, x, t, clip_denoised=True, model_kwargs={}, eta=eta)
+                arrays[f'{name}/{tag}/ddim_eta{eta}'] = ds['sample'].numpy()
+            arrays[f'{name}/{tag}/q_sample'] = d.q_sample(x0, t, noise=noise).numpy()
+            xt = d.q_sample(x0, t, noise=noise)
+            vb = d._vb_terms_bpd(model, x_start=x0, x_t=xt, t=t, clip_denoised=True, model_kwargs={}, latent_mask=lat)
+            arrays[f'{name}/{tag}/vb'] = vb['output'].numpy()
+        gd.th.randn_like = NoiseReplay(2000)
+        bpd = d.calc_bpd_loop_subsampled(model, x0, clip_denoised=True, model_kwargs={}, latent_mask=lat,
+                                         t_seq=case['t_seq'])
+        for k, v in bpd.items():
+            arrays[f'{name}/bpd/{k}'] = v.numpy()
+        gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'diffusion.npz'), **arrays)
+    print('diffusion', len(arrays))
+
+
+def dump_chain():
+    """Script-style sampling (scripts/video_sample.py:50-190), ddim_sample_loop and the
+    ELBO loop (scripts/video_nll.py:142-188) for the tiny model, with replayed noise."""
+    c = CHAIN_CASE
+    arrays = {}
+    model, diffusion = load_ref_model(c['cfg'], c['respacing'])
+    B, T = c['batch'], c['video_length']
+    video = synth.make_video((B, T, 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    samples = torch.zeros_like(video)
+    samples[:, :c['obs_length']] = video[:, :c['obs_length']]
+    it = inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])
+    gd.th.randn_like = NoiseReplay(c['noise_seed'])
+    with torch.no_grad():
+        for obs, lat in it:
+            x0 = torch.cat([samples[:, obs], samples[:, lat]], dim=1).clone()
+            fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+            om = torch.zeros_like(x0[:, :, :1, :1, :1])
+            om[:, :len(obs)] = 1
+            kw = dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om,
+                      kinda_marg_mask=torch.zeros_like(om), x_t_minus_1=x0, observed_frames='x_0')
+            cur = x0.clone()
+            for step in reversed(range(diffusion.num_timesteps)):
+                cur = diffusion.p_sample(model, cur, t=torch.tensor([step] * B), clip_denoised=True,
+                                         model_kwargs=kw)['sample']
+            samples[:, lat] = cur[:, -len(lat):]
+    arrays['chain/samples'] = samples.numpy()
+    print('chain', float(samples.abs().max()), float(samples.std()))
+
+    # ddim_sample_loop on the first window (gaussian_diffusion.py:670-748)
+    it = inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])
+    obs, lat = next(iter(it))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+    fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    kw = dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+              x_t_minus_1=x0, observed_frames='x_0')
+    gd.th.randn_like = NoiseReplay(c['noise_seed'] + 500)
+    init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 499)
+    with torch.no_grad():
+        out = diffusion.ddim_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw,
+                                         device='cpu')
+    arrays['ddim_loop/sample'] = out.numpy()
+
+    # ELBO with ragged index lists (video_nll.py:142-188)
+    model, diffusion = load_ref_model(c['cfg'], c['bpd_respacing'])
+    inp = bpd_case_inputs(c)
+    gd.th.randn_like = NoiseReplay(c['noise_seed'] + 900)
+    kw = dict(frame_indices=inp['frame_indices'], x0=inp['x0'], obs_mask=inp['obs_mask'],
+              latent_mask=inp['latent_mask'], kinda_marg_mask=inp['kinda_marg_mask'],
+              x_t_minus_1=inp['x0'], observed_frames='x_0')
+    metrics = diffusion.calc_bpd_loop_subsampled(model, inp['x0'], clip_denoised=True, model_kwargs=kw,
+                                                 latent_mask=inp['latent_mask'], t_seq=None)
+    for k, v in metrics.items():
+        arrays[f'bpd/{k}'] = v.numpy()
+    print('bpd total', metrics['total_bpd'])
+    gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'chain.npz'), **arrays)
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    os.makedirs(GOLD, exist_ok=True)
+    dump_specs()
+    dump_strategies()
+    dump_diffusion()
+    dump_unet()
+    dump_chain()

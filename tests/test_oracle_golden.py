@@ -1,0 +1,122 @@
+"""The CPU oracle (oracle/) against fixtures produced by the unmodified reference
+(oracle/make_golden.py).  No GPU, no product code."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_rel
+from oracle import cases, diffusion_oracle as D, strategies_oracle as S, synth, unet_oracle as U
+
+
+def test_frame_index_schedules_bit_exact(golden):
+    for rec in golden.json('frame_indices'):
+        got = [[o, l] for o, l in S.schedule(rec['mode'], rec['T'], rec['obs'], rec['max_frames'], rec['step_size'])]
+        assert got == rec['steps'], rec['mode']
+
+
+@pytest.mark.parametrize('case', cases.DIFFUSION_CASES, ids=lambda c: c['name'])
+def test_schedule_tables_and_sampler_math(golden, case):
+    g = golden.npz('diffusion')
+    n = case['name']
+    s = D.Schedule(1000, case['schedule'], case['respacing'])
+    pairs = dict(betas=s.betas, alphas_cumprod=s.acp, alphas_cumprod_prev=s.acp_prev, sqrt_alphas_cumprod=s.sqrt_acp,
+                 sqrt_one_minus_alphas_cumprod=s.sqrt_1m_acp, log_one_minus_alphas_cumprod=s.log_1m_acp,
+                 sqrt_recip_alphas_cumprod=s.sqrt_recip_acp, sqrt_recipm1_alphas_cumprod=s.sqrt_recipm1_acp,
+                 posterior_variance=s.post_var, posterior_log_variance_clipped=s.post_logvar,
+                 posterior_mean_coef1=s.post_c1, posterior_mean_coef2=s.post_c2)
+    for k, v in pairs.items():
+        np.testing.assert_array_equal(v, g[f'{n}/{k}'], err_msg=k)          # float64, bit-exact
+    assert s.timestep_map == g[f'{n}/timestep_map'].tolist()
+    shape = case['shape']
+    x, x0, noise = synth.make_noise(shape, 11), synth.make_video(shape, 12), synth.make_noise(shape, 13)
+    lat = torch.zeros(shape[0], shape[1], 1, 1, 1)
+    lat[:, shape[1] // 2:] = 1
+    for tag, tl in case['ts'].items():
+        t = torch.tensor(tl)
+        eps = cases.fake_eps(x, s.model_time(t))
+        ps = D.p_sample(s, eps, x, t, noise)
+        np.testing.assert_allclose(ps['sample'].numpy(), g[f'{n}/{tag}/p_sample'], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(ps['pred_xstart'].numpy(), g[f'{n}/{tag}/pred_xstart'], rtol=0, atol=1e-6)
+        pm = D.p_mean_variance(s, eps, x, t, clip_denoised=False)
+        np.testing.assert_allclose(pm['mean'].numpy(), g[f'{n}/{tag}/mean_noclip'], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(pm['log_variance'].numpy(), g[f'{n}/{tag}/log_variance'], rtol=0, atol=0)
+        for eta in (0.0, 0.7):
+            ds = D.ddim_sample(s, eps, x, t, noise, eta=eta)
+            np.testing.assert_allclose(ds['sample'].numpy(), g[f'{n}/{tag}/ddim_eta{eta}'], rtol=0, atol=2e-6)
+        xt = D.q_sample(s, x0, t, noise)
+        np.testing.assert_allclose(xt.numpy(), g[f'{n}/{tag}/q_sample'], rtol=0, atol=1e-6)
+        vb = D.vb_terms(s, cases.fake_eps(xt, s.model_time(t)), x0, xt, t, lat)
+        np.testing.assert_allclose(vb['output'].numpy(), g[f'{n}/{tag}/vb'], rtol=1e-5, atol=1e-6)
+    t_seq = case['t_seq'] if case['t_seq'] is not None else list(range(s.num_timesteps))[::-1]
+    noises = [synth.make_noise(shape, 2000 + i) for i in range(len(t_seq))]
+    bpd = D.calc_bpd_loop(s, lambda xt, t: cases.fake_eps(xt, s.model_time(t)), x0, lat, noises, t_seq)
+    for k, v in bpd.items():
+        np.testing.assert_allclose(v.numpy(), g[f'{n}/bpd/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize('case', cases.UNET_CASES, ids=lambda c: c['name'])
+def test_unet_forward_matches_reference(golden, case):
+    g = golden.npz('unet')
+    spec = golden.json('spec_' + case['cfg'])
+    sd = synth.make_state_dict(spec, seed=1)
+    cfg = U.model_config(**cases.ref_config(case['cfg']))
+    inp = cases.unet_case_inputs(case)
+    taps = {}
+    with torch.no_grad():
+        out = U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'],
+                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps)
+    assert max_rel(out.numpy(), g[f"{case['name']}/eps"]) < 2e-5
+    checked = 0
+    for key, val in taps.items():
+        gk = f"{case['name']}/tap/" + ('emb' if key == 'emb' else key.rsplit('.', 1)[0])
+        assert gk in g.files, gk
+        np.testing.assert_allclose(synth.fingerprint(val), g[gk], rtol=2e-4, atol=2e-4, err_msg=key)
+        checked += 1
+    assert checked == len([k for k in g.files if k.startswith(case['name'] + '/tap/')])
+
+
+def test_spec_shapes_cover_oracle_plan(golden):
+    """Every key the oracle reads exists in the reference's state_dict spec (all four configs)."""
+    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):
+        spec = golden.json('spec_' + name)
+        cfg = U.model_config(**cases.ref_config(name))
+        inp, mid, out, _ = U.block_plan(cfg)
+        n_res = sum(k == 'res' for m in inp + [mid] + out for k, _ in m)
+        n_attn = sum(k == 'attn' for m in inp + [mid] + out for k, _ in m)
+        assert n_res == len([k for k in spec if k.endswith('in_layers.2.weight')])
+        assert n_attn == len([k for k in spec if k.endswith('temporal_attention.qkv.weight')])
+
+
+class _Replay:
+    def __init__(self, base):
+        self.i, self.base = 0, base
+
+    def __call__(self, shape):
+        z = synth.make_noise(shape, seed=self.base + self.i)
+        self.i += 1
+        return z
+
+
+def test_tiny_chain_ddim_loop_and_elbo_match_reference(golden):
+    from oracle import pipeline_oracle as P
+    g = golden.npz('chain')
+    c = cases.CHAIN_CASE
+    sd = synth.make_state_dict(golden.json('spec_' + c['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(c['cfg']))
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    with torch.no_grad():
+        sched = D.Schedule(1000, 'linear', c['respacing'])
+        samples = P.infer_video(sd, cfg, sched, video, c['mode'], c['max_frames'], c['obs_length'], c['step_size'],
+                                _Replay(c['noise_seed']))
+        assert np.abs(samples.numpy() - g['chain/samples']).max() < 5e-4
+        obs, lat = next(S.schedule(c['mode'], c['video_length'], c['obs_length'], c['max_frames'], c['step_size']))
+        x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+        fi, om, lm, km = (torch.from_numpy(a) for a in S.window_tensors(obs, lat, c['batch']))
+        kw = dict(x0=x0, obs_mask=om, latent_mask=lm, kinda_marg_mask=km, frame_indices=fi)
+        init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 499)
+        out = P.ddim_sample_loop(sd, cfg, sched, init, kw, _Replay(c['noise_seed'] + 500))
+        assert np.abs(out.numpy() - g['ddim_loop/sample']).max() < 5e-4
+        sched4 = D.Schedule(1000, 'linear', c['bpd_respacing'])
+        raw, _ = P.run_bpd_evaluation(sd, cfg, sched4, cases.bpd_case_inputs(c), _Replay(c['noise_seed'] + 900))
+        for k, v in raw.items():
+            np.testing.assert_allclose(v.numpy(), g[f'bpd/{k}'], rtol=2e-4, atol=1e-6, err_msg=k)
