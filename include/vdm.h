@@ -1,0 +1,183 @@
+/*
+ * libvdm.so -- C ABI of the B200-native video-diffusion hot path.
+ *
+ * The reference (cliangyu/video-diffusion) is pure Python/PyTorch and has no FFI layer;
+ * its "interface" for this path is the set of ATen ops issued by
+ *   improved_diffusion/unet.py            (CondMargVideoModel / UNetVideoModel forward)
+ *   improved_diffusion/gaussian_diffusion.py (p_mean_variance, p_sample, ddim_sample, _vb_terms_bpd)
+ * Each entry point below replaces the group of reference ops cited beside it.  The Python
+ * host mirror (the video_diffusion_b200 package) binds them with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns all memory (the library never allocates device memory, never frees,
+ *     never synchronises); every call is asynchronous on `stream` and CUDA-graph capturable;
+ *   - returns 0 on success, <0 for invalid arguments / unsupported shapes, >0 = cudaError_t;
+ *     vdm_last_error_string() gives a thread-local message;
+ *   - activations are channels-last: row m = (image n, y, x), n = b*F + f, C contiguous.
+ */
+#ifndef VDM_H_
+#define VDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vdm_stream_t; /* cudaStream_t */
+
+enum { VDM_F32 = 0, VDM_BF16 = 1 };
+
+int vdm_version(void);
+const char* vdm_last_error_string(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t vdm_launch_count(void);
+
+/* ---- implicit-GEMM convolution / linear ------------------------------------------------
+ * Replaces nn.Conv2d 3x3 / 1x1 (unet.py:61, 90-95, 141, 156-160, 172-173, 618, 748) and
+ * nn.Linear (unet.py:143-150, 418-419, 606-610, 274-277) together with the ops fused around
+ * them: bias, residual/skip add (unet.py:198, 538), emb add (unet.py:196), concat-free
+ * second K range for the 1x1 skip projection, SiLU on a second output.
+ *
+ *   out[m][n] = sum_{tap,c} A1[pix(m)+tap][c] * W[n][tap*C1+c]  + sum_c A2[m][c] * W[n][taps*C1+c]
+ *               + bias[n] + rowbias[img(m)][n] + residual[m][n]
+ *
+ * dtype VDM_BF16: A1/A2/W are bf16, the kernel is the tcgen05/TMEM/TMA one (fp32 accumulate).
+ * dtype VDM_F32 : A1/A2/W are fp32, SIMT fp32 kernel (reference-accuracy mode).
+ */
+typedef struct {
+  int32_t dtype;        /* VDM_F32 | VDM_BF16: type of a1, a2, w */
+  int32_t taps;         /* 1 (linear / 1x1) or 9 (3x3, pad 1) */
+  int32_t a1_mode;      /* 0: A1 is [n][H][W][C1] at output resolution (stride 1)
+                           1: stride-2 conv.  bf16: A1 is parity planes [n][py][px][H][W][C1] of the
+                              2H x 2W input; fp32: A1 is the raw [n][2H][2W][C1] input
+                           2: nearest-x2 upsample folded in (fp32 only): A1 is [n][H/2][W/2][C1] */
+  int32_t n_img, H, W;  /* output geometry; M = n_img*H*W.  For linear: n_img=M, H=W=1 */
+  int32_t C1, C2;       /* channels of A1 / A2 (C2 = 0: no second range) */
+  int32_t N;            /* output channels */
+  const void* a1;
+  const void* a2;       /* [M][C2] or NULL */
+  const void* w;        /* [N][taps*C1 + C2], K contiguous */
+  const float* bias;    /* [N] or NULL */
+  const float* rowbias; /* [n_img][ld_rowbias] or NULL (per-image channel bias) */
+  int32_t ld_rowbias;
+  const float* residual; /* [M][ld_res] or NULL */
+  int32_t ld_res;
+  float* out_f32;       /* [M][ld_out] or NULL; with out_nchw: [n_img][N][H][W] */
+  void* out_bf16;       /* [M][ld_out_bf16] or NULL */
+  int32_t ld_out, ld_out_bf16;
+  int32_t out_nchw;
+  float* out_silu_f32;  /* optional second output silu(out) [M][ld_out] (fp32 kernel only) */
+} vdm_gemm_args;
+
+int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
+
+/* ---- GroupNorm32 (+SiLU, + scale/shift), producer of GEMM A operands --------------------
+ * Replaces GroupNorm32 (nn.py:15-17) + SiLU (nn.py:10-12) + `h*(1+scale)+shift`
+ * (unet.py:190-194) + th.cat of the U-Net skip (unet.py:826-828) + F.interpolate x2
+ * (unet.py:63-69) + the dtype cast feeding the next conv.
+ * stats: sum / sum-of-squares accumulators [n_img][32][2] (double), zeroed by the caller. */
+int vdm_gn_stats(const float* src1, int32_t C1, const float* src2, int32_t C2,
+                 int32_t n_img, int32_t HW, double* stats, vdm_stream_t stream);
+
+typedef struct {
+  const float* src1; int32_t C1;      /* [n_img*HW][C1] */
+  const float* src2; int32_t C2;      /* optional second source, concatenated along C */
+  int32_t n_img, H, W;
+  const double* stats;                /* NULL: no normalisation (plain cast / concat) */
+  const float* gamma; const float* beta;   /* [C1+C2] */
+  const float* scale_shift;           /* optional [n_img][ld_ss]: scale = [0,C), shift = [C,2C) */
+  int32_t ld_ss;
+  int32_t silu;
+  int32_t out_mode;                   /* 0 plain, 1 nearest-x2 upsampled, 2 stride-2 parity planes */
+  int32_t out_dtype;                  /* VDM_F32 | VDM_BF16 */
+  void* out;                          /* GEMM A operand */
+  float* out_f32_copy;                /* optional fp32 copy of the plain output (attention residual) */
+} vdm_gn_apply_args;
+
+int vdm_gn_apply(const vdm_gn_apply_args* args, vdm_stream_t stream);
+
+/* GroupNorm over (C/32 channels x T frames) per (b, pixel): the temporal-attention norm
+ * (unet.py:473-474 on x.reshape(B*D, C, T)).  x: [B][T][HW][C] fp32. */
+int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C,
+                    const float* gamma, const float* beta, float* out_f32,
+                    void* out_a, int32_t out_dtype, vdm_stream_t stream);
+
+/* out[m][c] = h[m][c] + enc[m % HW][c]  (spatial_encoding add, unet.py:841-844); out may alias h */
+int vdm_add_spatial_encoding(const float* h, const float* enc, float* out, int32_t n_img, int32_t HW,
+                             int32_t C, vdm_stream_t stream);
+
+/* ---- conditioning mix + input-conv im2col -----------------------------------------------
+ * Replaces CondMargVideoModel.forward's masking / indicator channels / per-frame timesteps
+ * (unet.py:951-1013, cond_emb_type='channel', observed_frames='x_0').
+ * x, x0: [B][F][3][H][W] fp32 (reference layout); masks: [B][F] fp32.
+ * a_out: im2col rows [B*F*H*W][64] (K index = tap*5 + c, zero padded), dtype out_dtype.
+ * t_frame[B*F] = t[b] * (1 - obs[b][f]);  attn_mask[B*F] = min(obs+lat+kinda, 1). */
+int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
+                 const float* kinda_marg_mask, const float* t, int32_t B, int32_t F, int32_t H,
+                 int32_t W, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
+                 vdm_stream_t stream);
+
+/* sinusoidal timestep embedding (nn.py:89-107): out[n] = [cos(t*f_i) | sin(t*f_i)] */
+int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, float* out,
+                           vdm_stream_t stream);
+
+/* ---- RPE net hidden layer (unet.py:283-296) ----------------------------------------------
+ * hidden[net][(b*T+i)*T+j][c] = silu(e_t[b*T+i][net*C + c] + Wd[net][c][:]·feat(d_ij) + bd[net][c])
+ * with d_ij = fi[b][i]-fi[b][j], feat = (log1p(max(d,0)), log1p(max(-d,0)), d==0).
+ * e_t: [B*T][ld_et] holds embed_diffusion_time(temb) (+ its bias) of the 3 nets (q,k,v). */
+int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int64_t* frame_indices, const float* wd,
+                   const float* bd, int32_t B, int32_t T, int32_t C, void* out, int32_t out_dtype,
+                   vdm_stream_t stream);
+
+/* ---- temporal attention with in-kernel RPE bias (unet.py:477-536) -------------------------
+ * qkv: [B*T*HW][3C] fp32 (row (b,t,pix); columns (3, heads, hd)); R_q/R_k/R_v: [B*T*T][C] fp32
+ * (row (b,i,j), columns (heads, hd)); mask: [B][T] fp32 (1 = real frame).
+ * out_a: [B*T*HW][C] attention output as GEMM A operand for proj_out. */
+int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, const float* r_v,
+                      const float* mask, int32_t allow_pad_interactions, int32_t B, int32_t T,
+                      int32_t HW, int32_t heads, int32_t hd, void* out_a, int32_t out_dtype,
+                      vdm_stream_t stream);
+
+/* ---- spatial attention (unet.py:258-266 -> 477-536 without RPE / mask) --------------------
+ * qkv: [n_img*L][3C] (dtype qkv_dtype); softmax(q k^T / sqrt(hd)) v per (image, head).
+ * qkv_dtype VDM_BF16 -> tensor-core flash kernel; VDM_F32 -> fp32 SIMT kernel. */
+int vdm_attn_spatial(const void* qkv, int32_t qkv_dtype, int32_t n_img, int32_t L, int32_t heads,
+                     int32_t hd, void* out_a, int32_t out_dtype, vdm_stream_t stream);
+
+/* ---- sampler step (gaussian_diffusion.py:326-343, 374-382, 208-227, 438-443, 597-634) ----
+ * tables: [VDM_TAB_COUNT][n_steps] fp32 (see enum), t: [B] int64 indices into the tables.
+ * mode 0: ancestral p_sample; mode 1: DDIM with eta.  Elementwise over B*per_batch. */
+enum {
+  VDM_TAB_SQRT_RECIP_ACP = 0, VDM_TAB_SQRT_RECIPM1_ACP, VDM_TAB_POST_C1, VDM_TAB_POST_C2,
+  VDM_TAB_MODEL_LOGVAR, VDM_TAB_MODEL_VAR, VDM_TAB_ACP, VDM_TAB_ACP_PREV, VDM_TAB_POST_LOGVAR,
+  VDM_TAB_SQRT_ACP, VDM_TAB_SQRT_1M_ACP, VDM_TAB_LOG_1M_ACP, VDM_TAB_COUNT
+};
+
+int vdm_sampler_step(int32_t mode, const float* x, const float* eps, const float* noise,
+                     const int64_t* t, const float* tables, int32_t n_steps, int32_t B,
+                     int64_t per_batch, int32_t clip_denoised, float eta, float* sample,
+                     float* pred_xstart, float* mean, vdm_stream_t stream);
+
+/* q_sample (gaussian_diffusion.py:190-206): out = sqrt_acp[t]*x0 + sqrt_1m_acp[t]*noise */
+int vdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables,
+                 int32_t n_steps, int32_t B, int64_t per_batch, float* out, vdm_stream_t stream);
+
+/* ---- ELBO terms (gaussian_diffusion.py:750-788, 970-988; losses.py:12-70; nn.py:73-77) ----
+ * acc[b][0..2] += (vb term in bits, xstart_mse, eps_mse), each already divided by the FULL
+ * per-batch element count (masked sum / full count).  acc zeroed by the caller.
+ * latent_mask: [B][F]; per_frame = per_batch / F. */
+int vdm_vb_terms(const float* x0, const float* x_t, const float* eps, const float* noise,
+                 const int64_t* t, const float* tables, int32_t n_steps, const float* latent_mask,
+                 int32_t B, int32_t F, int64_t per_frame, int32_t clip_denoised, double* acc,
+                 vdm_stream_t stream);
+
+/* prior_bpd (gaussian_diffusion.py:909-926): acc[b] += KL(q(x_T|x0) || N(0,1)) in bits */
+int vdm_prior_bpd(const float* x0, const float* tables, int32_t n_steps, const float* latent_mask,
+                  int32_t B, int32_t F, int64_t per_frame, double* acc, vdm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDM_H_ */

@@ -1,0 +1,329 @@
+"""Per-kernel parity on the B200: every libvdm entry point against a plain PyTorch fp32
+restatement of the same op (TF32 disabled) or against the CPU oracle's sampler maths."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import diffusion_oracle as D  # noqa: E402
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from video_diffusion_b200 import _lib
+    _lib.load()          # fail loudly if the extension is missing
+    yield
+
+
+def ops():
+    from video_diffusion_b200 import ops as o
+    return o
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def nhwc(x):   # (n,C,H,W) -> [n*H*W, C]
+    n, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(n * h * w, c).contiguous()
+
+
+def from_nhwc(m, n, h, w):
+    return m.view(n, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_w(w):  # OIHW -> [O][tap*I + i]
+    o, i, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).contiguous()
+
+
+def relerr(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+CONV_CASES = [
+    # n, H, W, C1, N, mode, C2
+    (2, 64, 64, 64, 128, 0, 0),
+    (3, 32, 32, 128, 64, 0, 0),
+    (2, 16, 16, 192, 384, 0, 0),
+    (5, 8, 8, 128, 128, 0, 0),       # M = 320: ragged last tile
+    (10, 4, 4, 64, 64, 0, 0),        # several images per tile, ragged
+    (2, 16, 16, 64, 128, 1, 0),      # stride 2 (input 32x32)
+    (3, 8, 8, 128, 128, 0, 64),      # fused 1x1 skip operand
+    (2, 32, 32, 64, 128, 2, 0),      # upsample folded (materialised for the bf16 kernel)
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['simt_f32', 'tcgen05_bf16'])
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'n%d_%dx%d_c%d_n%d_m%d_c2_%d' % c)
+def test_conv3x3(case, dtype):
+    n, H, W, C1, N, mode, C2 = case
+    o = ops()
+    srcH, srcW = (2 * H, 2 * W) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
+    x = rnd(n, C1, srcH, srcW, seed=1)
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5)
+    bias = rnd(N, seed=3)
+    res = rnd(n * H * W, N, seed=4)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    xin = F.interpolate(x, scale_factor=2, mode='nearest') if mode == 2 else x
+    ref = F.conv2d(xin, w, bias, stride=2 if mode == 1 else 1, padding=1)
+    wp = pack_w(w)
+    a2 = None
+    if C2:
+        x2 = rnd(n, C2, H, W, seed=5)
+        w2 = rnd(N, C2, 1, 1, seed=6, scale=C2 ** -0.5)
+        if dtype == torch.bfloat16:
+            x2, w2 = x2.bfloat16().float(), w2.bfloat16().float()
+        ref = ref + F.conv2d(x2, w2)
+        wp = torch.cat([wp, w2.view(N, C2)], dim=1).contiguous()
+        a2 = nhwc(x2).to(dtype)
+    ref = nhwc(ref) + res
+    a1_mode = mode
+    if dtype == torch.bfloat16:
+        if mode == 1:      # parity planes [n][py][px][H][W][C]
+            a1 = x.view(n, C1, H, 2, W, 2).permute(0, 3, 5, 2, 4, 1).contiguous().view(-1, C1)
+        elif mode == 2:    # the bf16 kernel consumes the materialised upsample
+            a1, a1_mode = nhwc(xin), 0
+        else:
+            a1 = nhwc(x)
+    else:
+        a1 = nhwc(x)
+    out = torch.empty(n * H * W, N, device='cuda')
+    out_b = torch.empty(n * H * W, N, device='cuda', dtype=torch.bfloat16)
+    o.gemm(a1.to(dtype), wp.to(dtype), N, n_img=n, H=H, W=W, taps=9, a1_mode=a1_mode, a2=a2, bias=bias,
+           residual=res, out_f32=out, out_bf16=out_b, C1=C1)
+    torch.cuda.synchronize()
+    tol = 2e-5 if dtype == torch.float32 else 2e-5   # bf16 inputs are pre-rounded: only summation order differs
+    assert relerr(out, ref) < tol
+    assert relerr(out_b, ref) < 6e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['simt_f32', 'tcgen05_bf16'])
+def test_linear_rowbias_nchw_and_silu(dtype):
+    o = ops()
+    M, K, N = 300, 128, 192
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    if dtype == torch.bfloat16:
+        a, w = a.bfloat16().float(), w.bfloat16().float()
+    bias = rnd(N, seed=3)
+    ref = a @ w.t() + bias
+    out = torch.empty(M, N, device='cuda')
+    sil = torch.empty(M, N, device='cuda') if dtype == torch.float32 else None
+    o.gemm(a.to(dtype), w.to(dtype), N, n_img=M, H=1, W=1, taps=1, bias=bias, out_f32=out, out_silu=sil)
+    assert relerr(out, ref) < 2e-5
+    if sil is not None:
+        assert relerr(sil, F.silu(ref)) < 2e-5
+    # per-image bias + NCHW store of a 3-channel 3x3 conv (the output head)
+    n, H, W, C1 = 3, 16, 16, 64
+    x = rnd(n, C1, H, W, seed=5)
+    wc = rnd(3, C1, 3, 3, seed=6, scale=(9 * C1) ** -0.5)
+    if dtype == torch.bfloat16:
+        x, wc = x.bfloat16().float(), wc.bfloat16().float()
+    b3 = rnd(3, seed=7)
+    ref = F.conv2d(x, wc, b3, padding=1)
+    out = torch.empty(n, 3, H, W, device='cuda')
+    o.gemm(nhwc(x).to(dtype), pack_w(wc).to(dtype), 3, n_img=n, H=H, W=W, taps=9, bias=b3, out_f32=out, out_nchw=True)
+    assert relerr(out, ref) < 2e-5
+    rb = rnd(n, 2 * 64, seed=8)
+    wq = rnd(64, C1, 3, 3, seed=9, scale=(9 * C1) ** -0.5)
+    if dtype == torch.bfloat16:
+        wq = wq.bfloat16().float()
+    ref = nhwc(F.conv2d(x, wq, None, padding=1) + rb[:, :64, None, None])
+    out = torch.empty(n * H * W, 64, device='cuda')
+    o.gemm(nhwc(x).to(dtype), pack_w(wq).to(dtype), 64, n_img=n, H=H, W=W, taps=9, rowbias=rb, out_f32=out)
+    assert relerr(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize('C1,C2', [(64, 0), (128, 64), (512, 384), (192, 0)])
+@pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
+def test_groupnorm_apply(C1, C2, out_dtype):
+    o = ops()
+    n, H, W = 3, 8, 8
+    Cc = C1 + C2
+    x1 = rnd(n, C1, H, W, seed=1) * 2 + 0.5
+    x2 = rnd(n, C2, H, W, seed=2) if C2 else None
+    gamma, beta = rnd(Cc, seed=3), rnd(Cc, seed=4)
+    ss = rnd(n, 2 * Cc, seed=5, scale=0.3)
+    xc = torch.cat([x1, x2], 1) if C2 else x1
+    ref = F.group_norm(xc, 32, gamma, beta, eps=1e-5) * (1 + ss[:, :Cc, None, None]) + ss[:, Cc:, None, None]
+    ref = F.silu(ref)
+    stats = torch.zeros(n, 32, 2, device='cuda', dtype=torch.float64)
+    s1, s2 = nhwc(x1), (nhwc(x2) if C2 else None)
+    o.gn_stats(s1, s2, n, H * W, stats)
+    out = torch.empty(n * H * W, Cc, device='cuda', dtype=out_dtype)
+    o.gn_apply(s1, s2, n, H, W, out, stats=stats, gamma=gamma, beta=beta, scale_shift=ss, silu=True)
+    assert relerr(out, nhwc(ref)) < (1e-5 if out_dtype == torch.float32 else 5e-3)
+    # plain norm + fp32 copy, x2 upsample and parity layouts of the raw cast
+    cp = torch.empty(n * H * W, Cc, device='cuda')
+    o.gn_apply(s1, s2, n, H, W, out, stats=stats, gamma=gamma, beta=beta, copy=cp)
+    assert relerr(cp, nhwc(F.group_norm(xc, 32, gamma, beta, eps=1e-5))) < 1e-5
+    up = torch.empty(n * 4 * H * W, Cc, device='cuda', dtype=out_dtype)
+    o.gn_apply(s1, s2, n, H, W, up, out_mode=1)
+    assert relerr(up, nhwc(F.interpolate(xc, scale_factor=2, mode='nearest'))) < 5e-3
+    par = torch.empty(n * H * W, Cc, device='cuda', dtype=out_dtype)
+    o.gn_apply(s1, s2, n, H, W, par, out_mode=2)
+    refp = xc.view(n, Cc, H // 2, 2, W // 2, 2).permute(0, 3, 5, 2, 4, 1).reshape(-1, Cc)
+    assert relerr(par, refp) < 5e-3
+
+
+def test_groupnorm_temporal_and_spatial_encoding():
+    o = ops()
+    B, T, HW, Cc = 2, 5, 16, 64
+    x = rnd(B, T, HW, Cc, seed=1) + 0.3
+    gamma, beta = rnd(Cc, seed=2), rnd(Cc, seed=3)
+    xr = x.permute(0, 2, 3, 1).reshape(B * HW, Cc, T)              # (B*D, C, T) as the reference
+    ref = F.group_norm(xr, 32, gamma, beta, eps=1e-5).view(B, HW, Cc, T).permute(0, 3, 1, 2)
+    out = torch.empty_like(x)
+    outa = torch.empty_like(x, dtype=torch.bfloat16)
+    o.gn_temporal(x, B, T, HW, Cc, gamma, beta, out, outa)
+    assert relerr(out, ref) < 1e-5
+    assert relerr(outa, ref) < 5e-3
+    h = rnd(B * T * HW, Cc, seed=4)
+    enc = rnd(HW, Cc, seed=5)
+    ref = (h.view(B * T, HW, Cc) + enc).view(-1, Cc)
+    o.add_spatial_encoding(h, enc, h, B * T, HW, Cc)
+    assert relerr(h, ref) < 1e-7
+
+
+def test_cond_mix_and_timestep_embedding():
+    from oracle import unet_oracle as U
+    o = ops()
+    B, Fr, H, W = 2, 3, 8, 8
+    x, x0 = rnd(B, Fr, 3, H, W, seed=1), rnd(B, Fr, 3, H, W, seed=2)
+    obs = torch.tensor([[1., 0, 0], [1, 1, 0]]).cuda()
+    lat = torch.tensor([[0., 1, 0], [0, 0, 1]]).cuda()
+    kin = torch.tensor([[0., 0, 0], [0, 0, 0]]).cuda()
+    t = torch.tensor([250.0, 999.0]).cuda()
+    a = torch.empty(B * Fr * H * W, 64, device='cuda')
+    tf = torch.empty(B * Fr, device='cuda')
+    am = torch.empty(B * Fr, device='cuda')
+    o.cond_mix(x, x0, obs, lat, kin, t, B, Fr, H, W, a, tf, am)
+    m = lambda v: v.view(B, Fr, 1, 1, 1)
+    any_ = (obs + lat + kin).clamp(max=1)
+    ones = torch.ones_like(x[:, :, :1])
+    xin = torch.cat([x * m(lat) + x0 * m(obs) + x * (1 - m(any_)), ones * m(obs), ones * m(kin)], 2).view(B * Fr, 5, H, W)
+    cols = F.unfold(xin, 3, padding=1).view(B * Fr, 5, 9, H * W).permute(0, 3, 2, 1).reshape(-1, 45)
+    assert torch.equal(a[:, :45], cols)
+    assert float(a[:, 45:].abs().max()) == 0
+    assert torch.equal(tf.view(B, Fr), t.view(B, 1) * (1 - obs))
+    assert torch.equal(am.view(B, Fr), any_)
+    tt = torch.tensor([0.0, 1.0, 17.0, 503.25, 999.0]).cuda()
+    emb = torch.empty(5, 128, device='cuda')
+    o.timestep_embedding(tt, 128, emb)
+    assert float((emb.cpu() - U.sinusoid(tt.cpu(), 128)).abs().max()) < 2e-4   # sin/cos of args up to 1e3
+
+
+def _attn_ref(qkv, heads, mask=None, R=None, pad_interact=True):
+    """qkv: (B, D, L, 3C) -> (B, D, L, C) following unet.py:477-536."""
+    B, Dd, L, C3 = qkv.shape
+    Cc = C3 // 3
+    hd = Cc // heads
+    q, k, v = (qkv.view(B, Dd, L, 3, heads, hd)[:, :, :, i].permute(0, 1, 3, 2, 4) for i in range(3))
+    scale = hd ** -0.5
+    q = q * scale
+    att = q @ k.transpose(-1, -2)
+    if R is not None:
+        rq, rk, rv = (r.view(B, L, L, heads, hd) for r in R)
+        att = att + torch.einsum('bdhtf,btshf->bdhts', q, rk)
+        att = att + torch.einsum('bdhtf,btshf->bdhts', k * scale, rq).transpose(-1, -2)
+    if mask is not None:
+        allowed = mask[:, None, :] * mask[:, :, None]
+        if pad_interact:
+            allowed = allowed + (1 - mask[:, None, :]) * (1 - mask[:, :, None])
+        else:
+            i = torch.arange(L)
+            allowed[:, i, i] = 1
+        att = att.masked_fill((allowed == 0).view(B, 1, 1, L, L), float('-inf'))
+    w = torch.softmax(att, -1)
+    out = w @ v
+    if R is not None:
+        out = out + torch.einsum('bdhts,btshf->bdhtf', w, rv)
+    return out.permute(0, 1, 3, 2, 4).reshape(B, Dd, L, Cc)
+
+
+@pytest.mark.parametrize('T,hd,pad', [(20, 96, True), (10, 32, False), (7, 128, True)])
+def test_attention_temporal(T, hd, pad):
+    o = ops()
+    B, HW, heads = 2, 19, 4
+    Cc = heads * hd
+    qkv = rnd(B, T, HW, 3 * Cc, seed=1)
+    R = [rnd(B * T * T, Cc, seed=2 + i, scale=0.5) for i in range(3)]
+    mask = torch.ones(B, T).cuda()
+    mask[0, T - 2:] = 0
+    ref = _attn_ref(qkv.permute(0, 2, 1, 3), heads, mask, R, pad).permute(0, 2, 1, 3)   # back to (B,T,HW,C)
+    out = torch.empty(B, T, HW, Cc, device='cuda')
+    o.attn_temporal(qkv, R[0], R[1], R[2], mask, pad, B, T, HW, heads, hd, out)
+    assert relerr(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize('L,hd', [(256, 96), (64, 128), (256, 32)])
+def test_attention_spatial_f32(L, hd):
+    o = ops()
+    n, heads = 3, 4
+    Cc = heads * hd
+    qkv = rnd(n, L, 3 * Cc, seed=1)
+    ref = _attn_ref(qkv.view(n, 1, L, 3 * Cc), heads).view(n, L, Cc)
+    out = torch.empty(n, L, Cc, device='cuda')
+    o.attn_spatial(qkv, n, L, heads, hd, out)
+    assert relerr(out, ref) < 2e-5
+
+
+def test_rpe_hidden():
+    o = ops()
+    B, T, Cc = 2, 6, 64
+    e_t = rnd(B * T, 3 * Cc, seed=1)
+    fi = torch.tensor([[0, 1, 2, 10, 11, 30], [5, 3, 3, 100, 7, 8]]).cuda()
+    wd, bd = rnd(3, Cc, 3, seed=2), rnd(3, Cc, seed=3)
+    out = torch.empty(3, B * T * T, Cc, device='cuda')
+    o.rpe_hidden(e_t, fi, wd, bd, B, T, Cc, out)
+    d = (fi[:, :, None] - fi[:, None, :]).float()
+    feats = torch.stack([torch.log1p(d.clamp(min=0)), torch.log1p((-d).clamp(min=0)), (d == 0).float()], -1)
+    for net in range(3):
+        ed = feats @ wd[net].t() + bd[net]
+        ref = F.silu(e_t.view(B, T, 1, 3, Cc)[:, :, :, net] + ed).reshape(B * T * T, Cc)
+        assert relerr(out[net], ref) < 1e-5
+
+
+@pytest.mark.parametrize('respacing', ['', 'ddim10'])
+def test_sampler_kernels_match_oracle(respacing):
+    from video_diffusion_b200.gaussian_diffusion import device_tables
+    o = ops()
+    s = D.Schedule(1000, 'linear', respacing)
+    tab = device_tables(s_like=s).cuda()
+    shape = (3, 4, 3, 8, 8)
+    x, eps, z, x0 = (rnd(*shape, seed=i) for i in range(4))
+    x0 = x0.clamp(-1, 1)
+    n = s.num_timesteps
+    for tl in ([0, 1, n - 1], [n // 2, 0, 3]):
+        t = torch.tensor(tl).cuda()
+        ref = D.p_sample(s, eps.cpu(), x.cpu(), t.cpu(), z.cpu())
+        pred = torch.empty_like(x)
+        got = o.sampler_step(0, x, eps, z, t, tab, pred_xstart=pred)
+        assert float((got.cpu() - ref['sample']).abs().max()) < 2e-6
+        assert float((pred.cpu() - ref['pred_xstart']).abs().max()) < 2e-6
+        for eta in (0.0, 0.7):
+            ref = D.ddim_sample(s, eps.cpu(), x.cpu(), t.cpu(), z.cpu(), eta=eta)
+            got = o.sampler_step(1, x, eps, z, t, tab, eta=eta)
+            assert float((got.cpu() - ref['sample']).abs().max()) < 4e-6
+        assert float((o.q_sample(x0, z, t, tab).cpu() - D.q_sample(s, x0.cpu(), t.cpu(), z.cpu())).abs().max()) < 1e-6
+        lat = torch.tensor([[0., 1, 1, 0], [1, 1, 1, 1], [0, 0, 0, 1]]).cuda()
+        xt = D.q_sample(s, x0.cpu(), t.cpu(), z.cpu())
+        ref = D.vb_terms(s, eps.cpu(), x0.cpu(), xt, t.cpu(), lat.cpu().view(3, 4, 1, 1, 1))
+        acc = torch.zeros(3, 3, device='cuda', dtype=torch.float64)
+        o.vb_terms(x0, xt.cuda(), eps, z, t, tab, lat, True, acc)
+        np.testing.assert_allclose(acc[:, 0].cpu().numpy(), ref['output'].numpy(), rtol=2e-5, atol=1e-7)
+        ref_x = D.mean_flat((ref['pred_xstart'] - x0.cpu()) ** 2, lat.cpu().view(3, 4, 1, 1, 1))
+        np.testing.assert_allclose(acc[:, 1].cpu().numpy(), ref_x.numpy(), rtol=2e-5)
+    acc = torch.zeros(3, device='cuda', dtype=torch.float64)
+    o.prior_bpd(x0, tab, lat, acc)
+    np.testing.assert_allclose(acc.cpu().numpy(), D.prior_bpd(s, x0.cpu(), lat.cpu().view(3, 4, 1, 1, 1)).numpy(), rtol=2e-5)

@@ -1,0 +1,114 @@
+"""Whole-forward parity on the B200: the CUDA model against (a) golden eps produced by the
+unmodified reference and (b) the CPU oracle's per-block activations, on identical de-zeroed
+random weights, inputs and frame indices.  Tolerances are BASELINE.json's: eps max-rel
+<= 1e-3 in fp32 mode, <= 2e-2 in bf16 mode (max-rel = max|a-b| / max|b|)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import max_rel  # noqa: E402
+from oracle import cases, synth, unet_oracle as U  # noqa: E402
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from video_diffusion_b200 import _lib
+    _lib.load()
+    yield
+
+
+def build_model(cfg_name, golden, dtype, respacing=''):
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config(cfg_name))
+    kw['timestep_respacing'] = respacing
+    model, diffusion = create_video_model_and_diffusion(compute_dtype=dtype, **kw)
+    model.load_state_dict(synth.make_state_dict(golden.json('spec_' + cfg_name), seed=1))
+    return model.cuda().eval(), diffusion
+
+
+def tap_name(node):
+    k, p = node['kind'], node['p']
+    if k == 'conv_in':
+        return 'h_in', 'input_blocks.0.0.conv'
+    if k == 'res':
+        return p + '.out', p + '.res'
+    if k == 'attn':
+        return p + '.spatial_attention.out', p + '.attn'
+    if k == 'down':
+        return p + '.out', p[:-3] + '.down'
+    return p + '.out', p[:-5] + '.up'
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('case', cases.UNET_CASES, ids=lambda c: c['name'])
+def test_forward_matches_reference_and_oracle(golden, case, dtype):
+    g = golden.npz('unet')
+    model, _ = build_model(case['cfg'], golden, dtype)
+    model.use_cuda_graph = False
+    inp = cases.unet_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    with torch.no_grad():
+        out, attn = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+    torch.cuda.synchronize()
+    assert attn is None and out.shape == inp['x'].shape
+    # per-block activations against the oracle (diagnostic + gate)
+    sd = synth.make_state_dict(golden.json('spec_' + case['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(case['cfg']))
+    taps = {}
+    with torch.no_grad():
+        ref = U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'],
+                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps)
+    ws = next(iter(model._workspaces.values()))
+    worst = 0.0
+    for node in model.plan:
+        buf, tap = tap_name(node)
+        t = taps[tap]
+        n, c, h, w = t.shape
+        got = ws.bufs[buf].float().cpu().view(n, h, w, c).permute(0, 3, 1, 2)
+        err = max_rel(got.numpy(), t.numpy())
+        worst = max(worst, err)
+        if err > TOL[dtype]:
+            print(f'  {tap:45s} rel err {err:.3e}')
+    e_ref = max_rel(out.cpu().numpy(), g[f"{case['name']}/eps"])
+    e_orc = max_rel(out.cpu().numpy(), ref.numpy())
+    print(f"{case['name']} {dtype}: eps max-rel vs reference {e_ref:.3e}, vs oracle {e_orc:.3e}, worst block {worst:.3e}")
+    assert e_ref <= TOL[dtype]
+    assert worst <= 2.5 * TOL[dtype]
+
+
+def test_cuda_graph_replay_equals_eager(golden):
+    case = cases.UNET_CASES[0]
+    model, _ = build_model(case['cfg'], golden, torch.bfloat16)
+    inp = cases.unet_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    x = inp['x'].cuda()
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        eager, _ = model(x, inp['t_model'].cuda(), **kw)
+        model.use_cuda_graph = True
+        a, _ = model(x, inp['t_model'].cuda(), **kw)         # capture + replay
+        b, _ = model(x * 0.5, inp['t_model'].cuda() * 0.3, **kw)
+        c, _ = model(x, inp['t_model'].cuda(), **kw)         # replay with the first inputs again
+    assert torch.equal(a, eager) and torch.equal(c, eager) and not torch.equal(b, eager)
+
+
+def test_unsupported_paths_raise(golden):
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config('tiny'))
+    with pytest.raises(NotImplementedError):
+        create_video_model_and_diffusion(**dict(kw, use_rpe_net=False))
+    with pytest.raises(AssertionError):
+        create_video_model_and_diffusion(**dict(kw, rp_alpha=None, rp_beta=None, rp_gamma=None))
+    model, _ = create_video_model_and_diffusion(**kw)
+    x = torch.zeros(1, 4, 3, 32, 32)
+    with pytest.raises(RuntimeError):      # CPU tensors: no fallback
+        model.eval()(x, torch.zeros(1), x0=x, obs_mask=x[:, :, :1, :1, :1], latent_mask=x[:, :, :1, :1, :1],
+                     kinda_marg_mask=x[:, :, :1, :1, :1], x_t_minus_1=x, observed_frames='x_0')

@@ -1,0 +1,105 @@
+"""ctypes binding of libvdm.so (the C ABI declared in include/vdm.h).
+
+There is deliberately no fallback: if the CUDA extension is missing or a call fails,
+everything here raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libvdm.so')
+
+F32, BF16 = 0, 1
+TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOGVAR=4, MODEL_VAR=5, ACP=6,
+           ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11)
+TAB_COUNT = 12
+
+EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
+           'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
+           'vdm_attn_temporal', 'vdm_attn_spatial', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
+           'vdm_prior_bpd']
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('dtype', _i32), ('taps', _i32), ('a1_mode', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
+                ('C1', _i32), ('C2', _i32), ('N', _i32), ('a1', _vp), ('a2', _vp), ('w', _vp), ('bias', _vp),
+                ('rowbias', _vp), ('ld_rowbias', _i32), ('residual', _vp), ('ld_res', _i32), ('out_f32', _vp),
+                ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
+                ('out_silu_f32', _vp)]
+
+
+class GnApplyArgs(C.Structure):
+    _fields_ = [('src1', _vp), ('C1', _i32), ('src2', _vp), ('C2', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
+                ('stats', _vp), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
+                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('out_f32_copy', _vp)]
+
+
+_lib = None
+
+
+def load():
+    """Load libvdm.so (built by `__graft_entry__.build()` / `make -C video_diffusion_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"`. '
+                           'There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.vdm_version.restype = _i32
+    lib.vdm_last_error_string.restype = C.c_char_p
+    lib.vdm_launch_count.restype = _i64
+    sig = {
+        'vdm_gemm': [C.POINTER(GemmArgs), _vp],
+        'vdm_gn_stats': [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
+        'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
+        'vdm_gn_temporal': [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
+        'vdm_add_spatial_encoding': [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+        'vdm_cond_mix': [_vp] * 6 + [_i32] * 4 + [_vp, _i32, _vp, _vp, _vp],
+        'vdm_timestep_embedding': [_vp, _i32, _i32, _vp, _vp],
+        'vdm_rpe_hidden': [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
+        'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
+        'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+        'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
+        'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],
+        'vdm_vb_terms': [_vp] * 6 + [_i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp],
+        'vdm_prior_bpd': [_vp, _vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _i32
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().vdm_last_error_string().decode(errors='replace')
+        raise RuntimeError(f'libvdm {what} failed (rc={rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'libvdm needs contiguous CUDA tensors'
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(load().vdm_launch_count())
+
+
+def dt(code_or_dtype):
+    if isinstance(code_or_dtype, int):
+        return torch.bfloat16 if code_or_dtype == BF16 else torch.float32
+    return BF16 if code_or_dtype == torch.bfloat16 else F32

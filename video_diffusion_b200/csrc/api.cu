@@ -1,0 +1,37 @@
+// extern "C" surface shared by all kernels: version, error string, launch counter, GEMM dispatch.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace vdm {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream);
+int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream);
+
+}  // namespace vdm
+
+extern "C" int vdm_version(void) { return 100; }
+extern "C" const char* vdm_last_error_string(void) { return vdm::g_err; }
+extern "C" int64_t vdm_launch_count(void) { return vdm::g_launches.load(); }
+
+extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
+  VDM_REQUIRE(a != nullptr, "gemm: NULL args");
+  VDM_REQUIRE(a->a1 && a->w, "gemm: NULL operand");
+  VDM_REQUIRE(a->out_f32 || a->out_bf16, "gemm: no output");
+  VDM_REQUIRE(a->n_img > 0 && a->H > 0 && a->W > 0 && a->N > 0, "gemm: bad geometry");
+  if (a->dtype == VDM_BF16) return vdm::gemm_tc(a, (cudaStream_t)stream);
+  if (a->dtype == VDM_F32) return vdm::gemm_simt(a, (cudaStream_t)stream);
+  vdm::set_error("gemm: unknown dtype %d", a->dtype);
+  return -1;
+}

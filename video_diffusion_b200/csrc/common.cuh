@@ -1,0 +1,62 @@
+// Shared helpers for libvdm.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/vdm.h"
+
+namespace vdm {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define VDM_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::vdm::set_error(__VA_ARGS__);  \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+// Call right after a kernel launch: counts it and converts launch errors.
+#define VDM_AFTER_LAUNCH(name)                                                        \
+  do {                                                                                \
+    ::vdm::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      ::vdm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
+      return (int)e__;                                                                \
+    }                                                                                 \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// exact-ish SiLU used where the reference computes x*sigmoid(x) in fp32
+__device__ __forceinline__ float silu_precise(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+template <typename T>
+__device__ __forceinline__ void store_elem(T* p, float v);
+template <>
+__device__ __forceinline__ void store_elem<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace vdm

@@ -1,0 +1,501 @@
+// Implicit-GEMM convolution / linear on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill = conv padding) -> shared memory
+//   -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue (bias / per-image
+//   bias / residual / bf16 or fp32 or NCHW store).
+//
+// One CTA computes a 128 (pixels) x BLOCK_N (out channels) tile.  The K loop walks
+// taps x (C1/64) chunks of A1 -- each chunk one shifted 5-D TMA box of the channels-last
+// activation -- followed by C2/64 chunks of the optional second operand (fused 1x1 skip
+// projection, unet.py:172-173,198).  Warp roles: warp 0 TMA producer, warp 1 TMEM
+// allocator + MMA issuer (single thread), warps 2..5 epilogue (one TMEM lane quarter each).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace vdm {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  int M, N;
+  int taps, c1_chunks, c2_chunks;
+  int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes
+  int is_linear;  // A1 addressed as 2-D [M][C1]
+  int H, W, HW;
+  const float* bias;
+  const float* rowbias;
+  int ld_rowbias;
+  const float* residual;
+  int ld_res;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_out, ld_out_bf16;
+  int out_nchw;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fail loudly, never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      printf("vdm gemm_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+template <int BLOCK_N>
+constexpr uint32_t instr_desc() {
+  return (1u << 4)                          // accumulator fp32
+         | (1u << 7) | (1u << 10)           // A, B = bf16
+         | ((uint32_t)(BLOCK_N >> 3) << 17) // N
+         | ((uint32_t)(BLOCK_M >> 4) << 24);  // M
+}
+
+template <int BLOCK_N>
+constexpr int tmem_cols() { return BLOCK_N < 32 ? 32 : BLOCK_N; }
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STRIDE;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
+                                                              const __grid_constant__ CUtensorMap tm_a2,
+                                                              const __grid_constant__ CUtensorMap tm_w,
+                                                              const TcParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int m0 = blockIdx.y * BLOCK_M;
+  const int num_kb = p.taps * p.c1_chunks + p.c2_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(tmem_cols<BLOCK_N>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      int img0 = 0, y0 = 0, x0 = 0;
+      if (!p.is_linear) {
+        img0 = m0 / p.HW;
+        const int rem = m0 - img0 * p.HW;
+        y0 = rem / p.W;
+        x0 = rem - y0 * p.W;
+      }
+      const int k1 = p.taps * p.c1_chunks;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + L::A_BYTES;
+        mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
+        if (kb < k1) {
+          const int tap = kb / p.c1_chunks;
+          const int cc = kb - tap * p.c1_chunks;
+          if (p.is_linear) {
+            tma_load_5d(a_dst, &tm_a1, full_bar(stage), cc * BLOCK_K, m0, 0, 0, 0);
+          } else {
+            int dy = 0, dx = 0, plane = 0;
+            if (p.taps == 9) {
+              const int r = tap / 3, s = tap - r * 3;
+              if (p.a1_mode == 0) {
+                dy = r - 1;
+                dx = s - 1;
+              } else {  // stride 2 on parity planes: r -> (parity, offset) = (1,-1), (0,0), (1,0)
+                const int py = (r != 1), px = (s != 1);
+                dy = (r == 0) ? -1 : 0;
+                dx = (s == 0) ? -1 : 0;
+                plane = py * 2 + px;
+              }
+            }
+            tma_load_5d(a_dst, &tm_a1, full_bar(stage), cc * BLOCK_K, x0 + dx, y0 + dy, plane, img0);
+          }
+        } else {
+          tma_load_5d(a_dst, &tm_a2, full_bar(stage), (kb - k1) * BLOCK_K, m0, 0, 0, 0);
+        }
+        tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
+        const uint64_t a_desc = make_smem_desc(a_addr);
+        const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool row_ok = row < p.M;
+    int img = 0, pix = 0;
+    if (p.rowbias != nullptr || p.out_nchw) {
+      img = row / p.HW;
+      pix = row - img * p.HW;
+    }
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int j = 0; j < BLOCK_N / CHUNK; ++j) {
+      uint32_t acc[CHUNK];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * CHUNK);
+      if constexpr (CHUNK == 32) tmem_ld_32(taddr, acc);
+      else tmem_ld_16(taddr, acc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+      const int nb = n0 + j * CHUNK;
+      if (p.out_nchw) {
+        for (int i = 0; i < CHUNK; ++i) {
+          const int n = nb + i;
+          if (n < p.N) {
+            float v = __uint_as_float(acc[i]);
+            if (p.bias) v += p.bias[n];
+            p.out_f32[((size_t)img * p.N + n) * p.HW + pix] = v;
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < CHUNK; i += 4) {
+        const int n = nb + i;
+        if (n >= p.N) break;  // N is a multiple of 4 on this path
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(acc[i + e]);
+        if (p.bias) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
+          v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (p.rowbias) {
+          const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)img * p.ld_rowbias + n);
+          v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (p.residual) {
+          const float4 r = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + n);
+          v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + n) = make_float4(v[0], v[1], v[2], v[3]);
+        if (p.out_bf16) {
+          uint2 pk;
+          pk.x = pack_bf16x2(v[0], v[1]);
+          pk.y = pack_bf16x2(v[2], v[3]);
+          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)row * p.ld_out_bf16 + n) = pk;
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N>())
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// bf16 tensor of up to 5 dims (innermost first), 128B swizzle, zero OOB fill.
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return -2;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstrides[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return -3;
+  }
+  return 0;
+}
+
+// [rows][C] matrix viewed as 5-D (C, rows, 1, 1, 1) with a (64, 128, 1, 1, 1) box.
+int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C) {
+  uint64_t dims[5] = {(uint64_t)C, (uint64_t)rows, 1, 1, 1};
+  uint64_t st[5] = {2, (uint64_t)C * 2, (uint64_t)C * 2 * rows, (uint64_t)C * 2 * rows, (uint64_t)C * 2 * rows};
+  uint32_t box[5] = {BLOCK_K, BLOCK_M, 1, 1, 1};
+  return encode_map(map, base, 5, dims, st, box);
+}
+
+template <int BLOCK_N, int STAGES>
+int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+           cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
+  gemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+  VDM_AFTER_LAUNCH("gemm_tc");
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
+  const int64_t M = (int64_t)a->n_img * a->H * a->W;
+  VDM_REQUIRE(a->taps == 1 || a->taps == 9, "gemm_tc: taps must be 1 or 9");
+  VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
+  VDM_REQUIRE(a->C2 % BLOCK_K == 0, "gemm_tc: C2=%d must be a multiple of 64", a->C2);
+  VDM_REQUIRE(a->a1_mode == 0 || (a->a1_mode == 1 && a->taps == 9), "gemm_tc: unsupported a1_mode %d", a->a1_mode);
+  VDM_REQUIRE(a->out_nchw || a->N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", a->N);
+  VDM_REQUIRE(a->out_silu_f32 == nullptr, "gemm_tc: out_silu_f32 is only supported by the fp32 kernel");
+  VDM_REQUIRE(!a->out_nchw || (a->out_f32 && !a->residual && !a->rowbias && !a->out_bf16),
+              "gemm_tc: NCHW output supports bias only");
+  const int HW = a->H * a->W;
+  const bool is_linear = (a->taps == 1);
+  TcParams p{};
+  p.M = (int)M;
+  p.N = a->N;
+  p.taps = a->taps;
+  p.c1_chunks = a->C1 / BLOCK_K;
+  p.c2_chunks = a->C2 / BLOCK_K;
+  p.a1_mode = a->a1_mode;
+  p.is_linear = is_linear;
+  p.H = a->H; p.W = a->W; p.HW = HW;
+  p.bias = a->bias; p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias;
+  p.residual = a->residual; p.ld_res = a->ld_res;
+  p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
+
+  CUtensorMap ma1, ma2, mw;
+  int rc;
+  if (is_linear) {
+    rc = encode_rows_map(&ma1, a->a1, M, a->C1);
+  } else {
+    // tile = 128 consecutive pixels of the channels-last image stack
+    const int W = a->W, H = a->H;
+    VDM_REQUIRE((W <= 128 && 128 % W == 0) || W % 128 == 0, "gemm_tc: unsupported width %d", W);
+    uint32_t bw = W < 128 ? W : 128, bh = 1, bn = 1;
+    if (W < 128) {
+      if (HW >= 128) {
+        VDM_REQUIRE(HW % 128 == 0, "gemm_tc: H*W=%d must be a multiple of 128", HW);
+        bh = 128 / W;
+      } else {
+        VDM_REQUIRE(128 % HW == 0, "gemm_tc: H*W=%d must divide 128", HW);
+        bh = H;
+        bn = 128 / HW;
+      }
+    }
+    const uint64_t C = a->C1;
+    const uint64_t planes = a->a1_mode == 1 ? 4 : 1;
+    uint64_t dims[5] = {C, (uint64_t)W, (uint64_t)H, planes, (uint64_t)a->n_img};
+    uint64_t st[5] = {2, C * 2, C * 2 * W, C * 2 * W * H, C * 2 * W * H * planes};
+    uint32_t box[5] = {BLOCK_K, bw, bh, 1, bn};
+    rc = encode_map(&ma1, a->a1, 5, dims, st, box);
+  }
+  if (rc) return rc;
+  if (a->C2 > 0) {
+    VDM_REQUIRE(a->a2 != nullptr, "gemm_tc: a2 is NULL");
+    rc = encode_rows_map(&ma2, a->a2, M, a->C2);
+    if (rc) return rc;
+  } else {
+    ma2 = ma1;
+  }
+  const int64_t K = (int64_t)a->taps * a->C1 + a->C2;
+  const int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
+    uint64_t st[2] = {2, (uint64_t)K * 2};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+    rc = encode_map(&mw, a->w, 2, dims, st, box);
+    if (rc) return rc;
+  }
+  switch (block_n) {
+    case 128: return launch<128, 3>(ma1, ma2, mw, p, stream);
+    case 64: return launch<64, 4>(ma1, ma2, mw, p, stream);
+    default: return launch<16, 4>(ma1, ma2, mw, p, stream);
+  }
+}
+
+}  // namespace vdm

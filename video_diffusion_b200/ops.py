@@ -1,0 +1,129 @@
+"""Tensor-level wrappers over the C ABI (one Python function per libvdm entry point).
+
+Every function launches asynchronously on torch's current CUDA stream and returns the
+output tensors it was given / allocated.  Nothing here computes on the host.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
+
+
+def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
+         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0):
+    """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm)."""
+    lib = _lib.load()
+    g = GemmArgs()
+    g.dtype = dt(a1.dtype)
+    g.taps, g.a1_mode = taps, a1_mode
+    g.n_img, g.H, g.W = n_img, H, W
+    g.C1 = a1.shape[-1] if C1 is None else C1
+    g.C2 = C2 if a2 is None else a2.shape[-1]
+    g.N = N
+    g.a1, g.a2, g.w = ptr(a1), ptr(a2), ptr(w)
+    g.bias = ptr(bias)
+    g.rowbias = None if rowbias is None else rowbias.data_ptr()
+    g.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
+    g.residual = ptr(residual)
+    g.ld_res = residual.shape[-1] if residual is not None else 0
+    g.out_f32, g.out_bf16 = ptr(out_f32), ptr(out_bf16)
+    g.ld_out = out_f32.shape[-1] if (out_f32 is not None and not out_nchw) else (
+        out_silu.shape[-1] if out_silu is not None else 0)
+    g.ld_out_bf16 = out_bf16.shape[-1] if out_bf16 is not None else 0
+    g.out_nchw = int(out_nchw)
+    g.out_silu_f32 = ptr(out_silu)
+    check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm')
+
+
+def gn_stats(src1, src2, n_img, HW, stats):
+    lib = _lib.load()
+    check(lib.vdm_gn_stats(ptr(src1), src1.shape[-1], ptr(src2), 0 if src2 is None else src2.shape[-1],
+                           n_img, HW, ptr(stats), stream()), 'vdm_gn_stats')
+
+
+def gn_apply(src1, src2, n_img, H, W, out, *, stats=None, gamma=None, beta=None, scale_shift=None, silu=False,
+             out_mode=0, copy=None):
+    lib = _lib.load()
+    a = GnApplyArgs()
+    a.src1, a.C1 = ptr(src1), src1.shape[-1]
+    a.src2, a.C2 = ptr(src2), (0 if src2 is None else src2.shape[-1])
+    a.n_img, a.H, a.W = n_img, H, W
+    a.stats, a.gamma, a.beta = ptr(stats), ptr(gamma), ptr(beta)
+    a.scale_shift = None if scale_shift is None else scale_shift.data_ptr()
+    a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)
+    a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
+    a.out, a.out_f32_copy = ptr(out), ptr(copy)
+    check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply')
+
+
+def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):
+    lib = _lib.load()
+    check(lib.vdm_gn_temporal(ptr(x), B, T, HW, Cc, ptr(gamma), ptr(beta), ptr(out_f32), ptr(out_a), dt(out_a.dtype),
+                              stream()), 'vdm_gn_temporal')
+
+
+def add_spatial_encoding(h, enc, out, n_img, HW, Cc):
+    check(_lib.load().vdm_add_spatial_encoding(ptr(h), ptr(enc), ptr(out), n_img, HW, Cc, stream()),
+          'vdm_add_spatial_encoding')
+
+
+def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask):
+    check(_lib.load().vdm_cond_mix(ptr(x), ptr(x0), ptr(obs), ptr(lat), ptr(kinda), ptr(t), B, F, H, W, ptr(a_out),
+                                   dt(a_out.dtype), ptr(t_frame), ptr(attn_mask), stream()), 'vdm_cond_mix')
+
+
+def timestep_embedding(t_frame, dim, out):
+    check(_lib.load().vdm_timestep_embedding(ptr(t_frame), t_frame.numel(), dim, ptr(out), stream()),
+          'vdm_timestep_embedding')
+
+
+def rpe_hidden(e_t, frame_indices, wd, bd, B, T, Cc, out):
+    check(_lib.load().vdm_rpe_hidden(e_t.data_ptr(), e_t.stride(0), ptr(frame_indices), ptr(wd), ptr(bd), B, T, Cc,
+                                     ptr(out), dt(out.dtype), stream()), 'vdm_rpe_hidden')
+
+
+def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, out):
+    check(_lib.load().vdm_attn_temporal(ptr(qkv), ptr(r_q), ptr(r_k), ptr(r_v), ptr(mask), int(pad_interact), B, T,
+                                        HW, heads, hd, ptr(out), dt(out.dtype), stream()), 'vdm_attn_temporal')
+
+
+def attn_spatial(qkv, n_img, L, heads, hd, out):
+    check(_lib.load().vdm_attn_spatial(ptr(qkv), dt(qkv.dtype), n_img, L, heads, hd, ptr(out), dt(out.dtype),
+                                       stream()), 'vdm_attn_spatial')
+
+
+def sampler_step(mode, x, eps, noise, t, tables, clip_denoised=True, eta=0.0, sample=None, pred_xstart=None,
+                 mean=None):
+    B = x.shape[0]
+    per_batch = x.numel() // B
+    if sample is None:
+        sample = torch.empty_like(x)
+    check(_lib.load().vdm_sampler_step(mode, ptr(x), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B,
+                                       per_batch, int(clip_denoised), float(eta), ptr(sample), ptr(pred_xstart),
+                                       ptr(mean), stream()), 'vdm_sampler_step')
+    return sample
+
+
+def q_sample(x0, noise, t, tables, out=None):
+    B = x0.shape[0]
+    if out is None:
+        out = torch.empty_like(x0)
+    check(_lib.load().vdm_q_sample(ptr(x0), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B, x0.numel() // B,
+                                   ptr(out), stream()), 'vdm_q_sample')
+    return out
+
+
+def vb_terms(x0, x_t, eps, noise, t, tables, latent_mask, clip_denoised, acc):
+    B, F = x0.shape[0], x0.shape[1]
+    per_frame = x0.numel() // (B * F)
+    check(_lib.load().vdm_vb_terms(ptr(x0), ptr(x_t), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1],
+                                   ptr(latent_mask), B, F, per_frame, int(clip_denoised), ptr(acc), stream()),
+          'vdm_vb_terms')
+
+
+def prior_bpd(x0, tables, latent_mask, acc):
+    B, F = x0.shape[0], x0.shape[1]
+    check(_lib.load().vdm_prior_bpd(ptr(x0), ptr(tables), tables.shape[1], ptr(latent_mask), B, F,
+                                    x0.numel() // (B * F), ptr(acc), stream()), 'vdm_prior_bpd')

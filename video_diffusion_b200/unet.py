@@ -1,0 +1,552 @@
+"""B200-native video U-Net behind the reference's model API.
+
+`UNetModel` / `UNetVideoModel` / `CondMargVideoModel` take the reference's constructor kwargs
+(improved_diffusion/unet.py:564-586, 880-896, 932-947), expose parameters under the reference's
+`state_dict` key names (so `load_state_dict(reference_checkpoint['state_dict'])` works unchanged)
+and keep its forward signatures and return values (unet.py:898-912, 949-1026).  No sub-module has a
+forward of its own: the model pre-packs its weights for the kernels (OIHW -> [Cout][tap][Cin] in the
+compute dtype, fused skip projections, batched embedding projections) and executes one flat plan
+of libvdm launches over channels-last activations, optionally replayed as a CUDA graph.
+
+compute_dtype = torch.bfloat16 (default): tcgen05 tensor-core GEMMs, bf16 operands, fp32 accumulate,
+fp32 residual stream / GroupNorm statistics / softmax.  compute_dtype = torch.float32: the
+reference-accuracy mode (fp32 SIMT kernels everywhere).
+
+Unsupported configurations raise NotImplementedError -- there is no PyTorch / CPU fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+def _uniform(shape, bound):
+    return torch.empty(shape).uniform_(-bound, bound)
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
+                 num_heads=1, num_heads_upsample=-1, use_scale_shift_norm=False, use_spatial_encoding=False,
+                 image_size=None, temporal_augment_type=None, use_rpe_net=False, bucket_params=None,
+                 allow_interactions_between_padding=False, compute_dtype=None):
+        super().__init__()
+        if dims != 2 or not conv_resample or num_classes is not None:
+            raise NotImplementedError('only dims=2, conv_resample=True, num_classes=None are supported')
+        if not use_rpe_net:
+            raise NotImplementedError('bucketed lookup-table RPE (use_rpe_net=False) is not supported yet')
+        if bucket_params is None:   # the reference asserts this too (unet.py:423-427)
+            raise AssertionError('rp_alpha / rp_beta / rp_gamma must be set')
+        if num_heads_upsample not in (-1, num_heads):
+            raise NotImplementedError('num_heads_upsample != num_heads')
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions = num_res_blocks, tuple(attention_resolutions)
+        self.dropout, self.channel_mult, self.num_heads = dropout, tuple(channel_mult), num_heads
+        self.use_scale_shift_norm, self.image_size = use_scale_shift_norm, image_size
+        self.allow_interactions_between_padding = allow_interactions_between_padding
+        self.num_classes, self.use_checkpoint, self.conv_resample = None, use_checkpoint, conv_resample
+        self.compute_dtype = compute_dtype or torch.bfloat16
+        self.use_cuda_graph = True
+        self.time_embed_dim = E = model_channels * 4
+        if model_channels % 64 or (model_channels // num_heads) % 4:
+            raise NotImplementedError('model_channels must be a multiple of 64')
+
+        # ---- enumerate modules exactly like the reference constructor (unet.py:605-749) ----
+        ch = model_channels
+        self._lin('time_embed.0', ch, E)
+        self._lin('time_embed.2', E, E)
+        self.plan = [dict(kind='conv_in', p='input_blocks.0.0', group='input_blocks.0')]
+        self._conv('input_blocks.0.0', in_channels, ch, 3)
+        chans, ds, idx = [ch], 1, 1
+        self.n_blocks_before_attn = None
+        first_attn = None
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                if ds in self.attention_resolutions and self.n_blocks_before_attn is None:
+                    self.n_blocks_before_attn = idx
+                    first_attn = (ds, ch)
+                self._res(f'input_blocks.{idx}.0', ch, mult * model_channels, f'input_blocks.{idx}')
+                ch = mult * model_channels
+                if ds in self.attention_resolutions:
+                    self._attn(f'input_blocks.{idx}.1', ch, f'input_blocks.{idx}')
+                chans.append(ch)
+                idx += 1
+            if level != len(channel_mult) - 1:
+                self._conv(f'input_blocks.{idx}.0.op', ch, ch, 3)
+                self.plan.append(dict(kind='down', p=f'input_blocks.{idx}.0.op', group=f'input_blocks.{idx}', C=ch))
+                chans.append(ch)
+                ds *= 2
+                idx += 1
+        if self.n_blocks_before_attn is None:
+            self.n_blocks_before_attn = idx
+            first_attn = (ds, ch)
+        if use_spatial_encoding:
+            res = image_size // first_attn[0]
+            self.spatial_encoding = nn.Parameter(torch.randn(1, first_attn[1], res, res))
+        else:
+            self.spatial_encoding = None
+        self._res('middle_block.0', ch, ch, 'middle_block')
+        self._attn('middle_block.1', ch, 'middle_block')
+        self._res('middle_block.2', ch, ch, 'middle_block')
+        idx = 0
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                group = f'output_blocks.{idx}'
+                self._res(f'{group}.0', ch + chans.pop(), model_channels * mult, group, cat=True)
+                ch = model_channels * mult
+                j = 1
+                if ds in self.attention_resolutions:
+                    self._attn(f'{group}.1', ch, group)
+                    j = 2
+                if level and i == num_res_blocks:
+                    self._conv(f'{group}.{j}.conv', ch, ch, 3)
+                    self.plan.append(dict(kind='up', p=f'{group}.{j}.conv', group=group, C=ch))
+                    ds //= 2
+                idx += 1
+        self._gn('out.0', ch)
+        self._conv('out.2', model_channels, out_channels, 3, zero=True)
+        self._packed = None
+        self._workspaces = {}
+
+    # ---- parameter registration under the reference's names ------------------------------------
+    def _reg(self, path, tensor):
+        mod = self
+        parts = path.split('.')
+        for name in parts[:-1]:
+            if name not in mod._modules:
+                mod.add_module(name, nn.Module())
+            mod = mod._modules[name]
+        mod.register_parameter(parts[-1], nn.Parameter(tensor))
+
+    def _conv(self, p, cin, cout, k, zero=False):
+        fan = cin * k * k
+        self._reg(p + '.weight', torch.zeros(cout, cin, k, k) if zero else _uniform((cout, cin, k, k), fan ** -0.5))
+        self._reg(p + '.bias', torch.zeros(cout) if zero else _uniform((cout,), fan ** -0.5))
+
+    def _lin(self, p, cin, cout, zero=False):
+        self._reg(p + '.weight', torch.zeros(cout, cin) if zero else _uniform((cout, cin), cin ** -0.5))
+        self._reg(p + '.bias', torch.zeros(cout) if zero else _uniform((cout,), cin ** -0.5))
+
+    def _gn(self, p, c):
+        self._reg(p + '.weight', torch.ones(c))
+        self._reg(p + '.bias', torch.zeros(c))
+
+    def _res(self, p, cin, cout, group, cat=False):
+        self._gn(p + '.in_layers.0', cin)
+        self._conv(p + '.in_layers.2', cin, cout, 3)
+        self._lin(p + '.emb_layers.1', self.time_embed_dim, 2 * cout if self.use_scale_shift_norm else cout)
+        self._gn(p + '.out_layers.0', cout)
+        self._conv(p + '.out_layers.3', cout, cout, 3, zero=True)
+        if cin != cout:
+            self._conv(p + '.skip_connection', cin, cout, 1)
+        self.plan.append(dict(kind='res', p=p, group=group, cin=cin, cout=cout, skip=cin != cout, cat=cat))
+
+    def _attn(self, p, c, group):
+        for which in ('spatial_attention', 'temporal_attention'):
+            q = f'{p}.{which}'
+            self._lin(q + '.qkv', c, 3 * c)
+            self._lin(q + '.proj_out', c, c, zero=True)
+            self._gn(q + '.norm', c)
+            if which == 'temporal_attention':
+                for r in ('rpe_q', 'rpe_k', 'rpe_v'):
+                    self._lin(f'{q}.{r}.rpe_net.embed_distances', 3, c)
+                    self._lin(f'{q}.{r}.rpe_net.embed_diffusion_time', self.time_embed_dim, c)
+                    self._lin(f'{q}.{r}.rpe_net.out', c, c, zero=True)
+        self.plan.append(dict(kind='attn', p=p, group=group, C=c))
+
+    # ---- state handling --------------------------------------------------------------------------
+    def _invalidate(self):
+        self._packed = None
+        self._workspaces = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return out
+
+    def set_compute_dtype(self, dtype):
+        assert dtype in (torch.bfloat16, torch.float32)
+        self.compute_dtype = dtype
+        self._invalidate()
+        return self
+
+    @property
+    def inner_dtype(self):
+        return torch.float32
+
+    # ---- weight pre-packing ----------------------------------------------------------------------
+    @torch.no_grad()
+    def _pack(self):
+        sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('the B200 model only runs on a CUDA device; there is no CPU fallback (call .to("cuda"))')
+        adt = self.compute_dtype
+        P = {}
+
+        def conv_w(key):     # OIHW -> [O][tap*I + i]
+            w = sd[key]
+            return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+        def put(name, t, dtype=torch.float32):
+            P[name] = t.to(device=dev, dtype=dtype).contiguous()
+
+        put('te_w0', sd['time_embed.0.weight']); put('te_b0', sd['time_embed.0.bias'])
+        put('te_w2', sd['time_embed.2.weight']); put('te_b2', sd['time_embed.2.bias'])
+        w_in = sd['input_blocks.0.0.weight']                  # (ch, Cin, 3, 3) -> im2col columns k = tap*5 + c
+        w5 = torch.zeros(w_in.shape[0], 9, 5)
+        w5[:, :, :w_in.shape[1]] = w_in.permute(0, 2, 3, 1).reshape(w_in.shape[0], 9, w_in.shape[1])
+        pad = torch.zeros(w_in.shape[0], 64)
+        pad[:, :45] = w5.reshape(w_in.shape[0], 45)
+        put('in_w', pad, adt); put('in_b', sd['input_blocks.0.0.bias'])
+        emb_w, emb_b, rpe_w, rpe_b = [], [], [], []
+        emb_off = rpe_off = 0
+        for node in self.plan:
+            p = node['p']
+            if node['kind'] == 'res':
+                put(p + '.gn1_w', sd[p + '.in_layers.0.weight']); put(p + '.gn1_b', sd[p + '.in_layers.0.bias'])
+                put(p + '.gn2_w', sd[p + '.out_layers.0.weight']); put(p + '.gn2_b', sd[p + '.out_layers.0.bias'])
+                put(p + '.w1', conv_w(p + '.in_layers.2.weight'), adt); put(p + '.b1', sd[p + '.in_layers.2.bias'])
+                w2, b2 = conv_w(p + '.out_layers.3.weight'), sd[p + '.out_layers.3.bias']
+                if node['skip']:
+                    ws = sd[p + '.skip_connection.weight']
+                    if ws.shape[-1] != 1:
+                        raise NotImplementedError('3x3 skip convolution')
+                    w2 = torch.cat([w2, ws.reshape(ws.shape[0], -1)], dim=1)
+                    b2 = b2 + sd[p + '.skip_connection.bias']
+                put(p + '.w2', w2, adt); put(p + '.b2', b2)
+                emb_w.append(sd[p + '.emb_layers.1.weight']); emb_b.append(sd[p + '.emb_layers.1.bias'])
+                node['emb_off'] = emb_off
+                emb_off += emb_w[-1].shape[0]
+            elif node['kind'] == 'attn':
+                for which in ('temporal_attention', 'spatial_attention'):
+                    q = f'{p}.{which}'
+                    put(q + '.gn_w', sd[q + '.norm.weight']); put(q + '.gn_b', sd[q + '.norm.bias'])
+                    put(q + '.qkv_w', sd[q + '.qkv.weight'], adt); put(q + '.qkv_b', sd[q + '.qkv.bias'])
+                    put(q + '.proj_w', sd[q + '.proj_out.weight'], adt); put(q + '.proj_b', sd[q + '.proj_out.bias'])
+                q = p + '.temporal_attention'
+                nets = ('rpe_q', 'rpe_k', 'rpe_v')
+                put(q + '.rpe_wd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.weight'] for r in nets]))
+                put(q + '.rpe_bd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.bias'] for r in nets]))
+                for r in nets:
+                    put(f'{q}.{r}.out_w', sd[f'{q}.{r}.rpe_net.out.weight'], adt)
+                    put(f'{q}.{r}.out_b', sd[f'{q}.{r}.rpe_net.out.bias'])
+                    rpe_w.append(sd[f'{q}.{r}.rpe_net.embed_diffusion_time.weight'])
+                    rpe_b.append(sd[f'{q}.{r}.rpe_net.embed_diffusion_time.bias'])
+                node['rpe_off'] = rpe_off
+                rpe_off += 3 * node['C']
+            elif node['kind'] in ('down', 'up'):
+                put(p + '.w', conv_w(p + '.weight'), adt); put(p + '.b', sd[p + '.bias'])
+        put('emb_w', torch.cat(emb_w)); put('emb_b', torch.cat(emb_b))
+        put('rpe_t_w', torch.cat(rpe_w)); put('rpe_t_b', torch.cat(rpe_b))
+        put('out_gn_w', sd['out.0.weight']); put('out_gn_b', sd['out.0.bias'])
+        put('out_w', conv_w('out.2.weight'), adt); put('out_b', sd['out.2.bias'])
+        if self.spatial_encoding is not None:
+            enc = sd['spatial_encoding'][0]                    # (C, res, res) -> [res*res][C]
+            put('enc', enc.permute(1, 2, 0).reshape(-1, enc.shape[0]))
+        self._n_gn = 2 * sum(n['kind'] == 'res' for n in self.plan) + sum(n['kind'] == 'attn' for n in self.plan) + 1
+        self._packed = P
+
+    # ---- execution -------------------------------------------------------------------------------
+    class _Workspace:
+        def __init__(self, B, F, H, W, dev, n_gn):
+            self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
+            self.bufs = {}
+            self.graph = None
+            N = B * F
+            f32 = torch.float32
+            self.x = torch.empty(B, F, 3, H, W, device=dev, dtype=f32)
+            self.x0 = torch.empty_like(self.x)
+            self.obs = torch.empty(B, F, device=dev, dtype=f32)
+            self.lat = torch.empty_like(self.obs)
+            self.kinda = torch.empty_like(self.obs)
+            self.t = torch.empty(B, device=dev, dtype=f32)
+            self.t_override = torch.empty(N, device=dev, dtype=f32)
+            self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
+            self.stats = torch.zeros(n_gn, N, 32, 2, device=dev, dtype=torch.float64)
+            self.stat_i = 0
+            self.out = None
+
+        def buf(self, name, shape, dtype=torch.float32):
+            b = self.bufs.get(name)
+            if b is None:
+                b = self.bufs[name] = torch.empty(shape, device=self.dev, dtype=dtype)
+            return b
+
+        def next_stats(self):
+            s = self.stats[self.stat_i]
+            self.stat_i += 1
+            return s
+
+    def _res_block(self, ws, node, src1, src2, n_img, H, W, emb_out):
+        P, adt, p = self._packed, self.compute_dtype, node['p']
+        Cin, Cout, M = node['cin'], node['cout'], n_img * H * W
+        st = ws.next_stats()
+        ops.gn_stats(src1, src2, n_img, H * W, st)
+        a1 = ws.buf(p + '.a1', (M, Cin), adt)
+        ops.gn_apply(src1, src2, n_img, H, W, a1, stats=st, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'], silu=True)
+        h1 = ws.buf(p + '.h1', (M, Cout))
+        off = node['emb_off']
+        ss = self.use_scale_shift_norm
+        ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'],
+                 rowbias=None if ss else emb_out[:, off:off + Cout], out_f32=h1)
+        st2 = ws.next_stats()
+        ops.gn_stats(h1, None, n_img, H * W, st2)
+        a2 = ws.buf(p + '.a2', (M, Cout), adt)
+        ops.gn_apply(h1, None, n_img, H, W, a2, stats=st2, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
+                     scale_shift=emb_out[:, off:off + 2 * Cout] if ss else None, silu=True)
+        out = ws.buf(p + '.out', (M, Cout))
+        if node['skip']:
+            araw = ws.buf(p + '.araw', (M, Cin), adt)
+            ops.gn_apply(src1, src2, n_img, H, W, araw)                     # cast (+ concat) of the raw input
+            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, a2=araw, bias=P[p + '.b2'], out_f32=out)
+        else:
+            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b2'], residual=src1,
+                     out_f32=out)
+        return out
+
+    def _attention(self, ws, node, h, B, T, H, W, rpe_et, amask):
+        P, adt, p, C = self._packed, self.compute_dtype, node['p'], node['C']
+        HW, heads = H * W, self.num_heads
+        hd = C // heads
+        N = B * T
+        M = N * HW
+        lin = dict(n_img=M, H=1, W=1, taps=1)
+        # ---- temporal attention with RPE (unet.py:246-255, 471-540)
+        q = p + '.temporal_attention'
+        xn = ws.buf(q + '.xn', (M, C))
+        xa = ws.buf(q + '.xa', (M, C), adt)
+        ops.gn_temporal(h, B, T, HW, C, P[q + '.gn_w'], P[q + '.gn_b'], xn, xa)
+        qkv = ws.buf(q + '.qkv', (M, 3 * C))
+        ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+        hid = ws.buf(q + '.hid', (3, B * T * T, C), adt)
+        off = node['rpe_off']
+        ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
+        R = []
+        for i, r in enumerate(('rpe_q', 'rpe_k', 'rpe_v')):
+            Rn = ws.buf(f'{q}.{r}.R', (B * T * T, C))
+            ops.gemm(hid[i], P[f'{q}.{r}.out_w'], C, n_img=B * T * T, H=1, W=1, taps=1, bias=P[f'{q}.{r}.out_b'],
+                     out_f32=Rn)
+            R.append(Rn)
+        att = ws.buf(q + '.att', (M, C), adt)
+        ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads, hd,
+                          att)
+        h2 = ws.buf(q + '.out', (M, C))
+        ops.gemm(att, P[q + '.proj_w'], C, bias=P[q + '.proj_b'], residual=xn, out_f32=h2, **lin)   # + NORMALISED x
+        # ---- spatial attention (unet.py:258-266)
+        q = p + '.spatial_attention'
+        st = ws.next_stats()
+        ops.gn_stats(h2, None, N, HW, st)
+        xn = ws.buf(q + '.xn', (M, C))
+        xa = ws.buf(q + '.xa', (M, C), adt)
+        ops.gn_apply(h2, None, N, H, W, xa, stats=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
+        qkv = ws.buf(q + '.qkv', (M, 3 * C))
+        ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+        att = ws.buf(q + '.att', (M, C), adt)
+        ops.attn_spatial(qkv, N, HW, heads, hd, att)
+        h3 = ws.buf(q + '.out', (M, C))
+        ops.gemm(att, P[q + '.proj_w'], C, bias=P[q + '.proj_b'], residual=xn, out_f32=h3, **lin)
+        return h3
+
+    def _run(self, ws, T_attn, per_frame_t):
+        """The whole forward as a flat sequence of libvdm launches on the current stream."""
+        P, adt = self._packed, self.compute_dtype
+        B, F, H, W = ws.B, ws.F, ws.H, ws.W
+        N, ch, E = B * F, self.model_channels, self.time_embed_dim
+        ws.stat_i = 0
+        ws.stats.zero_()
+        a_in = ws.buf('a_in', (N * H * W, 64), adt)
+        t_frame, amask = ws.buf('t_frame', (N,)), ws.buf('amask', (N,))
+        ops.cond_mix(ws.x, ws.x0, ws.obs, ws.lat, ws.kinda, ws.t, B, F, H, W, a_in, t_frame, amask)
+        if per_frame_t:
+            t_frame = ws.t_override
+        temb = ws.buf('temb', (N, ch))
+        ops.timestep_embedding(t_frame, ch, temb)
+        lin = dict(n_img=N, H=1, W=1, taps=1)
+        l0, l0s = ws.buf('te_l0', (N, E)), ws.buf('te_l0s', (N, E))
+        ops.gemm(temb, P['te_w0'], E, bias=P['te_b0'], out_f32=l0, out_silu=l0s, **lin)
+        emb, embs = ws.buf('emb', (N, E)), ws.buf('embs', (N, E))
+        ops.gemm(l0s, P['te_w2'], E, bias=P['te_b2'], out_f32=emb, out_silu=embs, **lin)
+        emb_out = ws.buf('emb_out', (N, P['emb_w'].shape[0]))
+        ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
+        rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0]))
+        ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+
+        hs, h, cur_group, n_groups_done = [], None, None, 0
+        in_groups = True
+
+        def close_group():
+            nonlocal h, n_groups_done
+            if in_groups:
+                hs.append(h)
+                n_groups_done += 1
+                if n_groups_done == self.n_blocks_before_attn and 'enc' in P:
+                    hn = ws.buf('h_enc', tuple(h.shape))
+                    ops.add_spatial_encoding(h, P['enc'], hn, N, H * W, h.shape[1])
+                    h = hn
+
+        for node in self.plan:
+            if node['group'] != cur_group:
+                if cur_group is not None:
+                    close_group()
+                cur_group = node['group']
+                if cur_group.startswith('middle') or cur_group.startswith('output'):
+                    in_groups = False
+            kind, p = node['kind'], node['p']
+            if kind == 'conv_in':
+                h = ws.buf('h_in', (N * H * W, ch))
+                ops.gemm(a_in, P['in_w'], ch, n_img=N * H * W, H=1, W=1, taps=1, bias=P['in_b'], out_f32=h)
+            elif kind == 'res':
+                skip = hs.pop() if node['cat'] else None
+                h = self._res_block(ws, node, h, skip, N, H, W, emb_out)
+            elif kind == 'attn':
+                if T_attn != F:
+                    raise NotImplementedError('cross_frame_attention=False')
+                h = self._attention(ws, node, h, B, F, H, W, rpe_et, amask)
+            elif kind == 'down':
+                C = node['C']
+                out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C))
+                if adt == torch.bfloat16:
+                    planes = ws.buf(p + '.planes', (N * H * W, C), adt)
+                    ops.gn_apply(h, None, N, H, W, planes, out_mode=2)
+                    a1 = planes
+                else:
+                    a1 = h
+                ops.gemm(a1, P[p + '.w'], C, n_img=N, H=H // 2, W=W // 2, taps=9, a1_mode=1, bias=P[p + '.b'],
+                         out_f32=out, C1=C)
+                h, H, W = out, H // 2, W // 2
+            elif kind == 'up':
+                C = node['C']
+                out = ws.buf(p + '.out', (N * 4 * H * W, C))
+                if adt == torch.bfloat16:
+                    up = ws.buf(p + '.up', (N * 4 * H * W, C), adt)
+                    ops.gn_apply(h, None, N, H, W, up, out_mode=1)
+                    ops.gemm(up, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, bias=P[p + '.b'], out_f32=out)
+                else:
+                    ops.gemm(h, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
+                             out_f32=out, C1=C)
+                h, H, W = out, 2 * H, 2 * W
+        st = ws.next_stats()
+        ops.gn_stats(h, None, N, H * W, st)
+        a = ws.buf('out.a', (N * H * W, ch), adt)
+        ops.gn_apply(h, None, N, H, W, a, stats=st, gamma=P['out_gn_w'], beta=P['out_gn_b'], silu=True)
+        if ws.out is None:
+            ws.out = torch.empty(B, F, self.out_channels, H, W, device=ws.dev)
+        ops.gemm(a, P['out_w'], self.out_channels, n_img=N, H=H, W=W, taps=9, bias=P['out_b'], out_f32=ws.out,
+                 out_nchw=True)
+        return ws.out
+
+    def _execute(self, x, x0, obs, lat, kinda, t, frame_indices, T_attn, per_frame_t=None, clone=True):
+        if self.training:
+            raise NotImplementedError('the B200 model is inference-only: call .eval()')
+        if not x.is_cuda:
+            raise RuntimeError('the B200 model needs CUDA tensors; there is no CPU fallback')
+        if self._packed is None:
+            self._pack()
+        B, F, Cc, H, W = x.shape
+        if Cc != 3:
+            raise NotImplementedError('3-channel frames only')
+        key = (B, F, H, W, str(x.device), per_frame_t is not None)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device, self._n_gn)
+        ws.x.copy_(x)
+        ws.x0.copy_(x0)
+        ws.obs.copy_(obs.reshape(B, F))
+        ws.lat.copy_(lat.reshape(B, F))
+        ws.kinda.copy_(kinda.reshape(B, F))
+        ws.t.copy_(t.reshape(B))
+        ws.fi.copy_(frame_indices.reshape(B, F))
+        if per_frame_t is not None:
+            ws.t_override.copy_(per_frame_t.reshape(B * F))
+        if self.use_cuda_graph:
+            if ws.graph is None:
+                self._run(ws, T_attn, per_frame_t is not None)           # warm-up: allocates every buffer
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(ws, T_attn, per_frame_t is not None)
+                ws.graph = g
+            ws.graph.replay()
+            out = ws.out
+        else:
+            out = self._run(ws, T_attn, per_frame_t is not None)
+        return out.clone() if clone else out
+
+    def forward(self, x, timesteps, y=None, attn_mask=None, T=1, return_attn_weights=False, frame_indices=None,
+                **kwargs):
+        raise NotImplementedError('image-model entry point: use UNetVideoModel / CondMargVideoModel')
+
+
+class UNetVideoModel(UNetModel):
+    def __init__(self, T, use_frame_encoding, cross_frame_attention, enforce_position_invariance, *args, **kwargs):
+        if use_frame_encoding:
+            raise NotImplementedError('use_frame_encoding=True is not supported yet')
+        if not cross_frame_attention:
+            raise NotImplementedError('cross_frame_attention=False is not supported yet')
+        self.T = T
+        self.use_frame_encoding, self.cross_frame_attention = use_frame_encoding, cross_frame_attention
+        self.enforce_position_invariance = enforce_position_invariance
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x, timesteps, frame_indices=None, attn_mask=None, return_attn_weights=False, **kwargs):
+        """Unconditioned video forward (unet.py:898-912): timesteps holds one value per frame."""
+        if return_attn_weights:
+            raise NotImplementedError('return_attn_weights=True')
+        B, F = x.shape[:2]
+        if frame_indices is None:
+            frame_indices = torch.arange(F, device=x.device).view(1, F).expand(B, F)
+        ones = torch.ones(B, F, device=x.device)
+        zeros = torch.zeros(B, F, device=x.device)
+        mask = ones if attn_mask is None else attn_mask.reshape(B, F).float()
+        # latent everywhere -> the conditioning mix is the identity; attention mask = given mask
+        out = self._execute(x, x, zeros, mask, zeros, timesteps.reshape(-1)[:B].float(), frame_indices, F,
+                            per_frame_t=timesteps.reshape(B * F).float())
+        return out, None
+
+
+class CondMargVideoModel(UNetVideoModel):
+    def __init__(self, cond_emb_type, **kwargs):
+        if cond_emb_type.replace('-initzero', '') != 'channel':
+            raise NotImplementedError(f"cond_emb_type={cond_emb_type!r}: only 'channel' is supported")
+        kwargs['in_channels'] += 2
+        super().__init__(**kwargs)
+        if cond_emb_type == 'channel-initzero':
+            self.input_blocks._modules['0']._modules['0'].weight.data[:, 3] = 0.0
+        self.cond_emb_type = 'channel'
+
+    def forward(self, x, x0=None, obs_mask=None, latent_mask=None, kinda_marg_mask=None, timesteps=None,
+                frame_indices=None, return_attn_weights=False, **kwargs):
+        """unet.py:949-1026.  Called as model(x, t, **model_kwargs) (gaussian_diffusion.py:274) or
+        model(x, timesteps=t, **model_kwargs) (respace.py:119)."""
+        if timesteps is None:
+            raise TypeError('timesteps is required')
+        if kwargs.get('observed_frames', 'x_0') != 'x_0':
+            raise NotImplementedError("only observed_frames='x_0' is supported")
+        if 'x_t_minus_1' not in kwargs or 'observed_frames' not in kwargs:
+            raise KeyError('x_t_minus_1')   # the reference requires both kwargs (unet.py:958-974)
+        if return_attn_weights:
+            raise NotImplementedError('return_attn_weights=True')
+        B, F = x.shape[:2]
+        if frame_indices is None:
+            frame_indices = torch.arange(F, device=x.device).view(1, F).expand(B, F)
+        out = self._execute(x, x0, obs_mask, latent_mask, kinda_marg_mask, timesteps.float(), frame_indices, F)
+        return out, None
+
+    def __call__(self, x, *args, **kwargs):
+        # model(x, t, x0=..., ...) : map the positional timestep onto the keyword
+        if args:
+            kwargs['timesteps'] = args[0]
+            args = args[1:]
+        return super().__call__(x, *args, **kwargs)
+
+
+def param_spec(model):
+    return {k: list(v.shape) for k, v in model.state_dict().items()}
