@@ -326,4 +326,5 @@ def test_sampler_kernels_match_oracle(respacing):
         np.testing.assert_allclose(acc[:, 1].cpu().numpy(), ref_x.numpy(), rtol=2e-5)
     acc = torch.zeros(3, device='cuda', dtype=torch.float64)
     o.prior_bpd(x0, tab, lat, acc)
-    np.testing.assert_allclose(acc.cpu().numpy(), D.prior_bpd(s, x0.cpu(), lat.cpu().view(3, 4, 1, 1, 1)).numpy(), rtol=2e-5)
+    np.testing.assert_allclose(acc.cpu().numpy(), D.prior_bpd(s, x0.cpu(), lat.cpu().view(3, 4, 1, 1, 1)).numpy(), rtol=2e-5,
+                               atol=2e-7)   # -1 - lv + e^lv + m^2 cancels to ~1e-5 in fp32
