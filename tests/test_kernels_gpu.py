@@ -278,6 +278,19 @@ def test_attention_spatial_f32(L, hd):
     assert relerr(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('L,hd', [(256, 96), (64, 128), (256, 32), (100, 64)])
+def test_attention_spatial_tensor_core(L, hd):
+    o = ops()
+    n, heads = 3, 4
+    Cc = heads * hd
+    qkv = rnd(n, L, 3 * Cc, seed=1).bfloat16()
+    ref = _attn_ref(qkv.float().view(n, 1, L, 3 * Cc), heads).view(n, L, Cc)
+    for odt in (torch.float32, torch.bfloat16):
+        out = torch.empty(n, L, Cc, device='cuda', dtype=odt)
+        o.attn_spatial(qkv, n, L, heads, hd, out)
+        assert relerr(out, ref) < (4e-3 if odt == torch.float32 else 8e-3)   # P is rounded to bf16 for the PV product
+
+
 def test_rpe_hidden():
     o = ops()
     B, T, Cc = 2, 6, 64

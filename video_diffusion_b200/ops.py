@@ -10,6 +10,25 @@ import torch
 from . import _lib
 from ._lib import BF16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
 
+# Optional per-launch timing (bench.py / profiling only): when PROFILE is a list, every wrapper
+# brackets its launch with CUDA events on the current stream and appends
+# (kernel name, start event, end event, algorithmic flops, algorithmic bytes).
+PROFILE = None
+
+
+def _timed(name, fn, flops=0.0, nbytes=0.0):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((name, e0, e1, flops, nbytes))
+
+
+def _nbytes(*tensors):
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
+
 
 def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
          out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0):
@@ -34,13 +53,17 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     g.ld_out_bf16 = out_bf16.shape[-1] if out_bf16 is not None else 0
     g.out_nchw = int(out_nchw)
     g.out_silu_f32 = ptr(out_silu)
-    check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm')
+    M = n_img * H * W
+    K = taps * g.C1 + g.C2
+    name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if taps == 9 else '_linear')
+    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K)
 
 
 def gn_stats(src1, src2, n_img, HW, stats):
     lib = _lib.load()
-    check(lib.vdm_gn_stats(ptr(src1), src1.shape[-1], ptr(src2), 0 if src2 is None else src2.shape[-1],
-                           n_img, HW, ptr(stats), stream()), 'vdm_gn_stats')
+    _timed('gn_stats', lambda: check(lib.vdm_gn_stats(ptr(src1), src1.shape[-1], ptr(src2),
+                                                      0 if src2 is None else src2.shape[-1], n_img, HW, ptr(stats),
+                                                      stream()), 'vdm_gn_stats'), nbytes=_nbytes(src1, src2))
 
 
 def gn_apply(src1, src2, n_img, H, W, out, *, stats=None, gamma=None, beta=None, scale_shift=None, silu=False,
@@ -55,43 +78,50 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats=None, gamma=None, beta=None,
     a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)
     a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
     a.out, a.out_f32_copy = ptr(out), ptr(copy)
-    check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply')
+    _timed('gn_apply', lambda: check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply'),
+           nbytes=_nbytes(src1, src2, out, copy))
 
 
 def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):
     lib = _lib.load()
-    check(lib.vdm_gn_temporal(ptr(x), B, T, HW, Cc, ptr(gamma), ptr(beta), ptr(out_f32), ptr(out_a), dt(out_a.dtype),
-                              stream()), 'vdm_gn_temporal')
+    _timed('gn_temporal', lambda: check(lib.vdm_gn_temporal(ptr(x), B, T, HW, Cc, ptr(gamma), ptr(beta), ptr(out_f32),
+                                                            ptr(out_a), dt(out_a.dtype), stream()), 'vdm_gn_temporal'),
+           nbytes=_nbytes(x, out_f32, out_a))
 
 
 def add_spatial_encoding(h, enc, out, n_img, HW, Cc):
-    check(_lib.load().vdm_add_spatial_encoding(ptr(h), ptr(enc), ptr(out), n_img, HW, Cc, stream()),
-          'vdm_add_spatial_encoding')
+    _timed('add_spatial_encoding', lambda: check(_lib.load().vdm_add_spatial_encoding(
+        ptr(h), ptr(enc), ptr(out), n_img, HW, Cc, stream()), 'vdm_add_spatial_encoding'), nbytes=_nbytes(h, out))
 
 
 def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask):
-    check(_lib.load().vdm_cond_mix(ptr(x), ptr(x0), ptr(obs), ptr(lat), ptr(kinda), ptr(t), B, F, H, W, ptr(a_out),
-                                   dt(a_out.dtype), ptr(t_frame), ptr(attn_mask), stream()), 'vdm_cond_mix')
+    _timed('cond_mix', lambda: check(_lib.load().vdm_cond_mix(
+        ptr(x), ptr(x0), ptr(obs), ptr(lat), ptr(kinda), ptr(t), B, F, H, W, ptr(a_out), dt(a_out.dtype), ptr(t_frame),
+        ptr(attn_mask), stream()), 'vdm_cond_mix'), nbytes=_nbytes(x, x0, a_out))
 
 
 def timestep_embedding(t_frame, dim, out):
-    check(_lib.load().vdm_timestep_embedding(ptr(t_frame), t_frame.numel(), dim, ptr(out), stream()),
-          'vdm_timestep_embedding')
+    _timed('timestep_embedding', lambda: check(_lib.load().vdm_timestep_embedding(
+        ptr(t_frame), t_frame.numel(), dim, ptr(out), stream()), 'vdm_timestep_embedding'))
 
 
 def rpe_hidden(e_t, frame_indices, wd, bd, B, T, Cc, out):
-    check(_lib.load().vdm_rpe_hidden(e_t.data_ptr(), e_t.stride(0), ptr(frame_indices), ptr(wd), ptr(bd), B, T, Cc,
-                                     ptr(out), dt(out.dtype), stream()), 'vdm_rpe_hidden')
+    _timed('rpe_hidden', lambda: check(_lib.load().vdm_rpe_hidden(
+        e_t.data_ptr(), e_t.stride(0), ptr(frame_indices), ptr(wd), ptr(bd), B, T, Cc, ptr(out), dt(out.dtype),
+        stream()), 'vdm_rpe_hidden'), nbytes=_nbytes(out))
 
 
 def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, out):
-    check(_lib.load().vdm_attn_temporal(ptr(qkv), ptr(r_q), ptr(r_k), ptr(r_v), ptr(mask), int(pad_interact), B, T,
-                                        HW, heads, hd, ptr(out), dt(out.dtype), stream()), 'vdm_attn_temporal')
+    _timed('attn_temporal', lambda: check(_lib.load().vdm_attn_temporal(
+        ptr(qkv), ptr(r_q), ptr(r_k), ptr(r_v), ptr(mask), int(pad_interact), B, T, HW, heads, hd, ptr(out),
+        dt(out.dtype), stream()), 'vdm_attn_temporal'), flops=2.0 * 5 * B * HW * heads * T * T * hd,
+           nbytes=_nbytes(qkv, out))
 
 
 def attn_spatial(qkv, n_img, L, heads, hd, out):
-    check(_lib.load().vdm_attn_spatial(ptr(qkv), dt(qkv.dtype), n_img, L, heads, hd, ptr(out), dt(out.dtype),
-                                       stream()), 'vdm_attn_spatial')
+    _timed('attn_spatial', lambda: check(_lib.load().vdm_attn_spatial(
+        ptr(qkv), dt(qkv.dtype), n_img, L, heads, hd, ptr(out), dt(out.dtype), stream()), 'vdm_attn_spatial'),
+           flops=4.0 * n_img * heads * L * L * hd, nbytes=_nbytes(qkv, out))
 
 
 def sampler_step(mode, x, eps, noise, t, tables, clip_denoised=True, eta=0.0, sample=None, pred_xstart=None,
@@ -100,9 +130,10 @@ def sampler_step(mode, x, eps, noise, t, tables, clip_denoised=True, eta=0.0, sa
     per_batch = x.numel() // B
     if sample is None:
         sample = torch.empty_like(x)
-    check(_lib.load().vdm_sampler_step(mode, ptr(x), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B,
-                                       per_batch, int(clip_denoised), float(eta), ptr(sample), ptr(pred_xstart),
-                                       ptr(mean), stream()), 'vdm_sampler_step')
+    _timed('sampler_step', lambda: check(_lib.load().vdm_sampler_step(
+        mode, ptr(x), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B, per_batch, int(clip_denoised),
+        float(eta), ptr(sample), ptr(pred_xstart), ptr(mean), stream()), 'vdm_sampler_step'),
+           nbytes=_nbytes(x, eps, noise, sample, pred_xstart, mean))
     return sample
 
 

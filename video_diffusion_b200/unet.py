@@ -347,8 +347,11 @@ class UNetModel(nn.Module):
         xn = ws.buf(q + '.xn', (M, C))
         xa = ws.buf(q + '.xa', (M, C), adt)
         ops.gn_apply(h2, None, N, H, W, xa, stats=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
-        qkv = ws.buf(q + '.qkv', (M, 3 * C))
-        ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+        qkv = ws.buf(q + '.qkv', (M, 3 * C), adt)       # bf16 mode: tensor-core flash kernel on bf16 q, k, v
+        if adt == torch.bfloat16:
+            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+        else:
+            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
         att = ws.buf(q + '.att', (M, C), adt)
         ops.attn_spatial(qkv, N, HW, heads, hd, att)
         h3 = ws.buf(q + '.out', (M, C))
