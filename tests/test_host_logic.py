@@ -1,0 +1,118 @@
+"""CPU tests of the product's host-side logic: frame-index schedules (bit-exact vs the reference),
+schedule tables / respacing, state_dict compatibility, C-ABI surface, and the world_size-2 gather."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, diffusion_oracle as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frame_index_schedules_bit_exact(golden):
+    from video_diffusion_b200.inference_util import inference_strategies
+    for rec in golden.json('frame_indices'):
+        it = inference_strategies[rec['mode']](video_length=rec['T'], num_obs=rec['obs'], max_frames=rec['max_frames'],
+                                               step_size=rec['step_size'])
+        got = [[[int(i) for i in o], [int(i) for i in l]] for o, l in it]
+        assert got == rec['steps'], rec['mode']
+
+
+def test_exp_past_overrun_asserts_like_reference():
+    from video_diffusion_b200.inference_util import inference_strategies
+    with pytest.raises(AssertionError):      # (T - obs) % step != 0 -> latent index >= T
+        list(inference_strategies['exp-past'](video_length=300, num_obs=36, max_frames=20, step_size=7))
+    with pytest.raises(NotImplementedError):
+        inference_strategies['adaptive-autoreg'](video_length=30, num_obs=5, max_frames=10, step_size=5)
+
+
+def test_masks_match_reference_script():
+    from video_diffusion_b200.sampling import get_masks
+    x0 = torch.zeros(2, 7, 3, 4, 4)
+    obs, lat, kin = get_masks(x0, 3)
+    assert obs.shape == (2, 7, 1, 1, 1)
+    assert obs.flatten().tolist() == [1, 1, 1, 0, 0, 0, 0] * 2
+    assert torch.equal(lat, 1 - obs) and float(kin.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('case', cases.DIFFUSION_CASES, ids=lambda c: c['name'])
+def test_schedule_tables_bit_exact(golden, case):
+    from video_diffusion_b200 import create_gaussian_diffusion
+    from video_diffusion_b200.gaussian_diffusion import device_tables
+    g = golden.npz('diffusion')
+    d = create_gaussian_diffusion(steps=1000, noise_schedule=case['schedule'], timestep_respacing=case['respacing'],
+                                  rescale_timesteps=True, rescale_learned_sigmas=True)
+    for attr in ('betas', 'alphas_cumprod', 'alphas_cumprod_prev', 'sqrt_alphas_cumprod',
+                 'sqrt_one_minus_alphas_cumprod', 'log_one_minus_alphas_cumprod', 'sqrt_recip_alphas_cumprod',
+                 'sqrt_recipm1_alphas_cumprod', 'posterior_variance', 'posterior_log_variance_clipped',
+                 'posterior_mean_coef1', 'posterior_mean_coef2'):
+        np.testing.assert_array_equal(getattr(d, attr), g[f"{case['name']}/{attr}"], err_msg=attr)
+    assert d.timestep_map == g[f"{case['name']}/timestep_map"].tolist()
+    s = D.Schedule(1000, case['schedule'], case['respacing'])
+    assert torch.equal(device_tables(d), device_tables(s_like=s))
+
+
+def test_state_dict_keys_and_shapes_match_reference(golden):
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):
+        kw = video_model_and_diffusion_defaults()
+        kw.update(cases.ref_config(name))
+        with torch.device('meta'):
+            model, _ = create_video_model_and_diffusion(**kw)
+        assert {k: list(v.shape) for k, v in model.state_dict().items()} == golden.json('spec_' + name)
+
+
+def test_zero_init_modules_like_reference():
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config('tiny'))
+    model, _ = create_video_model_and_diffusion(**kw)
+    sd = model.state_dict()
+    zero = [k for k in sd if re.search(r'out_layers\.3|proj_out|rpe_net\.out|^out\.2', k)]
+    assert zero and all(float(sd[k].abs().sum()) == 0 for k in zero)
+    assert float(sd['input_blocks.1.0.in_layers.2.weight'].abs().sum()) > 0
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from video_diffusion_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'vdm.h')).read()
+    declared = sorted(set(re.findall(r'\b(vdm_[a-z0-9_]+)\s*\(', header)))
+    assert declared and set(declared) == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)       # loads without a GPU; no compute calls here
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.vdm_version.restype = ctypes.c_int
+    assert lib.vdm_version() >= 100
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from video_diffusion_b200 import dist as vd
+    vd.init('gloo')
+    tasks = vd.shard_tasks(5, rank, world)                      # 5 tasks of 2 videos, 9 videos in total
+    ids = [i for t in tasks for i in vd.task_video_indices(t, 2, 9)]
+    rows = torch.stack([torch.full((3, 2), i, dtype=torch.uint8) for i in ids])
+    out, out_ids = vd.gather_ragged(rows, torch.tensor(ids))
+    q.put((rank, out_ids.tolist(), out[:, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_ragged_gather_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, ids, vals in res:
+        assert ids == list(range(9)) and vals == list(range(9))

@@ -1,0 +1,111 @@
+"""End-to-end parity on the B200 for the two callers of the hot path, tiny config (C1):
+script-style sampling (`infer_video`), `ddim_sample_loop`, and the ELBO loop, against fixtures
+produced by the unmodified reference with the same weights and replayed noise."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases, synth  # noqa: E402
+from test_model_gpu import build_model  # noqa: E402
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    yield
+
+
+class Replay:
+    """Stands in for th.randn_like exactly like oracle/make_golden.py's NoiseReplay."""
+
+    def __init__(self, base):
+        self.i, self.base = 0, base
+
+    def __call__(self, like):
+        z = synth.make_noise(tuple(like.shape), seed=self.base + self.i).to(like.device)
+        self.i += 1
+        return z
+
+
+@pytest.fixture
+def replay():
+    saved = torch.randn_like
+
+    def install(base):
+        torch.randn_like = Replay(base)
+    yield install
+    torch.randn_like = saved
+
+
+def psnr(a, b):
+    """10 log10(1/MSE) on [0,1] images after uint8 quantisation (scripts/video_eval.py:218-225)."""
+    a = np.clip((a + 1) * 127.5, 0, 255).astype(np.uint8).astype(np.float64) / 255
+    b = np.clip((b + 1) * 127.5, 0, 255).astype(np.uint8).astype(np.float64) / 255
+    return 10 * np.log10(1.0 / max(np.mean((a - b) ** 2), 1e-12))
+
+
+@pytest.mark.parametrize('dtype,min_psnr,tol', [(torch.float32, 55.0, 2e-3), (torch.bfloat16, 30.0, None)],
+                         ids=['fp32', 'bf16'])
+def test_infer_video_independent_ddim10_matches_reference(golden, replay, dtype, min_psnr, tol):
+    from video_diffusion_b200.sampling import infer_video
+    c = cases.CHAIN_CASE
+    g = golden.npz('chain')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    replay(c['noise_seed'])
+    samples, _ = infer_video(c['mode'], model, diffusion, video, c['max_frames'], c['obs_length'], c['step_size'])
+    ref = g['chain/samples']
+    assert samples.shape == ref.shape
+    np.testing.assert_array_equal(samples[:, :c['obs_length']], ref[:, :c['obs_length']])   # observed prefix untouched
+    p = psnr(samples, ref)
+    print(f'infer_video {dtype}: PSNR vs reference = {p:.1f} dB, max abs diff = {np.abs(samples - ref).max():.3e}')
+    assert p >= min_psnr
+    if tol is not None:
+        assert np.abs(samples - ref).max() < tol
+
+
+@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 30.0)], ids=['fp32', 'bf16'])
+def test_ddim_sample_loop_matches_reference(golden, replay, dtype, min_psnr):
+    from video_diffusion_b200.inference_util import inference_strategies
+    c = cases.CHAIN_CASE
+    g = golden.npz('chain')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    obs, lat = next(iter(inference_strategies[c['mode']](video_length=c['video_length'], num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1).cuda()
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    kw = dict(frame_indices=torch.tensor(obs + lat).repeat(c['batch'], 1).cuda(), x0=x0, obs_mask=om,
+              latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om), x_t_minus_1=x0, observed_frames='x_0')
+    init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 499).cuda()
+    replay(c['noise_seed'] + 500)
+    out = diffusion.ddim_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw)
+    p = psnr(out.cpu().numpy(), g['ddim_loop/sample'])
+    print(f'ddim_sample_loop {dtype}: PSNR vs reference = {p:.1f} dB')
+    assert p >= min_psnr
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_elbo_within_half_percent(golden, replay, dtype):
+    from video_diffusion_b200.sampling import run_bpd_evaluation
+    c = cases.CHAIN_CASE
+    g = golden.npz('chain')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=c['bpd_respacing'])
+    video = synth.make_video((len(c['bpd_obs']), c['video_length'], 3, c['image_size'], c['image_size']),
+                             seed=c['video_seed'] + 1)
+    replay(c['noise_seed'] + 900)
+    got = run_bpd_evaluation(model, diffusion, video, True, c['bpd_obs'], c['bpd_lat'])
+    mf = max(len(o) + len(l) for o, l in zip(c['bpd_obs'], c['bpd_lat']))
+    ref_total = g['bpd/total_bpd'] * mf
+    rel = np.abs(got['total_bpd'] - ref_total) / np.abs(ref_total)
+    print(f'ELBO {dtype}: per-video relative error {rel}')
+    assert rel.max() < 5e-3                       # BASELINE.json: per-video ELBO within 0.5 %
+    np.testing.assert_allclose(got['prior_bpd'], g['bpd/prior_bpd'] * mf, rtol=5e-3, atol=1e-6)
+    np.testing.assert_allclose(got['vb'], g['bpd/vb'].sum(1) * mf, rtol=5e-3)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(got['mse'], g['bpd/mse'].sum(1) * mf, rtol=2e-3)
+        np.testing.assert_allclose(got['xstart_mse'], g['bpd/xstart_mse'].sum(1) * mf, rtol=2e-3)

@@ -3,15 +3,17 @@
 //   -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue (bias / per-image
 //   bias / residual / bf16 or fp32 or NCHW store).
 //
-// One CTA computes a 128 (pixels) x BLOCK_N (out channels) tile.  The K loop walks
-// taps x (C1/64) chunks of A1 -- each chunk one shifted 5-D TMA box of the channels-last
-// activation -- followed by C2/64 chunks of the optional second operand (fused 1x1 skip
-// projection, unet.py:172-173,198).  Warp roles: warp 0 TMA producer, warp 1 TMEM
-// allocator + MMA issuer (single thread), warps 2..5 epilogue (one TMEM lane quarter each).
+// Persistent kernel, one CTA per SM, looping over 128 (pixels) x BLOCK_N (out channels) tiles.  The
+// K loop walks taps x (C1/64) chunks of A1 -- each chunk one shifted 5-D TMA box of the
+// channels-last activation -- followed by C2/64 chunks of the optional second operand (fused 1x1
+// skip projection, unet.py:172-173,198).  Warp roles: warp 0 TMA producer, warp 1 TMEM allocator +
+// MMA issuer (single thread), warps 2..9 epilogue; two accumulator stages in TMEM let the epilogue
+// of one tile overlap the MMAs of the next.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -23,7 +25,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct TcParams {
   int M, N;
@@ -61,14 +64,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must fail loudly, never hang the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must fail loudly, never hang the GPU box.  On a timeout the kernel
+// reports which barrier stalled, raises a device-wide abort flag (every later wait returns at once,
+// so the grid drains and the message is flushed) and the host sees the flag after the launch.
+__device__ int g_gemm_abort = 0;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("vdm gemm_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
+    if (*reinterpret_cast<volatile int*>(&g_gemm_abort)) return;
+    if (clock64() - t0 > 600000000LL) {  // ~0.3 s
+      printf("vdm gemm_tc: mbarrier timeout tag=%d parity=%u (block %d thread %d)\n", tag, parity, blockIdx.x,
+             threadIdx.x);
+      atomicExch(&g_gemm_abort, 1);
+      return;
     }
   }
 }
@@ -141,53 +150,72 @@ constexpr uint32_t instr_desc() {
          | ((uint32_t)(BLOCK_M >> 4) << 24);  // M
 }
 
-template <int BLOCK_N>
-constexpr int tmem_cols() { return BLOCK_N < 32 ? 32 : BLOCK_N; }
+template <int BLOCK_N, int M_SUB>
+constexpr int tmem_cols() { return 2 * M_SUB * BLOCK_N < 32 ? 32 : 2 * M_SUB * BLOCK_N; }   // two accumulator stages
 
-template <int BLOCK_N, int STAGES>
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BLOCK_N, int M_SUB, int STAGES>
 struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int CHUNK = (BLOCK_N < 32 || M_SUB > 1) ? 16 : 32;
+  static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_BYTES = M_SUB * A_SUB_BYTES;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_STRIDE;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;                    // epilogue staging
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;         // + alignment slack
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
-                                                              const __grid_constant__ CUtensorMap tm_a2,
-                                                              const __grid_constant__ CUtensorMap tm_w,
-                                                              const TcParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every role loops over the CTA's
+// tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running together share A in L2).
+//   warp 0      : TMA producer (one lane), STAGES-deep smem ring
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (one lane), two accumulator stages in TMEM
+//   warps 2..9  : epilogue; the accumulator of tile i drains while the MMAs of tile i+1 run
+template <int BLOCK_N, int M_SUB, int STAGES, bool HAS_RES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
+                                                                 const __grid_constant__ CUtensorMap tm_a2,
+                                                                 const __grid_constant__ CUtensorMap tm_w,
+                                                                 const TcParams p) {
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
+  constexpr int TILE_M = BLOCK_M * M_SUB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 1) * 8);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * BLOCK_M;
   const int num_kb = p.taps * p.c1_chunks + p.c2_chunks;
+  const int n_tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
-                 "n"(tmem_cols<BLOCK_N>())
+                 "n"(tmem_cols<BLOCK_N, M_SUB>())
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -201,28 +229,34 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a1)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
-      int img0 = 0, y0 = 0, x0 = 0;
-      if (!p.is_linear) {
-        img0 = m0 / p.HW;
-        const int rem = m0 - img0 * p.HW;
-        y0 = rem / p.W;
-        x0 = rem - y0 * p.W;
-      }
       const int k1 = p.taps * p.c1_chunks;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
-        const uint32_t b_dst = a_dst + L::A_BYTES;
-        mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
-        if (kb < k1) {
-          const int tap = kb / p.c1_chunks;
-          const int cc = kb - tap * p.c1_chunks;
-          if (p.is_linear) {
-            tma_load_5d(a_dst, &tm_a1, full_bar(stage), cc * BLOCK_K, m0, 0, 0, 0);
-          } else {
-            int dy = 0, dx = 0, plane = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * BLOCK_N;
+        const int m0 = (tile / n_tiles_n) * TILE_M;
+        int img0[M_SUB], y0[M_SUB], x0[M_SUB];
+#pragma unroll
+        for (int sub = 0; sub < M_SUB; ++sub) {
+          img0[sub] = y0[sub] = x0[sub] = 0;
+          if (!p.is_linear) {
+            const int ms = m0 + sub * BLOCK_M;
+            img0[sub] = ms / p.HW;
+            const int rem = ms - img0[sub] * p.HW;
+            y0[sub] = rem / p.W;
+            x0[sub] = rem - y0[sub] * p.W;
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+          const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + L::A_BYTES;
+          mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
+          int dy = 0, dx = 0, plane = 0, c0 = 0;
+          const bool first_range = kb < k1;
+          if (first_range) {
+            const int tap = kb / p.c1_chunks;
+            c0 = (kb - tap * p.c1_chunks) * BLOCK_K;
             if (p.taps == 9) {
               const int r = tap / 3, s = tap - r * 3;
               if (p.a1_mode == 0) {
@@ -235,15 +269,21 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
                 plane = py * 2 + px;
               }
             }
-            tma_load_5d(a_dst, &tm_a1, full_bar(stage), cc * BLOCK_K, x0 + dx, y0 + dy, plane, img0);
+          } else {
+            c0 = (kb - k1) * BLOCK_K;
           }
-        } else {
-          tma_load_5d(a_dst, &tm_a2, full_bar(stage), (kb - k1) * BLOCK_K, m0, 0, 0, 0);
-        }
-        tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
+#pragma unroll
+          for (int sub = 0; sub < M_SUB; ++sub) {
+            const uint32_t dst = a_dst + sub * L::A_SUB_BYTES;
+            if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+            else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+            else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
+          }
+          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -253,85 +293,154 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       constexpr uint32_t idesc = instr_desc<BLOCK_N>();
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);   // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
-        const uint64_t a_desc = make_smem_desc(a_addr);
-        const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * M_SUB * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
+          const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
-        }
-        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-      umma_commit(tmem_full_bar);  // accumulator complete
-    }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool row_ok = row < p.M;
-    int img = 0, pix = 0;
-    if (p.rowbias != nullptr || p.out_nchw) {
-      img = row / p.HW;
-      pix = row - img * p.HW;
-    }
-    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
-#pragma unroll 1
-    for (int j = 0; j < BLOCK_N / CHUNK; ++j) {
-      uint32_t acc[CHUNK];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * CHUNK);
-      if constexpr (CHUNK == 32) tmem_ld_32(taddr, acc);
-      else tmem_ld_16(taddr, acc);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok) continue;
-      const int nb = n0 + j * CHUNK;
-      if (p.out_nchw) {
-        for (int i = 0; i < CHUNK; ++i) {
-          const int n = nb + i;
-          if (n < p.N) {
-            float v = __uint_as_float(acc[i]);
-            if (p.bias) v += p.bias[n];
-            p.out_f32[((size_t)img * p.N + n) * p.HW + pix] = v;
+          for (int sub = 0; sub < M_SUB; ++sub) {
+            const uint64_t a_desc = make_smem_desc(a_addr + sub * L::A_SUB_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
-        continue;
+        umma_commit(tmem_full_bar(as));  // accumulator complete
       }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM hands each lane one accumulator ROW; writing rows straight to global memory would touch
+    // 32 cache lines per instruction.  Each warp stages its 32 x CHUNK block in shared memory (row
+    // stride CHUNK+4 floats keeps 128-bit accesses conflict-free both ways) and re-reads it so that
+    // CHUNK/4 lanes cover one contiguous row segment: fully coalesced residual loads and stores.
+    constexpr int CHUNK = L::CHUNK;
+    constexpr int N_CHUNKS = BLOCK_N / CHUNK;
+    constexpr int STG_LD = CHUNK + 4;
+    constexpr int LPR = CHUNK / 4;   // lanes per row
+    constexpr int RPI = 32 / LPR;    // rows per instruction
+    constexpr int NRES = 32 / RPI;   // float4 per lane per chunk
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // the two warps of a quarter split the column chunks
+    float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFFSET) + ew * (32 * STG_LD);
+    const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int n0 = (tile % n_tiles_n) * BLOCK_N;
+      const int mt0 = (tile / n_tiles_n) * TILE_M;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      float4 res_cur[NRES];
+      // chunk index jj enumerates (sub-tile, column chunk): jj = sub * N_CHUNKS + j
+      auto load_residual = [&](float4 (&dst)[NRES], int jj) {
+        if constexpr (HAS_RES) {
+          const int m0 = mt0 + (jj / N_CHUNKS) * BLOCK_M;
+          const int n = n0 + (jj % N_CHUNKS) * CHUNK + c4;
 #pragma unroll
-      for (int i = 0; i < CHUNK; i += 4) {
-        const int n = nb + i;
-        if (n >= p.N) break;  // N is a multiple of 4 on this path
-        float v[4];
+          for (int i = 0; i < NRES; ++i) {
+            const int orow = m0 + q * 32 + i * RPI + r_sub;
+            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (orow < p.M && n < p.N)
+              dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
+          }
+        }
+      };
+      // fetched one chunk ahead -- the first one while this tile's MMAs are still running
+      constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
+      if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
+      mbar_wait(tmem_full_bar(as), aphase, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int jj = half; jj < TOTAL_CHUNKS; jj += 2) {
+        const int sub = jj / N_CHUNKS, j = jj - sub * N_CHUNKS;
+        const int m0 = mt0 + sub * BLOCK_M;
+        const int row = m0 + q * 32 + lane;
+        uint32_t acc[CHUNK];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)(as * M_SUB * BLOCK_N + sub * BLOCK_N + j * CHUNK);
+        if constexpr (CHUNK == 32) tmem_ld_32(taddr, acc);
+        else tmem_ld_16(taddr, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nb = n0 + j * CHUNK;
+        if (p.out_nchw) {  // lanes = consecutive pixels: already coalesced per channel
+          if (row < p.M) {
+            const int img = row / p.HW, pix = row - img * p.HW;
+            for (int i = 0; i < CHUNK; ++i) {
+              const int n = nb + i;
+              if (n < p.N) {
+                float v = __uint_as_float(acc[i]);
+                if (p.bias) v += p.bias[n];
+                p.out_f32[((size_t)img * p.N + n) * p.HW + pix] = v;
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(acc[i + e]);
-        if (p.bias) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
-          v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        for (int i = 0; i < CHUNK; i += 4)
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + i) =
+              make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                          __uint_as_float(acc[i + 3]));
+        __syncwarp();
+        float4 res_next[NRES];
+        if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
+        const int n = nb + c4;
+        if (n < p.N) {  // N is a multiple of 4 on this path
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += RPI) {
+            const int rl = rr + r_sub;
+            const int orow = m0 + q * 32 + rl;
+            if (orow < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (p.rowbias) {
+                const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)(orow / p.HW) * p.ld_rowbias + n);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if constexpr (HAS_RES) {
+                const float4 r = res_cur[rr / RPI];
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+              }
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)orow * p.ld_out + n) = v;
+              if (p.out_bf16) {
+                uint2 pk;
+                pk.x = pack_bf16x2(v.x, v.y);
+                pk.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orow * p.ld_out_bf16 + n) = pk;
+              }
+            }
+          }
         }
-        if (p.rowbias) {
-          const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)img * p.ld_rowbias + n);
-          v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        if constexpr (HAS_RES) {
+          if (jj + 2 < TOTAL_CHUNKS) {
+#pragma unroll
+            for (int i = 0; i < NRES; ++i) res_cur[i] = res_next[i];
+          }
         }
-        if (p.residual) {
-          const float4 r = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ld_res + n);
-          v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
-        }
-        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ld_out + n) = make_float4(v[0], v[1], v[2], v[3]);
-        if (p.out_bf16) {
-          uint2 pk;
-          pk.x = pack_bf16x2(v[0], v[1]);
-          pk.y = pack_bf16x2(v[2], v[3]);
-          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)row * p.ld_out_bf16 + n) = pk;
-        }
+        __syncwarp();
       }
+      // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
     }
   }
 
@@ -339,7 +448,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N>())
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N, M_SUB>())
                  : "memory");
   }
 }
@@ -400,24 +509,32 @@ int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C)
   return encode_map(map, base, 5, dims, st, box);
 }
 
-template <int BLOCK_N, int STAGES>
-int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
-           cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+template <int BLOCK_N, int M_SUB, int STAGES, bool HAS_RES>
+int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, HAS_RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
-  dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M);
-  gemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+  const int tiles = ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M * M_SUB - 1) / (BLOCK_M * M_SUB));
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, HAS_RES><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
   VDM_AFTER_LAUNCH("gemm_tc");
   return 0;
+}
+
+template <int BLOCK_N, int M_SUB, int STAGES>
+int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+           cudaStream_t stream) {
+  if (p.residual) return launch_inst<BLOCK_N, M_SUB, STAGES, true>(ma1, ma2, mw, p, stream);
+  return launch_inst<BLOCK_N, M_SUB, STAGES, false>(ma1, ma2, mw, p, stream);
 }
 
 }  // namespace
@@ -483,7 +600,17 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     ma2 = ma1;
   }
   const int64_t K = (int64_t)a->taps * a->C1 + a->C2;
-  const int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
+  int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
+  // 256x128 CTA tiles (two 128-row sub-tiles sharing every weight tile) halve the L2->smem operand
+  // traffic per FLOP; use them unless the layer is too small to fill the SMs that way.
+  int m_sub = 1;
+  if (block_n == 128) {
+    const int64_t t1 = ((M + 127) / 128) * (a->N / 128), t2 = ((M + 255) / 256) * (a->N / 128);
+    const int sms = num_sms();
+    const double cost1 = (double)((t1 + sms - 1) / sms) * 1.35, cost2 = (double)((t2 + sms - 1) / sms) * 2.0;
+    if (cost2 <= cost1 && K >= 1024) m_sub = 2;   // short-K GEMMs are epilogue-bound: keep the 32-column epilogue
+  }
+  if (const char* e = getenv("VDM_GEMM_MSUB")) m_sub = atoi(e) == 2 && block_n == 128 ? 2 : 1;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
     uint64_t st[2] = {2, (uint64_t)K * 2};
@@ -492,9 +619,11 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   switch (block_n) {
-    case 128: return launch<128, 3>(ma1, ma2, mw, p, stream);
-    case 64: return launch<64, 4>(ma1, ma2, mw, p, stream);
-    default: return launch<16, 4>(ma1, ma2, mw, p, stream);
+    case 128:
+      if (m_sub == 2) return launch<128, 2, 4>(ma1, ma2, mw, p, stream);
+      return launch<128, 1, 5>(ma1, ma2, mw, p, stream);
+    case 64: return launch<64, 1, 6>(ma1, ma2, mw, p, stream);
+    default: return launch<16, 1, 8>(ma1, ma2, mw, p, stream);
   }
 }
 

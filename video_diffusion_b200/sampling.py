@@ -1,0 +1,106 @@
+"""The two callers of the hot path, with the reference scripts' signatures:
+
+`infer_video` (scripts/video_sample.py:50-190) -- window assembly from an inference strategy,
+ancestral chain started from `x0.clone()`, write-back of the latent frames -- and
+`run_bpd_evaluation` (scripts/video_nll.py:142-188) -- ragged obs/latent packing + ELBO loop.
+
+B200-first differences (results unchanged): the video being generated stays resident in HBM for
+the whole job (the reference bounces every window through host memory, :143-146 / :185), frames
+are gathered / scattered by index on the device, and there is exactly one device->host copy at
+the end.  `to_uint8` / `save_samples` reproduce the on-disk format (:266-272).
+"""
+import os
+
+import numpy as np
+import torch
+
+from .inference_util import inference_strategies
+
+
+def get_masks(x0, num_obs):
+    """Observation / latent / kinda-marginal masks of a window whose first num_obs frames are observed."""
+    obs_mask = torch.zeros_like(x0[:, :, :1, :1, :1])
+    obs_mask[:, :num_obs] = 1
+    return obs_mask, 1 - obs_mask, torch.zeros_like(obs_mask)
+
+
+@torch.no_grad()
+def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size=1, optimal_schedule_path=None, *,
+                use_gradient_method=False, observed_frames='x_0', device=None, return_tensor=False):
+    """batch: (B, T, C, H, W) in [-1, 1].  Returns the sampled videos as a numpy array (and a dummy
+    `all_timestep_samples`, like the reference with save_all_timesteps off)."""
+    if use_gradient_method:
+        raise NotImplementedError('use_gradient_method needs autograd through the network')
+    if 'adaptive' in mode or 'goal-directed' in mode:
+        raise NotImplementedError(f'inference mode {mode!r}')
+    device = device or next(model.parameters()).device
+    B, T = batch.shape[:2]
+    video = batch.to(device, non_blocking=True).float()
+    samples = torch.zeros_like(video)
+    samples[:, :obs_length] = video[:, :obs_length]
+    schedule = iter(inference_strategies[mode](video_length=T, num_obs=obs_length, max_frames=max_frames,
+                                               step_size=step_size, optimal_schedule_path=optimal_schedule_path))
+    steps = list(range(diffusion.num_timesteps))[::-1]
+    t_all = torch.arange(diffusion.num_timesteps, device=device).view(-1, 1).expand(-1, B).contiguous()
+    for obs_idx, lat_idx in schedule:
+        idx = torch.tensor(list(obs_idx) + list(lat_idx), device=device, dtype=torch.long)
+        x0 = samples.index_select(1, idx)
+        frame_indices = idx.view(1, -1).repeat(B, 1)
+        obs_mask, latent_mask, kinda_marg_mask = get_masks(x0, len(obs_idx))
+        kwargs = dict(frame_indices=frame_indices, x0=x0, obs_mask=obs_mask, latent_mask=latent_mask,
+                      kinda_marg_mask=kinda_marg_mask, x_t_minus_1=x0, observed_frames=observed_frames)
+        local = x0.clone()
+        for step in steps:
+            local = diffusion.p_sample(model, local, t=t_all[step], clip_denoised=True, model_kwargs=kwargs,
+                                       return_attn_weights=False)['sample']
+        n_lat = len(lat_idx)
+        samples[:, idx[-n_lat:]] = local[:, -n_lat:]
+    if return_tensor:
+        return samples
+    return samples.cpu().numpy(), np.zeros([1], dtype=np.float32)
+
+
+def to_uint8(samples):
+    """(x+1)/2*255 clipped to uint8, as written to sample_XXXX-k.npy (scripts/video_sample.py:266-268)."""
+    if torch.is_tensor(samples):
+        return ((samples + 1) * 127.5).clamp(0, 255).to(torch.uint8)
+    return ((np.asarray(samples) + 1) * 127.5).clip(0, 255).astype(np.uint8)
+
+
+def save_samples(out_dir, samples_uint8, dataset_indices, sample_idx=0):
+    """One `sample_{idx:04d}-{k}.npy` of shape (T, 3, H, W) per video (scripts/video_sample.py:211-272)."""
+    os.makedirs(out_dir, exist_ok=True)
+    paths = []
+    for vid, idx in zip(samples_uint8, dataset_indices):
+        path = os.path.join(out_dir, f'sample_{int(idx):04d}-{sample_idx}.npy')
+        np.save(path, np.asarray(vid))
+        paths.append(path)
+    return paths
+
+
+@torch.no_grad()
+def run_bpd_evaluation(model, diffusion, batch, clip_denoised, obs_indices, lat_indices, t_seq=None, device=None):
+    """ELBO of `lat_indices` frames given `obs_indices` frames, per video; index lists may be ragged
+    across the batch (padded rows are masked out of attention and of the loss)."""
+    device = device or next(model.parameters()).device
+    batch = batch.to(device).float()
+    B = batch.shape[0]
+    max_frames = max(len(o) + len(l) for o, l in zip(obs_indices, lat_indices))
+    x0 = torch.zeros_like(batch[:, :max_frames])
+    obs_mask = torch.zeros_like(x0[:, :, :1, :1, :1])
+    lat_mask = torch.zeros_like(obs_mask)
+    frame_indices = torch.zeros(B, max_frames, device=device, dtype=torch.long)
+    for i, (o, l) in enumerate(zip(obs_indices, lat_indices)):
+        sel = torch.tensor(list(o) + list(l), device=device, dtype=torch.long)
+        n = sel.numel()
+        x0[i, :n] = batch[i].index_select(0, sel)
+        obs_mask[i, :len(o)] = 1.0
+        lat_mask[i, len(o):n] = 1.0
+        frame_indices[i, :n] = sel
+    # the reference script omits these two kwargs and crashes on them
+    model_kwargs = dict(frame_indices=frame_indices, x0=x0, obs_mask=obs_mask, latent_mask=lat_mask,
+                        kinda_marg_mask=torch.zeros_like(obs_mask), x_t_minus_1=x0, observed_frames='x_0')
+    metrics = diffusion.calc_bpd_loop_subsampled(model, x0, clip_denoised=clip_denoised, model_kwargs=model_kwargs,
+                                                 latent_mask=lat_mask, t_seq=t_seq)
+    metrics = {k: (v.sum(dim=1) if v.ndim > 1 else v) * max_frames for k, v in metrics.items()}
+    return {k: v.detach().cpu().numpy() for k, v in metrics.items()}
