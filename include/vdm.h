@@ -27,7 +27,7 @@ extern "C" {
 
 typedef void* vdm_stream_t; /* cudaStream_t */
 
-enum { VDM_F32 = 0, VDM_BF16 = 1 };
+enum { VDM_F32 = 0, VDM_BF16 = 1, VDM_F64 = 2, VDM_I64 = 3 };
 
 int vdm_version(void);
 const char* vdm_last_error_string(void);
@@ -69,6 +69,11 @@ typedef struct {
   int32_t ld_out, ld_out_bf16;
   int32_t out_nchw;
   float* out_silu_f32;  /* optional second output silu(out) [M][ld_out] (fp32 kernel only) */
+  int64_t* stats_out;   /* optional (bf16 kernel only, H*W % 32 == 0): per-image, per-output-channel sums of the
+                           stored values, [n_img][2][N] (plane 0: sum, plane 1: sum of squares) as 64-bit
+                           fixed point (units of 2^-24), accumulated with integer atomics -- deterministic --
+                           into a buffer the caller zeroed: the GroupNorm statistics of the NEXT layer come
+                           out of this epilogue for free (nn.py:15-17) */
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
@@ -77,15 +82,19 @@ int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
  * Replaces GroupNorm32 (nn.py:15-17) + SiLU (nn.py:10-12) + `h*(1+scale)+shift`
  * (unet.py:190-194) + th.cat of the U-Net skip (unet.py:826-828) + F.interpolate x2
  * (unet.py:63-69) + the dtype cast feeding the next conv.
- * stats: sum / sum-of-squares accumulators [n_img][32][2] (double), zeroed by the caller. */
-int vdm_gn_stats(const float* src1, int32_t C1, const float* src2, int32_t C2,
-                 int32_t n_img, int32_t HW, double* stats, vdm_stream_t stream);
+ * Statistics are kept per (image, channel): [n_img][2][C] (plane 0: sum over H*W, plane 1: sum of
+ * squares); the apply kernel folds channels into the 32 groups, so a skip tensor can be re-grouped by
+ * whichever concat consumes it.  vdm_gn_stats fills a double-precision table (caller zeroes it); the
+ * bf16 GEMM epilogue fills a 64-bit fixed-point one (vdm_gemm_args.stats_out). */
+int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t HW, double* stats, vdm_stream_t stream);
 
 typedef struct {
   const float* src1; int32_t C1;      /* [n_img*HW][C1] */
   const float* src2; int32_t C2;      /* optional second source, concatenated along C */
   int32_t n_img, H, W;
-  const double* stats;                /* NULL: no normalisation (plain cast / concat) */
+  const void* stats1;                 /* [n_img][2][C1] of src1; NULL: no normalisation (plain cast / concat) */
+  const void* stats2;                 /* [n_img][2][C2] of src2 */
+  int32_t stats_dtype;                /* VDM_I64 (GEMM epilogue, fixed point) | VDM_F64 (vdm_gn_stats) */
   const float* gamma; const float* beta;   /* [C1+C2] */
   const float* scale_shift;           /* optional [n_img][ld_ss]: scale = [0,C), shift = [C,2C) */
   int32_t ld_ss;
@@ -93,6 +102,8 @@ typedef struct {
   int32_t out_mode;                   /* 0 plain, 1 nearest-x2 upsampled, 2 stride-2 parity planes */
   int32_t out_dtype;                  /* VDM_F32 | VDM_BF16 */
   void* out;                          /* GEMM A operand */
+  void* out_raw;                      /* optional second output: the un-normalised input cast to out_dtype, plain
+                                         layout (A operand of the 1x1 skip projection, unet.py:172-173) */
   float* out_f32_copy;                /* optional fp32 copy of the plain output (attention residual) */
 } vdm_gn_apply_args;
 

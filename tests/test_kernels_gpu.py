@@ -144,6 +144,12 @@ def test_linear_rowbias_nchw_and_silu(dtype):
     assert relerr(out, ref) < 2e-5
 
 
+def _chan_stats(x, dtype=torch.float64):
+    """[n][2][C] per-(image, channel) sum and sum of squares of an NCHW tensor."""
+    xd = x.double()
+    return torch.stack([xd.sum(dim=(2, 3)), (xd * xd).sum(dim=(2, 3))], dim=1).to(dtype).contiguous()
+
+
 @pytest.mark.parametrize('C1,C2', [(64, 0), (128, 64), (512, 384), (192, 0)])
 @pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
 def test_groupnorm_apply(C1, C2, out_dtype):
@@ -157,15 +163,28 @@ def test_groupnorm_apply(C1, C2, out_dtype):
     xc = torch.cat([x1, x2], 1) if C2 else x1
     ref = F.group_norm(xc, 32, gamma, beta, eps=1e-5) * (1 + ss[:, :Cc, None, None]) + ss[:, Cc:, None, None]
     ref = F.silu(ref)
-    stats = torch.zeros(n, 32, 2, device='cuda', dtype=torch.float64)
     s1, s2 = nhwc(x1), (nhwc(x2) if C2 else None)
-    o.gn_stats(s1, s2, n, H * W, stats)
+    st1 = torch.zeros(n, 2, C1, device='cuda', dtype=torch.float64)
+    o.gn_stats(s1, n, H * W, st1)
+    assert relerr(st1, _chan_stats(x1)) < 1e-12
+    st2 = None
+    if C2:
+        st2 = torch.zeros(n, 2, C2, device='cuda', dtype=torch.float64)
+        o.gn_stats(s2, n, H * W, st2)
     out = torch.empty(n * H * W, Cc, device='cuda', dtype=out_dtype)
-    o.gn_apply(s1, s2, n, H, W, out, stats=stats, gamma=gamma, beta=beta, scale_shift=ss, silu=True)
-    assert relerr(out, nhwc(ref)) < (1e-5 if out_dtype == torch.float32 else 5e-3)
+    raw = torch.empty(n * H * W, Cc, device='cuda', dtype=out_dtype)
+    o.gn_apply(s1, s2, n, H, W, out, stats1=st1, stats2=st2, gamma=gamma, beta=beta, scale_shift=ss, silu=True,
+               out_raw=raw)
+    tol = 1e-5 if out_dtype == torch.float32 else 5e-3
+    assert relerr(out, nhwc(ref)) < tol
+    assert relerr(raw, nhwc(xc)) < tol
+    # fixed-point per-channel tables, as the bf16 GEMM epilogue produces them
+    fx = lambda t: None if t is None else (t * 2 ** 24).round().long()
+    o.gn_apply(s1, s2, n, H, W, out, stats1=fx(st1), stats2=fx(st2), gamma=gamma, beta=beta, scale_shift=ss, silu=True)
+    assert relerr(out, nhwc(ref)) < max(tol, 2e-5)
     # plain norm + fp32 copy, x2 upsample and parity layouts of the raw cast
     cp = torch.empty(n * H * W, Cc, device='cuda')
-    o.gn_apply(s1, s2, n, H, W, out, stats=stats, gamma=gamma, beta=beta, copy=cp)
+    o.gn_apply(s1, s2, n, H, W, out, stats1=st1, stats2=st2, gamma=gamma, beta=beta, copy=cp)
     assert relerr(cp, nhwc(F.group_norm(xc, 32, gamma, beta, eps=1e-5))) < 1e-5
     up = torch.empty(n * 4 * H * W, Cc, device='cuda', dtype=out_dtype)
     o.gn_apply(s1, s2, n, H, W, up, out_mode=1)
@@ -174,6 +193,27 @@ def test_groupnorm_apply(C1, C2, out_dtype):
     o.gn_apply(s1, s2, n, H, W, par, out_mode=2)
     refp = xc.view(n, Cc, H // 2, 2, W // 2, 2).permute(0, 3, 5, 2, 4, 1).reshape(-1, Cc)
     assert relerr(par, refp) < 5e-3
+
+
+def test_gemm_epilogue_groupnorm_statistics():
+    """The bf16 GEMM's fused per-(image, channel) sums against sums of its own stored output."""
+    o = ops()
+    for (n, H, W, C1, N, taps) in [(3, 16, 16, 64, 128, 9), (5, 8, 8, 128, 384, 9), (2, 32, 32, 64, 64, 9),
+                                   (4, 8, 8, 128, 256, 1), (160, 8, 8, 64, 128, 9)]:
+        x = rnd(n, C1, H, W, seed=1).bfloat16()
+        w = rnd(N, taps * C1, seed=2, scale=(taps * C1) ** -0.5).bfloat16()
+        bias, res = rnd(N, seed=3), rnd(n * H * W, N, seed=4)
+        out = torch.empty(n * H * W, N, device='cuda')
+        st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+        o.gemm(nhwc(x.float()).bfloat16(), w, N, n_img=n, H=H, W=W, taps=taps, bias=bias, residual=res, out_f32=out,
+               stats_out=st)
+        got = st.double() / 2 ** 24
+        ref = _chan_stats(from_nhwc(out, n, H, W))
+        assert relerr(got[:, 0], ref[:, 0]) < 2e-6 and relerr(got[:, 1], ref[:, 1]) < 2e-6
+        st2 = torch.zeros_like(st)
+        o.gemm(nhwc(x.float()).bfloat16(), w, N, n_img=n, H=H, W=W, taps=taps, bias=bias, residual=res, out_f32=out,
+               stats_out=st2)
+        assert torch.equal(st, st2)          # integer accumulation: bit-reproducible
 
 
 def test_groupnorm_temporal_and_spatial_encoding():
@@ -251,7 +291,7 @@ def _attn_ref(qkv, heads, mask=None, R=None, pad_interact=True):
     return out.permute(0, 1, 3, 2, 4).reshape(B, Dd, L, Cc)
 
 
-@pytest.mark.parametrize('T,hd,pad', [(20, 96, True), (10, 32, False), (7, 128, True)])
+@pytest.mark.parametrize('T,hd,pad', [(20, 96, True), (10, 32, False), (7, 128, True)])  # noqa
 def test_attention_temporal(T, hd, pad):
     o = ops()
     B, HW, heads = 2, 19, 4

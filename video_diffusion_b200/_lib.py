@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvdm.so')
 
-F32, BF16 = 0, 1
+F32, BF16, F64, I64 = 0, 1, 2, 3
 TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOGVAR=4, MODEL_VAR=5, ACP=6,
            ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11)
 TAB_COUNT = 12
@@ -29,13 +29,13 @@ class GemmArgs(C.Structure):
                 ('C1', _i32), ('C2', _i32), ('N', _i32), ('a1', _vp), ('a2', _vp), ('w', _vp), ('bias', _vp),
                 ('rowbias', _vp), ('ld_rowbias', _i32), ('residual', _vp), ('ld_res', _i32), ('out_f32', _vp),
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
-                ('out_silu_f32', _vp)]
+                ('out_silu_f32', _vp), ('stats_out', _vp)]
 
 
 class GnApplyArgs(C.Structure):
     _fields_ = [('src1', _vp), ('C1', _i32), ('src2', _vp), ('C2', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
-                ('stats', _vp), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
-                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('out_f32_copy', _vp)]
+                ('stats1', _vp), ('stats2', _vp), ('stats_dtype', _i32), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
+                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('out_raw', _vp), ('out_f32_copy', _vp)]
 
 
 _lib = None
@@ -55,7 +55,7 @@ def load():
     lib.vdm_launch_count.restype = _i64
     sig = {
         'vdm_gemm': [C.POINTER(GemmArgs), _vp],
-        'vdm_gn_stats': [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
+        'vdm_gn_stats': [_vp, _i32, _i32, _i32, _vp, _vp],
         'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
         'vdm_gn_temporal': [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
         'vdm_add_spatial_encoding': [_vp, _vp, _vp, _i32, _i32, _i32, _vp],

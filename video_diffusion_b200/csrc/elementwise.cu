@@ -7,46 +7,31 @@ namespace vdm {
 namespace {
 
 // ------------------------------------------------------------------ GroupNorm statistics
-// grid (pixel chunks, n_img); block = (C/V) x rows threads; each thread owns V channels.
-template <int V>
-__global__ void gn_stats_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2, int C2, int HW,
-                                int pix_per_block, double* __restrict__ stats) {
-  __shared__ double sg[32][2];
-  const int C = C1 + C2, CV = C / V, cpg = C / 32;
-  const int cq = threadIdx.x % CV, prow = threadIdx.x / CV, rows = blockDim.x / CV;
+// Per-(image, channel) sum and sum of squares: stats[n][0][c], stats[n][1][c] (double).
+// grid (pixel chunks, n_img); block = (C/4) x rows threads; each thread owns 4 channels.
+__global__ void gn_stats_kernel(const float* __restrict__ src, int C, int HW, int pix_per_block,
+                                double* __restrict__ stats) {
+  const int C4 = C / 4;
+  const int cq = threadIdx.x % C4, prow = threadIdx.x / C4, rows = blockDim.x / C4;
   const int n = blockIdx.y;
-  if (threadIdx.x < 64) (&sg[0][0])[threadIdx.x] = 0.0;
-  __syncthreads();
-  const int c = cq * V;
-  const float* src;
-  int cs, ld;
-  if (c < C1) { src = s1; cs = c; ld = C1; } else { src = s2; cs = c - C1; ld = C2; }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  double s = 0.0, ss = 0.0;
-  if (prow < rows) {
-    for (int p = p0 + prow; p < p1; p += rows) {
-      const float* ptr = src + ((size_t)n * HW + p) * ld + cs;
-      float v[V];
-      if constexpr (V == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(ptr));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(ptr));
-        v[0] = t.x; v[1] = t.y;
-      }
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int p = p0 + prow; p < p1; p += rows) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + ((size_t)n * HW + p) * C + cq * 4));
+    const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s += (double)v[i];
-        ss += (double)v[i] * (double)v[i];
-      }
+    for (int i = 0; i < 4; ++i) {
+      s[i] += (double)v[i];
+      ss[i] += (double)v[i] * (double)v[i];
     }
-    const int g = c / cpg;  // V divides cpg, so the V channels share a group
-    atomicAdd(&sg[g][0], s);
-    atomicAdd(&sg[g][1], ss);
   }
-  __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&stats[(size_t)n * 64 + threadIdx.x], (&sg[0][0])[threadIdx.x]);
+  double* d = stats + (size_t)n * 2 * C + cq * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(d + i, s[i]);
+    atomicAdd(d + C + i, ss[i]);
+  }
 }
 
 // ------------------------------------------------------------------ GroupNorm apply
@@ -54,128 +39,192 @@ struct ApplyParams {
   const float* s1; int C1;
   const float* s2; int C2;
   int n_img, H, W;
-  const double* stats;
+  const void* st1; const void* st2; int st_kind;   // VDM_F64: double sums, VDM_I64: fixed-point 2^-24
   const float* gamma; const float* beta;
   const float* ss; int ld_ss;
   int silu, out_mode;
-  void* out; float* copy;
+  void* out; void* out_raw; float* copy;
   int pix_per_block;
 };
 
-// grid (pixel chunks, n_img); dynamic smem: 2*C floats (per-channel multiplier / offset)
+// grid (pixel chunks, n_img); block = (C/8) x rows threads: a thread owns 8 channels for a strided set
+// of pixels, so its per-channel multiplier / offset live in registers for the whole loop.
+// dynamic smem: 2*C doubles (per-channel sums) + 64 floats (group mean / rstd)
 template <typename OutT>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
-  extern __shared__ float sm[];
-  const int C = p.C1 + p.C2, cpg = C / 32, HW = p.H * p.W;
-  float* mulc = sm;
-  float* addc = sm + C;
+__global__ void gn_apply_kernel(const ApplyParams p) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int C = p.C1 + p.C2, cpg = C / 32, HW = p.H * p.W, C8 = C / 8;
+  double* chs = reinterpret_cast<double*>(sm_raw);
+  double* chss = chs + C;
+  float* gmean = reinterpret_cast<float*>(chss + C);
+  float* grstd = gmean + 32;
   const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 1.f, b = 0.f;
-    if (p.stats) {
-      const int g = c / cpg;
+  const int c8 = threadIdx.x % C8, prow = threadIdx.x / C8, rows = blockDim.x / C8;
+  const int c = c8 * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 1.f; b[i] = 0.f; }
+  if (p.st1 != nullptr) {
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      const bool first = ch < p.C1;
+      const void* st = first ? p.st1 : p.st2;
+      const int Cs = first ? p.C1 : p.C2, cs = first ? ch : ch - p.C1;
+      const size_t i0 = (size_t)n * 2 * Cs + cs;
+      if (p.st_kind == VDM_F64) {
+        chs[ch] = reinterpret_cast<const double*>(st)[i0];
+        chss[ch] = reinterpret_cast<const double*>(st)[i0 + Cs];
+      } else {
+        chs[ch] = (double)reinterpret_cast<const long long*>(st)[i0] * (1.0 / 16777216.0);
+        chss[ch] = (double)reinterpret_cast<const long long*>(st)[i0 + Cs] * (1.0 / 16777216.0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double s = 0, q = 0;
+      for (int j = 0; j < cpg; ++j) { s += chs[threadIdx.x * cpg + j]; q += chss[threadIdx.x * cpg + j]; }
       const double cnt = (double)HW * cpg;
-      const double mean = p.stats[(size_t)n * 64 + g * 2] / cnt;
-      double var = p.stats[(size_t)n * 64 + g * 2 + 1] / cnt - mean * mean;
+      const double mean = s / cnt;
+      double var = q / cnt - mean * mean;
       if (var < 0) var = 0;
-      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-      a = rstd * p.gamma[c];
-      b = p.beta[c] - (float)mean * a;
+      gmean[threadIdx.x] = (float)mean;
+      grstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
     }
-    if (p.ss) {
-      const float sc = 1.0f + p.ss[(size_t)n * p.ld_ss + c];
-      a *= sc;
-      b = b * sc + p.ss[(size_t)n * p.ld_ss + C + c];
-    }
-    mulc[c] = a;
-    addc[c] = b;
-  }
-  __syncthreads();
-  const int C8 = C / 8;
-  const int p0 = blockIdx.x * p.pix_per_block;
-  const int npix = min(HW, p0 + p.pix_per_block) - p0;
-  OutT* out = reinterpret_cast<OutT*>(p.out);
-  for (int idx = threadIdx.x; idx < npix * C8; idx += blockDim.x) {
-    const int pl = idx / C8, c = (idx - pl * C8) * 8;
-    const int pix = p0 + pl;
-    const float* src = (c < p.C1) ? p.s1 + ((size_t)n * HW + pix) * p.C1 + c
-                                  : p.s2 + ((size_t)n * HW + pix) * p.C2 + (c - p.C1);
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = fmaf(v[i], mulc[c + i], addc[c + i]);
-      if (p.silu) y = silu_precise(y);
-      v[i] = y;
+      const int g = (c + i) / cpg;
+      a[i] = grstd[g] * p.gamma[c + i];
+      b[i] = p.beta[c + i] - gmean[g] * a[i];
     }
-    if (p.copy) {
-      float* cp = p.copy + ((size_t)n * HW + pix) * C + c;
-      *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (p.ss != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sc = 1.0f + p.ss[(size_t)n * p.ld_ss + c + i];
+      a[i] *= sc;
+      b[i] = b[i] * sc + p.ss[(size_t)n * p.ld_ss + C + c + i];
     }
-    auto store8 = [&](size_t row) {
-      OutT* o = out + row * C + c;
-      if constexpr (sizeof(OutT) == 2) {
-        uint4 pk;
-        pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-        pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(o) = pk;
-      } else {
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      }
-    };
-    if (p.out_mode == 0) {
-      store8((size_t)n * HW + pix);
+  }
+  const float* src = (c < p.C1) ? p.s1 + (size_t)n * HW * p.C1 + c : p.s2 + (size_t)n * HW * p.C2 + (c - p.C1);
+  const int ld = (c < p.C1) ? p.C1 : p.C2;
+  OutT* out = reinterpret_cast<OutT*>(p.out);
+  OutT* out_raw = reinterpret_cast<OutT*>(p.out_raw);
+  const int p0 = blockIdx.x * p.pix_per_block;
+  const int p1 = min(HW, p0 + p.pix_per_block);
+  auto store8 = [&](OutT* o, const float (&v)[8]) {
+    if constexpr (sizeof(OutT) == 2) {
+      uint4 pk;
+      pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+      pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(o) = pk;
     } else {
-      const int y = pix / p.W, x = pix - y * p.W;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  };
+  for (int pix = p0 + prow; pix < p1; pix += rows) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * ld));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * ld + 4));
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      y[i] = fmaf(x[i], a[i], b[i]);
+      if (p.silu) y[i] = silu_precise(y[i]);
+    }
+    const size_t row = (size_t)n * HW + pix;
+    if (out_raw) store8(out_raw + row * C + c, x);
+    if (p.copy) {
+      float* cp = p.copy + row * C + c;
+      *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(cp + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (p.out_mode == 0) {
+      store8(out + row * C + c, y);
+    } else {
+      const int yy = pix / p.W, xx = pix - yy * p.W;
       if (p.out_mode == 1) {  // nearest x2
         const int W2 = 2 * p.W;
-        const size_t r0 = ((size_t)n * 2 * p.H + 2 * y) * W2 + 2 * x;
-        store8(r0); store8(r0 + 1); store8(r0 + W2); store8(r0 + W2 + 1);
+        const size_t r0 = ((size_t)n * 2 * p.H + 2 * yy) * W2 + 2 * xx;
+        store8(out + r0 * C + c, y); store8(out + (r0 + 1) * C + c, y);
+        store8(out + (r0 + W2) * C + c, y); store8(out + (r0 + W2 + 1) * C + c, y);
       } else {                // parity planes of a stride-2 conv input
         const int Hh = p.H / 2, Wh = p.W / 2;
-        const int plane = (y & 1) * 2 + (x & 1);
-        store8((((size_t)n * 4 + plane) * Hh + (y >> 1)) * Wh + (x >> 1));
+        const int plane = (yy & 1) * 2 + (xx & 1);
+        store8(out + ((((size_t)n * 4 + plane) * Hh + (yy >> 1)) * Wh + (xx >> 1)) * C + c, y);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------ temporal GroupNorm
-// x: [B][T][HW][C]; one thread per (b, pixel, group): stats over T frames x cpg channels.
+// x: [B][T][HW][C]; GroupNorm over (C/32 channels x T frames) per (b, pixel).  One warp per pixel:
+// pass 1 streams the pixel's T x C values with coalesced float4 loads and accumulates per-channel
+// sums in shared memory, 32 lanes fold them into group statistics, pass 2 re-reads (L1/L2-hot),
+// normalises and writes the fp32 residual copy and the GEMM A operand.
 template <typename OutT>
 __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restrict__ x, int T, int HW, int C,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ out_f32,
                                                            OutT* __restrict__ out_a) {
-  const int g = threadIdx.x & 31;
-  const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float smt[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * 8 + warp;
   const int b = blockIdx.y;
   if (pix >= HW) return;
-  const int cpg = C / 32;
+  float* chs = smt + warp * (2 * C + 64);
+  float* chq = chs + C;
+  float* ga = chq + C;          // per-group multiplier (rstd) and mean
+  float* gm = ga + 32;
+  const int cpg = C / 32, C4 = C / 4;
   const size_t frame_stride = (size_t)HW * C;
-  const float* base = x + (size_t)b * T * frame_stride + (size_t)pix * C + g * cpg;
-  float s = 0.f;
-  for (int t = 0; t < T; ++t)
-    for (int j = 0; j < cpg; ++j) s += base[t * frame_stride + j];
-  const float mean = s / (float)(T * cpg);
-  float ss = 0.f;
-  for (int t = 0; t < T; ++t)
-    for (int j = 0; j < cpg; ++j) {
-      const float d = base[t * frame_stride + j] - mean;
-      ss = fmaf(d, d, ss);
+  const float* base = x + (size_t)b * T * frame_stride + (size_t)pix * C;
+  for (int q4 = lane; q4 < C4; q4 += 32) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int t = 0; t < T; ++t) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + t * frame_stride + q4 * 4));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
     }
-  const float rstd = rsqrtf(ss / (float)(T * cpg) + 1e-5f);
-  const size_t obase = (size_t)b * T * frame_stride + (size_t)pix * C + g * cpg;
-  for (int t = 0; t < T; ++t)
-    for (int j = 0; j < cpg; ++j) {
-      const int c = g * cpg + j;
-      const float y = (base[t * frame_stride + j] - mean) * rstd * gamma[c] + beta[c];
-      if (out_f32) out_f32[obase + t * frame_stride + j] = y;
-      store_elem<OutT>(out_a + obase + t * frame_stride + j, y);
+    *reinterpret_cast<float4*>(chs + q4 * 4) = s;
+    *reinterpret_cast<float4*>(chq + q4 * 4) = q;
+  }
+  __syncwarp();
+  {
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) { s += chs[lane * cpg + j]; q += chq[lane * cpg + j]; }
+    const float cnt = (float)(T * cpg);
+    const float mean = s / cnt;
+    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    gm[lane] = mean;
+    ga[lane] = rsqrtf(var + 1e-5f);
+  }
+  __syncwarp();
+  for (int q4 = lane; q4 < C4; q4 += 32) {
+    const int c = q4 * 4;
+    float a[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int g = (c + i) / cpg;
+      a[i] = ga[g] * gamma[c + i];
+      bb[i] = beta[c + i] - gm[g] * a[i];
     }
+    for (int t = 0; t < T; ++t) {
+      const size_t off = (size_t)b * T * frame_stride + t * frame_stride + (size_t)pix * C + c;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+      const float y0 = fmaf(v.x, a[0], bb[0]), y1 = fmaf(v.y, a[1], bb[1]);
+      const float y2 = fmaf(v.z, a[2], bb[2]), y3 = fmaf(v.w, a[3], bb[3]);
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 pk;
+        pk.x = pack_bf16x2(y0, y1);
+        pk.y = pack_bf16x2(y2, y3);
+        *reinterpret_cast<uint2*>(out_a + off) = pk;
+      } else {
+        *reinterpret_cast<float4*>(out_a + off) = make_float4(y0, y1, y2, y3);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* h, const float* __restrict__ enc,
@@ -286,24 +335,17 @@ __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict
 
 using namespace vdm;
 
-extern "C" int vdm_gn_stats(const float* src1, int32_t C1, const float* src2, int32_t C2, int32_t n_img, int32_t HW,
-                            double* stats, vdm_stream_t stream) {
-  const int C = C1 + C2;
-  VDM_REQUIRE(src1 && stats && C1 > 0 && (C2 == 0 || src2), "gn_stats: NULL pointer");
-  VDM_REQUIRE(C % 64 == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C <= 2048, "gn_stats: unsupported channels %d+%d", C1, C2);
-  const int cpg = C / 32;
-  const int V = (cpg % 4 == 0) ? 4 : 2;
-  const int CV = C / V;
-  VDM_REQUIRE(CV <= 1024, "gn_stats: too many channels");
-  const int rows = CV >= 256 ? 1 : 256 / CV;
-  const int threads = CV * rows;
+extern "C" int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t HW, double* stats,
+                            vdm_stream_t stream) {
+  VDM_REQUIRE(src && stats && C > 0, "gn_stats: NULL pointer");
+  VDM_REQUIRE(C % 32 == 0 && C <= 4096, "gn_stats: unsupported channel count %d", C);
+  const int C4 = C / 4;
+  const int rows = C4 >= 256 ? 1 : 256 / C4;
+  const int threads = C4 * rows;
   int ppb = 256;
   while (ppb > 16 && (long long)((HW + ppb - 1) / ppb) * n_img < 2LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, n_img);
-  if (V == 4)
-    gn_stats_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>(src1, C1, src2, C2, HW, ppb, stats);
-  else
-    gn_stats_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>(src1, C1, src2, C2, HW, ppb, stats);
+  gn_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, C, HW, ppb, stats);
   VDM_AFTER_LAUNCH("gn_stats");
   return 0;
 }
@@ -311,23 +353,30 @@ extern "C" int vdm_gn_stats(const float* src1, int32_t C1, const float* src2, in
 extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   const int C = a->C1 + a->C2;
   VDM_REQUIRE(a->src1 && a->out && (a->C2 == 0 || a->src2), "gn_apply: NULL pointer");
-  VDM_REQUIRE(C % 64 == 0 && a->C1 % 8 == 0 && a->C2 % 8 == 0, "gn_apply: unsupported channels %d+%d", a->C1, a->C2);
-  VDM_REQUIRE(!a->stats || (a->gamma && a->beta), "gn_apply: gamma/beta missing");
+  VDM_REQUIRE(C % 32 == 0 && a->C1 % 8 == 0 && a->C2 % 8 == 0 && C <= 2048, "gn_apply: unsupported channels %d+%d",
+              a->C1, a->C2);
+  VDM_REQUIRE(!a->stats1 || (a->gamma && a->beta), "gn_apply: gamma/beta missing");
+  VDM_REQUIRE(!a->stats1 || a->C2 == 0 || a->stats2, "gn_apply: stats2 missing");
+  VDM_REQUIRE(!a->stats1 || a->stats_dtype == VDM_F64 || a->stats_dtype == VDM_I64, "gn_apply: bad stats_dtype");
   VDM_REQUIRE(a->out_mode >= 0 && a->out_mode <= 2, "gn_apply: bad out_mode");
   VDM_REQUIRE(a->out_mode != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "gn_apply: parity split needs even H, W");
   VDM_REQUIRE(a->out_mode == 0 || a->out_f32_copy == nullptr, "gn_apply: fp32 copy only with plain output");
-  ApplyParams p{a->src1, a->C1, a->src2, a->C2, a->n_img, a->H, a->W, a->stats, a->gamma, a->beta,
-                a->scale_shift, a->ld_ss, a->silu, a->out_mode, a->out, a->out_f32_copy, 0};
+  ApplyParams p{a->src1, a->C1, a->src2, a->C2, a->n_img, a->H, a->W, a->stats1, a->stats2,
+                a->stats_dtype, a->gamma, a->beta, a->scale_shift, a->ld_ss, a->silu, a->out_mode,
+                a->out, a->out_raw, a->out_f32_copy, 0};
   const int HW = a->H * a->W;
-  int ppb = 64;
-  while (ppb > 4 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
+  const int C8 = C / 8;
+  const int rows = C8 >= 256 ? 1 : 256 / C8;
+  const int threads = C8 * rows;
+  int ppb = rows * 16;
+  while (ppb > rows && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
   p.pix_per_block = ppb;
   dim3 grid((HW + ppb - 1) / ppb, a->n_img);
-  const size_t smem = 2 * (size_t)C * sizeof(float);
+  const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);
   if (a->out_dtype == VDM_BF16)
-    gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    gn_apply_kernel<__nv_bfloat16><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   else
-    gn_apply_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    gn_apply_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
   VDM_AFTER_LAUNCH("gn_apply");
   return 0;
 }
@@ -335,13 +384,19 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
 extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C, const float* gamma,
                                const float* beta, float* out_f32, void* out_a, int32_t out_dtype, vdm_stream_t stream) {
   VDM_REQUIRE(x && gamma && beta && out_a, "gn_temporal: NULL pointer");
-  VDM_REQUIRE(C % 32 == 0, "gn_temporal: C must be a multiple of 32");
+  VDM_REQUIRE(C % 32 == 0 && C <= 1024, "gn_temporal: C=%d must be a multiple of 32, <= 1024", C);
   dim3 grid((HW + 7) / 8, B);
-  if (out_dtype == VDM_BF16)
-    gn_temporal_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32,
-                                                                             (__nv_bfloat16*)out_a);
-  else
-    gn_temporal_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32, (float*)out_a);
+  const size_t smem = 8 * (2 * (size_t)C + 64) * sizeof(float);
+  if (out_dtype == VDM_BF16) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
+    gn_temporal_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32,
+                                                                                (__nv_bfloat16*)out_a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
+    gn_temporal_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32, (float*)out_a);
+  }
   VDM_AFTER_LAUNCH("gn_temporal");
   return 0;
 }

@@ -122,6 +122,7 @@ int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream) {
               a->C1, a->C2);
   VDM_REQUIRE(a->a1_mode >= 0 && a->a1_mode <= 2, "gemm_simt: bad a1_mode");
   VDM_REQUIRE(a->C2 == 0 || a->a2 != nullptr, "gemm_simt: a2 is NULL");
+  VDM_REQUIRE(a->stats_out == nullptr, "gemm_simt: stats_out is only produced by the bf16 tensor-core kernel");
   SimtParams p{};
   p.M = a->n_img * a->H * a->W;
   p.N = a->N;

@@ -43,6 +43,7 @@ struct TcParams {
   __nv_bfloat16* out_bf16;
   int ld_out, ld_out_bf16;
   int out_nchw;
+  int64_t* stats_out;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,7 +167,10 @@ struct SmemLayout {
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_STRIDE;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;                    // epilogue staging
-  static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
+  static constexpr int TOTAL_CHUNKS = M_SUB * (BLOCK_N / CHUNK);
+  static constexpr int PART_FLOATS = ((TOTAL_CHUNKS + 1) / 2) * CHUNK * 2;    // per-warp GroupNorm partial sums
+  static constexpr int WARP_STG_FLOATS = 32 * (CHUNK + 4) + PART_FLOATS;
+  static constexpr int STG_BYTES = EPI_WARPS * WARP_STG_FLOATS * 4;
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;         // + alignment slack
@@ -338,7 +342,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int half = ew >> 2;        // the two warps of a quarter split the column chunks
-    float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFFSET) + ew * (32 * STG_LD);
+    float* stg_base = reinterpret_cast<float*>(smem_gen + L::STG_OFFSET);
+    float* stg = stg_base + ew * L::WARP_STG_FLOATS;
+    float* part = stg + 32 * STG_LD;
     const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         float4 res_next[NRES];
         if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
         const int n = nb + c4;
+        float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n < p.N) {  // N is a multiple of 4 on this path
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
@@ -419,6 +426,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const float4 r = res_cur[rr / RPI];
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
               }
+              ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+              ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+              ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
               if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)orow * p.ld_out + n) = v;
               if (p.out_bf16) {
                 uint2 pk;
@@ -427,6 +437,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orow * p.ld_out_bf16 + n) = pk;
               }
             }
+          }
+        }
+        if (p.stats_out != nullptr) {
+          // GroupNorm statistics of the stored tile, step 1: fold the lanes that share a column quad and
+          // park the warp's 32-row partial sums in shared memory.
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {
+            ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
+            ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
+            ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
+            ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
+          }
+          if (r_sub == 0) {
+            float* dst = part + (jj >> 1) * (2 * CHUNK) + c4;
+            *reinterpret_cast<float4*>(dst) = ssum;
+            *reinterpret_cast<float4*>(dst + CHUNK) = ssq;
           }
         }
         if constexpr (HAS_RES) {
@@ -441,6 +467,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+      if (p.stats_out != nullptr) {
+        // step 2 (all epilogue warps): one thread per (channel, plane) adds the row-block partials in a
+        // fixed order and accumulates them into the per-(image, channel) table with 64-bit fixed-point
+        // atomics -- integer addition is associative, so the statistics (and everything downstream) are
+        // bit-reproducible from run to run.
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        const int te = threadIdx.x - 64;
+        if (te < 2 * BLOCK_N) {
+          const int plane = te / BLOCK_N, nl = te - plane * BLOCK_N;
+          const int j = nl / CHUNK, cl = nl - j * CHUNK;
+          if (n0 + nl < p.N) {
+            float acc = 0.f;
+            int cur_img = -1;
+            unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out);
+            auto flush = [&]() {
+              if (cur_img >= 0) {
+                const long long fx = __double2ll_rn((double)acc * 16777216.0);
+                atomicAdd(tab + ((size_t)cur_img * 2 + plane) * p.N + n0 + nl, (unsigned long long)fx);
+              }
+            };
+#pragma unroll 1
+            for (int sub = 0; sub < M_SUB; ++sub) {
+              const int jj = sub * N_CHUNKS + j;
+              const int hw = jj & 1;   // which of a quarter's two warps handled this chunk
+#pragma unroll 1
+              for (int qq = 0; qq < 4; ++qq) {
+                const int row0 = mt0 + sub * BLOCK_M + qq * 32;
+                if (row0 >= p.M) break;
+                const int img = row0 / p.HW;
+                if (img != cur_img) {
+                  flush();
+                  acc = 0.f;
+                  cur_img = img;
+                }
+                const int wew = hw * 4 + ((qq - 2) & 3);
+                acc += stg_base[wew * L::WARP_STG_FLOATS + 32 * STG_LD + (jj >> 1) * (2 * CHUNK) + plane * CHUNK + cl];
+              }
+            }
+            flush();
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      }
     }
   }
 
@@ -547,6 +616,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   VDM_REQUIRE(a->a1_mode == 0 || (a->a1_mode == 1 && a->taps == 9), "gemm_tc: unsupported a1_mode %d", a->a1_mode);
   VDM_REQUIRE(a->out_nchw || a->N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", a->N);
   VDM_REQUIRE(a->out_silu_f32 == nullptr, "gemm_tc: out_silu_f32 is only supported by the fp32 kernel");
+  VDM_REQUIRE(a->stats_out == nullptr || (!a->out_nchw && (a->H * a->W) % 32 == 0),
+              "gemm_tc: stats_out needs H*W %% 32 == 0 and a channels-last output");
   VDM_REQUIRE(!a->out_nchw || (a->out_f32 && !a->residual && !a->rowbias && !a->out_bf16),
               "gemm_tc: NCHW output supports bias only");
   const int HW = a->H * a->W;
@@ -564,6 +635,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.residual = a->residual; p.ld_res = a->ld_res;
   p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
+  p.stats_out = a->stats_out;
 
   CUtensorMap ma1, ma2, mw;
   int rc;

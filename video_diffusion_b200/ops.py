@@ -31,7 +31,7 @@ def _nbytes(*tensors):
 
 
 def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
-         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0):
+         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None):
     """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm)."""
     lib = _lib.load()
     g = GemmArgs()
@@ -53,33 +53,36 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     g.ld_out_bf16 = out_bf16.shape[-1] if out_bf16 is not None else 0
     g.out_nchw = int(out_nchw)
     g.out_silu_f32 = ptr(out_silu)
+    g.stats_out = ptr(stats_out)
     M = n_img * H * W
     K = taps * g.C1 + g.C2
     name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if taps == 9 else '_linear')
     _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K)
 
 
-def gn_stats(src1, src2, n_img, HW, stats):
+def gn_stats(src, n_img, HW, stats):
+    """Per-(image, channel) sum / sum of squares of src [n_img*HW][C] into stats [n_img][2][C] (float64, zeroed)."""
     lib = _lib.load()
-    _timed('gn_stats', lambda: check(lib.vdm_gn_stats(ptr(src1), src1.shape[-1], ptr(src2),
-                                                      0 if src2 is None else src2.shape[-1], n_img, HW, ptr(stats),
-                                                      stream()), 'vdm_gn_stats'), nbytes=_nbytes(src1, src2))
+    _timed('gn_stats', lambda: check(lib.vdm_gn_stats(ptr(src), src.shape[-1], n_img, HW, ptr(stats), stream()),
+                                     'vdm_gn_stats'), nbytes=_nbytes(src))
 
 
-def gn_apply(src1, src2, n_img, H, W, out, *, stats=None, gamma=None, beta=None, scale_shift=None, silu=False,
-             out_mode=0, copy=None):
+def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=None, beta=None, scale_shift=None,
+             silu=False, out_mode=0, copy=None, out_raw=None):
     lib = _lib.load()
     a = GnApplyArgs()
     a.src1, a.C1 = ptr(src1), src1.shape[-1]
     a.src2, a.C2 = ptr(src2), (0 if src2 is None else src2.shape[-1])
     a.n_img, a.H, a.W = n_img, H, W
-    a.stats, a.gamma, a.beta = ptr(stats), ptr(gamma), ptr(beta)
+    a.stats1, a.stats2 = ptr(stats1), ptr(stats2)
+    a.stats_dtype = _lib.F64 if (stats1 is not None and stats1.dtype == torch.float64) else _lib.I64
+    a.gamma, a.beta = ptr(gamma), ptr(beta)
     a.scale_shift = None if scale_shift is None else scale_shift.data_ptr()
     a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)
     a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
-    a.out, a.out_f32_copy = ptr(out), ptr(copy)
+    a.out, a.out_raw, a.out_f32_copy = ptr(out), ptr(out_raw), ptr(copy)
     _timed('gn_apply', lambda: check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply'),
-           nbytes=_nbytes(src1, src2, out, copy))
+           nbytes=_nbytes(src1, src2, out, copy, out_raw))
 
 
 def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):

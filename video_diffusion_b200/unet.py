@@ -256,7 +256,7 @@ class UNetModel(nn.Module):
 
     # ---- execution -------------------------------------------------------------------------------
     class _Workspace:
-        def __init__(self, B, F, H, W, dev, n_gn):
+        def __init__(self, B, F, H, W, dev):
             self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
             self.bufs = {}
             self.graph = None
@@ -270,8 +270,7 @@ class UNetModel(nn.Module):
             self.t = torch.empty(B, device=dev, dtype=f32)
             self.t_override = torch.empty(N, device=dev, dtype=f32)
             self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
-            self.stats = torch.zeros(n_gn, N, 32, 2, device=dev, dtype=torch.float64)
-            self.stat_i = 0
+            self.stat_bufs = {}
             self.out = None
 
         def buf(self, name, shape, dtype=torch.float32):
@@ -280,40 +279,68 @@ class UNetModel(nn.Module):
                 b = self.bufs[name] = torch.empty(shape, device=self.dev, dtype=dtype)
             return b
 
-        def next_stats(self):
-            s = self.stats[self.stat_i]
-            self.stat_i += 1
-            return s
+        def stats(self, name, n_img, C, dtype):
+            """Per-(image, channel) sum / sum-of-squares table [n_img][2][C]; zeroed at the start of every forward."""
+            b = self.stat_bufs.get(name)
+            if b is None:
+                b = self.stat_bufs[name] = torch.zeros(n_img, 2, C, device=self.dev, dtype=dtype)
+            return b
 
-    def _res_block(self, ws, node, src1, src2, n_img, H, W, emb_out):
+        def zero_stats(self):
+            if self.stat_bufs:
+                torch._foreach_zero_(list(self.stat_bufs.values()))
+
+    # GroupNorm statistics travel with the activation as (tensor, stats): in bf16 mode the producing GEMM's
+    # epilogue accumulates them (deterministic fixed-point atomics); otherwise the standalone kernel does (float64).
+    def _fused_stats(self, ws, name, n_img, HW, C):
+        if self.compute_dtype == torch.bfloat16 and HW % 32 == 0:
+            return ws.stats(name + '.st', n_img, C, torch.int64)
+        return None
+
+    def _stats_of(self, ws, name, h, st, n_img, HW):
+        if st is None:
+            st = ws.stats(name + '.st64', n_img, h.shape[1], torch.float64)
+            ops.gn_stats(h, n_img, HW, st)
+        return st
+
+    def _res_block(self, ws, node, x1, x2, n_img, H, W, emb_out):
+        """x1, x2: (tensor, stats) pairs; x2 is the U-Net skip (concatenated along C) or None."""
         P, adt, p = self._packed, self.compute_dtype, node['p']
-        Cin, Cout, M = node['cin'], node['cout'], n_img * H * W
-        st = ws.next_stats()
-        ops.gn_stats(src1, src2, n_img, H * W, st)
+        Cin, Cout, HW = node['cin'], node['cout'], H * W
+        M = n_img * HW
+        src1, src2 = x1[0], (x2[0] if x2 is not None else None)
+        st1 = self._stats_of(ws, p + '.in1', src1, x1[1], n_img, HW)
+        st2 = self._stats_of(ws, p + '.in2', src2, x2[1], n_img, HW) if x2 is not None else None
+        if st2 is not None and st1.dtype != st2.dtype:
+            raise RuntimeError('internal: mixed statistics precision in a concat GroupNorm')
         a1 = ws.buf(p + '.a1', (M, Cin), adt)
-        ops.gn_apply(src1, src2, n_img, H, W, a1, stats=st, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'], silu=True)
+        araw = ws.buf(p + '.araw', (M, Cin), adt) if node['skip'] else None
+        # one pass over the block input: normalised+SiLU operand of conv1 and the raw cast for the 1x1 skip
+        ops.gn_apply(src1, src2, n_img, H, W, a1, stats1=st1, stats2=st2, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'],
+                     silu=True, out_raw=araw)
         h1 = ws.buf(p + '.h1', (M, Cout))
         off = node['emb_off']
         ss = self.use_scale_shift_norm
+        st_h1 = self._fused_stats(ws, p + '.h1', n_img, HW, Cout)
         ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'],
-                 rowbias=None if ss else emb_out[:, off:off + Cout], out_f32=h1)
-        st2 = ws.next_stats()
-        ops.gn_stats(h1, None, n_img, H * W, st2)
+                 rowbias=None if ss else emb_out[:, off:off + Cout], out_f32=h1, stats_out=st_h1)
+        st_h1 = self._stats_of(ws, p + '.h1', h1, st_h1, n_img, HW)
         a2 = ws.buf(p + '.a2', (M, Cout), adt)
-        ops.gn_apply(h1, None, n_img, H, W, a2, stats=st2, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
+        ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
                      scale_shift=emb_out[:, off:off + 2 * Cout] if ss else None, silu=True)
         out = ws.buf(p + '.out', (M, Cout))
+        st_out = self._fused_stats(ws, p + '.out', n_img, HW, Cout)
         if node['skip']:
-            araw = ws.buf(p + '.araw', (M, Cin), adt)
-            ops.gn_apply(src1, src2, n_img, H, W, araw)                     # cast (+ concat) of the raw input
-            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, a2=araw, bias=P[p + '.b2'], out_f32=out)
+            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, a2=araw, bias=P[p + '.b2'], out_f32=out,
+                     stats_out=st_out)
         else:
             ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b2'], residual=src1,
-                     out_f32=out)
-        return out
+                     out_f32=out, stats_out=st_out)
+        return out, st_out
 
-    def _attention(self, ws, node, h, B, T, H, W, rpe_et, amask):
+    def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask):
         P, adt, p, C = self._packed, self.compute_dtype, node['p'], node['C']
+        h = x[0]
         HW, heads = H * W, self.num_heads
         hd = C // heads
         N = B * T
@@ -339,14 +366,17 @@ class UNetModel(nn.Module):
         ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads, hd,
                           att)
         h2 = ws.buf(q + '.out', (M, C))
-        ops.gemm(att, P[q + '.proj_w'], C, bias=P[q + '.proj_b'], residual=xn, out_f32=h2, **lin)   # + NORMALISED x
+        st = self._fused_stats(ws, q + '.out', N, HW, C)
+        # + NORMALISED x.  The rows of this GEMM are (image, pixel), so the epilogue statistics are
+        # exactly the per-image GroupNorm sums the spatial attention needs next.
+        ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h2,
+                 stats_out=st)
+        st = self._stats_of(ws, q + '.out', h2, st, N, HW)
         # ---- spatial attention (unet.py:258-266)
         q = p + '.spatial_attention'
-        st = ws.next_stats()
-        ops.gn_stats(h2, None, N, HW, st)
         xn = ws.buf(q + '.xn', (M, C))
         xa = ws.buf(q + '.xa', (M, C), adt)
-        ops.gn_apply(h2, None, N, H, W, xa, stats=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
+        ops.gn_apply(h2, None, N, H, W, xa, stats1=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
         qkv = ws.buf(q + '.qkv', (M, 3 * C), adt)       # bf16 mode: tensor-core flash kernel on bf16 q, k, v
         if adt == torch.bfloat16:
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
@@ -355,16 +385,17 @@ class UNetModel(nn.Module):
         att = ws.buf(q + '.att', (M, C), adt)
         ops.attn_spatial(qkv, N, HW, heads, hd, att)
         h3 = ws.buf(q + '.out', (M, C))
-        ops.gemm(att, P[q + '.proj_w'], C, bias=P[q + '.proj_b'], residual=xn, out_f32=h3, **lin)
-        return h3
+        st3 = self._fused_stats(ws, q + '.out', N, HW, C)
+        ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h3,
+                 stats_out=st3)
+        return h3, st3
 
     def _run(self, ws, T_attn, per_frame_t):
         """The whole forward as a flat sequence of libvdm launches on the current stream."""
         P, adt = self._packed, self.compute_dtype
         B, F, H, W = ws.B, ws.F, ws.H, ws.W
         N, ch, E = B * F, self.model_channels, self.time_embed_dim
-        ws.stat_i = 0
-        ws.stats.zero_()
+        ws.zero_stats()
         a_in = ws.buf('a_in', (N * H * W, 64), adt)
         t_frame, amask = ws.buf('t_frame', (N,)), ws.buf('amask', (N,))
         ops.cond_mix(ws.x, ws.x0, ws.obs, ws.lat, ws.kinda, ws.t, B, F, H, W, a_in, t_frame, amask)
@@ -382,18 +413,19 @@ class UNetModel(nn.Module):
         rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0]))
         ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
 
-        hs, h, cur_group, n_groups_done = [], None, None, 0
+        # activations travel as (tensor, per-channel GroupNorm statistics or None)
+        hs, x, cur_group, n_groups_done = [], None, None, 0
         in_groups = True
 
         def close_group():
-            nonlocal h, n_groups_done
+            nonlocal x, n_groups_done
             if in_groups:
-                hs.append(h)
+                hs.append(x)
                 n_groups_done += 1
                 if n_groups_done == self.n_blocks_before_attn and 'enc' in P:
-                    hn = ws.buf('h_enc', tuple(h.shape))
-                    ops.add_spatial_encoding(h, P['enc'], hn, N, H * W, h.shape[1])
-                    h = hn
+                    hn = ws.buf('h_enc', tuple(x[0].shape))
+                    ops.add_spatial_encoding(x[0], P['enc'], hn, N, H * W, x[0].shape[1])
+                    x = (hn, None)
 
         for node in self.plan:
             if node['group'] != cur_group:
@@ -405,41 +437,46 @@ class UNetModel(nn.Module):
             kind, p = node['kind'], node['p']
             if kind == 'conv_in':
                 h = ws.buf('h_in', (N * H * W, ch))
-                ops.gemm(a_in, P['in_w'], ch, n_img=N * H * W, H=1, W=1, taps=1, bias=P['in_b'], out_f32=h)
+                st = self._fused_stats(ws, 'h_in', N, H * W, ch)
+                ops.gemm(a_in, P['in_w'], ch, n_img=N, H=H, W=W, taps=1, bias=P['in_b'], out_f32=h, stats_out=st)
+                x = (h, st)
             elif kind == 'res':
                 skip = hs.pop() if node['cat'] else None
-                h = self._res_block(ws, node, h, skip, N, H, W, emb_out)
+                x = self._res_block(ws, node, x, skip, N, H, W, emb_out)
             elif kind == 'attn':
                 if T_attn != F:
                     raise NotImplementedError('cross_frame_attention=False')
-                h = self._attention(ws, node, h, B, F, H, W, rpe_et, amask)
+                x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask)
             elif kind == 'down':
                 C = node['C']
                 out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C))
                 if adt == torch.bfloat16:
                     planes = ws.buf(p + '.planes', (N * H * W, C), adt)
-                    ops.gn_apply(h, None, N, H, W, planes, out_mode=2)
+                    ops.gn_apply(x[0], None, N, H, W, planes, out_mode=2)
                     a1 = planes
                 else:
-                    a1 = h
+                    a1 = x[0]
+                st = self._fused_stats(ws, p + '.out', N, (H // 2) * (W // 2), C)
                 ops.gemm(a1, P[p + '.w'], C, n_img=N, H=H // 2, W=W // 2, taps=9, a1_mode=1, bias=P[p + '.b'],
-                         out_f32=out, C1=C)
-                h, H, W = out, H // 2, W // 2
+                         out_f32=out, C1=C, stats_out=st)
+                x, H, W = (out, st), H // 2, W // 2
             elif kind == 'up':
                 C = node['C']
                 out = ws.buf(p + '.out', (N * 4 * H * W, C))
+                st = self._fused_stats(ws, p + '.out', N, 4 * H * W, C)
                 if adt == torch.bfloat16:
                     up = ws.buf(p + '.up', (N * 4 * H * W, C), adt)
-                    ops.gn_apply(h, None, N, H, W, up, out_mode=1)
-                    ops.gemm(up, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, bias=P[p + '.b'], out_f32=out)
+                    ops.gn_apply(x[0], None, N, H, W, up, out_mode=1)
+                    ops.gemm(up, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, bias=P[p + '.b'], out_f32=out,
+                             stats_out=st)
                 else:
-                    ops.gemm(h, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
+                    ops.gemm(x[0], P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
                              out_f32=out, C1=C)
-                h, H, W = out, 2 * H, 2 * W
-        st = ws.next_stats()
-        ops.gn_stats(h, None, N, H * W, st)
+                x, H, W = (out, st), 2 * H, 2 * W
+        h = x[0]
+        st = self._stats_of(ws, 'out', h, x[1], N, H * W)
         a = ws.buf('out.a', (N * H * W, ch), adt)
-        ops.gn_apply(h, None, N, H, W, a, stats=st, gamma=P['out_gn_w'], beta=P['out_gn_b'], silu=True)
+        ops.gn_apply(h, None, N, H, W, a, stats1=st, gamma=P['out_gn_w'], beta=P['out_gn_b'], silu=True)
         if ws.out is None:
             ws.out = torch.empty(B, F, self.out_channels, H, W, device=ws.dev)
         ops.gemm(a, P['out_w'], self.out_channels, n_img=N, H=H, W=W, taps=9, bias=P['out_b'], out_f32=ws.out,
@@ -459,7 +496,7 @@ class UNetModel(nn.Module):
         key = (B, F, H, W, str(x.device), per_frame_t is not None)
         ws = self._workspaces.get(key)
         if ws is None:
-            ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device, self._n_gn)
+            ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device)
         ws.x.copy_(x)
         ws.x0.copy_(x0)
         ws.obs.copy_(obs.reshape(B, F))
