@@ -227,13 +227,17 @@ def main():
         step_resident()
         launches_per_step = _lib.launch_count() - n0
         # per-kernel-class CUDA-event profile (eager), 3 passes, first discarded
-        prof = {}
+        prof, prof_shapes = {}, {}
         for it in range(3):
             ops.PROFILE = []
             step_resident()
             torch.cuda.synchronize()
             if it:
-                for name, e0, e1, fl, nb in ops.PROFILE:
+                for name, e0, e1, fl, nb, meta in ops.PROFILE:
+                    if meta and it == 2:
+                        shapes = prof_shapes.setdefault((name, meta), dict(ms=0.0, flops=fl, n=0))
+                        shapes['ms'] += e0.elapsed_time(e1)
+                        shapes['n'] += 1
                     d = prof.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
                     d['ms'] += e0.elapsed_time(e1) / 2
                     d['flops'] += fl / 2
@@ -299,7 +303,11 @@ def main():
         if args.profile_json:
             with open(args.profile_json, 'w') as f:
                 json.dump({'per_kernel_class_per_step': prof, 'ms_per_step_graph': ms / args.steps,
-                           'ms_per_step_eager_sum': total_prof_ms}, f, indent=1)
+                           'ms_per_step_eager_sum': total_prof_ms,
+                           'gemm_shapes': [dict(kernel=k[0], shape=k[1], launches=v['n'], ms_total=v['ms'],
+                                                tflops=v['flops'] * v['n'] / v['ms'] / 1e9 if v['ms'] else 0)
+                                           for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]['ms'])]},
+                          f, indent=1)
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

@@ -122,15 +122,14 @@ __global__ void gn_apply_kernel(const ApplyParams p) {
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   };
-  for (int pix = p0 + prow; pix < p1; pix += rows) {
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * ld));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * ld + 4));
+  auto process = [&](int pix, const float4& v0, const float4& v1) {
     const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[i] = fmaf(x[i], a[i], b[i]);
-      if (p.silu) y[i] = silu_precise(y[i]);
+      // bf16 operands tolerate the fast exp / divide; the fp32 path keeps the precise SiLU
+      if (p.silu) y[i] = (sizeof(OutT) == 2) ? silu_f(y[i]) : silu_precise(y[i]);
     }
     const size_t row = (size_t)n * HW + pix;
     if (out_raw) store8(out_raw + row * C + c, x);
@@ -154,6 +153,26 @@ __global__ void gn_apply_kernel(const ApplyParams p) {
         store8(out + ((((size_t)n * 4 + plane) * Hh + (yy >> 1)) * Wh + (xx >> 1)) * C + c, y);
       }
     }
+  };
+  // four pixels per iteration: all eight 16-byte loads are in flight before any is consumed
+  constexpr int U = 4;
+  int pix = p0 + prow;
+  for (; pix + (U - 1) * rows < p1; pix += U * rows) {
+    float4 v0[U], v1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float* ptr = src + (size_t)(pix + u * rows) * ld;
+      v0[u] = __ldg(reinterpret_cast<const float4*>(ptr));
+      v1[u] = __ldg(reinterpret_cast<const float4*>(ptr + 4));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) process(pix + u * rows, v0[u], v1[u]);
+  }
+  for (; pix < p1; pix += rows) {
+    const float* ptr = src + (size_t)pix * ld;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(ptr));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(ptr + 4));
+    process(pix, v0, v1);
   }
 }
 
@@ -368,8 +387,8 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   const int C8 = C / 8;
   const int rows = C8 >= 256 ? 1 : 256 / C8;
   const int threads = C8 * rows;
-  int ppb = rows * 16;
-  while (ppb > rows && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
+  int ppb = rows * 32;
+  while (ppb > rows * 4 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
   p.pix_per_block = ppb;
   dim3 grid((HW + ppb - 1) / ppb, a->n_img);
   const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);

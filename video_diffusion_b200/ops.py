@@ -16,14 +16,14 @@ from ._lib import BF16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
 PROFILE = None
 
 
-def _timed(name, fn, flops=0.0, nbytes=0.0):
+def _timed(name, fn, flops=0.0, nbytes=0.0, meta=''):
     if PROFILE is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fn()
     e1.record()
-    PROFILE.append((name, e0, e1, flops, nbytes))
+    PROFILE.append((name, e0, e1, flops, nbytes, meta))
 
 
 def _nbytes(*tensors):
@@ -57,7 +57,8 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     M = n_img * H * W
     K = taps * g.C1 + g.C2
     name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if taps == 9 else '_linear')
-    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K)
+    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K,
+           meta=f'M={M} N={N} K={K} HxW={H}x{W} mode={a1_mode} res={int(residual is not None)} stats={int(stats_out is not None)}')
 
 
 def gn_stats(src, n_img, HW, stats):
