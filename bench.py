@@ -235,7 +235,7 @@ def main():
             if it:
                 for name, e0, e1, fl, nb, meta in ops.PROFILE:
                     if meta and it == 2:
-                        shapes = prof_shapes.setdefault((name, meta), dict(ms=0.0, flops=fl, n=0))
+                        shapes = prof_shapes.setdefault((name, meta), dict(ms=0.0, flops=fl, n=0, bytes=nb))
                         shapes['ms'] += e0.elapsed_time(e1)
                         shapes['n'] += 1
                     d = prof.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
@@ -305,7 +305,8 @@ def main():
                 json.dump({'per_kernel_class_per_step': prof, 'ms_per_step_graph': ms / args.steps,
                            'ms_per_step_eager_sum': total_prof_ms,
                            'gemm_shapes': [dict(kernel=k[0], shape=k[1], launches=v['n'], ms_total=v['ms'],
-                                                tflops=v['flops'] * v['n'] / v['ms'] / 1e9 if v['ms'] else 0)
+                                                tflops=v['flops'] * v['n'] / v['ms'] / 1e9 if v['ms'] else 0,
+                                                gbs=v['bytes'] * v['n'] / v['ms'] / 1e6 if v['ms'] else 0)
                                            for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]['ms'])]},
                           f, indent=1)
         print(json.dumps(result))

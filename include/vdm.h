@@ -89,7 +89,7 @@ int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
 int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t HW, double* stats, vdm_stream_t stream);
 
 typedef struct {
-  const float* src1; int32_t C1;      /* [n_img*HW][C1] */
+  const void* src1; int32_t C1;       /* [n_img*HW][C1], fp32 (or bf16 when src1_dtype == VDM_BF16 and C2 == 0) */
   const float* src2; int32_t C2;      /* optional second source, concatenated along C */
   int32_t n_img, H, W;
   const void* stats1;                 /* [n_img][2][C1] of src1; NULL: no normalisation (plain cast / concat) */
@@ -102,6 +102,7 @@ typedef struct {
   int32_t out_mode;                   /* 0 plain, 1 nearest-x2 upsampled, 2 stride-2 parity planes */
   int32_t out_dtype;                  /* VDM_F32 | VDM_BF16 */
   void* out;                          /* GEMM A operand */
+  int32_t src1_dtype;                 /* VDM_F32 | VDM_BF16 */
   void* out_raw;                      /* optional second output: the un-normalised input cast to out_dtype, plain
                                          layout (A operand of the 1x1 skip projection, unet.py:172-173) */
   float* out_f32_copy;                /* optional fp32 copy of the plain output (attention residual) */

@@ -43,7 +43,7 @@ inline int num_sms() {
   return n;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-ish SiLU used where the reference computes x*sigmoid(x) in fp32
 __device__ __forceinline__ float silu_precise(float x) { return x * (1.0f / (1.0f + expf(-x))); }
 

@@ -36,7 +36,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ src, int C, int HW, in
 
 // ------------------------------------------------------------------ GroupNorm apply
 struct ApplyParams {
-  const float* s1; int C1;
+  const void* s1; int C1;
   const float* s2; int C2;
   int n_img, H, W;
   const void* st1; const void* st2; int st_kind;   // VDM_F64: double sums, VDM_I64: fixed-point 2^-24
@@ -50,8 +50,18 @@ struct ApplyParams {
 // grid (pixel chunks, n_img); block = (C/8) x rows threads: a thread owns 8 channels for a strided set
 // of pixels, so its per-channel multiplier / offset live in registers for the whole loop.
 // dynamic smem: 2*C doubles (per-channel sums) + 64 floats (group mean / rstd)
-template <typename OutT>
-__global__ void gn_apply_kernel(const ApplyParams p) {
+// MODE: 0 plain, 1 nearest-x2, 2 stride-2 parity planes; RAW / COPY: optional extra outputs.
+__device__ __forceinline__ float silu_tanh(float x) {
+  // x*sigmoid(x) with sigmoid(x) = 0.5 + 0.5*tanh(x/2): ONE MUFU op per element (tanh.approx, rel. error
+  // ~2^-11, well below the bf16 rounding of the result) instead of ex2 + rcp -- this kernel would
+  // otherwise be bound by the 16/clk/SM special-function units rather than by HBM.
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
+template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int C = p.C1 + p.C2, cpg = C / 32, HW = p.H * p.W, C8 = C / 8;
   double* chs = reinterpret_cast<double*>(sm_raw);
@@ -105,12 +115,31 @@ __global__ void gn_apply_kernel(const ApplyParams p) {
       b[i] = b[i] * sc + p.ss[(size_t)n * p.ld_ss + C + c + i];
     }
   }
-  const float* src = (c < p.C1) ? p.s1 + (size_t)n * HW * p.C1 + c : p.s2 + (size_t)n * HW * p.C2 + (c - p.C1);
+  const bool silu = p.silu != 0;
+  // bf16 input (a conv output kept only in bf16) is single-source; fp32 input may be a two-source concat
   const int ld = (c < p.C1) ? p.C1 : p.C2;
-  OutT* out = reinterpret_cast<OutT*>(p.out);
-  OutT* out_raw = reinterpret_cast<OutT*>(p.out_raw);
+  const InT* src = (c < p.C1) ? reinterpret_cast<const InT*>(p.s1) + (size_t)n * HW * p.C1 + c
+                              : reinterpret_cast<const InT*>(p.s2) + (size_t)n * HW * p.C2 + (c - p.C1);
+  OutT* const out = reinterpret_cast<OutT*>(p.out) + c;
+  OutT* const out_raw = RAW ? reinterpret_cast<OutT*>(p.out_raw) + (size_t)n * HW * C + c : nullptr;
+  float* const copy = COPY ? p.copy + (size_t)n * HW * C + c : nullptr;
   const int p0 = blockIdx.x * p.pix_per_block;
   const int p1 = min(HW, p0 + p.pix_per_block);
+  auto load8 = [&](const InT* ptr, float (&x)[8]) {
+    if constexpr (sizeof(InT) == 2) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(ptr));
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {       // bf16 -> fp32 is a 16-bit shift
+        x[2 * i] = __uint_as_float(w[i] << 16);
+        x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    } else {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(ptr));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(ptr + 4));
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+    }
+  };
   auto store8 = [&](OutT* o, const float (&v)[8]) {
     if constexpr (sizeof(OutT) == 2) {
       uint4 pk;
@@ -122,57 +151,49 @@ __global__ void gn_apply_kernel(const ApplyParams p) {
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   };
-  auto process = [&](int pix, const float4& v0, const float4& v1) {
-    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  auto process = [&](int pix, const float (&x)[8]) {
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[i] = fmaf(x[i], a[i], b[i]);
-      // bf16 operands tolerate the fast exp / divide; the fp32 path keeps the precise SiLU
-      if (p.silu) y[i] = (sizeof(OutT) == 2) ? silu_f(y[i]) : silu_precise(y[i]);
+      if (silu) y[i] = (sizeof(OutT) == 2) ? silu_tanh(y[i]) : silu_precise(y[i]);
     }
-    const size_t row = (size_t)n * HW + pix;
-    if (out_raw) store8(out_raw + row * C + c, x);
-    if (p.copy) {
-      float* cp = p.copy + row * C + c;
+    if constexpr (RAW) store8(out_raw + (size_t)pix * C, x);
+    if constexpr (COPY) {
+      float* cp = copy + (size_t)pix * C;
       *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
       *reinterpret_cast<float4*>(cp + 4) = make_float4(y[4], y[5], y[6], y[7]);
     }
-    if (p.out_mode == 0) {
-      store8(out + row * C + c, y);
+    if constexpr (MODE == 0) {
+      store8(out + ((size_t)n * HW + pix) * C, y);
     } else {
       const int yy = pix / p.W, xx = pix - yy * p.W;
-      if (p.out_mode == 1) {  // nearest x2
+      if constexpr (MODE == 1) {  // nearest x2
         const int W2 = 2 * p.W;
         const size_t r0 = ((size_t)n * 2 * p.H + 2 * yy) * W2 + 2 * xx;
-        store8(out + r0 * C + c, y); store8(out + (r0 + 1) * C + c, y);
-        store8(out + (r0 + W2) * C + c, y); store8(out + (r0 + W2 + 1) * C + c, y);
-      } else {                // parity planes of a stride-2 conv input
+        store8(out + r0 * C, y); store8(out + (r0 + 1) * C, y);
+        store8(out + (r0 + W2) * C, y); store8(out + (r0 + W2 + 1) * C, y);
+      } else {                    // parity planes of a stride-2 conv input
         const int Hh = p.H / 2, Wh = p.W / 2;
         const int plane = (yy & 1) * 2 + (xx & 1);
-        store8(out + ((((size_t)n * 4 + plane) * Hh + (yy >> 1)) * Wh + (xx >> 1)) * C + c, y);
+        store8(out + ((((size_t)n * 4 + plane) * Hh + (yy >> 1)) * Wh + (xx >> 1)) * C, y);
       }
     }
   };
-  // four pixels per iteration: all eight 16-byte loads are in flight before any is consumed
+  // four pixels per iteration: all loads are in flight before any is consumed
   constexpr int U = 4;
   int pix = p0 + prow;
   for (; pix + (U - 1) * rows < p1; pix += U * rows) {
-    float4 v0[U], v1[U];
+    float x[U][8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float* ptr = src + (size_t)(pix + u * rows) * ld;
-      v0[u] = __ldg(reinterpret_cast<const float4*>(ptr));
-      v1[u] = __ldg(reinterpret_cast<const float4*>(ptr + 4));
-    }
+    for (int u = 0; u < U; ++u) load8(src + (size_t)(pix + u * rows) * ld, x[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) process(pix + u * rows, v0[u], v1[u]);
+    for (int u = 0; u < U; ++u) process(pix + u * rows, x[u]);
   }
   for (; pix < p1; pix += rows) {
-    const float* ptr = src + (size_t)pix * ld;
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(ptr));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(ptr + 4));
-    process(pix, v0, v1);
+    float x[8];
+    load8(src + (size_t)pix * ld, x);
+    process(pix, x);
   }
 }
 
@@ -392,10 +413,26 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   p.pix_per_block = ppb;
   dim3 grid((HW + ppb - 1) / ppb, a->n_img);
   const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);
-  if (a->out_dtype == VDM_BF16)
-    gn_apply_kernel<__nv_bfloat16><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
-  else
-    gn_apply_kernel<float><<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+  VDM_REQUIRE(a->src1_dtype != VDM_BF16 || (a->C2 == 0 && a->out_dtype == VDM_BF16),
+              "gn_apply: bf16 input needs a single source and bf16 output");
+  const bool raw = a->out_raw != nullptr, copy = a->out_f32_copy != nullptr;
+  VDM_REQUIRE(a->out_mode == 0 || (!raw && !copy), "gn_apply: extra outputs only with the plain layout");
+  VDM_REQUIRE(!(raw && copy), "gn_apply: out_raw and out_f32_copy are mutually exclusive");
+#define VDM_GN_LAUNCH(OUT, IN, MODE, RAW, COPY) \
+  gn_apply_kernel<OUT, IN, MODE, RAW, COPY><<<grid, threads, smem, (cudaStream_t)stream>>>(p)
+#define VDM_GN_BY_MODE(OUT, IN)                                              \
+  do {                                                                       \
+    if (a->out_mode == 1) VDM_GN_LAUNCH(OUT, IN, 1, false, false);           \
+    else if (a->out_mode == 2) VDM_GN_LAUNCH(OUT, IN, 2, false, false);      \
+    else if (raw) VDM_GN_LAUNCH(OUT, IN, 0, true, false);                    \
+    else if (copy) VDM_GN_LAUNCH(OUT, IN, 0, false, true);                   \
+    else VDM_GN_LAUNCH(OUT, IN, 0, false, false);                            \
+  } while (0)
+  if (a->src1_dtype == VDM_BF16) VDM_GN_BY_MODE(__nv_bfloat16, __nv_bfloat16);
+  else if (a->out_dtype == VDM_BF16) VDM_GN_BY_MODE(__nv_bfloat16, float);
+  else VDM_GN_BY_MODE(float, float);
+#undef VDM_GN_BY_MODE
+#undef VDM_GN_LAUNCH
   VDM_AFTER_LAUNCH("gn_apply");
   return 0;
 }

@@ -82,8 +82,11 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
     a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)
     a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
     a.out, a.out_raw, a.out_f32_copy = ptr(out), ptr(out_raw), ptr(copy)
+    a.src1_dtype = dt(src1.dtype)
     _timed('gn_apply', lambda: check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply'),
-           nbytes=_nbytes(src1, src2, out, copy, out_raw))
+           nbytes=_nbytes(src1, src2, out, copy, out_raw),
+           meta=f'n={n_img} HxW={H}x{W} C={a.C1}+{a.C2} in={src1.dtype} norm={int(stats1 is not None)} '
+                f'silu={int(silu)} mode={out_mode} raw={int(out_raw is not None)} copy={int(copy is not None)}')
 
 
 def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):

@@ -49,6 +49,7 @@ class UNetModel(nn.Module):
         self.num_classes, self.use_checkpoint, self.conv_resample = None, use_checkpoint, conv_resample
         self.compute_dtype = compute_dtype or torch.bfloat16
         self.use_cuda_graph = True
+        self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
             raise NotImplementedError('model_channels must be a multiple of 64')
@@ -318,13 +319,21 @@ class UNetModel(nn.Module):
         # one pass over the block input: normalised+SiLU operand of conv1 and the raw cast for the 1x1 skip
         ops.gn_apply(src1, src2, n_img, H, W, a1, stats1=st1, stats2=st2, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'],
                      silu=True, out_raw=araw)
-        h1 = ws.buf(p + '.h1', (M, Cout))
         off = node['emb_off']
         ss = self.use_scale_shift_norm
         st_h1 = self._fused_stats(ws, p + '.h1', n_img, HW, Cout)
-        ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'],
-                 rowbias=None if ss else emb_out[:, off:off + Cout], out_f32=h1, stats_out=st_h1)
-        st_h1 = self._stats_of(ws, p + '.h1', h1, st_h1, n_img, HW)
+        rb = None if ss else emb_out[:, off:off + Cout]
+        if st_h1 is not None and self.bf16_intermediate:
+            # conv1's output is only ever consumed by GroupNorm -> SiLU -> bf16: keep it in bf16 (its
+            # statistics come from the fp32 accumulators in the epilogue), halving its HBM traffic
+            h1 = ws.buf(p + '.h1b', (M, Cout), torch.bfloat16)
+            ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb,
+                     out_bf16=h1, stats_out=st_h1)
+        else:
+            h1 = ws.buf(p + '.h1', (M, Cout))
+            ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb,
+                     out_f32=h1, stats_out=st_h1)
+            st_h1 = self._stats_of(ws, p + '.h1', h1, st_h1, n_img, HW)
         a2 = ws.buf(p + '.a2', (M, Cout), adt)
         ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
                      scale_shift=emb_out[:, off:off + 2 * Cout] if ss else None, silu=True)
