@@ -48,11 +48,13 @@ int64_t vdm_launch_count(void);
  */
 typedef struct {
   int32_t dtype;        /* VDM_F32 | VDM_BF16: type of a1, a2, w */
-  int32_t taps;         /* 1 (linear / 1x1) or 9 (3x3, pad 1) */
+  int32_t taps;         /* 1 (linear / 1x1), 9 (3x3, pad 1) or 4 (a1_mode 3) */
   int32_t a1_mode;      /* 0: A1 is [n][H][W][C1] at output resolution (stride 1)
                            1: stride-2 conv.  bf16: A1 is parity planes [n][py][px][H][W][C1] of the
                               2H x 2W input; fp32: A1 is the raw [n][2H][2W][C1] input
-                           2: nearest-x2 upsample folded in (fp32 only): A1 is [n][H/2][W/2][C1] */
+                           2: nearest-x2 upsample folded in (fp32 only): A1 is [n][H/2][W/2][C1]
+                           3: nearest-x2 upsample folded into four 2x2 parity convolutions (bf16 only):
+                              A1 is [n][H/2][W/2][C1], taps = 4, w is [4][N][4*C1] (see fold in unet.py) */
   int32_t n_img, H, W;  /* output geometry; M = n_img*H*W.  For linear: n_img=M, H=W=1 */
   int32_t C1, C2;       /* channels of A1 / A2 (C2 = 0: no second range) */
   int32_t N;            /* output channels */

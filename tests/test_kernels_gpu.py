@@ -107,6 +107,40 @@ def test_conv3x3(case, dtype):
     assert relerr(out_b, ref) < 6e-3
 
 
+@pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128)])
+def test_upsample_conv_folded_into_parity_convs(case):
+    """nearest-x2 + conv3x3 as four 2x2 convs on the low-res input (a1_mode 3) vs F.interpolate + F.conv2d."""
+    from video_diffusion_b200.unet import fold_upsample_weights
+    o = ops()
+    n, H, W, C1, N = case                      # H, W: OUTPUT resolution
+    x = rnd(n, C1, H // 2, W // 2, seed=1).bfloat16().float()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5)
+    bias = rnd(N, seed=3)
+    wf = fold_upsample_weights(w).cuda().bfloat16()
+    # reference with the SAME (folded, bf16-rounded) weights: exact algebra, only summation order differs
+    ref = torch.empty(n, N, H, W, device='cuda')
+    xp = F.pad(x, (1, 1, 1, 1))
+    wf4 = wf.float().view(4, N, 2, 2, C1).permute(0, 1, 4, 2, 3)
+    for a in range(2):
+        for b in range(2):
+            win = xp[:, :, a:a + H // 2 + 1, b:b + W // 2 + 1]
+            ref[:, :, a::2, b::2] = F.conv2d(win, wf4[2 * a + b], bias)
+    # and the folding itself against the un-folded definition in fp32
+    full = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, bias, padding=1)
+    wf32 = fold_upsample_weights(w).cuda().view(4, N, 2, 2, C1).permute(0, 1, 4, 2, 3)
+    chk = torch.empty_like(full)
+    for a in range(2):
+        for b in range(2):
+            chk[:, :, a::2, b::2] = F.conv2d(xp[:, :, a:a + H // 2 + 1, b:b + W // 2 + 1], wf32[2 * a + b], bias)
+    assert relerr(chk, full) < 1e-5
+    out = torch.empty(n * H * W, N, device='cuda')
+    st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64) if (H // 2) * (W // 2) % 32 == 0 else None
+    o.gemm(nhwc(x).bfloat16(), wf, N, n_img=n, H=H, W=W, taps=4, a1_mode=3, bias=bias, out_f32=out, stats_out=st, C1=C1)
+    assert relerr(out, nhwc(ref)) < 2e-5
+    if st is not None:
+        assert relerr(st.double()[:, 0] / 2 ** 24, _chan_stats(from_nhwc(out, n, H, W))[:, 0]) < 2e-6
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['simt_f32', 'tcgen05_bf16'])
 def test_linear_rowbias_nchw_and_silu(dtype):
     o = ops()

@@ -31,7 +31,8 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 struct TcParams {
   int M, N;
   int taps, c1_chunks, c2_chunks;
-  int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes
+  int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes, 3 nearest-x2 upsample folded into 2x2 taps
+  int tiles_per_par;  // a1_mode 3: tiles per output parity (tile index = parity * tiles_per_par + ...)
   int is_linear;  // A1 addressed as 2-D [M][C1]
   int H, W, HW;
   const float* bias;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.c1_chunks + p.c2_chunks;
   const int n_tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
+  const int n_tiles = (p.a1_mode == 3 ? 4 : 1) * n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -237,8 +238,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles_n) * BLOCK_N;
-        const int m0 = (tile / n_tiles_n) * TILE_M;
+        int par = 0, tl = tile;
+        if (p.a1_mode == 3) {
+          par = tile / p.tiles_per_par;
+          tl = tile - par * p.tiles_per_par;
+        }
+        const int n0 = (tl % n_tiles_n) * BLOCK_N;
+        const int m0 = (tl / n_tiles_n) * TILE_M;
         int img0[M_SUB], y0[M_SUB], x0[M_SUB];
 #pragma unroll
         for (int sub = 0; sub < M_SUB; ++sub) {
@@ -261,7 +267,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (first_range) {
             const int tap = kb / p.c1_chunks;
             c0 = (kb - tap * p.c1_chunks) * BLOCK_K;
-            if (p.taps == 9) {
+            if (p.a1_mode == 3) {   // output parity (a, b): rows {y-1, y} / {y, y+1}, same for columns
+              const int i = tap >> 1, j = tap & 1;
+              dy = (par >> 1) ? i : i - 1;
+              dx = (par & 1) ? j : j - 1;
+            } else if (p.taps == 9) {
               const int r = tap / 3, s = tap - r * 3;
               if (p.a1_mode == 0) {
                 dy = r - 1;
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
             else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
           }
-          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0);
+          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + par * p.N);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -348,8 +358,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int n0 = (tile % n_tiles_n) * BLOCK_N;
-      const int mt0 = (tile / n_tiles_n) * TILE_M;
+      int par = 0, tl = tile;
+      if (p.a1_mode == 3) {
+        par = tile / p.tiles_per_par;
+        tl = tile - par * p.tiles_per_par;
+      }
+      const int n0 = (tl % n_tiles_n) * BLOCK_N;
+      const int mt0 = (tl / n_tiles_n) * TILE_M;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       float4 res_cur[NRES];
@@ -429,12 +444,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
               ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
               ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)orow * p.ld_out + n) = v;
+              size_t drow = (size_t)orow;
+              if (p.a1_mode == 3) {   // low-res pixel (img, y, x) of parity (a, b) -> high-res row
+                const int img = orow / p.HW, rem = orow - img * p.HW;
+                const int yy = rem / p.W, xx = rem - yy * p.W;
+                drow = ((size_t)img * 2 * p.H + 2 * yy + (par >> 1)) * (2 * p.W) + 2 * xx + (par & 1);
+              }
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
               if (p.out_bf16) {
                 uint2 pk;
                 pk.x = pack_bf16x2(v.x, v.y);
                 pk.y = pack_bf16x2(v.z, v.w);
-                *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orow * p.ld_out_bf16 + n) = pk;
+                *reinterpret_cast<uint2*>(p.out_bf16 + drow * p.ld_out_bf16 + n) = pk;
               }
             }
           }
@@ -599,6 +620,26 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
   return 0;
 }
 
+template <int M_SUB, int STAGES>
+int launch_upfold(const CUtensorMap& ma1, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+  using L = SmemLayout<128, M_SUB, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, M_SUB, STAGES, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = 4 * p.tiles_per_par;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<128, M_SUB, STAGES, false><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma1, mw, p);
+  VDM_AFTER_LAUNCH("gemm_tc");
+  return 0;
+}
+
 template <int BLOCK_N, int M_SUB, int STAGES>
 int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
            cudaStream_t stream) {
@@ -608,8 +649,11 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
 
 }  // namespace
 
+int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream);
+
 int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   const int64_t M = (int64_t)a->n_img * a->H * a->W;
+  if (a->a1_mode == 3) return gemm_tc_upfold(a, stream);
   VDM_REQUIRE(a->taps == 1 || a->taps == 9, "gemm_tc: taps must be 1 or 9");
   VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
   VDM_REQUIRE(a->C2 % BLOCK_K == 0, "gemm_tc: C2=%d must be a multiple of 64", a->C2);
@@ -697,6 +741,60 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     case 64: return launch<64, 1, 6>(ma1, ma2, mw, p, stream);
     default: return launch<16, 1, 8>(ma1, ma2, mw, p, stream);
   }
+}
+
+// nearest-x2 upsample + 3x3 conv (unet.py:63-72) as four 2x2 convolutions, one per output parity, on
+// the LOW-resolution input: every output pixel (2y+a, 2x+b) only ever sees two distinct input rows and
+// columns, so the 3x3 weights fold into 2x2 ones (summed on the host at pack time).  4/9 of the FLOPs,
+// and the 4x larger upsampled tensor is never materialised.  w: [4 parities][N][4*C1].
+int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
+  VDM_REQUIRE(a->taps == 4, "gemm_tc: a1_mode 3 takes the 4-tap folded weights");
+  VDM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "gemm_tc: upsample output must be even");
+  VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0 && a->C2 == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
+  VDM_REQUIRE(a->N % 128 == 0, "gemm_tc: folded upsample needs N %% 128 == 0");
+  VDM_REQUIRE(!a->out_nchw && !a->residual && !a->rowbias && !a->out_silu_f32, "gemm_tc: unsupported epilogue for a1_mode 3");
+  const int Hl = a->H / 2, Wl = a->W / 2, HWl = Hl * Wl;
+  VDM_REQUIRE(a->stats_out == nullptr || HWl % 32 == 0, "gemm_tc: stats_out needs (H/2)*(W/2) %% 32 == 0");
+  const int64_t M = (int64_t)a->n_img * HWl;
+  TcParams p{};
+  p.M = (int)M; p.N = a->N; p.taps = 4; p.c1_chunks = a->C1 / BLOCK_K; p.c2_chunks = 0;
+  p.a1_mode = 3; p.is_linear = 0; p.H = Hl; p.W = Wl; p.HW = HWl;
+  p.bias = a->bias; p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.stats_out = a->stats_out;
+  VDM_REQUIRE((Wl <= 128 && 128 % Wl == 0) || Wl % 128 == 0, "gemm_tc: unsupported width %d", Wl);
+  uint32_t bw = Wl < 128 ? Wl : 128, bh = 1, bn = 1;
+  if (Wl < 128) {
+    if (HWl >= 128) {
+      VDM_REQUIRE(HWl % 128 == 0, "gemm_tc: H*W=%d must be a multiple of 128", HWl);
+      bh = 128 / Wl;
+    } else {
+      VDM_REQUIRE(128 % HWl == 0, "gemm_tc: H*W=%d must divide 128", HWl);
+      bh = Hl;
+      bn = 128 / HWl;
+    }
+  }
+  CUtensorMap ma1, mw;
+  const uint64_t C = a->C1;
+  uint64_t dims[5] = {C, (uint64_t)Wl, (uint64_t)Hl, 1, (uint64_t)a->n_img};
+  uint64_t st[5] = {2, C * 2, C * 2 * Wl, C * 2 * Wl * Hl, C * 2 * Wl * Hl};
+  uint32_t box[5] = {BLOCK_K, bw, bh, 1, bn};
+  int rc = encode_map(&ma1, a->a1, 5, dims, st, box);
+  if (rc) return rc;
+  const int64_t K = 4 * (int64_t)a->C1;
+  uint64_t wd[2] = {(uint64_t)K, (uint64_t)a->N * 4};
+  uint64_t ws[2] = {2, (uint64_t)K * 2};
+  uint32_t wb[2] = {BLOCK_K, 128};
+  rc = encode_map(&mw, a->w, 2, wd, ws, wb);
+  if (rc) return rc;
+  const int64_t t2 = ((M + 255) / 256) * (a->N / 128), t1 = ((M + 127) / 128) * (a->N / 128);
+  const int sms = num_sms();
+  const bool two = (double)((4 * t2 + sms - 1) / sms) * 2.0 <= (double)((4 * t1 + sms - 1) / sms) * 1.35;
+  if (two) {
+    p.tiles_per_par = (int)t2;
+    return launch_upfold<2, 4>(ma1, mw, p, stream);
+  }
+  p.tiles_per_par = (int)t1;
+  return launch_upfold<1, 5>(ma1, mw, p, stream);
 }
 
 }  // namespace vdm

@@ -26,6 +26,25 @@ def _uniform(shape, bound):
     return torch.empty(shape).uniform_(-bound, bound)
 
 
+def fold_upsample_weights(w):
+    """(O, I, 3, 3) conv weights -> [4 parities][O][4*I] weights of the equivalent 2x2 convolutions on the
+    low-resolution input of `F.interpolate(x, 2, 'nearest')` followed by the 3x3 conv (unet.py:63-72).
+    Output pixel (2y+a, 2x+b) reads upsampled rows 2y+a-1..2y+a+1, i.e. low-res rows {y-1, y, y} (a=0) or
+    {y, y, y+1} (a=1): the three row taps collapse to two with weights (w0, w1+w2) or (w0+w1, w2); columns
+    alike.  Parity index = 2a+b, tap index = 2i+j, K index = tap*I + c."""
+    w = w.float()
+    rows = [torch.stack([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], dim=2),      # a = 0 : (O, I, 2, 3)
+            torch.stack([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], dim=2)]      # a = 1
+    out = []
+    for a in range(2):
+        r = rows[a]
+        cols = [torch.stack([r[..., 0], r[..., 1] + r[..., 2]], dim=3),     # b = 0 : (O, I, 2, 2)
+                torch.stack([r[..., 0] + r[..., 1], r[..., 2]], dim=3)]     # b = 1
+        for b in range(2):
+            out.append(cols[b].permute(0, 2, 3, 1).reshape(w.shape[0], -1))  # (O, [i][j][c])
+    return torch.stack(out, dim=0).reshape(4 * w.shape[0], -1).contiguous()
+
+
 class UNetModel(nn.Module):
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -245,6 +264,8 @@ class UNetModel(nn.Module):
                 rpe_off += 3 * node['C']
             elif node['kind'] in ('down', 'up'):
                 put(p + '.w', conv_w(p + '.weight'), adt); put(p + '.b', sd[p + '.bias'])
+                if node['kind'] == 'up' and adt == torch.bfloat16:
+                    put(p + '.wfold', fold_upsample_weights(sd[p + '.weight']), adt)
         put('emb_w', torch.cat(emb_w)); put('emb_b', torch.cat(emb_b))
         put('rpe_t_w', torch.cat(rpe_w)); put('rpe_t_b', torch.cat(rpe_b))
         put('out_gn_w', sd['out.0.weight']); put('out_gn_b', sd['out.0.bias'])
@@ -472,8 +493,15 @@ class UNetModel(nn.Module):
             elif kind == 'up':
                 C = node['C']
                 out = ws.buf(p + '.out', (N * 4 * H * W, C))
-                st = self._fused_stats(ws, p + '.out', N, 4 * H * W, C)
-                if adt == torch.bfloat16:
+                fold = adt == torch.bfloat16 and C % 128 == 0
+                st = self._fused_stats(ws, p + '.out', N, H * W if fold else 4 * H * W, C)
+                if fold:
+                    # nearest-x2 + 3x3 conv == four 2x2 parity convs on the low-res input (4/9 of the FLOPs)
+                    lo = ws.buf(p + '.lo', (N * H * W, C), adt)
+                    ops.gn_apply(x[0], None, N, H, W, lo)
+                    ops.gemm(lo, P[p + '.wfold'], C, n_img=N, H=2 * H, W=2 * W, taps=4, a1_mode=3, bias=P[p + '.b'],
+                             out_f32=out, stats_out=st, C1=C)
+                elif adt == torch.bfloat16:
                     up = ws.buf(p + '.up', (N * 4 * H * W, C), adt)
                     ops.gn_apply(x[0], None, N, H, W, up, out_mode=1)
                     ops.gemm(up, P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, bias=P[p + '.b'], out_f32=out,
