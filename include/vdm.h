@@ -96,7 +96,8 @@ typedef struct {
   int32_t n_img, H, W;
   const void* stats1;                 /* [n_img][2][C1] of src1; NULL: no normalisation (plain cast / concat) */
   const void* stats2;                 /* [n_img][2][C2] of src2 */
-  int32_t stats_dtype;                /* VDM_I64 (GEMM epilogue, fixed point) | VDM_F64 (vdm_gn_stats) */
+  int32_t stats_dtype;                /* of stats1: VDM_I64 (GEMM epilogue, fixed point) | VDM_F64 (vdm_gn_stats) */
+  int32_t stats2_dtype;               /* of stats2 */
   const float* gamma; const float* beta;   /* [C1+C2] */
   const float* scale_shift;           /* optional [n_img][ld_ss]: scale = [0,C), shift = [C,2C) */
   int32_t ld_ss;

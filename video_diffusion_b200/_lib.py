@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
 
 class GnApplyArgs(C.Structure):
     _fields_ = [('src1', _vp), ('C1', _i32), ('src2', _vp), ('C2', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
-                ('stats1', _vp), ('stats2', _vp), ('stats_dtype', _i32), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
+                ('stats1', _vp), ('stats2', _vp), ('stats_dtype', _i32), ('stats2_dtype', _i32), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
                 ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('src1_dtype', _i32), ('out_raw', _vp), ('out_f32_copy', _vp)]
 
 

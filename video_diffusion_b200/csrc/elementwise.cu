@@ -39,7 +39,7 @@ struct ApplyParams {
   const void* s1; int C1;
   const float* s2; int C2;
   int n_img, H, W;
-  const void* st1; const void* st2; int st_kind;   // VDM_F64: double sums, VDM_I64: fixed-point 2^-24
+  const void* st1; const void* st2; int st_kind, st_kind2;   // VDM_F64: double sums, VDM_I64: fixed-point 2^-24
   const float* gamma; const float* beta;
   const float* ss; int ld_ss;
   int silu, out_mode;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
       const void* st = first ? p.st1 : p.st2;
       const int Cs = first ? p.C1 : p.C2, cs = first ? ch : ch - p.C1;
       const size_t i0 = (size_t)n * 2 * Cs + cs;
-      if (p.st_kind == VDM_F64) {
+      if ((first ? p.st_kind : p.st_kind2) == VDM_F64) {
         chs[ch] = reinterpret_cast<const double*>(st)[i0];
         chss[ch] = reinterpret_cast<const double*>(st)[i0 + Cs];
       } else {
@@ -402,7 +402,7 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_mode != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "gn_apply: parity split needs even H, W");
   VDM_REQUIRE(a->out_mode == 0 || a->out_f32_copy == nullptr, "gn_apply: fp32 copy only with plain output");
   ApplyParams p{a->src1, a->C1, a->src2, a->C2, a->n_img, a->H, a->W, a->stats1, a->stats2,
-                a->stats_dtype, a->gamma, a->beta, a->scale_shift, a->ld_ss, a->silu, a->out_mode,
+                a->stats_dtype, a->stats2_dtype, a->gamma, a->beta, a->scale_shift, a->ld_ss, a->silu, a->out_mode,
                 a->out, a->out_raw, a->out_f32_copy, 0};
   const int HW = a->H * a->W;
   const int C8 = C / 8;

@@ -77,6 +77,7 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
     a.n_img, a.H, a.W = n_img, H, W
     a.stats1, a.stats2 = ptr(stats1), ptr(stats2)
     a.stats_dtype = _lib.F64 if (stats1 is not None and stats1.dtype == torch.float64) else _lib.I64
+    a.stats2_dtype = _lib.F64 if (stats2 is not None and stats2.dtype == torch.float64) else _lib.I64
     a.gamma, a.beta = ptr(gamma), ptr(beta)
     a.scale_shift = None if scale_shift is None else scale_shift.data_ptr()
     a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)

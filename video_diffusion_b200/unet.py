@@ -333,8 +333,6 @@ class UNetModel(nn.Module):
         src1, src2 = x1[0], (x2[0] if x2 is not None else None)
         st1 = self._stats_of(ws, p + '.in1', src1, x1[1], n_img, HW)
         st2 = self._stats_of(ws, p + '.in2', src2, x2[1], n_img, HW) if x2 is not None else None
-        if st2 is not None and st1.dtype != st2.dtype:
-            raise RuntimeError('internal: mixed statistics precision in a concat GroupNorm')
         a1 = ws.buf(p + '.a1', (M, Cin), adt)
         araw = ws.buf(p + '.araw', (M, Cin), adt) if node['skip'] else None
         # one pass over the block input: normalised+SiLU operand of conv1 and the raw cast for the 1x1 skip
