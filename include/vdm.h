@@ -71,6 +71,11 @@ typedef struct {
   int32_t ld_out, ld_out_bf16;
   int32_t out_nchw;
   float* out_silu_f32;  /* optional second output silu(out) [M][ld_out] (fp32 kernel only) */
+  int32_t lda1;         /* taps == 1 only: row stride of A1 in elements (0 = C1), so a column block of a wider
+                           matrix (e.g. the q or k third of qkv) can be the operand */
+  int32_t w_group_tiles; /* bf16 kernel, taps == 1: 0 = one weight matrix; g > 0 = grouped weights, w is
+                           [groups][N][K] and the 128-row tile m uses group m / g (RPE tables differ per
+                           (batch, frame) block of rows) */
   int64_t* stats_out;   /* optional (bf16 kernel only, H*W % 32 == 0): per-image, per-output-channel sums of the
                            stored values, [n_img][2][N] (plane 0: sum, plane 1: sum of squares) as 64-bit
                            fixed point (units of 2^-24), accumulated with integer atomics -- deterministic --
@@ -154,6 +159,25 @@ int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, cons
                       const float* mask, int32_t allow_pad_interactions, int32_t B, int32_t T,
                       int32_t HW, int32_t heads, int32_t hd, void* out_a, int32_t out_dtype,
                       vdm_stream_t stream);
+
+/* ---- temporal attention, tensor-core path (bf16 mode) ------------------------------------------
+ * The RPE einsums contract against tables that depend on (batch, frame) but not on the pixel, so over
+ * the pixels of one (b, t) they are GEMMs: vdm_rpe_expand builds block-diagonal-over-heads bf16 weight
+ * blocks from R_q / R_k / R_v ([B*T*T][C] fp32), one per group g = b*T + t, `groups_per_tile` groups
+ * per 128-row tile (1 if HW >= 128, 128/HW otherwise):
+ *   bk, bq: [ceil(G/gpt)][128*gpt][C]   row sub*128 + h*T + j, column h*hd + f   (bq pre-scaled by hd^-0.5)
+ *   bv    : [ceil(G/gpt)][C][128*gpt]
+ * The host then runs vdm_gemm with w_group_tiles on q -> Sk and k -> Sq ([M][128*gpt] fp32), calls
+ * vdm_attn_temporal_tc (scale*q.k^T + scale*Sk + Sq^T, mask, fp32 softmax, P.V on mma.sync; writes
+ * P as bf16 [M][128*gpt] into a buffer whose padding columns the caller zeroed once, and PV fp32
+ * [M][C]) and a last grouped vdm_gemm (P x bv, residual PV) for the attn.R_v term (unet.py:357-378). */
+int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, int32_t B, int32_t T,
+                   int32_t heads, int32_t hd, int32_t groups_per_tile, void* bq, void* bk, void* bv,
+                   vdm_stream_t stream);
+int vdm_attn_temporal_tc(const void* qkv, const float* sk, const float* sq, const float* mask,
+                         int32_t allow_pad_interactions, int32_t B, int32_t T, int32_t HW,
+                         int32_t heads, int32_t hd, int32_t groups_per_tile, void* pm, float* pv,
+                         vdm_stream_t stream);
 
 /* ---- spatial attention (unet.py:258-266 -> 477-536 without RPE / mask) --------------------
  * qkv: [n_img*L][3C] (dtype qkv_dtype); softmax(q k^T / sqrt(hd)) v per (image, head).

@@ -340,6 +340,48 @@ def test_attention_temporal(T, hd, pad):
     assert relerr(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('T,hd,HW,pad', [(20, 96, 256, True), (10, 32, 64, False), (7, 128, 128, True),
+                                          (20, 128, 64, True)])
+def test_attention_temporal_tensor_core_path(T, hd, HW, pad):
+    """RPE terms as grouped tcgen05 GEMMs + mma.sync attention core, against the fp32 einsum restatement."""
+    o = ops()
+    B, heads = 3, 4
+    Cc = heads * hd
+    M = B * T * HW
+    qkv = rnd(B, T, HW, 3 * Cc, seed=1).bfloat16()
+    R = [rnd(B * T * T, Cc, seed=2 + i, scale=0.5) for i in range(3)]
+    mask = torch.ones(B, T).cuda()
+    mask[0, T - 2:] = 0
+    # reference on the same bf16-rounded q, k, v and bf16-rounded R tables
+    Rb = [r.bfloat16().float() for r in R]
+    Rb[0] = (R[0] * hd ** -0.5).bfloat16().float() * hd ** 0.5           # bq is rounded after the scale
+    ref = _attn_ref(qkv.float().permute(0, 2, 1, 3), heads, mask, Rb, pad).permute(0, 2, 1, 3).reshape(M, Cc)
+    gpt, tpg = (1, HW // 128) if HW >= 128 else (128 // HW, 1)
+    SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
+    bq = torch.empty(ntg * SW, Cc, device='cuda', dtype=torch.bfloat16)
+    bk = torch.empty_like(bq)
+    bv = torch.empty(ntg * Cc, SW, device='cuda', dtype=torch.bfloat16)
+    o.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv)
+    q2 = qkv.view(M, 3 * Cc)
+    lin = dict(n_img=M, H=1, W=1, taps=1)
+    sk, sq = torch.empty(M, SW, device='cuda'), torch.empty(M, SW, device='cuda')
+    o.gemm(q2[:, :Cc], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=Cc, **lin)
+    o.gemm(q2[:, Cc:2 * Cc], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=Cc, **lin)
+    # spot-check the grouped GEMM: Sk[(b,t,d)][(h,s)] = q . Rk[b,t,s,h,:]
+    qf = qkv.float().view(B, T, HW, 3, heads, hd)[:, :, :, 0]
+    sk_ref = torch.einsum('btdhf,btshf->btdhs', qf, Rb[1].view(B, T, T, heads, hd))
+    got = sk.view(B, T, HW, SW)
+    for t in range(T):
+        sub = torch.stack([got[b, t, :, ((b * T + t) % gpt) * 128:((b * T + t) % gpt) * 128 + heads * T] for b in range(B)])
+        assert relerr(sub.reshape(B, HW, heads, T), sk_ref[:, t]) < 2e-5
+    pm = torch.zeros(M, SW, device='cuda', dtype=torch.bfloat16)
+    pv = torch.empty(M, Cc, device='cuda')
+    o.attn_temporal_tc(q2, sk, sq, mask, pad, B, T, HW, heads, hd, gpt, pm, pv)
+    att = torch.empty(M, Cc, device='cuda', dtype=torch.bfloat16)
+    o.gemm(pm, bv, Cc, residual=pv, out_bf16=att, w_group_tiles=tpg, **lin)
+    assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
+
+
 @pytest.mark.parametrize('L,hd', [(256, 96), (64, 128), (256, 32)])
 def test_attention_spatial_f32(L, hd):
     o = ops()

@@ -18,7 +18,7 @@ TAB_COUNT = 12
 
 EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
            'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
-           'vdm_attn_temporal', 'vdm_attn_spatial', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
+           'vdm_attn_temporal', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
            'vdm_prior_bpd']
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ('C1', _i32), ('C2', _i32), ('N', _i32), ('a1', _vp), ('a2', _vp), ('w', _vp), ('bias', _vp),
                 ('rowbias', _vp), ('ld_rowbias', _i32), ('residual', _vp), ('ld_res', _i32), ('out_f32', _vp),
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
-                ('out_silu_f32', _vp), ('stats_out', _vp)]
+                ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp)]
 
 
 class GnApplyArgs(C.Structure):
@@ -64,6 +64,8 @@ def load():
         'vdm_rpe_hidden': [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
         'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
         'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+        'vdm_rpe_expand': [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+        'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
         'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
         'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],
         'vdm_vb_terms': [_vp] * 6 + [_i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp],

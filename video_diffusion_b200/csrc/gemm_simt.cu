@@ -123,6 +123,7 @@ int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream) {
   VDM_REQUIRE(a->a1_mode >= 0 && a->a1_mode <= 2, "gemm_simt: bad a1_mode");
   VDM_REQUIRE(a->C2 == 0 || a->a2 != nullptr, "gemm_simt: a2 is NULL");
   VDM_REQUIRE(a->stats_out == nullptr, "gemm_simt: stats_out is only produced by the bf16 tensor-core kernel");
+  VDM_REQUIRE(a->lda1 == 0 && a->w_group_tiles == 0, "gemm_simt: lda1 / grouped weights are bf16-kernel features");
   SimtParams p{};
   p.M = a->n_img * a->H * a->W;
   p.N = a->N;

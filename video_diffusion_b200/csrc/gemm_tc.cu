@@ -32,6 +32,7 @@ struct TcParams {
   int M, N;
   int taps, c1_chunks, c2_chunks;
   int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes, 3 nearest-x2 upsample folded into 2x2 taps
+  int w_group_tiles;  // grouped weights: 128-row tile m reads weight rows (m / w_group_tiles) * N + n
   int tiles_per_par;  // a1_mode 3: tiles per output parity (tile index = parity * tiles_per_par + ...)
   int is_linear;  // A1 addressed as 2-D [M][C1]
   int H, W, HW;
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
             else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
           }
-          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + par * p.N);
+          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K,
+                      n0 + par * p.N + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -591,10 +593,11 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   return 0;
 }
 
-// [rows][C] matrix viewed as 5-D (C, rows, 1, 1, 1) with a (64, 128, 1, 1, 1) box.
-int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C) {
+// [rows][C] matrix (row stride ld elements) viewed as 5-D (C, rows, 1, 1, 1) with a (64, 128, 1, 1, 1) box.
+int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C, int64_t ld = 0) {
+  if (ld == 0) ld = C;
   uint64_t dims[5] = {(uint64_t)C, (uint64_t)rows, 1, 1, 1};
-  uint64_t st[5] = {2, (uint64_t)C * 2, (uint64_t)C * 2 * rows, (uint64_t)C * 2 * rows, (uint64_t)C * 2 * rows};
+  uint64_t st[5] = {2, (uint64_t)ld * 2, (uint64_t)ld * 2 * rows, (uint64_t)ld * 2 * rows, (uint64_t)ld * 2 * rows};
   uint32_t box[5] = {BLOCK_K, BLOCK_M, 1, 1, 1};
   return encode_map(map, base, 5, dims, st, box);
 }
@@ -680,11 +683,14 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   p.stats_out = a->stats_out;
+  p.w_group_tiles = a->w_group_tiles;
+  VDM_REQUIRE(a->w_group_tiles == 0 || (is_linear && a->C2 == 0 && !a->out_nchw), "gemm_tc: grouped weights need taps == 1");
+  VDM_REQUIRE(a->lda1 == 0 || (is_linear && a->lda1 >= a->C1 && a->lda1 % 8 == 0), "gemm_tc: bad lda1");
 
   CUtensorMap ma1, ma2, mw;
   int rc;
   if (is_linear) {
-    rc = encode_rows_map(&ma1, a->a1, M, a->C1);
+    rc = encode_rows_map(&ma1, a->a1, M, a->C1, a->lda1);
   } else {
     // tile = 128 consecutive pixels of the channels-last image stack
     const int W = a->W, H = a->H;
@@ -724,11 +730,13 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     const int64_t t1 = ((M + 127) / 128) * (a->N / 128), t2 = ((M + 255) / 256) * (a->N / 128);
     const int sms = num_sms();
     const double cost1 = (double)((t1 + sms - 1) / sms) * 1.35, cost2 = (double)((t2 + sms - 1) / sms) * 2.0;
-    if (cost2 <= cost1 && K >= 1024) m_sub = 2;   // short-K GEMMs are epilogue-bound: keep the 32-column epilogue
+    if (cost2 <= cost1 && K >= 1024 && a->w_group_tiles == 0) m_sub = 2;   // short-K GEMMs are epilogue-bound: keep the 32-column epilogue
   }
-  if (const char* e = getenv("VDM_GEMM_MSUB")) m_sub = atoi(e) == 2 && block_n == 128 ? 2 : 1;
+  if (const char* e = getenv("VDM_GEMM_MSUB")) m_sub = atoi(e) == 2 && block_n == 128 && a->w_group_tiles == 0 ? 2 : 1;
+  VDM_REQUIRE(a->w_group_tiles == 0 || a->N % block_n == 0, "gemm_tc: grouped weights need N %% %d == 0", block_n);
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
+    const int64_t groups = a->w_group_tiles ? ((M + BLOCK_M - 1) / BLOCK_M + a->w_group_tiles - 1) / a->w_group_tiles : 1;
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N * groups};
     uint64_t st[2] = {2, (uint64_t)K * 2};
     uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
     rc = encode_map(&mw, a->w, 2, dims, st, box);

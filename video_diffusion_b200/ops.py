@@ -31,7 +31,8 @@ def _nbytes(*tensors):
 
 
 def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
-         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None):
+         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
+         w_group_tiles=0):
     """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm)."""
     lib = _lib.load()
     g = GemmArgs()
@@ -41,7 +42,12 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     g.C1 = a1.shape[-1] if C1 is None else C1
     g.C2 = C2 if a2 is None else a2.shape[-1]
     g.N = N
-    g.a1, g.a2, g.w = ptr(a1), ptr(a2), ptr(w)
+    if a1.dim() == 2 and not a1.is_contiguous() and a1.stride(1) == 1:      # column block of a wider matrix
+        g.a1, g.lda1 = a1.data_ptr(), a1.stride(0)
+    else:
+        g.a1, g.lda1 = ptr(a1), 0
+    g.a2, g.w = ptr(a2), ptr(w)
+    g.w_group_tiles = w_group_tiles
     g.bias = ptr(bias)
     g.rowbias = None if rowbias is None else rowbias.data_ptr()
     g.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
@@ -124,6 +130,19 @@ def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, o
         ptr(qkv), ptr(r_q), ptr(r_k), ptr(r_v), ptr(mask), int(pad_interact), B, T, HW, heads, hd, ptr(out),
         dt(out.dtype), stream()), 'vdm_attn_temporal'), flops=2.0 * 5 * B * HW * heads * T * T * hd,
            nbytes=_nbytes(qkv, out))
+
+
+def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv):
+    _timed('rpe_expand', lambda: check(_lib.load().vdm_rpe_expand(
+        ptr(r_q), ptr(r_k), ptr(r_v), B, T, heads, hd, gpt, ptr(bq), ptr(bk), ptr(bv), stream()), 'vdm_rpe_expand'),
+           nbytes=_nbytes(bq, bk, bv))
+
+
+def attn_temporal_tc(qkv, sk, sq, mask, pad_interact, B, T, HW, heads, hd, gpt, pm, pv):
+    _timed('attn_temporal_tc', lambda: check(_lib.load().vdm_attn_temporal_tc(
+        ptr(qkv), ptr(sk), ptr(sq), ptr(mask), int(pad_interact), B, T, HW, heads, hd, gpt, ptr(pm), ptr(pv),
+        stream()), 'vdm_attn_temporal_tc'), flops=4.0 * B * HW * heads * T * T * hd,
+           nbytes=_nbytes(qkv, sk, sq, pm, pv))
 
 
 def attn_spatial(qkv, n_img, L, heads, hd, out):

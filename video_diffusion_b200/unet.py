@@ -69,6 +69,7 @@ class UNetModel(nn.Module):
         self.compute_dtype = compute_dtype or torch.bfloat16
         self.use_cuda_graph = True
         self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
+        self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
             raise NotImplementedError('model_channels must be a multiple of 64')
@@ -301,6 +302,12 @@ class UNetModel(nn.Module):
                 b = self.bufs[name] = torch.empty(shape, device=self.dev, dtype=dtype)
             return b
 
+        def zeros(self, name, shape, dtype=torch.float32):
+            b = self.bufs.get(name)
+            if b is None:
+                b = self.bufs[name] = torch.zeros(shape, device=self.dev, dtype=dtype)
+            return b
+
         def stats(self, name, n_img, C, dtype):
             """Per-(image, channel) sum / sum-of-squares table [n_img][2][C]; zeroed at the start of every forward."""
             b = self.stat_bufs.get(name)
@@ -379,8 +386,6 @@ class UNetModel(nn.Module):
         xn = ws.buf(q + '.xn', (M, C))
         xa = ws.buf(q + '.xa', (M, C), adt)
         ops.gn_temporal(h, B, T, HW, C, P[q + '.gn_w'], P[q + '.gn_b'], xn, xa)
-        qkv = ws.buf(q + '.qkv', (M, 3 * C))
-        ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
         hid = ws.buf(q + '.hid', (3, B * T * T, C), adt)
         off = node['rpe_off']
         ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
@@ -391,8 +396,32 @@ class UNetModel(nn.Module):
                      out_f32=Rn)
             R.append(Rn)
         att = ws.buf(q + '.att', (M, C), adt)
-        ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads, hd,
-                          att)
+        tc_path = (adt == torch.bfloat16 and self.temporal_tensor_cores and heads * T <= 128 and T <= 32
+                   and hd in (32, 64, 96, 128) and (HW % 128 == 0 or HW == 64))
+        if tc_path:
+            # RPE terms as pixel-batched GEMMs with per-(b, t) weight groups, the rest on mma.sync
+            gpt = 1 if HW >= 128 else 128 // HW          # (b, t) groups per 128-row tile
+            tpg = max(1, HW // 128)                      # 128-row tiles per group
+            SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
+            qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
+            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
+            bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
+            bv = ws.buf(q + '.bv', (ntg * C, SW), adt)
+            ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv)
+            sk, sq = ws.buf(q + '.sk', (M, SW)), ws.buf(q + '.sq', (M, SW))
+            ops.gemm(qkv[:, :C], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
+            ops.gemm(qkv[:, C:2 * C], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
+            pm = ws.zeros(q + '.pm', (M, SW), adt)       # padding columns stay zero forever
+            pv = ws.buf(q + '.pv', (M, C))
+            ops.attn_temporal_tc(qkv, sk, sq, amask, self.allow_interactions_between_padding, B, T, HW, heads, hd,
+                                 gpt, pm, pv)
+            ops.gemm(pm, bv, C, residual=pv, out_bf16=att, w_group_tiles=tpg, **lin)
+        else:
+            qkv = ws.buf(q + '.qkv', (M, 3 * C))
+            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+            ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads,
+                              hd, att)
         h2 = ws.buf(q + '.out', (M, C))
         st = self._fused_stats(ws, q + '.out', N, HW, C)
         # + NORMALISED x.  The rows of this GEMM are (image, pixel), so the epilogue statistics are
