@@ -171,7 +171,8 @@ int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, cons
  * vdm_attn_temporal_tc (scale*q.k^T + scale*Sk + Sq^T, mask, fp32 softmax, P.V on mma.sync; writes
  * P as bf16 [M][128*gpt] into a buffer whose padding columns the caller zeroed once, and PV fp32
  * [M][C]) and a last grouped vdm_gemm (P x bv, residual PV) for the attn.R_v term (unet.py:357-378). */
-int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, int32_t B, int32_t T,
+int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v,
+                   const float* bias /* optional [3][C] (q, k, v) added to the tables */, int32_t B, int32_t T,
                    int32_t heads, int32_t hd, int32_t groups_per_tile, void* bq, void* bk, void* bv,
                    vdm_stream_t stream);
 int vdm_attn_temporal_tc(const void* qkv, const float* sk, const float* sq, const float* mask,

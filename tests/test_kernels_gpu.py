@@ -361,7 +361,7 @@ def test_attention_temporal_tensor_core_path(T, hd, HW, pad):
     bq = torch.empty(ntg * SW, Cc, device='cuda', dtype=torch.bfloat16)
     bk = torch.empty_like(bq)
     bv = torch.empty(ntg * Cc, SW, device='cuda', dtype=torch.bfloat16)
-    o.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv)
+    o.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv)      # (bias=None: tables already complete)
     q2 = qkv.view(M, 3 * Cc)
     lin = dict(n_img=M, H=1, W=1, taps=1)
     sk, sq = torch.empty(M, SW, device='cuda'), torch.empty(M, SW, device='cuda')

@@ -20,25 +20,51 @@ namespace {
 //   which 0/1 (Bk / Bq): out[tg][sub*128 + h*T + j][h'*hd + f] = (h' == h) * mul * R[(g*T + j)][h*hd + f]
 //   which 2    (Bv)    : out[tg][h*hd + f][sub*128 + h'*T + j] = (h' == h) * R[(g*T + j)][h*hd + f]
 __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
-                                                          const float* __restrict__ r_v, int G, int T, int heads,
-                                                          int hd, int gpt, float scale, __nv_bfloat16* __restrict__ bq,
+                                                          const float* __restrict__ r_v,
+                                                          const float* __restrict__ bias,   // [3][C] (q, k, v) or NULL
+                                                          int G, int T, int heads, int hd, int gpt, float scale,
+                                                          __nv_bfloat16* __restrict__ bq,
                                                           __nv_bfloat16* __restrict__ bk,
                                                           __nv_bfloat16* __restrict__ bv) {
+  // one thread = 8 consecutive outputs (one 16-byte store)
   const int C = heads * hd, SW = 128 * gpt;
-  const int which = blockIdx.z;
+  const int which = blockIdx.z;   // 0: Bk, 1: Bq, 2: Bv
   const int tg = blockIdx.y;
   const float* R = which == 0 ? r_k : (which == 1 ? r_q : r_v);
+  const float* bs = bias ? bias + (which == 0 ? 1 : (which == 1 ? 0 : 2)) * C : nullptr;
   __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + (size_t)tg * SW * C;
   const float mul = which == 1 ? scale : 1.0f;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < SW * C; idx += gridDim.x * blockDim.x) {
-    int n, c;                      // n: index inside the 128*gpt block, c: channel (h', f)
-    if (which < 2) { n = idx / C; c = idx - n * C; } else { c = idx / SW; n = idx - c * SW; }
-    const int sub = n >> 7, r = n & 127;
-    const int g = tg * gpt + sub;
-    const int h = r / T, j = r - h * T;
-    float v = 0.f;
-    if (g < G && h < heads && c / hd == h) v = mul * R[((size_t)g * T + j) * C + c];
-    out[idx] = __float2bfloat16_rn(v);
+  const int nvec = SW * C / 8;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    if (which < 2) {                      // out[n][c .. c+7]
+      const int n = v / (C / 8), c = (v - n * (C / 8)) * 8;
+      const int sub = n >> 7, r = n & 127;
+      const int g = tg * gpt + sub, h = r / T, j = r - h * T;
+      if (g < G && h < heads && c / hd == h) {
+        const float* src = R + ((size_t)g * T + j) * C + c;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = mul * (x[i] + (bs ? bs[c + i] : 0.f));
+      }
+    } else {                              // out[c][n .. n+7]
+      const int c = v / (SW / 8), n0 = (v - c * (SW / 8)) * 8;
+      const int hc = c / hd;
+      const float bc = bs ? bs[c] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = n0 + i, sub = n >> 7, r = n & 127;
+        const int g = tg * gpt + sub, h = r / T, j = r - h * T;
+        if (g < G && h == hc) o[i] = __ldg(R + ((size_t)g * T + j) * C + c) + bc;
+      }
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+    pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+    reinterpret_cast<uint4*>(out)[v] = pk;
   }
 }
 
@@ -249,15 +275,17 @@ int launch_attn(const void* qkv, const float* sk, const float* sq, const float* 
 
 using namespace vdm;
 
-extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, int32_t B, int32_t T, int32_t heads,
-                              int32_t hd, int32_t groups_per_tile, void* bq, void* bk, void* bv, vdm_stream_t stream) {
+extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t B,
+                              int32_t T, int32_t heads, int32_t hd, int32_t groups_per_tile, void* bq, void* bk,
+                              void* bv, vdm_stream_t stream) {
   VDM_REQUIRE(r_q && r_k && r_v && bq && bk && bv, "rpe_expand: NULL pointer");
   VDM_REQUIRE(heads * T <= 128 && groups_per_tile >= 1, "rpe_expand: heads*T = %d must be <= 128", heads * T);
   const int G = B * T, gpt = groups_per_tile;
   const int tgs = (G + gpt - 1) / gpt;
-  const int total = 128 * gpt * heads * hd;
-  dim3 grid(std::min((total + 255) / 256, 64), tgs, 3);
-  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
+  VDM_REQUIRE(hd % 8 == 0, "rpe_expand: head_dim must be a multiple of 8");
+  const int nvec = 128 * gpt * heads * hd / 8;
+  dim3 grid(std::min((nvec + 255) / 256, 32), tgs, 3);
+  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
                                                             (__nv_bfloat16*)bq, (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
   VDM_AFTER_LAUNCH("rpe_expand");
   return 0;

@@ -349,24 +349,42 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
   if ((dim & 1) && i == 0) out[(size_t)row * dim + dim - 1] = 0.f;
 }
 
-// hidden[net][(b*T+i)*T+j][c]
+// hidden[net][(b*T+i)*T+j][c]; one thread = 8 channels of one (net, row)
 template <typename OutT>
 __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict__ e_t, int ld_et,
                                                           const long long* __restrict__ fi, const float* __restrict__ wd,
                                                           const float* __restrict__ bd, int B, int T, int C,
                                                           OutT* __restrict__ out) {
-  const int net = blockIdx.z;
-  const int row = blockIdx.y;  // (b*T + i)*T + j
-  const int bi = row / T, j = row - bi * T;
-  const int b = bi / T;
-  const long long d = fi[bi] - fi[b * T + j];
-  const float df = (float)d;
-  const float f0 = log1pf(fmaxf(df, 0.f)), f1 = log1pf(fmaxf(-df, 0.f)), f2 = (d == 0) ? 1.f : 0.f;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    const float* w = wd + ((size_t)net * C + c) * 3;
-    const float ed = fmaf(f2, w[2], fmaf(f1, w[1], f0 * w[0])) + bd[net * C + c];
-    const float h = e_t[(size_t)bi * ld_et + net * C + c] + ed;
-    store_elem<OutT>(out + ((size_t)net * B * T * T + row) * C + c, silu_precise(h));
+  const int C8 = C / 8;
+  const int rows = B * T * T;
+  const long long total = (long long)3 * rows * C8;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(v % C8) * 8;
+    const long long rr = v / C8;
+    const int row = (int)(rr % rows), net = (int)(rr / rows);
+    const int bi = row / T, j = row - bi * T;
+    const int b = bi / T;
+    const long long d = fi[bi] - fi[b * T + j];
+    const float df = (float)d;
+    const float f0 = log1pf(fmaxf(df, 0.f)), f1 = log1pf(fmaxf(-df, 0.f)), f2 = (d == 0) ? 1.f : 0.f;
+    const float* et = e_t + (size_t)bi * ld_et + net * C + c;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* w = wd + ((size_t)net * C + c + i) * 3;
+      const float ed = fmaf(f2, w[2], fmaf(f1, w[1], f0 * w[0])) + bd[net * C + c + i];
+      y[i] = silu_precise(et[i] + ed);
+    }
+    OutT* o = out + ((size_t)net * rows + row) * C + c;
+    if constexpr (sizeof(OutT) == 2) {
+      uint4 pk;
+      pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+      pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(o) = pk;
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
   }
 }
 
@@ -497,7 +515,9 @@ extern "C" int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int64_t* fr
                               const float* bd, int32_t B, int32_t T, int32_t C, void* out, int32_t out_dtype,
                               vdm_stream_t stream) {
   VDM_REQUIRE(e_t && frame_indices && wd && bd && out, "rpe_hidden: NULL pointer");
-  dim3 grid((C + 255) / 256, B * T * T, 3);
+  VDM_REQUIRE(C % 8 == 0, "rpe_hidden: C must be a multiple of 8");
+  const long long total = (long long)3 * B * T * T * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
   if (out_dtype == VDM_BF16)
     rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, (const long long*)frame_indices,
                                                                             wd, bd, B, T, C, (__nv_bfloat16*)out);

@@ -132,9 +132,10 @@ def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, o
            nbytes=_nbytes(qkv, out))
 
 
-def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv):
+def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv, bias=None):
     _timed('rpe_expand', lambda: check(_lib.load().vdm_rpe_expand(
-        ptr(r_q), ptr(r_k), ptr(r_v), B, T, heads, hd, gpt, ptr(bq), ptr(bk), ptr(bv), stream()), 'vdm_rpe_expand'),
+        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), B, T, heads, hd, gpt, ptr(bq), ptr(bk), ptr(bv), stream()),
+        'vdm_rpe_expand'),
            nbytes=_nbytes(bq, bk, bv))
 
 

@@ -256,6 +256,8 @@ class UNetModel(nn.Module):
                 nets = ('rpe_q', 'rpe_k', 'rpe_v')
                 put(q + '.rpe_wd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.weight'] for r in nets]))
                 put(q + '.rpe_bd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.bias'] for r in nets]))
+                put(q + '.rpe_out_w', torch.cat([sd[f'{q}.{r}.rpe_net.out.weight'] for r in nets]), adt)
+                put(q + '.rpe_out_b', torch.stack([sd[f'{q}.{r}.rpe_net.out.bias'] for r in nets]))
                 for r in nets:
                     put(f'{q}.{r}.out_w', sd[f'{q}.{r}.rpe_net.out.weight'], adt)
                     put(f'{q}.{r}.out_b', sd[f'{q}.{r}.rpe_net.out.bias'])
@@ -269,6 +271,8 @@ class UNetModel(nn.Module):
                     put(p + '.wfold', fold_upsample_weights(sd[p + '.weight']), adt)
         put('emb_w', torch.cat(emb_w)); put('emb_b', torch.cat(emb_b))
         put('rpe_t_w', torch.cat(rpe_w)); put('rpe_t_b', torch.cat(rpe_b))
+        if adt == torch.bfloat16:
+            put('emb_w_a', torch.cat(emb_w), adt); put('rpe_t_w_a', torch.cat(rpe_w), adt)
         put('out_gn_w', sd['out.0.weight']); put('out_gn_b', sd['out.0.bias'])
         put('out_w', conv_w('out.2.weight'), adt); put('out_b', sd['out.2.bias'])
         if self.spatial_encoding is not None:
@@ -389,15 +393,24 @@ class UNetModel(nn.Module):
         hid = ws.buf(q + '.hid', (3, B * T * T, C), adt)
         off = node['rpe_off']
         ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
-        R = []
-        for i, r in enumerate(('rpe_q', 'rpe_k', 'rpe_v')):
-            Rn = ws.buf(f'{q}.{r}.R', (B * T * T, C))
-            ops.gemm(hid[i], P[f'{q}.{r}.out_w'], C, n_img=B * T * T, H=1, W=1, taps=1, bias=P[f'{q}.{r}.out_b'],
-                     out_f32=Rn)
-            R.append(Rn)
-        att = ws.buf(q + '.att', (M, C), adt)
         tc_path = (adt == torch.bfloat16 and self.temporal_tensor_cores and heads * T <= 128 and T <= 32
                    and hd in (32, 64, 96, 128) and (HW % 128 == 0 or HW == 64))
+        rows = B * T * T
+        if tc_path and rows % 128 == 0:
+            # the three RPE nets' output layers as ONE grouped GEMM (weights differ per net = per row block);
+            # their biases are added when the tables are expanded
+            Rall = ws.buf(q + '.Rall', (3 * rows, C))
+            ops.gemm(hid.view(3 * rows, C), P[q + '.rpe_out_w'], C, n_img=3 * rows, H=1, W=1, taps=1, out_f32=Rall,
+                     w_group_tiles=rows // 128)
+            R, r_bias = [Rall[i * rows:(i + 1) * rows] for i in range(3)], P[q + '.rpe_out_b']
+        else:
+            R, r_bias = [], None
+            for i, r in enumerate(('rpe_q', 'rpe_k', 'rpe_v')):
+                Rn = ws.buf(f'{q}.{r}.R', (rows, C))
+                ops.gemm(hid[i], P[f'{q}.{r}.out_w'], C, n_img=rows, H=1, W=1, taps=1, bias=P[f'{q}.{r}.out_b'],
+                         out_f32=Rn)
+                R.append(Rn)
+        att = ws.buf(q + '.att', (M, C), adt)
         if tc_path:
             # RPE terms as pixel-batched GEMMs with per-(b, t) weight groups, the rest on mma.sync
             gpt = 1 if HW >= 128 else 128 // HW          # (b, t) groups per 128-row tile
@@ -408,7 +421,7 @@ class UNetModel(nn.Module):
             bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
             bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
             bv = ws.buf(q + '.bv', (ntg * C, SW), adt)
-            ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv)
+            ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv, bias=r_bias)
             sk, sq = ws.buf(q + '.sk', (M, SW)), ws.buf(q + '.sq', (M, SW))
             ops.gemm(qkv[:, :C], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
             ops.gemm(qkv[:, C:2 * C], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
@@ -466,9 +479,18 @@ class UNetModel(nn.Module):
         emb, embs = ws.buf('emb', (N, E)), ws.buf('embs', (N, E))
         ops.gemm(l0s, P['te_w2'], E, bias=P['te_b2'], out_f32=emb, out_silu=embs, **lin)
         emb_out = ws.buf('emb_out', (N, P['emb_w'].shape[0]))
-        ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
         rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0]))
-        ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+        if adt == torch.bfloat16:
+            # the two wide projections of the embedding (all ResBlock scale/shift vectors, all RPE-net time
+            # terms) go through the tensor-core GEMM on bf16 copies of silu(emb) / emb
+            embs_b, emb_b = ws.buf('embs_b', (N, E), adt), ws.buf('emb_b', (N, E), adt)
+            ops.gn_apply(embs, None, N, 1, 1, embs_b)
+            ops.gn_apply(emb, None, N, 1, 1, emb_b)
+            ops.gemm(embs_b, P['emb_w_a'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
+            ops.gemm(emb_b, P['rpe_t_w_a'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+        else:
+            ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
+            ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
         hs, x, cur_group, n_groups_done = [], None, None, 0
