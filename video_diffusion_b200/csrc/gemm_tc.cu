@@ -183,13 +183,19 @@ struct SmemLayout {
 //   warp 0      : TMA producer (one lane), STAGES-deep smem ring
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one lane), two accumulator stages in TMEM
 //   warps 2..9  : epilogue; the accumulator of tile i drains while the MMAs of tile i+1 run
-template <int BLOCK_N, int M_SUB, int STAGES, bool HAS_RES>
+// EPI selects the epilogue at compile time (the epilogue is instruction-issue bound, so every option that
+// is a runtime branch inside its row loop costs throughput): bit 0 residual add, bit 1 bf16 output (else
+// fp32), bit 2 GroupNorm statistics; bit 3 = generic path with every option decided at run time (per-image
+// bias, both outputs, NCHW store, folded-upsample row remap, ragged N).
+template <int BLOCK_N, int M_SUB, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
                                                                  const __grid_constant__ CUtensorMap tm_a2,
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const TcParams p) {
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
   constexpr int TILE_M = BLOCK_M * M_SUB;
+  constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
+  constexpr bool STATS = GEN || (EPI & 4) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         else tmem_ld_16(taddr, acc);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + j * CHUNK;
-        if (p.out_nchw) {  // lanes = consecutive pixels: already coalesced per channel
+        if (GEN && p.out_nchw) {  // lanes = consecutive pixels: already coalesced per channel
           if (row < p.M) {
             const int img = row / p.HW, pix = row - img * p.HW;
             for (int i = 0; i < CHUNK; ++i) {
@@ -425,7 +431,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
         const int n = nb + c4;
         float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < p.N) {  // N is a multiple of 4 on this path
+        if constexpr (!GEN) {
+          // lean path: N is a multiple of BLOCK_N, exactly one output, no per-image bias / row remap
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+          const int row_first = m0 + q * 32 + r_sub;
+          const bool full = m0 + BLOCK_M <= p.M;
+          const float* sp = stg + r_sub * STG_LD + c4;
+          float* o32 = nullptr;
+          __nv_bfloat16* o16 = nullptr;
+          if constexpr (BF16_OUT) o16 = p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n;
+          else o32 = p.out_f32 + (size_t)row_first * p.ld_out + n;
+#pragma unroll
+          for (int i = 0; i < NRES; ++i) {
+            if (full || row_first + i * RPI < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if constexpr (HAS_RES) {
+                v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
+              }
+              if constexpr (STATS) {
+                ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+                ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+                ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+              }
+              if constexpr (BF16_OUT) {
+                uint2 pk;
+                pk.x = pack_bf16x2(v.x, v.y);
+                pk.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(o16 + (size_t)(i * RPI) * p.ld_out_bf16) = pk;
+              } else {
+                *reinterpret_cast<float4*>(o32 + (size_t)(i * RPI) * p.ld_out) = v;
+              }
+            }
+          }
+        } else if (n < p.N) {  // N is a multiple of 4 on this path
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
@@ -462,7 +502,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
         }
-        if (p.stats_out != nullptr) {
+        if (STATS && p.stats_out != nullptr) {
           // GroupNorm statistics of the stored tile, step 1: fold the lanes that share a column quad and
           // park the warp's 32-row partial sums in shared memory.
 #pragma unroll
@@ -490,7 +530,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));
-      if (p.stats_out != nullptr) {
+      if (STATS && p.stats_out != nullptr) {
         // step 2 (all epilogue warps): one thread per (channel, plane) adds the row-block partials in a
         // fixed order and accumulates them into the per-(image, channel) table with 64-bit fixed-point
         // atomics -- integer addition is associative, so the statistics (and everything downstream) are
@@ -602,13 +642,13 @@ int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C,
   return encode_map(map, base, 5, dims, st, box);
 }
 
-template <int BLOCK_N, int M_SUB, int STAGES, bool HAS_RES>
+template <int BLOCK_N, int M_SUB, int STAGES, int EPI>
 int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                 cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, HAS_RES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -616,38 +656,37 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
     }
     configured = true;
   }
-  const int tiles = ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M * M_SUB - 1) / (BLOCK_M * M_SUB));
+  const int tiles = (p.a1_mode == 3 ? 4 * p.tiles_per_par
+                                    : ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M * M_SUB - 1) / (BLOCK_M * M_SUB)));
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, HAS_RES><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+  gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
   VDM_AFTER_LAUNCH("gemm_tc");
   return 0;
 }
 
-template <int M_SUB, int STAGES>
-int launch_upfold(const CUtensorMap& ma1, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
-  using L = SmemLayout<128, M_SUB, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, M_SUB, STAGES, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
-  const int tiles = 4 * p.tiles_per_par;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<128, M_SUB, STAGES, false><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma1, mw, p);
-  VDM_AFTER_LAUNCH("gemm_tc");
-  return 0;
+// epilogue variant for this call (see the kernel's EPI parameter)
+int epilogue_variant(const TcParams& p, int block_n) {
+  const bool one_out = (p.out_f32 != nullptr) != (p.out_bf16 != nullptr);
+  const bool fast = !p.out_nchw && !p.rowbias && p.a1_mode != 3 && one_out && p.N % block_n == 0;
+  if (!fast) return 8 | (p.residual ? 1 : 0);
+  return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
 }
 
 template <int BLOCK_N, int M_SUB, int STAGES>
 int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
            cudaStream_t stream) {
-  if (p.residual) return launch_inst<BLOCK_N, M_SUB, STAGES, true>(ma1, ma2, mw, p, stream);
-  return launch_inst<BLOCK_N, M_SUB, STAGES, false>(ma1, ma2, mw, p, stream);
+  switch (epilogue_variant(p, BLOCK_N)) {
+    case 0: return launch_inst<BLOCK_N, M_SUB, STAGES, 0>(ma1, ma2, mw, p, stream);
+    case 1: return launch_inst<BLOCK_N, M_SUB, STAGES, 1>(ma1, ma2, mw, p, stream);
+    case 2: return launch_inst<BLOCK_N, M_SUB, STAGES, 2>(ma1, ma2, mw, p, stream);
+    case 3: return launch_inst<BLOCK_N, M_SUB, STAGES, 3>(ma1, ma2, mw, p, stream);
+    case 4: return launch_inst<BLOCK_N, M_SUB, STAGES, 4>(ma1, ma2, mw, p, stream);
+    case 5: return launch_inst<BLOCK_N, M_SUB, STAGES, 5>(ma1, ma2, mw, p, stream);
+    case 6: return launch_inst<BLOCK_N, M_SUB, STAGES, 6>(ma1, ma2, mw, p, stream);
+    case 7: return launch_inst<BLOCK_N, M_SUB, STAGES, 7>(ma1, ma2, mw, p, stream);
+    case 9: return launch_inst<BLOCK_N, M_SUB, STAGES, 9>(ma1, ma2, mw, p, stream);
+    default: return launch_inst<BLOCK_N, M_SUB, STAGES, 8>(ma1, ma2, mw, p, stream);
+  }
 }
 
 }  // namespace
@@ -799,10 +838,10 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   const bool two = (double)((4 * t2 + sms - 1) / sms) * 2.0 <= (double)((4 * t1 + sms - 1) / sms) * 1.35;
   if (two) {
     p.tiles_per_par = (int)t2;
-    return launch_upfold<2, 4>(ma1, mw, p, stream);
+    return launch_inst<128, 2, 4, 8>(ma1, ma1, mw, p, stream);
   }
   p.tiles_per_par = (int)t1;
-  return launch_upfold<1, 5>(ma1, mw, p, stream);
+  return launch_inst<128, 1, 5, 8>(ma1, ma1, mw, p, stream);
 }
 
 }  // namespace vdm
