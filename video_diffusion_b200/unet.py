@@ -283,7 +283,7 @@ class UNetModel(nn.Module):
 
     # ---- execution -------------------------------------------------------------------------------
     class _Workspace:
-        def __init__(self, B, F, H, W, dev):
+        def __init__(self, B, F, H, W, dev, stat_capacity):
             self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
             self.bufs = {}
             self.graph = None
@@ -298,6 +298,8 @@ class UNetModel(nn.Module):
             self.t_override = torch.empty(N, device=dev, dtype=f32)
             self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
             self.stat_bufs = {}
+            self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
+            self.pool_used = 0
             self.out = None
 
         def buf(self, name, shape, dtype=torch.float32):
@@ -313,15 +315,21 @@ class UNetModel(nn.Module):
             return b
 
         def stats(self, name, n_img, C, dtype):
-            """Per-(image, channel) sum / sum-of-squares table [n_img][2][C]; zeroed at the start of every forward."""
+            """Per-(image, channel) sum / sum-of-squares table [n_img][2][C], carved out of one 8-byte pool that a
+            single memset clears at the start of every forward."""
             b = self.stat_bufs.get(name)
             if b is None:
-                b = self.stat_bufs[name] = torch.zeros(n_img, 2, C, device=self.dev, dtype=dtype)
+                n = n_img * 2 * C
+                if self.pool_used + n > self.pool.numel():
+                    raise RuntimeError('internal: GroupNorm statistics pool too small')
+                b = self.pool[self.pool_used:self.pool_used + n].view(dtype).view(n_img, 2, C)
+                self.pool_used += n
+                self.stat_bufs[name] = b
             return b
 
         def zero_stats(self):
-            if self.stat_bufs:
-                torch._foreach_zero_(list(self.stat_bufs.values()))
+            if self.pool_used:
+                self.pool[:self.pool_used].zero_()
 
     # GroupNorm statistics travel with the activation as (tensor, stats): in bf16 mode the producing GEMM's
     # epilogue accumulates them (deterministic fixed-point atomics); otherwise the standalone kernel does (float64).
@@ -582,7 +590,9 @@ class UNetModel(nn.Module):
         key = (B, F, H, W, str(x.device), per_frame_t is not None)
         ws = self._workspaces.get(key)
         if ws is None:
-            ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device)
+            chans = sum((n['cin'] + 3 * n['cout']) if n['kind'] == 'res' else 3 * n.get('C', self.model_channels)
+                        for n in self.plan) + 2 * self.model_channels
+            ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device, 2 * B * F * chans)
         ws.x.copy_(x)
         ws.x0.copy_(x0)
         ws.obs.copy_(obs.reshape(B, F))
