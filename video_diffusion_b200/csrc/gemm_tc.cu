@@ -121,6 +121,60 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- 2-CTA (cta_group::2) forms: the CTA pair of a cluster executes one M=256 MMA; the even CTA (leader)
+// issues it, operands come from BOTH CTAs' shared memory at identical offsets, TMA loads issued by either
+// CTA signal the LEADER's mbarrier (cluster address with the peer bit cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on CTA `rank`'s copy of a barrier (remote arrive through the cluster address space)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -145,27 +199,31 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int UMMA_M = BLOCK_M>
 constexpr uint32_t instr_desc() {
   return (1u << 4)                          // accumulator fp32
          | (1u << 7) | (1u << 10)           // A, B = bf16
          | ((uint32_t)(BLOCK_N >> 3) << 17) // N
-         | ((uint32_t)(BLOCK_M >> 4) << 24);  // M
+         | ((uint32_t)(UMMA_M >> 4) << 24);  // M (256 = one MMA across the CTA pair)
 }
 
 template <int BLOCK_N, int M_SUB>
-constexpr int tmem_cols() { return 2 * M_SUB * BLOCK_N < 32 ? 32 : 2 * M_SUB * BLOCK_N; }   // two accumulator stages
+constexpr int tmem_cols() {   // two accumulator stages, rounded up to the power of two tcgen05.alloc wants
+  int need = 2 * M_SUB * BLOCK_N, c = 32;
+  while (c < need) c *= 2;
+  return c;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N, int M_SUB, int STAGES>
+template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
 struct SmemLayout {
   static constexpr int CHUNK = (BLOCK_N < 32 || M_SUB > 1) ? 16 : 32;
   static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int A_BYTES = M_SUB * A_SUB_BYTES;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;   // 2-CTA: each CTA holds half of N
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_STRIDE;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;                    // epilogue staging
@@ -187,13 +245,17 @@ struct SmemLayout {
 // is a runtime branch inside its row loop costs throughput): bit 0 residual add, bit 1 bf16 output (else
 // fp32), bit 2 GroupNorm statistics; bit 3 = generic path with every option decided at run time (per-image
 // bias, both outputs, NCHW store, folded-upsample row remap, ragged N).
-template <int BLOCK_N, int M_SUB, int STAGES, int EPI>
+template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
                                                                  const __grid_constant__ CUtensorMap tm_a2,
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const TcParams p) {
-  using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
-  constexpr int TILE_M = BLOCK_M * M_SUB;
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
+  static_assert(!CTA2 || M_SUB == 1, "2-CTA tiles are 256 x BLOCK_N: one 128-row sub-tile per CTA");
+  constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);     // rows per work tile (CTA or CTA pair)
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader
+  const int work_id0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
   constexpr bool STATS = GEN || (EPI & 4) != 0;
   extern __shared__ uint8_t smem_raw[];
@@ -219,20 +281,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), EPI_WARPS);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS * (CTA2 ? 2 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
-                 "n"(tmem_cols<BLOCK_N, M_SUB>())
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {   // the same warp of BOTH CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                   "n"(tmem_cols<BLOCK_N, M_SUB>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                   "n"(tmem_cols<BLOCK_N, M_SUB>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // peer barriers must be initialised before any remote arrive
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -244,14 +315,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int k1 = p.taps * p.c1_chunks;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = work_id0; tile < n_tiles; tile += work_step) {
         int par = 0, tl = tile;
         if (p.a1_mode == 3) {
           par = tile / p.tiles_per_par;
           tl = tile - par * p.tiles_per_par;
         }
         const int n0 = (tl % n_tiles_n) * BLOCK_N;
-        const int m0 = (tl / n_tiles_n) * TILE_M;
+        const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
         int img0[M_SUB], y0[M_SUB], x0[M_SUB];
 #pragma unroll
         for (int sub = 0; sub < M_SUB; ++sub) {
@@ -268,7 +339,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
           const uint32_t b_dst = a_dst + L::A_BYTES;
-          mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
+          if constexpr (CTA2) {   // the leader's barrier counts the bytes landing in both CTAs
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * (L::A_BYTES + L::B_BYTES));
+          } else {
+            mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
+          }
           int dy = 0, dx = 0, plane = 0, c0 = 0;
           const bool first_range = kb < k1;
           if (first_range) {
@@ -296,12 +371,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
           for (int sub = 0; sub < M_SUB; ++sub) {
             const uint32_t dst = a_dst + sub * L::A_SUB_BYTES;
-            if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
-            else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
-            else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
+            if constexpr (CTA2) {
+              if (!first_range) tma_load_5d_2cta(dst, &tm_a2, full_bar(stage), c0, m0, 0, 0, 0);
+              else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, m0, 0, 0, 0);
+              else tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
+            } else {
+              if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
+            }
           }
-          tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K,
-                      n0 + par * p.N + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
+          if constexpr (CTA2)   // this CTA's half of the weight tile
+            tma_load_2d_2cta(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + (int)cta_rank * (BLOCK_N / 2));
+          else
+            tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K,
+                        n0 + par * p.N + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -311,12 +395,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc<BLOCK_N>();
+    if (lane == 0 && cta_rank == 0) {   // 2-CTA: only the leader issues
+      constexpr uint32_t idesc = instr_desc<BLOCK_N, CTA2 ? 256 : BLOCK_M>();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);   // epilogue has drained this accumulator stage
@@ -333,16 +417,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+              if constexpr (CTA2) umma_bf16_2cta(tmem_acc, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+              else umma_bf16(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CTA2) umma_commit_2cta(empty_bar(stage));
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tmem_full_bar(as));  // accumulator complete
+        if constexpr (CTA2) umma_commit_2cta(tmem_full_bar(as));   // accumulator complete (both CTAs' epilogues)
+        else umma_commit(tmem_full_bar(as));
       }
     }
   } else {
@@ -365,14 +453,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     float* part = stg + 32 * STG_LD;
     const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
       int par = 0, tl = tile;
       if (p.a1_mode == 3) {
         par = tile / p.tiles_per_par;
         tl = tile - par * p.tiles_per_par;
       }
       const int n0 = (tl % n_tiles_n) * BLOCK_N;
-      const int mt0 = (tl / n_tiles_n) * TILE_M;
+      const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       float4 res_cur[NRES];
@@ -529,15 +617,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
+        else mbar_arrive(tmem_empty_bar(as));
+      }
       if (STATS && p.stats_out != nullptr) {
         // step 2 (all epilogue warps): one thread per (channel, plane) adds the row-block partials in a
         // fixed order and accumulates them into the per-(image, channel) table with 64-bit fixed-point
         // atomics -- integer addition is associative, so the statistics (and everything downstream) are
         // bit-reproducible from run to run.
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        const int te = threadIdx.x - 64;
-        if (te < 2 * BLOCK_N) {
+#pragma unroll 1
+        for (int te = threadIdx.x - 64; te < 2 * BLOCK_N; te += EPI_WARPS * 32) {
           const int plane = te / BLOCK_N, nl = te - plane * BLOCK_N;
           const int j = nl / CHUNK, cl = nl - j * CHUNK;
           if (n0 + nl < p.N) {
@@ -577,11 +668,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer still uses it
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N, M_SUB>())
-                 : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(tmem_cols<BLOCK_N, M_SUB>())
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(tmem_cols<BLOCK_N, M_SUB>())
+                   : "memory");
   }
 }
 
@@ -642,13 +740,14 @@ int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C,
   return encode_map(map, base, 5, dims, st, box);
 }
 
-template <int BLOCK_N, int M_SUB, int STAGES, int EPI>
+template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
 int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                 cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, M_SUB, STAGES>;
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -656,10 +755,33 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
     }
     configured = true;
   }
+  constexpr int TILE_ROWS = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
   const int tiles = (p.a1_mode == 3 ? 4 * p.tiles_per_par
-                                    : ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M * M_SUB - 1) / (BLOCK_M * M_SUB)));
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+                                    : ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS));
+  if constexpr (CTA2) {
+    // one CTA pair (a 2-CTA cluster on one TPC) per work tile; persistent over pairs
+    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, ma1, ma2, mw, p);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (2-CTA): launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+  }
   VDM_AFTER_LAUNCH("gemm_tc");
   return 0;
 }
@@ -672,20 +794,20 @@ int epilogue_variant(const TcParams& p, int block_n) {
   return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
 }
 
-template <int BLOCK_N, int M_SUB, int STAGES>
+template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
 int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
            cudaStream_t stream) {
   switch (epilogue_variant(p, BLOCK_N)) {
-    case 0: return launch_inst<BLOCK_N, M_SUB, STAGES, 0>(ma1, ma2, mw, p, stream);
-    case 1: return launch_inst<BLOCK_N, M_SUB, STAGES, 1>(ma1, ma2, mw, p, stream);
-    case 2: return launch_inst<BLOCK_N, M_SUB, STAGES, 2>(ma1, ma2, mw, p, stream);
-    case 3: return launch_inst<BLOCK_N, M_SUB, STAGES, 3>(ma1, ma2, mw, p, stream);
-    case 4: return launch_inst<BLOCK_N, M_SUB, STAGES, 4>(ma1, ma2, mw, p, stream);
-    case 5: return launch_inst<BLOCK_N, M_SUB, STAGES, 5>(ma1, ma2, mw, p, stream);
-    case 6: return launch_inst<BLOCK_N, M_SUB, STAGES, 6>(ma1, ma2, mw, p, stream);
-    case 7: return launch_inst<BLOCK_N, M_SUB, STAGES, 7>(ma1, ma2, mw, p, stream);
-    case 9: return launch_inst<BLOCK_N, M_SUB, STAGES, 9>(ma1, ma2, mw, p, stream);
-    default: return launch_inst<BLOCK_N, M_SUB, STAGES, 8>(ma1, ma2, mw, p, stream);
+    case 0: return launch_inst<BLOCK_N, M_SUB, STAGES, 0, CTA2>(ma1, ma2, mw, p, stream);
+    case 1: return launch_inst<BLOCK_N, M_SUB, STAGES, 1, CTA2>(ma1, ma2, mw, p, stream);
+    case 2: return launch_inst<BLOCK_N, M_SUB, STAGES, 2, CTA2>(ma1, ma2, mw, p, stream);
+    case 3: return launch_inst<BLOCK_N, M_SUB, STAGES, 3, CTA2>(ma1, ma2, mw, p, stream);
+    case 4: return launch_inst<BLOCK_N, M_SUB, STAGES, 4, CTA2>(ma1, ma2, mw, p, stream);
+    case 5: return launch_inst<BLOCK_N, M_SUB, STAGES, 5, CTA2>(ma1, ma2, mw, p, stream);
+    case 6: return launch_inst<BLOCK_N, M_SUB, STAGES, 6, CTA2>(ma1, ma2, mw, p, stream);
+    case 7: return launch_inst<BLOCK_N, M_SUB, STAGES, 7, CTA2>(ma1, ma2, mw, p, stream);
+    case 9: return launch_inst<BLOCK_N, M_SUB, STAGES, 9, CTA2>(ma1, ma2, mw, p, stream);
+    default: return launch_inst<BLOCK_N, M_SUB, STAGES, 8, CTA2>(ma1, ma2, mw, p, stream);
   }
 }
 
@@ -773,13 +895,32 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   }
   if (const char* e = getenv("VDM_GEMM_MSUB")) m_sub = atoi(e) == 2 && block_n == 128 && a->w_group_tiles == 0 ? 2 : 1;
   VDM_REQUIRE(a->w_group_tiles == 0 || a->N % block_n == 0, "gemm_tc: grouped weights need N %% %d == 0", block_n);
+  // 2-CTA pairs (cta_group::2, 256 x N tiles): each SM feeds half of the weight tile from its own shared
+  // memory, which is what limits the single-CTA kernel on long-K layers
+  bool cta2 = false;
+  {
+    int mode = 1;   // VDM_GEMM_CTA2: 0 = never, 1 = heuristic (default), 2 = whenever legal (tests)
+    if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
+    const bool legal = !a->out_nchw && a->N % 128 == 0 && a->w_group_tiles == 0 && a->a1_mode <= 1;
+    const int bn2 = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
+    const int64_t pair_tiles = ((M + 255) / 256) * (a->N / bn2);
+    // measured: 256- and 192-wide pair tiles beat the single-CTA kernel by ~20 % on long-K layers, 128-wide
+    // pair tiles lose to the 256x128 single-CTA tile
+    cta2 = legal && mode > 0 && (mode >= 2 || (bn2 >= 192 && K >= 1024 && pair_tiles >= 40));
+    if (cta2) block_n = bn2;
+  }
   {
     const int64_t groups = a->w_group_tiles ? ((M + BLOCK_M - 1) / BLOCK_M + a->w_group_tiles - 1) / a->w_group_tiles : 1;
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N * groups};
     uint64_t st[2] = {2, (uint64_t)K * 2};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(cta2 ? block_n / 2 : block_n)};
     rc = encode_map(&mw, a->w, 2, dims, st, box);
     if (rc) return rc;
+  }
+  if (cta2) {
+    if (block_n == 256) return launch<256, 1, 5, true>(ma1, ma2, mw, p, stream);
+    if (block_n == 192) return launch<192, 1, 6, true>(ma1, ma2, mw, p, stream);
+    return launch<128, 1, 7, true>(ma1, ma2, mw, p, stream);
   }
   switch (block_n) {
     case 128:
