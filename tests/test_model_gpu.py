@@ -83,6 +83,36 @@ def test_forward_matches_reference_and_oracle(golden, case, dtype):
     assert worst <= 2.5 * TOL[dtype]
 
 
+@pytest.mark.parametrize('cfg_name,B,F,bound', [('c2', 2, 20, None), ('c4', 1, 6, None)], ids=['c2_64x64', 'c4_128x128'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_full_size_models_match_oracle(golden, cfg_name, B, F, bound, dtype):
+    """The benchmarked architectures (64x64 MineRL-sized and 128x128 CARLA-sized U-Nets: head_dim 96/128,
+    256x128 and 2-CTA GEMM tiles, folded upsampling, tensor-core temporal attention) against the pinned CPU
+    oracle on identical de-zeroed weights, ragged masks and non-contiguous frame indices."""
+    model, _ = build_model(cfg_name, golden, dtype)
+    size = {'c2': 64, 'c4': 128}[cfg_name]
+    x0 = synth.make_video((B, F, 3, size, size), seed=41)
+    x = synth.make_noise((B, F, 3, size, size), seed=42)
+    obs = torch.zeros(B, F, 1, 1, 1)
+    lat = torch.zeros(B, F, 1, 1, 1)
+    for b in range(B):
+        n_obs = 2 + b
+        obs[b, :n_obs] = 1
+        lat[b, n_obs:F - b] = 1                       # row 1 ends with one padding frame
+    fi = torch.stack([torch.randperm(200, generator=torch.Generator().manual_seed(7 + b))[:F] for b in range(B)])
+    t = torch.tensor([411.0, 37.0][:B])
+    kw = dict(x0=x0, obs_mask=obs, latent_mask=lat, kinda_marg_mask=torch.zeros_like(obs), frame_indices=fi,
+              x_t_minus_1=x0, observed_frames='x_0')
+    with torch.no_grad():
+        out, _ = model(x.cuda(), t.cuda(), **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        sd = synth.make_state_dict(golden.json('spec_' + cfg_name), seed=1)
+        cfg = U.model_config(**cases.ref_config(cfg_name))
+        ref = U.cond_marg_forward(sd, cfg, x, x0, obs, lat, torch.zeros_like(obs), t, fi)
+    err = max_rel(out.cpu().numpy(), ref.numpy())
+    print(f'{cfg_name} {dtype}: eps max-rel vs oracle {err:.3e}')
+    assert err <= TOL[dtype]
+
+
 def test_cuda_graph_replay_equals_eager(golden):
     case = cases.UNET_CASES[0]
     model, _ = build_model(case['cfg'], golden, torch.bfloat16)
