@@ -228,8 +228,7 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_STRIDE;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;                    // epilogue staging
   static constexpr int TOTAL_CHUNKS = M_SUB * (BLOCK_N / CHUNK);
-  static constexpr int PART_FLOATS = ((TOTAL_CHUNKS + 1) / 2) * CHUNK * 2;    // per-warp GroupNorm partial sums
-  static constexpr int WARP_STG_FLOATS = 32 * (CHUNK + 4) + PART_FLOATS;
+  static constexpr int WARP_STG_FLOATS = 32 * (CHUNK + 4);
   static constexpr int STG_BYTES = EPI_WARPS * WARP_STG_FLOATS * 4;
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
@@ -450,7 +449,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int half = ew >> 2;        // the two warps of a quarter split the column chunks
     float* stg_base = reinterpret_cast<float*>(smem_gen + L::STG_OFFSET);
     float* stg = stg_base + ew * L::WARP_STG_FLOATS;
-    float* part = stg + 32 * STG_LD;
     const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
     int it = 0;
     for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
@@ -591,8 +589,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         if (STATS && p.stats_out != nullptr) {
-          // GroupNorm statistics of the stored tile, step 1: fold the lanes that share a column quad and
-          // park the warp's 32-row partial sums in shared memory.
+          // GroupNorm statistics of the stored tile: fold the lanes that share a column quad, then add this
+          // warp's 32-row partial sums to the per-(image, channel) table with 64-bit fixed-point atomics.
+          // Integer addition is associative, so the statistics (and everything downstream) are bit-reproducible
+          // from run to run without any cross-warp ordering.
 #pragma unroll
           for (int o = LPR; o < 32; o <<= 1) {
             ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
@@ -600,10 +600,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
             ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
           }
-          if (r_sub == 0) {
-            float* dst = part + (jj >> 1) * (2 * CHUNK) + c4;
-            *reinterpret_cast<float4*>(dst) = ssum;
-            *reinterpret_cast<float4*>(dst + CHUNK) = ssq;
+          const int row0 = m0 + q * 32;      // the warp's 32 rows lie in one image (H*W % 32 == 0)
+          if (r_sub == 0 && n < p.N && row0 < p.M) {
+            unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) +
+                                      (size_t)(row0 / p.HW) * 2 * p.N + n;
+            const float sv[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const long long fx = __double2ll_rn((double)sv[e] * 16777216.0);
+              atomicAdd(tab + (e >> 2) * p.N + (e & 3), (unsigned long long)fx);
+            }
           }
         }
         if constexpr (HAS_RES) {
@@ -620,49 +626,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       if (lane == 0) {
         if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
         else mbar_arrive(tmem_empty_bar(as));
-      }
-      if (STATS && p.stats_out != nullptr) {
-        // step 2 (all epilogue warps): one thread per (channel, plane) adds the row-block partials in a
-        // fixed order and accumulates them into the per-(image, channel) table with 64-bit fixed-point
-        // atomics -- integer addition is associative, so the statistics (and everything downstream) are
-        // bit-reproducible from run to run.
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-#pragma unroll 1
-        for (int te = threadIdx.x - 64; te < 2 * BLOCK_N; te += EPI_WARPS * 32) {
-          const int plane = te / BLOCK_N, nl = te - plane * BLOCK_N;
-          const int j = nl / CHUNK, cl = nl - j * CHUNK;
-          if (n0 + nl < p.N) {
-            float acc = 0.f;
-            int cur_img = -1;
-            unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out);
-            auto flush = [&]() {
-              if (cur_img >= 0) {
-                const long long fx = __double2ll_rn((double)acc * 16777216.0);
-                atomicAdd(tab + ((size_t)cur_img * 2 + plane) * p.N + n0 + nl, (unsigned long long)fx);
-              }
-            };
-#pragma unroll 1
-            for (int sub = 0; sub < M_SUB; ++sub) {
-              const int jj = sub * N_CHUNKS + j;
-              const int hw = jj & 1;   // which of a quarter's two warps handled this chunk
-#pragma unroll 1
-              for (int qq = 0; qq < 4; ++qq) {
-                const int row0 = mt0 + sub * BLOCK_M + qq * 32;
-                if (row0 >= p.M) break;
-                const int img = row0 / p.HW;
-                if (img != cur_img) {
-                  flush();
-                  acc = 0.f;
-                  cur_img = img;
-                }
-                const int wew = hw * 4 + ((qq - 2) & 3);
-                acc += stg_base[wew * L::WARP_STG_FLOATS + 32 * STG_LD + (jj >> 1) * (2 * CHUNK) + plane * CHUNK + cl];
-              }
-            }
-            flush();
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
     }
   }
