@@ -147,9 +147,11 @@ int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, float* 
  * hidden[net][(b*T+i)*T+j][c] = silu(e_t[b*T+i][net*C + c] + Wd[net][c][:]·feat(d_ij) + bd[net][c])
  * with d_ij = fi[b][i]-fi[b][j], feat = (log1p(max(d,0)), log1p(max(-d,0)), d==0).
  * e_t: [B*T][ld_et] holds embed_diffusion_time(temb) (+ its bias) of the 3 nets (q,k,v). */
-int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int64_t* frame_indices, const float* wd,
-                   const float* bd, int32_t B, int32_t T, int32_t C, void* out, int32_t out_dtype,
-                   vdm_stream_t stream);
+int vdm_rpe_hidden(const float* e_t, int32_t ld_et,
+                   const int32_t* et_offsets /* optional [n_blocks]: first e_t column of each block's (q,k,v) triple */,
+                   int32_t n_blocks /* attention blocks batched in this call; wd, bd, out hold 3*n_blocks nets */,
+                   const int64_t* frame_indices, const float* wd, const float* bd, int32_t B, int32_t T,
+                   int32_t C, void* out, int32_t out_dtype, vdm_stream_t stream);
 
 /* ---- temporal attention with in-kernel RPE bias (unet.py:477-536) -------------------------
  * qkv: [B*T*HW][3C] fp32 (row (b,t,pix); columns (3, heads, hd)); R_q/R_k/R_v: [B*T*T][C] fp32
@@ -172,9 +174,13 @@ int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, cons
  * P as bf16 [M][128*gpt] into a buffer whose padding columns the caller zeroed once, and PV fp32
  * [M][C]) and a last grouped vdm_gemm (P x bv, residual PV) for the attn.R_v term (unet.py:357-378). */
 int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v,
-                   const float* bias /* optional [3][C] (q, k, v) added to the tables */, int32_t B, int32_t T,
-                   int32_t heads, int32_t hd, int32_t groups_per_tile, void* bq, void* bk, void* bv,
-                   vdm_stream_t stream);
+                   const float* bias /* optional [n_blocks][3][C] (q, k, v) added to the tables */,
+                   int32_t n_blocks /* attention blocks batched in this call */,
+                   int64_t r_block_stride /* elements between consecutive blocks' tables */, int32_t B, int32_t T,
+                   int32_t heads, int32_t hd, int32_t groups_per_tile,
+                   int32_t zero_fill /* 1: write every element; 0: the caller zeroed bq/bk/bv once and only this
+                                        function (same shapes) writes them, so the structural zeros are skipped */,
+                   void* bq, void* bk, void* bv, vdm_stream_t stream);
 int vdm_attn_temporal_tc(const void* qkv, const float* sk, const float* sq, const float* mask,
                          int32_t allow_pad_interactions, int32_t B, int32_t T, int32_t HW,
                          int32_t heads, int32_t hd, int32_t groups_per_tile, void* pm, float* pv,

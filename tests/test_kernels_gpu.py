@@ -423,6 +423,43 @@ def test_rpe_hidden():
         assert relerr(out[net], ref) < 1e-5
 
 
+def test_rpe_tables_batched_over_blocks_equal_per_block_calls():
+    """n_blocks > 1 (the model's one-launch-per-(C, HW)-group path) is bit-identical to per-block launches."""
+    o = ops()
+    B, T, heads, hd, nb, HW = 2, 8, 4, 32, 3, 64
+    Cc, rows = heads * hd, B * T * T
+    width = 3 * Cc * nb + 40
+    e_t = rnd(B * T, width, seed=1)
+    offs = [40, 40 + 6 * Cc, 40 + 3 * Cc]                      # deliberately not in order
+    fi = torch.randint(0, 50, (B, T), generator=torch.Generator().manual_seed(0)).cuda()
+    wd, bd = rnd(nb * 3, Cc, 3, seed=2), rnd(nb * 3, Cc, seed=3)
+    hid = torch.empty(nb, 3, rows, Cc, device='cuda', dtype=torch.bfloat16)
+    o.rpe_hidden(e_t, fi, wd, bd, B, T, Cc, hid, et_offsets=torch.tensor(offs, dtype=torch.int32).cuda(), n_blocks=nb)
+    for i in range(nb):
+        one = torch.empty(3, rows, Cc, device='cuda', dtype=torch.bfloat16)
+        o.rpe_hidden(e_t[:, offs[i]:offs[i] + 3 * Cc], fi, wd[3 * i:3 * i + 3], bd[3 * i:3 * i + 3], B, T, Cc, one)
+        assert torch.equal(one, hid[i])
+    R = rnd(nb, 3, rows, Cc, seed=4, scale=0.5)
+    bias = rnd(nb, 3, Cc, seed=5)
+    gpt = 128 // HW
+    SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
+    bq = torch.empty(nb, ntg * SW, Cc, device='cuda', dtype=torch.bfloat16)
+    bk = torch.empty_like(bq)
+    bv = torch.empty(nb, ntg * Cc, SW, device='cuda', dtype=torch.bfloat16)
+    o.rpe_expand(R[0, 0], R[0, 1], R[0, 2], B, T, heads, hd, gpt, bq, bk, bv, bias=bias, n_blocks=nb,
+                 r_block_stride=3 * rows * Cc)
+    for i in range(nb):
+        q1, k1, v1 = torch.empty_like(bq[0]), torch.empty_like(bk[0]), torch.empty_like(bv[0])
+        o.rpe_expand(R[i, 0], R[i, 1], R[i, 2], B, T, heads, hd, gpt, q1, k1, v1, bias=bias[i])
+        assert torch.equal(q1, bq[i]) and torch.equal(k1, bk[i]) and torch.equal(v1, bv[i])
+    # zero_fill=False rewrites only the live (block-diagonal) entries of buffers that were zeroed once
+    zq, zk, zv = torch.zeros_like(bq), torch.zeros_like(bk), torch.zeros_like(bv)
+    for _ in range(2):
+        o.rpe_expand(R[0, 0], R[0, 1], R[0, 2], B, T, heads, hd, gpt, zq, zk, zv, bias=bias, n_blocks=nb,
+                     r_block_stride=3 * rows * Cc, zero_fill=False)
+    assert torch.equal(zq, bq) and torch.equal(zk, bk) and torch.equal(zv, bv)
+
+
 @pytest.mark.parametrize('respacing', ['', 'ddim10'])
 def test_sampler_kernels_match_oracle(respacing):
     from video_diffusion_b200.gaussian_diffusion import device_tables

@@ -61,10 +61,10 @@ def load():
         'vdm_add_spatial_encoding': [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
         'vdm_cond_mix': [_vp] * 6 + [_i32] * 4 + [_vp, _i32, _vp, _vp, _vp],
         'vdm_timestep_embedding': [_vp, _i32, _i32, _vp, _vp],
-        'vdm_rpe_hidden': [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
+        'vdm_rpe_hidden': [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
         'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
         'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
-        'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+        'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
         'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
         'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
         'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],

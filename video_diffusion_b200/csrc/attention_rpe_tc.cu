@@ -22,17 +22,19 @@ namespace {
 __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
                                                           const float* __restrict__ r_v,
                                                           const float* __restrict__ bias,   // [3][C] (q, k, v) or NULL
+                                                          long long r_block_stride, int tgs,   // batching over blocks
                                                           int G, int T, int heads, int hd, int gpt, float scale,
                                                           __nv_bfloat16* __restrict__ bq,
                                                           __nv_bfloat16* __restrict__ bk,
                                                           __nv_bfloat16* __restrict__ bv) {
   // one thread = 8 consecutive outputs (one 16-byte store)
   const int C = heads * hd, SW = 128 * gpt;
-  const int which = blockIdx.z;   // 0: Bk, 1: Bq, 2: Bv
+  const int which = blockIdx.z % 3;   // 0: Bk, 1: Bq, 2: Bv
+  const int blk = blockIdx.z / 3;     // attention block (tables / biases / outputs are strided by block)
   const int tg = blockIdx.y;
-  const float* R = which == 0 ? r_k : (which == 1 ? r_q : r_v);
-  const float* bs = bias ? bias + (which == 0 ? 1 : (which == 1 ? 0 : 2)) * C : nullptr;
-  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + (size_t)tg * SW * C;
+  const float* R = (which == 0 ? r_k : (which == 1 ? r_q : r_v)) + (size_t)blk * r_block_stride;
+  const float* bs = bias ? bias + ((size_t)blk * 3 + (which == 0 ? 1 : (which == 1 ? 0 : 2))) * C : nullptr;
+  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + ((size_t)blk * tgs + tg) * SW * C;
   const float mul = which == 1 ? scale : 1.0f;
   const int nvec = SW * C / 8;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
@@ -65,6 +67,65 @@ __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict
     pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
     pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
     reinterpret_cast<uint4*>(out)[v] = pk;
+  }
+}
+
+// The same operands when the buffers were zeroed once and keep their shape: only the live (block-diagonal) entries
+// are rewritten.  grid = (gpt * ceil(C / 64), tile groups, 3 * blocks).
+//   Bk / Bq: the CTAs of one tile group stride over its live 16-byte vectors (coalesced 32-byte reads of R)
+//   Bv     : CTA = one (b, t) group x 64 channels; the [T][64] slab of R is transposed through shared memory
+__global__ void __launch_bounds__(256) rpe_expand_live_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
+                                                               const float* __restrict__ r_v, const float* __restrict__ bias,
+                                                               long long r_block_stride, int tgs, int G, int T, int heads,
+                                                               int hd, int gpt, float scale, __nv_bfloat16* __restrict__ bq,
+                                                               __nv_bfloat16* __restrict__ bk, __nv_bfloat16* __restrict__ bv) {
+  __shared__ float tile[32][65];
+  const int C = heads * hd, SW = 128 * gpt;
+  const int which = blockIdx.z % 3, blk = blockIdx.z / 3, tg = blockIdx.y;
+  const float* R = (which == 0 ? r_k : (which == 1 ? r_q : r_v)) + (size_t)blk * r_block_stride;
+  const float* bs = bias ? bias + ((size_t)blk * 3 + (which == 0 ? 1 : (which == 1 ? 0 : 2))) * C : nullptr;
+  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + ((size_t)blk * tgs + tg) * SW * C;
+  if (which < 2) {
+    const float mul = which == 1 ? scale : 1.0f;
+    const int hd8 = hd / 8, HT = heads * T;
+    const int live = gpt * HT * hd8;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < live; v += gridDim.x * blockDim.x) {
+      const int rl = v / hd8, f = (v - rl * hd8) * 8;
+      const int sub = rl / HT, hj = rl - sub * HT;
+      const int h = hj / T, j = hj - h * T;
+      const int g = tg * gpt + sub;
+      if (g >= G) continue;
+      const int c = h * hd + f;
+      const float* src = R + ((size_t)g * T + j) * C + c;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = mul * (x[i] + (bs ? bs[c + i] : 0.f));
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(out + (size_t)(sub * 128 + hj) * C + c) = pk;
+    }
+  } else {
+    const int nchunk = (C + 63) / 64;
+    const int sub = blockIdx.x / nchunk, c0 = (blockIdx.x - sub * nchunk) * 64;
+    const int g = tg * gpt + sub;
+    if (g >= G) return;
+    const int cw = min(64, C - c0);               // channels in this chunk (multiple of 8)
+    const int v4 = cw / 4;
+    for (int i = threadIdx.x; i < T * v4; i += blockDim.x) {
+      const int j = i / v4, q = (i - j * v4) * 4;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(R + ((size_t)g * T + j) * C + c0 + q));
+      tile[j][q] = a.x; tile[j][q + 1] = a.y; tile[j][q + 2] = a.z; tile[j][q + 3] = a.w;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cw * T; i += blockDim.x) {
+      const int cl = i / T, j = i - cl * T;
+      const int c = c0 + cl;
+      const float val = tile[j][cl] + (bs ? bs[c] : 0.f);
+      out[(size_t)c * SW + sub * 128 + (c / hd) * T + j] = __float2bfloat16_rn(val);
+    }
   }
 }
 
@@ -275,8 +336,9 @@ int launch_attn(const void* qkv, const float* sk, const float* sq, const float* 
 
 using namespace vdm;
 
-extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t B,
-                              int32_t T, int32_t heads, int32_t hd, int32_t groups_per_tile, void* bq, void* bk,
+extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, const float* bias,
+                              int32_t n_blocks, int64_t r_block_stride, int32_t B, int32_t T, int32_t heads,
+                              int32_t hd, int32_t groups_per_tile, int32_t zero_fill, void* bq, void* bk,
                               void* bv, vdm_stream_t stream) {
   VDM_REQUIRE(r_q && r_k && r_v && bq && bk && bv, "rpe_expand: NULL pointer");
   VDM_REQUIRE(heads * T <= 128 && groups_per_tile >= 1, "rpe_expand: heads*T = %d must be <= 128", heads * T);
@@ -284,8 +346,18 @@ extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r
   const int tgs = (G + gpt - 1) / gpt;
   VDM_REQUIRE(hd % 8 == 0, "rpe_expand: head_dim must be a multiple of 8");
   const int nvec = 128 * gpt * heads * hd / 8;
-  dim3 grid(std::min((nvec + 255) / 256, 32), tgs, 3);
-  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
+  VDM_REQUIRE(n_blocks >= 1, "rpe_expand: n_blocks must be >= 1");
+  if (!zero_fill) {
+    VDM_REQUIRE(T <= 32, "rpe_expand: T=%d must be <= 32", T);
+    dim3 grid(gpt * ((heads * hd + 63) / 64), tgs, 3 * n_blocks);
+    rpe_expand_live_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, G, T, heads, hd,
+                                                                   gpt, 1.0f / sqrtf((float)hd), (__nv_bfloat16*)bq,
+                                                                   (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
+    VDM_AFTER_LAUNCH("rpe_expand");
+    return 0;
+  }
+  dim3 grid(std::min((nvec + 255) / 256, 32), tgs, 3 * n_blocks);
+  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
                                                             (__nv_bfloat16*)bq, (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
   VDM_AFTER_LAUNCH("rpe_expand");
   return 0;

@@ -349,41 +349,58 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
   if ((dim & 1) && i == 0) out[(size_t)row * dim + dim - 1] = 0.f;
 }
 
-// hidden[net][(b*T+i)*T+j][c]; one thread = 8 channels of one (net, row)
+// hidden[net][(b*T+i)*T+j][c]; one thread = 8 channels of one (net, b, i) and walks j, so the distance-embedding
+// weights, its bias and the diffusion-time term stay in registers (unet.py:283-296)
 template <typename OutT>
 __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict__ e_t, int ld_et,
+                                                          const int* __restrict__ et_off, int n_nets,
                                                           const long long* __restrict__ fi, const float* __restrict__ wd,
                                                           const float* __restrict__ bd, int B, int T, int C,
                                                           OutT* __restrict__ out) {
   const int C8 = C / 8;
-  const int rows = B * T * T;
-  const long long total = (long long)3 * rows * C8;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(v % C8) * 8;
-    const long long rr = v / C8;
-    const int row = (int)(rr % rows), net = (int)(rr / rows);
-    const int bi = row / T, j = row - bi * T;
+  const int BT = B * T;
+  const int total = n_nets * BT * C8;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+    const int c = (v % C8) * 8;
+    const int rr = v / C8;
+    const int bi = rr % BT, net = rr / BT;
     const int b = bi / T;
-    const long long d = fi[bi] - fi[b * T + j];
-    const float df = (float)d;
-    const float f0 = log1pf(fmaxf(df, 0.f)), f1 = log1pf(fmaxf(-df, 0.f)), f2 = (d == 0) ? 1.f : 0.f;
-    const float* et = e_t + (size_t)bi * ld_et + net * C + c;
-    float y[8];
+    // nets come in (q, k, v) triples, one triple per attention block; et_off gives each block's first column
+    const float* et = e_t + (size_t)bi * ld_et + (et_off ? et_off[net / 3] : 0) + (net % 3) * C + c;
+    float w0[8], w1[8], w2[8], base[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float* w = wd + ((size_t)net * C + c + i) * 3;
-      const float ed = fmaf(f2, w[2], fmaf(f1, w[1], f0 * w[0])) + bd[net * C + c + i];
-      y[i] = silu_precise(et[i] + ed);
+      w0[i] = w[0]; w1[i] = w[1]; w2[i] = w[2];
+      base[i] = bd[net * C + c + i];
     }
-    OutT* o = out + ((size_t)net * rows + row) * C + c;
-    if constexpr (sizeof(OutT) == 2) {
-      uint4 pk;
-      pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-      pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(o) = pk;
-    } else {
-      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    float e[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(et)), bb = __ldg(reinterpret_cast<const float4*>(et + 4));
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = bb.x; e[5] = bb.y; e[6] = bb.z; e[7] = bb.w;
+    }
+    const long long fi_i = fi[bi];
+    OutT* o = out + ((size_t)net * BT * T + (size_t)bi * T) * C + c;
+    for (int j = 0; j < T; ++j, o += C) {
+      const long long d = fi_i - fi[b * T + j];
+      const float df = (float)d;
+      const float f0 = log1pf(fmaxf(df, 0.f)), f1 = log1pf(fmaxf(-df, 0.f)), f2 = (d == 0) ? 1.f : 0.f;
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ed = fmaf(f2, w2[i], fmaf(f1, w1[i], f0 * w0[i])) + base[i];
+        const float x = e[i] + ed;
+        if constexpr (sizeof(OutT) == 2) y[i] = silu_f(x); else y[i] = silu_precise(x);
+      }
+      if constexpr (sizeof(OutT) == 2) {
+        uint4 pk;
+        pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+        pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(o) = pk;
+      } else {
+        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
     }
   }
 }
@@ -511,18 +528,22 @@ extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t d
   return 0;
 }
 
-extern "C" int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int64_t* frame_indices, const float* wd,
-                              const float* bd, int32_t B, int32_t T, int32_t C, void* out, int32_t out_dtype,
-                              vdm_stream_t stream) {
+extern "C" int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int32_t* et_offsets, int32_t n_blocks,
+                              const int64_t* frame_indices, const float* wd, const float* bd, int32_t B, int32_t T,
+                              int32_t C, void* out, int32_t out_dtype, vdm_stream_t stream) {
   VDM_REQUIRE(e_t && frame_indices && wd && bd && out, "rpe_hidden: NULL pointer");
   VDM_REQUIRE(C % 8 == 0, "rpe_hidden: C must be a multiple of 8");
-  const long long total = (long long)3 * B * T * T * (C / 8);
+  VDM_REQUIRE(n_blocks >= 1, "rpe_hidden: n_blocks must be >= 1");
+  VDM_REQUIRE(ld_et % 4 == 0 && ((uintptr_t)e_t & 15) == 0, "rpe_hidden: e_t rows must be 16-byte aligned");
+  const int n_nets = 3 * n_blocks;
+  const long long total = (long long)n_nets * B * T * (C / 8);
+  VDM_REQUIRE(total < (1LL << 31), "rpe_hidden: problem too large");
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
   if (out_dtype == VDM_BF16)
-    rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, (const long long*)frame_indices,
+    rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices,
                                                                             wd, bd, B, T, C, (__nv_bfloat16*)out);
   else
-    rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, (const long long*)frame_indices, wd, bd,
+    rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices, wd, bd,
                                                                     B, T, C, (float*)out);
   VDM_AFTER_LAUNCH("rpe_hidden");
   return 0;

@@ -119,10 +119,11 @@ def timestep_embedding(t_frame, dim, out):
         ptr(t_frame), t_frame.numel(), dim, ptr(out), stream()), 'vdm_timestep_embedding'))
 
 
-def rpe_hidden(e_t, frame_indices, wd, bd, B, T, Cc, out):
+def rpe_hidden(e_t, frame_indices, wd, bd, B, T, Cc, out, et_offsets=None, n_blocks=1):
+    """First layer of the RPE nets for n_blocks attention blocks at once (wd, bd, out hold 3*n_blocks nets)."""
     _timed('rpe_hidden', lambda: check(_lib.load().vdm_rpe_hidden(
-        e_t.data_ptr(), e_t.stride(0), ptr(frame_indices), ptr(wd), ptr(bd), B, T, Cc, ptr(out), dt(out.dtype),
-        stream()), 'vdm_rpe_hidden'), nbytes=_nbytes(out))
+        e_t.data_ptr(), e_t.stride(0), ptr(et_offsets), n_blocks, ptr(frame_indices), ptr(wd), ptr(bd), B, T, Cc,
+        ptr(out), dt(out.dtype), stream()), 'vdm_rpe_hidden'), nbytes=_nbytes(out))
 
 
 def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, out):
@@ -132,11 +133,11 @@ def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, o
            nbytes=_nbytes(qkv, out))
 
 
-def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv, bias=None):
+def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv, bias=None, n_blocks=1, r_block_stride=0,
+               zero_fill=True):
     _timed('rpe_expand', lambda: check(_lib.load().vdm_rpe_expand(
-        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), B, T, heads, hd, gpt, ptr(bq), ptr(bk), ptr(bv), stream()),
-        'vdm_rpe_expand'),
-           nbytes=_nbytes(bq, bk, bv))
+        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, B, T, heads, hd, gpt, int(zero_fill), ptr(bq), ptr(bk),
+        ptr(bv), stream()), 'vdm_rpe_expand'), nbytes=_nbytes(bq, bk, bv))
 
 
 def attn_temporal_tc(qkv, sk, sq, mask, pad_interact, B, T, HW, heads, hd, gpt, pm, pv):

@@ -385,7 +385,59 @@ class UNetModel(nn.Module):
                      out_f32=out, stats_out=st_out)
         return out, st_out
 
-    def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask):
+    def _tc_temporal_ok(self, T, C, HW):
+        heads = self.num_heads
+        return (self.compute_dtype == torch.bfloat16 and self.temporal_tensor_cores and heads * T <= 128 and T <= 32
+                and C // heads in (32, 64, 96, 128) and (HW % 128 == 0 or HW == 64))
+
+    def _rpe_tables(self, ws, rpe_et, B, T, H, W):
+        """RPE tables of every temporal-attention block, batched: the blocks that share (C, HW) go through ONE
+        rpe_hidden launch, ONE grouped output-layer GEMM and ONE expansion into the per-(b, t) GEMM operands
+        (unet.py:283-296, 357-378).  They depend only on the timestep embedding and the frame indices, so they are
+        computed ahead of the U-Net body.  Returns {block prefix: (bq, bk, bv)}."""
+        P, adt, heads = self._packed, self.compute_dtype, self.num_heads
+        rows = B * T * T
+        tables, groups = {}, {}
+        if rows % 128:
+            return tables
+        h, w = H, W
+        for node in self.plan:
+            if node['kind'] == 'down':
+                h, w = h // 2, w // 2
+            elif node['kind'] == 'up':
+                h, w = 2 * h, 2 * w
+            elif node['kind'] == 'attn' and self._tc_temporal_ok(T, node['C'], h * w):
+                groups.setdefault((node['C'], h * w), []).append(node)
+        for (C, HW), nodes in groups.items():
+            nb, key = len(nodes), f'rpe_group.{C}.{HW}'
+            if key + '.wd' not in P:
+                qs = [n['p'] + '.temporal_attention' for n in nodes]
+                P[key + '.wd'] = torch.cat([P[q + '.rpe_wd'] for q in qs]).contiguous()
+                P[key + '.bd'] = torch.cat([P[q + '.rpe_bd'] for q in qs]).contiguous()
+                P[key + '.out_w'] = torch.cat([P[q + '.rpe_out_w'] for q in qs]).contiguous()
+                P[key + '.out_b'] = torch.stack([P[q + '.rpe_out_b'] for q in qs]).contiguous()
+                P[key + '.et_off'] = torch.tensor([n['rpe_off'] for n in nodes], dtype=torch.int32, device=rpe_et.device)
+            hid = ws.buf(key + '.hid', (nb * 3 * rows, C), adt)
+            ops.rpe_hidden(rpe_et, ws.fi, P[key + '.wd'], P[key + '.bd'], B, T, C, hid, et_offsets=P[key + '.et_off'],
+                           n_blocks=nb)
+            Rall = ws.buf(key + '.R', (nb * 3 * rows, C))
+            ops.gemm(hid, P[key + '.out_w'], C, n_img=nb * 3 * rows, H=1, W=1, taps=1, out_f32=Rall,
+                     w_group_tiles=rows // 128)
+            gpt = 1 if HW >= 128 else 128 // HW
+            SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
+            # the operands are block-diagonal over heads (~85 % structural zeros): zeroed once with the workspace,
+            # afterwards only the live entries are rewritten
+            bq = ws.zeros(key + '.bq', (nb, ntg * SW, C), adt)
+            bk = ws.zeros(key + '.bk', (nb, ntg * SW, C), adt)
+            bv = ws.zeros(key + '.bv', (nb, ntg * C, SW), adt)
+            ops.rpe_expand(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, C // heads, gpt,
+                           bq, bk, bv, bias=P[key + '.out_b'], n_blocks=nb, r_block_stride=3 * rows * C,
+                           zero_fill=False)
+            for i, n in enumerate(nodes):
+                tables[n['p']] = (bq[i], bk[i], bv[i])
+        return tables
+
+    def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask, tables=None):
         P, adt, p, C = self._packed, self.compute_dtype, node['p'], node['C']
         h = x[0]
         HW, heads = H * W, self.num_heads
@@ -398,20 +450,13 @@ class UNetModel(nn.Module):
         xn = ws.buf(q + '.xn', (M, C))
         xa = ws.buf(q + '.xa', (M, C), adt)
         ops.gn_temporal(h, B, T, HW, C, P[q + '.gn_w'], P[q + '.gn_b'], xn, xa)
-        hid = ws.buf(q + '.hid', (3, B * T * T, C), adt)
-        off = node['rpe_off']
-        ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
-        tc_path = (adt == torch.bfloat16 and self.temporal_tensor_cores and heads * T <= 128 and T <= 32
-                   and hd in (32, 64, 96, 128) and (HW % 128 == 0 or HW == 64))
+        tc_path = self._tc_temporal_ok(T, C, HW)
         rows = B * T * T
-        if tc_path and rows % 128 == 0:
-            # the three RPE nets' output layers as ONE grouped GEMM (weights differ per net = per row block);
-            # their biases are added when the tables are expanded
-            Rall = ws.buf(q + '.Rall', (3 * rows, C))
-            ops.gemm(hid.view(3 * rows, C), P[q + '.rpe_out_w'], C, n_img=3 * rows, H=1, W=1, taps=1, out_f32=Rall,
-                     w_group_tiles=rows // 128)
-            R, r_bias = [Rall[i * rows:(i + 1) * rows] for i in range(3)], P[q + '.rpe_out_b']
-        else:
+        pre = tables.get(p) if tables else None
+        if pre is None:
+            hid = ws.buf(q + '.hid', (3, rows, C), adt)
+            off = node['rpe_off']
+            ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
             R, r_bias = [], None
             for i, r in enumerate(('rpe_q', 'rpe_k', 'rpe_v')):
                 Rn = ws.buf(f'{q}.{r}.R', (rows, C))
@@ -426,10 +471,13 @@ class UNetModel(nn.Module):
             SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
             qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
-            bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
-            bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
-            bv = ws.buf(q + '.bv', (ntg * C, SW), adt)
-            ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv, bias=r_bias)
+            if pre is not None:
+                bq, bk, bv = pre
+            else:
+                bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
+                bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
+                bv = ws.buf(q + '.bv', (ntg * C, SW), adt)
+                ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv, bias=r_bias)
             sk, sq = ws.buf(q + '.sk', (M, SW)), ws.buf(q + '.sq', (M, SW))
             ops.gemm(qkv[:, :C], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
             ops.gemm(qkv[:, C:2 * C], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
@@ -500,6 +548,8 @@ class UNetModel(nn.Module):
             ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
             ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
 
+        tables = self._rpe_tables(ws, rpe_et, B, F, H, W) if T_attn == F else None
+
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
         hs, x, cur_group, n_groups_done = [], None, None, 0
         in_groups = True
@@ -533,7 +583,7 @@ class UNetModel(nn.Module):
             elif kind == 'attn':
                 if T_attn != F:
                     raise NotImplementedError('cross_frame_attention=False')
-                x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask)
+                x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables)
             elif kind == 'down':
                 C = node['C']
                 out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C))
