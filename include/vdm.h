@@ -34,6 +34,11 @@ const char* vdm_last_error_string(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t vdm_launch_count(void);
 
+/* Diagnostics: when buf (device, >= 8 * grid u64) is non-NULL every later bf16 vdm_gemm launch writes per-CTA cycle
+ * counters [producer wait-empty, MMA wait-accumulator, MMA wait-operands, MMA total, epilogue wait, epilogue total].
+ * NULL switches it off (default). */
+void vdm_gemm_set_trace(void* buf);
+
 /* ---- implicit-GEMM convolution / linear ------------------------------------------------
  * Replaces nn.Conv2d 3x3 / 1x1 (unet.py:61, 90-95, 141, 156-160, 172-173, 618, 748) and
  * nn.Linear (unet.py:143-150, 418-419, 606-610, 274-277) together with the ops fused around

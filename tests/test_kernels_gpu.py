@@ -178,6 +178,25 @@ def test_linear_rowbias_nchw_and_silu(dtype):
     assert relerr(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3),
+                                       (4, 8, 8, 64, 3)])
+def test_output_head_conv_small_n(n, H, W, C1, N, monkeypatch):
+    """C -> 3 / 6 channel 3x3 conv with a planar (NCHW) store: the halo-tile mma.sync kernel and, for shapes it does
+    not take (8x8 here) or when switched off, the tcgen05 GEMM; both against conv2d on the same bf16-rounded data."""
+    o = ops()
+    x = rnd(n, C1, H, W, seed=1).bfloat16().float()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
+    b = rnd(N, seed=3)
+    ref = F.conv2d(x, w, b, padding=1)
+    for disable in (False, True):
+        if disable:
+            monkeypatch.setenv('VDM_NO_SMALL_N', '1')
+        out = torch.full((n, N, H, W), float('nan'), device='cuda')
+        o.gemm(nhwc(x).bfloat16(), pack_w(w).bfloat16(), N, n_img=n, H=H, W=W, taps=9, bias=b, out_f32=out,
+               out_nchw=True)
+        assert relerr(out, ref) < 2e-5
+
+
 def _chan_stats(x, dtype=torch.float64):
     """[n][2][C] per-(image, channel) sum and sum of squares of an NCHW tensor."""
     xd = x.double()

@@ -16,7 +16,7 @@ TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOG
            ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11)
 TAB_COUNT = 12
 
-EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
+EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
            'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
            'vdm_attn_temporal', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
            'vdm_prior_bpd']

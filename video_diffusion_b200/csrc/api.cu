@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream);
+void gemm_tc_set_trace(void* buf);
 int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream);
 
 }  // namespace vdm
@@ -24,6 +25,7 @@ int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream);
 extern "C" int vdm_version(void) { return 100; }
 extern "C" const char* vdm_last_error_string(void) { return vdm::g_err; }
 extern "C" int64_t vdm_launch_count(void) { return vdm::g_launches.load(); }
+extern "C" void vdm_gemm_set_trace(void* buf) { vdm::gemm_tc_set_trace(buf); }
 
 extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a != nullptr, "gemm: NULL args");

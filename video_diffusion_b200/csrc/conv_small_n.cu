@@ -1,0 +1,125 @@
+// 3x3 convolution with a handful of output channels (the U-Net's `out` head, unet.py:745-749: C -> 3 or 6).
+//
+// On the tcgen05 GEMM this layer wastes the tensor core (a 128 x 16 tile keeps 3 columns) and re-reads its
+// activation tile from L2 once per tap.  Here a CTA stages the 128-pixel tile WITH its one-pixel halo in shared
+// memory once (cp.async, zero fill outside the image = the conv padding), and each of its 8 warps computes
+// 16 pixels x 8 channels with mma.sync m16n8k16: ldmatrix takes one address per row, so the nine taps are just
+// nine different row addresses into the same halo tile.  Output is written planar (NCHW fp32), the layout the
+// sampler consumes.
+#include "common.cuh"
+
+namespace vdm {
+namespace {
+
+constexpr int TILE_PIX = 128;
+constexpr int PAD = 8;   // bf16 elements of padding per pixel / weight row: 16 B shifts keep ldmatrix conflict-free
+
+__device__ __forceinline__ void cp16_zfill(void* smem, const void* gmem, bool valid) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a), "l"(gmem), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat16* __restrict__ x,   // [n_img][H][W][C]
+                                                               const __nv_bfloat16* __restrict__ w,   // [N][9*C]
+                                                               const float* __restrict__ bias, int H, int W, int C,
+                                                               int N, float* __restrict__ out /* [n_img][N][H*W] */) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int R = TILE_PIX / W;                 // image rows per tile
+  const int Wp = W + 2, Cp = C + PAD;
+  __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem);                 // [(R+2)][Wp][Cp]
+  __nv_bfloat16* wsm = halo + (size_t)(R + 2) * Wp * Cp;                        // [9][8][Cp]
+  const int tiles_per_img = H * W / TILE_PIX;
+  const int img = blockIdx.x / tiles_per_img;
+  const int y0 = (blockIdx.x - img * tiles_per_img) * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C8 = C / 8;
+
+  // ---- stage the halo tile and the weights
+  const __nv_bfloat16* ximg = x + (size_t)img * H * W * C;
+  for (int i = tid; i < (R + 2) * Wp * C8; i += blockDim.x) {
+    const int c8 = i % C8, pix = i / C8;
+    const int xx = pix % Wp - 1, yy = y0 + pix / Wp - 1;
+    const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
+    cp16_zfill(halo + (size_t)pix * Cp + c8 * 8, ok ? ximg + ((size_t)yy * W + xx) * C + c8 * 8 : ximg, ok);
+  }
+  for (int i = tid; i < 9 * 8 * C8; i += blockDim.x) {
+    const int c8 = i % C8, n = (i / C8) % 8, tap = i / (8 * C8);
+    cp16_zfill(wsm + (size_t)(tap * 8 + n) * Cp + c8 * 8, n < N ? w + ((size_t)n * 9 + tap) * C + c8 * 8 : w, n < N);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- warp = 16 consecutive pixels of one image row
+  const int p0 = warp * 16;
+  const int ry = p0 / W, rx = p0 - ry * W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int a_row = lane & 15, a_k = (lane >> 4) * 8;       // ldmatrix.x4 row / k-half supplied by this lane
+  const int b_n = lane >> 2, b_k = (lane & 3) * 2;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;              // halo coordinates already include the -1
+    const __nv_bfloat16* arow = halo + ((size_t)(ry + dy) * Wp + rx + dx + a_row) * Cp + a_k;
+    const __nv_bfloat16* brow = wsm + (size_t)(tap * 8 + b_n) * Cp + b_k;
+#pragma unroll 4
+    for (int k0 = 0; k0 < C; k0 += 16) {
+      uint32_t a[4];
+      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(arow + k0);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + k0);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + k0 + 8);
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+          "{%0, %1, %2, %3};"
+          : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+  }
+  // accumulator layout: acc[0,1] = (row lane/4, cols 2*(lane%4) + {0,1}); acc[2,3] = row + 8
+  const int HW = H * W;
+  const int pix = (y0 + ry) * W + rx + (lane >> 2);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int n = (lane & 3) * 2 + e;
+    if (n < N) {
+      const float bv = bias ? bias[n] : 0.f;
+      float* o = out + ((size_t)img * N + n) * HW + pix;
+      o[0] = acc[e] + bv;
+      o[8] = acc[2 + e] + bv;
+    }
+  }
+}
+
+}  // namespace
+
+// Returns -100 if the shape is not handled here (the caller falls back to the tensor-core
+// GEMM), 0 on success.
+int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
+  const int W = a->W, H = a->H, C = a->C1, N = a->N;
+  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 16 == 0 && W >= 16 &&
+        W <= TILE_PIX && TILE_PIX % W == 0 && (H * W) % TILE_PIX == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
+        !a->rowbias && !a->stats_out))
+    return -100;
+  const int R = TILE_PIX / W;
+  const size_t smem = ((size_t)(R + 2) * (W + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16);
+  if (smem > 200 * 1024) return -100;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv3x3_small_n: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = smem;
+  }
+  const int grid = a->n_img * (H * W / TILE_PIX);
+  conv3x3_small_n_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->a1),
+                                                     reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, C, N,
+                                                     a->out_f32);
+  VDM_AFTER_LAUNCH("conv3x3_small_n");
+  return 0;
+}
+
+}  // namespace vdm

@@ -27,6 +27,13 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+// Diagnostics build (make TRACE=1): per-role cycle counters (vdm_gemm_set_trace) and the VDM_GEMM_DEBUG timing
+// experiments.  Off by default: the single MMA-issuing thread is the critical path and must stay branch-free.
+#ifdef VDM_GEMM_TRACE
+constexpr bool kTrace = true;
+#else
+constexpr bool kTrace = false;
+#endif
 
 struct TcParams {
   int M, N;
@@ -46,6 +53,8 @@ struct TcParams {
   int ld_out, ld_out_bf16;
   int out_nchw;
   int64_t* stats_out;
+  int dbg;                     // diagnostics (VDM_GEMM_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs (results are garbage)
+  unsigned long long* trace;   // diagnostics (vdm_gemm_set_trace): per-CTA wait / busy cycle counters, else NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -250,7 +259,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const TcParams p) {
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
-  static_assert(!CTA2 || M_SUB == 1, "2-CTA tiles are 256 x BLOCK_N: one 128-row sub-tile per CTA");
   constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);     // rows per work tile (CTA or CTA pair)
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader
   const int work_id0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -314,6 +322,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int k1 = p.taps * p.c1_chunks;
       int stage = 0;
       uint32_t phase = 0;
+      long long tr_wait = 0;
       for (int tile = work_id0; tile < n_tiles; tile += work_step) {
         int par = 0, tl = tile;
         if (p.a1_mode == 3) {
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           tl = tile - par * p.tiles_per_par;
         }
         const int n0 = (tl % n_tiles_n) * BLOCK_N;
-        const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
+        const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);   // a CTA's rows are contiguous
         int img0[M_SUB], y0[M_SUB], x0[M_SUB];
 #pragma unroll
         for (int sub = 0; sub < M_SUB; ++sub) {
@@ -335,9 +344,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+          if (kTrace && p.trace) {
+            const long long t0 = clock64();
+            mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+            tr_wait += clock64() - t0;
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+          }
           const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
           const uint32_t b_dst = a_dst + L::A_BYTES;
+          if (kTrace && (p.dbg & 1)) {        // timing experiment: operands are whatever the slot holds
+            if (cta_rank == 0) mbar_arrive(full_bar(stage));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           if constexpr (CTA2) {   // the leader's barrier counts the bytes landing in both CTAs
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * (L::A_BYTES + L::B_BYTES));
           } else {
@@ -371,8 +394,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           for (int sub = 0; sub < M_SUB; ++sub) {
             const uint32_t dst = a_dst + sub * L::A_SUB_BYTES;
             if constexpr (CTA2) {
-              if (!first_range) tma_load_5d_2cta(dst, &tm_a2, full_bar(stage), c0, m0, 0, 0, 0);
-              else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, m0, 0, 0, 0);
+              if (!first_range) tma_load_5d_2cta(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
               else tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
             } else {
               if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
           if constexpr (CTA2)   // this CTA's half of the weight tile
-            tma_load_2d_2cta(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + (int)cta_rank * (BLOCK_N / 2));
+            tma_load_2d_2cta(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + par * p.N + (int)cta_rank * (BLOCK_N / 2));
           else
             tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K,
                         n0 + par * p.N + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
@@ -391,6 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
       }
+      if (kTrace && p.trace) p.trace[blockIdx.x * 8 + 0] = (unsigned long long)tr_wait;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -399,24 +423,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long tr_acc = 0, tr_full = 0;
+      const long long tr_start = (kTrace && p.trace) ? clock64() : 0;
       for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);   // epilogue has drained this accumulator stage
+        if (kTrace && p.trace) {
+          const long long t0 = clock64();
+          mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);
+          tr_acc += clock64() - t0;
+        } else {
+          mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);   // epilogue has drained this accumulator stage
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * M_SUB * BLOCK_N);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase, 1);
+          if (kTrace && p.trace) {
+            const long long t0 = clock64();
+            mbar_wait(full_bar(stage), phase, 1);
+            tr_full += clock64() - t0;
+          } else {
+            mbar_wait(full_bar(stage), phase, 1);
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
           const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
           for (int sub = 0; sub < M_SUB; ++sub) {
+            if (kTrace && (p.dbg & 2)) break;
             const uint64_t a_desc = make_smem_desc(a_addr + sub * L::A_SUB_BYTES);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              if constexpr (CTA2) umma_bf16_2cta(tmem_acc, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+              if constexpr (CTA2) umma_bf16_2cta(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
               else umma_bf16(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
             }
           }
@@ -430,6 +469,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         if constexpr (CTA2) umma_commit_2cta(tmem_full_bar(as));   // accumulator complete (both CTAs' epilogues)
         else umma_commit(tmem_full_bar(as));
+      }
+      if (kTrace && p.trace) {
+        p.trace[blockIdx.x * 8 + 1] = (unsigned long long)tr_acc;
+        p.trace[blockIdx.x * 8 + 2] = (unsigned long long)tr_full;
+        p.trace[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - tr_start);
       }
     }
   } else {
@@ -451,6 +495,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     float* stg = stg_base + ew * L::WARP_STG_FLOATS;
     const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
     int it = 0;
+    long long tr_wait = 0;
+    const long long tr_start = (kTrace && p.trace) ? clock64() : 0;
     for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
       int par = 0, tl = tile;
       if (p.a1_mode == 3) {
@@ -458,7 +504,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         tl = tile - par * p.tiles_per_par;
       }
       const int n0 = (tl % n_tiles_n) * BLOCK_N;
-      const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
+      const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       float4 res_cur[NRES];
@@ -479,7 +525,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       // fetched one chunk ahead -- the first one while this tile's MMAs are still running
       constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
       if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
-      mbar_wait(tmem_full_bar(as), aphase, 2);
+      if (kTrace && p.trace) {
+        const long long t0 = clock64();
+        mbar_wait(tmem_full_bar(as), aphase, 2);
+        tr_wait += clock64() - t0;
+      } else {
+        mbar_wait(tmem_full_bar(as), aphase, 2);
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int jj = half; jj < TOTAL_CHUNKS; jj += 2) {
@@ -627,6 +679,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
         else mbar_arrive(tmem_empty_bar(as));
       }
+    }
+    if (kTrace && p.trace && ew == 0 && lane == 0) {
+      p.trace[blockIdx.x * 8 + 4] = (unsigned long long)tr_wait;
+      p.trace[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - tr_start);
     }
   }
 
@@ -777,10 +833,18 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
 }  // namespace
 
 int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream);
+int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream);   // conv_small_n.cu; -100 = shape not handled
+
+static unsigned long long* g_trace_buf = nullptr;
+void gemm_tc_set_trace(void* buf) { g_trace_buf = reinterpret_cast<unsigned long long*>(buf); }
 
 int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   const int64_t M = (int64_t)a->n_img * a->H * a->W;
   if (a->a1_mode == 3) return gemm_tc_upfold(a, stream);
+  if (a->out_nchw && a->N <= 8 && !getenv("VDM_NO_SMALL_N")) {
+    const int rc = conv3x3_small_n(a, stream);
+    if (rc != -100) return rc;
+  }
   VDM_REQUIRE(a->taps == 1 || a->taps == 9, "gemm_tc: taps must be 1 or 9");
   VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
   VDM_REQUIRE(a->C2 % BLOCK_K == 0, "gemm_tc: C2=%d must be a multiple of 64", a->C2);
@@ -808,6 +872,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   p.stats_out = a->stats_out;
   p.w_group_tiles = a->w_group_tiles;
+  p.trace = g_trace_buf;
+  if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE(a->w_group_tiles == 0 || (is_linear && a->C2 == 0 && !a->out_nchw), "gemm_tc: grouped weights need taps == 1");
   VDM_REQUIRE(a->lda1 == 0 || (is_linear && a->lda1 >= a->C1 && a->lda1 % 8 == 0), "gemm_tc: bad lda1");
 
@@ -862,14 +928,19 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   // memory, which is what limits the single-CTA kernel on long-K layers
   bool cta2 = false;
   {
-    int mode = 1;   // VDM_GEMM_CTA2: 0 = never, 1 = heuristic (default), 2 = whenever legal (tests)
+    int mode = 1;   // VDM_GEMM_CTA2: 0 = never, 1 = heuristic (default), 2 = whenever legal (tests), 3 = heuristic + 512x128 pair tiles
     if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
     const bool legal = !a->out_nchw && a->N % 128 == 0 && a->w_group_tiles == 0 && a->a1_mode <= 1;
     const int bn2 = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
     const int64_t pair_tiles = ((M + 255) / 256) * (a->N / bn2);
-    // measured: 256- and 192-wide pair tiles beat the single-CTA kernel by ~20 % on long-K layers, 128-wide
-    // pair tiles lose to the 256x128 single-CTA tile
-    cta2 = legal && mode > 0 && (mode >= 2 || (bn2 >= 192 && K >= 1024 && pair_tiles >= 40));
+    // Two measured ceilings (profiles/gemm_trace.py): TMA operand delivery from L2 saturates near 10 TB/s over
+    // the chip, and an N=128 MMA (both operands in shared memory) retires in ~112 cycles instead of 64, an N=256
+    // one in ~165 instead of 128.  So: 256- and 192-wide pair tiles beat the single-CTA kernel by ~20 % on
+    // long-K layers; 512x128 pair tiles only tie with the single-CTA 256x128 tile (mode 3 selects them); wide
+    // short-K linears (qkv, N >= 1024) gain 15-18 % from pair tiles.
+    cta2 = legal && mode > 0 &&
+           (mode == 2 || (bn2 >= 192 && pair_tiles >= 40 && (K >= 1024 || a->N >= 1024)) ||
+            (bn2 == 128 && m_sub == 2 && mode == 3));
     if (cta2) block_n = bn2;
   }
   {
@@ -883,6 +954,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   if (cta2) {
     if (block_n == 256) return launch<256, 1, 5, true>(ma1, ma2, mw, p, stream);
     if (block_n == 192) return launch<192, 1, 6, true>(ma1, ma2, mw, p, stream);
+    if (m_sub == 2) return launch<128, 2, 5, true>(ma1, ma2, mw, p, stream);
     return launch<128, 1, 7, true>(ma1, ma2, mw, p, stream);
   }
   switch (block_n) {
@@ -912,6 +984,8 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   p.a1_mode = 3; p.is_linear = 0; p.H = Hl; p.W = Wl; p.HW = HWl;
   p.bias = a->bias; p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.stats_out = a->stats_out;
+  p.trace = g_trace_buf;
+  if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE((Wl <= 128 && 128 % Wl == 0) || Wl % 128 == 0, "gemm_tc: unsupported width %d", Wl);
   uint32_t bw = Wl < 128 ? Wl : 128, bh = 1, bn = 1;
   if (Wl < 128) {
@@ -932,11 +1006,22 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   int rc = encode_map(&ma1, a->a1, 5, dims, st, box);
   if (rc) return rc;
   const int64_t K = 4 * (int64_t)a->C1;
+  // pair tiles (256 low-res pixels x 256 / 192 channels per parity) where the layer is wide enough
+  int mode = 1;
+  if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
+  const int bn2 = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 0);
+  const int64_t pair_tiles = bn2 ? ((M + 255) / 256) * (a->N / bn2) : 0;
+  const bool cta2 = mode > 0 && bn2 && 4 * pair_tiles >= 40;
   uint64_t wd[2] = {(uint64_t)K, (uint64_t)a->N * 4};
   uint64_t ws[2] = {2, (uint64_t)K * 2};
-  uint32_t wb[2] = {BLOCK_K, 128};
+  uint32_t wb[2] = {BLOCK_K, (uint32_t)(cta2 ? bn2 / 2 : 128)};
   rc = encode_map(&mw, a->w, 2, wd, ws, wb);
   if (rc) return rc;
+  if (cta2) {
+    p.tiles_per_par = (int)pair_tiles;
+    if (bn2 == 256) return launch_inst<256, 1, 5, 8, true>(ma1, ma1, mw, p, stream);
+    return launch_inst<192, 1, 6, 8, true>(ma1, ma1, mw, p, stream);
+  }
   const int64_t t2 = ((M + 255) / 256) * (a->N / 128), t1 = ((M + 127) / 128) * (a->N / 128);
   const int sms = num_sms();
   const bool two = (double)((4 * t2 + sms - 1) / sms) * 2.0 <= (double)((4 * t1 + sms - 1) / sms) * 1.35;
