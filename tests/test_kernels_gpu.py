@@ -107,6 +107,56 @@ def test_conv3x3(case, dtype):
     assert relerr(out_b, ref) < 6e-3
 
 
+HALO_CASES = [
+    # n, H, W, C1, N, C2, residual
+    (3, 64, 64, 128, 128, 0, True),      # 512-row pair tiles, M not a multiple of 512 * k -> ragged pair
+    (2, 64, 64, 64, 128, 128, False),    # fused 1x1 skip operand
+    (5, 32, 32, 128, 256, 0, False),     # 256-wide pair tiles
+    (4, 32, 32, 64, 256, 64, True),
+    (7, 16, 16, 192, 384, 0, True),      # 192-wide pair tiles, odd image count
+    (4, 16, 16, 64, 192, 0, False),
+    (6, 16, 32, 64, 128, 0, False),      # non-square image
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES, ids=lambda c: 'n%d_%dx%d_c%d_n%d_c2_%d_res%d' % c)
+def test_conv3x3_halo_kernel(case, monkeypatch):
+    """The halo variant of the 3x3 conv (vertical taps share one activation slot) against conv2d and against the
+    plain tcgen05 path (same products, different fp32 summation order), with statistics."""
+    n, H, W, C1, N, C2, use_res = case
+    o = ops()
+    x = rnd(n, C1, H, W, seed=1).bfloat16().float()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
+    bias = rnd(N, seed=3)
+    res = rnd(n * H * W, N, seed=4) if use_res else None
+    ref = F.conv2d(x, w, bias, padding=1)
+    wp, a2 = pack_w(w), None
+    if C2:
+        x2 = rnd(n, C2, H, W, seed=5).bfloat16().float()
+        w2 = rnd(N, C2, 1, 1, seed=6, scale=C2 ** -0.5).bfloat16().float()
+        ref = ref + F.conv2d(x2, w2)
+        wp = torch.cat([wp, w2.view(N, C2)], dim=1).contiguous()
+        a2 = nhwc(x2).bfloat16()
+    ref = nhwc(ref) + (res if use_res else 0)
+    outs = []
+    for mode in ('2', '0'):
+        monkeypatch.setenv('VDM_GEMM_HALO', mode)
+        out = torch.full((n * H * W, N), float('nan'), device='cuda')
+        st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+        o.gemm(nhwc(x).bfloat16(), wp.bfloat16(), N, n_img=n, H=H, W=W, taps=9, a2=a2, bias=bias, residual=res,
+               out_f32=out, stats_out=st, C1=C1)
+        assert relerr(out, ref) < 2e-5
+        outs.append((out, st))
+    assert relerr(outs[0][0], outs[1][0]) < 5e-6
+    assert relerr(outs[0][1].double(), outs[1][1].double()) < 1e-5
+    # bf16 output variant
+    monkeypatch.setenv('VDM_GEMM_HALO', '2')
+    out_b = torch.empty(n * H * W, N, device='cuda', dtype=torch.bfloat16)
+    o.gemm(nhwc(x).bfloat16(), wp.bfloat16(), N, n_img=n, H=H, W=W, taps=9, a2=a2, bias=bias, residual=res,
+           out_bf16=out_b, C1=C1)
+    assert relerr(out_b, ref) < 6e-3
+
+
 @pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128)])
 def test_upsample_conv_folded_into_parity_convs(case):
     """nearest-x2 + conv3x3 as four 2x2 convs on the low-res input (a1_mode 3) vs F.interpolate + F.conv2d."""

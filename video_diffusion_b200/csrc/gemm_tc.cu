@@ -244,6 +244,225 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;         // + alignment slack
 };
 
+// ===================== epilogue role (warps 2..9), shared by the kernels below =====================
+// tmem_full_bar0 / tmem_empty_bar0: shared-memory addresses of the two-entry barrier arrays of the accumulator stages.
+template <int BLOCK_N, int M_SUB, int EPI, bool CTA2>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base, uint32_t tmem_base,
+                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int n_tiles,
+                                              int n_tiles_n, int work_id0, int work_step, uint32_t cta_rank, int warp,
+                                              int lane) {
+  constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
+  constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
+  constexpr bool STATS = GEN || (EPI & 4) != 0;
+  auto tmem_full_bar = [&](int a) { return tmem_full_bar0 + 8u * a; };
+  auto tmem_empty_bar = [&](int a) { return tmem_empty_bar0 + 8u * a; };
+  // TMEM hands each lane one accumulator ROW; writing rows straight to global memory would touch
+  // 32 cache lines per instruction.  Each warp stages its 32 x CHUNK block in shared memory (row
+  // stride CHUNK+4 floats keeps 128-bit accesses conflict-free both ways) and re-reads it so that
+  // CHUNK/4 lanes cover one contiguous row segment: fully coalesced residual loads and stores.
+  constexpr int CHUNK = (BLOCK_N < 32 || M_SUB > 1) ? 16 : 32;
+  constexpr int N_CHUNKS = BLOCK_N / CHUNK;
+  constexpr int STG_LD = CHUNK + 4;
+  constexpr int LPR = CHUNK / 4;   // lanes per row
+  constexpr int RPI = 32 / LPR;    // rows per instruction
+  constexpr int NRES = 32 / RPI;   // float4 per lane per chunk
+  const int ew = warp - 2;
+  const int q = warp & 3;          // TMEM lane quarter this warp may access
+  const int half = ew >> 2;        // the two warps of a quarter split the column chunks
+  float* stg = stg_base + ew * (32 * (CHUNK + 4));
+  const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
+  int it = 0;
+  long long tr_wait = 0;
+  const long long tr_start = (kTrace && p.trace) ? clock64() : 0;
+  for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+    int par = 0, tl = tile;
+    if (p.a1_mode == 3) {
+      par = tile / p.tiles_per_par;
+      tl = tile - par * p.tiles_per_par;
+    }
+    const int n0 = (tl % n_tiles_n) * BLOCK_N;
+    const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    float4 res_cur[NRES];
+    // chunk index jj enumerates (sub-tile, column chunk): jj = sub * N_CHUNKS + j
+    auto load_residual = [&](float4 (&dst)[NRES], int jj) {
+      if constexpr (HAS_RES) {
+        const int m0 = mt0 + (jj / N_CHUNKS) * BLOCK_M;
+        const int n = n0 + (jj % N_CHUNKS) * CHUNK + c4;
+#pragma unroll
+        for (int i = 0; i < NRES; ++i) {
+          const int orow = m0 + q * 32 + i * RPI + r_sub;
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (orow < p.M && n < p.N)
+            dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
+        }
+      }
+    };
+    // fetched one chunk ahead -- the first one while this tile's MMAs are still running
+    constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
+    if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
+    if (kTrace && p.trace) {
+      const long long t0 = clock64();
+      mbar_wait(tmem_full_bar(as), aphase, 2);
+      tr_wait += clock64() - t0;
+    } else {
+      mbar_wait(tmem_full_bar(as), aphase, 2);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int jj = half; jj < TOTAL_CHUNKS; jj += 2) {
+      const int sub = jj / N_CHUNKS, j = jj - sub * N_CHUNKS;
+      const int m0 = mt0 + sub * BLOCK_M;
+      const int row = m0 + q * 32 + lane;
+      uint32_t acc[CHUNK];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                             (uint32_t)(as * M_SUB * BLOCK_N + sub * BLOCK_N + j * CHUNK);
+      if constexpr (CHUNK == 32) tmem_ld_32(taddr, acc);
+      else tmem_ld_16(taddr, acc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nb = n0 + j * CHUNK;
+      if (GEN && p.out_nchw) {  // lanes = consecutive pixels: already coalesced per channel
+        if (row < p.M) {
+          const int img = row / p.HW, pix = row - img * p.HW;
+          for (int i = 0; i < CHUNK; ++i) {
+            const int n = nb + i;
+            if (n < p.N) {
+              float v = __uint_as_float(acc[i]);
+              if (p.bias) v += p.bias[n];
+              p.out_f32[((size_t)img * p.N + n) * p.HW + pix] = v;
+            }
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < CHUNK; i += 4)
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + i) =
+            make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                        __uint_as_float(acc[i + 3]));
+      __syncwarp();
+      float4 res_next[NRES];
+      if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
+      const int n = nb + c4;
+      float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (!GEN) {
+        // lean path: N is a multiple of BLOCK_N, exactly one output, no per-image bias / row remap
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+        const int row_first = m0 + q * 32 + r_sub;
+        const bool full = m0 + BLOCK_M <= p.M;
+        const float* sp = stg + r_sub * STG_LD + c4;
+        float* o32 = nullptr;
+        __nv_bfloat16* o16 = nullptr;
+        if constexpr (BF16_OUT) o16 = p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n;
+        else o32 = p.out_f32 + (size_t)row_first * p.ld_out + n;
+#pragma unroll
+        for (int i = 0; i < NRES; ++i) {
+          if (full || row_first + i * RPI < p.M) {
+            float4 v = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if constexpr (HAS_RES) {
+              v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
+            }
+            if constexpr (STATS) {
+              ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+              ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+              ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+            }
+            if constexpr (BF16_OUT) {
+              uint2 pk;
+              pk.x = pack_bf16x2(v.x, v.y);
+              pk.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(o16 + (size_t)(i * RPI) * p.ld_out_bf16) = pk;
+            } else {
+              *reinterpret_cast<float4*>(o32 + (size_t)(i * RPI) * p.ld_out) = v;
+            }
+          }
+        }
+      } else if (n < p.N) {  // N is a multiple of 4 on this path
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += RPI) {
+          const int rl = rr + r_sub;
+          const int orow = m0 + q * 32 + rl;
+          if (orow < p.M) {
+            float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (p.rowbias) {
+              const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)(orow / p.HW) * p.ld_rowbias + n);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if constexpr (HAS_RES) {
+              const float4 r = res_cur[rr / RPI];
+              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+            ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+            ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+            size_t drow = (size_t)orow;
+            if (p.a1_mode == 3) {   // low-res pixel (img, y, x) of parity (a, b) -> high-res row
+              const int img = orow / p.HW, rem = orow - img * p.HW;
+              const int yy = rem / p.W, xx = rem - yy * p.W;
+              drow = ((size_t)img * 2 * p.H + 2 * yy + (par >> 1)) * (2 * p.W) + 2 * xx + (par & 1);
+            }
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
+            if (p.out_bf16) {
+              uint2 pk;
+              pk.x = pack_bf16x2(v.x, v.y);
+              pk.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(p.out_bf16 + drow * p.ld_out_bf16 + n) = pk;
+            }
+          }
+        }
+      }
+      if (STATS && p.stats_out != nullptr) {
+        // GroupNorm statistics of the stored tile: fold the lanes that share a column quad, then add this
+        // warp's 32-row partial sums to the per-(image, channel) table with 64-bit fixed-point atomics.
+        // Integer addition is associative, so the statistics (and everything downstream) are bit-reproducible
+        // from run to run without any cross-warp ordering.
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
+          ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
+          ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
+          ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
+        }
+        const int row0 = m0 + q * 32;      // the warp's 32 rows lie in one image (H*W % 32 == 0)
+        if (r_sub == 0 && n < p.N && row0 < p.M) {
+          unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) +
+                                    (size_t)(row0 / p.HW) * 2 * p.N + n;
+          const float sv[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const long long fx = __double2ll_rn((double)sv[e] * 16777216.0);
+            atomicAdd(tab + (e >> 2) * p.N + (e & 3), (unsigned long long)fx);
+          }
+        }
+      }
+      if constexpr (HAS_RES) {
+        if (jj + 2 < TOTAL_CHUNKS) {
+#pragma unroll
+          for (int i = 0; i < NRES; ++i) res_cur[i] = res_next[i];
+        }
+      }
+      __syncwarp();
+    }
+    // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA warp
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
+      else mbar_arrive(tmem_empty_bar(as));
+    }
+  }
+  if (kTrace && p.trace && ew == 0 && lane == 0) {
+    p.trace[blockIdx.x * 8 + 4] = (unsigned long long)tr_wait;
+    p.trace[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - tr_start);
+  }
+}
+
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every role loops over the CTA's
 // tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running together share A in L2).
 //   warp 0      : TMA producer (one lane), STAGES-deep smem ring
@@ -478,212 +697,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // TMEM hands each lane one accumulator ROW; writing rows straight to global memory would touch
-    // 32 cache lines per instruction.  Each warp stages its 32 x CHUNK block in shared memory (row
-    // stride CHUNK+4 floats keeps 128-bit accesses conflict-free both ways) and re-reads it so that
-    // CHUNK/4 lanes cover one contiguous row segment: fully coalesced residual loads and stores.
-    constexpr int CHUNK = L::CHUNK;
-    constexpr int N_CHUNKS = BLOCK_N / CHUNK;
-    constexpr int STG_LD = CHUNK + 4;
-    constexpr int LPR = CHUNK / 4;   // lanes per row
-    constexpr int RPI = 32 / LPR;    // rows per instruction
-    constexpr int NRES = 32 / RPI;   // float4 per lane per chunk
-    const int ew = warp - 2;
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;        // the two warps of a quarter split the column chunks
-    float* stg_base = reinterpret_cast<float*>(smem_gen + L::STG_OFFSET);
-    float* stg = stg_base + ew * L::WARP_STG_FLOATS;
-    const int r_sub = lane / LPR, c4 = (lane % LPR) * 4;
-    int it = 0;
-    long long tr_wait = 0;
-    const long long tr_start = (kTrace && p.trace) ? clock64() : 0;
-    for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
-      int par = 0, tl = tile;
-      if (p.a1_mode == 3) {
-        par = tile / p.tiles_per_par;
-        tl = tile - par * p.tiles_per_par;
-      }
-      const int n0 = (tl % n_tiles_n) * BLOCK_N;
-      const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      float4 res_cur[NRES];
-      // chunk index jj enumerates (sub-tile, column chunk): jj = sub * N_CHUNKS + j
-      auto load_residual = [&](float4 (&dst)[NRES], int jj) {
-        if constexpr (HAS_RES) {
-          const int m0 = mt0 + (jj / N_CHUNKS) * BLOCK_M;
-          const int n = n0 + (jj % N_CHUNKS) * CHUNK + c4;
-#pragma unroll
-          for (int i = 0; i < NRES; ++i) {
-            const int orow = m0 + q * 32 + i * RPI + r_sub;
-            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (orow < p.M && n < p.N)
-              dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
-          }
-        }
-      };
-      // fetched one chunk ahead -- the first one while this tile's MMAs are still running
-      constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
-      if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
-      if (kTrace && p.trace) {
-        const long long t0 = clock64();
-        mbar_wait(tmem_full_bar(as), aphase, 2);
-        tr_wait += clock64() - t0;
-      } else {
-        mbar_wait(tmem_full_bar(as), aphase, 2);
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int jj = half; jj < TOTAL_CHUNKS; jj += 2) {
-        const int sub = jj / N_CHUNKS, j = jj - sub * N_CHUNKS;
-        const int m0 = mt0 + sub * BLOCK_M;
-        const int row = m0 + q * 32 + lane;
-        uint32_t acc[CHUNK];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                               (uint32_t)(as * M_SUB * BLOCK_N + sub * BLOCK_N + j * CHUNK);
-        if constexpr (CHUNK == 32) tmem_ld_32(taddr, acc);
-        else tmem_ld_16(taddr, acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int nb = n0 + j * CHUNK;
-        if (GEN && p.out_nchw) {  // lanes = consecutive pixels: already coalesced per channel
-          if (row < p.M) {
-            const int img = row / p.HW, pix = row - img * p.HW;
-            for (int i = 0; i < CHUNK; ++i) {
-              const int n = nb + i;
-              if (n < p.N) {
-                float v = __uint_as_float(acc[i]);
-                if (p.bias) v += p.bias[n];
-                p.out_f32[((size_t)img * p.N + n) * p.HW + pix] = v;
-              }
-            }
-          }
-          continue;
-        }
-#pragma unroll
-        for (int i = 0; i < CHUNK; i += 4)
-          *reinterpret_cast<float4*>(stg + lane * STG_LD + i) =
-              make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
-                          __uint_as_float(acc[i + 3]));
-        __syncwarp();
-        float4 res_next[NRES];
-        if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
-        const int n = nb + c4;
-        float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (!GEN) {
-          // lean path: N is a multiple of BLOCK_N, exactly one output, no per-image bias / row remap
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
-          const int row_first = m0 + q * 32 + r_sub;
-          const bool full = m0 + BLOCK_M <= p.M;
-          const float* sp = stg + r_sub * STG_LD + c4;
-          float* o32 = nullptr;
-          __nv_bfloat16* o16 = nullptr;
-          if constexpr (BF16_OUT) o16 = p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n;
-          else o32 = p.out_f32 + (size_t)row_first * p.ld_out + n;
-#pragma unroll
-          for (int i = 0; i < NRES; ++i) {
-            if (full || row_first + i * RPI < p.M) {
-              float4 v = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              if constexpr (HAS_RES) {
-                v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
-              }
-              if constexpr (STATS) {
-                ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
-                ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
-                ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
-              }
-              if constexpr (BF16_OUT) {
-                uint2 pk;
-                pk.x = pack_bf16x2(v.x, v.y);
-                pk.y = pack_bf16x2(v.z, v.w);
-                *reinterpret_cast<uint2*>(o16 + (size_t)(i * RPI) * p.ld_out_bf16) = pk;
-              } else {
-                *reinterpret_cast<float4*>(o32 + (size_t)(i * RPI) * p.ld_out) = v;
-              }
-            }
-          }
-        } else if (n < p.N) {  // N is a multiple of 4 on this path
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int rr = 0; rr < 32; rr += RPI) {
-            const int rl = rr + r_sub;
-            const int orow = m0 + q * 32 + rl;
-            if (orow < p.M) {
-              float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              if (p.rowbias) {
-                const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)(orow / p.HW) * p.ld_rowbias + n);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              if constexpr (HAS_RES) {
-                const float4 r = res_cur[rr / RPI];
-                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-              }
-              ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
-              ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
-              ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
-              size_t drow = (size_t)orow;
-              if (p.a1_mode == 3) {   // low-res pixel (img, y, x) of parity (a, b) -> high-res row
-                const int img = orow / p.HW, rem = orow - img * p.HW;
-                const int yy = rem / p.W, xx = rem - yy * p.W;
-                drow = ((size_t)img * 2 * p.H + 2 * yy + (par >> 1)) * (2 * p.W) + 2 * xx + (par & 1);
-              }
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
-              if (p.out_bf16) {
-                uint2 pk;
-                pk.x = pack_bf16x2(v.x, v.y);
-                pk.y = pack_bf16x2(v.z, v.w);
-                *reinterpret_cast<uint2*>(p.out_bf16 + drow * p.ld_out_bf16 + n) = pk;
-              }
-            }
-          }
-        }
-        if (STATS && p.stats_out != nullptr) {
-          // GroupNorm statistics of the stored tile: fold the lanes that share a column quad, then add this
-          // warp's 32-row partial sums to the per-(image, channel) table with 64-bit fixed-point atomics.
-          // Integer addition is associative, so the statistics (and everything downstream) are bit-reproducible
-          // from run to run without any cross-warp ordering.
-#pragma unroll
-          for (int o = LPR; o < 32; o <<= 1) {
-            ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
-            ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
-            ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
-            ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
-          }
-          const int row0 = m0 + q * 32;      // the warp's 32 rows lie in one image (H*W % 32 == 0)
-          if (r_sub == 0 && n < p.N && row0 < p.M) {
-            unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) +
-                                      (size_t)(row0 / p.HW) * 2 * p.N + n;
-            const float sv[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const long long fx = __double2ll_rn((double)sv[e] * 16777216.0);
-              atomicAdd(tab + (e >> 2) * p.N + (e & 3), (unsigned long long)fx);
-            }
-          }
-        }
-        if constexpr (HAS_RES) {
-          if (jj + 2 < TOTAL_CHUNKS) {
-#pragma unroll
-            for (int i = 0; i < NRES; ++i) res_cur[i] = res_next[i];
-          }
-        }
-        __syncwarp();
-      }
-      // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA warp
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
-        else mbar_arrive(tmem_empty_bar(as));
-      }
-    }
-    if (kTrace && p.trace && ew == 0 && lane == 0) {
-      p.trace[blockIdx.x * 8 + 4] = (unsigned long long)tr_wait;
-      p.trace[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - tr_start);
-    }
+    epilogue_role<BLOCK_N, M_SUB, EPI, CTA2>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), tmem_base,
+                                             tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
+                                             work_step, cta_rank, warp, lane);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -699,6 +715,205 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                    "n"(tmem_cols<BLOCK_N, M_SUB>())
                    : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 3x3 stride-1 convolution, "halo" variant (always a CTA pair).
+//
+// The plain kernel fetches one shifted activation box per tap: nine L2 -> shared-memory copies of the same
+// pixels, and TMA operand delivery (~10 TB/s over the chip) is what bounds it.  Here one TMA box per
+// (64-channel chunk, horizontal shift dx) brings the CTA's R image rows PLUS the row above and below
+// ((R + 2) x W pixels, out-of-image rows / columns zero-filled = the padding).  The three vertical taps then
+// are the same shared-memory slot read at a start offset of dy * W pixel rows (W * 128 B, a multiple of the
+// 1024 B swizzle atom for W >= 8), so A traffic drops from 9 to 3 * (R + 2) / R tile loads per chunk.
+// Activation slots and weight tiles travel in two independent mbarrier rings (SA x A_SLOT, SB x B_SLOT);
+// an optional second operand (fused 1x1 skip projection) appends plain 128-row tiles to the same rings.
+template <int BLOCK_N, int M_SUB, int SA, int SB>
+struct HaloLayout {
+  static constexpr int CHUNK = (M_SUB > 1) ? 16 : 32;
+  static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_SLOT = (M_SUB + 1) * A_SUB_BYTES;   // (R + 2) * W <= M_SUB * 128 + 128 pixels for W <= 64
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the weight tile
+  static constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_OFFSET = SA * A_SLOT;
+  static constexpr int STG_OFFSET = B_OFFSET + SB * B_SLOT;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
+                                                                      const __grid_constant__ CUtensorMap tm_a2,
+                                                                      const __grid_constant__ CUtensorMap tm_w,
+                                                                      const TcParams p) {
+  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB>;
+  constexpr int CTA_ROWS = BLOCK_M * M_SUB;
+  constexpr int TILE_M = 2 * CTA_ROWS;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int work_id0 = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = p.N / BLOCK_N;
+  const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
+  const int halo_rows = CTA_ROWS / p.W + 2;
+  const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * SA + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS * 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(tmem_cols<BLOCK_N, M_SUB>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      auto load_b = [&](int k_elem, int n0) {
+        mbar_wait(b_empty(sb), pb ^ 1u, 4);
+        if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::B_BYTES);
+        tma_load_2d_2cta(smem_base + L::B_OFFSET + sb * L::B_SLOT, &tm_w, b_full(sb), k_elem,
+                         n0 + (int)cta_rank * (BLOCK_N / 2));
+        if (++sb == SB) {
+          sb = 0;
+          pb ^= 1u;
+        }
+      };
+      for (int tile = work_id0; tile < n_tiles; tile += work_step) {
+        const int n0 = (tile % n_tiles_n) * BLOCK_N;
+        const int m0 = (tile / n_tiles_n) * TILE_M + (int)cta_rank * CTA_ROWS;
+        const int img = m0 / p.HW;
+        const int y0 = (m0 - img * p.HW) / p.W;
+        for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(a_empty(sa), pa ^ 1u, 0);
+            if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * halo_bytes);
+            tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            if (++sa == SA) {
+              sa = 0;
+              pa ^= 1u;
+            }
+            for (int dy = 0; dy < 3; ++dy) load_b(((dy * 3 + dx) * p.c1_chunks + chunk) * BLOCK_K, n0);
+          }
+        }
+        for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          mbar_wait(a_empty(sa), pa ^ 1u, 0);
+          if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * M_SUB * L::A_SUB_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < M_SUB; ++sub)
+            tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                             m0 + sub * BLOCK_M, 0, 0, 0);
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+          load_b((9 * p.c1_chunks + chunk) * BLOCK_K, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = instr_desc<BLOCK_N, 256>();
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      const uint32_t dy_bytes = (uint32_t)p.W * (BLOCK_K * 2);   // one image row of the halo slot
+      for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * M_SUB * BLOCK_N);
+        uint32_t accumulate = 0;
+        // one weight tile against the activation rows starting at a_addr (per sub-tile: + 128 pixel rows)
+        auto mma_block = [&](uint32_t a_addr) {
+          mbar_wait(b_full(sb), pb, 5);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t b_desc = make_smem_desc(smem_base + L::B_OFFSET + sb * L::B_SLOT);
+#pragma unroll
+          for (int sub = 0; sub < M_SUB; ++sub) {
+            const uint64_t a_desc = make_smem_desc(a_addr + sub * L::A_SUB_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_2cta(tmem_acc + (uint32_t)(sub * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc,
+                             accumulate | (uint32_t)k);   // each sub-tile's first MMA of the tile overwrites
+          }
+          accumulate = 1;
+          umma_commit_2cta(b_empty(sb));
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1u;
+          }
+        };
+        const int n_units = 3 * p.c1_chunks;
+        for (int u = 0; u < n_units; ++u) {
+          mbar_wait(a_full(sa), pa, 1);
+          const uint32_t a_slot = smem_base + sa * L::A_SLOT;
+          for (int dy = 0; dy < 3; ++dy) mma_block(a_slot + dy * dy_bytes);
+          umma_commit_2cta(a_empty(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          mbar_wait(a_full(sa), pa, 1);
+          mma_block(smem_base + sa * L::A_SLOT);
+          umma_commit_2cta(a_empty(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        umma_commit_2cta(tmem_full_bar(as));
+      }
+    }
+  } else {
+    epilogue_role<BLOCK_N, M_SUB, EPI, true>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), tmem_base,
+                                             tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
+                                             work_step, cta_rank, warp, lane);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(tmem_cols<BLOCK_N, M_SUB>())
+                 : "memory");
   }
 }
 
@@ -830,6 +1045,62 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
   }
 }
 
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI>
+int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                     cudaStream_t stream) {
+  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  constexpr int TILE_ROWS = 2 * BLOCK_M * M_SUB;
+  const int tiles = (p.N / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS);
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI>, mh, ma2, mw, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc (halo): launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  VDM_AFTER_LAUNCH("gemm_tc_halo");
+  return 0;
+}
+
+template <int BLOCK_N, int M_SUB, int SA, int SB>
+int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                cudaStream_t stream) {
+  switch (epilogue_variant(p, BLOCK_N)) {
+    case 0: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 0>(mh, ma2, mw, p, stream);
+    case 1: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 1>(mh, ma2, mw, p, stream);
+    case 2: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 2>(mh, ma2, mw, p, stream);
+    case 3: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 3>(mh, ma2, mw, p, stream);
+    case 4: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 4>(mh, ma2, mw, p, stream);
+    case 5: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 5>(mh, ma2, mw, p, stream);
+    case 6: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 6>(mh, ma2, mw, p, stream);
+    case 7: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 7>(mh, ma2, mw, p, stream);
+    case 9: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 9>(mh, ma2, mw, p, stream);
+    default: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 8>(mh, ma2, mw, p, stream);
+  }
+}
+
 }  // namespace
 
 int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream);
@@ -912,6 +1183,35 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     ma2 = ma1;
   }
   const int64_t K = (int64_t)a->taps * a->C1 + a->C2;
+  // 3x3 stride-1 layers whose CTA tile is a whole number of image rows inside one image: halo kernel (the three
+  // vertical taps share one activation slot); VDM_GEMM_HALO=0 switches it off
+  {
+    const char* e = getenv("VDM_GEMM_HALO");   // 0 off, 1 heuristic (default), 2 whenever legal (tests)
+    const int hmode = e ? atoi(e) : 1;
+    const int bn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 0));
+    const int msub = bn == 128 ? 2 : 1;
+    const int rows = BLOCK_M * msub;
+    const bool ok = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
+                    bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
+                    (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
+    if (ok) {
+      CUtensorMap mh, mw2;
+      const uint64_t C = a->C1;
+      uint64_t dims[5] = {C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->n_img};
+      uint64_t st[5] = {2, C * 2, C * 2 * a->W, C * 2 * a->W * a->H, C * 2 * a->W * a->H};
+      uint32_t box[5] = {BLOCK_K, (uint32_t)a->W, (uint32_t)(rows / a->W + 2), 1, 1};
+      rc = encode_map(&mh, a->a1, 5, dims, st, box);
+      if (rc) return rc;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      uint32_t wbox[2] = {BLOCK_K, (uint32_t)(bn / 2)};
+      rc = encode_map(&mw2, a->w, 2, wdims, wst, wbox);
+      if (rc) return rc;
+      if (bn == 256) return launch_halo<256, 1, 3, 5>(mh, ma2, mw2, p, stream);
+      if (bn == 192) return launch_halo<192, 1, 3, 6>(mh, ma2, mw2, p, stream);
+      return launch_halo<128, 2, 3, 6>(mh, ma2, mw2, p, stream);
+    }
+  }
   int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
   // 256x128 CTA tiles (two 128-row sub-tiles sharing every weight tile) halve the L2->smem operand
   // traffic per FLOP; use them unless the layer is too small to fill the SMs that way.
