@@ -69,6 +69,7 @@ class UNetModel(nn.Module):
         self.compute_dtype = compute_dtype or torch.bfloat16
         self.use_cuda_graph = True
         self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
+        self.overlap_rpe_tables = True    # RPE tables on a side stream, concurrent with the first U-Net blocks
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
@@ -301,6 +302,7 @@ class UNetModel(nn.Module):
             self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
             self.pool_used = 0
             self.out = None
+            self.side = self.ev_fork = self.ev_join = None
 
         def buf(self, name, shape, dtype=torch.float32):
             b = self.bufs.get(name)
@@ -548,7 +550,22 @@ class UNetModel(nn.Module):
             ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
             ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
 
-        tables = self._rpe_tables(ws, rpe_et, B, F, H, W) if T_attn == F else None
+        # The RPE tables depend only on the embedding: fork them onto a side stream (a parallel branch of the CUDA
+        # graph) so they fill the gaps of the first blocks; joined right before the first attention block.
+        tables, rpe_join = None, None
+        if T_attn == F:
+            if self.overlap_rpe_tables and ops.PROFILE is None:
+                main = torch.cuda.current_stream()
+                if ws.side is None:
+                    ws.side, ws.ev_fork, ws.ev_join = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+                ws.ev_fork.record(main)
+                ws.side.wait_event(ws.ev_fork)
+                with torch.cuda.stream(ws.side):
+                    tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
+                    ws.ev_join.record(ws.side)
+                rpe_join = ws.ev_join
+            else:
+                tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
         hs, x, cur_group, n_groups_done = [], None, None, 0
@@ -583,6 +600,9 @@ class UNetModel(nn.Module):
             elif kind == 'attn':
                 if T_attn != F:
                     raise NotImplementedError('cross_frame_attention=False')
+                if rpe_join is not None:
+                    torch.cuda.current_stream().wait_event(rpe_join)
+                    rpe_join = None
                 x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables)
             elif kind == 'down':
                 C = node['C']
@@ -617,6 +637,8 @@ class UNetModel(nn.Module):
                     ops.gemm(x[0], P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
                              out_f32=out, C1=C)
                 x, H, W = (out, st), 2 * H, 2 * W
+        if rpe_join is not None:          # no attention block consumed the tables: still join the branch
+            torch.cuda.current_stream().wait_event(rpe_join)
         h = x[0]
         st = self._stats_of(ws, 'out', h, x[1], N, H * W)
         a = ws.buf('out.a', (N * H * W, ch), adt)
