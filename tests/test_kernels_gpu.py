@@ -319,9 +319,11 @@ def test_gemm_epilogue_groupnorm_statistics():
         assert torch.equal(st, st2)          # integer accumulation: bit-reproducible
 
 
-def test_groupnorm_temporal_and_spatial_encoding():
+@pytest.mark.parametrize('B,T,HW,Cc', [(2, 5, 16, 64), (2, 20, 64, 384), (3, 7, 16, 512), (1, 32, 4, 128),
+                                        (2, 20, 16, 640), (2, 33, 4, 128), (2, 6, 16, 192)])
+def test_groupnorm_temporal_and_spatial_encoding(B, T, HW, Cc):
+    """Both temporal GroupNorm kernels: the register-resident single pass (C % 128 == 0, T <= 32) and the general one."""
     o = ops()
-    B, T, HW, Cc = 2, 5, 16, 64
     x = rnd(B, T, HW, Cc, seed=1) + 0.3
     gamma, beta = rnd(Cc, seed=2), rnd(Cc, seed=3)
     xr = x.permute(0, 2, 3, 1).reshape(B * HW, Cc, T)              # (B*D, C, T) as the reference

@@ -35,13 +35,23 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C8 = C / 8;
 
-  // ---- stage the halo tile and the weights
+  // ---- stage the halo tile and the weights (index = pixel * C8 + chunk, advanced without divisions)
   const __nv_bfloat16* ximg = x + (size_t)img * H * W * C;
-  for (int i = tid; i < (R + 2) * Wp * C8; i += blockDim.x) {
-    const int c8 = i % C8, pix = i / C8;
-    const int xx = pix % Wp - 1, yy = y0 + pix / Wp - 1;
-    const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
-    cp16_zfill(halo + (size_t)pix * Cp + c8 * 8, ok ? ximg + ((size_t)yy * W + xx) * C + c8 * 8 : ximg, ok);
+  {
+    const int total = (R + 2) * Wp * C8;
+    const int step_pix = (int)blockDim.x / C8, step_c8 = (int)blockDim.x % C8;
+    const int step_y = step_pix / Wp, step_x = step_pix % Wp;
+    int c8 = tid % C8, pix = tid / C8;
+    int hy = pix / Wp, hx = pix % Wp;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int xx = hx - 1, yy = y0 + hy - 1;
+      const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
+      cp16_zfill(halo + (size_t)pix * Cp + c8 * 8, ok ? ximg + ((size_t)yy * W + xx) * C + c8 * 8 : ximg, ok);
+      c8 += step_c8; pix += step_pix; hx += step_x; hy += step_y;
+      if (c8 >= C8) { c8 -= C8; ++pix; ++hx; }
+      if (hx >= Wp) { hx -= Wp; ++hy; }
+      if (hx >= Wp) { hx -= Wp; ++hy; }
+    }
   }
   for (int i = tid; i < 9 * 8 * C8; i += blockDim.x) {
     const int c8 = i % C8, n = (i / C8) % 8, tap = i / (8 * C8);
@@ -54,7 +64,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
   // ---- warp = 16 consecutive pixels of one image row
   const int p0 = warp * 16;
   const int ry = p0 / W, rx = p0 - ry * W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two chains: even / odd k-steps
   const int a_row = lane & 15, a_k = (lane >> 4) * 8;       // ldmatrix.x4 row / k-half supplied by this lane
   const int b_n = lane >> 2, b_k = (lane & 3) * 2;
 #pragma unroll 1
@@ -62,21 +72,32 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
     const int dy = tap / 3, dx = tap - dy * 3;              // halo coordinates already include the -1
     const __nv_bfloat16* arow = halo + ((size_t)(ry + dy) * Wp + rx + dx + a_row) * Cp + a_k;
     const __nv_bfloat16* brow = wsm + (size_t)(tap * 8 + b_n) * Cp + b_k;
-#pragma unroll 4
-    for (int k0 = 0; k0 < C; k0 += 16) {
-      uint32_t a[4];
+#pragma unroll 2
+    for (int k0 = 0; k0 < C; k0 += 32) {
+      uint32_t a[4], a2[4];
       const uint32_t addr = (uint32_t)__cvta_generic_to_shared(arow + k0);
       asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                    : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a2[0]), "=r"(a2[1]), "=r"(a2[2]), "=r"(a2[3]) : "r"(addr + 32u));
       const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + k0);
       const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + k0 + 8);
+      const uint32_t b2 = *reinterpret_cast<const uint32_t*>(brow + k0 + 16);
+      const uint32_t b3 = *reinterpret_cast<const uint32_t*>(brow + k0 + 24);
       asm volatile(
           "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
           "{%0, %1, %2, %3};"
           : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
           : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+          "{%0, %1, %2, %3};"
+          : "+f"(acc2[0]), "+f"(acc2[1]), "+f"(acc2[2]), "+f"(acc2[3])
+          : "r"(a2[0]), "r"(a2[1]), "r"(a2[2]), "r"(a2[3]), "r"(b2), "r"(b3));
     }
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
   // accumulator layout: acc[0,1] = (row lane/4, cols 2*(lane%4) + {0,1}); acc[2,3] = row + 8
   const int HW = H * W;
   const int pix = (y0 + ry) * W + rx + (lane >> 2);
@@ -98,7 +119,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
 // GEMM), 0 on success.
 int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   const int W = a->W, H = a->H, C = a->C1, N = a->N;
-  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 16 == 0 && W >= 16 &&
+  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 32 == 0 && W >= 16 &&
         W <= TILE_PIX && TILE_PIX % W == 0 && (H * W) % TILE_PIX == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
         !a->rowbias && !a->stats_out))
     return -100;

@@ -267,6 +267,68 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
   }
 }
 
+// Single-pass variant for C % 128 == 0 and T <= 32: a warp owns one (b, pixel, slab of `gps` groups); each lane keeps
+// its float4 column of all T frames in registers, the lanes of a group fold their sums with shuffles, and the values
+// are normalised and written without touching memory twice.  B * HW * n_slabs warps: enough parallelism for the
+// 8x8 level too (the kernel above launches only B * HW / 8 blocks there).
+template <typename OutT>
+__global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __restrict__ x, int B, int T, int HW, int C,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                float* __restrict__ out_f32, OutT* __restrict__ out_a,
+                                                                int gps, int n_slabs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * 4 + warp;
+  if (wg >= (long long)B * HW * n_slabs) return;
+  const int slab = (int)(wg % n_slabs);
+  const int pix = (int)((wg / n_slabs) % HW), b = (int)(wg / ((long long)n_slabs * HW));
+  const int cpg = C / 32, l4 = cpg / 4;            // channels / float4 lanes per group
+  const int g = slab * gps + lane / l4;
+  const bool active = lane / l4 < gps && g < 32;
+  const int c = active ? g * cpg + (lane % l4) * 4 : 0;
+  const size_t frame_stride = (size_t)HW * C;
+  const size_t off0 = (size_t)b * T * frame_stride + (size_t)pix * C + c;
+  float4 v[32];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t < T && active) {
+      v[t] = __ldg(reinterpret_cast<const float4*>(x + off0 + t * frame_stride));
+      s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+      q = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, q))));
+    }
+  }
+  float gs = 0.f, gq = 0.f;
+  const int base = lane - lane % l4;
+  for (int j = 0; j < l4; ++j) {
+    gs += __shfl_sync(0xffffffffu, s, (base + j) & 31);
+    gq += __shfl_sync(0xffffffffu, q, (base + j) & 31);
+  }
+  if (!active) return;
+  const float cnt = (float)(T * cpg);
+  const float mean = gs / cnt;
+  const float rstd = rsqrtf(fmaxf(gq / cnt - mean * mean, 0.f) + 1e-5f);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+  const float a0 = rstd * gm.x, a1 = rstd * gm.y, a2 = rstd * gm.z, a3 = rstd * gm.w;
+  const float b0 = bt.x - mean * a0, b1 = bt.y - mean * a1, b2 = bt.z - mean * a2, b3 = bt.w - mean * a3;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t < T) {
+      const size_t off = off0 + t * frame_stride;
+      const float y0 = fmaf(v[t].x, a0, b0), y1 = fmaf(v[t].y, a1, b1), y2 = fmaf(v[t].z, a2, b2), y3 = fmaf(v[t].w, a3, b3);
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 pk;
+        pk.x = pack_bf16x2(y0, y1);
+        pk.y = pack_bf16x2(y2, y3);
+        *reinterpret_cast<uint2*>(out_a + off) = pk;
+      } else {
+        *reinterpret_cast<float4*>(out_a + off) = make_float4(y0, y1, y2, y3);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* h, const float* __restrict__ enc,
                                                                     float* out, long long total4, long long per_img4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
@@ -476,6 +538,22 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
                                const float* beta, float* out_f32, void* out_a, int32_t out_dtype, vdm_stream_t stream) {
   VDM_REQUIRE(x && gamma && beta && out_a, "gn_temporal: NULL pointer");
   VDM_REQUIRE(C % 32 == 0 && C <= 1024, "gn_temporal: C=%d must be a multiple of 32, <= 1024", C);
+  if (C % 128 == 0 && T <= 32) {   // register-resident single pass
+    const int l4 = C / 128;                       // float4 lanes per group
+    int gps = 32 / l4;                            // groups a warp can hold ...
+    while (32 % gps) --gps;                       // ... evened out so every slab has the same number
+    const int n_slabs = 32 / gps;
+    const long long warps = (long long)B * HW * n_slabs;
+    const unsigned grid = (unsigned)((warps + 3) / 4);
+    if (out_dtype == VDM_BF16)
+      gn_temporal_regs_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32,
+                                                                                  (__nv_bfloat16*)out_a, gps, n_slabs);
+    else
+      gn_temporal_regs_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32,
+                                                                          (float*)out_a, gps, n_slabs);
+    VDM_AFTER_LAUNCH("gn_temporal");
+    return 0;
+  }
   dim3 grid((HW + 7) / 8, B);
   const size_t smem = 8 * (2 * (size_t)C + 64) * sizeof(float);
   if (out_dtype == VDM_BF16) {

@@ -299,6 +299,17 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         }
       }
     };
+    // The residual tile (up to 128 KB) is far more than the one-chunk-ahead register prefetch below keeps in
+    // flight, which made the residual read latency-bound (~1.6 TB/s).  Pull the whole tile into L2 now, while
+    // this tile's MMAs are still running; the LDGs below then hit L2.
+    if constexpr (HAS_RES) {
+      constexpr int LINES_PER_ROW = BLOCK_N / 32;   // 128-byte lines per tile row
+      for (int i = ew * 32 + lane; i < M_SUB * BLOCK_M * LINES_PER_ROW; i += EPI_WARPS * 32) {
+        const int row = mt0 + i / LINES_PER_ROW, n = n0 + (i % LINES_PER_ROW) * 32;
+        if (row < p.M && n < p.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)row * p.ld_res + n));
+      }
+    }
     // fetched one chunk ahead -- the first one while this tile's MMAs are still running
     constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
     if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
