@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Three representative gemm_tc launches for an ncu capture: python profiles/gemm_ncu_probe.py"""
+"""Representative tcgen05 GEMM launches of the C2 step for an ncu capture (halo conv kernel at the 64x64 / 32x32 /
+16x16 levels, the plain pair-tile kernel at 8x8, the qkv and proj linears): python profiles/gemm_ncu_probe.py"""
 import os
 import sys
 
@@ -10,7 +11,11 @@ from video_diffusion_b200 import ops  # noqa: E402
 
 dev = 'cuda'
 N_IMG = 160
-for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_128_128', 64, 64, 128, 128, 9, False, False),
+for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_256_128', 64, 64, 256, 128, 9, False, True),
+                                                     ('conv64_128_128_res', 64, 64, 128, 128, 9, True, False),
+                                                     ('conv32_256_256', 32, 32, 256, 256, 9, False, True),
+                                                     ('conv16_384_384', 16, 16, 384, 384, 9, True, False),
+                                                     ('conv8_512_512', 8, 8, 512, 512, 9, True, False),
                                                      ('qkv16', 16, 16, 384, 1152, 1, False, True),
                                                      ('proj16', 16, 16, 384, 384, 1, True, False)]:
     M = N_IMG * H * W
@@ -21,9 +26,9 @@ for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_128_128', 64, 64, 12
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
     st = torch.zeros(N_IMG, 2, N, device=dev, dtype=torch.int64)
     geo = dict(n_img=N_IMG, H=H, W=W)
-    for _ in range(3):
+    for _ in range(2):
         if bf16_out:
-            ops.gemm(a1, w, N, taps=taps, bias=bias, residual=resid, out_bf16=out, **geo)
+            ops.gemm(a1, w, N, taps=taps, bias=bias, residual=resid, out_bf16=out, stats_out=st if taps == 9 else None, **geo)
         else:
             ops.gemm(a1, w, N, taps=taps, bias=bias, residual=resid, out_f32=out, stats_out=st, **geo)
     torch.cuda.synchronize()
