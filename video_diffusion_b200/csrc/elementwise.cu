@@ -1,6 +1,8 @@
 // HBM-bound producer kernels around the GEMMs: GroupNorm statistics / apply (+SiLU,
 // +scale-shift, + concat, + x2 upsample, + stride-2 parity split), temporal GroupNorm,
 // conditioning mix + input-conv im2col, timestep sinusoid, RPE-net hidden layer.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vdm {
@@ -507,6 +509,7 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   const int threads = C8 * rows;
   int ppb = rows * 32;
   while (ppb > rows * 4 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
+  if (const char* e = getenv("VDM_GN_PPB")) ppb = std::max(rows, atoi(e) / rows * rows);
   p.pix_per_block = ppb;
   dim3 grid((HW + ppb - 1) / ppb, a->n_img);
   const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);

@@ -53,6 +53,7 @@ struct TcParams {
   int ld_out, ld_out_bf16;
   int out_nchw;
   int64_t* stats_out;
+  int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory (pays off for long K)
   int dbg;                     // diagnostics (VDM_GEMM_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs (results are garbage)
   unsigned long long* trace;   // diagnostics (vdm_gemm_set_trace): per-CTA wait / busy cycle counters, else NULL
 };
@@ -239,15 +240,20 @@ struct SmemLayout {
   static constexpr int TOTAL_CHUNKS = M_SUB * (BLOCK_N / CHUNK);
   static constexpr int WARP_STG_FLOATS = 32 * (CHUNK + 4);
   static constexpr int STG_BYTES = EPI_WARPS * WARP_STG_FLOATS * 4;
-  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int STAT_IMGS = 2;                                         // images a CTA tile may span (H*W >= 64)
+  static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;                  // GroupNorm partial sums per lane quarter
+  static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;         // + alignment slack
 };
 
 // ===================== epilogue role (warps 2..9), shared by the kernels below =====================
 // tmem_full_bar0 / tmem_empty_bar0: shared-memory addresses of the two-entry barrier arrays of the accumulator stages.
-template <int BLOCK_N, int M_SUB, int EPI, bool CTA2>
-__device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base, uint32_t tmem_base,
+// stab: zeroed shared-memory table [4 lane quarters][stat_imgs][2][BLOCK_N] of fp32 GroupNorm partial sums.
+template <int BLOCK_N, int M_SUB, int CHUNK, int EPI, bool CTA2>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base, float* stab,
+                                              int stat_imgs, uint32_t tmem_base,
                                               uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int n_tiles,
                                               int n_tiles_n, int work_id0, int work_step, uint32_t cta_rank, int warp,
                                               int lane) {
@@ -260,7 +266,6 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
   // 32 cache lines per instruction.  Each warp stages its 32 x CHUNK block in shared memory (row
   // stride CHUNK+4 floats keeps 128-bit accesses conflict-free both ways) and re-reads it so that
   // CHUNK/4 lanes cover one contiguous row segment: fully coalesced residual loads and stores.
-  constexpr int CHUNK = (BLOCK_N < 32 || M_SUB > 1) ? 16 : 32;
   constexpr int N_CHUNKS = BLOCK_N / CHUNK;
   constexpr int STG_LD = CHUNK + 4;
   constexpr int LPR = CHUNK / 4;   // lanes per row
@@ -282,6 +287,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     }
     const int n0 = (tl % n_tiles_n) * BLOCK_N;
     const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);
+    // GroupNorm statistics go through a shared-memory table (one global atomic per (image, channel) and tile
+    // instead of one per 32 rows) whenever this CTA's rows span at most stat_imgs images.  Every (quarter, column)
+    // entry has exactly one writer warp, so plain read-modify-writes in a fixed order: deterministic.
+    const int img_first = mt0 / p.HW;
+    const bool use_tab = STATS && p.stats_out != nullptr && p.stats_via_smem &&
+                         (mt0 + BLOCK_M * M_SUB - 1) / p.HW - img_first < stat_imgs;
+    float* const tabq = stab + (size_t)q * stat_imgs * 2 * BLOCK_N;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     float4 res_cur[NRES];
@@ -429,26 +441,41 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         }
       }
       if (STATS && p.stats_out != nullptr) {
-        // GroupNorm statistics of the stored tile: fold the lanes that share a column quad, then add this
-        // warp's 32-row partial sums to the per-(image, channel) table with 64-bit fixed-point atomics.
-        // Integer addition is associative, so the statistics (and everything downstream) are bit-reproducible
-        // from run to run without any cross-warp ordering.
-#pragma unroll
-        for (int o = LPR; o < 32; o <<= 1) {
-          ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
-          ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
-          ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
-          ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
-        }
         const int row0 = m0 + q * 32;      // the warp's 32 rows lie in one image (H*W % 32 == 0)
-        if (r_sub == 0 && n < p.N && row0 < p.M) {
-          unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) +
-                                    (size_t)(row0 / p.HW) * 2 * p.N + n;
-          const float sv[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+        if (use_tab) {
+          // transpose the lanes' partial sums through the (now idle) staging block so that a lane owns a column
+          __syncwarp();
+          float* part = stg;               // [RPI row groups][sum, sum of squares][CHUNK]
+          *reinterpret_cast<float4*>(part + (r_sub * 2 + 0) * CHUNK + c4) = ssum;
+          *reinterpret_cast<float4*>(part + (r_sub * 2 + 1) * CHUNK + c4) = ssq;
+          __syncwarp();
+          float* trow = tabq + (size_t)(row0 / p.HW - img_first) * 2 * BLOCK_N + (nb - n0);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const long long fx = __double2ll_rn((double)sv[e] * 16777216.0);
-            atomicAdd(tab + (e >> 2) * p.N + (e & 3), (unsigned long long)fx);
+          for (int idx = lane; idx < 2 * CHUNK; idx += 32) {
+            const int k = idx / CHUNK, col = idx - k * CHUNK;
+            float sacc = 0.f;
+#pragma unroll
+            for (int r = 0; r < RPI; ++r) sacc += part[(r * 2 + k) * CHUNK + col];
+            if (row0 < p.M) trow[k * BLOCK_N + col] += sacc;
+          }
+        } else {
+          // direct route: fold the lanes that share a column quad, then add this warp's 32-row partial sums to the
+          // per-(image, channel) table with 64-bit fixed-point atomics (integer addition is associative, so the
+          // statistics and everything downstream are bit-reproducible from run to run)
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {
+            ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
+            ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, o); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, o);
+            ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, o); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, o);
+            ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, o); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, o);
+          }
+          if (r_sub == 0 && n < p.N && row0 < p.M) {
+            const float sv[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+            unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) +
+                                      (size_t)(row0 / p.HW) * 2 * p.N + n;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)   // 2^24 scaling of a float is exact
+              atomicAdd(tab + (e >> 2) * p.N + (e & 3), (unsigned long long)__float2ll_rn(sv[e] * 16777216.0f));
           }
         }
       }
@@ -466,6 +493,26 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     if (lane == 0) {
       if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
       else mbar_arrive(tmem_empty_bar(as));
+    }
+    if (use_tab) {
+      // all eight epilogue warps have added their partial sums: one thread per (image, statistic, channel) folds
+      // the four quarters in fixed point (order-free) and issues the only global atomic of this tile for it
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const int per_q = stat_imgs * 2 * BLOCK_N;
+      for (int i = ew * 32 + lane; i < per_q; i += EPI_WARPS * 32) {
+        long long fx = 0;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          fx += __float2ll_rn(stab[qq * per_q + i] * 16777216.0f);
+          stab[qq * per_q + i] = 0.f;
+        }
+        if (fx != 0) {
+          const int img = img_first + i / (2 * BLOCK_N), k = (i / BLOCK_N) & 1, col = n0 + i % BLOCK_N;
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.stats_out) + ((size_t)img * 2 + k) * p.N + col,
+                    (unsigned long long)fx);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // table is clean before the next tile adds
     }
   }
   if (kTrace && p.trace && ew == 0 && lane == 0) {
@@ -511,6 +558,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int n_tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int n_tiles = (p.a1_mode == 3 ? 4 : 1) * n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
 
+  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
+    reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -708,7 +757,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    epilogue_role<BLOCK_N, M_SUB, EPI, CTA2>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), tmem_base,
+    epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, CTA2>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
+                                             reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
+                                             L::STAT_IMGS, tmem_base,
                                              tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
                                              work_step, cta_rank, warp, lane);
   }
@@ -742,7 +793,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // an optional second operand (fused 1x1 skip projection) appends plain 128-row tiles to the same rings.
 template <int BLOCK_N, int M_SUB, int SA, int SB>
 struct HaloLayout {
-  static constexpr int CHUNK = (M_SUB > 1) ? 16 : 32;
+  static constexpr int CHUNK = 32;   // columns per epilogue step
   static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int A_SLOT = (M_SUB + 1) * A_SUB_BYTES;   // (R + 2) * W <= M_SUB * 128 + 128 pixels for W <= 64
   static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the weight tile
@@ -750,7 +801,10 @@ struct HaloLayout {
   static constexpr int B_OFFSET = SA * A_SLOT;
   static constexpr int STG_OFFSET = B_OFFSET + SB * B_SLOT;
   static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
-  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int STAT_IMGS = 1;                                   // a halo CTA tile lies inside one image
+  static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
@@ -784,6 +838,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
   const int halo_rows = CTA_ROWS / p.W + 2;
   const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
 
+  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
+    reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2 * SA + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; ++a) {
@@ -913,7 +969,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
       }
     }
   } else {
-    epilogue_role<BLOCK_N, M_SUB, EPI, true>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), tmem_base,
+    epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, true>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
+                                             reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
+                                             L::STAT_IMGS, tmem_base,
                                              tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
                                              work_step, cta_rank, warp, lane);
   }
@@ -1153,6 +1211,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   p.stats_out = a->stats_out;
+  p.stats_via_smem = (int64_t)a->taps * a->C1 + a->C2 >= 1024;   // short-K tiles: two barriers per tile cost more than the atomics
   p.w_group_tiles = a->w_group_tiles;
   p.trace = g_trace_buf;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
@@ -1220,7 +1279,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
       if (rc) return rc;
       if (bn == 256) return launch_halo<256, 1, 3, 5>(mh, ma2, mw2, p, stream);
       if (bn == 192) return launch_halo<192, 1, 3, 6>(mh, ma2, mw2, p, stream);
-      return launch_halo<128, 2, 3, 6>(mh, ma2, mw2, p, stream);
+      return launch_halo<128, 2, 3, 4>(mh, ma2, mw2, p, stream);
     }
   }
   int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
@@ -1265,7 +1324,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   if (cta2) {
     if (block_n == 256) return launch<256, 1, 5, true>(ma1, ma2, mw, p, stream);
     if (block_n == 192) return launch<192, 1, 6, true>(ma1, ma2, mw, p, stream);
-    if (m_sub == 2) return launch<128, 2, 5, true>(ma1, ma2, mw, p, stream);
+    if (m_sub == 2) return launch<128, 2, 4, true>(ma1, ma2, mw, p, stream);
     return launch<128, 1, 7, true>(ma1, ma2, mw, p, stream);
   }
   switch (block_n) {
@@ -1295,6 +1354,7 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   p.a1_mode = 3; p.is_linear = 0; p.H = Hl; p.W = Wl; p.HW = HWl;
   p.bias = a->bias; p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.stats_out = a->stats_out;
+  p.stats_via_smem = 1;
   p.trace = g_trace_buf;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE((Wl <= 128 && 128 % Wl == 0) || Wl % 128 == 0, "gemm_tc: unsupported width %d", Wl);
