@@ -380,10 +380,16 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         __nv_bfloat16* o16 = nullptr;
         if constexpr (BF16_OUT) o16 = p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n;
         else o32 = p.out_f32 + (size_t)row_first * p.ld_out + n;
+        // all staged rows first (independent LDS in flight), then the arithmetic and the stores: left to the
+        // compiler the loop came out as a serial load -> convert -> store chain of ~130 cycles per row group
+        float4 vv[NRES];
+#pragma unroll
+        for (int i = 0; i < NRES; ++i) vv[i] = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
+        __syncwarp();   // keeps ptxas from sinking the loads back next to their uses
 #pragma unroll
         for (int i = 0; i < NRES; ++i) {
           if (full || row_first + i * RPI < p.M) {
-            float4 v = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
+            float4 v = vv[i];
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             if constexpr (HAS_RES) {
               v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
