@@ -42,21 +42,33 @@ __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat
   constexpr int CH = HD / 8;   // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sK = sQ + BQ * LDS;
-  __nv_bfloat16* sV = sK + BKV * LDS;
+  __nv_bfloat16* sKV = sQ + BQ * LDS;   // two buffers of [K tile | V tile]: tile t+1 streams in while tile t is used
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, n = blockIdx.z;
   const int C = heads * HD;
   const size_t row_stride = (size_t)3 * C;
   const __nv_bfloat16* base = qkv + (size_t)n * L * row_stride + h * HD;
 
+  auto load_kv = [&](int k0, int buf) {
+    __nv_bfloat16* dK = sKV + (size_t)buf * 2 * BKV * LDS;
+    __nv_bfloat16* dV = dK + BKV * LDS;
+    for (int idx = tid; idx < BKV * CH; idx += 128) {
+      const int r = idx / CH, c = idx - r * CH;
+      const bool ok = k0 + r < L;
+      const __nv_bfloat16* src = base + (size_t)(ok ? k0 + r : 0) * row_stride + c * 8;
+      cp_async_16(dK + r * LDS + c * 8, src + C, ok);
+      cp_async_16(dV + r * LDS + c * 8, src + 2 * C, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   for (int idx = tid; idx < BQ * CH; idx += 128) {
     const int r = idx / CH, c = idx - r * CH;
     const bool ok = q0 + r < L;
     cp_async_16(sQ + r * LDS + c * 8, base + (size_t)(ok ? q0 + r : 0) * row_stride + c * 8, ok);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  load_kv(0, 0);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // Q has landed (the first K/V tile may still be in flight)
   __syncthreads();
 
   uint32_t qf[HD / 16][4];
@@ -69,18 +81,17 @@ __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < L; k0 += BKV) {
-    __syncthreads();  // everyone is done with the previous K/V tile
-    for (int idx = tid; idx < BKV * CH; idx += 128) {
-      const int r = idx / CH, c = idx - r * CH;
-      const bool ok = k0 + r < L;
-      const __nv_bfloat16* src = base + (size_t)(ok ? k0 + r : 0) * row_stride + c * 8;
-      cp_async_16(sK + r * LDS + c * 8, src + C, ok);
-      cp_async_16(sV + r * LDS + c * 8, src + 2 * C, ok);
+  int buf = 0;
+  for (int k0 = 0; k0 < L; k0 += BKV, buf ^= 1) {
+    if (k0 + BKV < L) {
+      load_kv(k0 + BKV, buf ^ 1);   // that buffer was released by the barrier at the end of the previous iteration
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    const __nv_bfloat16* sK = sKV + (size_t)buf * 2 * BKV * LDS;
+    const __nv_bfloat16* sV = sK + BKV * LDS;
 
     // S = Q K^T for this warp's 16 rows x 64 keys
     float s[BKV / 8][4];
@@ -151,6 +162,7 @@ __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat
         mma_bf16(o[nt + 1], pa, b[2], b[3]);
       }
     }
+    __syncthreads();   // all warps are done with this K/V buffer before the next prefetch overwrites it
   }
   // finalize: row sums live as per-lane partials within each quad
 #pragma unroll
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat
 
 template <int HD, typename OutT>
 int launch(const void* qkv, int n_img, int L, int heads, void* out, cudaStream_t stream) {
-  const size_t smem = (size_t)(BQ + 2 * BKV) * (HD + 8) * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)(BQ + 4 * BKV) * (HD + 8) * sizeof(__nv_bfloat16);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_spatial_mma_kernel<HD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
