@@ -116,3 +116,47 @@ def test_sharding_and_ragged_gather_world2():
         assert p.exitcode == 0
     for _, ids, vals in res:
         assert ids == list(range(9)) and vals == list(range(9))
+
+
+def test_result_paths_and_run_identifiers_match_reference(golden, tmp_path):
+    """Naming produced by the reference's own test_util.py (oracle/make_golden_formats.py)."""
+    import argparse
+    from video_diffusion_b200 import test_util as T
+    g = golden.json('formats')
+    for item in g['paths']:
+        c = item['case']
+        ck = tmp_path / c['checkpoint']
+        ck.parent.mkdir(parents=True, exist_ok=True)
+        torch.save(dict(state_dict={}, config={}, step=c['step']), ck)
+        args = argparse.Namespace(use_ddim=c['use_ddim'], timestep_respacing=c['timestep_respacing'],
+                                  eval_dir=c['eval_dir'], checkpoint_path=str(ck))
+        assert str(T.get_model_results_path(args, postfix=c['postfix'])) == item['expect']
+    for item in g['ids']:
+        assert T.get_eval_run_identifier(argparse.Namespace(**item['case']), postfix=item['postfix']) == item['expect']
+
+
+def test_checkpoint_loader_and_elbo_pickles(golden, tmp_path):
+    """Reference checkpoint layout {'state_dict','config','step'} (test_util.py:31-62) with an old config that lacks
+    the newer keys; ELBO pickles laid out like scripts/video_nll.py:126-137."""
+    import pickle
+    from oracle import synth
+    from video_diffusion_b200 import test_util as T, video_model_and_diffusion_defaults
+    cfg = video_model_and_diffusion_defaults()
+    cfg.update(cases.ref_config('tiny'))
+    for k in ('enforce_position_invariance', 'cond_emb_type'):      # a checkpoint written before these existed
+        cfg.pop(k, None)
+    sd = synth.make_state_dict(golden.json('spec_tiny'), seed=1)
+    path = tmp_path / 'checkpoints' / 'run' / 'ema_latest.pt'
+    path.parent.mkdir(parents=True)
+    torch.save(dict(state_dict=sd, config=cfg, step=42), path)
+    (model, diffusion), margs = T.load_checkpoint(str(path), 'cpu', use_ddim=True, timestep_respacing='10')
+    assert margs.cond_emb_type == 'channel' and margs.enforce_position_invariance is False
+    assert diffusion.num_timesteps == 10 and not model.training
+    got = model.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+
+    rets = [dict(total_bpd=np.arange(3.0) + i, vb=np.ones((3, 5)) * i) for i in range(2)]   # two index types
+    paths = T.save_elbos(tmp_path / 'eval', rets, dataset_indices=[7, 8, 11], postfix='_s')
+    assert [p.name for p in paths] == ['elbo_7_s.pkl', 'elbo_8_s.pkl', 'elbo_11_s.pkl']
+    d = pickle.load(open(paths[1], 'rb'))
+    assert d['total_bpd'].shape == (2,) and d['vb'].shape == (2, 5) and d['total_bpd'][1] == 2.0
