@@ -376,39 +376,48 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         const int row_first = m0 + q * 32 + r_sub;
         const bool full = m0 + BLOCK_M <= p.M;
         const float* sp = stg + r_sub * STG_LD + c4;
-        float* o32 = nullptr;
-        __nv_bfloat16* o16 = nullptr;
-        if constexpr (BF16_OUT) o16 = p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n;
-        else o32 = p.out_f32 + (size_t)row_first * p.ld_out + n;
         // all staged rows first (independent LDS in flight), then the arithmetic and the stores: left to the
         // compiler the loop came out as a serial load -> convert -> store chain of ~130 cycles per row group
         float4 vv[NRES];
 #pragma unroll
         for (int i = 0; i < NRES; ++i) vv[i] = *reinterpret_cast<const float4*>(sp + i * RPI * STG_LD);
         __syncwarp();   // keeps ptxas from sinking the loads back next to their uses
-#pragma unroll
-        for (int i = 0; i < NRES; ++i) {
-          if (full || row_first + i * RPI < p.M) {
-            float4 v = vv[i];
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if constexpr (HAS_RES) {
-              v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
-            }
-            if constexpr (STATS) {
-              ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
-              ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
-              ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
-            }
-            if constexpr (BF16_OUT) {
-              uint2 pk;
-              pk.x = pack_bf16x2(v.x, v.y);
-              pk.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(o16 + (size_t)(i * RPI) * p.ld_out_bf16) = pk;
-            } else {
-              *reinterpret_cast<float4*>(o32 + (size_t)(i * RPI) * p.ld_out) = v;
-            }
+        // the epilogue is instruction-issue bound: one running output pointer (no per-row 64-bit multiply) and,
+        // for full tiles, no per-row bounds test
+        auto finish_row = [&](int i, auto* optr) {
+          float4 v = vv[i];
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if constexpr (HAS_RES) {
+            v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
           }
-        }
+          if constexpr (STATS) {
+            ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+            ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+            ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+          }
+          if constexpr (BF16_OUT) {
+            uint2 pk;
+            pk.x = pack_bf16x2(v.x, v.y);
+            pk.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(optr) = pk;
+          } else {
+            *reinterpret_cast<float4*>(optr) = v;
+          }
+        };
+        auto store_rows = [&](auto* optr, const size_t step) {
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < NRES; ++i, optr += step) finish_row(i, optr);
+          } else {
+#pragma unroll
+            for (int i = 0; i < NRES; ++i, optr += step)
+              if (row_first + i * RPI < p.M) finish_row(i, optr);
+          }
+        };
+        if constexpr (BF16_OUT)
+          store_rows(p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
+        else
+          store_rows(p.out_f32 + (size_t)row_first * p.ld_out + n, (size_t)RPI * p.ld_out);
       } else if (n < p.N) {  // N is a multiple of 4 on this path
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
