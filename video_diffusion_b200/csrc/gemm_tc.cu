@@ -53,7 +53,7 @@ struct TcParams {
   int ld_out, ld_out_bf16;
   int out_nchw;
   int64_t* stats_out;
-  int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory (pays off for long K)
+  int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory
   int dbg;                     // diagnostics (VDM_GEMM_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs (results are garbage)
   unsigned long long* trace;   // diagnostics (vdm_gemm_set_trace): per-CTA wait / busy cycle counters, else NULL
 };
@@ -325,6 +325,14 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     // fetched one chunk ahead -- the first one while this tile's MMAs are still running
     constexpr int TOTAL_CHUNKS = M_SUB * N_CHUNKS;
     if (half < TOTAL_CHUNKS) load_residual(res_cur, half);
+    // the bias quad of the next chunk is fetched one chunk ahead as well: the streaming stores keep evicting it
+    // from L1, and waiting ~500 cycles for it at its first use was a quarter of the per-chunk time
+    auto load_bias = [&](int jj) {
+      const int n = n0 + (jj % N_CHUNKS) * CHUNK + c4;
+      return (p.bias && n < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 bias_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (half < TOTAL_CHUNKS) bias_cur = load_bias(half);
     if (kTrace && p.trace) {
       const long long t0 = clock64();
       mbar_wait(tmem_full_bar(as), aphase, 2);
@@ -366,13 +374,16 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
                         __uint_as_float(acc[i + 3]));
       __syncwarp();
       float4 res_next[NRES];
-      if (jj + 2 < TOTAL_CHUNKS) load_residual(res_next, jj + 2);
+      float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jj + 2 < TOTAL_CHUNKS) {
+        load_residual(res_next, jj + 2);
+        bias_next = load_bias(jj + 2);
+      }
       const int n = nb + c4;
       float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (!GEN) {
         // lean path: N is a multiple of BLOCK_N, exactly one output, no per-image bias / row remap
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+        const float4 bv = bias_cur;
         const int row_first = m0 + q * 32 + r_sub;
         const bool full = m0 + BLOCK_M <= p.M;
         const float* sp = stg + r_sub * STG_LD + c4;
@@ -419,8 +430,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         else
           store_rows(p.out_f32 + (size_t)row_first * p.ld_out + n, (size_t)RPI * p.ld_out);
       } else if (n < p.N) {  // N is a multiple of 4 on this path
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+        const float4 bv = bias_cur;
 #pragma unroll
         for (int rr = 0; rr < 32; rr += RPI) {
           const int rl = rr + r_sub;
@@ -500,6 +510,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           for (int i = 0; i < NRES; ++i) res_cur[i] = res_next[i];
         }
       }
+      bias_cur = bias_next;
       __syncwarp();
     }
     // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA warp
@@ -1226,7 +1237,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   p.stats_out = a->stats_out;
-  p.stats_via_smem = (int64_t)a->taps * a->C1 + a->C2 >= 1024;   // short-K tiles: two barriers per tile cost more than the atomics
+  p.stats_via_smem = 1;
   p.w_group_tiles = a->w_group_tiles;
   p.trace = g_trace_buf;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
