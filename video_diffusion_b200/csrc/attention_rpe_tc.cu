@@ -189,8 +189,40 @@ __global__ void __launch_bounds__(128) attn_temporal_mma_kernel(const __nv_bfloa
       cp16(sV + r * LDS + c * 8, src + 2 * C, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+  // The RPE bias terms and the mask do not depend on the staged tiles: fetch them while the cp.async copies are in
+  // flight, so the kernel waits for one memory round trip instead of two.
+  const int r0 = w2 * 16 + (lane >> 2);
+  float bias_k[2][8], bias_q[2][8], allow[2][8];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = r0 + half * 8;
+    const bool row_ok = live && r < T;
+    const int gr = b * T + (row_ok ? r : 0);
+    const float* sk_row = sk + ((size_t)gr * D + d) * SW + (gr % gpt) * 128 + h * T;
+    const float m_r = row_ok ? mask[b * T + r] : 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = nt * 8 + 2 * (lane & 3) + e;
+        float bk = 0.f, bq = 0.f, al = 0.f;
+        if (row_ok && col < T) {
+          const int gs = b * T + col;
+          bq = sq[((size_t)gs * D + d) * SW + (gs % gpt) * 128 + h * T + r];
+          bk = sk_row[col];
+          const float m_s = mask[b * T + col];
+          al = m_r * m_s;
+          if (pad_interact) al += (1.f - m_r) * (1.f - m_s);
+          else if (col == r) al = 1.f;
+        }
+        bias_k[half][nt * 2 + e] = bk;
+        bias_q[half][nt * 2 + e] = bq;
+        allow[half][nt * 2 + e] = al;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (!live) return;
 
@@ -211,31 +243,19 @@ __global__ void __launch_bounds__(128) attn_temporal_mma_kernel(const __nv_bfloa
     }
   }
   // logits = scale*(q.k + Sk) + Sq, mask, softmax over the key axis (rows r0 and r0 + 8 of this lane)
-  const int r0 = w2 * 16 + (lane >> 2);
   float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int r = r0 + half * 8;
     const bool row_ok = r < T;
-    const int gr = b * T + (row_ok ? r : 0);
-    const float* sk_row = sk + ((size_t)gr * D + d) * SW + (gr % gpt) * 128 + h * T;
-    const float m_r = row_ok ? mask[b * T + r] : 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = nt * 8 + 2 * (lane & 3) + e;
         float v = -INFINITY;
-        if (row_ok && col < T) {
-          const int gs = b * T + col;
-          const float bias_q = sq[((size_t)gs * D + d) * SW + (gs % gpt) * 128 + h * T + r];
-          v = scale * (s[nt][half * 2 + e] + sk_row[col]) + bias_q;
-          const float m_s = mask[b * T + col];
-          float allowed = m_r * m_s;
-          if (pad_interact) allowed += (1.f - m_r) * (1.f - m_s);
-          else if (col == r) allowed = 1.f;
-          if (allowed == 0.f) v = -INFINITY;
-        }
+        if (row_ok && col < T && allow[half][nt * 2 + e] != 0.f)
+          v = scale * (s[nt][half * 2 + e] + bias_k[half][nt * 2 + e]) + bias_q[half][nt * 2 + e];
         s[nt][half * 2 + e] = v;
         mx[half] = fmaxf(mx[half], v);
       }
