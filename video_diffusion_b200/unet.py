@@ -302,7 +302,8 @@ class UNetModel(nn.Module):
             self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
             self.pool_used = 0
             self.out = None
-            self.side = self.ev_fork = self.ev_join = None
+            self.side = self.ev_fork = self.ev_emb = self.ev_join = None
+            self.emb_join = None
 
         def buf(self, name, shape, dtype=torch.float32):
             b = self.bufs.get(name)
@@ -363,6 +364,9 @@ class UNetModel(nn.Module):
         ss = self.use_scale_shift_norm
         st_h1 = self._fused_stats(ws, p + '.h1', n_img, HW, Cout)
         rb = None if ss else emb_out[:, off:off + Cout]
+        if rb is not None and ws.emb_join is not None:
+            torch.cuda.current_stream().wait_event(ws.emb_join)
+            ws.emb_join = None
         if st_h1 is not None and self.bf16_intermediate:
             # conv1's output is only ever consumed by GroupNorm -> SiLU -> bf16: keep it in bf16 (its
             # statistics come from the fp32 accumulators in the epilogue), halving its HBM traffic
@@ -374,6 +378,9 @@ class UNetModel(nn.Module):
             ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb,
                      out_f32=h1, stats_out=st_h1)
             st_h1 = self._stats_of(ws, p + '.h1', h1, st_h1, n_img, HW)
+        if ws.emb_join is not None:      # first consumer of the embedding projections: join the side branch
+            torch.cuda.current_stream().wait_event(ws.emb_join)
+            ws.emb_join = None
         a2 = ws.buf(p + '.a2', (M, Cout), adt)
         ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
                      scale_shift=emb_out[:, off:off + 2 * Cout] if ss else None, silu=True)
@@ -529,42 +536,53 @@ class UNetModel(nn.Module):
         ops.cond_mix(ws.x, ws.x0, ws.obs, ws.lat, ws.kinda, ws.t, B, F, H, W, a_in, t_frame, amask)
         if per_frame_t:
             t_frame = ws.t_override
-        temb = ws.buf('temb', (N, ch))
-        ops.timestep_embedding(t_frame, ch, temb)
-        lin = dict(n_img=N, H=1, W=1, taps=1)
-        l0, l0s = ws.buf('te_l0', (N, E)), ws.buf('te_l0s', (N, E))
-        ops.gemm(temb, P['te_w0'], E, bias=P['te_b0'], out_f32=l0, out_silu=l0s, **lin)
-        emb, embs = ws.buf('emb', (N, E)), ws.buf('embs', (N, E))
-        ops.gemm(l0s, P['te_w2'], E, bias=P['te_b2'], out_f32=emb, out_silu=embs, **lin)
         emb_out = ws.buf('emb_out', (N, P['emb_w'].shape[0]))
         rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0]))
-        if adt == torch.bfloat16:
-            # the two wide projections of the embedding (all ResBlock scale/shift vectors, all RPE-net time
-            # terms) go through the tensor-core GEMM on bf16 copies of silu(emb) / emb
-            embs_b, emb_b = ws.buf('embs_b', (N, E), adt), ws.buf('emb_b', (N, E), adt)
-            ops.gn_apply(embs, None, N, 1, 1, embs_b)
-            ops.gn_apply(emb, None, N, 1, 1, emb_b)
-            ops.gemm(embs_b, P['emb_w_a'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
-            ops.gemm(emb_b, P['rpe_t_w_a'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
-        else:
-            ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
-            ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+        lin = dict(n_img=N, H=1, W=1, taps=1)
 
-        # The RPE tables depend only on the embedding: fork them onto a side stream (a parallel branch of the CUDA
-        # graph) so they fill the gaps of the first blocks; joined right before the first attention block.
-        tables, rpe_join = None, None
-        if T_attn == F:
-            if self.overlap_rpe_tables and ops.PROFILE is None:
-                main = torch.cuda.current_stream()
-                if ws.side is None:
-                    ws.side, ws.ev_fork, ws.ev_join = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
-                ws.ev_fork.record(main)
-                ws.side.wait_event(ws.ev_fork)
-                with torch.cuda.stream(ws.side):
-                    tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
-                    ws.ev_join.record(ws.side)
-                rpe_join = ws.ev_join
+        def embedding_branch():
+            """timestep embedding MLP -> the two wide projections (unet.py:605-610, 156-160, 283-296)."""
+            temb = ws.buf('temb', (N, ch))
+            ops.timestep_embedding(t_frame, ch, temb)
+            l0, l0s = ws.buf('te_l0', (N, E)), ws.buf('te_l0s', (N, E))
+            ops.gemm(temb, P['te_w0'], E, bias=P['te_b0'], out_f32=l0, out_silu=l0s, **lin)
+            emb, embs = ws.buf('emb', (N, E)), ws.buf('embs', (N, E))
+            ops.gemm(l0s, P['te_w2'], E, bias=P['te_b2'], out_f32=emb, out_silu=embs, **lin)
+            if adt == torch.bfloat16:
+                # the two wide projections of the embedding (all ResBlock scale/shift vectors, all RPE-net time
+                # terms) go through the tensor-core GEMM on bf16 copies of silu(emb) / emb
+                embs_b, emb_b = ws.buf('embs_b', (N, E), adt), ws.buf('emb_b', (N, E), adt)
+                ops.gn_apply(embs, None, N, 1, 1, embs_b)
+                ops.gn_apply(emb, None, N, 1, 1, emb_b)
+                ops.gemm(embs_b, P['emb_w_a'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
+                ops.gemm(emb_b, P['rpe_t_w_a'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
             else:
+                ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
+                ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+
+        # The embedding path and the RPE tables depend only on the timesteps and frame indices: they run on a side
+        # stream (a parallel branch of the CUDA graph) under the input conv and the first block, where their small
+        # latency-bound launches would otherwise leave the GPU idle.  Two joins: the embedding projections before
+        # the first scale/shift GroupNorm, the tables before the first attention block.
+        tables, rpe_join = None, None
+        ws.emb_join = None
+        if self.overlap_rpe_tables and ops.PROFILE is None:
+            main = torch.cuda.current_stream()
+            if ws.side is None:
+                ws.side = torch.cuda.Stream()
+                ws.ev_fork, ws.ev_emb, ws.ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            ws.ev_fork.record(main)
+            ws.side.wait_event(ws.ev_fork)
+            with torch.cuda.stream(ws.side):
+                embedding_branch()
+                ws.ev_emb.record(ws.side)
+                if T_attn == F:
+                    tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
+                ws.ev_join.record(ws.side)
+            ws.emb_join, rpe_join = ws.ev_emb, ws.ev_join
+        else:
+            embedding_branch()
+            if T_attn == F:
                 tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
