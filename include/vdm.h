@@ -86,6 +86,13 @@ typedef struct {
                            fixed point (units of 2^-24), accumulated with integer atomics -- deterministic --
                            into a buffer the caller zeroed: the GroupNorm statistics of the NEXT layer come
                            out of this epilogue for free (nn.py:15-17) */
+  int32_t n_prob;       /* bf16 kernel, taps == 1: > 1 runs that many same-shape plain linears in ONE launch: problem i
+                           reads the A1 column block starting at i * prob_a_cols (lda1 spans them all), the weight
+                           rows starting at i * prob_w_rows and writes at out + i * prob_out_stride elements.  Used for
+                           the q -> Sk and k -> Sq RPE GEMMs of a temporal attention block (unet.py:357-366) */
+  int32_t prob_a_cols;
+  int64_t prob_w_rows;
+  int64_t prob_out_stride;
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
@@ -181,7 +188,9 @@ int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, cons
 int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v,
                    const float* bias /* optional [n_blocks][3][C] (q, k, v) added to the tables */,
                    int32_t n_blocks /* attention blocks batched in this call */,
-                   int64_t r_block_stride /* elements between consecutive blocks' tables */, int32_t B, int32_t T,
+                   int64_t r_block_stride /* elements between consecutive blocks' tables */,
+                   int64_t qk_block_stride /* elements between consecutive blocks' bq (and bk) operands; 0 = packed */,
+                   int32_t B, int32_t T,
                    int32_t heads, int32_t hd, int32_t groups_per_tile,
                    int32_t zero_fill /* 1: write every element; 0: the caller zeroed bq/bk/bv once and only this
                                         function (same shapes) writes them, so the structural zeros are skipped */,

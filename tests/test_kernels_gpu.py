@@ -453,6 +453,28 @@ def test_attention_temporal_tensor_core_path(T, hd, HW, pad):
     assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
 
 
+@pytest.mark.parametrize('M,C,SW,tpg', [(640, 128, 128, 1), (1536, 64, 256, 1), (1024, 192, 128, 2)])
+def test_gemm_problem_batch_equals_separate_launches(M, C, SW, tpg):
+    """n_prob = 2: q -> Sk and k -> Sq (column blocks of one qkv matrix, stacked grouped weights, stacked outputs) in
+    one launch, bit-identical to the two separate grouped GEMMs."""
+    o = ops()
+    qkv = rnd(M, 3 * C, seed=1).bfloat16()
+    groups = (M // 128 + tpg - 1) // tpg
+    rows = groups * SW
+    bkq = rnd(2, rows, C, seed=2, scale=C ** -0.5).bfloat16()
+    lin = dict(n_img=M, H=1, W=1, taps=1)
+    sk, sq = torch.empty(M, SW, device='cuda'), torch.empty(M, SW, device='cuda')
+    o.gemm(qkv[:, :C], bkq[0], SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
+    o.gemm(qkv[:, C:2 * C], bkq[1], SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
+    both = torch.full((2, M, SW), float('nan'), device='cuda')
+    o.gemm(qkv[:, :C], bkq.view(2 * rows, C), SW, out_f32=both, w_group_tiles=tpg, C1=C, n_prob=2, prob_a_cols=C,
+           prob_w_rows=rows, prob_out_stride=M * SW, **lin)
+    assert torch.equal(both[0], sk) and torch.equal(both[1], sq)
+    ref = torch.einsum('gmk,gnk->gmn', qkv[:, :C].float().view(groups, -1, C) if tpg == 1 and M // 128 == groups else
+                       qkv[:, :C].float().view(groups, -1, C), bkq[0].float().view(groups, SW, C)).reshape(M, SW)
+    assert relerr(sk, ref) < 2e-5
+
+
 @pytest.mark.parametrize('L,hd', [(256, 96), (64, 128), (256, 32)])
 def test_attention_spatial_f32(L, hd):
     o = ops()

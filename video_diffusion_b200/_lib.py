@@ -29,7 +29,8 @@ class GemmArgs(C.Structure):
                 ('C1', _i32), ('C2', _i32), ('N', _i32), ('a1', _vp), ('a2', _vp), ('w', _vp), ('bias', _vp),
                 ('rowbias', _vp), ('ld_rowbias', _i32), ('residual', _vp), ('ld_res', _i32), ('out_f32', _vp),
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
-                ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp)]
+                ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp), ('n_prob', _i32),
+                ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64)]
 
 
 class GnApplyArgs(C.Structure):
@@ -64,7 +65,7 @@ def load():
         'vdm_rpe_hidden': [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
         'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
         'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
-        'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+        'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
         'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
         'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
         'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict
                                                           const float* __restrict__ r_v,
                                                           const float* __restrict__ bias,   // [3][C] (q, k, v) or NULL
                                                           long long r_block_stride, int tgs,   // batching over blocks
+                                                          long long qk_block_stride,
                                                           int G, int T, int heads, int hd, int gpt, float scale,
                                                           __nv_bfloat16* __restrict__ bq,
                                                           __nv_bfloat16* __restrict__ bk,
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict
   const int tg = blockIdx.y;
   const float* R = (which == 0 ? r_k : (which == 1 ? r_q : r_v)) + (size_t)blk * r_block_stride;
   const float* bs = bias ? bias + ((size_t)blk * 3 + (which == 0 ? 1 : (which == 1 ? 0 : 2))) * C : nullptr;
-  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + ((size_t)blk * tgs + tg) * SW * C;
+  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) +
+                       (which < 2 ? (size_t)blk * qk_block_stride : (size_t)blk * tgs * SW * C) + (size_t)tg * SW * C;
   const float mul = which == 1 ? scale : 1.0f;
   const int nvec = SW * C / 8;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict
 //   Bv     : CTA = one (b, t) group x 64 channels; the [T][64] slab of R is transposed through shared memory
 __global__ void __launch_bounds__(256) rpe_expand_live_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
                                                                const float* __restrict__ r_v, const float* __restrict__ bias,
-                                                               long long r_block_stride, int tgs, int G, int T, int heads,
+                                                               long long r_block_stride, int tgs,
+                                                               long long qk_block_stride, int G, int T, int heads,
                                                                int hd, int gpt, float scale, __nv_bfloat16* __restrict__ bq,
                                                                __nv_bfloat16* __restrict__ bk, __nv_bfloat16* __restrict__ bv) {
   __shared__ float tile[32][65];
@@ -84,7 +87,8 @@ __global__ void __launch_bounds__(256) rpe_expand_live_kernel(const float* __res
   const int which = blockIdx.z % 3, blk = blockIdx.z / 3, tg = blockIdx.y;
   const float* R = (which == 0 ? r_k : (which == 1 ? r_q : r_v)) + (size_t)blk * r_block_stride;
   const float* bs = bias ? bias + ((size_t)blk * 3 + (which == 0 ? 1 : (which == 1 ? 0 : 2))) * C : nullptr;
-  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) + ((size_t)blk * tgs + tg) * SW * C;
+  __nv_bfloat16* out = (which == 0 ? bk : (which == 1 ? bq : bv)) +
+                       (which < 2 ? (size_t)blk * qk_block_stride : (size_t)blk * tgs * SW * C) + (size_t)tg * SW * C;
   if (which < 2) {
     const float mul = which == 1 ? scale : 1.0f;
     const int hd8 = hd / 8, HT = heads * T;
@@ -357,7 +361,8 @@ int launch_attn(const void* qkv, const float* sk, const float* sq, const float* 
 using namespace vdm;
 
 extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r_v, const float* bias,
-                              int32_t n_blocks, int64_t r_block_stride, int32_t B, int32_t T, int32_t heads,
+                              int32_t n_blocks, int64_t r_block_stride, int64_t qk_block_stride, int32_t B,
+                              int32_t T, int32_t heads,
                               int32_t hd, int32_t groups_per_tile, int32_t zero_fill, void* bq, void* bk,
                               void* bv, vdm_stream_t stream) {
   VDM_REQUIRE(r_q && r_k && r_v && bq && bk && bv, "rpe_expand: NULL pointer");
@@ -367,17 +372,18 @@ extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r
   VDM_REQUIRE(hd % 8 == 0, "rpe_expand: head_dim must be a multiple of 8");
   const int nvec = 128 * gpt * heads * hd / 8;
   VDM_REQUIRE(n_blocks >= 1, "rpe_expand: n_blocks must be >= 1");
+  if (qk_block_stride == 0) qk_block_stride = (int64_t)tgs * 128 * gpt * heads * hd;
   if (!zero_fill) {
     VDM_REQUIRE(T <= 32, "rpe_expand: T=%d must be <= 32", T);
     dim3 grid(gpt * ((heads * hd + 63) / 64), tgs, 3 * n_blocks);
-    rpe_expand_live_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, G, T, heads, hd,
+    rpe_expand_live_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd,
                                                                    gpt, 1.0f / sqrtf((float)hd), (__nv_bfloat16*)bq,
                                                                    (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
     VDM_AFTER_LAUNCH("rpe_expand");
     return 0;
   }
   dim3 grid(std::min((nvec + 255) / 256, 32), tgs, 3 * n_blocks);
-  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
+  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
                                                             (__nv_bfloat16*)bq, (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
   VDM_AFTER_LAUNCH("rpe_expand");
   return 0;

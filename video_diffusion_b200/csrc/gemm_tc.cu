@@ -40,7 +40,11 @@ struct TcParams {
   int taps, c1_chunks, c2_chunks;
   int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes, 3 nearest-x2 upsample folded into 2x2 taps
   int w_group_tiles;  // grouped weights: 128-row tile m reads weight rows (m / w_group_tiles) * N + n
-  int tiles_per_par;  // a1_mode 3: tiles per output parity (tile index = parity * tiles_per_par + ...)
+  int tiles_per_par;  // > 0: tile index = par * tiles_per_par + ...; par = output parity (a1_mode 3) or problem of a batch
+  int n_par;          // number of parities / problems (1 when tiles_per_par == 0)
+  int par_w_rows;     // weight rows per par (added to the weight row coordinate)
+  int par_a_cols;     // batch of problems: A1 column offset per problem
+  long long par_out_stride;   // batch of problems: output element offset per problem
   int is_linear;  // A1 addressed as 2-D [M][C1]
   int H, W, HW;
   const float* bias;
@@ -281,7 +285,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
   const long long tr_start = (kTrace && p.trace) ? clock64() : 0;
   for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
     int par = 0, tl = tile;
-    if (p.a1_mode == 3) {
+    if (p.tiles_per_par > 0) {
       par = tile / p.tiles_per_par;
       tl = tile - par * p.tiles_per_par;
     }
@@ -426,9 +430,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           }
         };
         if constexpr (BF16_OUT)
-          store_rows(p.out_bf16 + (size_t)row_first * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
+          store_rows(p.out_bf16 + par * p.par_out_stride + (size_t)row_first * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
         else
-          store_rows(p.out_f32 + (size_t)row_first * p.ld_out + n, (size_t)RPI * p.ld_out);
+          store_rows(p.out_f32 + par * p.par_out_stride + (size_t)row_first * p.ld_out + n, (size_t)RPI * p.ld_out);
       } else if (n < p.N) {  // N is a multiple of 4 on this path
         const float4 bv = bias_cur;
 #pragma unroll
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.c1_chunks + p.c2_chunks;
   const int n_tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int n_tiles = (p.a1_mode == 3 ? 4 : 1) * n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
+  const int n_tiles = p.n_par * n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
 
   for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
     reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
@@ -630,7 +634,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       long long tr_wait = 0;
       for (int tile = work_id0; tile < n_tiles; tile += work_step) {
         int par = 0, tl = tile;
-        if (p.a1_mode == 3) {
+        if (p.tiles_per_par > 0) {
           par = tile / p.tiles_per_par;
           tl = tile - par * p.tiles_per_par;
         }
@@ -700,19 +704,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const uint32_t dst = a_dst + sub * L::A_SUB_BYTES;
             if constexpr (CTA2) {
               if (!first_range) tma_load_5d_2cta(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
-              else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0 + par * p.par_a_cols, m0 + sub * BLOCK_M, 0, 0, 0);
               else tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
             } else {
               if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
-              else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0 + par * p.par_a_cols, m0 + sub * BLOCK_M, 0, 0, 0);
               else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
             }
           }
           if constexpr (CTA2)   // this CTA's half of the weight tile
-            tma_load_2d_2cta(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + par * p.N + (int)cta_rank * (BLOCK_N / 2));
+            tma_load_2d_2cta(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K, n0 + par * p.par_w_rows + (int)cta_rank * (BLOCK_N / 2));
           else
             tma_load_2d(b_dst, &tm_w, full_bar(stage), kb * BLOCK_K,
-                        n0 + par * p.N + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
+                        n0 + par * p.par_w_rows + (p.w_group_tiles ? ((m0 / BLOCK_M) / p.w_group_tiles) * p.N : 0));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -1085,8 +1089,7 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
     configured = true;
   }
   constexpr int TILE_ROWS = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
-  const int tiles = (p.a1_mode == 3 ? 4 * p.tiles_per_par
-                                    : ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS));
+  const int tiles = p.n_par * ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS);
   if constexpr (CTA2) {
     // one CTA pair (a 2-CTA cluster on one TPC) per work tile; persistent over pairs
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -1239,6 +1242,18 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.stats_out = a->stats_out;
   p.stats_via_smem = 1;
   p.w_group_tiles = a->w_group_tiles;
+  p.n_par = 1;
+  const int n_prob = a->n_prob > 1 ? a->n_prob : 1;
+  if (n_prob > 1) {   // several same-shape linears in one launch (column blocks of one A1, stacked weights, stacked outputs)
+    VDM_REQUIRE(is_linear && a->C2 == 0 && !a->out_nchw && !a->residual && !a->rowbias && !a->stats_out && !a->bias,
+                "gemm_tc: a problem batch takes plain linears only");
+    VDM_REQUIRE(a->prob_a_cols % BLOCK_K == 0 && a->lda1 >= a->C1 + (n_prob - 1) * a->prob_a_cols,
+                "gemm_tc: problem batch: bad A1 column stride");
+    p.n_par = n_prob;
+    p.par_a_cols = a->prob_a_cols;
+    p.par_w_rows = (int)a->prob_w_rows;
+    p.par_out_stride = a->prob_out_stride;
+  }
   p.trace = g_trace_buf;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE(a->w_group_tiles == 0 || (is_linear && a->C2 == 0 && !a->out_nchw), "gemm_tc: grouped weights need taps == 1");
@@ -1247,7 +1262,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   CUtensorMap ma1, ma2, mw;
   int rc;
   if (is_linear) {
-    rc = encode_rows_map(&ma1, a->a1, M, a->C1, a->lda1);
+    rc = encode_rows_map(&ma1, a->a1, M, a->C1 + (n_prob - 1) * (n_prob > 1 ? a->prob_a_cols : 0), a->lda1);
   } else {
     // tile = 128 consecutive pixels of the channels-last image stack
     const int W = a->W, H = a->H;
@@ -1326,7 +1341,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   {
     int mode = 1;   // VDM_GEMM_CTA2: 0 = never, 1 = heuristic (default), 2 = whenever legal (tests), 3 = heuristic + 512x128 pair tiles
     if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
-    const bool legal = !a->out_nchw && a->N % 128 == 0 && a->w_group_tiles == 0 && a->a1_mode <= 1;
+    const bool legal = !a->out_nchw && a->N % 128 == 0 && a->w_group_tiles == 0 && a->a1_mode <= 1 && n_prob == 1;
     const int bn2 = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
     const int64_t pair_tiles = ((M + 255) / 256) * (a->N / bn2);
     // Two measured ceilings (profiles/gemm_trace.py): TMA operand delivery from L2 saturates near 10 TB/s over
@@ -1341,7 +1356,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   }
   {
     const int64_t groups = a->w_group_tiles ? ((M + BLOCK_M - 1) / BLOCK_M + a->w_group_tiles - 1) / a->w_group_tiles : 1;
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N * groups};
+    uint64_t dims[2] = {(uint64_t)K, n_prob > 1 ? (uint64_t)a->prob_w_rows * n_prob : (uint64_t)a->N * groups};
     uint64_t st[2] = {2, (uint64_t)K * 2};
     uint32_t box[2] = {BLOCK_K, (uint32_t)(cta2 ? block_n / 2 : block_n)};
     rc = encode_map(&mw, a->w, 2, dims, st, box);
@@ -1353,6 +1368,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     if (m_sub == 2) return launch<128, 2, 4, true>(ma1, ma2, mw, p, stream);
     return launch<128, 1, 7, true>(ma1, ma2, mw, p, stream);
   }
+  if (n_prob > 1)
+    p.tiles_per_par = ((a->N + block_n - 1) / block_n) * (int)((M + BLOCK_M * m_sub - 1) / (BLOCK_M * m_sub));
   switch (block_n) {
     case 128:
       if (m_sub == 2) return launch<128, 2, 4>(ma1, ma2, mw, p, stream);
@@ -1381,6 +1398,8 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   p.bias = a->bias; p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.stats_out = a->stats_out;
   p.stats_via_smem = 1;
+  p.n_par = 4;
+  p.par_w_rows = a->N;
   p.trace = g_trace_buf;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE((Wl <= 128 && 128 % Wl == 0) || Wl % 128 == 0, "gemm_tc: unsupported width %d", Wl);

@@ -32,7 +32,7 @@ def _nbytes(*tensors):
 
 def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
          out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
-         w_group_tiles=0):
+         w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0):
     """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm)."""
     lib = _lib.load()
     g = GemmArgs()
@@ -48,6 +48,7 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
         g.a1, g.lda1 = ptr(a1), 0
     g.a2, g.w = ptr(a2), ptr(w)
     g.w_group_tiles = w_group_tiles
+    g.n_prob, g.prob_a_cols, g.prob_w_rows, g.prob_out_stride = n_prob, prob_a_cols, prob_w_rows, prob_out_stride
     g.bias = ptr(bias)
     g.rowbias = None if rowbias is None else rowbias.data_ptr()
     g.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
@@ -63,8 +64,8 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     M = n_img * H * W
     K = taps * g.C1 + g.C2
     name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if taps == 9 else '_linear')
-    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K,
-           meta=f'M={M} N={N} K={K} HxW={H}x{W} mode={a1_mode} res={int(residual is not None)} stats={int(stats_out is not None)}')
+    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K * n_prob,
+           meta=f'M={M} N={N} K={K} HxW={H}x{W} mode={a1_mode} res={int(residual is not None)} stats={int(stats_out is not None)}' + (f' x{n_prob}' if n_prob > 1 else ''))
 
 
 def gn_stats(src, n_img, HW, stats):
@@ -134,9 +135,9 @@ def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, o
 
 
 def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv, bias=None, n_blocks=1, r_block_stride=0,
-               zero_fill=True):
+               zero_fill=True, qk_block_stride=0):
     _timed('rpe_expand', lambda: check(_lib.load().vdm_rpe_expand(
-        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, B, T, heads, hd, gpt, int(zero_fill), ptr(bq), ptr(bk),
+        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, qk_block_stride, B, T, heads, hd, gpt, int(zero_fill), ptr(bq), ptr(bk),
         ptr(bv), stream()), 'vdm_rpe_expand'), nbytes=_nbytes(bq, bk, bv))
 
 

@@ -436,14 +436,14 @@ class UNetModel(nn.Module):
             SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
             # the operands are block-diagonal over heads (~85 % structural zeros): zeroed once with the workspace,
             # afterwards only the live entries are rewritten
-            bq = ws.zeros(key + '.bq', (nb, ntg * SW, C), adt)
-            bk = ws.zeros(key + '.bk', (nb, ntg * SW, C), adt)
+            # bk and bq of a block sit back to back, so q -> Sk and k -> Sq run as ONE two-problem GEMM launch
+            bkq = ws.zeros(key + '.bkq', (nb, 2, ntg * SW, C), adt)
             bv = ws.zeros(key + '.bv', (nb, ntg * C, SW), adt)
             ops.rpe_expand(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, C // heads, gpt,
-                           bq, bk, bv, bias=P[key + '.out_b'], n_blocks=nb, r_block_stride=3 * rows * C,
-                           zero_fill=False)
+                           bkq[0, 1], bkq[0, 0], bv, bias=P[key + '.out_b'], n_blocks=nb, r_block_stride=3 * rows * C,
+                           zero_fill=False, qk_block_stride=2 * ntg * SW * C)
             for i, n in enumerate(nodes):
-                tables[n['p']] = (bq[i], bk[i], bv[i])
+                tables[n['p']] = (bkq[i], bv[i])
         return tables
 
     def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask, tables=None):
@@ -480,16 +480,19 @@ class UNetModel(nn.Module):
             SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
             qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            sksq = ws.buf(q + '.sksq', (2, M, SW))
+            sk, sq = sksq[0], sksq[1]
             if pre is not None:
-                bq, bk, bv = pre
+                bkq, bv = pre
+                ops.gemm(qkv[:, :C], bkq.view(2 * ntg * SW, C), SW, out_f32=sksq, w_group_tiles=tpg, C1=C, n_prob=2,
+                         prob_a_cols=C, prob_w_rows=ntg * SW, prob_out_stride=M * SW, **lin)
             else:
                 bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
                 bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
                 bv = ws.buf(q + '.bv', (ntg * C, SW), adt)
                 ops.rpe_expand(R[0], R[1], R[2], B, T, heads, hd, gpt, bq, bk, bv, bias=r_bias)
-            sk, sq = ws.buf(q + '.sk', (M, SW)), ws.buf(q + '.sq', (M, SW))
-            ops.gemm(qkv[:, :C], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
-            ops.gemm(qkv[:, C:2 * C], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
+                ops.gemm(qkv[:, :C], bk, SW, out_f32=sk, w_group_tiles=tpg, C1=C, **lin)
+                ops.gemm(qkv[:, C:2 * C], bq, SW, out_f32=sq, w_group_tiles=tpg, C1=C, **lin)
             pm = ws.zeros(q + '.pm', (M, SW), adt)       # padding columns stay zero forever
             pv = ws.buf(q + '.pv', (M, C))
             ops.attn_temporal_tc(qkv, sk, sq, amask, self.allow_interactions_between_padding, B, T, HW, heads, hd,
