@@ -174,6 +174,12 @@ int vdm_attn_temporal(const float* qkv, const float* r_q, const float* r_k, cons
                       int32_t HW, int32_t heads, int32_t hd, void* out_a, int32_t out_dtype,
                       vdm_stream_t stream);
 
+/* Lookup-table RPE, use_rpe_net=False (replaces RPE.get_bucket_ids + lookup_table_weight[bucket_ids],
+ * unet.py:326-347).  tables [3][n_buckets][C] (q, k, v nets; n_buckets = 2*beta+1), frame_indices [B][T] int64;
+ * out [3][B*T*T][C] fp32 = the three R tables the attention kernels / vdm_rpe_expand consume. */
+int vdm_rpe_lookup(const float* tables, const int64_t* frame_indices, int32_t B, int32_t T, int32_t C,
+                   int32_t n_buckets, double alpha, double beta, double gamma, float* out, vdm_stream_t stream);
+
 /* ---- temporal attention, tensor-core path (bf16 mode) ------------------------------------------
  * The RPE einsums contract against tables that depend on (batch, frame) but not on the pixel, so over
  * the pixels of one (b, t) they are GEMMs: vdm_rpe_expand builds block-diagonal-over-heads bf16 weight

@@ -11,12 +11,17 @@ _CFG = {
     'tiny_nrb2': dict(image_size=32, num_channels=64, num_res_blocks=2, T=30),
     'c2':        dict(image_size=64, num_channels=128, num_res_blocks=2, T=500),
     'c4':        dict(image_size=128, num_channels=128, num_res_blocks=2, T=1000),
+    # use_rpe_net=False: bucketed lookup-table RPE; alpha < beta < gamma (gamma off the integer grid) exercises all
+    # three pieces of the index function
+    'tiny_lut':  dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, use_rpe_net=False, rp_alpha=3, rp_beta=7,
+                      rp_gamma=20.5),
 }
 
 
 def ref_config(name):
     c = dict(_CFG[name])
-    c.update(rp_alpha=c['T'], rp_beta=c['T'], rp_gamma=c['T'])
+    for k in ('rp_alpha', 'rp_beta', 'rp_gamma'):
+        c.setdefault(k, c['T'])
     return c
 
 
@@ -39,6 +44,12 @@ UNET_CASES = [
          frame_indices=[[0, 1, 2, 10, 11, 12, 13, 14, 0, 0], [3, 7, 9, 11, 12, 13, 20, 21, 22, 23]]),
     dict(name='tiny_nrb2_window', cfg='tiny_nrb2', B=1, F=7, n_obs=[2], n_lat=[5], t=[999],
          frame_indices=[[4, 29, 10, 11, 12, 13, 14]]),
+]
+
+# lookup-table RPE (stored in tests/golden/unet_lut.npz)
+UNET_LUT_CASES = [
+    dict(name='tiny_lut_ragged', cfg='tiny_lut', B=2, F=10, n_obs=[3, 6], n_lat=[5, 4], t=[17, 803],
+         frame_indices=[[0, 1, 2, 10, 11, 12, 13, 14, 0, 0], [3, 7, 9, 11, 12, 13, 20, 25, 28, 29]]),
 ]
 
 

@@ -34,7 +34,8 @@ from improved_diffusion.script_util import (create_gaussian_diffusion,       # n
                                             video_model_and_diffusion_defaults)
 
 from oracle import synth                                                      # noqa: E402
-from oracle.cases import (CHAIN_CASE, DIFFUSION_CASES, STRATEGY_GRID, UNET_CASES, bpd_case_inputs,  # noqa: E402
+from oracle.cases import (CHAIN_CASE, DIFFUSION_CASES, STRATEGY_GRID, UNET_CASES, UNET_LUT_CASES,  # noqa: E402
+                          bpd_case_inputs,
                           fake_eps, model_kwargs_for, ref_config, unet_case_inputs)
 
 
@@ -59,8 +60,8 @@ def build(cfg_name, respacing='', device='cpu'):
     return model.eval(), diffusion
 
 
-def dump_specs():
-    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):
+def dump_specs(names=('tiny', 'tiny_nrb2', 'c2', 'c4')):
+    for name in names:
         model, _ = build(name, device='meta')
         spec = {k: list(v.shape) for k, v in model.state_dict().items()}
         with open(os.path.join(GOLD, f'spec_{name}.json'), 'w') as f:
@@ -86,9 +87,9 @@ def load_ref_model(cfg_name, respacing=''):
     return model, diffusion
 
 
-def dump_unet():
+def dump_unet(cases_list=UNET_CASES, fname='unet.npz'):
     arrays = {}
-    for case in UNET_CASES:
+    for case in cases_list:
         model, _ = load_ref_model(case['cfg'])
         inp = unet_case_inputs(case)
         taps = {}
@@ -109,7 +110,7 @@ def dump_unet():
         for k, v in taps.items():
             arrays[f"{case['name']}/tap/{k}"] = synth.fingerprint(v)
         print('unet', case['name'], float(out.abs().max()), float(out.std()))
-    np.savez_compressed(os.path.join(GOLD, 'unet.npz'), **arrays)
+    np.savez_compressed(os.path.join(GOLD, fname), **arrays)
 
 
 def dump_diffusion():
@@ -222,6 +223,10 @@ def dump_chain():
 if __name__ == '__main__':
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['lut']:       # only the lookup-table RPE fixtures (leaves the other files untouched)
+        dump_specs(('tiny_lut',))
+        dump_unet(UNET_LUT_CASES, 'unet_lut.npz')
+        sys.exit(0)
     dump_specs()
     dump_strategies()
     dump_diffusion()

@@ -33,9 +33,10 @@ CHANNEL_MULT = {256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4),
 def model_config(image_size, num_channels=128, num_res_blocks=2, num_heads=4,
                  attention_resolutions='16,8', use_scale_shift_norm=True,
                  use_spatial_encoding=True, allow_interactions_between_padding=True,
-                 learn_sigma=False, **_ignored):
+                 learn_sigma=False, use_rpe_net=True, rp_alpha=None, rp_beta=None, rp_gamma=None, **_ignored):
     """Architecture facts the oracle needs (script_util.py:229-300)."""
     return dict(
+        rpe_net=use_rpe_net, rp=(rp_alpha, rp_beta, rp_gamma),
         image_size=image_size, ch=num_channels, nrb=num_res_blocks, heads=num_heads,
         mult=CHANNEL_MULT[image_size],
         attn_ds=tuple(image_size // int(r) for r in attention_resolutions.split(',')),
@@ -134,7 +135,24 @@ def rpe_table(sd, p, temb, dist, heads):
     return r.view(B, T, T, heads, C // heads)
 
 
-def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact, with_rpe):
+def rpe_bucket_ids(dist, alpha, beta, gamma):
+    """Piecewise index function of the lookup-table RPE (unet.py:326-338, eq. 18 of arXiv 2107.14222): identity up to
+    alpha, logarithmic up to gamma, clipped at beta; float32 arithmetic and truncation as the reference does them."""
+    ids = dist.clone()
+    far = ids.abs() > alpha
+    if far.any():
+        coef = torch.log(ids[far].abs() / alpha) / math.log(gamma / alpha)
+        mag = torch.minimum(torch.tensor(beta), alpha + coef * (beta - alpha)).int()
+        ids[far] = mag * torch.sign(ids[far])
+    return ids
+
+
+def rpe_lookup(sd, p, dist, rp):
+    """R[b,i,j,h,f] = table[bucket(dist)] (unet.py:340-347); negative buckets index from the end of the table."""
+    return sd[p + 'lookup_table_weight'][rpe_bucket_ids(dist, *rp)]
+
+
+def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact, with_rpe, rp=None):
     """unet.py:471-540.  x: (B, D, C, L) attends over the last axis L."""
     B, D, C, L = x.shape
     hd = C // heads
@@ -148,9 +166,12 @@ def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact,
     if with_rpe:
         dist = frame_indices[:, :, None] - frame_indices[:, None, :]
         tb = temb.view(B, L, -1)
-        r_k = rpe_table(sd, p + 'rpe_k.rpe_net.', tb, dist, heads)
-        r_q = rpe_table(sd, p + 'rpe_q.rpe_net.', tb, dist, heads)
-        r_v = rpe_table(sd, p + 'rpe_v.rpe_net.', tb, dist, heads)
+        if p + 'rpe_k.lookup_table_weight' in sd:          # use_rpe_net=False
+            r_k, r_q, r_v = (rpe_lookup(sd, p + f'rpe_{n}.', dist, rp) for n in 'kqv')
+        else:
+            r_k = rpe_table(sd, p + 'rpe_k.rpe_net.', tb, dist, heads)
+            r_q = rpe_table(sd, p + 'rpe_q.rpe_net.', tb, dist, heads)
+            r_v = rpe_table(sd, p + 'rpe_v.rpe_net.', tb, dist, heads)
         logits = logits + torch.einsum('bdhtf,btshf->bdhts', q, r_k)
         logits = logits + torch.einsum('bdhtf,btshf->bdhts', k * scale, r_q).transpose(-1, -2)
     if attn_mask is not None:
@@ -179,7 +200,7 @@ def factorized_attention(sd, p, x, temb, frame_indices, attn_mask, T, cfg):
     B = BT // T
     xt = x.view(B, T, C, H, W).permute(0, 3, 4, 2, 1).reshape(B, H * W, C, T)
     xt = rpe_attention(sd, p + 'temporal_attention.', xt, temb, frame_indices,
-                       attn_mask.reshape(B, T), cfg['heads'], cfg['pad_interact'], True)
+                       attn_mask.reshape(B, T), cfg['heads'], cfg['pad_interact'], True, rp=cfg.get('rp'))
     xs = xt.view(B, H, W, C, T).permute(0, 4, 3, 1, 2).reshape(B, T, C, H * W)
     xs = rpe_attention(sd, p + 'spatial_attention.', xs, temb, None, None,
                        cfg['heads'], cfg['pad_interact'], False)

@@ -58,7 +58,7 @@ def test_schedule_tables_bit_exact(golden, case):
 
 def test_state_dict_keys_and_shapes_match_reference(golden):
     from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
-    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):
+    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4', 'tiny_lut'):     # tiny_lut: use_rpe_net=False lookup tables
         kw = video_model_and_diffusion_defaults()
         kw.update(cases.ref_config(name))
         with torch.device('meta'):

@@ -553,6 +553,24 @@ def test_rpe_tables_batched_over_blocks_equal_per_block_calls():
     assert torch.equal(zq, bq) and torch.equal(zk, bk) and torch.equal(zv, bv)
 
 
+@pytest.mark.parametrize('alpha,beta,gamma', [(3, 7, 20.5), (30, 30, 30), (2, 5, 9.5), (1, 12, 40.25)])
+def test_rpe_lookup_matches_oracle_bucket_function(alpha, beta, gamma):
+    """use_rpe_net=False: table[bucket(distance)] with the reference's piecewise bucket function (oracle restatement
+    of unet.py:326-347; gamma is kept off the integer grid, where the reference itself is 1-ulp fragile)."""
+    from oracle import unet_oracle as U
+    o = ops()
+    B, T, Cc = 2, 9, 64
+    fi = torch.tensor([[0, 1, 2, 3, 5, 8, 13, 21, 29], [29, 4, 4, 0, 17, 18, 9, 25, 2]])
+    tables = rnd(3, 2 * beta + 1, Cc, seed=3)
+    out = torch.empty(3, B * T * T, Cc, device='cuda')
+    o.rpe_lookup(tables, fi.cuda(), B, T, Cc, alpha, beta, gamma, out)
+    dist = fi[:, :, None] - fi[:, None, :]
+    ids = U.rpe_bucket_ids(dist, alpha, beta, gamma)
+    for net in range(3):
+        ref = tables[net].cpu()[ids].reshape(B * T * T, Cc)
+        assert torch.equal(out[net].cpu(), ref)
+
+
 @pytest.mark.parametrize('respacing', ['', 'ddim10'])
 def test_sampler_kernels_match_oracle(respacing):
     from video_diffusion_b200.gaussian_diffusion import device_tables

@@ -47,9 +47,9 @@ def tap_name(node):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
-@pytest.mark.parametrize('case', cases.UNET_CASES, ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES, ids=lambda c: c['name'])
 def test_forward_matches_reference_and_oracle(golden, case, dtype):
-    g = golden.npz('unet')
+    g = golden.npz('unet_lut' if case in cases.UNET_LUT_CASES else 'unet')
     model, _ = build_model(case['cfg'], golden, dtype)
     model.use_cuda_graph = False
     inp = cases.unet_case_inputs(case)
@@ -134,7 +134,7 @@ def test_unsupported_paths_raise(golden):
     kw = video_model_and_diffusion_defaults()
     kw.update(cases.ref_config('tiny'))
     with pytest.raises(NotImplementedError):
-        create_video_model_and_diffusion(**dict(kw, use_rpe_net=False))
+        create_video_model_and_diffusion(**dict(kw, cond_emb_type='duplicate'))
     with pytest.raises(AssertionError):
         create_video_model_and_diffusion(**dict(kw, rp_alpha=None, rp_beta=None, rp_gamma=None))
     model, _ = create_video_model_and_diffusion(**kw)

@@ -54,9 +54,9 @@ def test_schedule_tables_and_sampler_math(golden, case):
         np.testing.assert_allclose(v.numpy(), g[f'{n}/bpd/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
 
 
-@pytest.mark.parametrize('case', cases.UNET_CASES, ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES, ids=lambda c: c['name'])
 def test_unet_forward_matches_reference(golden, case):
-    g = golden.npz('unet')
+    g = golden.npz('unet_lut' if case in cases.UNET_LUT_CASES else 'unet')
     spec = golden.json('spec_' + case['cfg'])
     sd = synth.make_state_dict(spec, seed=1)
     cfg = U.model_config(**cases.ref_config(case['cfg']))

@@ -469,6 +469,36 @@ __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict
   }
 }
 
+// Lookup-table RPE (use_rpe_net=False, unet.py:326-347): R[net][(b*T+i)*T+j][:] = table[net][bucket(d)][:] with
+// d = frame_indices[b][i] - frame_indices[b][j] and the piecewise bucket function of eq. 18 in arXiv 2107.14222,
+// evaluated in float32 with the reference's operation order (no FMA contraction) and truncation; a negative bucket
+// indexes the table from its end, like the reference's tensor indexing.
+__global__ void __launch_bounds__(256) rpe_lookup_kernel(const float* __restrict__ tables, const long long* __restrict__ fi,
+                                                          int B, int T, int C, int n_buckets, double alpha, float alpha_f,
+                                                          float beta_f, float beta_minus_alpha, float log_ratio,
+                                                          float* __restrict__ out) {
+  const int C4 = C / 4, rows = B * T * T;
+  const long long total = (long long)3 * rows * C4;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(v % C4);
+    const long long rr = v / C4;
+    const int row = (int)(rr % rows), net = (int)(rr / rows);
+    const int bi = row / T, j = row - bi * T, b = bi / T;
+    const long long d = fi[bi] - fi[b * T + j];
+    const long long ad = d < 0 ? -d : d;
+    long long bucket = d;
+    if ((double)ad > alpha) {
+      const float coef = __fdiv_rn(logf(__fdiv_rn((float)ad, alpha_f)), log_ratio);
+      const float val = __fadd_rn(alpha_f, __fmul_rn(coef, beta_minus_alpha));
+      const long long mag = (long long)(int)fminf(beta_f, val);
+      bucket = d < 0 ? -mag : mag;
+    }
+    if (bucket < 0) bucket += n_buckets;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(tables + ((size_t)net * n_buckets + bucket) * C) + c4);
+    reinterpret_cast<float4*>(out + ((size_t)net * rows + row) * C)[c4] = t;
+  }
+}
+
 }  // namespace
 }  // namespace vdm
 
@@ -627,5 +657,20 @@ extern "C" int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int32_t* et
     rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices, wd, bd,
                                                                     B, T, C, (float*)out);
   VDM_AFTER_LAUNCH("rpe_hidden");
+  return 0;
+}
+
+extern "C" int vdm_rpe_lookup(const float* tables, const int64_t* frame_indices, int32_t B, int32_t T, int32_t C,
+                              int32_t n_buckets, double alpha, double beta, double gamma, float* out,
+                              vdm_stream_t stream) {
+  VDM_REQUIRE(tables && frame_indices && out, "rpe_lookup: NULL pointer");
+  VDM_REQUIRE(C % 4 == 0 && B > 0 && T > 0, "rpe_lookup: bad shape");
+  VDM_REQUIRE(alpha > 0 && (double)n_buckets >= 2 * beta + 1, "rpe_lookup: table has %d rows, needs 2*beta+1", n_buckets);
+  const long long total = (long long)3 * B * T * T * (C / 4);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  rpe_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tables, (const long long*)frame_indices, B, T, C, n_buckets,
+                                                            alpha, (float)alpha, (float)beta, (float)(beta - alpha),
+                                                            (float)log(gamma / alpha), out);
+  VDM_AFTER_LAUNCH("rpe_lookup");
   return 0;
 }

@@ -134,6 +134,13 @@ def attn_temporal(qkv, r_q, r_k, r_v, mask, pad_interact, B, T, HW, heads, hd, o
            nbytes=_nbytes(qkv, out))
 
 
+def rpe_lookup(tables, frame_indices, B, T, Cc, alpha, beta, gamma, out):
+    """Lookup-table RPE (use_rpe_net=False): out [3][B*T*T][C] from tables [3][2*beta+1][C]."""
+    _timed('rpe_lookup', lambda: check(_lib.load().vdm_rpe_lookup(
+        ptr(tables), ptr(frame_indices), B, T, Cc, tables.shape[1], float(alpha), float(beta), float(gamma), ptr(out),
+        stream()), 'vdm_rpe_lookup'), nbytes=_nbytes(out))
+
+
 def rpe_expand(r_q, r_k, r_v, B, T, heads, hd, gpt, bq, bk, bv, bias=None, n_blocks=1, r_block_stride=0,
                zero_fill=True, qk_block_stride=0):
     _timed('rpe_expand', lambda: check(_lib.load().vdm_rpe_expand(

@@ -54,10 +54,9 @@ class UNetModel(nn.Module):
         super().__init__()
         if dims != 2 or not conv_resample or num_classes is not None:
             raise NotImplementedError('only dims=2, conv_resample=True, num_classes=None are supported')
-        if not use_rpe_net:
-            raise NotImplementedError('bucketed lookup-table RPE (use_rpe_net=False) is not supported yet')
         if bucket_params is None:   # the reference asserts this too (unet.py:423-427)
             raise AssertionError('rp_alpha / rp_beta / rp_gamma must be set')
+        self.use_rpe_net, self.bucket_params = bool(use_rpe_net), dict(bucket_params)
         if num_heads_upsample not in (-1, num_heads):
             raise NotImplementedError('num_heads_upsample != num_heads')
         self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
@@ -171,7 +170,11 @@ class UNetModel(nn.Module):
             self._lin(q + '.qkv', c, 3 * c)
             self._lin(q + '.proj_out', c, c, zero=True)
             self._gn(q + '.norm', c)
-            if which == 'temporal_attention':
+            if which == 'temporal_attention' and not self.use_rpe_net:
+                for r in ('rpe_q', 'rpe_k', 'rpe_v'):      # bucketed lookup table (unet.py:326-328), zero-initialised
+                    self._reg(f'{q}.{r}.lookup_table_weight',
+                              torch.zeros(2 * self.bucket_params['beta'] + 1, self.num_heads, c // self.num_heads))
+            elif which == 'temporal_attention':
                 for r in ('rpe_q', 'rpe_k', 'rpe_v'):
                     self._lin(f'{q}.{r}.rpe_net.embed_distances', 3, c)
                     self._lin(f'{q}.{r}.rpe_net.embed_diffusion_time', self.time_embed_dim, c)
@@ -255,6 +258,10 @@ class UNetModel(nn.Module):
                     put(q + '.proj_w', sd[q + '.proj_out.weight'], adt); put(q + '.proj_b', sd[q + '.proj_out.bias'])
                 q = p + '.temporal_attention'
                 nets = ('rpe_q', 'rpe_k', 'rpe_v')
+                if not self.use_rpe_net:
+                    put(q + '.rpe_lut', torch.stack([sd[f'{q}.{r}.lookup_table_weight'].reshape(-1, node['C'])
+                                                     for r in nets]))
+                    continue
                 put(q + '.rpe_wd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.weight'] for r in nets]))
                 put(q + '.rpe_bd', torch.stack([sd[f'{q}.{r}.rpe_net.embed_distances.bias'] for r in nets]))
                 put(q + '.rpe_out_w', torch.cat([sd[f'{q}.{r}.rpe_net.out.weight'] for r in nets]), adt)
@@ -271,9 +278,12 @@ class UNetModel(nn.Module):
                 if node['kind'] == 'up' and adt == torch.bfloat16:
                     put(p + '.wfold', fold_upsample_weights(sd[p + '.weight']), adt)
         put('emb_w', torch.cat(emb_w)); put('emb_b', torch.cat(emb_b))
-        put('rpe_t_w', torch.cat(rpe_w)); put('rpe_t_b', torch.cat(rpe_b))
+        if rpe_w:
+            put('rpe_t_w', torch.cat(rpe_w)); put('rpe_t_b', torch.cat(rpe_b))
         if adt == torch.bfloat16:
-            put('emb_w_a', torch.cat(emb_w), adt); put('rpe_t_w_a', torch.cat(rpe_w), adt)
+            put('emb_w_a', torch.cat(emb_w), adt)
+            if rpe_w:
+                put('rpe_t_w_a', torch.cat(rpe_w), adt)
         put('out_gn_w', sd['out.0.weight']); put('out_gn_b', sd['out.0.bias'])
         put('out_w', conv_w('out.2.weight'), adt); put('out_b', sd['out.2.bias'])
         if self.spatial_encoding is not None:
@@ -407,7 +417,7 @@ class UNetModel(nn.Module):
         P, adt, heads = self._packed, self.compute_dtype, self.num_heads
         rows = B * T * T
         tables, groups = {}, {}
-        if rows % 128:
+        if rows % 128 or not self.use_rpe_net:
             return tables
         h, w = H, W
         for node in self.plan:
@@ -462,7 +472,13 @@ class UNetModel(nn.Module):
         tc_path = self._tc_temporal_ok(T, C, HW)
         rows = B * T * T
         pre = tables.get(p) if tables else None
-        if pre is None:
+        if pre is None and not self.use_rpe_net:
+            # lookup-table RPE: the three tables are gathered by the bucketed frame distances (unet.py:326-347)
+            Rall = ws.buf(q + '.Rlut', (3, rows, C))
+            bp = self.bucket_params
+            ops.rpe_lookup(P[q + '.rpe_lut'], ws.fi, B, T, C, bp['alpha'], bp['beta'], bp['gamma'], Rall)
+            R, r_bias = [Rall[0], Rall[1], Rall[2]], None
+        elif pre is None:
             hid = ws.buf(q + '.hid', (3, rows, C), adt)
             off = node['rpe_off']
             ops.rpe_hidden(rpe_et[:, off:off + 3 * C], ws.fi, P[q + '.rpe_wd'], P[q + '.rpe_bd'], B, T, C, hid)
@@ -540,7 +556,7 @@ class UNetModel(nn.Module):
         if per_frame_t:
             t_frame = ws.t_override
         emb_out = ws.buf('emb_out', (N, P['emb_w'].shape[0]))
-        rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0]))
+        rpe_et = ws.buf('rpe_et', (N, P['rpe_t_w'].shape[0])) if self.use_rpe_net else None
         lin = dict(n_img=N, H=1, W=1, taps=1)
 
         def embedding_branch():
@@ -558,10 +574,12 @@ class UNetModel(nn.Module):
                 ops.gn_apply(embs, None, N, 1, 1, embs_b)
                 ops.gn_apply(emb, None, N, 1, 1, emb_b)
                 ops.gemm(embs_b, P['emb_w_a'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
-                ops.gemm(emb_b, P['rpe_t_w_a'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+                if self.use_rpe_net:
+                    ops.gemm(emb_b, P['rpe_t_w_a'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
             else:
                 ops.gemm(embs, P['emb_w'], P['emb_w'].shape[0], bias=P['emb_b'], out_f32=emb_out, **lin)
-                ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
+                if self.use_rpe_net:
+                    ops.gemm(emb, P['rpe_t_w'], P['rpe_t_w'].shape[0], bias=P['rpe_t_b'], out_f32=rpe_et, **lin)
 
         # The embedding path and the RPE tables depend only on the timesteps and frame indices: they run on a side
         # stream (a parallel branch of the CUDA graph) under the input conv and the first block, where their small
