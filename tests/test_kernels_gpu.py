@@ -116,6 +116,9 @@ HALO_CASES = [
     (7, 16, 16, 192, 384, 0, True),      # 192-wide pair tiles, odd image count
     (4, 16, 16, 64, 192, 0, False),
     (6, 16, 32, 64, 128, 0, False),      # non-square image
+    (12, 8, 8, 128, 256, 0, True),       # 8x8: two images per 128-row tile, rows interleaved (y, image, x)
+    (7, 8, 8, 64, 512, 128, False),      # 8x8, odd image count, fused skip operand
+    (4, 8, 8, 192, 256, 0, False),
 ]
 
 

@@ -255,7 +255,9 @@ struct SmemLayout {
 // ===================== epilogue role (warps 2..9), shared by the kernels below =====================
 // tmem_full_bar0 / tmem_empty_bar0: shared-memory addresses of the two-entry barrier arrays of the accumulator stages.
 // stab: zeroed shared-memory table [4 lane quarters][stat_imgs][2][BLOCK_N] of fp32 GroupNorm partial sums.
-template <int BLOCK_N, int M_SUB, int CHUNK, int EPI, bool CTA2>
+// ILV (8x8 level of the halo kernel): the CTA's 128 tile rows are two whole images interleaved by image row,
+// tile row l = (y, image, x) with x fastest, i.e. global row = first + (l>>3 & 1)*64 + (l>>4)*8 + (l&7).
+template <int BLOCK_N, int M_SUB, int CHUNK, int EPI, bool CTA2, bool ILV = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base, float* stab,
                                               int stat_imgs, uint32_t tmem_base,
                                               uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int n_tiles,
@@ -264,6 +266,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
   constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
   constexpr bool STATS = GEN || (EPI & 4) != 0;
+  static_assert(!ILV || (!GEN && M_SUB == 1 && CHUNK == 32), "interleaved 8x8 tiles: lean epilogue, 32-column chunks");
+  auto ilv_row = [](int l) { return ((l >> 3) & 1) * 64 + (l >> 4) * 8 + (l & 7); };   // tile row -> row offset
   auto tmem_full_bar = [&](int a) { return tmem_full_bar0 + 8u * a; };
   auto tmem_empty_bar = [&](int a) { return tmem_empty_bar0 + 8u * a; };
   // TMEM hands each lane one accumulator ROW; writing rows straight to global memory would touch
@@ -308,7 +312,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         const int n = n0 + (jj % N_CHUNKS) * CHUNK + c4;
 #pragma unroll
         for (int i = 0; i < NRES; ++i) {
-          const int orow = m0 + q * 32 + i * RPI + r_sub;
+          const int orow = ILV ? m0 + ilv_row(q * 32 + i * RPI + r_sub) : m0 + q * 32 + i * RPI + r_sub;
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (orow < p.M && n < p.N)
             dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
@@ -385,6 +389,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
       }
       const int n = nb + c4;
       float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 ssum1 = make_float4(0.f, 0.f, 0.f, 0.f), ssq1 = make_float4(0.f, 0.f, 0.f, 0.f);   // ILV: second image
       if constexpr (!GEN) {
         // lean path: N is a multiple of BLOCK_N, exactly one output, no per-image bias / row remap
         const float4 bv = bias_cur;
@@ -406,9 +411,15 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
             v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
           }
           if constexpr (STATS) {
-            ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
-            ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
-            ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+            if (ILV && (((i * RPI) >> 3) & 1)) {   // rows 8..15, 24..31 of the warp belong to the second image
+              ssum1.x += v.x; ssum1.y += v.y; ssum1.z += v.z; ssum1.w += v.w;
+              ssq1.x = fmaf(v.x, v.x, ssq1.x); ssq1.y = fmaf(v.y, v.y, ssq1.y);
+              ssq1.z = fmaf(v.z, v.z, ssq1.z); ssq1.w = fmaf(v.w, v.w, ssq1.w);
+            } else {
+              ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
+              ssq.x = fmaf(v.x, v.x, ssq.x); ssq.y = fmaf(v.y, v.y, ssq.y);
+              ssq.z = fmaf(v.z, v.z, ssq.z); ssq.w = fmaf(v.w, v.w, ssq.w);
+            }
           }
           if constexpr (BF16_OUT) {
             uint2 pk;
@@ -420,7 +431,14 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           }
         };
         auto store_rows = [&](auto* optr, const size_t step) {
-          if (full) {
+          if constexpr (ILV) {   // optr = the tile's first row; every row group has its own offset
+            const size_t ld = step / RPI;
+#pragma unroll
+            for (int i = 0; i < NRES; ++i) {
+              const int off = ilv_row(q * 32 + i * RPI + r_sub);
+              if (full || m0 + off < p.M) finish_row(i, optr + (size_t)off * ld);
+            }
+          } else if (full) {
 #pragma unroll
             for (int i = 0; i < NRES; ++i, optr += step) finish_row(i, optr);
           } else {
@@ -429,10 +447,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
               if (row_first + i * RPI < p.M) finish_row(i, optr);
           }
         };
+        const int row_base = ILV ? m0 : row_first;
         if constexpr (BF16_OUT)
-          store_rows(p.out_bf16 + par * p.par_out_stride + (size_t)row_first * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
+          store_rows(p.out_bf16 + par * p.par_out_stride + (size_t)row_base * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
         else
-          store_rows(p.out_f32 + par * p.par_out_stride + (size_t)row_first * p.ld_out + n, (size_t)RPI * p.ld_out);
+          store_rows(p.out_f32 + par * p.par_out_stride + (size_t)row_base * p.ld_out + n, (size_t)RPI * p.ld_out);
       } else if (n < p.N) {  // N is a multiple of 4 on this path
         const float4 bv = bias_cur;
 #pragma unroll
@@ -478,14 +497,28 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           *reinterpret_cast<float4*>(part + (r_sub * 2 + 0) * CHUNK + c4) = ssum;
           *reinterpret_cast<float4*>(part + (r_sub * 2 + 1) * CHUNK + c4) = ssq;
           __syncwarp();
-          float* trow = tabq + (size_t)(row0 / p.HW - img_first) * 2 * BLOCK_N + (nb - n0);
+          float* trow = tabq + (size_t)(ILV ? 0 : row0 / p.HW - img_first) * 2 * BLOCK_N + (nb - n0);
 #pragma unroll
           for (int idx = lane; idx < 2 * CHUNK; idx += 32) {
             const int k = idx / CHUNK, col = idx - k * CHUNK;
             float sacc = 0.f;
 #pragma unroll
             for (int r = 0; r < RPI; ++r) sacc += part[(r * 2 + k) * CHUNK + col];
-            if (row0 < p.M) trow[k * BLOCK_N + col] += sacc;
+            if (ILV || row0 < p.M) trow[k * BLOCK_N + col] += sacc;   // ILV: every warp holds rows of the first image
+          }
+          if constexpr (ILV) {   // the second image's partial sums, table row 1
+            __syncwarp();
+            *reinterpret_cast<float4*>(part + (r_sub * 2 + 0) * CHUNK + c4) = ssum1;
+            *reinterpret_cast<float4*>(part + (r_sub * 2 + 1) * CHUNK + c4) = ssq1;
+            __syncwarp();
+#pragma unroll
+            for (int idx = lane; idx < 2 * CHUNK; idx += 32) {
+              const int k = idx / CHUNK, col = idx - k * CHUNK;
+              float sacc = 0.f;
+#pragma unroll
+              for (int r = 0; r < RPI; ++r) sacc += part[(r * 2 + k) * CHUNK + col];
+              if (mt0 + 64 < p.M) trow[(2 + k) * BLOCK_N + col] += sacc;
+            }
           }
         } else {
           // direct route: fold the lanes that share a column quad, then add this warp's 32-row partial sums to the
@@ -821,7 +854,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // 1024 B swizzle atom for W >= 8), so A traffic drops from 9 to 3 * (R + 2) / R tile loads per chunk.
 // Activation slots and weight tiles travel in two independent mbarrier rings (SA x A_SLOT, SB x B_SLOT);
 // an optional second operand (fused 1x1 skip projection) appends plain 128-row tiles to the same rings.
-template <int BLOCK_N, int M_SUB, int SA, int SB>
+template <int BLOCK_N, int M_SUB, int SA, int SB, bool ILV = false>
 struct HaloLayout {
   static constexpr int CHUNK = 32;   // columns per epilogue step
   static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -831,7 +864,7 @@ struct HaloLayout {
   static constexpr int B_OFFSET = SA * A_SLOT;
   static constexpr int STG_OFFSET = B_OFFSET + SB * B_SLOT;
   static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
-  static constexpr int STAT_IMGS = 1;                                   // a halo CTA tile lies inside one image
+  static constexpr int STAT_IMGS = ILV ? 2 : 1;                         // a halo CTA tile lies inside one image (ILV: two 8x8 images)
   static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
@@ -839,12 +872,13 @@ struct HaloLayout {
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI>
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
                                                                       const __grid_constant__ CUtensorMap tm_a2,
                                                                       const __grid_constant__ CUtensorMap tm_w,
                                                                       const TcParams p) {
-  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB>;
+  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
+  static_assert(!ILV || M_SUB == 1, "interleaved 8x8 tiles are 128 rows");
   constexpr int CTA_ROWS = BLOCK_M * M_SUB;
   constexpr int TILE_M = 2 * CTA_ROWS;
   const uint32_t cta_rank = cluster_ctarank();
@@ -865,8 +899,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = p.N / BLOCK_N;
   const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
-  const int halo_rows = CTA_ROWS / p.W + 2;
-  const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
+  // ILV: the tile is two whole 8x8 images; the box is (64 ch, 8 x, 2 images, 8 + 2 rows), so a tap's 128 rows are
+  // again one contiguous run of the slot, (image row, image, x)-ordered
+  const int halo_rows = ILV ? p.H + 2 : CTA_ROWS / p.W + 2;
+  const uint32_t halo_bytes = (uint32_t)(halo_rows * (ILV ? 2 * p.W : p.W)) * (BLOCK_K * 2);
 
   for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
     reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
@@ -917,7 +953,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(a_empty(sa), pa ^ 1u, 0);
             if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * halo_bytes);
-            tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            if constexpr (ILV) tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, img, -1, 0);
+            else tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
             if (++sa == SA) {
               sa = 0;
               pa ^= 1u;
@@ -928,10 +965,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
           mbar_wait(a_empty(sa), pa ^ 1u, 0);
           if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * M_SUB * L::A_SUB_BYTES);
+          if constexpr (ILV) {   // tm_a2 is the (C2, x, image, y) view: rows land in the tile's (y, image, x) order
+            tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
+          } else {
 #pragma unroll
-          for (int sub = 0; sub < M_SUB; ++sub)
-            tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
-                             m0 + sub * BLOCK_M, 0, 0, 0);
+            for (int sub = 0; sub < M_SUB; ++sub)
+              tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                               m0 + sub * BLOCK_M, 0, 0, 0);
+          }
           if (++sa == SA) {
             sa = 0;
             pa ^= 1u;
@@ -947,7 +988,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
-      const uint32_t dy_bytes = (uint32_t)p.W * (BLOCK_K * 2);   // one image row of the halo slot
+      const uint32_t dy_bytes = (uint32_t)(ILV ? 2 * p.W : p.W) * (BLOCK_K * 2);   // one image row of the halo slot
       for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -999,7 +1040,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
       }
     }
   } else {
-    epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, true>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
+    epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, true, ILV>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
                                              reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
                                              L::STAT_IMGS, tmem_base,
                                              tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
@@ -1143,14 +1184,14 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
   }
 }
 
-template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI>
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false>
 int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                      cudaStream_t stream) {
-  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB>;
+  using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1173,13 +1214,29 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI>, mh, ma2, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (halo): launch failed: %s", cudaGetErrorString(e));
     return (int)e;
   }
   VDM_AFTER_LAUNCH("gemm_tc_halo");
   return 0;
+}
+
+// interleaved 8x8 tiles: lean epilogue variants only (the caller checked epilogue_variant < 8)
+template <int BLOCK_N, int SA, int SB>
+int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                    cudaStream_t stream) {
+  switch (epilogue_variant(p, BLOCK_N)) {
+    case 0: return launch_halo_inst<BLOCK_N, 1, SA, SB, 0, true>(mh, ma2, mw, p, stream);
+    case 1: return launch_halo_inst<BLOCK_N, 1, SA, SB, 1, true>(mh, ma2, mw, p, stream);
+    case 2: return launch_halo_inst<BLOCK_N, 1, SA, SB, 2, true>(mh, ma2, mw, p, stream);
+    case 3: return launch_halo_inst<BLOCK_N, 1, SA, SB, 3, true>(mh, ma2, mw, p, stream);
+    case 4: return launch_halo_inst<BLOCK_N, 1, SA, SB, 4, true>(mh, ma2, mw, p, stream);
+    case 5: return launch_halo_inst<BLOCK_N, 1, SA, SB, 5, true>(mh, ma2, mw, p, stream);
+    case 6: return launch_halo_inst<BLOCK_N, 1, SA, SB, 6, true>(mh, ma2, mw, p, stream);
+    default: return launch_halo_inst<BLOCK_N, 1, SA, SB, 7, true>(mh, ma2, mw, p, stream);
+  }
 }
 
 template <int BLOCK_N, int M_SUB, int SA, int SB>
@@ -1302,6 +1359,35 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     const int bn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 0));
     const int msub = bn == 128 ? 2 : 1;
     const int rows = BLOCK_M * msub;
+    // 8x8 level: a 128-row tile is two whole images -> interleaved halo tiles (lean epilogues, 256-wide only)
+    const bool ok8 = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
+                     a->W == 8 && a->H == 8 && a->N % 256 == 0 && epilogue_variant(p, 256) < 8 &&
+                     (hmode == 2 || ((M + 255) / 256) * (a->N / 256) >= 40);
+    if (ok8) {
+      CUtensorMap mh, mw2;
+      const uint64_t C = a->C1;
+      // dims (C, x, image, y): the image dimension sits between x and y, so the box lands (y, image, x)-ordered
+      uint64_t dims[5] = {C, 8, (uint64_t)a->n_img, 8, 1};
+      uint64_t st[5] = {2, C * 2, C * 2 * 64, C * 2 * 8, C * 2 * 64 * (uint64_t)a->n_img};
+      uint32_t box[5] = {BLOCK_K, 8, 2, 10, 1};
+      rc = encode_map(&mh, a->a1, 5, dims, st, box);
+      if (rc) return rc;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      uint32_t wbox[2] = {BLOCK_K, 128};
+      rc = encode_map(&mw2, a->w, 2, wdims, wst, wbox);
+      if (rc) return rc;
+      CUtensorMap ma2p = mh;
+      if (a->C2 > 0) {   // the fused 1x1 skip operand through the same (x, image, y) view
+        const uint64_t C2 = a->C2;
+        uint64_t d2[5] = {C2, 8, (uint64_t)a->n_img, 8, 1};
+        uint64_t s2[5] = {2, C2 * 2, C2 * 2 * 64, C2 * 2 * 8, C2 * 2 * 64 * (uint64_t)a->n_img};
+        uint32_t b2[5] = {BLOCK_K, 8, 2, 8, 1};
+        rc = encode_map(&ma2p, a->a2, 5, d2, s2, b2);
+        if (rc) return rc;
+      }
+      return launch_halo_ilv<256, 3, 4>(mh, ma2p, mw2, p, stream);
+    }
     const bool ok = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
                     bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
