@@ -160,10 +160,15 @@ def test_conv3x3_halo_kernel(case, monkeypatch):
     assert relerr(out_b, ref) < 6e-3
 
 
-@pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128)])
-def test_upsample_conv_folded_into_parity_convs(case):
-    """nearest-x2 + conv3x3 as four 2x2 convs on the low-res input (a1_mode 3) vs F.interpolate + F.conv2d."""
+@pytest.mark.parametrize('halo', ['0', '2'], ids=['plain', 'halo'])
+@pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128), (5, 64, 64, 128, 256),
+                                  (3, 128, 128, 64, 128), (7, 32, 64, 64, 384)])
+def test_upsample_conv_folded_into_parity_convs(case, halo, monkeypatch):
+    """nearest-x2 + conv3x3 as four 2x2 convs on the low-res input (a1_mode 3) vs F.interpolate + F.conv2d; `halo`:
+    the variant that keeps both vertical parities of a tile as two accumulators sharing every activation box (low-res
+    widths 16 / 32 / 64; other shapes fall back to the plain kernel)."""
     from video_diffusion_b200.unet import fold_upsample_weights
+    monkeypatch.setenv('VDM_GEMM_HALO', halo)
     o = ops()
     n, H, W, C1, N = case                      # H, W: OUTPUT resolution
     x = rnd(n, C1, H // 2, W // 2, seed=1).bfloat16().float()
@@ -191,7 +196,9 @@ def test_upsample_conv_folded_into_parity_convs(case):
     o.gemm(nhwc(x).bfloat16(), wf, N, n_img=n, H=H, W=W, taps=4, a1_mode=3, bias=bias, out_f32=out, stats_out=st, C1=C1)
     assert relerr(out, nhwc(ref)) < 2e-5
     if st is not None:
-        assert relerr(st.double()[:, 0] / 2 ** 24, _chan_stats(from_nhwc(out, n, H, W))[:, 0]) < 2e-6
+        cs = _chan_stats(from_nhwc(out, n, H, W))
+        assert relerr(st.double()[:, 0] / 2 ** 24, cs[:, 0]) < 2e-6
+        assert relerr(st.double()[:, 1] / 2 ** 24, cs[:, 1]) < 2e-6
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['simt_f32', 'tcgen05_bf16'])

@@ -257,13 +257,17 @@ struct SmemLayout {
 // stab: zeroed shared-memory table [4 lane quarters][stat_imgs][2][BLOCK_N] of fp32 GroupNorm partial sums.
 // ILV (8x8 level of the halo kernel): the CTA's 128 tile rows are two whole images interleaved by image row,
 // tile row l = (y, image, x) with x fastest, i.e. global row = first + (l>>3 & 1)*64 + (l>>4)*8 + (l&7).
-template <int BLOCK_N, int M_SUB, int CHUNK, int EPI, bool CTA2, bool ILV = false>
+// UPF (folded-upsample halo kernel): the M_SUB = 2 accumulators of a CTA are the two vertical output parities
+// (a = 0, 1) of the SAME 128 low-resolution pixels; the tile's `par` is the horizontal parity b.
+template <int BLOCK_N, int M_SUB, int CHUNK, int EPI, bool CTA2, bool ILV = false, bool UPF = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base, float* stab,
                                               int stat_imgs, uint32_t tmem_base,
                                               uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int n_tiles,
                                               int n_tiles_n, int work_id0, int work_step, uint32_t cta_rank, int warp,
                                               int lane) {
-  constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
+  constexpr int CTA_M = BLOCK_M * (UPF ? 1 : M_SUB);          // distinct A rows per CTA
+  constexpr int TILE_M = CTA_M * (CTA2 ? 2 : 1);
+  static_assert(!UPF || ((EPI & 8) != 0 && M_SUB == 2), "folded upsample: generic epilogue, two parity accumulators");
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
   constexpr bool STATS = GEN || (EPI & 4) != 0;
   static_assert(!ILV || (!GEN && M_SUB == 1 && CHUNK == 32), "interleaved 8x8 tiles: lean epilogue, 32-column chunks");
@@ -294,13 +298,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
       tl = tile - par * p.tiles_per_par;
     }
     const int n0 = (tl % n_tiles_n) * BLOCK_N;
-    const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * (BLOCK_M * M_SUB);
+    const int mt0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * CTA_M;
     // GroupNorm statistics go through a shared-memory table (one global atomic per (image, channel) and tile
     // instead of one per 32 rows) whenever this CTA's rows span at most stat_imgs images.  Every (quarter, column)
     // entry has exactly one writer warp, so plain read-modify-writes in a fixed order: deterministic.
     const int img_first = mt0 / p.HW;
     const bool use_tab = STATS && p.stats_out != nullptr && p.stats_via_smem &&
-                         (mt0 + BLOCK_M * M_SUB - 1) / p.HW - img_first < stat_imgs;
+                         (mt0 + CTA_M - 1) / p.HW - img_first < stat_imgs;
     float* const tabq = stab + (size_t)q * stat_imgs * 2 * BLOCK_N;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -352,7 +356,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
 #pragma unroll 1
     for (int jj = half; jj < TOTAL_CHUNKS; jj += 2) {
       const int sub = jj / N_CHUNKS, j = jj - sub * N_CHUNKS;
-      const int m0 = mt0 + sub * BLOCK_M;
+      const int m0 = mt0 + (UPF ? 0 : sub * BLOCK_M);
+      const int opar = UPF ? sub * 2 + par : par;   // output parity (a, b) of this accumulator
       const int row = m0 + q * 32 + lane;
       uint32_t acc[CHUNK];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
@@ -476,7 +481,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
             if (p.a1_mode == 3) {   // low-res pixel (img, y, x) of parity (a, b) -> high-res row
               const int img = orow / p.HW, rem = orow - img * p.HW;
               const int yy = rem / p.W, xx = rem - yy * p.W;
-              drow = ((size_t)img * 2 * p.H + 2 * yy + (par >> 1)) * (2 * p.W) + 2 * xx + (par & 1);
+              drow = ((size_t)img * 2 * p.H + 2 * yy + (opar >> 1)) * (2 * p.W) + 2 * xx + (opar & 1);
             }
             if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
             if (p.out_bf16) {
@@ -1058,6 +1063,180 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------
+// Folded nearest-x2 upsample + 3x3 conv (four 2x2 parity convs on the low-resolution input), halo variant.
+// A CTA pair owns 256 low-res pixels x 128 output channels x ONE horizontal parity b and keeps BOTH vertical
+// parities a = 0, 1 as two accumulators: per (64-channel chunk, horizontal tap j) one halo box (the CTA's R rows
+// plus the row above and below) serves all four (a, vertical tap i) combinations -- the tap of parity a reads the
+// slot at a start offset of (a + i) image rows.  A traffic: 2 boxes per chunk instead of 8 tile loads.
+template <int SA, int SB>
+struct UpfoldHaloLayout {
+  static constexpr int BLOCK_N = 128, CHUNK = 32;
+  static constexpr int A_SLOT = 2 * BLOCK_M * BLOCK_K * 2;     // (R + 2) * W <= 256 pixel rows for W <= 64
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the weight tile
+  static constexpr int B_SLOT = B_BYTES;
+  static constexpr int B_OFFSET = SA * A_SLOT;
+  static constexpr int STG_OFFSET = B_OFFSET + SB * B_SLOT;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * (CHUNK + 4) * 4;
+  static constexpr int STAT_IMGS = 1;
+  static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+  static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int SA, int SB>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
+                                                                             const __grid_constant__ CUtensorMap tm_w,
+                                                                             const TcParams p) {
+  using L = UpfoldHaloLayout<SA, SB>;
+  constexpr int BLOCK_N = L::BLOCK_N, CTA_ROWS = BLOCK_M, TILE_M = 2 * CTA_ROWS;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int work_id0 = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = p.N / BLOCK_N;
+  const int n_tiles = 2 * p.tiles_per_par;                    // tile = b * tiles_per_par + m_tile * n_tiles_n + n_tile
+  const int halo_rows = CTA_ROWS / p.W + 2;
+  const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
+
+  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
+    reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * SA + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS * 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(tmem_cols<BLOCK_N, 2>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = work_id0; tile < n_tiles; tile += work_step) {
+        const int b = tile / p.tiles_per_par, tl = tile - b * p.tiles_per_par;
+        const int n0 = (tl % n_tiles_n) * BLOCK_N;
+        const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * CTA_ROWS;
+        const int img = m0 / p.HW;
+        const int y0 = (m0 - img * p.HW) / p.W;
+        for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
+          for (int j = 0; j < 2; ++j) {
+            mbar_wait(a_empty(sa), pa ^ 1u, 0);
+            if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * halo_bytes);
+            tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, b ? j : j - 1, y0 - 1, 0,
+                             img);
+            if (++sa == SA) {
+              sa = 0;
+              pa ^= 1u;
+            }
+            for (int ai = 0; ai < 4; ++ai) {   // (a, i) = (0,0), (0,1), (1,0), (1,1): the MMA thread's order
+              const int a = ai >> 1, i = ai & 1;
+              mbar_wait(b_empty(sb), pb ^ 1u, 4);
+              if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::B_BYTES);
+              tma_load_2d_2cta(smem_base + L::B_OFFSET + sb * L::B_SLOT, &tm_w, b_full(sb),
+                               ((i * 2 + j) * p.c1_chunks + chunk) * BLOCK_K,
+                               (a * 2 + b) * p.N + n0 + (int)cta_rank * (BLOCK_N / 2));
+              if (++sb == SB) {
+                sb = 0;
+                pb ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = instr_desc<BLOCK_N, 256>();
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      const uint32_t dy_bytes = (uint32_t)p.W * (BLOCK_K * 2);
+      for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 2 * BLOCK_N);
+        uint32_t started[2] = {0u, 0u};     // per vertical parity: has its accumulator been written in this tile?
+        const int n_units = 2 * p.c1_chunks;
+        for (int u = 0; u < n_units; ++u) {
+          mbar_wait(a_full(sa), pa, 1);
+          const uint32_t a_slot = smem_base + sa * L::A_SLOT;
+#pragma unroll
+          for (int ai = 0; ai < 4; ++ai) {
+            const int a = ai >> 1, i = ai & 1;
+            mbar_wait(b_full(sb), pb, 5);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_desc = make_smem_desc(a_slot + (uint32_t)(a + i) * dy_bytes);
+            const uint64_t b_desc = make_smem_desc(smem_base + L::B_OFFSET + sb * L::B_SLOT);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_2cta(tmem_acc + (uint32_t)(a * BLOCK_N), a_desc + 2u * k, b_desc + 2u * k, idesc,
+                             started[a] | (uint32_t)k);
+            started[a] = 1u;
+            umma_commit_2cta(b_empty(sb));
+            if (++sb == SB) {
+              sb = 0;
+              pb ^= 1u;
+            }
+          }
+          umma_commit_2cta(a_empty(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        umma_commit_2cta(tmem_full_bar(as));
+      }
+    }
+  } else {
+    epilogue_role<BLOCK_N, 2, L::CHUNK, 8, true, false, true>(
+        p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
+        L::STAT_IMGS, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0, work_step, cta_rank,
+        warp, lane);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N, 2>())
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side: tensor maps
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -1254,6 +1433,43 @@ int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap
     case 9: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 9>(mh, ma2, mw, p, stream);
     default: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 8>(mh, ma2, mw, p, stream);
   }
+}
+
+template <int SA, int SB>
+int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+  using L = UpfoldHaloLayout<SA, SB>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_upfold_halo_kernel<SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (upfold halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = 2 * p.tiles_per_par;
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_upfold_halo_kernel<SA, SB>, mh, mw, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc (upfold halo): launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  VDM_AFTER_LAUNCH("gemm_tc_upfold_halo");
+  return 0;
 }
 
 }  // namespace
@@ -1511,6 +1727,27 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   // pair tiles (256 low-res pixels x 256 / 192 channels per parity) where the layer is wide enough
   int mode = 1;
   if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
+  {
+    // halo variant: both vertical parities of 256 low-res pixels x 128 channels per CTA pair share every activation box
+    const char* e = getenv("VDM_GEMM_HALO");
+    const int hmode = e ? atoi(e) : 1;
+    const int64_t tiles_b = ((M + 255) / 256) * (a->N / 128);
+    if (mode > 0 && hmode > 0 && a->N % 128 == 0 && Wl >= 16 && Wl <= 64 && 128 % Wl == 0 && HWl % 128 == 0 &&
+        (hmode == 2 || 2 * tiles_b >= 40)) {
+      CUtensorMap mh, mwh;
+      uint32_t hbox[5] = {BLOCK_K, (uint32_t)Wl, (uint32_t)(128 / Wl + 2), 1, 1};
+      rc = encode_map(&mh, a->a1, 5, dims, st, hbox);
+      if (rc) return rc;
+      uint64_t wd2[2] = {(uint64_t)K, (uint64_t)a->N * 4};
+      uint64_t ws2[2] = {2, (uint64_t)K * 2};
+      uint32_t wb2[2] = {BLOCK_K, 64};
+      rc = encode_map(&mwh, a->w, 2, wd2, ws2, wb2);
+      if (rc) return rc;
+      p.n_par = 2;
+      p.tiles_per_par = (int)tiles_b;
+      return launch_upfold_halo<3, 8>(mh, mwh, p, stream);
+    }
+  }
   const int bn2 = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 0);
   const int64_t pair_tiles = bn2 ? ((M + 255) / 256) * (a->N / bn2) : 0;
   const bool cta2 = mode > 0 && bn2 && 4 * pair_tiles >= 40;
