@@ -267,7 +267,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
                                               int lane) {
   constexpr int CTA_M = BLOCK_M * (UPF ? 1 : M_SUB);          // distinct A rows per CTA
   constexpr int TILE_M = CTA_M * (CTA2 ? 2 : 1);
-  static_assert(!UPF || ((EPI & 8) != 0 && M_SUB == 2), "folded upsample: generic epilogue, two parity accumulators");
+  static_assert(!UPF || (M_SUB == 2 && (EPI & 1) == 0), "folded upsample: two parity accumulators, no residual");
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
   constexpr bool STATS = GEN || (EPI & 4) != 0;
   static_assert(!ILV || (!GEN && M_SUB == 1 && CHUNK == 32), "interleaved 8x8 tiles: lean epilogue, 32-column chunks");
@@ -306,6 +306,18 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     const bool use_tab = STATS && p.stats_out != nullptr && p.stats_via_smem &&
                          (mt0 + CTA_M - 1) / p.HW - img_first < stat_imgs;
     float* const tabq = stab + (size_t)q * stat_imgs * 2 * BLOCK_N;
+    // UPF, lean path: high-resolution output row of each of this lane's row groups for vertical parity 0 (parity 1
+    // is one output image row = 2W rows further); the same for every chunk of the tile
+    int up_row[UPF ? NRES : 1];
+    if constexpr (UPF && !GEN) {
+#pragma unroll
+      for (int i = 0; i < NRES; ++i) {
+        const int orow = mt0 + q * 32 + i * RPI + r_sub;
+        const int img = orow / p.HW, rem = orow - img * p.HW;
+        const int yy = rem / p.W, xx = rem - yy * p.W;
+        up_row[i] = (img * 2 * p.H + 2 * yy) * (2 * p.W) + 2 * xx + par;
+      }
+    }
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     float4 res_cur[NRES];
@@ -436,7 +448,12 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           }
         };
         auto store_rows = [&](auto* optr, const size_t step) {
-          if constexpr (ILV) {   // optr = the tile's first row; every row group has its own offset
+          if constexpr (UPF) {   // optr = the output's first row; rows are scattered over the high-resolution image
+            const size_t ld = step / RPI;
+#pragma unroll
+            for (int i = 0; i < NRES; ++i)
+              if (full || row_first + i * RPI < p.M) finish_row(i, optr + (size_t)(up_row[i] + sub * 2 * p.W) * ld);
+          } else if constexpr (ILV) {   // optr = the tile's first row; every row group has its own offset
             const size_t ld = step / RPI;
 #pragma unroll
             for (int i = 0; i < NRES; ++i) {
@@ -452,7 +469,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
               if (row_first + i * RPI < p.M) finish_row(i, optr);
           }
         };
-        const int row_base = ILV ? m0 : row_first;
+        const int row_base = UPF ? 0 : (ILV ? m0 : row_first);
         if constexpr (BF16_OUT)
           store_rows(p.out_bf16 + par * p.par_out_stride + (size_t)row_base * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
         else
@@ -1085,7 +1102,7 @@ struct UpfoldHaloLayout {
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int SA, int SB>
+template <int SA, int SB, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
                                                                              const __grid_constant__ CUtensorMap tm_w,
                                                                              const TcParams p) {
@@ -1221,7 +1238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(con
       }
     }
   } else {
-    epilogue_role<BLOCK_N, 2, L::CHUNK, 8, true, false, true>(
+    epilogue_role<BLOCK_N, 2, L::CHUNK, EPI, true, false, true>(
         p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET), reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
         L::STAT_IMGS, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0, work_step, cta_rank,
         warp, lane);
@@ -1435,13 +1452,13 @@ int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap
   }
 }
 
-template <int SA, int SB>
-int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+template <int SA, int SB, int EPI>
+int launch_upfold_halo_inst(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
   using L = UpfoldHaloLayout<SA, SB>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_upfold_halo_kernel<SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_upfold_halo_kernel<SA, SB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (upfold halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1463,13 +1480,29 @@ int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcPar
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_upfold_halo_kernel<SA, SB>, mh, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_upfold_halo_kernel<SA, SB, EPI>, mh, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (upfold halo): launch failed: %s", cudaGetErrorString(e));
     return (int)e;
   }
   VDM_AFTER_LAUNCH("gemm_tc_upfold_halo");
   return 0;
+}
+
+// lean epilogues (one output, N a multiple of 128) when possible, else the generic one
+template <int SA, int SB>
+int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
+  const bool one_out = (p.out_f32 != nullptr) != (p.out_bf16 != nullptr);
+  if (one_out && !p.rowbias && !p.residual) {
+    const int v = (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
+    switch (v) {
+      case 0: return launch_upfold_halo_inst<SA, SB, 0>(mh, mw, p, stream);
+      case 2: return launch_upfold_halo_inst<SA, SB, 2>(mh, mw, p, stream);
+      case 4: return launch_upfold_halo_inst<SA, SB, 4>(mh, mw, p, stream);
+      default: return launch_upfold_halo_inst<SA, SB, 6>(mh, mw, p, stream);
+    }
+  }
+  return launch_upfold_halo_inst<SA, SB, 8>(mh, mw, p, stream);
 }
 
 }  // namespace
