@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Representative tcgen05 GEMM launches of the C2 step for an ncu capture (halo conv kernel at the 64x64 / 32x32 /
-16x16 levels, the plain pair-tile kernel at 8x8, the qkv and proj linears): python profiles/gemm_ncu_probe.py"""
+16x16 levels, its interleaved-tile form at 8x8, the folded-upsample halo kernel, the qkv and proj linears): python profiles/gemm_ncu_probe.py"""
 import os
 import sys
 
@@ -32,4 +32,14 @@ for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_256_128', 64, 64, 25
         else:
             ops.gemm(a1, w, N, taps=taps, bias=bias, residual=resid, out_f32=out, stats_out=st, **geo)
     torch.cuda.synchronize()
+# folded nearest-x2 upsample + conv3x3 (low-res 32x32 -> 64x64, 256 -> 256 channels)
+from video_diffusion_b200.unet import fold_upsample_weights  # noqa: E402
+x = torch.randn(N_IMG * 32 * 32, 256, device=dev).bfloat16()
+wf = fold_upsample_weights(torch.randn(256, 256, 3, 3) * 0.02).to(dev).bfloat16()
+out = torch.empty(N_IMG * 64 * 64, 256, device=dev)
+st = torch.zeros(N_IMG, 2, 256, device=dev, dtype=torch.int64)
+for _ in range(2):
+    ops.gemm(x, wf, 256, n_img=N_IMG, H=64, W=64, taps=4, a1_mode=3, bias=torch.zeros(256, device=dev), out_f32=out,
+             stats_out=st, C1=256)
+torch.cuda.synchronize()
 print('done')
