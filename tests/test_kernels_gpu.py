@@ -162,7 +162,7 @@ def test_conv3x3_halo_kernel(case, monkeypatch):
 
 @pytest.mark.parametrize('halo', ['0', '2'], ids=['plain', 'halo'])
 @pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128), (5, 64, 64, 128, 256),
-                                  (3, 128, 128, 64, 128), (7, 32, 64, 64, 384)])
+                                  (3, 128, 128, 64, 128), (7, 32, 64, 64, 384), (1, 16, 32, 64, 128), (3, 16, 32, 128, 256)])
 def test_upsample_conv_folded_into_parity_convs(case, halo, monkeypatch):
     """nearest-x2 + conv3x3 as four 2x2 convs on the low-res input (a1_mode 3) vs F.interpolate + F.conv2d; `halo`:
     the variant that keeps both vertical parities of a tile as two accumulators sharing every activation box (low-res
