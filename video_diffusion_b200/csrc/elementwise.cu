@@ -76,6 +76,26 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 1.f; b[i] = 0.f; }
+  // Everything that does not depend on the statistics is requested first, so the small launches (8x8, 16x16 levels)
+  // wait for one memory round trip instead of a chain of four: the first pixel rows of this thread go to L2, the
+  // affine parameters into registers.
+  {
+    const int ldp = (c < p.C1) ? p.C1 : p.C2;
+    constexpr size_t esz = sizeof(InT);
+    const char* base = (c < p.C1) ? reinterpret_cast<const char*>(p.s1) + ((size_t)n * HW * p.C1 + c) * esz
+                                  : reinterpret_cast<const char*>(p.s2) + ((size_t)n * HW * p.C2 + (c - p.C1)) * esz;
+    const int pf0 = blockIdx.x * p.pix_per_block + prow;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pix = pf0 + u * rows;
+      if (pix < HW) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * ldp * esz));
+    }
+  }
+  float gam[8], bet[8];
+  if (p.st1 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gam[i] = __ldg(p.gamma + c + i); bet[i] = __ldg(p.beta + c + i); }
+  }
   if (p.st1 != nullptr) {
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
       const bool first = ch < p.C1;
@@ -105,8 +125,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int g = (c + i) / cpg;
-      a[i] = grstd[g] * p.gamma[c + i];
-      b[i] = p.beta[c + i] - gmean[g] * a[i];
+      a[i] = grstd[g] * gam[i];
+      b[i] = bet[i] - gmean[g] * a[i];
     }
   }
   if (p.ss != nullptr) {
@@ -538,7 +558,7 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   const int rows = C8 >= 256 ? 1 : 256 / C8;
   const int threads = C8 * rows;
   int ppb = rows * 32;
-  while (ppb > rows * 4 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
+  while (ppb > rows * 8 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;
   if (const char* e = getenv("VDM_GN_PPB")) ppb = std::max(rows, atoi(e) / rows * rows);
   p.pix_per_block = ppb;
   dim3 grid((HW + ppb - 1) / ppb, a->n_img);
