@@ -189,6 +189,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       : "memory");
 }
 
+// ---- cluster multicast forms used by the transposed halo kernel (two independent cta_group::1 CTAs that share
+// every weight tile): a TMA load lands at the same shared-memory offset in every CTA of the mask and signals the
+// mbarrier at the same offset there; a commit arrives on the barrier of every CTA of the mask.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -1254,6 +1272,268 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------
+// 3x3 stride-1 convolution with 128 output channels, operand roles swapped ("transposed" halo kernel).
+//
+// With both operands in shared memory an N=128 MMA retires in ~112 cycles instead of 64, an N=256 one in ~165
+// instead of 128 -- and the 64x64 level only has 128 output channels.  So here the WEIGHT tile is the M=128
+// operand and 256 pixels are the N operand: D^T[cout][pixel] = W[cout][k] * X[pixel][k]^T, one 128 x 256 MMA per
+// K step.  Both operands are K-major tiles exactly as before, so the halo slot (the CTA's R image rows plus the
+// row above and below, the vertical tap = a start offset of dy * W pixel rows) simply becomes the B operand.
+// A cluster of two CTAs works on 2 x 256 pixels with independent cta_group::1 MMAs and shares every weight tile:
+// each CTA loads one half of it and multicasts it to both (w_empty collects the commits of both CTAs).
+// The accumulator comes out transposed -- TMEM lane = output channel, column = pixel -- which makes the epilogue
+// simple: a warp's 32 lanes are 32 consecutive channels of one pixel (one coalesced 128-byte store, no staging
+// through shared memory) and the GroupNorm statistics are plain per-lane running sums.
+template <int SA, int SB>
+struct HaloTLayout {
+  static constexpr int PIX = 256;                                   // pixels per CTA tile = MMA N
+  static constexpr int A_SLOT = (PIX / BLOCK_M + 1) * BLOCK_M * BLOCK_K * 2;   // (R + 2) * W <= 384 pixel rows, W <= 64
+  static constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;              // 128 output channels x 64 k
+  static constexpr int W_OFFSET = SA * A_SLOT;
+  static constexpr int BAR_OFFSET = W_OFFSET + SB * W_BYTES;
+  static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int SA, int SB, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo,
+                                                                        const __grid_constant__ CUtensorMap tm_a2,
+                                                                        const __grid_constant__ CUtensorMap tm_w,
+                                                                        const TcParams p) {
+  using L = HaloTLayout<SA, SB>;
+  constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
+  constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int work_id0 = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.M + TILE_M - 1) / TILE_M;          // N == 128: one output-channel tile
+  const int halo_rows = PIX / p.W + 2;
+  const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 2);       // both CTAs of the cluster must have consumed the tile
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();       // peer barriers exist before any multicast load / commit can reach them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_halo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      auto load_w = [&](int k_elem) {     // this CTA's 64 output channels of the tile, to both CTAs
+        mbar_wait(w_empty(sb), pb ^ 1u, 4);
+        mbar_expect_tx(w_full(sb), L::W_BYTES);
+        tma_load_2d_multicast(smem_base + L::W_OFFSET + sb * L::W_BYTES + cta_rank * (L::W_BYTES / 2), &tm_w, w_full(sb),
+                              k_elem, (int)cta_rank * (BLOCK_M / 2), (uint16_t)3);
+        if (++sb == SB) {
+          sb = 0;
+          pb ^= 1u;
+        }
+      };
+      for (int tile = work_id0; tile < n_tiles; tile += work_step) {
+        const int m0 = tile * TILE_M + (int)cta_rank * PIX;
+        const int img = m0 / p.HW;
+        const int y0 = (m0 - img * p.HW) / p.W;
+        for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(a_empty(sa), pa ^ 1u, 0);
+            mbar_expect_tx(a_full(sa), halo_bytes);
+            tma_load_5d(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            if (++sa == SA) {
+              sa = 0;
+              pa ^= 1u;
+            }
+            for (int dy = 0; dy < 3; ++dy) load_w(((dy * 3 + dx) * p.c1_chunks + chunk) * BLOCK_K);
+          }
+        }
+        for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          mbar_wait(a_empty(sa), pa ^ 1u, 0);
+          mbar_expect_tx(a_full(sa), PIX * BLOCK_K * 2);
+#pragma unroll
+          for (int sub = 0; sub < PIX / BLOCK_M; ++sub)
+            tma_load_5d(smem_base + sa * L::A_SLOT + sub * (BLOCK_M * BLOCK_K * 2), &tm_a2, a_full(sa), chunk * BLOCK_K,
+                        m0 + sub * BLOCK_M, 0, 0, 0);
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+          load_w((9 * p.c1_chunks + chunk) * BLOCK_K);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc<PIX, BLOCK_M>();    // M = 128 output channels, N = 256 pixels
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      const uint32_t dy_bytes = (uint32_t)p.W * (BLOCK_K * 2);
+      for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * PIX);
+        uint32_t accumulate = 0;
+        auto mma_block = [&](uint32_t pix_addr) {
+          mbar_wait(w_full(sb), pb, 5);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t w_desc = make_smem_desc(smem_base + L::W_OFFSET + sb * L::W_BYTES);
+          const uint64_t x_desc = make_smem_desc(pix_addr);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_acc, w_desc + 2u * k, x_desc + 2u * k, idesc, accumulate | (uint32_t)k);
+          accumulate = 1;
+          umma_commit_multicast(w_empty(sb), (uint16_t)3);
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1u;
+          }
+        };
+        const int n_units = 3 * p.c1_chunks;
+        for (int u = 0; u < n_units; ++u) {
+          mbar_wait(a_full(sa), pa, 1);
+          const uint32_t a_slot = smem_base + sa * L::A_SLOT;
+          for (int dy = 0; dy < 3; ++dy) mma_block(a_slot + dy * dy_bytes);
+          umma_commit(a_empty(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          mbar_wait(a_full(sa), pa, 1);
+          mma_block(smem_base + sa * L::A_SLOT);
+          umma_commit(a_empty(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        umma_commit(tmem_full_bar(as));
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9): lane = output channel, TMEM column = pixel =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                 // TMEM lane quarter: channels q*32 .. q*32+31
+    const int half = ew >> 2;               // pixel columns half*128 .. +127
+    const int c = q * 32 + lane;
+    const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
+    int it = 0;
+    for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int row0 = tile * TILE_M + (int)cta_rank * PIX + half * 128;      // first pixel row of this warp
+      float rsum = 0.f, rsq = 0.f;
+      float res_cur[32];
+      auto load_res = [&](float (&dst)[32], int chunk) {
+        if constexpr (HAS_RES) {
+          const float* rp = p.residual + (size_t)(row0 + chunk * 32) * p.ld_res + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[i] = (row0 + chunk * 32 + i < p.M) ? __ldg(rp + (size_t)i * p.ld_res) : 0.f;
+        }
+      };
+      if constexpr (HAS_RES) {   // this warp's residual block (128 rows x 128 B) into L2 while the MMAs still run
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = row0 + j * 32 + lane;
+          if (r < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)r * p.ld_res + q * 32));
+        }
+      }
+      load_res(res_cur, 0);
+      mbar_wait(tmem_full_bar(as), aphase, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t acc[32];
+        tmem_ld_32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PIX + half * 128 + chunk * 32), acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float res_next[32];
+        if (chunk + 1 < 4) load_res(res_next, chunk + 1);
+        const int r = row0 + chunk * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (r + i < p.M) {
+            float v = __uint_as_float(acc[i]) + bias_c;
+            if constexpr (HAS_RES) v += res_cur[i];
+            if constexpr (STATS) {
+              rsum += v;
+              rsq = fmaf(v, v, rsq);
+            }
+            if constexpr (BF16_OUT) p.out_bf16[(size_t)(r + i) * p.ld_out_bf16 + c] = __float2bfloat16_rn(v);
+            else p.out_f32[(size_t)(r + i) * p.ld_out + c] = v;
+          }
+        }
+        if constexpr (HAS_RES) {
+          if (chunk + 1 < 4) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) res_cur[i] = res_next[i];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+      if constexpr (STATS) {
+        // this warp's 128 pixels lie in one image (H*W % 256 == 0): two fixed-point atomics per channel
+        if (p.stats_out != nullptr && row0 < p.M) {
+          unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) + (size_t)(row0 / p.HW) * 2 * p.N + c;
+          atomicAdd(tab, (unsigned long long)__float2ll_rn(rsum * 16777216.0f));
+          atomicAdd(tab + p.N, (unsigned long long)__float2ll_rn(rsq * 16777216.0f));
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();       // no CTA exits while its peer may still multicast into it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side: tensor maps
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -1505,6 +1785,59 @@ int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcPar
   return launch_upfold_halo_inst<SA, SB, 8>(mh, mw, p, stream);
 }
 
+template <int SA, int SB, int EPI>
+int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                       cudaStream_t stream) {
+  using L = HaloTLayout<SA, SB>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (transposed halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = (p.M + 2 * L::PIX - 1) / (2 * L::PIX);
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI>, mh, ma2, mw, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc (transposed halo): launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  VDM_AFTER_LAUNCH("gemm_tc_halo_t");
+  return 0;
+}
+
+template <int SA, int SB>
+int launch_halo_t(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                  cudaStream_t stream) {
+  switch (epilogue_variant(p, 128)) {
+    case 0: return launch_halo_t_inst<SA, SB, 0>(mh, ma2, mw, p, stream);
+    case 1: return launch_halo_t_inst<SA, SB, 1>(mh, ma2, mw, p, stream);
+    case 2: return launch_halo_t_inst<SA, SB, 2>(mh, ma2, mw, p, stream);
+    case 3: return launch_halo_t_inst<SA, SB, 3>(mh, ma2, mw, p, stream);
+    case 4: return launch_halo_t_inst<SA, SB, 4>(mh, ma2, mw, p, stream);
+    case 5: return launch_halo_t_inst<SA, SB, 5>(mh, ma2, mw, p, stream);
+    case 6: return launch_halo_t_inst<SA, SB, 6>(mh, ma2, mw, p, stream);
+    default: return launch_halo_t_inst<SA, SB, 7>(mh, ma2, mw, p, stream);
+  }
+}
+
 }  // namespace
 
 int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream);
@@ -1640,6 +1973,23 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     const bool ok = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
                     bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
+    // N == 128 (the 64x64 level): weights as the M operand, 256 pixels as N; VDM_GEMM_HALO_T=0 keeps the plain halo tiles
+    const char* et = getenv("VDM_GEMM_HALO_T");
+    if (ok && a->N == 128 && (!et || atoi(et) != 0) && 256 % a->W == 0 && HW % 256 == 0 && epilogue_variant(p, 128) < 8) {
+      CUtensorMap mh, mwt;
+      const uint64_t C = a->C1;
+      uint64_t dims[5] = {C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->n_img};
+      uint64_t st[5] = {2, C * 2, C * 2 * a->W, C * 2 * a->W * a->H, C * 2 * a->W * a->H};
+      uint32_t box[5] = {BLOCK_K, (uint32_t)a->W, (uint32_t)(256 / a->W + 2), 1, 1};
+      rc = encode_map(&mh, a->a1, 5, dims, st, box);
+      if (rc) return rc;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      uint32_t wbox[2] = {BLOCK_K, 64};
+      rc = encode_map(&mwt, a->w, 2, wdims, wst, wbox);
+      if (rc) return rc;
+      return launch_halo_t<3, 4>(mh, ma2, mwt, p, stream);
+    }
     if (ok) {
       CUtensorMap mh, mw2;
       const uint64_t C = a->C1;
