@@ -296,20 +296,20 @@ def main():
                      'flops_per_step': alg_fl, 'executed_flops_per_step': g_fl, 'executed_tflops': executed,
                      'timing': 'CUDA events per launch, eager pass with the launch queue kept full (not under a profiler)'},
     }
-    # the single heaviest launch shape of the step (3x3 conv 64x64, 256 -> 128, halo kernel), per launch: live CUDA-event
+    # the single heaviest launch shape of the step (3x3 conv 64x64, 256 -> 128, transposed-role halo kernel), per launch: live CUDA-event
     # time of this run; DRAM traffic from the committed `ncu --set full` capture of the same launch
-    # (profiles/ncu_gemm_halo_r1f.md: 336.5 MB read + 140.9 MB written; algorithmic 335.5 + 167.8 MB)
+    # (profiles/ncu_gemm_halo_r1g.md: 336.5 MB read + 141.1 MB written; algorithmic 335.5 + 167.8 MB)
     top = [(k, v) for k, v in prof_shapes.items() if k[0] == 'gemm_tc_conv3x3' and 'M=655360 N=128 K=2304' in k[1]]
     if top:
         (_, meta), v = top[0]
         t_launch = v['ms'] / v['n'] / 1e3
         tf = v['flops'] / t_launch / 1e12
-        result['roofline']['traffic'] = 477.5e6
+        result['roofline']['traffic'] = 477.6e6
         result['roofline']['top_launch'] = {
-            'kernel': 'gemm_tc_halo_kernel<128,2,3,4,6>: conv3x3 64x64 256->128, ' + meta, 'us': t_launch * 1e6,
+            'kernel': 'gemm_tc_halo_t_kernel<3,4,6>: conv3x3 64x64 256->128, ' + meta, 'us': t_launch * 1e6,
             'achieved': tf, 'frac': tf / pk['tflops'] if pk['tflops'] else None, 'flops': v['flops'],
-            'algorithmic_bytes': 655360 * 256 * 2 + 655360 * 128 * 2, 'traffic': 477.5e6,
-            'traffic_source': 'ncu --set full, profiles/ncu_gemm_halo_r1f.md (dram__bytes_read.sum + dram__bytes_write.sum)'}
+            'algorithmic_bytes': 655360 * 256 * 2 + 655360 * 128 * 2, 'traffic': 477.6e6,
+            'traffic_source': 'ncu --set full, profiles/ncu_gemm_halo_r1g.md (dram__bytes_read.sum + dram__bytes_write.sum)'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step = cpu_port_step(sd, 1, threads)

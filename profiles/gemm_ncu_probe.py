@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Representative tcgen05 GEMM launches of the C2 step for an ncu capture (halo conv kernel at the 64x64 / 32x32 /
-16x16 levels, its interleaved-tile form at 8x8, the folded-upsample halo kernel, the qkv and proj linears): python profiles/gemm_ncu_probe.py"""
+16x16 levels (transposed-role kernel for the 128-channel 64x64 layers), its interleaved-tile form at 8x8, the folded-upsample halo kernel, the qkv and proj linears): python profiles/gemm_ncu_probe.py"""
 import os
 import sys
 
