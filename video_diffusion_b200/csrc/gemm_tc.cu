@@ -1319,7 +1319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tiles = (p.M + TILE_M - 1) / TILE_M;          // N == 128: one output-channel tile
+  const int n_tiles_n = p.N / BLOCK_M;                       // 128 output channels per tile; n fastest, so the
+  const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);   // CTAs of a wave share the activation rows in L2
   const int halo_rows = PIX / p.W + 2;
   const uint32_t halo_bytes = (uint32_t)(halo_rows * p.W) * (BLOCK_K * 2);
 
@@ -1358,18 +1359,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      int n0 = 0;
       auto load_w = [&](int k_elem) {     // this CTA's 64 output channels of the tile, to both CTAs
         mbar_wait(w_empty(sb), pb ^ 1u, 4);
         mbar_expect_tx(w_full(sb), L::W_BYTES);
         tma_load_2d_multicast(smem_base + L::W_OFFSET + sb * L::W_BYTES + cta_rank * (L::W_BYTES / 2), &tm_w, w_full(sb),
-                              k_elem, (int)cta_rank * (BLOCK_M / 2), (uint16_t)3);
+                              k_elem, n0 + (int)cta_rank * (BLOCK_M / 2), (uint16_t)3);
         if (++sb == SB) {
           sb = 0;
           pb ^= 1u;
         }
       };
       for (int tile = work_id0; tile < n_tiles; tile += work_step) {
-        const int m0 = tile * TILE_M + (int)cta_rank * PIX;
+        n0 = (tile % n_tiles_n) * BLOCK_M;
+        const int m0 = (tile / n_tiles_n) * TILE_M + (int)cta_rank * PIX;
         const int img = m0 / p.HW;
         const int y0 = (m0 - img * p.HW) / p.W;
         for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
@@ -1457,13 +1460,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter: channels q*32 .. q*32+31
     const int half = ew >> 2;               // pixel columns half*128 .. +127
-    const int c = q * 32 + lane;
-    const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
     int it = 0;
     for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const int row0 = tile * TILE_M + (int)cta_rank * PIX + half * 128;      // first pixel row of this warp
+      const int c = (tile % n_tiles_n) * BLOCK_M + q * 32 + lane;
+      const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
+      const int row0 = (tile / n_tiles_n) * TILE_M + (int)cta_rank * PIX + half * 128;   // first row of this warp
       float rsum = 0.f, rsq = 0.f;
       float res_cur[32];
       auto load_res = [&](float (&dst)[32], int chunk) {
@@ -1477,7 +1480,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = row0 + j * 32 + lane;
-          if (r < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)r * p.ld_res + q * 32));
+          if (r < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)r * p.ld_res + c - lane));
         }
       }
       load_res(res_cur, 0);
@@ -1800,7 +1803,7 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
     }
     configured = true;
   }
-  const int tiles = (p.M + 2 * L::PIX - 1) / (2 * L::PIX);
+  const int tiles = (p.N / BLOCK_M) * ((p.M + 2 * L::PIX - 1) / (2 * L::PIX));
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
@@ -1973,9 +1976,13 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     const bool ok = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
                     bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
-    // N == 128 (the 64x64 level): weights as the M operand, 256 pixels as N; VDM_GEMM_HALO_T=0 keeps the plain halo tiles
+    // transposed-role kernel: weights as the M operand (128-channel tiles), 256 pixels as N
     const char* et = getenv("VDM_GEMM_HALO_T");
-    if (ok && a->N == 128 && (!et || atoi(et) != 0) && 256 % a->W == 0 && HW % 256 == 0 && epilogue_variant(p, 128) < 8) {
+    // measured per level: faster than the pair tiles for 128 and 384 output channels (where those are 128 / 192
+    // wide), slightly slower for 256.  VDM_GEMM_HALO_T: 0 off, 1 that rule (default), 2 every N % 128 == 0
+    const int tmode = et ? atoi(et) : 1;
+    if (ok && a->N % 128 == 0 && (a->N % 256 != 0 || tmode == 2) && tmode > 0 && 256 % a->W == 0 && HW % 256 == 0 &&
+        epilogue_variant(p, 128) < 8) {
       CUtensorMap mh, mwt;
       const uint64_t C = a->C1;
       uint64_t dims[5] = {C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->n_img};
