@@ -298,7 +298,7 @@ def main():
     }
     # the single heaviest launch shape of the step (3x3 conv 64x64, 256 -> 128, transposed-role halo kernel), per launch: live CUDA-event
     # time of this run; DRAM traffic from the committed `ncu --set full` capture of the same launch
-    # (profiles/ncu_gemm_halo_r1g.md: 336.5 MB read + 141.1 MB written; algorithmic 335.5 + 167.8 MB)
+    # (profiles/ncu_gemm_halo_r1h.md: 336.5 MB read + 141.1 MB written; algorithmic 335.5 + 167.8 MB)
     top = [(k, v) for k, v in prof_shapes.items() if k[0] == 'gemm_tc_conv3x3' and 'M=655360 N=128 K=2304' in k[1]]
     if top:
         (_, meta), v = top[0]
@@ -309,7 +309,7 @@ def main():
             'kernel': 'gemm_tc_halo_t_kernel<3,4,6>: conv3x3 64x64 256->128, ' + meta, 'us': t_launch * 1e6,
             'achieved': tf, 'frac': tf / pk['tflops'] if pk['tflops'] else None, 'flops': v['flops'],
             'algorithmic_bytes': 655360 * 256 * 2 + 655360 * 128 * 2, 'traffic': 477.6e6,
-            'traffic_source': 'ncu --set full, profiles/ncu_gemm_halo_r1g.md (dram__bytes_read.sum + dram__bytes_write.sum)'}
+            'traffic_source': 'ncu --set full, profiles/ncu_gemm_halo_r1h.md (dram__bytes_read.sum + dram__bytes_write.sum)'}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step = cpu_port_step(sd, 1, threads)
