@@ -1,14 +1,19 @@
 // Implicit-GEMM convolution / linear on the 5th-gen tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill = conv padding) -> shared memory
 //   -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue (bias / per-image
-//   bias / residual / bf16 or fp32 or NCHW store).
+//   bias / residual / bf16 or fp32 or NCHW store, GroupNorm statistics of the stored tile).
 //
-// Persistent kernel, one CTA per SM, looping over 128 (pixels) x BLOCK_N (out channels) tiles.  The
-// K loop walks taps x (C1/64) chunks of A1 -- each chunk one shifted 5-D TMA box of the
-// channels-last activation -- followed by C2/64 chunks of the optional second operand (fused 1x1
-// skip projection, unet.py:172-173,198).  Warp roles: warp 0 TMA producer, warp 1 TMEM allocator +
-// MMA issuer (single thread), warps 2..9 epilogue; two accumulator stages in TMEM let the epilogue
-// of one tile overlap the MMAs of the next.
+// All kernels are persistent and warp-specialised: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (single
+// thread), warps 2..9 epilogue; two accumulator stages in TMEM let the epilogue of one tile overlap the MMAs of the
+// next.  Four kernels share the helpers and (except the transposed one) the epilogue below:
+//   gemm_tc_kernel              one shifted 5-D TMA box per (tap, 64-channel chunk), then the C2/64 chunks of the
+//                               optional second operand (fused 1x1 skip projection, unet.py:172-173,198); single CTA
+//                               or CTA pair (cta_group::2): linears, stride-2 convs, small layers
+//   gemm_tc_halo_kernel         3x3 stride-1: the three vertical taps share one activation slot (tile rows + halo);
+//                               interleaved-tile form for the 8x8 level (two images per tile)
+//   gemm_tc_halo_t_kernel       the same with operand roles swapped (weights = M, 256 pixels = N), weight tiles
+//                               multicast across a 2-CTA cluster, staging-free epilogue: 128- and 384-channel levels
+//   gemm_tc_upfold_halo_kernel  nearest-x2 upsample folded into 2x2 parity convs, both vertical parities per tile
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
