@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
 // its float4 column of all T frames in registers, the lanes of a group fold their sums with shuffles, and the values
 // are normalised and written without touching memory twice.  B * HW * n_slabs warps: enough parallelism for the
 // 8x8 level too (the kernel above launches only B * HW / 8 blocks there).
-template <typename OutT>
+template <typename OutT, int TMAX>
 __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __restrict__ x, int B, int T, int HW, int C,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta,
@@ -310,12 +310,17 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   const int c = active ? g * cpg + (lane % l4) * 4 : 0;
   const size_t frame_stride = (size_t)HW * C;
   const size_t off0 = (size_t)b * T * frame_stride + (size_t)pix * C + c;
-  float4 v[32];
+  float4 v[TMAX];          // TMAX >= T: the frame loop is fully unrolled, every load is in flight before the first use
   float s = 0.f, q = 0.f;
+  const float4* src = reinterpret_cast<const float4*>(x + off0);
+  const size_t stride4 = frame_stride / 4;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < TMAX; ++t) {
+    if (t < T && active) v[t] = __ldg(src + t * stride4);
+  }
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
     if (t < T && active) {
-      v[t] = __ldg(reinterpret_cast<const float4*>(x + off0 + t * frame_stride));
       s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
       q = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, q))));
     }
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   const float a0 = rstd * gm.x, a1 = rstd * gm.y, a2 = rstd * gm.z, a3 = rstd * gm.w;
   const float b0 = bt.x - mean * a0, b1 = bt.y - mean * a1, b2 = bt.z - mean * a2, b3 = bt.w - mean * a3;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
       const size_t off = off0 + t * frame_stride;
       const float y0 = fmaf(v[t].x, a0, b0), y1 = fmaf(v[t].y, a1, b1), y2 = fmaf(v[t].z, a2, b2), y3 = fmaf(v[t].w, a3, b3);
@@ -598,12 +603,20 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
     const int n_slabs = 32 / gps;
     const long long warps = (long long)B * HW * n_slabs;
     const unsigned grid = (unsigned)((warps + 3) / 4);
-    if (out_dtype == VDM_BF16)
-      gn_temporal_regs_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32,
-                                                                                  (__nv_bfloat16*)out_a, gps, n_slabs);
-    else
-      gn_temporal_regs_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32,
-                                                                          (float*)out_a, gps, n_slabs);
+#define VDM_GNT(TM)                                                                                                  \
+  do {                                                                                                               \
+    if (out_dtype == VDM_BF16)                                                                                       \
+      gn_temporal_regs_kernel<__nv_bfloat16, TM><<<grid, 128, 0, (cudaStream_t)stream>>>(                            \
+          x, B, T, HW, C, gamma, beta, out_f32, (__nv_bfloat16*)out_a, gps, n_slabs);                                \
+    else                                                                                                             \
+      gn_temporal_regs_kernel<float, TM><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32, \
+                                                                                (float*)out_a, gps, n_slabs);        \
+  } while (0)
+    if (T <= 8) VDM_GNT(8);
+    else if (T <= 16) VDM_GNT(16);
+    else if (T <= 24) VDM_GNT(24);
+    else VDM_GNT(32);
+#undef VDM_GNT
     VDM_AFTER_LAUNCH("gn_temporal");
     return 0;
   }
