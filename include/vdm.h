@@ -136,23 +136,28 @@ int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C,
                     const float* gamma, const float* beta, float* out_f32,
                     void* out_a, int32_t out_dtype, vdm_stream_t stream);
 
-/* out[m][c] = h[m][c] + enc[m % HW][c]  (spatial_encoding add, unet.py:841-844); out may alias h */
-int vdm_add_spatial_encoding(const float* h, const float* enc, float* out, int32_t n_img, int32_t HW,
-                             int32_t C, vdm_stream_t stream);
+/* out[m][c] = (h[m][c] + enc[m % HW][c]) + frame_emb[m / HW][c]: the learned spatial_encoding add
+ * (unet.py:841-844) and, with use_frame_encoding, the per-frame sinusoid (unet.py:914-926; frame_emb is
+ * vdm_timestep_embedding of the frame indices with max_period = 10 T).  Either addend may be NULL, not both;
+ * out may alias h. */
+int vdm_add_spatial_encoding(const float* h, const float* enc, const float* frame_emb, float* out,
+                             int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream);
 
 /* ---- conditioning mix + input-conv im2col -----------------------------------------------
- * Replaces CondMargVideoModel.forward's masking / indicator channels / per-frame timesteps
- * (unet.py:951-1013, cond_emb_type='channel', observed_frames='x_0').
- * x, x0: [B][F][3][H][W] fp32 (reference layout); masks: [B][F] fp32.
- * a_out: im2col rows [B*F*H*W][64] (K index = tap*5 + c, zero padded), dtype out_dtype.
- * t_frame[B*F] = t[b] * (1 - obs[b][f]);  attn_mask[B*F] = min(obs+lat+kinda, 1). */
+ * Replaces CondMargVideoModel.forward's masking / indicator channels / per-frame timesteps (unet.py:951-1019).
+ * x, x0: [B][F][3][H][W] fp32 (reference layout; x0 = whichever tensor observed_frames selects); masks: [B][F] fp32.
+ * mode follows cond_emb_type: 0 'channel' (5 input channels), 1 'duplicate' / 'all' (6), 2 't=0' (3, x unchanged).
+ * a_out: im2col rows [B*F*H*W][64] (K index = tap*Cin + c, zero padded), dtype out_dtype.
+ * t_frame[B*F] = t[b] * (1 - obs[b][f]) in mode 0 (observed_frames='x_0'), t[b] otherwise;
+ * attn_mask[B*F] = min(obs+lat+kinda, 1). */
 int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
                  const float* kinda_marg_mask, const float* t, int32_t B, int32_t F, int32_t H,
-                 int32_t W, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
+                 int32_t W, int32_t mode, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
                  vdm_stream_t stream);
 
-/* sinusoidal timestep embedding (nn.py:89-107): out[n] = [cos(t*f_i) | sin(t*f_i)] */
-int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, float* out,
+/* sinusoidal embedding (nn.py:89-107, 110-122): out[n] = [cos(t*f_i) | sin(t*f_i)], f_i = exp(-ln(max_period) i / half);
+ * max_period = 10000 for diffusion time, 10 T for frame indices */
+int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, double max_period, float* out,
                            vdm_stream_t stream);
 
 /* ---- RPE net hidden layer (unet.py:283-296) ----------------------------------------------

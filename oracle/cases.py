@@ -15,6 +15,12 @@ _CFG = {
     # three pieces of the index function
     'tiny_lut':  dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, use_rpe_net=False, rp_alpha=3, rp_beta=7,
                       rp_gamma=20.5),
+    # model variants of SURVEY 8(f)-2: other conditioning embeddings, frame-index sinusoid
+    'tiny_dup':  dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, cond_emb_type='duplicate'),
+    'tiny_t0':   dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, cond_emb_type='t=0'),
+    'tiny_fe':   dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, use_frame_encoding=True),
+    'tiny_fei':  dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, use_frame_encoding=True,
+                      enforce_position_invariance=True),
 }
 
 
@@ -51,6 +57,32 @@ UNET_LUT_CASES = [
     dict(name='tiny_lut_ragged', cfg='tiny_lut', B=2, F=10, n_obs=[3, 6], n_lat=[5, 4], t=[17, 803],
          frame_indices=[[0, 1, 2, 10, 11, 12, 13, 14, 0, 0], [3, 7, 9, 11, 12, 13, 20, 25, 28, 29]]),
 ]
+
+
+# cond_emb_type / use_frame_encoding / observed_frames variants (stored in tests/golden/unet_variants.npz); `observed`
+# selects kwargs['observed_frames'], x_t_minus_1 and hybrid are seeded tensors (variant_kwargs)
+_RAGGED = dict(B=2, F=10, n_obs=[3, 6], n_lat=[5, 4], t=[17, 803],
+               frame_indices=[[0, 1, 2, 10, 11, 12, 13, 14, 0, 0], [3, 7, 9, 11, 12, 13, 20, 25, 28, 29]])
+UNET_VARIANT_CASES = [
+    dict(name='dup_ragged', cfg='tiny_dup', **_RAGGED),
+    dict(name='t0_ragged', cfg='tiny_t0', **_RAGGED),
+    dict(name='t0_no_obs', cfg='tiny_t0', B=2, F=6, n_obs=[0, 2], n_lat=[6, 4], t=[250, 600],
+         frame_indices=[[0, 1, 2, 3, 4, 5], [9, 8, 7, 6, 5, 4]]),
+    dict(name='fe_ragged', cfg='tiny_fe', **_RAGGED),
+    dict(name='fei_ragged', cfg='tiny_fei', **_RAGGED),
+    dict(name='obs_xt', cfg='tiny', observed='x_t', **_RAGGED),
+    dict(name='obs_xtm1', cfg='tiny', observed='x_t_minus_1', **_RAGGED),
+    dict(name='obs_hybrid500', cfg='tiny', observed='hybrid_500', **_RAGGED),
+]
+
+
+def variant_kwargs(case, inp):
+    """model kwargs of a variant case: the reference's names, seeded x_t_minus_1 / hybrid tensors."""
+    kw = model_kwargs_for(inp)
+    kw['observed_frames'] = case.get('observed', 'x_0')
+    kw['x_t_minus_1'] = synth.make_noise(tuple(inp['x'].shape), seed=23)
+    kw['hybrid'] = synth.make_video(tuple(inp['x'].shape), seed=24)
+    return kw
 
 
 def unet_case_inputs(case):

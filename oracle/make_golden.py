@@ -35,8 +35,8 @@ from improved_diffusion.script_util import (create_gaussian_diffusion,       # n
 
 from oracle import synth                                                      # noqa: E402
 from oracle.cases import (CHAIN_CASE, DIFFUSION_CASES, STRATEGY_GRID, UNET_CASES, UNET_LUT_CASES,  # noqa: E402
-                          bpd_case_inputs,
-                          fake_eps, model_kwargs_for, ref_config, unet_case_inputs)
+                          UNET_VARIANT_CASES, bpd_case_inputs, fake_eps, model_kwargs_for, ref_config,
+                          unet_case_inputs, variant_kwargs)
 
 
 class NoiseReplay:
@@ -102,8 +102,9 @@ def dump_unet(cases_list=UNET_CASES, fname='unet.npz'):
         for j, mod in enumerate(model.middle_block):
             hooks.append(mod.register_forward_hook(lambda m, a, o, key=f'middle_block.{j}': taps.__setitem__(key, o)))
         hooks.append(model.time_embed.register_forward_hook(lambda m, a, o: taps.__setitem__('emb', o)))
+        kw = variant_kwargs(case, inp) if fname == 'unet_variants.npz' else model_kwargs_for(inp)
         with torch.no_grad():
-            out, _ = model(inp['x'], timesteps=inp['t_model'], **model_kwargs_for(inp))
+            out, _ = model(inp['x'], timesteps=inp['t_model'].clone(), **kw)
         for h in hooks:
             h.remove()
         arrays[f"{case['name']}/eps"] = out.numpy()
@@ -226,6 +227,10 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['lut']:       # only the lookup-table RPE fixtures (leaves the other files untouched)
         dump_specs(('tiny_lut',))
         dump_unet(UNET_LUT_CASES, 'unet_lut.npz')
+        sys.exit(0)
+    if sys.argv[1:] == ['variants']:  # cond_emb_type / frame-encoding / observed_frames variants only
+        dump_specs(('tiny_dup', 'tiny_t0', 'tiny_fe', 'tiny_fei'))
+        dump_unet(UNET_VARIANT_CASES, 'unet_variants.npz')
         sys.exit(0)
     dump_specs()
     dump_strategies()

@@ -33,10 +33,14 @@ CHANNEL_MULT = {256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4),
 def model_config(image_size, num_channels=128, num_res_blocks=2, num_heads=4,
                  attention_resolutions='16,8', use_scale_shift_norm=True,
                  use_spatial_encoding=True, allow_interactions_between_padding=True,
-                 learn_sigma=False, use_rpe_net=True, rp_alpha=None, rp_beta=None, rp_gamma=None, **_ignored):
+                 learn_sigma=False, use_rpe_net=True, rp_alpha=None, rp_beta=None, rp_gamma=None,
+                 use_frame_encoding=False, enforce_position_invariance=False, T=None, cond_emb_type='channel',
+                 **_ignored):
     """Architecture facts the oracle needs (script_util.py:229-300)."""
     return dict(
         rpe_net=use_rpe_net, rp=(rp_alpha, rp_beta, rp_gamma),
+        frame_enc=use_frame_encoding, pos_inv=enforce_position_invariance, T=T,
+        cond=cond_emb_type.replace('-initzero', ''),
         image_size=image_size, ch=num_channels, nrb=num_res_blocks, heads=num_heads,
         mult=CHANNEL_MULT[image_size],
         attn_ds=tuple(image_size // int(r) for r in attention_resolutions.split(',')),
@@ -238,8 +242,14 @@ def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None):
     for i, mods in enumerate(inp):
         h = run(f'input_blocks.{i}.', mods, h)
         hs.append(h)
-        if i + 1 == before_attn and cfg['spatial_enc']:
-            h = h + sd['spatial_encoding']
+        if i + 1 == before_attn:                                  # unet.py:816-818, 841-844, 914-926
+            if cfg['spatial_enc']:
+                h = h + sd['spatial_encoding']
+            if cfg.get('frame_enc'):
+                fi = frame_indices.float()
+                if cfg['pos_inv']:
+                    fi = fi - fi.mean(dim=1, keepdim=True)
+                h = h + sinusoid(fi.reshape(-1), h.shape[1], max_period=cfg['T'] * 10)[:, :, None, None]
     h = run('middle_block.', mid, h)
     for i, mods in enumerate(outp):
         h = run(f'output_blocks.{i}.', mods, torch.cat([h, hs.pop()], dim=1))
@@ -248,19 +258,40 @@ def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None):
 
 
 def cond_marg_forward(sd, cfg, x, x0, obs_mask, latent_mask, kinda_marg_mask, timesteps,
-                      frame_indices=None, taps=None):
-    """CondMargVideoModel.forward with cond_emb_type='channel', observed_frames='x_0'
-    (unet.py:949-1026 + 898-912).  x, x0: (B,F,3,H,W); masks (B,F,1,1,1); timesteps (B,)."""
+                      frame_indices=None, taps=None, observed_frames='x_0', x_t_minus_1=None, hybrid=None):
+    """CondMargVideoModel.forward in eval mode (unet.py:949-1026 + 898-912) for cond_emb_type 'channel' (every
+    inference-time observed_frames choice), 'duplicate' / 'all' and 't=0'.
+    x, x0: (B,F,3,H,W); masks (B,F,1,1,1); timesteps (B,)."""
     B, Fr, C, H, W = x.shape
     anything = (obs_mask + latent_mask + kinda_marg_mask).clamp(max=1)
-    ones = torch.ones_like(x[:, :, :1])
-    x_in = torch.cat([x * latent_mask + x0 * obs_mask + x * (1 - anything),
-                      ones * obs_mask, ones * kinda_marg_mask], dim=2)
     t = timesteps.view(B, 1).expand(B, Fr)
     om = obs_mask.view(B, Fr)
-    t = torch.zeros_like(t) * om + t * (1 - om)          # observed frames are at diffusion time 0
+    cond = cfg.get('cond', 'channel')
+    if cond == 'channel':
+        if 'hybrid' in observed_frames:
+            thr = int(observed_frames.split('_')[-1])
+            below = (t < thr).int()
+            b5 = below[:, :, None, None, None]
+            observed = x_t_minus_1 * b5 + hybrid * (1 - b5)
+            t_obs = below * (t - 1) + (1 - below) * torch.ones_like(t) * thr
+        else:
+            observed = {'x_0': x0, 'x_t': x, 'x_t_minus_1': x_t_minus_1}[observed_frames]
+            t_obs = {'x_0': torch.zeros_like(t), 'x_t': t, 'x_t_minus_1': t - 1}[observed_frames]
+        ones = torch.ones_like(x[:, :, :1])
+        x_in = torch.cat([x * latent_mask + observed * obs_mask + x * (1 - anything),
+                          ones * obs_mask, ones * kinda_marg_mask], dim=2)
+        t = t_obs * om + t * (1 - om)
+    elif cond in ('duplicate', 'all'):
+        x_in = torch.cat([x * latent_mask + x * (1 - anything), x0 * obs_mask], dim=2)
+    elif cond == 't=0':
+        # the reference assigns -1 through a stride-0 expanded view (unet.py:1019): one observed frame sends the whole
+        # video's timesteps to -1
+        x_in = x
+        t = torch.where((om == 1).any(dim=1, keepdim=True), torch.full_like(t, -1.0), t)
+    else:
+        raise ValueError(cond)
     if frame_indices is None:
         frame_indices = torch.arange(Fr).view(1, Fr).expand(B, Fr)
-    out = unet_forward(sd, cfg, x_in.reshape(B * Fr, C + 2, H, W), t.reshape(B * Fr),
+    out = unet_forward(sd, cfg, x_in.reshape(B * Fr, x_in.shape[2], H, W), t.reshape(B * Fr),
                        frame_indices, anything, Fr, taps=taps)
     return out.view(B, Fr, cfg['out_ch'], H, W)

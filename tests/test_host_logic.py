@@ -58,7 +58,8 @@ def test_schedule_tables_bit_exact(golden, case):
 
 def test_state_dict_keys_and_shapes_match_reference(golden):
     from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
-    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4', 'tiny_lut'):     # tiny_lut: use_rpe_net=False lookup tables
+    # tiny_lut: use_rpe_net=False lookup tables; tiny_dup / tiny_t0: other cond_emb_type input widths
+    for name in ('tiny', 'tiny_nrb2', 'c2', 'c4', 'tiny_lut', 'tiny_dup', 'tiny_t0', 'tiny_fe'):
         kw = video_model_and_diffusion_defaults()
         kw.update(cases.ref_config(name))
         with torch.device('meta'):

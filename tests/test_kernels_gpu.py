@@ -348,6 +348,14 @@ def test_groupnorm_temporal_and_spatial_encoding(B, T, HW, Cc):
     ref = (h.view(B * T, HW, Cc) + enc).view(-1, Cc)
     o.add_spatial_encoding(h, enc, h, B * T, HW, Cc)
     assert relerr(h, ref) < 1e-7
+    # + per-frame sinusoid (use_frame_encoding, unet.py:914-926); either addend alone as well
+    femb = rnd(B * T, Cc, seed=6)
+    h2 = rnd(B * T * HW, Cc, seed=7)
+    both, only_f = torch.empty_like(h2), torch.empty_like(h2)
+    o.add_spatial_encoding(h2, enc, both, B * T, HW, Cc, frame_emb=femb)
+    o.add_spatial_encoding(h2, None, only_f, B * T, HW, Cc, frame_emb=femb)
+    assert torch.equal(both.view(B * T, HW, Cc), (h2.view(B * T, HW, Cc) + enc) + femb[:, None, :])
+    assert torch.equal(only_f.view(B * T, HW, Cc), h2.view(B * T, HW, Cc) + femb[:, None, :])
 
 
 def test_cond_mix_and_timestep_embedding():
@@ -372,10 +380,23 @@ def test_cond_mix_and_timestep_embedding():
     assert float(a[:, 45:].abs().max()) == 0
     assert torch.equal(tf.view(B, Fr), t.view(B, 1) * (1 - obs))
     assert torch.equal(am.view(B, Fr), any_)
+    # cond_emb_type 'duplicate' (6 channels) and 't=0' (x unchanged): unet.py:1014-1019
+    o.cond_mix(x, x0, obs, lat, kin, t, B, Fr, H, W, a, tf, am, mode=1)
+    xin = torch.cat([x * m(lat) + x * (1 - m(any_)), x0 * m(obs)], 2).view(B * Fr, 6, H, W)
+    cols = F.unfold(xin, 3, padding=1).view(B * Fr, 6, 9, H * W).permute(0, 3, 2, 1).reshape(-1, 54)
+    assert torch.equal(a[:, :54], cols) and float(a[:, 54:].abs().max()) == 0
+    assert torch.equal(tf.view(B, Fr), t.view(B, 1).expand(B, Fr))
+    o.cond_mix(x, x0, obs, lat, kin, t, B, Fr, H, W, a, tf, am, mode=2)
+    cols = F.unfold(x.view(B * Fr, 3, H, W), 3, padding=1).view(B * Fr, 3, 9, H * W).permute(0, 3, 2, 1).reshape(-1, 27)
+    assert torch.equal(a[:, :27], cols) and float(a[:, 27:].abs().max()) == 0
+    assert torch.equal(am.view(B, Fr), any_)
     tt = torch.tensor([0.0, 1.0, 17.0, 503.25, 999.0]).cuda()
     emb = torch.empty(5, 128, device='cuda')
     o.timestep_embedding(tt, 128, emb)
     assert float((emb.cpu() - U.sinusoid(tt.cpu(), 128)).abs().max()) < 2e-4   # sin/cos of args up to 1e3
+    fi = torch.tensor([0.0, 3.0, 29.0, -4.5, 12.5]).cuda()                     # frame indices, period 10 T
+    o.timestep_embedding(fi, 128, emb, max_period=300)
+    assert float((emb.cpu() - U.sinusoid(fi.cpu(), 128, max_period=300)).abs().max()) < 1e-5
 
 
 def _attn_ref(qkv, heads, mask=None, R=None, pad_interact=True):

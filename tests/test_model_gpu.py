@@ -47,13 +47,16 @@ def tap_name(node):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
-@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES, ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES + cases.UNET_VARIANT_CASES,
+                         ids=lambda c: c['name'])
 def test_forward_matches_reference_and_oracle(golden, case, dtype):
-    g = golden.npz('unet_lut' if case in cases.UNET_LUT_CASES else 'unet')
+    from test_oracle_golden import golden_file, oracle_kwargs
+    g = golden.npz(golden_file(case))
     model, _ = build_model(case['cfg'], golden, dtype)
     model.use_cuda_graph = False
     inp = cases.unet_case_inputs(case)
-    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    mk = cases.variant_kwargs(case, inp) if case in cases.UNET_VARIANT_CASES else cases.model_kwargs_for(inp)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in mk.items()}
     with torch.no_grad():
         out, attn = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
     torch.cuda.synchronize()
@@ -64,7 +67,8 @@ def test_forward_matches_reference_and_oracle(golden, case, dtype):
     taps = {}
     with torch.no_grad():
         ref = U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'],
-                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps)
+                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps,
+                                  **oracle_kwargs(case, inp))
     ws = next(iter(model._workspaces.values()))
     worst = 0.0
     for node in model.plan:
@@ -134,7 +138,9 @@ def test_unsupported_paths_raise(golden):
     kw = video_model_and_diffusion_defaults()
     kw.update(cases.ref_config('tiny'))
     with pytest.raises(NotImplementedError):
-        create_video_model_and_diffusion(**dict(kw, cond_emb_type='duplicate'))
+        create_video_model_and_diffusion(**dict(kw, cond_emb_type='concat'))
+    with pytest.raises(NotImplementedError):
+        create_video_model_and_diffusion(**dict(kw, cross_frame_attention=False))
     with pytest.raises(AssertionError):
         create_video_model_and_diffusion(**dict(kw, rp_alpha=None, rp_beta=None, rp_gamma=None))
     model, _ = create_video_model_and_diffusion(**kw)

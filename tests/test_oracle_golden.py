@@ -54,9 +54,23 @@ def test_schedule_tables_and_sampler_math(golden, case):
         np.testing.assert_allclose(v.numpy(), g[f'{n}/bpd/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
 
 
-@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES, ids=lambda c: c['name'])
+def golden_file(case):
+    return ('unet_lut' if case in cases.UNET_LUT_CASES else
+            'unet_variants' if case in cases.UNET_VARIANT_CASES else 'unet')
+
+
+def oracle_kwargs(case, inp):
+    """Extra oracle arguments of a variant case (observed_frames / x_t_minus_1 / hybrid)."""
+    if case not in cases.UNET_VARIANT_CASES:
+        return {}
+    kw = cases.variant_kwargs(case, inp)
+    return dict(observed_frames=kw['observed_frames'], x_t_minus_1=kw['x_t_minus_1'], hybrid=kw['hybrid'])
+
+
+@pytest.mark.parametrize('case', cases.UNET_CASES + cases.UNET_LUT_CASES + cases.UNET_VARIANT_CASES,
+                         ids=lambda c: c['name'])
 def test_unet_forward_matches_reference(golden, case):
-    g = golden.npz('unet_lut' if case in cases.UNET_LUT_CASES else 'unet')
+    g = golden.npz(golden_file(case))
     spec = golden.json('spec_' + case['cfg'])
     sd = synth.make_state_dict(spec, seed=1)
     cfg = U.model_config(**cases.ref_config(case['cfg']))
@@ -64,7 +78,8 @@ def test_unet_forward_matches_reference(golden, case):
     taps = {}
     with torch.no_grad():
         out = U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'],
-                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps)
+                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps,
+                                  **oracle_kwargs(case, inp))
     assert max_rel(out.numpy(), g[f"{case['name']}/eps"]) < 2e-5
     checked = 0
     for key, val in taps.items():

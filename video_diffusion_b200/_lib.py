@@ -59,9 +59,9 @@ def load():
         'vdm_gn_stats': [_vp, _i32, _i32, _i32, _vp, _vp],
         'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
         'vdm_gn_temporal': [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
-        'vdm_add_spatial_encoding': [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
-        'vdm_cond_mix': [_vp] * 6 + [_i32] * 4 + [_vp, _i32, _vp, _vp, _vp],
-        'vdm_timestep_embedding': [_vp, _i32, _i32, _vp, _vp],
+        'vdm_add_spatial_encoding': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+        'vdm_cond_mix': [_vp] * 6 + [_i32] * 5 + [_vp, _i32, _vp, _vp, _vp],
+        'vdm_timestep_embedding': [_vp, _i32, _i32, C.c_double, _vp, _vp],
         'vdm_rpe_hidden': [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
         'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
         'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],

@@ -1,6 +1,7 @@
 // HBM-bound producer kernels around the GEMMs: GroupNorm statistics / apply (+SiLU,
 // +scale-shift, + concat, + x2 upsample, + stride-2 parity split), temporal GroupNorm,
 // conditioning mix + input-conv im2col, timestep sinusoid, RPE-net hidden layer.
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -356,26 +357,38 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   }
 }
 
+// out = (h + enc[pixel]) + frame_emb[image]; either addend may be absent (unet.py:841-844, 914-926)
 __global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* h, const float* __restrict__ enc,
-                                                                    float* out, long long total4, long long per_img4) {
+                                                                    const float* __restrict__ frame_emb, float* out,
+                                                                    long long total4, long long per_img4, int C4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(h)[i];
-    const float4 e = __ldg(reinterpret_cast<const float4*>(enc) + (i % per_img4));
-    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    if (enc) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(enc) + (i % per_img4));
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    }
+    if (frame_emb) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(frame_emb) + (i / per_img4) * C4 + (i % C4));
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    }
     reinterpret_cast<float4*>(out)[i] = v;
   }
 }
 
 // ------------------------------------------------------------------ conditioning mix + im2col
-// One thread per output pixel (b, f, y, x): gathers the 3x3 neighbourhood of the 5-channel
-// conditioned input and writes one 64-wide im2col row (k = tap*5 + c, zero padded).
-template <typename OutT>
+// One thread per output pixel (b, f, y, x): gathers the 3x3 neighbourhood of the conditioned input and writes one
+// 64-wide im2col row (k = tap*CIN + c, zero padded).  MODE follows cond_emb_type (unet.py:975-1019):
+//   0 'channel'   CIN 5: x*lat + observed*obs + x*(1-any) | obs indicator | kinda_marg indicator; t_frame = t*(1-obs)
+//   1 'duplicate' CIN 6: x*lat + x*(1-any) | x0*obs;                                               t_frame = t
+//   2 't=0'       CIN 3: x unchanged;                                                              t_frame = t
+template <typename OutT, int MODE>
 __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__ x, const float* __restrict__ x0,
                                                         const float* __restrict__ obs, const float* __restrict__ lat,
                                                         const float* __restrict__ kinda, const float* __restrict__ t,
                                                         int B, int F, int H, int W, OutT* __restrict__ a_out,
                                                         float* __restrict__ t_frame, float* __restrict__ attn_mask) {
+  constexpr int CIN = MODE == 0 ? 5 : (MODE == 1 ? 6 : 3);
   const int HW = H * W;
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (m >= (long long)B * F * HW) return;
@@ -385,13 +398,12 @@ __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__
   const float any = fminf(o + l + k, 1.0f);
   if (pix == 0) {
     const float tb = t[n / F];
-    t_frame[n] = 0.0f * o + tb * (1.0f - o);
+    t_frame[n] = MODE == 0 ? 0.0f * o + tb * (1.0f - o) : tb;
     attn_mask[n] = any;
   }
   float row[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) row[i] = 0.f;
-  const float wx = l + (1.0f - any);  // x*latent + x*(1-anything)
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -402,13 +414,22 @@ __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const size_t off = (((size_t)n * 3 + c) * H + iy) * W + ix;
-        // x*latent_mask + x0*obs_mask + x*(1-anything_mask), in the reference's op order
-        row[tap * 5 + c] = __fadd_rn(__fadd_rn(__fmul_rn(x[off], l), __fmul_rn(x0[off], o)), __fmul_rn(x[off], 1.0f - any));
+        if constexpr (MODE == 0) {
+          // x*latent_mask + observed*obs_mask + x*(1-anything_mask), in the reference's op order
+          row[tap * CIN + c] =
+              __fadd_rn(__fadd_rn(__fmul_rn(x[off], l), __fmul_rn(x0[off], o)), __fmul_rn(x[off], 1.0f - any));
+        } else if constexpr (MODE == 1) {
+          row[tap * CIN + c] = __fadd_rn(__fmul_rn(x[off], l), __fmul_rn(x[off], 1.0f - any));
+          row[tap * CIN + 3 + c] = __fmul_rn(x0[off], o);
+        } else {
+          row[tap * CIN + c] = x[off];
+        }
       }
-      row[tap * 5 + 3] = o;
-      row[tap * 5 + 4] = k;
+      if constexpr (MODE == 0) {
+        row[tap * CIN + 3] = o;
+        row[tap * CIN + 4] = k;
+      }
     }
-  (void)wx;
   OutT* dst = a_out + (size_t)m * 64;
   if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
@@ -425,13 +446,14 @@ __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__
   }
 }
 
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float neg_log_period,
+                                          float* __restrict__ out) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * half) return;
   const int row = idx / half, i = idx - row * half;
-  // freqs = exp(-ln(10000) * i / half) in fp32 (nn.py:98-101)
-  const float freq = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), (float)half));
+  // freqs = exp(-ln(max_period) * i / half) in fp32 (nn.py:98-101)
+  const float freq = expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)i), (float)half));
   const float arg = __fmul_rn(t[row], freq);
   out[(size_t)row * dim + i] = cosf(arg);
   out[(size_t)row * dim + half + i] = sinf(arg);
@@ -636,38 +658,51 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
   return 0;
 }
 
-extern "C" int vdm_add_spatial_encoding(const float* h, const float* enc, float* out, int32_t n_img, int32_t HW,
-                                        int32_t C, vdm_stream_t stream) {
-  VDM_REQUIRE(h && enc && out && C % 4 == 0, "add_spatial_encoding: bad arguments");
+extern "C" int vdm_add_spatial_encoding(const float* h, const float* enc, const float* frame_emb, float* out,
+                                        int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream) {
+  VDM_REQUIRE(h && (enc || frame_emb) && out && C % 4 == 0, "add_spatial_encoding: bad arguments");
   const long long per4 = (long long)HW * C / 4, total4 = per4 * n_img;
   const int grid = (int)std::min<long long>((total4 + 255) / 256, (long long)num_sms() * 16);
-  add_spatial_encoding_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, enc, out, total4, per4);
+  add_spatial_encoding_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, enc, frame_emb, out, total4, per4, C / 4);
   VDM_AFTER_LAUNCH("add_spatial_encoding");
   return 0;
 }
 
-extern "C" int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
-                            const float* kinda_marg_mask, const float* t, int32_t B, int32_t F, int32_t H, int32_t W,
-                            void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask, vdm_stream_t stream) {
-  VDM_REQUIRE(x && x0 && obs_mask && latent_mask && kinda_marg_mask && t && a_out && t_frame && attn_mask,
-              "cond_mix: NULL pointer");
+template <int MODE>
+static void launch_cond_mix(const float* x, const float* x0, const float* obs, const float* lat, const float* kinda,
+                            const float* t, int B, int F, int H, int W, void* a_out, int out_dtype, float* t_frame,
+                            float* attn_mask, cudaStream_t stream) {
   const long long M = (long long)B * F * H * W;
   const int grid = (int)((M + 127) / 128);
   if (out_dtype == VDM_BF16)
-    cond_mix_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(x, x0, obs_mask, latent_mask, kinda_marg_mask,
-                                                                          t, B, F, H, W, (__nv_bfloat16*)a_out, t_frame,
-                                                                          attn_mask);
+    cond_mix_kernel<__nv_bfloat16, MODE><<<grid, 128, 0, stream>>>(x, x0, obs, lat, kinda, t, B, F, H, W,
+                                                                  (__nv_bfloat16*)a_out, t_frame, attn_mask);
   else
-    cond_mix_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(x, x0, obs_mask, latent_mask, kinda_marg_mask, t, B, F,
-                                                                  H, W, (float*)a_out, t_frame, attn_mask);
+    cond_mix_kernel<float, MODE><<<grid, 128, 0, stream>>>(x, x0, obs, lat, kinda, t, B, F, H, W, (float*)a_out,
+                                                          t_frame, attn_mask);
+}
+
+extern "C" int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
+                            const float* kinda_marg_mask, const float* t, int32_t B, int32_t F, int32_t H, int32_t W,
+                            int32_t mode, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
+                            vdm_stream_t stream) {
+  VDM_REQUIRE(x && x0 && obs_mask && latent_mask && kinda_marg_mask && t && a_out && t_frame && attn_mask,
+              "cond_mix: NULL pointer");
+  VDM_REQUIRE(mode >= 0 && mode <= 2, "cond_mix: mode must be 0 (channel), 1 (duplicate) or 2 (t=0)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0) launch_cond_mix<0>(x, x0, obs_mask, latent_mask, kinda_marg_mask, t, B, F, H, W, a_out, out_dtype, t_frame, attn_mask, s);
+  else if (mode == 1) launch_cond_mix<1>(x, x0, obs_mask, latent_mask, kinda_marg_mask, t, B, F, H, W, a_out, out_dtype, t_frame, attn_mask, s);
+  else launch_cond_mix<2>(x, x0, obs_mask, latent_mask, kinda_marg_mask, t, B, F, H, W, a_out, out_dtype, t_frame, attn_mask, s);
   VDM_AFTER_LAUNCH("cond_mix");
   return 0;
 }
 
-extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, float* out, vdm_stream_t stream) {
-  VDM_REQUIRE(t_frame && out && n > 0 && dim >= 2, "timestep_embedding: bad arguments");
+extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, double max_period, float* out,
+                                      vdm_stream_t stream) {
+  VDM_REQUIRE(t_frame && out && n > 0 && dim >= 2 && max_period > 0, "timestep_embedding: bad arguments");
   const int total = n * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_frame, n, dim, out);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_frame, n, dim,
+                                                                                  (float)(-std::log(max_period)), out);
   VDM_AFTER_LAUNCH("timestep_embedding");
   return 0;
 }

@@ -104,20 +104,21 @@ def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):
            nbytes=_nbytes(x, out_f32, out_a))
 
 
-def add_spatial_encoding(h, enc, out, n_img, HW, Cc):
+def add_spatial_encoding(h, enc, out, n_img, HW, Cc, frame_emb=None):
     _timed('add_spatial_encoding', lambda: check(_lib.load().vdm_add_spatial_encoding(
-        ptr(h), ptr(enc), ptr(out), n_img, HW, Cc, stream()), 'vdm_add_spatial_encoding'), nbytes=_nbytes(h, out))
+        ptr(h), ptr(enc), ptr(frame_emb), ptr(out), n_img, HW, Cc, stream()), 'vdm_add_spatial_encoding'),
+           nbytes=_nbytes(h, out))
 
 
-def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask):
+def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask, mode=0):
     _timed('cond_mix', lambda: check(_lib.load().vdm_cond_mix(
-        ptr(x), ptr(x0), ptr(obs), ptr(lat), ptr(kinda), ptr(t), B, F, H, W, ptr(a_out), dt(a_out.dtype), ptr(t_frame),
+        ptr(x), ptr(x0), ptr(obs), ptr(lat), ptr(kinda), ptr(t), B, F, H, W, mode, ptr(a_out), dt(a_out.dtype), ptr(t_frame),
         ptr(attn_mask), stream()), 'vdm_cond_mix'), nbytes=_nbytes(x, x0, a_out))
 
 
-def timestep_embedding(t_frame, dim, out):
+def timestep_embedding(t_frame, dim, out, max_period=10000.0):
     _timed('timestep_embedding', lambda: check(_lib.load().vdm_timestep_embedding(
-        ptr(t_frame), t_frame.numel(), dim, ptr(out), stream()), 'vdm_timestep_embedding'))
+        ptr(t_frame), t_frame.numel(), dim, float(max_period), ptr(out), stream()), 'vdm_timestep_embedding'))
 
 
 def rpe_hidden(e_t, frame_indices, wd, bd, B, T, Cc, out, et_offsets=None, n_blocks=1):

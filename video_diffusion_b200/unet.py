@@ -60,6 +60,7 @@ class UNetModel(nn.Module):
         if num_heads_upsample not in (-1, num_heads):
             raise NotImplementedError('num_heads_upsample != num_heads')
         self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self._cond_mode = 2          # input-mix mode of vdm_cond_mix: plain 3-channel frames unless a subclass says otherwise
         self.num_res_blocks, self.attention_resolutions = num_res_blocks, tuple(attention_resolutions)
         self.dropout, self.channel_mult, self.num_heads = dropout, tuple(channel_mult), num_heads
         self.use_scale_shift_norm, self.image_size = use_scale_shift_norm, image_size
@@ -225,11 +226,12 @@ class UNetModel(nn.Module):
 
         put('te_w0', sd['time_embed.0.weight']); put('te_b0', sd['time_embed.0.bias'])
         put('te_w2', sd['time_embed.2.weight']); put('te_b2', sd['time_embed.2.bias'])
-        w_in = sd['input_blocks.0.0.weight']                  # (ch, Cin, 3, 3) -> im2col columns k = tap*5 + c
-        w5 = torch.zeros(w_in.shape[0], 9, 5)
-        w5[:, :, :w_in.shape[1]] = w_in.permute(0, 2, 3, 1).reshape(w_in.shape[0], 9, w_in.shape[1])
+        w_in = sd['input_blocks.0.0.weight']                  # (ch, Cin, 3, 3) -> im2col columns k = tap*Cin + c
+        cin = w_in.shape[1]
+        if 9 * cin > 64:
+            raise NotImplementedError('input conv: at most 7 input channels')
         pad = torch.zeros(w_in.shape[0], 64)
-        pad[:, :45] = w5.reshape(w_in.shape[0], 45)
+        pad[:, :9 * cin] = w_in.permute(0, 2, 3, 1).reshape(w_in.shape[0], 9 * cin)
         put('in_w', pad, adt); put('in_b', sd['input_blocks.0.0.bias'])
         emb_w, emb_b, rpe_w, rpe_b = [], [], [], []
         emb_off = rpe_off = 0
@@ -308,6 +310,7 @@ class UNetModel(nn.Module):
             self.t = torch.empty(B, device=dev, dtype=f32)
             self.t_override = torch.empty(N, device=dev, dtype=f32)
             self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
+            self.fi_float = torch.empty(B, F, device=dev, dtype=f32)
             self.stat_bufs = {}
             self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
             self.pool_used = 0
@@ -552,7 +555,8 @@ class UNetModel(nn.Module):
         ws.zero_stats()
         a_in = ws.buf('a_in', (N * H * W, 64), adt)
         t_frame, amask = ws.buf('t_frame', (N,)), ws.buf('amask', (N,))
-        ops.cond_mix(ws.x, ws.x0, ws.obs, ws.lat, ws.kinda, ws.t, B, F, H, W, a_in, t_frame, amask)
+        ops.cond_mix(ws.x, ws.x0, ws.obs, ws.lat, ws.kinda, ws.t, B, F, H, W, a_in, t_frame, amask,
+                     mode=self._cond_mode)
         if per_frame_t:
             t_frame = ws.t_override
         emb_out = ws.buf('emb_out', (N, P['emb_w'].shape[0]))
@@ -615,9 +619,14 @@ class UNetModel(nn.Module):
             if in_groups:
                 hs.append(x)
                 n_groups_done += 1
-                if n_groups_done == self.n_blocks_before_attn and 'enc' in P:
+                frame_enc = getattr(self, 'use_frame_encoding', False)
+                if n_groups_done == self.n_blocks_before_attn and ('enc' in P or frame_enc):
                     hn = ws.buf('h_enc', tuple(x[0].shape))
-                    ops.add_spatial_encoding(x[0], P['enc'], hn, N, H * W, x[0].shape[1])
+                    femb = None
+                    if frame_enc:     # sinusoid of the (optionally centred) frame indices, period 10 T (unet.py:914-926)
+                        femb = ws.buf('frame_emb', (N, x[0].shape[1]))
+                        ops.timestep_embedding(ws.fi_float, x[0].shape[1], femb, max_period=self.T * 10)
+                    ops.add_spatial_encoding(x[0], P.get('enc'), hn, N, H * W, x[0].shape[1], frame_emb=femb)
                     x = (hn, None)
 
         for node in self.plan:
@@ -711,6 +720,9 @@ class UNetModel(nn.Module):
         ws.kinda.copy_(kinda.reshape(B, F))
         ws.t.copy_(t.reshape(B))
         ws.fi.copy_(frame_indices.reshape(B, F))
+        if getattr(self, 'use_frame_encoding', False):
+            fi = frame_indices.reshape(B, F).float()
+            ws.fi_float.copy_(fi - fi.mean(dim=1, keepdim=True) if self.enforce_position_invariance else fi)
         if per_frame_t is not None:
             ws.t_override.copy_(per_frame_t.reshape(B * F))
         if self.use_cuda_graph:
@@ -734,8 +746,6 @@ class UNetModel(nn.Module):
 
 class UNetVideoModel(UNetModel):
     def __init__(self, T, use_frame_encoding, cross_frame_attention, enforce_position_invariance, *args, **kwargs):
-        if use_frame_encoding:
-            raise NotImplementedError('use_frame_encoding=True is not supported yet')
         if not cross_frame_attention:
             raise NotImplementedError('cross_frame_attention=False is not supported yet')
         self.T = T
@@ -761,13 +771,25 @@ class UNetVideoModel(UNetModel):
 
 class CondMargVideoModel(UNetVideoModel):
     def __init__(self, cond_emb_type, **kwargs):
-        if cond_emb_type.replace('-initzero', '') != 'channel':
-            raise NotImplementedError(f"cond_emb_type={cond_emb_type!r}: only 'channel' is supported")
-        kwargs['in_channels'] += 2
+        """unet.py:932-947: 'channel' adds two indicator channels, 'duplicate' / 'all' double the input channels,
+        't=0' marks observed frames through the timestep only."""
+        base = cond_emb_type.replace('-initzero', '')
+        if 'channel' in cond_emb_type:
+            kwargs['in_channels'] += 2
+        elif 'duplicate' in cond_emb_type or 'all' in cond_emb_type:
+            kwargs['in_channels'] *= 2
+        elif cond_emb_type != 't=0':
+            raise NotImplementedError(f'cond_emb_type={cond_emb_type!r}')
         super().__init__(**kwargs)
+        w_in = self.input_blocks._modules['0']._modules['0'].weight.data
         if cond_emb_type == 'channel-initzero':
-            self.input_blocks._modules['0']._modules['0'].weight.data[:, 3] = 0.0
-        self.cond_emb_type = 'channel'
+            w_in[:, 3] = 0.0
+        if cond_emb_type in ('duplicate-initzero', 'all-initzero'):
+            w_in[:, 3:] = w_in[:, :3]
+        self.cond_emb_type = base
+        if base not in ('channel', 'duplicate', 'all', 't=0'):
+            raise NotImplementedError(f'cond_emb_type={cond_emb_type!r}')
+        self._cond_mode = {'channel': 0, 'duplicate': 1, 'all': 1, 't=0': 2}[base]
 
     def forward(self, x, x0=None, obs_mask=None, latent_mask=None, kinda_marg_mask=None, timesteps=None,
                 frame_indices=None, return_attn_weights=False, **kwargs):
@@ -775,16 +797,42 @@ class CondMargVideoModel(UNetVideoModel):
         model(x, timesteps=t, **model_kwargs) (respace.py:119)."""
         if timesteps is None:
             raise TypeError('timesteps is required')
-        if kwargs.get('observed_frames', 'x_0') != 'x_0':
-            raise NotImplementedError("only observed_frames='x_0' is supported")
-        if 'x_t_minus_1' not in kwargs or 'observed_frames' not in kwargs:
-            raise KeyError('x_t_minus_1')   # the reference requires both kwargs (unet.py:958-974, SURVEY Q3)
         if return_attn_weights:
             raise NotImplementedError('return_attn_weights=True')
         B, F = x.shape[:2]
         if frame_indices is None:
             frame_indices = torch.arange(F, device=x.device).view(1, F).expand(B, F)
-        out = self._execute(x, x0, obs_mask, latent_mask, kinda_marg_mask, timesteps.float(), frame_indices, F)
+        t = timesteps.float()
+        observed, per_frame_t = x0, None
+        if self.cond_emb_type == 'channel':
+            if 'x_t_minus_1' not in kwargs or 'observed_frames' not in kwargs:
+                raise KeyError('x_t_minus_1')   # the reference requires both kwargs (unet.py:958-974, SURVEY Q3)
+            which = kwargs['observed_frames']
+            om = obs_mask.reshape(B, F).float()
+            if 'hybrid' in which:
+                # unet.py:966-974, 1001-1009: below the threshold the observed frames are x_{t-1} at time t-1,
+                # above it kwargs['hybrid'] at time `threshold`
+                thr = int(which.split('_')[-1])
+                below = (t < thr).view(B, 1, 1, 1, 1)
+                observed = torch.where(below, kwargs['x_t_minus_1'], kwargs['hybrid'])
+                t_obs = torch.where(t < thr, t - 1, torch.full_like(t, float(thr)))
+            elif which == 'x_0':
+                t_obs = None                    # observed frames at time 0: the kernel's own per-frame timestep
+            elif which == 'x_t':
+                observed, t_obs = x, t
+            elif which == 'x_t_minus_1':
+                observed, t_obs = kwargs['x_t_minus_1'], t - 1
+            else:
+                raise NotImplementedError(f'observed_frames={which!r} (training-only or unknown)')
+            if t_obs is not None:
+                per_frame_t = t_obs.view(B, 1) * om + t.view(B, 1) * (1 - om)
+        elif self.cond_emb_type == 't=0':
+            # unet.py:1019 writes -1 through an expanded (stride-0) view of the timesteps: every frame of a video
+            # that has at least one observed frame ends up at t = -1.  Reproduced as the reference behaves.
+            any_obs = (obs_mask.reshape(B, F) == 1).any(dim=1)
+            per_frame_t = torch.where(any_obs, torch.full_like(t, -1.0), t).view(B, 1).expand(B, F).contiguous()
+        out = self._execute(x, observed, obs_mask, latent_mask, kinda_marg_mask, t, frame_indices, F,
+                            per_frame_t=per_frame_t)
         return out, None
 
     def __call__(self, x, *args, **kwargs):
