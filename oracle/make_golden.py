@@ -221,12 +221,54 @@ def dump_chain():
     np.savez_compressed(os.path.join(GOLD, 'chain.npz'), **arrays)
 
 
+P_LOOP_MODES = ('x_0', 'x_t_minus_1', 'hybrid_5')
+
+
+def dump_p_sample_loop():
+    """p_sample_loop (gaussian_diffusion.py:450-595) on the first window of the chain case, one run per
+    observed_frames mode.  The reference hard-codes `.cuda()` / `.to('cuda')` on two tiny tensors in this loop
+    (:567-573); for this CPU run those two calls are mapped to no-ops, nothing else is touched."""
+    c = CHAIN_CASE
+    model, diffusion = load_ref_model(c['cfg'], c['respacing'])
+    B, T = c['batch'], c['video_length']
+    video = synth.make_video((B, T, 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    it = inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])
+    obs, lat = next(iter(it))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+    fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    real_cuda, real_to = torch.Tensor.cuda, torch.Tensor.to
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = lambda self, *a, **k: self if a and a[0] == 'cuda' else real_to(self, *a, **k)
+    arrays = {}
+    try:
+        for mode in P_LOOP_MODES:
+            kw = dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+                      observed_frames=mode)
+            gd.th.randn_like = NoiseReplay(c['noise_seed'] + 700)
+            init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 699)
+            with torch.no_grad():
+                out, _ = diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True,
+                                                 model_kwargs=kw, device='cpu')
+            arrays[f'p_loop/{mode}'] = out.numpy()
+            print('p_sample_loop', mode, float(out.abs().max()), float(out.std()))
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = real_cuda, real_to
+        gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'p_loop.npz'), **arrays)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     if sys.argv[1:] == ['lut']:       # only the lookup-table RPE fixtures (leaves the other files untouched)
         dump_specs(('tiny_lut',))
         dump_unet(UNET_LUT_CASES, 'unet_lut.npz')
+        sys.exit(0)
+    if sys.argv[1:] == ['ploop']:
+        dump_p_sample_loop()
         sys.exit(0)
     if sys.argv[1:] == ['variants']:  # cond_emb_type / frame-encoding / observed_frames variants only
         dump_specs(('tiny_dup', 'tiny_t0', 'tiny_fe', 'tiny_fei'))

@@ -89,6 +89,35 @@ def test_ddim_sample_loop_matches_reference(golden, replay, dtype, min_psnr):
     assert p >= min_psnr
 
 
+@pytest.mark.parametrize('mode', ['x_0', 'x_t_minus_1', 'hybrid_5'])
+@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 30.0)], ids=['fp32', 'bf16'])
+def test_p_sample_loop_matches_reference(golden, replay, dtype, min_psnr, mode):
+    """p_sample_loop incl. its per-step re-noised conditioning tensors (gaussian_diffusion.py:565-582)."""
+    from video_diffusion_b200.inference_util import inference_strategies
+    c = cases.CHAIN_CASE
+    g = golden.npz('p_loop')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    obs, lat = next(iter(inference_strategies[c['mode']](video_length=c['video_length'], num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1).cuda()
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    kw = dict(frame_indices=torch.tensor(obs + lat).repeat(c['batch'], 1).cuda(), x0=x0, obs_mask=om,
+              latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om), observed_frames=mode)
+    keys = set(kw)
+    init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 699).cuda()
+    replay(c['noise_seed'] + 700)
+    out, _ = diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw)
+    assert set(kw) == keys                       # the caller's dict is not mutated (the reference's is, SURVEY Q4)
+    p = psnr(out.cpu().numpy(), g[f'p_loop/{mode}'])
+    print(f'p_sample_loop[{mode}] {dtype}: PSNR vs reference = {p:.1f} dB')
+    assert p >= min_psnr
+    if mode == 'hybrid_5':
+        with pytest.raises(IndexError):          # threshold indexes the (respaced) schedule tables
+            diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, model_kwargs=dict(kw, observed_frames='hybrid_500'))
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
 def test_elbo_within_half_percent(golden, replay, dtype):
     from video_diffusion_b200.sampling import run_bpd_evaluation

@@ -153,7 +153,9 @@ class GaussianDiffusion:
         if noise is None:
             noise = th.randn_like(x_start)
         assert noise.shape == x_start.shape
-        return ops.q_sample(x_start.contiguous(), noise.contiguous(), t.long().contiguous(),
+        t = t.long()
+        t = th.where(t < 0, t + self.num_timesteps, t)     # numpy-style negative index (the loop asks for t - 1 at t = 0)
+        return ops.q_sample(x_start.contiguous(), noise.contiguous(), t.contiguous(),
                             self.tables(x_start.device))
 
     def q_posterior_mean_variance(self, x_start, x_t, t):
@@ -229,19 +231,36 @@ class GaussianDiffusion:
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                   model_kwargs=None, latent_mask=None, device=None, progress=False,
                                   return_attn_weights=False, use_gradient_method=False):
-        """Ancestral chain from noise.  With observed_frames='x_0' (the only mode the CUDA model
-        supports) the reference's per-step x_t_minus_1 / x_random / hybrid tensors
-        (gaussian_diffusion.py:565-582) never reach the network, so they are not materialised;
-        the caller's model_kwargs dict is left untouched."""
+        """Ancestral chain from noise (gaussian_diffusion.py:528-595).  Every step re-noises x0 into the
+        x_t_minus_1 (and, for 'hybrid_<N>', hybrid) conditioning tensors with the reference's noise choice: the
+        chain's initial `noise` when one was given, fresh draws otherwise.  The draw for the training-only x_random
+        is kept (and discarded) so a seeded torch generator stays in step with the reference.  Works on a copy of
+        model_kwargs: the caller's dict is left untouched, and no `.cuda()` is hard-coded."""
         if return_attn_weights:
             raise NotImplementedError('attention-map logging is not supported')
         kw = dict(model_kwargs or {})
-        kw.setdefault('x_t_minus_1', kw.get('x0'))
         kw.setdefault('observed_frames', 'x_0')
-        return self._loop(lambda img, t: self.p_sample(model, img, t, clip_denoised=clip_denoised,
-                                                       denoised_fn=denoised_fn, model_kwargs=kw,
-                                                       use_gradient_method=use_gradient_method),
-                          model, shape, noise, device, progress)
+        which = kw['observed_frames']
+        x0 = kw.get('x0')
+        if x0 is None:
+            raise KeyError('x0')
+        kw.setdefault('x_t_minus_1', x0)
+
+        def step(img, t):
+            draw = (lambda: th.randn_like(x0)) if noise is None else (lambda: noise)
+            n_prev, n_random = draw(), draw()
+            del n_random                              # x_random only reaches the network in training mode
+            if which != 'x_0':
+                kw['x_t_minus_1'] = self.q_sample(x0, t - 1, noise=n_prev)
+            if 'hybrid' in which:
+                thr = int(which.split('_')[-1])
+                if thr >= self.num_timesteps:        # the reference indexes its schedule tables with it
+                    raise IndexError(f'hybrid threshold {thr} is out of range for {self.num_timesteps} timesteps')
+                kw['hybrid'] = self.q_sample(x0, th.full_like(t, thr), noise=draw())
+            return self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                 model_kwargs=kw, use_gradient_method=use_gradient_method)
+
+        return self._loop(step, model, shape, noise, device, progress)
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                       latent_mask=None, device=None, progress=False, return_attn_weights=False,
