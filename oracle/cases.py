@@ -122,6 +122,9 @@ DIFFUSION_CASES = [
          ts=dict(tmid=[0, 44]), t_seq=[44, 20, 0]),
 ]
 
+# video_optimal_schedule.py:77-207 probes the ELBO terms at one random timestep PER VIDEO: a 2-D t_seq (rows = videos)
+PROBE_T_SEQ = [[517, 3], [0, 999]]
+
 CHAIN_CASE = dict(cfg='tiny', image_size=32, respacing='ddim10', bpd_respacing='ddim4', batch=1, video_length=30,
                   obs_length=5, max_frames=10, step_size=5, mode='independent', video_seed=31, noise_seed=5000,
                   bpd_obs=[[0, 1, 2], [3, 7, 9, 11, 12, 13]], bpd_lat=[[10, 11, 12, 13, 14], [20, 21, 22, 23]])

@@ -187,8 +187,11 @@ def calc_bpd_loop(s, eps_fn, x0, latent_mask, noises, t_seq=None, clip_denoised=
     if t_seq is None:
         t_seq = list(range(s.num_timesteps))[::-1]
     vb, xs_mse, mse = [], [], []
+    two_d = isinstance(t_seq, np.ndarray) and t_seq.ndim == 2       # one row of timesteps per batch item (:960-969)
+    if two_d:
+        t_seq = t_seq.transpose()
     for i, tt in enumerate(t_seq):
-        t = torch.full((B,), tt, dtype=torch.long)
+        t = torch.as_tensor(tt, dtype=torch.long) if two_d else torch.full((B,), tt, dtype=torch.long)
         noise = noises[i]
         x_t = q_sample(s, x0, t, noise)
         out = vb_terms(s, eps_fn(x_t, t), x0, x_t, t, latent_mask, clip_denoised)

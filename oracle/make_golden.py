@@ -221,6 +221,26 @@ def dump_chain():
     np.savez_compressed(os.path.join(GOLD, 'chain.npz'), **arrays)
 
 
+def dump_probe():
+    """calc_bpd_loop_subsampled with a 2-D t_seq, one row of timesteps per video (gaussian_diffusion.py:960-969),
+    the way scripts/video_optimal_schedule.py:97-105 calls it; stand-in network, replayed noise."""
+    from oracle.cases import PROBE_T_SEQ
+    case = DIFFUSION_CASES[0]
+    d = create_gaussian_diffusion(steps=1000, noise_schedule=case['schedule'], timestep_respacing=case['respacing'],
+                                  rescale_timesteps=True, rescale_learned_sigmas=True)
+    shape = case['shape']
+    x0 = synth.make_video(shape, seed=12)
+    lat = torch.zeros(shape[0], shape[1], 1, 1, 1)
+    lat[:, shape[1] // 2:] = 1
+    model = lambda xx, timesteps, **kw: (fake_eps(xx, timesteps), None)
+    gd.th.randn_like = NoiseReplay(2500)
+    bpd = d.calc_bpd_loop_subsampled(model, x0, clip_denoised=True, model_kwargs={}, latent_mask=lat,
+                                     t_seq=np.array(PROBE_T_SEQ))
+    gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'probe.npz'), **{f'probe/{k}': v.numpy() for k, v in bpd.items()})
+    print('probe', bpd['vb'])
+
+
 P_LOOP_MODES = ('x_0', 'x_t_minus_1', 'hybrid_5')
 
 
@@ -269,6 +289,7 @@ if __name__ == '__main__':
         sys.exit(0)
     if sys.argv[1:] == ['ploop']:
         dump_p_sample_loop()
+        dump_probe()
         sys.exit(0)
     if sys.argv[1:] == ['variants']:  # cond_emb_type / frame-encoding / observed_frames variants only
         dump_specs(('tiny_dup', 'tiny_t0', 'tiny_fe', 'tiny_fei'))

@@ -54,6 +54,22 @@ def test_schedule_tables_and_sampler_math(golden, case):
         np.testing.assert_allclose(v.numpy(), g[f'{n}/bpd/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
 
 
+def test_per_video_timestep_probe_matches_reference(golden):
+    """2-D t_seq (one row of timesteps per video), the call scripts/video_optimal_schedule.py:97-105 makes."""
+    case = cases.DIFFUSION_CASES[0]
+    g = golden.npz('probe')
+    s = D.Schedule(1000, case['schedule'], case['respacing'])
+    shape = case['shape']
+    x0 = synth.make_video(shape, 12)
+    lat = torch.zeros(shape[0], shape[1], 1, 1, 1)
+    lat[:, shape[1] // 2:] = 1
+    t_seq = np.array(cases.PROBE_T_SEQ)
+    noises = [synth.make_noise(shape, 2500 + i) for i in range(t_seq.shape[1])]
+    bpd = D.calc_bpd_loop(s, lambda xt, t: cases.fake_eps(xt, s.model_time(t)), x0, lat, noises, t_seq)
+    for k, v in bpd.items():
+        np.testing.assert_allclose(v.numpy(), g[f'probe/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
+
+
 def golden_file(case):
     return ('unet_lut' if case in cases.UNET_LUT_CASES else
             'unet_variants' if case in cases.UNET_VARIANT_CASES else 'unet')
