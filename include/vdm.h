@@ -170,6 +170,16 @@ int vdm_rpe_hidden(const float* e_t, int32_t ld_et,
                    const int64_t* frame_indices, const float* wd, const float* bd, int32_t B, int32_t T,
                    int32_t C, void* out, int32_t out_dtype, vdm_stream_t stream);
 
+/* ---- head-averaged attention maps (logging only; return_attn_weights=True, unet.py:464-468) ----
+ * out[g][i][j] = | mean over heads of softmax_j(logits[i][j]) |, g = outer * n_inner + inner, [n_outer*n_inner][L][L].
+ * Sequence element l of g is the qkv row at qkv + outer*outer_stride + inner*inner_stride + l*seq_stride (strides in
+ * elements; row columns (3, heads, hd)).  Temporal attention: outer = b, inner = pixel, r_q / r_k: [B*L*L][C] RPE
+ * tables and mask [B][L] as for vdm_attn_temporal.  Spatial attention: outer = image, n_inner = 1, NULL tables / mask. */
+int vdm_attn_weights_mean(const void* qkv, int32_t qkv_dtype, int64_t n_outer, int64_t n_inner,
+                          int64_t outer_stride, int64_t inner_stride, int64_t seq_stride, int32_t L,
+                          int32_t heads, int32_t hd, const float* r_q, const float* r_k, const float* mask,
+                          int32_t allow_pad_interactions, float* out, vdm_stream_t stream);
+
 /* ---- temporal attention with in-kernel RPE bias (unet.py:477-536) -------------------------
  * qkv: [B*T*HW][3C] fp32 (row (b,t,pix); columns (3, heads, hd)); R_q/R_k/R_v: [B*T*T][C] fp32
  * (row (b,i,j), columns (heads, hd)); mask: [B][T] fp32 (1 = real frame).

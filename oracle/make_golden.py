@@ -241,6 +241,55 @@ def dump_probe():
     print('probe', bpd['vb'])
 
 
+def dump_attn():
+    """return_attn_weights=True (unet.py:464-468, 797-801; gaussian_diffusion.py:496-524): per-layer head-averaged
+    attention maps of one ragged forward, and the per-quartile averages p_sample_loop returns.  The maps are large
+    (B*F x 256 x 256), so the fixtures keep synth.fingerprint signatures (moments + strided samples)."""
+    arrays = {}
+    case = UNET_CASES[1]
+    model, _ = load_ref_model(case['cfg'])
+    inp = unet_case_inputs(case)
+    with torch.no_grad():
+        out, attns = model(inp['x'], timesteps=inp['t_model'], return_attn_weights=True, **model_kwargs_for(inp))
+    arrays['fwd/eps'] = synth.fingerprint(out, 64)
+    for key, layers in attns.items():
+        for i, a in enumerate(layers):
+            arrays[f'fwd/{key}/{i}'] = synth.fingerprint(a, 256)
+            arrays[f'fwd/{key}/{i}/shape'] = np.array(a.shape)
+    print('attn fwd', {k: len(v) for k, v in attns.items()})
+
+    c = CHAIN_CASE
+    model, diffusion = load_ref_model(c['cfg'], c['respacing'])
+    B, T = c['batch'], c['video_length']
+    video = synth.make_video((B, T, 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    it = inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])
+    obs, lat = next(iter(it))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+    fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    real_cuda, real_to = torch.Tensor.cuda, torch.Tensor.to
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = lambda self, *a, **k: self if a and a[0] == 'cuda' else real_to(self, *a, **k)
+    try:
+        kw = dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+                  observed_frames='x_0')
+        gd.th.randn_like = NoiseReplay(c['noise_seed'] + 700)
+        init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 699)
+        with torch.no_grad():
+            out, attns = diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True,
+                                                 model_kwargs=kw, device='cpu', return_attn_weights=True)
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = real_cuda, real_to
+        gd.th.randn_like = torch.randn_like
+    for tag, a in attns.items():
+        arrays['loop/' + tag] = synth.fingerprint(a, 512)
+        arrays['loop/' + tag + '/shape'] = np.array(a.shape)
+    print('attn loop', sorted(attns))
+    np.savez_compressed(os.path.join(GOLD, 'attn.npz'), **arrays)
+
+
 P_LOOP_MODES = ('x_0', 'x_t_minus_1', 'hybrid_5')
 
 
@@ -286,6 +335,9 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['lut']:       # only the lookup-table RPE fixtures (leaves the other files untouched)
         dump_specs(('tiny_lut',))
         dump_unet(UNET_LUT_CASES, 'unet_lut.npz')
+        sys.exit(0)
+    if sys.argv[1:] == ['attn']:
+        dump_attn()
         sys.exit(0)
     if sys.argv[1:] == ['ploop']:
         dump_p_sample_loop()

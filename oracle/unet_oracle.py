@@ -156,7 +156,7 @@ def rpe_lookup(sd, p, dist, rp):
     return sd[p + 'lookup_table_weight'][rpe_bucket_ids(dist, *rp)]
 
 
-def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact, with_rpe, rp=None):
+def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact, with_rpe, rp=None, log=None):
     """unet.py:471-540.  x: (B, D, C, L) attends over the last axis L."""
     B, D, C, L = x.shape
     hd = C // heads
@@ -190,6 +190,8 @@ def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact,
         neg[allowed == 0] = float('inf')
         logits = logits - neg.view(B, 1, 1, L, L)
     w = torch.softmax(logits.float(), dim=-1)
+    if log is not None:                                           # logging maps, unet.py:464-468
+        log.append(w.reshape(B * D, heads, L, L).mean(dim=1).abs())
     out = w @ v
     if with_rpe:
         out = out + torch.einsum('bdhts,btshf->bdhtf', w, r_v)
@@ -198,20 +200,22 @@ def rpe_attention(sd, p, x, temb, frame_indices, attn_mask, heads, pad_interact,
     return (xn + out).permute(0, 1, 3, 2)                          # residual on the NORMALISED x
 
 
-def factorized_attention(sd, p, x, temb, frame_indices, attn_mask, T, cfg):
+def factorized_attention(sd, p, x, temb, frame_indices, attn_mask, T, cfg, attn_log=None):
     """unet.py:236-268: temporal RPE attention, then spatial attention."""
     BT, C, H, W = x.shape
     B = BT // T
     xt = x.view(B, T, C, H, W).permute(0, 3, 4, 2, 1).reshape(B, H * W, C, T)
     xt = rpe_attention(sd, p + 'temporal_attention.', xt, temb, frame_indices,
-                       attn_mask.reshape(B, T), cfg['heads'], cfg['pad_interact'], True, rp=cfg.get('rp'))
+                       attn_mask.reshape(B, T), cfg['heads'], cfg['pad_interact'], True, rp=cfg.get('rp'),
+                       log=None if attn_log is None else attn_log['temporal'])
     xs = xt.view(B, H, W, C, T).permute(0, 4, 3, 1, 2).reshape(B, T, C, H * W)
     xs = rpe_attention(sd, p + 'spatial_attention.', xs, temb, None, None,
-                       cfg['heads'], cfg['pad_interact'], False)
+                       cfg['heads'], cfg['pad_interact'], False,
+                       log=None if attn_log is None else attn_log['spatial'])
     return xs.reshape(BT, C, H, W)
 
 
-def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None):
+def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None, attn_log=None):
     """UNetModel.forward (unet.py:768-839) on x (B*T, Cin, H, W), timesteps (B*T,)."""
     inp, mid, outp, before_attn = block_plan(cfg)
     emb = F.linear(sinusoid(timesteps, cfg['ch']), sd['time_embed.0.weight'], sd['time_embed.0.bias'])
@@ -227,7 +231,7 @@ def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None):
             elif kind == 'res':
                 h = res_block(sd, p, h, emb, cfg['scale_shift'])
             elif kind == 'attn':
-                h = factorized_attention(sd, p, h, emb, frame_indices, attn_mask, T, cfg)
+                h = factorized_attention(sd, p, h, emb, frame_indices, attn_mask, T, cfg, attn_log)
             elif kind == 'down':
                 h = F.conv2d(h, sd[p + 'op.weight'], sd[p + 'op.bias'], stride=2, padding=1)
             elif kind == 'up':
@@ -258,7 +262,8 @@ def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None):
 
 
 def cond_marg_forward(sd, cfg, x, x0, obs_mask, latent_mask, kinda_marg_mask, timesteps,
-                      frame_indices=None, taps=None, observed_frames='x_0', x_t_minus_1=None, hybrid=None):
+                      frame_indices=None, taps=None, observed_frames='x_0', x_t_minus_1=None, hybrid=None,
+                      attn_log=None):
     """CondMargVideoModel.forward in eval mode (unet.py:949-1026 + 898-912) for cond_emb_type 'channel' (every
     inference-time observed_frames choice), 'duplicate' / 'all' and 't=0'.
     x, x0: (B,F,3,H,W); masks (B,F,1,1,1); timesteps (B,)."""
@@ -293,5 +298,5 @@ def cond_marg_forward(sd, cfg, x, x0, obs_mask, latent_mask, kinda_marg_mask, ti
     if frame_indices is None:
         frame_indices = torch.arange(Fr).view(1, Fr).expand(B, Fr)
     out = unet_forward(sd, cfg, x_in.reshape(B * Fr, x_in.shape[2], H, W), t.reshape(B * Fr),
-                       frame_indices, anything, Fr, taps=taps)
+                       frame_indices, anything, Fr, taps=taps, attn_log=attn_log)
     return out.view(B, Fr, cfg['out_ch'], H, W)

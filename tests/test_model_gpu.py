@@ -133,6 +133,31 @@ def test_cuda_graph_replay_equals_eager(golden):
     assert torch.equal(a, eager) and torch.equal(c, eager) and not torch.equal(b, eager)
 
 
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 2e-4, 2e-6), (torch.bfloat16, 8e-2, 2e-3)],
+                         ids=['fp32', 'bf16'])
+def test_attention_map_logging_matches_reference(golden, dtype, rtol, atol):
+    """return_attn_weights=True returns the reference's {'spatial': [...], 'temporal': [...], 'mixed': []} lists of
+    |head-mean| attention maps (unet.py:464-468, 797-801) and leaves eps unchanged."""
+    g = golden.npz('attn')
+    case = cases.UNET_CASES[1]
+    model, _ = build_model(case['cfg'], golden, dtype)
+    inp = cases.unet_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    with torch.no_grad():
+        plain, none = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+        out, attns = model(inp['x'].cuda(), inp['t_model'].cuda(), return_attn_weights=True, **kw)
+    assert none is None and sorted(attns) == ['mixed', 'spatial', 'temporal'] and attns['mixed'] == []
+    assert max_rel(out.cpu().numpy(), plain.cpu().numpy()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    for key in ('spatial', 'temporal'):
+        assert len(attns[key]) == len([k for k in g.files if k.startswith(f'fwd/{key}/') and k.endswith('/shape')])
+        for i, a in enumerate(attns[key]):
+            assert list(a.shape) == g[f'fwd/{key}/{i}/shape'].tolist()
+            rows = a.sum(dim=-1)                         # every map is a mean of softmax rows
+            assert float((rows - 1).abs().max()) < 1e-4
+            np.testing.assert_allclose(synth.fingerprint(a.cpu(), 256), g[f'fwd/{key}/{i}'], rtol=rtol, atol=atol,
+                                       err_msg=f'{key}/{i}')
+
+
 def test_unsupported_paths_raise(golden):
     from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
     kw = video_model_and_diffusion_defaults()

@@ -70,6 +70,24 @@ def test_per_video_timestep_probe_matches_reference(golden):
         np.testing.assert_allclose(v.numpy(), g[f'probe/{k}'], rtol=1e-5, atol=1e-6, err_msg=k)
 
 
+def test_attention_map_logging_matches_reference(golden):
+    """return_attn_weights=True: per-layer | head-mean | attention maps (unet.py:464-468)."""
+    g = golden.npz('attn')
+    case = cases.UNET_CASES[1]
+    sd = synth.make_state_dict(golden.json('spec_' + case['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(case['cfg']))
+    inp = cases.unet_case_inputs(case)
+    log = {'spatial': [], 'temporal': [], 'mixed': []}
+    with torch.no_grad():
+        U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'], inp['kinda_marg_mask'],
+                            inp['t_model'], inp['frame_indices'], attn_log=log)
+    for key in ('spatial', 'temporal'):
+        assert len(log[key]) == len([k for k in g.files if k.startswith(f'fwd/{key}/') and k.endswith('/shape')])
+        for i, a in enumerate(log[key]):
+            assert list(a.shape) == g[f'fwd/{key}/{i}/shape'].tolist()
+            np.testing.assert_allclose(synth.fingerprint(a, 256), g[f'fwd/{key}/{i}'], rtol=1e-4, atol=1e-6)
+
+
 def golden_file(case):
     return ('unet_lut' if case in cases.UNET_LUT_CASES else
             'unet_variants' if case in cases.UNET_VARIANT_CASES else 'unet')

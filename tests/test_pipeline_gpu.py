@@ -118,6 +118,33 @@ def test_p_sample_loop_matches_reference(golden, replay, dtype, min_psnr, mode):
             diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, model_kwargs=dict(kw, observed_frames='hybrid_500'))
 
 
+def test_p_sample_loop_attention_quartiles_match_reference(golden, replay):
+    """p_sample_loop(return_attn_weights=True): per-quartile averaged maps (gaussian_diffusion.py:496-524)."""
+    from video_diffusion_b200.inference_util import inference_strategies
+    c = cases.CHAIN_CASE
+    g, gl = golden.npz('attn'), golden.npz('p_loop')
+    model, diffusion = build_model(c['cfg'], golden, torch.float32, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    obs, lat = next(iter(inference_strategies[c['mode']](video_length=c['video_length'], num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1).cuda()
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    kw = dict(frame_indices=torch.tensor(obs + lat).repeat(c['batch'], 1).cuda(), x0=x0, obs_mask=om,
+              latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om), observed_frames='x_0')
+    init = synth.make_noise(tuple(x0.shape), seed=c['noise_seed'] + 699).cuda()
+    replay(c['noise_seed'] + 700)
+    out, attns = diffusion.p_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw,
+                                         return_attn_weights=True)
+    assert psnr(out.cpu().numpy(), gl['p_loop/x_0']) >= 55.0
+    tags = sorted(k[len('loop/'):-len('/shape')] for k in g.files if k.startswith('loop/') and k.endswith('/shape'))
+    assert sorted(attns) == tags
+    for tag in tags:
+        assert list(attns[tag].shape) == g[f'loop/{tag}/shape'].tolist()
+        np.testing.assert_allclose(synth.fingerprint(attns[tag].cpu(), 512), g[f'loop/{tag}'], rtol=5e-4, atol=2e-6,
+                                   err_msg=tag)
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
 def test_elbo_within_half_percent(golden, replay, dtype):
     from video_diffusion_b200.sampling import run_bpd_evaluation

@@ -18,7 +18,7 @@ TAB_COUNT = 12
 
 EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
            'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
-           'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
+           'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
            'vdm_prior_bpd']
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -65,6 +65,7 @@ def load():
         'vdm_rpe_hidden': [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
         'vdm_attn_temporal': [_vp] * 5 + [_i32] * 6 + [_vp, _i32, _vp],
         'vdm_attn_spatial': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+        'vdm_attn_weights_mean': [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
         'vdm_rpe_lookup': [_vp, _vp, _i32, _i32, _i32, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp],
         'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
         'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],

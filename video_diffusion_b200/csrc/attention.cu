@@ -280,3 +280,117 @@ extern "C" int vdm_attn_spatial(const void* qkv, int32_t qkv_dtype, int32_t n_im
   VDM_AFTER_LAUNCH("attn_spatial");
   return 0;
 }
+
+// ---- head-averaged attention maps (logging; unet.py:464-468) ------------------------------------------------
+// out[g][i][j] = | mean_h softmax_j( logits_h[i][j] ) | for sequence g = (outer, inner).  One warp per (g, i); lane l
+// owns keys j = l, l + 32, ...  Recomputes the logits from q, k (and the RPE tables / frame mask of the temporal
+// attention) -- only launched when the caller asks for return_attn_weights=True.
+namespace vdm {
+namespace {
+
+constexpr int AW_WARPS = 4, AW_MAXK = 8;   // L <= 32 * AW_MAXK
+
+__device__ __forceinline__ float aw_ld(const float* p) { return *p; }
+__device__ __forceinline__ float aw_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename InT>
+__global__ void __launch_bounds__(AW_WARPS * 32) attn_weights_mean_kernel(
+    const InT* __restrict__ qkv, long long n_seq, int n_inner, long long outer_stride, long long inner_stride,
+    long long seq_stride, int L, int heads, int hd, const float* __restrict__ r_q, const float* __restrict__ r_k,
+    const float* __restrict__ mask, int pad_interact, float* __restrict__ out) {
+  __shared__ float qs[AW_WARPS][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wi = (long long)blockIdx.x * AW_WARPS + warp;
+  if (wi >= n_seq * L) return;
+  const long long g = wi / L;
+  const int i = (int)(wi - g * L);
+  const long long outer = g / n_inner, inner = g - outer * n_inner;
+  const InT* base = qkv + outer * outer_stride + inner * inner_stride;
+  const int C = heads * hd;
+  const float scale = rsqrtf((float)hd);
+  const float mi = mask ? mask[outer * L + i] : 1.f;
+  float acc[AW_MAXK];
+#pragma unroll
+  for (int u = 0; u < AW_MAXK; ++u) acc[u] = 0.f;
+  for (int h = 0; h < heads; ++h) {
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) qs[warp][d] = aw_ld(base + (long long)i * seq_stride + h * hd + d) * scale;
+    __syncwarp();
+    float lg[AW_MAXK];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < AW_MAXK; ++u) {
+      const int j = lane + 32 * u;
+      lg[u] = -INFINITY;
+      if (j < L) {
+        const InT* kj = base + (long long)j * seq_stride + C + h * hd;
+        float dot = 0.f;
+        if (r_k) {
+          // q'.k_j + q'.Rk[b][i][j][h] + (scale k_j).Rq[b][j][i][h]   (unet.py:489-509)
+          const float* rk = r_k + ((outer * L + i) * L + j) * C + h * hd;
+          const float* rq = r_q + ((outer * L + j) * L + i) * C + h * hd;
+          float dq = 0.f;
+          for (int d = 0; d < hd; ++d) {
+            const float kv = aw_ld(kj + d);
+            dot = fmaf(qs[warp][d], kv + rk[d], dot);
+            dq = fmaf(kv, rq[d], dq);
+          }
+          dot = fmaf(dq, scale, dot);
+        } else {
+          for (int d = 0; d < hd; ++d) dot = fmaf(qs[warp][d], aw_ld(kj + d), dot);
+        }
+        bool ok = true;
+        if (mask) {
+          const float mj = mask[outer * L + j];
+          float allowed = mi * mj;
+          if (pad_interact) allowed += (1.f - mi) * (1.f - mj);
+          else if (j == i) allowed = 1.f;
+          ok = allowed != 0.f;
+        }
+        lg[u] = ok ? dot : -INFINITY;
+        mx = fmaxf(mx, lg[u]);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < AW_MAXK; ++u) {
+      lg[u] = (lane + 32 * u < L) ? __expf(lg[u] - mx) : 0.f;
+      sum += lg[u];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int u = 0; u < AW_MAXK; ++u) acc[u] = fmaf(lg[u], inv, acc[u]);
+  }
+  float* o = out + wi * L;
+#pragma unroll
+  for (int u = 0; u < AW_MAXK; ++u)
+    if (lane + 32 * u < L) o[lane + 32 * u] = fabsf(acc[u] / (float)heads);
+}
+
+}  // namespace
+}  // namespace vdm
+
+extern "C" int vdm_attn_weights_mean(const void* qkv, int32_t qkv_dtype, int64_t n_outer, int64_t n_inner,
+                                     int64_t outer_stride, int64_t inner_stride, int64_t seq_stride, int32_t L,
+                                     int32_t heads, int32_t hd, const float* r_q, const float* r_k, const float* mask,
+                                     int32_t allow_pad_interactions, float* out, vdm_stream_t stream) {
+  VDM_REQUIRE(qkv && out && n_outer > 0 && n_inner > 0, "attn_weights_mean: bad arguments");
+  VDM_REQUIRE(L >= 1 && L <= 32 * AW_MAXK, "attn_weights_mean: sequence length %d must be in [1,%d]", L, 32 * AW_MAXK);
+  VDM_REQUIRE(hd >= 1 && hd <= 128, "attn_weights_mean: head_dim=%d must be <= 128", hd);
+  VDM_REQUIRE((r_q == nullptr) == (r_k == nullptr), "attn_weights_mean: r_q and r_k go together");
+  const long long n_seq = (long long)n_outer * n_inner;
+  const long long warps = n_seq * L;
+  const unsigned grid = (unsigned)((warps + AW_WARPS - 1) / AW_WARPS);
+  if (qkv_dtype == VDM_BF16)
+    attn_weights_mean_kernel<__nv_bfloat16><<<grid, AW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)qkv, n_seq, (int)n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, r_q, r_k,
+        mask, allow_pad_interactions, out);
+  else
+    attn_weights_mean_kernel<float><<<grid, AW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)qkv, n_seq, (int)n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, r_q, r_k, mask,
+        allow_pad_interactions, out);
+  VDM_AFTER_LAUNCH("attn_weights_mean");
+  return 0;
+}

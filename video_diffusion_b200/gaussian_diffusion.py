@@ -236,8 +236,6 @@ class GaussianDiffusion:
         chain's initial `noise` when one was given, fresh draws otherwise.  The draw for the training-only x_random
         is kept (and discarded) so a seeded torch generator stays in step with the reference.  Works on a copy of
         model_kwargs: the caller's dict is left untouched, and no `.cuda()` is hard-coded."""
-        if return_attn_weights:
-            raise NotImplementedError('attention-map logging is not supported')
         kw = dict(model_kwargs or {})
         kw.setdefault('observed_frames', 'x_0')
         which = kw['observed_frames']
@@ -258,21 +256,40 @@ class GaussianDiffusion:
                     raise IndexError(f'hybrid threshold {thr} is out of range for {self.num_timesteps} timesteps')
                 kw['hybrid'] = self.q_sample(x0, th.full_like(t, thr), noise=draw())
             return self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                 model_kwargs=kw, use_gradient_method=use_gradient_method)
+                                 model_kwargs=kw, return_attn_weights=return_attn_weights,
+                                 use_gradient_method=use_gradient_method)
 
         return self._loop(step, model, shape, noise, device, progress)
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                       latent_mask=None, device=None, progress=False, return_attn_weights=False,
                       use_gradient_method=False):
-        final = None
-        for final in self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
-                                                    denoised_fn=denoised_fn, model_kwargs=model_kwargs,
-                                                    latent_mask=latent_mask, device=device, progress=progress,
-                                                    return_attn_weights=return_attn_weights,
-                                                    use_gradient_method=use_gradient_method):
-            pass
-        return final['sample'], {}
+        """Returns (sample, attns).  With return_attn_weights the per-layer attention maps are averaged per quartile
+        of the chain under the keys 'attn/q<quartile>-<temporal|spatial>' (gaussian_diffusion.py:496-524): batch-mean
+        over the non-attended axis, spatial maps resized (nearest) to the first layer's size and renormalised."""
+        final, attns = None, {}
+        chain = self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                               denoised_fn=denoised_fn, model_kwargs=model_kwargs,
+                                               latent_mask=latent_mask, device=device, progress=progress,
+                                               return_attn_weights=return_attn_weights,
+                                               use_gradient_method=use_gradient_method)
+        for neg_t, final in enumerate(chain):
+            if not return_attn_weights:
+                continue
+            quartile = (4 * (self.num_timesteps - neg_t - 1)) // self.num_timesteps
+            for key, layers in final['attn'].items():
+                if len(layers) == 0:
+                    continue
+                tag = f'attn/q{quartile}-{key}'
+                largest = layers[0][0].shape
+                for layer in layers:
+                    B = shape[0]
+                    layer = layer.view(B, layer.shape[0] // B, *layer.shape[1:]).mean(dim=1)
+                    if 'temporal' not in key:
+                        resized = th.nn.functional.interpolate(layer.unsqueeze(0), size=largest, mode='nearest').squeeze(0)
+                        layer = resized / resized.mean() * layer.mean()
+                    attns[tag] = attns.get(tag, 0) + layer / (self.num_timesteps / 4)
+        return final['sample'], attns
 
     def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                      model_kwargs=None, latent_mask=None, device=None, progress=False, eta=0.0):

@@ -162,6 +162,14 @@ def attn_spatial(qkv, n_img, L, heads, hd, out):
            flops=4.0 * n_img * heads * L * L * hd, nbytes=_nbytes(qkv, out))
 
 
+def attn_weights_mean(qkv, n_outer, n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, out, r_q=None,
+                      r_k=None, mask=None, pad_interact=True):
+    """Head-averaged attention maps for return_attn_weights=True (logging only)."""
+    _timed('attn_weights_mean', lambda: check(_lib.load().vdm_attn_weights_mean(
+        ptr(qkv), dt(qkv.dtype), n_outer, n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, ptr(r_q),
+        ptr(r_k), ptr(mask), int(pad_interact), ptr(out), stream()), 'vdm_attn_weights_mean'))
+
+
 def sampler_step(mode, x, eps, noise, t, tables, clip_denoised=True, eta=0.0, sample=None, pred_xstart=None,
                  mean=None):
     B = x.shape[0]

@@ -459,7 +459,7 @@ class UNetModel(nn.Module):
                 tables[n['p']] = (bkq[i], bv[i])
         return tables
 
-    def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask, tables=None):
+    def _attention(self, ws, node, x, B, T, H, W, rpe_et, amask, tables=None, attn_log=None):
         P, adt, p, C = self._packed, self.compute_dtype, node['p'], node['C']
         h = x[0]
         HW, heads = H * W, self.num_heads
@@ -522,6 +522,13 @@ class UNetModel(nn.Module):
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
             ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads,
                               hd, att)
+        if attn_log is not None:
+            # logging only (unet.py:464-468): |mean over heads| of the (B*HW, T, T) attention maps, recomputed from
+            # q, k, the RPE tables and the frame mask
+            amap = torch.empty(B * HW, T, T, device=h.device)
+            ops.attn_weights_mean(qkv, B, HW, T * HW * 3 * C, 3 * C, HW * 3 * C, T, heads, hd, amap, r_q=R[0], r_k=R[1],
+                                  mask=amask, pad_interact=self.allow_interactions_between_padding)
+            attn_log['temporal'].append(amap)
         h2 = ws.buf(q + '.out', (M, C))
         st = self._fused_stats(ws, q + '.out', N, HW, C)
         # + NORMALISED x.  The rows of this GEMM are (image, pixel), so the epilogue statistics are
@@ -541,13 +548,17 @@ class UNetModel(nn.Module):
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
         att = ws.buf(q + '.att', (M, C), adt)
         ops.attn_spatial(qkv, N, HW, heads, hd, att)
+        if attn_log is not None:
+            amap = torch.empty(N, HW, HW, device=h.device)
+            ops.attn_weights_mean(qkv, N, 1, HW * 3 * C, 0, 3 * C, HW, heads, hd, amap)
+            attn_log['spatial'].append(amap)
         h3 = ws.buf(q + '.out', (M, C))
         st3 = self._fused_stats(ws, q + '.out', N, HW, C)
         ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h3,
                  stats_out=st3)
         return h3, st3
 
-    def _run(self, ws, T_attn, per_frame_t):
+    def _run(self, ws, T_attn, per_frame_t, attn_log=None):
         """The whole forward as a flat sequence of libvdm launches on the current stream."""
         P, adt = self._packed, self.compute_dtype
         B, F, H, W = ws.B, ws.F, ws.H, ws.W
@@ -601,13 +612,13 @@ class UNetModel(nn.Module):
             with torch.cuda.stream(ws.side):
                 embedding_branch()
                 ws.ev_emb.record(ws.side)
-                if T_attn == F:
+                if T_attn == F and attn_log is None:
                     tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
                 ws.ev_join.record(ws.side)
             ws.emb_join, rpe_join = ws.ev_emb, ws.ev_join
         else:
             embedding_branch()
-            if T_attn == F:
+            if T_attn == F and attn_log is None:        # the logging kernel reads the per-block fp32 tables
                 tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
@@ -651,7 +662,7 @@ class UNetModel(nn.Module):
                 if rpe_join is not None:
                     torch.cuda.current_stream().wait_event(rpe_join)
                     rpe_join = None
-                x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables)
+                x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables, attn_log)
             elif kind == 'down':
                 C = node['C']
                 out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C))
@@ -697,7 +708,8 @@ class UNetModel(nn.Module):
                  out_nchw=True)
         return ws.out
 
-    def _execute(self, x, x0, obs, lat, kinda, t, frame_indices, T_attn, per_frame_t=None, clone=True):
+    def _execute(self, x, x0, obs, lat, kinda, t, frame_indices, T_attn, per_frame_t=None, clone=True,
+                 attn_log=None):
         if self.training:
             raise NotImplementedError('the B200 model is inference-only: call .eval()')
         if not x.is_cuda:
@@ -725,7 +737,9 @@ class UNetModel(nn.Module):
             ws.fi_float.copy_(fi - fi.mean(dim=1, keepdim=True) if self.enforce_position_invariance else fi)
         if per_frame_t is not None:
             ws.t_override.copy_(per_frame_t.reshape(B * F))
-        if self.use_cuda_graph:
+        if attn_log is not None:             # attention-map logging: eager launches, per-block RPE tables
+            out = self._run(ws, T_attn, per_frame_t is not None, attn_log)
+        elif self.use_cuda_graph:
             if ws.graph is None:
                 self._run(ws, T_attn, per_frame_t is not None)           # warm-up: allocates every buffer
                 torch.cuda.synchronize()
@@ -755,8 +769,7 @@ class UNetVideoModel(UNetModel):
 
     def forward(self, x, timesteps, frame_indices=None, attn_mask=None, return_attn_weights=False, **kwargs):
         """Unconditioned video forward (unet.py:898-912): timesteps holds one value per frame."""
-        if return_attn_weights:
-            raise NotImplementedError('return_attn_weights=True')
+        attn_log = {'spatial': [], 'temporal': [], 'mixed': []} if return_attn_weights else None   # unet.py:797-801
         B, F = x.shape[:2]
         if frame_indices is None:
             frame_indices = torch.arange(F, device=x.device).view(1, F).expand(B, F)
@@ -765,8 +778,8 @@ class UNetVideoModel(UNetModel):
         mask = ones if attn_mask is None else attn_mask.reshape(B, F).float()
         # latent everywhere -> the conditioning mix is the identity; attention mask = given mask
         out = self._execute(x, x, zeros, mask, zeros, timesteps.reshape(-1)[:B].float(), frame_indices, F,
-                            per_frame_t=timesteps.reshape(B * F).float())
-        return out, None
+                            per_frame_t=timesteps.reshape(B * F).float(), attn_log=attn_log)
+        return out, attn_log
 
 
 class CondMargVideoModel(UNetVideoModel):
@@ -797,8 +810,7 @@ class CondMargVideoModel(UNetVideoModel):
         model(x, timesteps=t, **model_kwargs) (respace.py:119)."""
         if timesteps is None:
             raise TypeError('timesteps is required')
-        if return_attn_weights:
-            raise NotImplementedError('return_attn_weights=True')
+        attn_log = {'spatial': [], 'temporal': [], 'mixed': []} if return_attn_weights else None   # unet.py:797-801
         B, F = x.shape[:2]
         if frame_indices is None:
             frame_indices = torch.arange(F, device=x.device).view(1, F).expand(B, F)
@@ -832,8 +844,8 @@ class CondMargVideoModel(UNetVideoModel):
             any_obs = (obs_mask.reshape(B, F) == 1).any(dim=1)
             per_frame_t = torch.where(any_obs, torch.full_like(t, -1.0), t).view(B, 1).expand(B, F).contiguous()
         out = self._execute(x, observed, obs_mask, latent_mask, kinda_marg_mask, t, frame_indices, F,
-                            per_frame_t=per_frame_t)
-        return out, None
+                            per_frame_t=per_frame_t, attn_log=attn_log)
+        return out, attn_log
 
     def __call__(self, x, *args, **kwargs):
         # model(x, t, x0=..., ...) : map the positional timestep onto the keyword
