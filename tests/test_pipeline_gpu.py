@@ -67,6 +67,24 @@ def test_infer_video_independent_ddim10_matches_reference(golden, replay, dtype,
         assert np.abs(samples - ref).max() < tol
 
 
+def test_infer_video_save_all_timesteps(golden, replay):
+    """args.save_all_timesteps of scripts/video_sample.py:84-89,169-189: every chain state of every window."""
+    from video_diffusion_b200.sampling import infer_video
+    c = cases.CHAIN_CASE
+    g = golden.npz('chain')
+    model, diffusion = build_model(c['cfg'], golden, torch.float32, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    replay(c['noise_seed'])
+    samples, every = infer_video(c['mode'], model, diffusion, video, c['max_frames'], c['obs_length'], c['step_size'],
+                                 save_all_timesteps=True)
+    assert every.shape == (c['batch'], diffusion.num_timesteps, *video.shape[1:])
+    assert np.abs(samples - g['chain/samples']).max() < 2e-3
+    np.testing.assert_array_equal(every[:, -1], samples)                 # the last chain state is the sample
+    for k in range(diffusion.num_timesteps):                             # observed prefix at every timestep
+        np.testing.assert_array_equal(every[:, k, :c['obs_length']], video[:, :c['obs_length']].numpy())
+    assert np.abs(every[:, 0] - every[:, -1]).max() > 1e-2               # earlier states differ
+
+
 @pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 30.0)], ids=['fp32', 'bf16'])
 def test_ddim_sample_loop_matches_reference(golden, replay, dtype, min_psnr):
     from video_diffusion_b200.inference_util import inference_strategies

@@ -26,9 +26,12 @@ def get_masks(x0, num_obs):
 
 @torch.no_grad()
 def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size=1, optimal_schedule_path=None, *,
-                use_gradient_method=False, observed_frames='x_0', device=None, return_tensor=False):
-    """batch: (B, T, C, H, W) in [-1, 1].  Returns the sampled videos as a numpy array (and a dummy
-    `all_timestep_samples`, like the reference with save_all_timesteps off)."""
+                use_gradient_method=False, observed_frames='x_0', device=None, return_tensor=False,
+                save_all_timesteps=False):
+    """batch: (B, T, C, H, W) in [-1, 1].  Returns (samples, all_timestep_samples) as numpy arrays like
+    scripts/video_sample.py:50-190; `observed_frames` and `save_all_timesteps` are script globals (`args.*`) there and
+    keyword arguments here.  all_timestep_samples is (B, num_timesteps, T, C, H, W) in chain order with
+    save_all_timesteps, zeros([1]) otherwise.  Everything stays on the device until the final copy."""
     if use_gradient_method:
         raise NotImplementedError('use_gradient_method needs autograd through the network')
     if 'adaptive' in mode or 'goal-directed' in mode:
@@ -41,6 +44,10 @@ def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size
     schedule = iter(inference_strategies[mode](video_length=T, num_obs=obs_length, max_frames=max_frames,
                                                step_size=step_size, optimal_schedule_path=optimal_schedule_path))
     steps = list(range(diffusion.num_timesteps))[::-1]
+    all_steps = None
+    if save_all_timesteps:                                      # scripts/video_sample.py:84-89
+        all_steps = torch.zeros(B, len(steps), *video.shape[1:], device=device)
+        all_steps[:, :, :obs_length] = samples[:, :obs_length].unsqueeze(1)
     t_all = torch.arange(diffusion.num_timesteps, device=device).view(-1, 1).expand(-1, B).contiguous()
     for obs_idx, lat_idx in schedule:
         idx = torch.tensor(list(obs_idx) + list(lat_idx), device=device, dtype=torch.long)
@@ -50,14 +57,16 @@ def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size
         kwargs = dict(frame_indices=frame_indices, x0=x0, obs_mask=obs_mask, latent_mask=latent_mask,
                       kinda_marg_mask=kinda_marg_mask, x_t_minus_1=x0, observed_frames=observed_frames)
         local = x0.clone()
-        for step in steps:
+        n_lat = len(lat_idx)
+        for k, step in enumerate(steps):
             local = diffusion.p_sample(model, local, t=t_all[step], clip_denoised=True, model_kwargs=kwargs,
                                        return_attn_weights=False)['sample']
-        n_lat = len(lat_idx)
+            if all_steps is not None:
+                all_steps[:, k, idx[-n_lat:]] = local[:, -n_lat:]
         samples[:, idx[-n_lat:]] = local[:, -n_lat:]
     if return_tensor:
-        return samples
-    return samples.cpu().numpy(), np.zeros([1], dtype=np.float32)
+        return samples if all_steps is None else (samples, all_steps)
+    return samples.cpu().numpy(), (np.zeros([1], dtype=np.float32) if all_steps is None else all_steps.cpu().numpy())
 
 
 def to_uint8(samples):
