@@ -13,12 +13,15 @@ kernel, i.e. B*F = 160 frames denoised once.  Prints ONE JSON line (see the task
   roofline: tensor-core roofline of the dominant kernel class (gemm_tc: every conv / linear),
            per-launch CUDA-event times gathered live in a separate eager profiling pass,
   cpu_baseline: the CPU oracle port of the reference path timed on this box's host cores.
+  stock_gpu_baseline (only with --stock-gpu-baseline): the same forward through PyTorch eager cuDNN / cuBLAS kernels on
+           this GPU (TF32 and bf16 autocast) -- the stock-library figure of SURVEY 8(d), reported next to the value.
 `--impl reference` times that CPU path alone (the reference is pure PyTorch; it cannot travel to
 the GPU box, so its restatement in oracle/ stands in -- kind "port").
 Multi-GPU: one process per GPU (torchrun), the batch of videos is sharded, no collective on the
 data path (weak scaling); timing is the max over ranks.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -123,6 +126,45 @@ def cpu_port_step(sd, batch, threads):
     return step
 
 
+def stock_gpu_baseline(sd, batch, steps=5):
+    """The same U-Net forward through stock PyTorch eager kernels (cuDNN / cuBLAS) on this GPU: the oracle's functional
+    restatement moved to cuda:0, in the reference's own TF32 setting (scripts/video_sample.py:21-22) and under bf16
+    autocast.  A reported baseline ("the stock-library kernel to beat"), opt-in, never on the product path."""
+    from oracle import cases, diffusion_oracle as D, unet_oracle as U
+    cfg = U.model_config(**cases.ref_config(CFG))
+    sched = D.Schedule(1000, 'linear', '')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    w = {k: v.to(dev) for k, v in window_inputs(batch, seed=2).items()}
+    x = w['x0'].clone()
+    t = sched.model_time(torch.full((batch,), 500, dtype=torch.long)).to(dev)
+    out = {}
+    saved = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    try:
+        for name, ctx in (('tf32', contextlib.nullcontext()), ('bf16_autocast', torch.autocast('cuda', torch.bfloat16))):
+            def fwd():
+                with torch.no_grad(), ctx:
+                    return U.cond_marg_forward(sdg, cfg, x, w['x0'], w['obs_mask'], w['latent_mask'],
+                                               w['kinda_marg_mask'], t, w['frame_indices'])
+            for _ in range(2):
+                fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'ms_per_forward': ms, 'frames_per_s': batch * FRAMES / ms * 1e3}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    out['what'] = (f'torch {torch.__version__} eager (cuDNN/cuBLAS) U-Net forward of the oracle restatement on the GPU, '
+                   f'({batch},{FRAMES},3,{SIZE},{SIZE}) window, mean of {steps} after 2 warm-ups, CUDA events; forward only')
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -157,6 +199,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stock-gpu-baseline', action='store_true',
+                    help='also time the stock PyTorch eager (cuDNN/cuBLAS) forward on this GPU (reported baseline)')
     ap.add_argument('--profile-json', default=None, help='write the per-kernel-class breakdown here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -322,6 +366,8 @@ def main():
         result['cpu_baseline'] = {'value': FRAMES / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                   'sample': f'oracle port of the reference CPU path: U-Net forward + p_sample on one '
                                             f'(1,{FRAMES},3,{SIZE},{SIZE}) window (batch 1 of 8), mean of {n} after 1 warm-up'}
+    if rank == 0 and world == 1 and args.stock_gpu_baseline:
+        result['stock_gpu_baseline'] = stock_gpu_baseline(sd, B)
     if rank == 0:
         if args.profile_json:
             with open(args.profile_json, 'w') as f:
