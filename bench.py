@@ -40,6 +40,9 @@ N_OBS = 13                       # autoreg, step_size 7: 13 observed + 7 latent 
 FLOP_PER_FRAME = 63.40e9         # 10.144 TFLOP per (8 x 20)-frame forward
 GEMM_FLOP_SHARE = (9238.5 + 234.9 + 555.7) / 10144.0   # conv + addmm + mm share of it (the gemm_tc launches)
 METRIC = 'denoised video frames/sec (U-Net fwd, bf16)'
+WORKLOAD = ('C2: MineRL-sized FDM U-Net 64x64 (ch 128, mult 1-2-3-4, 2 res blocks, 4 heads, '
+            'attention at 16x16 and 8x8), max_frames=20, autoreg window 13 obs + 7 latent, '
+            'one ancestral p_sample step per step')
 
 
 def peaks():
@@ -202,7 +205,17 @@ def main():
     ap.add_argument('--stock-gpu-baseline', action='store_true',
                     help='also time the stock PyTorch eager (cuDNN/cuBLAS) forward on this GPU (reported baseline)')
     ap.add_argument('--profile-json', default=None, help='write the per-kernel-class breakdown here')
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c4'],
+                    help="c2 (default) is the configuration BASELINE.json's metric is quoted on; c4 = the 128x128 model")
     args = ap.parse_args()
+    if args.workload == 'c4':
+        # BASELINE.json configs[3]: 128x128, channel_mult (1,1,2,3,4), 2 res blocks; SURVEY 8(d): 21.713 TFLOP per
+        # (8 x 20)-frame forward, conv 95.8 %, the attention-level linears as in C2
+        global CFG, SIZE, FLOP_PER_FRAME, GEMM_FLOP_SHARE, WORKLOAD
+        CFG, SIZE, FLOP_PER_FRAME = 'c4', 128, 135.70e9
+        GEMM_FLOP_SHARE = (0.958 * 21713.0 + 234.9 + 555.7) / 21713.0
+        WORKLOAD = ('C4: 128x128 FDM U-Net (ch 128, mult 1-1-2-3-4, 2 res blocks, 4 heads, attention at 16x16 and 8x8), '
+                    'max_frames=20, autoreg window 13 obs + 7 latent, one ancestral p_sample step per step')
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         return run_reference(args)
@@ -320,9 +333,7 @@ def main():
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'C2: MineRL-sized FDM U-Net 64x64 (ch 128, mult 1-2-3-4, 2 res blocks, 4 heads, '
-                               'attention at 16x16 and 8x8), max_frames=20, autoreg window 13 obs + 7 latent, '
-                               'one ancestral p_sample step per step',
+        'config': {'workload': WORKLOAD,
                    'batch_per_gpu': B, 'frames_per_step_per_gpu': B * FRAMES, 'parallelism': f'dp{world} (videos sharded)',
                    'weights': 'random, de-zeroed (oracle/synth.py seed 1)', 'timestep_respacing': '',
                    'l2': 'no explicit flush: activations touched per step (several GB) exceed the 126 MB L2',

@@ -119,6 +119,9 @@ HALO_CASES = [
     (12, 8, 8, 128, 256, 0, True),       # 8x8: two images per 128-row tile, rows interleaved (y, image, x)
     (7, 8, 8, 64, 512, 128, False),      # 8x8, odd image count, fused skip operand
     (4, 8, 8, 192, 256, 0, False),
+    (3, 128, 128, 128, 128, 0, True),    # 128-pixel-wide images: wide-slot transposed kernel, ragged pair (odd count)
+    (2, 128, 128, 64, 128, 128, False),  # ... with the fused 1x1 skip operand
+    (1, 32, 128, 64, 256, 0, False),     # ... non-square, 256 output channels
 ]
 
 

@@ -1289,10 +1289,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(con
 // The accumulator comes out transposed -- TMEM lane = output channel, column = pixel -- which makes the epilogue
 // simple: a warp's 32 lanes are 32 consecutive channels of one pixel (one coalesced 128-byte store, no staging
 // through shared memory) and the GroupNorm statistics are plain per-lane running sums.
-template <int SA, int SB>
+template <int SA, int SB, bool WIDE = false>
 struct HaloTLayout {
   static constexpr int PIX = 256;                                   // pixels per CTA tile = MMA N
-  static constexpr int A_SLOT = (PIX / BLOCK_M + 1) * BLOCK_M * BLOCK_K * 2;   // (R + 2) * W <= 384 pixel rows, W <= 64
+  // (R + 2) * W pixel rows: <= 384 for W <= 64; the WIDE variant holds the 4 x 128 rows of a 128-pixel-wide image
+  static constexpr int A_SLOT = (PIX / BLOCK_M + (WIDE ? 2 : 1)) * BLOCK_M * BLOCK_K * 2;
   static constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;              // 128 output channels x 64 k
   static constexpr int W_OFFSET = SA * A_SLOT;
   static constexpr int BAR_OFFSET = W_OFFSET + SB * W_BYTES;
@@ -1300,12 +1301,12 @@ struct HaloTLayout {
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int SA, int SB, int EPI>
+template <int SA, int SB, int EPI, bool WIDE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo,
                                                                         const __grid_constant__ CUtensorMap tm_a2,
                                                                         const __grid_constant__ CUtensorMap tm_w,
                                                                         const TcParams p) {
-  using L = HaloTLayout<SA, SB>;
+  using L = HaloTLayout<SA, SB, WIDE>;
   constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
   const uint32_t cta_rank = cluster_ctarank();
@@ -1793,14 +1794,14 @@ int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcPar
   return launch_upfold_halo_inst<SA, SB, 8>(mh, mw, p, stream);
 }
 
-template <int SA, int SB, int EPI>
+template <int SA, int SB, int EPI, bool WIDE>
 int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                        cudaStream_t stream) {
-  using L = HaloTLayout<SA, SB>;
+  using L = HaloTLayout<SA, SB, WIDE>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (transposed halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1822,7 +1823,7 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI>, mh, ma2, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (transposed halo): launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1831,18 +1832,18 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
   return 0;
 }
 
-template <int SA, int SB>
+template <int SA, int SB, bool WIDE = false>
 int launch_halo_t(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                   cudaStream_t stream) {
   switch (epilogue_variant(p, 128)) {
-    case 0: return launch_halo_t_inst<SA, SB, 0>(mh, ma2, mw, p, stream);
-    case 1: return launch_halo_t_inst<SA, SB, 1>(mh, ma2, mw, p, stream);
-    case 2: return launch_halo_t_inst<SA, SB, 2>(mh, ma2, mw, p, stream);
-    case 3: return launch_halo_t_inst<SA, SB, 3>(mh, ma2, mw, p, stream);
-    case 4: return launch_halo_t_inst<SA, SB, 4>(mh, ma2, mw, p, stream);
-    case 5: return launch_halo_t_inst<SA, SB, 5>(mh, ma2, mw, p, stream);
-    case 6: return launch_halo_t_inst<SA, SB, 6>(mh, ma2, mw, p, stream);
-    default: return launch_halo_t_inst<SA, SB, 7>(mh, ma2, mw, p, stream);
+    case 0: return launch_halo_t_inst<SA, SB, 0, WIDE>(mh, ma2, mw, p, stream);
+    case 1: return launch_halo_t_inst<SA, SB, 1, WIDE>(mh, ma2, mw, p, stream);
+    case 2: return launch_halo_t_inst<SA, SB, 2, WIDE>(mh, ma2, mw, p, stream);
+    case 3: return launch_halo_t_inst<SA, SB, 3, WIDE>(mh, ma2, mw, p, stream);
+    case 4: return launch_halo_t_inst<SA, SB, 4, WIDE>(mh, ma2, mw, p, stream);
+    case 5: return launch_halo_t_inst<SA, SB, 5, WIDE>(mh, ma2, mw, p, stream);
+    case 6: return launch_halo_t_inst<SA, SB, 6, WIDE>(mh, ma2, mw, p, stream);
+    default: return launch_halo_t_inst<SA, SB, 7, WIDE>(mh, ma2, mw, p, stream);
   }
 }
 
@@ -1981,6 +1982,26 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
     const bool ok = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
                     bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
+    // 128-pixel-wide images (the top level of the 128x128 model): a 256-pixel tile is two image rows, the slot holds
+    // four -> the transposed-role kernel with 64 KB slots (two of them) for every N % 128 == 0
+    const bool okw = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
+                     a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 && epilogue_variant(p, 128) < 8 &&
+                     (hmode == 2 || ((M + 511) / 512) * (a->N / 128) >= 40);
+    if (okw) {
+      CUtensorMap mh, mwt;
+      const uint64_t C = a->C1;
+      uint64_t dims[5] = {C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->n_img};
+      uint64_t st[5] = {2, C * 2, C * 2 * a->W, C * 2 * a->W * a->H, C * 2 * a->W * a->H};
+      uint32_t box[5] = {BLOCK_K, (uint32_t)a->W, 4, 1, 1};
+      rc = encode_map(&mh, a->a1, 5, dims, st, box);
+      if (rc) return rc;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      uint32_t wbox[2] = {BLOCK_K, 64};
+      rc = encode_map(&mwt, a->w, 2, wdims, wst, wbox);
+      if (rc) return rc;
+      return launch_halo_t<2, 6, true>(mh, ma2, mwt, p, stream);
+    }
     // transposed-role kernel: weights as the M operand (128-channel tiles), 256 pixels as N
     const char* et = getenv("VDM_GEMM_HALO_T");
     // measured per level: faster than the pair tiles for 128 and 384 output channels (where those are 128 / 192
