@@ -241,7 +241,7 @@ def test_linear_rowbias_nchw_and_silu(dtype):
     assert relerr(out, ref) < 2e-5
 
 
-@pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3),
+@pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3), (2, 128, 128, 128, 3), (1, 6, 128, 64, 6),
                                        (4, 8, 8, 64, 3)])
 def test_output_head_conv_small_n(n, H, W, C1, N, monkeypatch):
     """C -> 3 / 6 channel 3x3 conv with a planar (NCHW) store: the halo-tile mma.sync kernel and, for shapes it does

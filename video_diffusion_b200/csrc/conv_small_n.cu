@@ -22,16 +22,22 @@ __device__ __forceinline__ void cp16_zfill(void* smem, const void* gmem, bool va
 
 __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat16* __restrict__ x,   // [n_img][H][W][C]
                                                                const __nv_bfloat16* __restrict__ w,   // [N][9*C]
-                                                               const float* __restrict__ bias, int H, int W, int C,
-                                                               int N, float* __restrict__ out /* [n_img][N][H*W] */) {
+                                                               const float* __restrict__ bias, int H, int W, int TW,
+                                                               int C, int N,
+                                                               float* __restrict__ out /* [n_img][N][H*W] */) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int R = TILE_PIX / W;                 // image rows per tile
-  const int Wp = W + 2, Cp = C + PAD;
+  // tile = R image rows x TW columns (TW = W up to 64 pixels; wider images are split into column strips so the halo
+  // tile stays small enough for three CTAs per SM)
+  const int R = TILE_PIX / TW;
+  const int Wp = TW + 2, Cp = C + PAD;
   __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem);                 // [(R+2)][Wp][Cp]
   __nv_bfloat16* wsm = halo + (size_t)(R + 2) * Wp * Cp;                        // [9][8][Cp]
+  const int strips = W / TW;
   const int tiles_per_img = H * W / TILE_PIX;
   const int img = blockIdx.x / tiles_per_img;
-  const int y0 = (blockIdx.x - img * tiles_per_img) * R;
+  const int t_in_img = blockIdx.x - img * tiles_per_img;
+  const int y0 = (t_in_img / strips) * R;
+  const int x0 = (t_in_img % strips) * TW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C8 = C / 8;
 
@@ -44,7 +50,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
     int c8 = tid % C8, pix = tid / C8;
     int hy = pix / Wp, hx = pix % Wp;
     for (int i = tid; i < total; i += blockDim.x) {
-      const int xx = hx - 1, yy = y0 + hy - 1;
+      const int xx = x0 + hx - 1, yy = y0 + hy - 1;
       const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
       cp16_zfill(halo + (size_t)pix * Cp + c8 * 8, ok ? ximg + ((size_t)yy * W + xx) * C + c8 * 8 : ximg, ok);
       c8 += step_c8; pix += step_pix; hx += step_x; hy += step_y;
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
 
   // ---- warp = 16 consecutive pixels of one image row
   const int p0 = warp * 16;
-  const int ry = p0 / W, rx = p0 - ry * W;
+  const int ry = p0 / TW, rx = p0 - ry * TW;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two chains: even / odd k-steps
   const int a_row = lane & 15, a_k = (lane >> 4) * 8;       // ldmatrix.x4 row / k-half supplied by this lane
   const int b_n = lane >> 2, b_k = (lane & 3) * 2;
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
   for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
   // accumulator layout: acc[0,1] = (row lane/4, cols 2*(lane%4) + {0,1}); acc[2,3] = row + 8
   const int HW = H * W;
-  const int pix = (y0 + ry) * W + rx + (lane >> 2);
+  const int pix = (y0 + ry) * W + x0 + rx + (lane >> 2);
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int n = (lane & 3) * 2 + e;
@@ -119,12 +125,13 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
 // GEMM), 0 on success.
 int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   const int W = a->W, H = a->H, C = a->C1, N = a->N;
+  const int TW = W > 64 ? 64 : W;             // column strips for wide images
   if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 32 == 0 && W >= 16 &&
-        W <= TILE_PIX && TILE_PIX % W == 0 && (H * W) % TILE_PIX == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
+        W % TW == 0 && TILE_PIX % TW == 0 && H % (TILE_PIX / TW) == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
         !a->rowbias && !a->stats_out))
     return -100;
-  const int R = TILE_PIX / W;
-  const size_t smem = ((size_t)(R + 2) * (W + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16);
+  const int R = TILE_PIX / TW;
+  const size_t smem = ((size_t)(R + 2) * (TW + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16);
   if (smem > 200 * 1024) return -100;
   static size_t configured = 0;
   if (smem > configured) {
@@ -137,7 +144,7 @@ int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   }
   const int grid = a->n_img * (H * W / TILE_PIX);
   conv3x3_small_n_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->a1),
-                                                     reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, C, N,
+                                                     reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW, C, N,
                                                      a->out_f32);
   VDM_AFTER_LAUNCH("conv3x3_small_n");
   return 0;
