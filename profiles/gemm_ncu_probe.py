@@ -13,6 +13,7 @@ dev = 'cuda'
 N_IMG = 160
 for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_256_128', 64, 64, 256, 128, 9, False, True),
                                                      ('conv64_128_128_res', 64, 64, 128, 128, 9, True, False),
+                                                     ('conv128_256_128 (C4 top level, wide-slot kernel)', 128, 128, 256, 128, 9, False, True),
                                                      ('conv32_256_256', 32, 32, 256, 256, 9, False, True),
                                                      ('conv16_384_384', 16, 16, 384, 384, 9, True, False),
                                                      ('conv8_512_512', 8, 8, 512, 512, 9, True, False),
