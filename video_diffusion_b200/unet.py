@@ -61,6 +61,8 @@ class UNetModel(nn.Module):
             raise NotImplementedError('num_heads_upsample != num_heads')
         self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
         self._cond_mode = 2          # input-mix mode of vdm_cond_mix: plain 3-channel frames unless a subclass says otherwise
+        self.use_frame_encoding = getattr(self, 'use_frame_encoding', False)      # set by UNetVideoModel before this ctor
+        self.enforce_position_invariance = getattr(self, 'enforce_position_invariance', False)
         self.num_res_blocks, self.attention_resolutions = num_res_blocks, tuple(attention_resolutions)
         self.dropout, self.channel_mult, self.num_heads = dropout, tuple(channel_mult), num_heads
         self.use_scale_shift_norm, self.image_size = use_scale_shift_norm, image_size
@@ -630,7 +632,7 @@ class UNetModel(nn.Module):
             if in_groups:
                 hs.append(x)
                 n_groups_done += 1
-                frame_enc = getattr(self, 'use_frame_encoding', False)
+                frame_enc = self.use_frame_encoding
                 if n_groups_done == self.n_blocks_before_attn and ('enc' in P or frame_enc):
                     hn = ws.buf('h_enc', tuple(x[0].shape))
                     femb = None
@@ -732,7 +734,7 @@ class UNetModel(nn.Module):
         ws.kinda.copy_(kinda.reshape(B, F))
         ws.t.copy_(t.reshape(B))
         ws.fi.copy_(frame_indices.reshape(B, F))
-        if getattr(self, 'use_frame_encoding', False):
+        if self.use_frame_encoding:
             fi = frame_indices.reshape(B, F).float()
             ws.fi_float.copy_(fi - fi.mean(dim=1, keepdim=True) if self.enforce_position_invariance else fi)
         if per_frame_t is not None:
