@@ -78,6 +78,25 @@ def test_zero_init_modules_like_reference():
     assert float(sd['input_blocks.1.0.in_layers.2.weight'].abs().sum()) > 0
 
 
+def test_cond_emb_type_constructors_like_reference():
+    """unet.py:932-947: input widths and the `-initzero` initialisations of the conditioning variants."""
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config('tiny'))
+    want = {'channel': (5, 0), 'channel-initzero': (5, 0), 'duplicate': (6, 1), 'duplicate-initzero': (6, 1),
+            'all': (6, 1), 'all-initzero': (6, 1), 't=0': (3, 2)}
+    for name, (cin, mode) in want.items():
+        model, _ = create_video_model_and_diffusion(**dict(kw, cond_emb_type=name))
+        w = model.state_dict()['input_blocks.0.0.weight']
+        assert w.shape[1] == cin and model._cond_mode == mode and model.cond_emb_type == name.replace('-initzero', '')
+        if name == 'channel-initzero':
+            assert float(w[:, 3].abs().sum()) == 0 and float(w[:, 4].abs().sum()) > 0
+        if name in ('duplicate-initzero', 'all-initzero'):
+            assert torch.equal(w[:, 3:], w[:, :3])
+    with pytest.raises(NotImplementedError):
+        create_video_model_and_diffusion(**dict(kw, cond_emb_type='concat'))
+
+
 def test_c_abi_exports_every_declared_symbol():
     from video_diffusion_b200 import _lib
     header = open(os.path.join(ROOT, 'include', 'vdm.h')).read()
