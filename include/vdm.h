@@ -229,13 +229,22 @@ int vdm_attn_spatial(const void* qkv, int32_t qkv_dtype, int32_t n_img, int32_t 
 
 /* ---- sampler step (gaussian_diffusion.py:326-343, 374-382, 208-227, 438-443, 597-634) ----
  * tables: [VDM_TAB_COUNT][n_steps] fp32 (see enum), t: [B] int64 indices into the tables.
- * mode 0: ancestral p_sample; mode 1: DDIM with eta.  Elementwise over B*per_batch. */
+ * mode 0: ancestral p_sample; mode 1: DDIM with eta; mode 2: DDIM reverse ODE step x_t -> x_{t+1}
+ * (:636-668, eta must be 0, noise unused).  Elementwise over B*per_batch.
+ * A timestep outside [0, n_steps) (the reference's numpy table lookup raises IndexError there) is clamped,
+ * so nothing is read out of bounds, and recorded: vdm_sampler_error() returns 1 once and clears the record. */
 enum {
   VDM_TAB_SQRT_RECIP_ACP = 0, VDM_TAB_SQRT_RECIPM1_ACP, VDM_TAB_POST_C1, VDM_TAB_POST_C2,
   VDM_TAB_MODEL_LOGVAR, VDM_TAB_MODEL_VAR, VDM_TAB_ACP, VDM_TAB_ACP_PREV, VDM_TAB_POST_LOGVAR,
-  VDM_TAB_SQRT_ACP, VDM_TAB_SQRT_1M_ACP, VDM_TAB_LOG_1M_ACP, VDM_TAB_COUNT
+  VDM_TAB_SQRT_ACP, VDM_TAB_SQRT_1M_ACP, VDM_TAB_LOG_1M_ACP,
+  VDM_TAB_POST_VAR,        /* posterior_variance (gaussian_diffusion.py:161-162) */
+  VDM_TAB_RECIP_POST_C1,   /* 1 / posterior_mean_coef1 (:386) */
+  VDM_TAB_POST_C2_DIV_C1,  /* posterior_mean_coef2 / posterior_mean_coef1 (:387-389) */
+  VDM_TAB_ACP_NEXT,        /* alphas_cumprod_next (:149, DDIM reverse ODE :658) */
+  VDM_TAB_COUNT
 };
 
+int vdm_sampler_error(void);
 int vdm_sampler_step(int32_t mode, const float* x, const float* eps, const float* noise,
                      const int64_t* t, const float* tables, int32_t n_steps, int32_t B,
                      int64_t per_batch, int32_t clip_denoised, float eta, float* sample,
@@ -244,6 +253,16 @@ int vdm_sampler_step(int32_t mode, const float* x, const float* eps, const float
 /* q_sample (gaussian_diffusion.py:190-206): out = sqrt_acp[t]*x0 + sqrt_1m_acp[t]*noise */
 int vdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables,
                  int32_t n_steps, int32_t B, int64_t per_batch, float* out, vdm_stream_t stream);
+
+/* Per-row linear combinations of the posterior / prediction helpers (gaussian_diffusion.py:148-157,
+ * 208-227, 374-396), coefficients gathered from table rows by t[b]:
+ *   op 0: out = tab[row_a]*a + tab[row_b]*b      q_posterior_mean_variance (POST_C1, POST_C2)
+ *   op 1: out = tab[row_a]*a - tab[row_b]*b      _predict_xstart_from_eps / _from_xprev
+ *   op 2: out = (tab[row_a]*a - b) / tab[row_b]  _predict_eps_from_xstart
+ *   op 3: out = tab[row_a]*a                     q_mean_variance (b unused) */
+int vdm_lincomb(int32_t op, const float* a, const float* b, const int64_t* t, const float* tables,
+                int32_t n_steps, int32_t row_a, int32_t row_b, int32_t B, int64_t per_batch, float* out,
+                vdm_stream_t stream);
 
 /* ---- ELBO terms (gaussian_diffusion.py:750-788, 970-988; losses.py:12-70; nn.py:73-77) ----
  * acc[b][0..2] += (vb term in bits, xstart_mse, eps_mse), each already divided by the FULL

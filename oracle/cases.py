@@ -24,6 +24,11 @@ _CFG = {
 }
 
 
+# the unconditioned entry point (UNetVideoModel.forward, unet.py:898-912): built directly, because the reference's
+# create_video_model(do_cond_marg=False) passes cond_emb_type to a constructor that does not take it
+_CFG['tiny_uncond'] = dict(image_size=32, num_channels=64, num_res_blocks=1, T=30, do_cond_marg=False)
+
+
 def ref_config(name):
     c = dict(_CFG[name])
     for k in ('rp_alpha', 'rp_beta', 'rp_gamma'):
@@ -74,6 +79,49 @@ UNET_VARIANT_CASES = [
     dict(name='obs_xtm1', cfg='tiny', observed='x_t_minus_1', **_RAGGED),
     dict(name='obs_hybrid500', cfg='tiny', observed='hybrid_500', **_RAGGED),
 ]
+
+
+# the benchmarked architectures at their real sizes, one video each: the reference itself runs these on the CPU in
+# seconds, so its eps and per-block fingerprints pin the full-size kernels (tests/golden/unet_full.npz)
+FULL_CASES = [
+    dict(name='c2_full', cfg='c2', B=1, F=20, n_obs=[7], n_lat=[12], t=[411.0]),     # one trailing padding frame
+    dict(name='c4_full', cfg='c4', B=1, F=4, n_obs=[1], n_lat=[3], t=[37.0]),
+]
+
+
+def full_case_inputs(case):
+    B, F = case['B'], case['F']
+    size = _CFG[case['cfg']]['image_size']
+    x0 = synth.make_video((B, F, 3, size, size), seed=41)
+    x = synth.make_noise((B, F, 3, size, size), seed=42)
+    obs = torch.zeros(B, F, 1, 1, 1)
+    lat = torch.zeros(B, F, 1, 1, 1)
+    for b in range(B):
+        obs[b, :case['n_obs'][b]] = 1
+        lat[b, case['n_obs'][b]:case['n_obs'][b] + case['n_lat'][b]] = 1
+    fi = torch.stack([torch.randperm(200, generator=torch.Generator().manual_seed(7 + b))[:F] for b in range(B)])
+    return dict(x=x, x0=x0, obs_mask=obs, latent_mask=lat, kinda_marg_mask=torch.zeros_like(obs), frame_indices=fi,
+                t_model=torch.tensor(case['t'], dtype=torch.float32))
+
+
+# UNetVideoModel.forward: per-frame timesteps (B, F), an attention mask with padding frames, no conditioning
+UNCOND_CASE = dict(name='uncond_ragged', cfg='tiny_uncond', B=2, F=8, n_valid=[8, 6],
+                   frame_indices=[[0, 1, 2, 3, 4, 5, 6, 7], [3, 7, 9, 11, 12, 13, 20, 25]])
+
+
+def uncond_case_inputs(case):
+    B, F = case['B'], case['F']
+    size = _CFG[case['cfg']]['image_size']
+    x = synth.make_noise((B, F, 3, size, size), seed=52)
+    t = torch.from_numpy(__import__('numpy').random.RandomState(53).randint(0, 1000, size=(B, F))).float()
+    mask = torch.zeros(B, F, 1, 1, 1)
+    for b in range(B):
+        mask[b, :case['n_valid'][b]] = 1
+    return dict(x=x, timesteps=t, attn_mask=mask, frame_indices=torch.tensor(case['frame_indices'], dtype=torch.long))
+
+
+# fixed-seed DDIM-50 chain (north_star's PSNR gate): tiny model, first window of CHAIN_CASE, replayed noise
+DDIM50_CASE = dict(respacing='ddim50', noise_seed=7000)
 
 
 def variant_kwargs(case, inp):

@@ -12,7 +12,8 @@ Citations (reference file:line):
   beta schedules ............... gaussian_diffusion.py:20-72
   derived tables ............... gaussian_diffusion.py:138-172
   respacing .................... respace.py:7-82, 103-119
-  q_sample / posterior ......... gaussian_diffusion.py:190-227
+  q_sample / posterior ......... gaussian_diffusion.py:171-227
+  _predict_* / ddim_reverse .... gaussian_diffusion.py:374-396, 636-668
   p_mean_variance (eps, fixed-large, clip) gaussian_diffusion.py:229-343, 374-382
   p_sample ..................... gaussian_diffusion.py:403-448
   ddim_sample .................. gaussian_diffusion.py:597-634
@@ -92,6 +93,10 @@ class Schedule:
         # fixed-large model variance (gaussian_diffusion.py:300-319)
         self.model_var = np.append(self.post_var[1], b[1:])
         self.model_logvar = np.log(self.model_var)
+        # gaussian_diffusion.py:149 (DDIM reverse ODE) and :384-390 (x_{t-1}-predicting parametrisation)
+        self.acp_next = np.append(acp[1:], 0.0)
+        self.recip_post_c1 = 1.0 / self.post_c1
+        self.post_c2_div_c1 = self.post_c2 / self.post_c1
 
     def model_time(self, t):
         """Timestep the network sees (respace.py:111-119, rescale_timesteps=True)."""
@@ -106,6 +111,40 @@ def _g(table, t, like):
 
 def q_sample(s, x0, t, noise):
     return _g(s.sqrt_acp, t, x0) * x0 + _g(s.sqrt_1m_acp, t, x0) * noise
+
+
+def q_mean_variance(s, x0, t):
+    """gaussian_diffusion.py:171-188"""
+    return (_g(s.sqrt_acp, t, x0) * x0, _g(1.0 - s.acp, t, x0).expand_as(x0), _g(s.log_1m_acp, t, x0).expand_as(x0))
+
+
+def q_posterior_mean_variance(s, x0, x_t, t):
+    """gaussian_diffusion.py:208-227"""
+    return (_g(s.post_c1, t, x_t) * x0 + _g(s.post_c2, t, x_t) * x_t, _g(s.post_var, t, x_t).expand_as(x_t),
+            _g(s.post_logvar, t, x_t).expand_as(x_t))
+
+
+def predict_xstart_from_eps(s, x_t, t, eps):
+    """gaussian_diffusion.py:374-382"""
+    return _g(s.sqrt_recip_acp, t, x_t) * x_t - _g(s.sqrt_recipm1_acp, t, x_t) * eps
+
+
+def predict_xstart_from_xprev(s, x_t, t, xprev):
+    """gaussian_diffusion.py:384-390"""
+    return _g(s.recip_post_c1, t, x_t) * xprev - _g(s.post_c2_div_c1, t, x_t) * x_t
+
+
+def predict_eps_from_xstart(s, x_t, t, pred_xstart):
+    """gaussian_diffusion.py:392-396"""
+    return (_g(s.sqrt_recip_acp, t, x_t) * x_t - pred_xstart) / _g(s.sqrt_recipm1_acp, t, x_t)
+
+
+def ddim_reverse_sample(s, eps, x, t, clip_denoised=True):
+    """gaussian_diffusion.py:636-668 (eta = 0)"""
+    out = p_mean_variance(s, eps, x, t, clip_denoised)
+    e = (_g(s.sqrt_recip_acp, t, x) * x - out['pred_xstart']) / _g(s.sqrt_recipm1_acp, t, x)
+    abn = _g(s.acp_next, t, x)
+    return dict(sample=out['pred_xstart'] * torch.sqrt(abn) + torch.sqrt(1 - abn) * e, pred_xstart=out['pred_xstart'])
 
 
 def p_mean_variance(s, eps, x, t, clip_denoised=True):

@@ -34,9 +34,9 @@ from improved_diffusion.script_util import (create_gaussian_diffusion,       # n
                                             video_model_and_diffusion_defaults)
 
 from oracle import synth                                                      # noqa: E402
-from oracle.cases import (CHAIN_CASE, DIFFUSION_CASES, STRATEGY_GRID, UNET_CASES, UNET_LUT_CASES,  # noqa: E402
-                          UNET_VARIANT_CASES, bpd_case_inputs, fake_eps, model_kwargs_for, ref_config,
-                          unet_case_inputs, variant_kwargs)
+from oracle.cases import (CHAIN_CASE, DDIM50_CASE, DIFFUSION_CASES, FULL_CASES, STRATEGY_GRID, UNCOND_CASE,  # noqa: E402
+                          UNET_CASES, UNET_LUT_CASES, UNET_VARIANT_CASES, bpd_case_inputs, fake_eps, full_case_inputs,
+                          model_kwargs_for, ref_config, uncond_case_inputs, unet_case_inputs, variant_kwargs)
 
 
 class NoiseReplay:
@@ -91,7 +91,7 @@ def dump_unet(cases_list=UNET_CASES, fname='unet.npz'):
     arrays = {}
     for case in cases_list:
         model, _ = load_ref_model(case['cfg'])
-        inp = unet_case_inputs(case)
+        inp = full_case_inputs(case) if fname == 'unet_full.npz' else unet_case_inputs(case)
         taps = {}
         hooks = []
         for grp in ('input_blocks', 'output_blocks'):
@@ -290,6 +290,92 @@ def dump_attn():
     np.savez_compressed(os.path.join(GOLD, 'attn.npz'), **arrays)
 
 
+def first_window_kwargs(c):
+    B, T = c['batch'], c['video_length']
+    video = synth.make_video((B, T, 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    it = inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])
+    obs, lat = next(iter(it))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+    fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    return x0, dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+                    x_t_minus_1=x0, observed_frames='x_0')
+
+
+def dump_ddim50():
+    """north_star's sampled-frames gate: a fixed-seed DDIM-50 `ddim_sample_loop` (gaussian_diffusion.py:670-748) on the
+    first window of the chain case, eta 0 and eta 1 (the stochastic branch draws replayed noise every step)."""
+    c, d = CHAIN_CASE, DDIM50_CASE
+    model, diffusion = load_ref_model(c['cfg'], d['respacing'])
+    assert diffusion.num_timesteps == 50
+    x0, kw = first_window_kwargs(c)
+    arrays = {}
+    for eta in (0.0, 1.0):
+        gd.th.randn_like = NoiseReplay(d['noise_seed'] + 1)
+        init = synth.make_noise(tuple(x0.shape), seed=d['noise_seed'])
+        with torch.no_grad():
+            out = diffusion.ddim_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw,
+                                             device='cpu', eta=eta)
+        arrays[f'ddim50/eta{eta}'] = out.numpy()
+        print('ddim50 eta', eta, float(out.abs().max()), float(out.std()))
+    gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'ddim50.npz'), **arrays)
+
+
+def dump_uncond():
+    """UNetVideoModel.forward (unet.py:898-912): the class is built directly (script_util.py:287-300 passes
+    cond_emb_type, which its constructor rejects), the state-dict spec goes to spec_tiny_uncond.json."""
+    from improved_diffusion.unet import UNetVideoModel
+    case = UNCOND_CASE
+    cfg = ref_config(case['cfg'])
+    model = UNetVideoModel(T=cfg['T'], use_frame_encoding=False, cross_frame_attention=True,
+                           enforce_position_invariance=False, in_channels=3, model_channels=cfg['num_channels'],
+                           out_channels=3, num_res_blocks=cfg['num_res_blocks'], attention_resolutions=(2, 4),
+                           channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True, use_spatial_encoding=True,
+                           image_size=cfg['image_size'], temporal_augment_type='add_manyhead_presoftmax_time',
+                           use_rpe_net=True, bucket_params=dict(alpha=cfg['T'], beta=cfg['T'], gamma=cfg['T']),
+                           allow_interactions_between_padding=True).eval()
+    spec = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, 'spec_tiny_uncond.json'), 'w') as f:
+        json.dump(spec, f, indent=0, sort_keys=True)
+    model.load_state_dict(synth.make_state_dict(spec, seed=1))
+    inp = uncond_case_inputs(case)
+    with torch.no_grad():
+        out, attn = model(inp['x'], inp['timesteps'], frame_indices=inp['frame_indices'], attn_mask=inp['attn_mask'])
+    assert attn is None
+    print('uncond', float(out.abs().max()), float(out.std()))
+    np.savez_compressed(os.path.join(GOLD, 'unet_uncond.npz'), **{f"{case['name']}/eps": out.numpy()})
+
+
+def dump_diffusion_extra():
+    """The posterior / prediction helpers and the DDIM reverse ODE (gaussian_diffusion.py:171-188, 208-227, 374-396,
+    636-668) for the stand-in network: the closed-form methods the first fixture set did not cover."""
+    arrays = {}
+    for case in DIFFUSION_CASES:
+        name = case['name']
+        d = create_gaussian_diffusion(steps=1000, noise_schedule=case['schedule'], timestep_respacing=case['respacing'],
+                                      rescale_timesteps=True, rescale_learned_sigmas=True)
+        shape = case['shape']
+        x, x0, noise = synth.make_noise(shape, seed=11), synth.make_video(shape, seed=12), synth.make_noise(shape, seed=13)
+        model = lambda xx, timesteps, **kw: (fake_eps(xx, timesteps), None)
+        for tag, t in case['ts'].items():
+            t = torch.tensor(t)
+            k = f'{name}/{tag}/'
+            m, v, lv = d.q_mean_variance(x0, t)
+            arrays[k + 'q_mean'], arrays[k + 'q_var'], arrays[k + 'q_logvar'] = m.numpy(), v.numpy(), lv.numpy()
+            m, v, lv = d.q_posterior_mean_variance(x0, x, t)
+            arrays[k + 'post_mean'], arrays[k + 'post_var'], arrays[k + 'post_logvar'] = m.numpy(), v.numpy(), lv.numpy()
+            arrays[k + 'xstart_from_eps'] = d._predict_xstart_from_eps(x, t, noise).numpy()
+            arrays[k + 'xstart_from_xprev'] = d._predict_xstart_from_xprev(x, t, noise).numpy()
+            arrays[k + 'eps_from_xstart'] = d._predict_eps_from_xstart(x, t, x0).numpy()
+            rv = d.ddim_reverse_sample(model, x, t, clip_denoised=True, model_kwargs={})
+            arrays[k + 'ddim_reverse'] = rv['sample'].numpy()
+    np.savez_compressed(os.path.join(GOLD, 'diffusion_extra.npz'), **arrays)
+    print('diffusion_extra', len(arrays))
+
+
 P_LOOP_MODES = ('x_0', 'x_t_minus_1', 'hybrid_5')
 
 
@@ -335,6 +421,12 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['lut']:       # only the lookup-table RPE fixtures (leaves the other files untouched)
         dump_specs(('tiny_lut',))
         dump_unet(UNET_LUT_CASES, 'unet_lut.npz')
+        sys.exit(0)
+    if sys.argv[1:] == ['round2']:    # full-size C2 / C4 forwards, unconditioned entry point, DDIM-50 chain, helpers
+        dump_unet(FULL_CASES, 'unet_full.npz')
+        dump_uncond()
+        dump_ddim50()
+        dump_diffusion_extra()
         sys.exit(0)
     if sys.argv[1:] == ['attn']:
         dump_attn()

@@ -50,5 +50,7 @@ def make_noise(shape, seed=3):
 def fingerprint(t, n=16):
     """Compact signature of a tensor: [mean, std, absmax, n strided samples]."""
     f = t.detach().float().reshape(-1)
-    idx = torch.linspace(0, f.numel() - 1, n).long()
+    # fp32 linspace (kept for the committed fixtures) cannot represent indices above 2^24 exactly
+    big = f.numel() > 2 ** 24
+    idx = torch.linspace(0, f.numel() - 1, n, dtype=torch.float64 if big else torch.float32).long().clamp_(max=f.numel() - 1)
     return torch.cat([torch.stack([f.mean(), f.std(), f.abs().max()]), f[idx]]).numpy()

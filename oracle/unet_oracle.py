@@ -261,6 +261,16 @@ def unet_forward(sd, cfg, x, timesteps, frame_indices, attn_mask, T, taps=None, 
     return F.conv2d(h, sd['out.2.weight'], sd['out.2.bias'], padding=1)
 
 
+def video_forward(sd, cfg, x, timesteps, frame_indices=None, attn_mask=None):
+    """UNetVideoModel.forward (unet.py:898-912): x (B,F,3,H,W), timesteps (B,F) -- one value per frame --,
+    attn_mask (B,F,1,1,1) (the reference flattens it, so it is required), no conditioning mix."""
+    B, Fr, C, H, W = x.shape
+    if frame_indices is None:
+        frame_indices = torch.arange(Fr).view(1, Fr).expand(B, Fr)
+    out = unet_forward(sd, cfg, x.reshape(B * Fr, C, H, W), timesteps.reshape(B * Fr), frame_indices, attn_mask, Fr)
+    return out.view(B, Fr, cfg['out_ch'], H, W)
+
+
 def cond_marg_forward(sd, cfg, x, x0, obs_mask, latent_mask, kinda_marg_mask, timesteps,
                       frame_indices=None, taps=None, observed_frames='x_0', x_t_minus_1=None, hybrid=None,
                       attn_log=None):

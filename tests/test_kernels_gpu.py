@@ -361,6 +361,38 @@ def test_groupnorm_temporal_and_spatial_encoding(B, T, HW, Cc):
     assert torch.equal(only_f.view(B * T, HW, Cc), h2.view(B * T, HW, Cc) + femb[:, None, :])
 
 
+def test_groupnorm_channels_with_large_mean():
+    """Channels with |mean| >> std (mean 50, std 0.5), as a trained residual stream can have: the temporal GroupNorm
+    kernels take the variance about the mean (two-pass, like the reference), and the bf16 GEMM epilogue's single-pass
+    fixed-point sums must still give a normalised output within the bf16-mode tolerance."""
+    o = ops()
+    # temporal kernels (register-resident and general)
+    for (B, T, HW, Cc) in [(2, 20, 16, 384), (2, 6, 16, 192)]:
+        x = rnd(B, T, HW, Cc, seed=1) * 0.5 + 50.0 * torch.sign(rnd(Cc, seed=9))
+        gamma, beta = rnd(Cc, seed=2), rnd(Cc, seed=3)
+        xr = x.permute(0, 2, 3, 1).reshape(B * HW, Cc, T)
+        ref = F.group_norm(xr.double(), 32, gamma.double(), beta.double(), eps=1e-5).view(B, HW, Cc, T).permute(0, 3, 1, 2)
+        out, outa = torch.empty_like(x), torch.empty_like(x, dtype=torch.bfloat16)
+        o.gn_temporal(x, B, T, HW, Cc, gamma, beta, out, outa)
+        torch_err = relerr(F.group_norm(xr, 32, gamma, beta, eps=1e-5).view(B, HW, Cc, T).permute(0, 3, 1, 2), ref)
+        assert relerr(out, ref) < max(2e-5, 2 * torch_err)
+    # GEMM-epilogue statistics -> GroupNorm apply: a 1x1 conv with identity-like weights and a +-50 bias
+    n, H, W, C = 3, 16, 16, 128
+    x = (rnd(n, C, H, W, seed=4) * 0.5).bfloat16()
+    w = torch.eye(C, device='cuda').bfloat16()
+    bias = 50.0 * torch.sign(rnd(C, seed=5))
+    h = torch.empty(n * H * W, C, device='cuda')
+    st = torch.zeros(n, 2, C, device='cuda', dtype=torch.int64)
+    o.gemm(nhwc(x.float()).bfloat16(), w, C, n_img=n, H=H, W=W, taps=1, bias=bias, out_f32=h, stats_out=st)
+    gamma, beta = rnd(C, seed=6), rnd(C, seed=7)
+    ref = F.group_norm(from_nhwc(h, n, H, W).double(), 32, gamma.double(), beta.double(), eps=1e-5)
+    out = torch.empty(n * H * W, C, device='cuda', dtype=torch.bfloat16)
+    o.gn_apply(h, None, n, H, W, out, stats1=st, gamma=gamma, beta=beta)
+    err = relerr(out, nhwc(ref))
+    print(f'epilogue-stats GroupNorm with mean/std = 100: max-rel error {err:.3e}')
+    assert err < 5e-3          # bf16 output rounding is 4e-3; the statistics must not add to it
+
+
 def test_cond_mix_and_timestep_embedding():
     from oracle import unet_oracle as U
     o = ops()

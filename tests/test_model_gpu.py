@@ -84,7 +84,7 @@ def test_forward_matches_reference_and_oracle(golden, case, dtype):
     e_orc = max_rel(out.cpu().numpy(), ref.numpy())
     print(f"{case['name']} {dtype}: eps max-rel vs reference {e_ref:.3e}, vs oracle {e_orc:.3e}, worst block {worst:.3e}")
     assert e_ref <= TOL[dtype]
-    assert worst <= 2.5 * TOL[dtype]
+    assert worst <= 1.5 * TOL[dtype]      # measured: <= 1.1 x TOL in bf16 (intermediate blocks), 3e-6 in fp32
 
 
 @pytest.mark.parametrize('cfg_name,B,F,bound', [('c2', 2, 20, None), ('c4', 1, 6, None)], ids=['c2_64x64', 'c4_128x128'])
@@ -115,6 +115,81 @@ def test_full_size_models_match_oracle(golden, cfg_name, B, F, bound, dtype):
     err = max_rel(out.cpu().numpy(), ref.numpy())
     print(f'{cfg_name} {dtype}: eps max-rel vs oracle {err:.3e}')
     assert err <= TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('case', cases.FULL_CASES, ids=lambda c: c['name'])
+def test_full_size_models_match_reference(golden, case, dtype):
+    """The benchmarked C2 / C4 architectures against the REFERENCE's own eps and per-block fingerprints at full size
+    (tests/golden/unet_full.npz, one video each): every full-size kernel path (head_dim 96 / 128, pair tiles, halo and
+    transposed-role kernels, folded upsample, tensor-core attention) is pinned to the reference, not only to the oracle."""
+    g = golden.npz('unet_full')
+    model, _ = build_model(case['cfg'], golden, dtype)
+    model.use_cuda_graph = False
+    inp = cases.full_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    with torch.no_grad():
+        out, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+    torch.cuda.synchronize()
+    ws = next(iter(model._workspaces.values()))
+    worst = 0.0
+    for node in model.plan:
+        buf, tap = tap_name(node)
+        ref = g[f"{case['name']}/tap/{tap.rsplit('.', 1)[0]}"]
+        t = ws.bufs[buf].float()
+        c = t.shape[-1]
+        n = inp['x'].shape[0] * inp['x'].shape[1]
+        hw = int(round((t.numel() // (n * c)) ** 0.5))
+        got = synth.fingerprint(t.view(n, hw, hw, c).permute(0, 3, 1, 2).contiguous().cpu())
+        err = float(np.abs(got - ref).max() / ref[2])            # ref[2] = the block's max |activation|
+        worst = max(worst, err)
+        if err > TOL[dtype]:
+            print(f'  {tap:45s} fingerprint err {err:.3e}')
+    e_ref = max_rel(out.cpu().numpy(), g[f"{case['name']}/eps"])
+    print(f"{case['name']} {dtype}: eps max-rel vs reference {e_ref:.3e}, worst block fingerprint {worst:.3e}")
+    assert e_ref <= TOL[dtype]
+    assert worst <= 1.5 * TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_unconditioned_video_model_matches_reference(golden, dtype):
+    """UNetVideoModel.forward (unet.py:898-912; do_cond_marg=False): one timestep per FRAME, the caller's attention
+    mask (with padding frames), no conditioning mix."""
+    from video_diffusion_b200.unet import CondMargVideoModel, UNetVideoModel
+    case = cases.UNCOND_CASE
+    g = golden.npz('unet_uncond')
+    model, _ = build_model(case['cfg'], golden, dtype)
+    assert isinstance(model, UNetVideoModel) and not isinstance(model, CondMargVideoModel)
+    inp = cases.uncond_case_inputs(case)
+    for graph in (False, True):
+        model.use_cuda_graph = graph
+        with torch.no_grad():
+            out, attn = model(inp['x'].cuda(), inp['timesteps'].cuda(), frame_indices=inp['frame_indices'].cuda(),
+                              attn_mask=inp['attn_mask'].cuda())
+        assert attn is None
+        err = max_rel(out.cpu().numpy(), g[f"{case['name']}/eps"])
+        print(f'uncond {dtype} graph={graph}: eps max-rel vs reference {err:.3e}')
+        assert err <= TOL[dtype]
+
+
+def test_in_place_weight_update_repacks(golden):
+    """Packed bf16 weights and CUDA graphs follow in-place parameter updates (EMA swap, p.data.copy_)."""
+    case = cases.UNET_CASES[0]
+    model, _ = build_model(case['cfg'], golden, torch.bfloat16)
+    inp = cases.unet_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    with torch.no_grad():
+        a, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+        w = model.out._modules['2'].weight
+        old = w.data.clone()
+        w.data.mul_(0.5)
+        model.out._modules['2'].bias.data.mul_(0.5)
+        b, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+        w.data.copy_(old)
+        model.out._modules['2'].bias.data.mul_(2.0)
+        c, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+    assert torch.allclose(b, 0.5 * a, rtol=2e-2, atol=1e-3) and not torch.allclose(b, a, rtol=1e-2, atol=1e-3)
+    assert torch.equal(c, a)
 
 
 def test_cuda_graph_replay_equals_eager(golden):

@@ -124,6 +124,78 @@ def test_unet_forward_matches_reference(golden, case):
     assert checked == len([k for k in g.files if k.startswith(case['name'] + '/tap/')])
 
 
+@pytest.mark.parametrize('case', cases.FULL_CASES, ids=lambda c: c['name'])
+def test_full_size_forward_matches_reference(golden, case):
+    """The benchmarked 64x64 (C2) and 128x128 (C4) architectures at full size: oracle vs the reference's own eps and
+    per-block fingerprints (tests/golden/unet_full.npz) -- pins the oracle where the GPU parity tests use it."""
+    g = golden.npz('unet_full')
+    sd = synth.make_state_dict(golden.json('spec_' + case['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(case['cfg']))
+    inp = cases.full_case_inputs(case)
+    taps = {}
+    with torch.no_grad():
+        out = U.cond_marg_forward(sd, cfg, inp['x'], inp['x0'], inp['obs_mask'], inp['latent_mask'],
+                                  inp['kinda_marg_mask'], inp['t_model'], inp['frame_indices'], taps=taps)
+    assert max_rel(out.numpy(), g[f"{case['name']}/eps"]) < 2e-5
+    for key, val in taps.items():
+        gk = f"{case['name']}/tap/" + ('emb' if key == 'emb' else key.rsplit('.', 1)[0])
+        np.testing.assert_allclose(synth.fingerprint(val), g[gk], rtol=2e-4, atol=2e-4, err_msg=key)
+
+
+def test_unconditioned_video_forward_matches_reference(golden):
+    """UNetVideoModel.forward (unet.py:898-912): per-frame timesteps, attention mask with padding frames."""
+    case = cases.UNCOND_CASE
+    g = golden.npz('unet_uncond')
+    sd = synth.make_state_dict(golden.json('spec_' + case['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(case['cfg']))
+    inp = cases.uncond_case_inputs(case)
+    with torch.no_grad():
+        out = U.video_forward(sd, cfg, inp['x'], inp['timesteps'], inp['frame_indices'], inp['attn_mask'])
+    assert max_rel(out.numpy(), g[f"{case['name']}/eps"]) < 2e-5
+
+
+@pytest.mark.parametrize('case', cases.DIFFUSION_CASES, ids=lambda c: c['name'])
+def test_posterior_and_prediction_helpers(golden, case):
+    """q_mean_variance, q_posterior_mean_variance, _predict_*, ddim_reverse_sample (gaussian_diffusion.py:171-227,
+    374-396, 636-668)."""
+    g, n = golden.npz('diffusion_extra'), case['name']
+    s = D.Schedule(1000, case['schedule'], case['respacing'])
+    shape = case['shape']
+    x, x0, noise = synth.make_noise(shape, 11), synth.make_video(shape, 12), synth.make_noise(shape, 13)
+    for tag, tl in case['ts'].items():
+        t = torch.tensor(tl)
+        k = f'{n}/{tag}/'
+        close = lambda a, key, tol=1e-6: np.testing.assert_allclose(a.numpy(), g[k + key], rtol=tol, atol=tol, err_msg=k + key)
+        for got, key in zip(D.q_mean_variance(s, x0, t), ('q_mean', 'q_var', 'q_logvar')):
+            close(got, key)
+        for got, key in zip(D.q_posterior_mean_variance(s, x0, x, t), ('post_mean', 'post_var', 'post_logvar')):
+            close(got, key)
+        close(D.predict_xstart_from_eps(s, x, t, noise), 'xstart_from_eps')
+        close(D.predict_xstart_from_xprev(s, x, t, noise), 'xstart_from_xprev', 2e-6)
+        close(D.predict_eps_from_xstart(s, x, t, x0), 'eps_from_xstart')
+        close(D.ddim_reverse_sample(s, cases.fake_eps(x, s.model_time(t)), x, t)['sample'], 'ddim_reverse', 2e-6)
+
+
+def test_ddim50_chain_matches_reference(golden):
+    """Fixed-seed DDIM-50 `ddim_sample_loop` (north_star's sampled-frames gate), eta 0 and the stochastic eta 1."""
+    from oracle import pipeline_oracle as P
+    g = golden.npz('ddim50')
+    c, d = cases.CHAIN_CASE, cases.DDIM50_CASE
+    sd = synth.make_state_dict(golden.json('spec_' + c['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(c['cfg']))
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    sched = D.Schedule(1000, 'linear', d['respacing'])
+    obs, lat = next(S.schedule(c['mode'], c['video_length'], c['obs_length'], c['max_frames'], c['step_size']))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1)
+    fi, om, lm, km = (torch.from_numpy(a) for a in S.window_tensors(obs, lat, c['batch']))
+    kw = dict(x0=x0, obs_mask=om, latent_mask=lm, kinda_marg_mask=km, frame_indices=fi)
+    for eta in (0.0, 1.0):
+        init = synth.make_noise(tuple(x0.shape), seed=d['noise_seed'])
+        with torch.no_grad():
+            out = P.ddim_sample_loop(sd, cfg, sched, init, kw, _Replay(d['noise_seed'] + 1), eta=eta)
+        assert np.abs(out.numpy() - g[f'ddim50/eta{eta}']).max() < 2e-3, eta
+
+
 def test_spec_shapes_cover_oracle_plan(golden):
     """Every key the oracle reads exists in the reference's state_dict spec (all four configs)."""
     for name in ('tiny', 'tiny_nrb2', 'c2', 'c4'):

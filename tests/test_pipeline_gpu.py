@@ -47,7 +47,7 @@ def psnr(a, b):
     return 10 * np.log10(1.0 / max(np.mean((a - b) ** 2), 1e-12))
 
 
-@pytest.mark.parametrize('dtype,min_psnr,tol', [(torch.float32, 55.0, 2e-3), (torch.bfloat16, 30.0, None)],
+@pytest.mark.parametrize('dtype,min_psnr,tol', [(torch.float32, 55.0, 2e-3), (torch.bfloat16, 40.0, None)],
                          ids=['fp32', 'bf16'])
 def test_infer_video_independent_ddim10_matches_reference(golden, replay, dtype, min_psnr, tol):
     from video_diffusion_b200.sampling import infer_video
@@ -85,7 +85,7 @@ def test_infer_video_save_all_timesteps(golden, replay):
     assert np.abs(every[:, 0] - every[:, -1]).max() > 1e-2               # earlier states differ
 
 
-@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 30.0)], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 40.0)], ids=['fp32', 'bf16'])
 def test_ddim_sample_loop_matches_reference(golden, replay, dtype, min_psnr):
     from video_diffusion_b200.inference_util import inference_strategies
     c = cases.CHAIN_CASE
@@ -107,8 +107,40 @@ def test_ddim_sample_loop_matches_reference(golden, replay, dtype, min_psnr):
     assert p >= min_psnr
 
 
+def _first_window(c):
+    from video_diffusion_b200.inference_util import inference_strategies
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    obs, lat = next(iter(inference_strategies[c['mode']](video_length=c['video_length'], num_obs=c['obs_length'],
+                                                         max_frames=c['max_frames'], step_size=c['step_size'])))
+    x0 = torch.cat([video[:, obs], torch.zeros_like(video[:, lat])], dim=1).cuda()
+    om = torch.zeros_like(x0[:, :, :1, :1, :1])
+    om[:, :len(obs)] = 1
+    return x0, dict(frame_indices=torch.tensor(obs + lat).repeat(c['batch'], 1).cuda(), x0=x0, obs_mask=om,
+                    latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om), x_t_minus_1=x0, observed_frames='x_0')
+
+
+# BASELINE.json: "final sampled frames matching within a stated PSNR bound after a fixed-seed DDIM-50 run".
+# Stated bound: fp32 mode >= 55 dB, bf16 mode >= 38 dB against the reference's frames for the same seed
+# (50 network calls compound the per-call bf16 error; eta = 1 re-injects replayed noise every step).
+@pytest.mark.parametrize('eta', [0.0, 1.0], ids=['eta0', 'eta1'])
+@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 38.0)], ids=['fp32', 'bf16'])
+def test_fixed_seed_ddim50_matches_reference(golden, replay, dtype, min_psnr, eta):
+    c, d = cases.CHAIN_CASE, cases.DDIM50_CASE
+    g = golden.npz('ddim50')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=d['respacing'])
+    assert diffusion.num_timesteps == 50
+    x0, kw = _first_window(c)
+    init = synth.make_noise(tuple(x0.shape), seed=d['noise_seed']).cuda()
+    replay(d['noise_seed'] + 1)
+    out = diffusion.ddim_sample_loop(model, tuple(x0.shape), noise=init, clip_denoised=True, model_kwargs=kw, eta=eta)
+    ref = g[f'ddim50/eta{eta}']
+    p = psnr(out.cpu().numpy(), ref)
+    print(f'DDIM-50 eta={eta} {dtype}: PSNR vs reference = {p:.1f} dB, max abs diff {np.abs(out.cpu().numpy() - ref).max():.3e}')
+    assert p >= min_psnr
+
+
 @pytest.mark.parametrize('mode', ['x_0', 'x_t_minus_1', 'hybrid_5'])
-@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 30.0)], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 40.0)], ids=['fp32', 'bf16'])
 def test_p_sample_loop_matches_reference(golden, replay, dtype, min_psnr, mode):
     """p_sample_loop incl. its per-step re-noised conditioning tensors (gaussian_diffusion.py:565-582)."""
     from video_diffusion_b200.inference_util import inference_strategies
@@ -183,6 +215,68 @@ def test_elbo_within_half_percent(golden, replay, dtype):
     if dtype == torch.float32:
         np.testing.assert_allclose(got['mse'], g['bpd/mse'].sum(1) * mf, rtol=2e-3)
         np.testing.assert_allclose(got['xstart_mse'], g['bpd/xstart_mse'].sum(1) * mf, rtol=2e-3)
+
+
+@pytest.mark.parametrize('case', cases.DIFFUSION_CASES, ids=lambda c: c['name'])
+def test_posterior_and_prediction_helpers_match_reference(golden, case):
+    """q_mean_variance, q_posterior_mean_variance, _predict_xstart_from_eps / _from_xprev, _predict_eps_from_xstart
+    and ddim_reverse_sample (gaussian_diffusion.py:171-188, 208-227, 374-396, 636-668) through the kernel-backed
+    methods (vdm_lincomb, vdm_sampler_step mode 2) against the reference's own outputs."""
+    from video_diffusion_b200 import create_gaussian_diffusion
+    g, n = golden.npz('diffusion_extra'), case['name']
+    d = create_gaussian_diffusion(steps=1000, noise_schedule=case['schedule'], timestep_respacing=case['respacing'],
+                                  rescale_timesteps=True, rescale_learned_sigmas=True)
+    shape = case['shape']
+    x, x0, noise = (synth.make_noise(shape, 11).cuda(), synth.make_video(shape, 12).cuda(),
+                    synth.make_noise(shape, 13).cuda())
+    model = lambda xx, timesteps, **kw: (cases.fake_eps(xx, timesteps), None)
+    for tag, tl in case['ts'].items():
+        t = torch.tensor(tl).cuda()
+        k = f'{n}/{tag}/'
+        amp = max(1.0, float(np.max(d.sqrt_recip_alphas_cumprod[np.array(tl)])) / 10)
+
+        def close(a, key, tol=2e-6):
+            ref = g[k + key]
+            assert tuple(a.shape) == ref.shape, key
+            np.testing.assert_allclose(a.cpu().numpy(), ref, rtol=tol, atol=tol * amp, err_msg=k + key)
+        for got, key in zip(d.q_mean_variance(x0, t), ('q_mean', 'q_var', 'q_logvar')):
+            close(got, key)
+        for got, key in zip(d.q_posterior_mean_variance(x0, x, t), ('post_mean', 'post_var', 'post_logvar')):
+            close(got, key)
+        close(d._predict_xstart_from_eps(x, t, noise), 'xstart_from_eps')
+        close(d._predict_xstart_from_xprev(x, t, noise), 'xstart_from_xprev', 4e-6)
+        close(d._predict_eps_from_xstart(x, t, x0), 'eps_from_xstart')
+        rv = d.ddim_reverse_sample(model, x, t, clip_denoised=True, model_kwargs={})
+        close(rv['sample'], 'ddim_reverse', 5e-6)
+        with pytest.raises(AssertionError):
+            d.ddim_reverse_sample(model, x, t, eta=0.5)
+
+
+def test_out_of_range_timesteps_and_wrong_dtypes_raise():
+    """The reference indexes its numpy schedule tables with t (IndexError outside the respaced range) and keeps
+    dtypes; the kernels reinterpret raw memory, so wrong dtypes raise and out-of-range timesteps are clamped,
+    recorded and reported as IndexError instead of reading out of bounds."""
+    from video_diffusion_b200 import create_gaussian_diffusion, ops
+    d = create_gaussian_diffusion(steps=1000, timestep_respacing='ddim10', rescale_timesteps=True)
+    model = lambda xx, timesteps, **kw: (cases.fake_eps(xx, timesteps), None)
+    x = synth.make_noise((2, 4, 3, 8, 8), 11).cuda()
+    ok = d.p_sample(model, x, torch.tensor([9, 0]).cuda(), model_kwargs={})['sample']
+    torch.cuda.synchronize()
+    ops.check_timesteps()                                   # in range: nothing recorded
+    assert torch.isfinite(ok).all()
+    d.p_sample(model, x, torch.tensor([999, 3]).cuda(), model_kwargs={})      # original timesteps on a 10-step chain
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        ops.check_timesteps()
+    ops.check_timesteps()                                   # the record is cleared once reported
+    d.q_sample(x, torch.tensor([10, 0]).cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        d.q_posterior_mean_variance(x, x, torch.tensor([1, 1]).cuda())      # reported by the next sampler-family call
+    with pytest.raises(TypeError):
+        d.p_sample(model, x.double(), torch.tensor([1, 1]).cuda(), model_kwargs={})
+    with pytest.raises(TypeError):
+        d.q_sample(x, torch.tensor([1, 1]).cuda(), noise=x.half())
 
 
 @pytest.mark.parametrize('case', cases.DIFFUSION_CASES, ids=lambda c: c['name'])

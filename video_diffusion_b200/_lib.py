@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(_HERE, 'libvdm.so')
 
 F32, BF16, F64, I64 = 0, 1, 2, 3
 TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOGVAR=4, MODEL_VAR=5, ACP=6,
-           ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11)
-TAB_COUNT = 12
+           ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11, POST_VAR=12, RECIP_POST_C1=13,
+           POST_C2_DIV_C1=14, ACP_NEXT=15)
+TAB_COUNT = 16
 
 EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
            'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
-           'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_vb_terms',
-           'vdm_prior_bpd']
+           'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_error', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_lincomb',
+           'vdm_vb_terms', 'vdm_prior_bpd']
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -54,6 +55,8 @@ def load():
     lib.vdm_version.restype = _i32
     lib.vdm_last_error_string.restype = C.c_char_p
     lib.vdm_launch_count.restype = _i64
+    lib.vdm_sampler_error.restype = _i32
+    lib.vdm_sampler_error.argtypes = []
     sig = {
         'vdm_gemm': [C.POINTER(GemmArgs), _vp],
         'vdm_gn_stats': [_vp, _i32, _i32, _i32, _vp, _vp],
@@ -71,6 +74,7 @@ def load():
         'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
         'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
         'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],
+        'vdm_lincomb': [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp],
         'vdm_vb_terms': [_vp] * 6 + [_i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp],
         'vdm_prior_bpd': [_vp, _vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp],
     }
@@ -88,11 +92,19 @@ def check(rc, what):
         raise RuntimeError(f'libvdm {what} failed (rc={rc}): {msg}')
 
 
-def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+def ptr(t, dtype=None):
+    """Device pointer of a tensor (None -> NULL).  The kernels reinterpret raw memory, so the tensor must be a
+    contiguous CUDA tensor ON THE CURRENT DEVICE (launches go to that device's current stream) and, when the entry
+    point fixes the element type, of exactly that dtype -- anything else raises instead of computing garbage."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), 'libvdm needs contiguous CUDA tensors'
+    if not (t.is_cuda and t.is_contiguous()):
+        raise ValueError('libvdm needs contiguous CUDA tensors')
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f'libvdm: tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()} '
+                           '(wrap the call in torch.cuda.device(tensor.device))')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f'libvdm: expected a {dtype} tensor, got {t.dtype}')
     return t.data_ptr()
 
 

@@ -339,14 +339,14 @@ template <int HD>
 int launch_attn(const void* qkv, const float* sk, const float* sq, const float* mask, int pad, int B, int T, int D,
                 int heads, int gpt, void* pm, float* pv, cudaStream_t stream) {
   const size_t smem = (size_t)2 * 3 * 32 * (HD + 8) * sizeof(__nv_bfloat16);
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(attn_temporal_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("attn_temporal_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   const int n_prob = B * D * heads;
   attn_temporal_mma_kernel<HD><<<(n_prob + 1) / 2, 128, smem, stream>>>(

@@ -191,15 +191,15 @@ __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat
 template <int HD, typename OutT>
 int launch(const void* qkv, int n_img, int L, int heads, void* out, cudaStream_t stream) {
   const size_t smem = (size_t)(BQ + 4 * BKV) * (HD + 8) * sizeof(__nv_bfloat16);
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(attn_spatial_mma_kernel<HD, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
       set_error("attn_spatial_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   dim3 grid((L + BQ - 1) / BQ, heads, n_img);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);

@@ -32,12 +32,24 @@ extern std::atomic<int64_t> g_launches;
     }                                                                                 \
   } while (0)
 
+// Host-side caches (SM count, "function attributes already set") are kept per CUDA device: a process may hold
+// models on several GPUs, and cudaFuncSetAttribute applies to the current device's context only.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+template <typename T>
+struct PerDevice {
+  T v[64] = {};
+  T& get() { return v[current_device() & 63]; }
+};
+
 inline int num_sms() {
-  static int n = 0;
+  static PerDevice<int> cache;
+  int& n = cache.get();
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
     if (n <= 0) n = 148;
   }
   return n;

@@ -139,14 +139,14 @@ int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   const int R = TILE_PIX / TW;
   const size_t smem = ((size_t)(R + 2) * (TW + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16);
   if (smem > 200 * 1024) return -100;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDevice<size_t> configured;
+  if (smem > configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv3x3_small_n: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = smem;
+    configured.get() = smem;
   }
   const int grid = a->n_img * (H * W / TILE_PIX);
   conv3x3_small_n_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->a1),

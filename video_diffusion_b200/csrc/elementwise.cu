@@ -242,41 +242,53 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
   const int cpg = C / 32, C4 = C / 4;
   const size_t frame_stride = (size_t)HW * C;
   const float* base = x + (size_t)b * T * frame_stride + (size_t)pix * C;
+  // Per-channel sums are taken about a pivot (the channel's value in the first frame), so channels with
+  // |mean| >> std lose no precision to E[x^2] - mean^2 cancellation (the reference's GroupNorm is two-pass).
+  // chs <- per-channel mean, chq <- per-channel sum of squared deviations from that mean.
   for (int q4 = lane; q4 < C4; q4 += 32) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + q4 * 4));
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (int t = 0; t < T; ++t) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + t * frame_stride + q4 * 4));
+    for (int t = 1; t < T; ++t) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(base + t * frame_stride + q4 * 4));
+      v.x -= v0.x; v.y -= v0.y; v.z -= v0.z; v.w -= v0.w;
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
     }
-    *reinterpret_cast<float4*>(chs + q4 * 4) = s;
-    *reinterpret_cast<float4*>(chq + q4 * 4) = q;
+    const float inv_t = 1.0f / (float)T;
+    *reinterpret_cast<float4*>(chs + q4 * 4) =
+        make_float4(v0.x + s.x * inv_t, v0.y + s.y * inv_t, v0.z + s.z * inv_t, v0.w + s.w * inv_t);
+    *reinterpret_cast<float4*>(chq + q4 * 4) =
+        make_float4(q.x - s.x * s.x * inv_t, q.y - s.y * s.y * inv_t, q.z - s.z * s.z * inv_t, q.w - s.w * s.w * inv_t);
   }
   __syncwarp();
   {
-    float s = 0.f, q = 0.f;
-    for (int j = 0; j < cpg; ++j) { s += chs[lane * cpg + j]; q += chq[lane * cpg + j]; }
-    const float cnt = (float)(T * cpg);
-    const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    float s = 0.f, m2 = 0.f;
+    for (int j = 0; j < cpg; ++j) s += chs[lane * cpg + j];
+    const float mean = s / (float)cpg;
+    for (int j = 0; j < cpg; ++j) {
+      const float d = chs[lane * cpg + j] - mean;
+      m2 += chq[lane * cpg + j] + (float)T * d * d;
+    }
+    const float var = fmaxf(m2 / (float)(T * cpg), 0.f);
     gm[lane] = mean;
     ga[lane] = rsqrtf(var + 1e-5f);
   }
   __syncwarp();
   for (int q4 = lane; q4 < C4; q4 += 32) {
     const int c = q4 * 4;
-    float a[4], bb[4];
+    float a[4], bb[4], mu[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int g = (c + i) / cpg;
       a[i] = ga[g] * gamma[c + i];
-      bb[i] = beta[c + i] - gm[g] * a[i];
+      bb[i] = beta[c + i];
+      mu[i] = gm[g];
     }
     for (int t = 0; t < T; ++t) {
       const size_t off = (size_t)b * T * frame_stride + t * frame_stride + (size_t)pix * C + c;
       const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
-      const float y0 = fmaf(v.x, a[0], bb[0]), y1 = fmaf(v.y, a[1], bb[1]);
-      const float y2 = fmaf(v.z, a[2], bb[2]), y3 = fmaf(v.w, a[3], bb[3]);
+      const float y0 = fmaf(v.x - mu[0], a[0], bb[0]), y1 = fmaf(v.y - mu[1], a[1], bb[1]);
+      const float y2 = fmaf(v.z - mu[2], a[2], bb[2]), y3 = fmaf(v.w - mu[3], a[3], bb[3]);
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   const size_t frame_stride = (size_t)HW * C;
   const size_t off0 = (size_t)b * T * frame_stride + (size_t)pix * C + c;
   float4 v[TMAX];          // TMAX >= T: the frame loop is fully unrolled, every load is in flight before the first use
-  float s = 0.f, q = 0.f;
+  float s = 0.f;
   const float4* src = reinterpret_cast<const float4*>(x + off0);
   const size_t stride4 = frame_stride / 4;
 #pragma unroll
@@ -321,29 +333,36 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   }
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
-    if (t < T && active) {
-      s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
-      q = fmaf(v[t].x, v[t].x, fmaf(v[t].y, v[t].y, fmaf(v[t].z, v[t].z, fmaf(v[t].w, v[t].w, q))));
-    }
+    if (t < T && active) s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
   }
-  float gs = 0.f, gq = 0.f;
   const int base = lane - lane % l4;
-  for (int j = 0; j < l4; ++j) {
-    gs += __shfl_sync(0xffffffffu, s, (base + j) & 31);
-    gq += __shfl_sync(0xffffffffu, q, (base + j) & 31);
-  }
-  if (!active) return;
+  float gs = 0.f;
+  for (int j = 0; j < l4; ++j) gs += __shfl_sync(0xffffffffu, s, (base + j) & 31);
   const float cnt = (float)(T * cpg);
   const float mean = gs / cnt;
-  const float rstd = rsqrtf(fmaxf(gq / cnt - mean * mean, 0.f) + 1e-5f);
+  // two-pass variance like the reference's GroupNorm: the values are still in registers, so the centred second
+  // pass costs no memory traffic and channels with |mean| >> std keep their precision
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    if (t < T && active) {
+      const float dx = v[t].x - mean, dy = v[t].y - mean, dz = v[t].z - mean, dw = v[t].w - mean;
+      q = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, q))));
+    }
+  }
+  float gq = 0.f;
+  for (int j = 0; j < l4; ++j) gq += __shfl_sync(0xffffffffu, q, (base + j) & 31);
+  if (!active) return;
+  const float rstd = rsqrtf(fmaxf(gq / cnt, 0.f) + 1e-5f);
   const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
   const float a0 = rstd * gm.x, a1 = rstd * gm.y, a2 = rstd * gm.z, a3 = rstd * gm.w;
-  const float b0 = bt.x - mean * a0, b1 = bt.y - mean * a1, b2 = bt.z - mean * a2, b3 = bt.w - mean * a3;
+  const float b0 = bt.x, b1 = bt.y, b2 = bt.z, b3 = bt.w;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
       const size_t off = off0 + t * frame_stride;
-      const float y0 = fmaf(v[t].x, a0, b0), y1 = fmaf(v[t].y, a1, b1), y2 = fmaf(v[t].z, a2, b2), y3 = fmaf(v[t].w, a3, b3);
+      const float y0 = fmaf(v[t].x - mean, a0, b0), y1 = fmaf(v[t].y - mean, a1, b1);
+      const float y2 = fmaf(v[t].z - mean, a2, b2), y3 = fmaf(v[t].w - mean, a3, b3);
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;

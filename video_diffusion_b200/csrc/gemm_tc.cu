@@ -1604,15 +1604,15 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
                 cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   constexpr int TILE_ROWS = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
   const int tiles = p.n_par * ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS);
@@ -1674,15 +1674,15 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
                      cudaStream_t stream) {
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   constexpr int TILE_ROWS = 2 * BLOCK_M * M_SUB;
   const int tiles = (p.N / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS);
@@ -1745,15 +1745,15 @@ template <int SA, int SB, int EPI>
 int launch_upfold_halo_inst(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
   using L = UpfoldHaloLayout<SA, SB>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_upfold_halo_kernel<SA, SB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (upfold halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   const int tiles = 2 * p.tiles_per_par;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -1799,15 +1799,15 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
                        cudaStream_t stream) {
   using L = HaloTLayout<SA, SB, WIDE>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (transposed halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
+    configured.get() = true;
   }
   const int tiles = (p.N / BLOCK_M) * ((p.M + 2 * L::PIX - 1) / (2 * L::PIX));
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;

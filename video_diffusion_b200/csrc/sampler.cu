@@ -8,8 +8,20 @@ namespace vdm {
 namespace {
 
 struct Coef {
-  float recip, recipm1, c1, c2, logvar, acp, acp_prev, post_logvar, sqrt_acp, sqrt_1m_acp, log_1m_acp;
+  float recip, recipm1, c1, c2, logvar, acp, acp_prev, post_logvar, sqrt_acp, sqrt_1m_acp, log_1m_acp, acp_next;
 };
+
+// The reference indexes numpy tables with t and raises IndexError outside [0, n_steps).  Here an out-of-range
+// timestep never reads past the table: it is clamped and recorded in a host-mapped flag that the next
+// vdm_sampler_error() call reports (the Python layer turns it into the reference's IndexError).
+__device__ int* g_t_error = nullptr;
+__device__ __forceinline__ long long check_t(long long t, int n_steps) {
+  if (t < 0 || t >= n_steps) {
+    if (g_t_error != nullptr) *reinterpret_cast<volatile int*>(g_t_error) = 1;
+    t = t < 0 ? 0 : n_steps - 1;
+  }
+  return t;
+}
 
 __device__ __forceinline__ Coef load_coef(const float* tab, int n_steps, long long t) {
   Coef c;
@@ -24,6 +36,7 @@ __device__ __forceinline__ Coef load_coef(const float* tab, int n_steps, long lo
   c.sqrt_acp = tab[VDM_TAB_SQRT_ACP * n_steps + t];
   c.sqrt_1m_acp = tab[VDM_TAB_SQRT_1M_ACP * n_steps + t];
   c.log_1m_acp = tab[VDM_TAB_LOG_1M_ACP * n_steps + t];
+  c.acp_next = tab[VDM_TAB_ACP_NEXT * n_steps + t];
   return c;
 }
 
@@ -49,6 +62,9 @@ __device__ __forceinline__ float step_value(int mode, const StepConsts& s, float
   float mean;
   if (mode == 0) {
     mean = add(mul(s.c.c1, pred), mul(s.c.c2, x));
+  } else if (mode == 2) {   // DDIM reverse ODE (gaussian_diffusion.py:651-666): x_{t+1} from x_t
+    const float e = __fdiv_rn(sub(mul(s.c.recip, x), pred), s.c.recipm1);
+    mean = add(mul(pred, s.sqrt_abp), mul(s.dir, e));
   } else {
     const float e = __fdiv_rn(sub(mul(s.c.recip, x), pred), s.c.recipm1);
     mean = add(mul(pred, s.sqrt_abp), mul(s.dir, e));
@@ -68,7 +84,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(int mode, const float
                                                             float* __restrict__ sample, float* __restrict__ pred_xstart,
                                                             float* __restrict__ mean_out) {
   const int b = blockIdx.y;
-  const long long tb = t[b];
+  const long long tb = check_t(t[b], n_steps);
   StepConsts s;
   s.c = load_coef(tab, n_steps, tb);
   const float nz = tb != 0 ? 1.0f : 0.0f;
@@ -76,6 +92,10 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(int mode, const float
     s.noise_scale = mul(nz, expf(mul(0.5f, s.c.logvar)));
     s.sqrt_abp = 0.f;
     s.dir = 0.f;
+  } else if (mode == 2) {
+    s.noise_scale = 0.f;
+    s.sqrt_abp = sqrtf(s.c.acp_next);
+    s.dir = sqrtf(sub(1.0f, s.c.acp_next));
   } else {
     const float ab = s.c.acp, abp = s.c.acp_prev;
     const float sigma = mul(mul(eta, sqrtf(__fdiv_rn(sub(1.0f, abp), sub(1.0f, ab)))),
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
                                                         const long long* __restrict__ t, const float* __restrict__ tab,
                                                         int n_steps, long long per_batch, float* __restrict__ out) {
   const int b = blockIdx.y;
-  const long long tb = t[b];
+  const long long tb = check_t(t[b], n_steps);
   const float a = tab[VDM_TAB_SQRT_ACP * n_steps + tb], s = tab[VDM_TAB_SQRT_1M_ACP * n_steps + tb];
   const long long base = (long long)b * per_batch;
   const long long nvec = per_batch / VEC;
@@ -132,6 +152,34 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
       *reinterpret_cast<float4*>(out + off) = o;
     } else {
       out[off] = add(mul(a, x0[off]), mul(s, noise[off]));
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) lincomb_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
+                                                       const long long* __restrict__ t, const float* __restrict__ tab,
+                                                       int n_steps, int row_a, int row_b, long long per_batch,
+                                                       float* __restrict__ out) {
+  const int bi = blockIdx.y;
+  const long long tb = check_t(t[bi], n_steps);
+  const float ca = tab[row_a * n_steps + tb], cb = op == 3 ? 0.f : tab[row_b * n_steps + tb];
+  auto f = [&](float av, float bv) {
+    if (op == 0) return add(mul(ca, av), mul(cb, bv));
+    if (op == 1) return sub(mul(ca, av), mul(cb, bv));
+    if (op == 2) return __fdiv_rn(sub(mul(ca, av), bv), cb);
+    return mul(ca, av);
+  };
+  const long long base = (long long)bi * per_batch;
+  const long long nvec = per_batch / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long off = base + i * VEC;
+    if constexpr (VEC == 4) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a + off));
+      const float4 bv = op == 3 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(b + off));
+      *reinterpret_cast<float4*>(out + off) = make_float4(f(av.x, bv.x), f(av.y, bv.y), f(av.z, bv.z), f(av.w, bv.w));
+    } else {
+      out[off] = f(a[off], op == 3 ? 0.f : b[off]);
     }
   }
 }
@@ -167,7 +215,7 @@ __global__ void __launch_bounds__(256) vb_terms_kernel(const float* __restrict__
   const int b = blockIdx.z, f = blockIdx.y;
   const float mask = latent_mask[b * F + f];
   if (mask == 0.0f) return;  // masked terms contribute exactly 0 (x*0 in the reference)
-  const long long tb = t[b];
+  const long long tb = check_t(t[b], n_steps);
   const Coef c = load_coef(tab, n_steps, tb);
   const float lv = c.logvar, tlv = c.post_logvar;
   const float log_scale = mul(0.5f, lv);
@@ -234,6 +282,28 @@ __global__ void __launch_bounds__(256) prior_bpd_kernel(const float* __restrict_
     atomicAdd(&acc[b], (double)r * (double)mask / ((double)per_frame * F) / 0.6931471805599453);
 }
 
+// host-mapped error flag, created on first use and published to the kernels through g_t_error
+int* g_t_error_host = nullptr;
+int ensure_error_flag() {
+  if (g_t_error_host) return 0;
+  int* h = nullptr;
+  cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocMapped);
+  if (e != cudaSuccess) {
+    set_error("sampler: cudaHostAlloc failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  *h = 0;
+  int* d = nullptr;
+  e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_t_error, &d, sizeof(d));
+  if (e != cudaSuccess) {
+    set_error("sampler: error flag setup failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  g_t_error_host = h;
+  return 0;
+}
+
 int grid_x_for(long long work_items, int other) {
   long long want = (work_items + 255) / 256;
   long long cap = (long long)num_sms() * 16 / (other > 0 ? other : 1);
@@ -252,8 +322,10 @@ extern "C" int vdm_sampler_step(int32_t mode, const float* x, const float* eps, 
                                 const float* tables, int32_t n_steps, int32_t B, int64_t per_batch,
                                 int32_t clip_denoised, float eta, float* sample, float* pred_xstart, float* mean,
                                 vdm_stream_t stream) {
-  VDM_REQUIRE(mode == 0 || mode == 1, "sampler_step: mode must be 0 (ancestral) or 1 (ddim)");
+  VDM_REQUIRE(mode >= 0 && mode <= 2, "sampler_step: mode must be 0 (ancestral), 1 (ddim) or 2 (ddim reverse)");
+  VDM_REQUIRE(mode != 2 || eta == 0.0f, "sampler_step: the reverse ODE is deterministic (eta must be 0)");
   VDM_REQUIRE(x && eps && noise && t && tables && sample, "sampler_step: NULL pointer");
+  if (int rc = ensure_error_flag()) return rc;
   VDM_REQUIRE(B > 0 && per_batch > 0 && n_steps > 0, "sampler_step: bad sizes");
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = per_batch % 4 == 0 && al(x) && al(eps) && al(noise) && al(sample) && (!pred_xstart || al(pred_xstart)) &&
@@ -274,6 +346,7 @@ extern "C" int vdm_sampler_step(int32_t mode, const float* x, const float* eps, 
 extern "C" int vdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables, int32_t n_steps,
                             int32_t B, int64_t per_batch, float* out, vdm_stream_t stream) {
   VDM_REQUIRE(x0 && noise && t && tables && out, "q_sample: NULL pointer");
+  if (int rc = ensure_error_flag()) return rc;
   VDM_REQUIRE(B > 0 && per_batch > 0, "q_sample: bad sizes");
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = per_batch % 4 == 0 && al(x0) && al(noise) && al(out);
@@ -286,10 +359,42 @@ extern "C" int vdm_q_sample(const float* x0, const float* noise, const int64_t* 
   return 0;
 }
 
+/* 1 if any sampler-family launch that has completed since the last call saw a timestep outside [0, n_steps);
+ * clears the flag.  Asynchronous like every CUDA error: synchronise first to be sure a given launch is covered. */
+extern "C" int vdm_sampler_error(void) {
+  if (!g_t_error_host) return 0;
+  const int v = *reinterpret_cast<volatile int*>(g_t_error_host);
+  if (v) *reinterpret_cast<volatile int*>(g_t_error_host) = 0;
+  return v;
+}
+
+extern "C" int vdm_lincomb(int32_t op, const float* a, const float* b, const int64_t* t, const float* tables,
+                           int32_t n_steps, int32_t row_a, int32_t row_b, int32_t B, int64_t per_batch, float* out,
+                           vdm_stream_t stream) {
+  VDM_REQUIRE(op >= 0 && op <= 3, "lincomb: unknown op %d", op);
+  VDM_REQUIRE(a && t && tables && out && (b || op == 3), "lincomb: NULL pointer");
+  if (int rc = ensure_error_flag()) return rc;
+  VDM_REQUIRE(row_a >= 0 && row_a < VDM_TAB_COUNT && (op == 3 || (row_b >= 0 && row_b < VDM_TAB_COUNT)),
+              "lincomb: table row out of range");
+  VDM_REQUIRE(B > 0 && per_batch > 0 && n_steps > 0, "lincomb: bad sizes");
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = per_batch % 4 == 0 && al(a) && (!b || al(b)) && al(out);
+  dim3 grid(grid_x_for(vec ? per_batch / 4 : per_batch, B), B);
+  if (vec)
+    lincomb_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
+                                                             per_batch, out);
+  else
+    lincomb_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
+                                                             per_batch, out);
+  VDM_AFTER_LAUNCH("lincomb");
+  return 0;
+}
+
 extern "C" int vdm_vb_terms(const float* x0, const float* x_t, const float* eps, const float* noise, const int64_t* t,
                             const float* tables, int32_t n_steps, const float* latent_mask, int32_t B, int32_t F,
                             int64_t per_frame, int32_t clip_denoised, double* acc, vdm_stream_t stream) {
   VDM_REQUIRE(x0 && x_t && eps && noise && t && tables && latent_mask && acc, "vb_terms: NULL pointer");
+  if (int rc = ensure_error_flag()) return rc;
   VDM_REQUIRE(B > 0 && F > 0 && per_frame > 0, "vb_terms: bad sizes");
   dim3 grid(grid_x_for(per_frame, B * F), F, B);
   vb_terms_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x_t, eps, noise, (const long long*)t, tables, n_steps,

@@ -4,7 +4,9 @@ Mirrors `improved_diffusion/gaussian_diffusion.py` of the reference for the infe
 same constructor, attributes (float64 numpy tables) and method signatures / return dict keys
 (`q_sample` :190, `p_mean_variance` :229, `p_sample` :403, `p_sample_loop[_progressive]`
 :450/:528, `ddim_sample` :597, `ddim_sample_loop[_progressive]` :670/:702, `_vb_terms_bpd`
-:750, `_prior_bpd` :909, `calc_bpd_loop[_subsampled]` :928/:1004).  Everything after the
+:750, `_prior_bpd` :909, `calc_bpd_loop[_subsampled]` :928/:1004, `q_posterior_mean_variance` :208,
+`_predict_xstart_from_eps / _from_xprev / _predict_eps_from_xstart` :374-396, `ddim_reverse_sample`
+:636).  Everything after the
 network call is ONE fused elementwise kernel per step (`vdm_sampler_step`, `vdm_vb_terms`),
 with the schedule coefficients gathered on the device from tables uploaded once -- the
 reference re-uploads eight 1000-entry float64 tables per step (:1019-1031).
@@ -69,7 +71,8 @@ def device_tables(diffusion=None, s_like=None, var_type=ModelVarType.FIXED_LARGE
                    POST_C1=s_like.post_c1, POST_C2=s_like.post_c2, MODEL_LOGVAR=s_like.model_logvar,
                    MODEL_VAR=s_like.model_var, ACP=s_like.acp, ACP_PREV=s_like.acp_prev,
                    POST_LOGVAR=s_like.post_logvar, SQRT_ACP=s_like.sqrt_acp, SQRT_1M_ACP=s_like.sqrt_1m_acp,
-                   LOG_1M_ACP=s_like.log_1m_acp)
+                   LOG_1M_ACP=s_like.log_1m_acp, POST_VAR=s_like.post_var, RECIP_POST_C1=s_like.recip_post_c1,
+                   POST_C2_DIV_C1=s_like.post_c2_div_c1, ACP_NEXT=s_like.acp_next)
     else:
         d = diffusion
         if var_type == ModelVarType.FIXED_LARGE:     # gaussian_diffusion.py:300-309
@@ -81,7 +84,9 @@ def device_tables(diffusion=None, s_like=None, var_type=ModelVarType.FIXED_LARGE
                    POST_C1=d.posterior_mean_coef1, POST_C2=d.posterior_mean_coef2, MODEL_LOGVAR=mlv, MODEL_VAR=mv,
                    ACP=d.alphas_cumprod, ACP_PREV=d.alphas_cumprod_prev, POST_LOGVAR=d.posterior_log_variance_clipped,
                    SQRT_ACP=d.sqrt_alphas_cumprod, SQRT_1M_ACP=d.sqrt_one_minus_alphas_cumprod,
-                   LOG_1M_ACP=d.log_one_minus_alphas_cumprod)
+                   LOG_1M_ACP=d.log_one_minus_alphas_cumprod, POST_VAR=d.posterior_variance,
+                   RECIP_POST_C1=1.0 / d.posterior_mean_coef1,
+                   POST_C2_DIV_C1=d.posterior_mean_coef2 / d.posterior_mean_coef1, ACP_NEXT=d.alphas_cumprod_next)
     n = len(src['ACP'])
     tab = np.zeros((_lib.TAB_COUNT, n), dtype=np.float64)
     for name, row in _lib.TAB.items():
@@ -145,8 +150,15 @@ class GaussianDiffusion:
         return out.contiguous(), attn
 
     # ---- forward process ---------------------------------------------------------------
+    def _lincomb(self, op, a, b, t, row_a, row_b='ACP'):
+        a = a.contiguous()
+        with th.cuda.device(a.device):
+            return ops.lincomb(op, a, None if b is None else b.contiguous(), t.long().contiguous(),
+                               self.tables(a.device), _lib.TAB[row_a], _lib.TAB[row_b])
+
     def q_mean_variance(self, x_start, t):
-        return (self._row('SQRT_ACP', t, x_start) * x_start, 1.0 - self._row('ACP', t, x_start),
+        """q(x_t | x_0) (gaussian_diffusion.py:171-188)."""
+        return (self._lincomb(3, x_start, None, t, 'SQRT_ACP'), 1.0 - self._row('ACP', t, x_start),
                 self._row('LOG_1M_ACP', t, x_start))
 
     def q_sample(self, x_start, t, noise=None):
@@ -155,17 +167,15 @@ class GaussianDiffusion:
         assert noise.shape == x_start.shape
         t = t.long()
         t = th.where(t < 0, t + self.num_timesteps, t)     # numpy-style negative index (the loop asks for t - 1 at t = 0)
-        return ops.q_sample(x_start.contiguous(), noise.contiguous(), t.contiguous(),
-                            self.tables(x_start.device))
+        with th.cuda.device(x_start.device):
+            return ops.q_sample(x_start.contiguous(), noise.contiguous(), t.contiguous(),
+                                self.tables(x_start.device))
 
     def q_posterior_mean_variance(self, x_start, x_t, t):
+        """q(x_{t-1} | x_t, x_0) (gaussian_diffusion.py:208-227)."""
         assert x_start.shape == x_t.shape
-        mean = self._row('POST_C1', t, x_t) * x_start + self._row('POST_C2', t, x_t) * x_t
-        return mean, self._row_var('posterior_variance', t, x_t), self._row('POST_LOGVAR', t, x_t)
-
-    def _row_var(self, attr, t, like):
-        v = th.from_numpy(getattr(self, attr)).to(like.device)[t].float()
-        return v.view(-1, *([1] * (like.dim() - 1))).expand(like.shape)
+        mean = self._lincomb(0, x_start, x_t, t, 'POST_C1', 'POST_C2')
+        return mean, self._row('POST_VAR', t, x_t), self._row('POST_LOGVAR', t, x_t)
 
     # ---- reverse process ---------------------------------------------------------------
     def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
@@ -177,25 +187,34 @@ class GaussianDiffusion:
         x = x.contiguous()
         eps, attn = self._eps(model, x, t, model_kwargs, return_attn_weights)
         pred, mean, scratch = th.empty_like(x), th.empty_like(x), th.empty_like(x)
-        ops.sampler_step(0, x, eps, x, t.long().contiguous(), self.tables(x.device), clip_denoised=clip_denoised,
-                         sample=scratch, pred_xstart=pred, mean=mean)
+        with th.cuda.device(x.device):
+            ops.sampler_step(0, x, eps, x, t.long().contiguous(), self.tables(x.device), clip_denoised=clip_denoised,
+                             sample=scratch, pred_xstart=pred, mean=mean)
         return {'mean': mean, 'variance': self._row('MODEL_VAR', t, x), 'log_variance': self._row('MODEL_LOGVAR', t, x),
                 'pred_xstart': pred, 'attn': attn}
 
     def _predict_xstart_from_eps(self, x_t, t, eps):
-        return self._row('SQRT_RECIP_ACP', t, x_t) * x_t - self._row('SQRT_RECIPM1_ACP', t, x_t) * eps
+        assert x_t.shape == eps.shape
+        return self._lincomb(1, x_t, eps, t, 'SQRT_RECIP_ACP', 'SQRT_RECIPM1_ACP')
+
+    def _predict_xstart_from_xprev(self, x_t, t, xprev):
+        """(xprev - coef2 * x_t) / coef1 in the reference's form (gaussian_diffusion.py:384-390)."""
+        assert x_t.shape == xprev.shape
+        return self._lincomb(1, xprev, x_t, t, 'RECIP_POST_C1', 'POST_C2_DIV_C1')
 
     def _predict_eps_from_xstart(self, x_t, t, pred_xstart):
-        return (self._row('SQRT_RECIP_ACP', t, x_t) * x_t - pred_xstart) / self._row('SQRT_RECIPM1_ACP', t, x_t)
+        return self._lincomb(2, x_t, pred_xstart, t, 'SQRT_RECIP_ACP', 'SQRT_RECIPM1_ACP')
 
     def _step(self, mode, model, x, t, clip_denoised, model_kwargs, eta=0.0, return_attn_weights=False):
         self._require_eps_model()
         x = x.contiguous()
         eps, attn = self._eps(model, x, t, model_kwargs, return_attn_weights)
-        noise = th.randn_like(x)                       # one draw per step, same order as the reference (:438, :628)
+        # one draw per step, same order as the reference (:438, :628); the reverse ODE draws nothing (:636-668)
+        noise = th.randn_like(x) if mode != 2 else x
         pred = th.empty_like(x)
-        sample = ops.sampler_step(mode, x, eps, noise, t.long().contiguous(), self.tables(x.device),
-                                  clip_denoised=clip_denoised, eta=eta, pred_xstart=pred)
+        with th.cuda.device(x.device):
+            sample = ops.sampler_step(mode, x, eps, noise, t.long().contiguous(), self.tables(x.device),
+                                      clip_denoised=clip_denoised, eta=eta, pred_xstart=pred)
         return sample, pred, attn
 
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
@@ -210,6 +229,14 @@ class GaussianDiffusion:
         if denoised_fn is not None:
             raise NotImplementedError('denoised_fn is a host callback')
         sample, pred, _ = self._step(1, model, x, t, clip_denoised, model_kwargs, eta=eta)
+        return {'sample': sample, 'pred_xstart': pred}
+
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """x_{t+1} from x_t with the DDIM reverse ODE (gaussian_diffusion.py:636-668)."""
+        assert eta == 0.0, 'Reverse ODE only for deterministic path'
+        if denoised_fn is not None:
+            raise NotImplementedError('denoised_fn is a host callback')
+        sample, pred, _ = self._step(2, model, x, t, clip_denoised, model_kwargs)
         return {'sample': sample, 'pred_xstart': pred}
 
     def _loop(self, step_fn, model, shape, noise, device, progress):
@@ -227,6 +254,7 @@ class GaussianDiffusion:
                 out = step_fn(img, t)
             yield out
             img = out['sample']
+        ops.check_timesteps()
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                   model_kwargs=None, latent_mask=None, device=None, progress=False,
@@ -320,16 +348,19 @@ class GaussianDiffusion:
         eps, _ = self._eps(model, x_t, t, model_kwargs)
         tl = t.long().contiguous()
         acc = th.zeros(x_t.shape[0], 3, device=x_t.device, dtype=th.float64)
-        ops.vb_terms(x_start, x_t, eps, eps, tl, self.tables(x_t.device), self._frame_mask(latent_mask, x_t),
-                     clip_denoised, acc)
         pred, scratch = th.empty_like(x_t), th.empty_like(x_t)
-        ops.sampler_step(0, x_t, eps, x_t, tl, self.tables(x_t.device), clip_denoised=clip_denoised, sample=scratch,
-                         pred_xstart=pred)
+        with th.cuda.device(x_t.device):
+            ops.vb_terms(x_start, x_t, eps, eps, tl, self.tables(x_t.device), self._frame_mask(latent_mask, x_t),
+                         clip_denoised, acc)
+            ops.sampler_step(0, x_t, eps, x_t, tl, self.tables(x_t.device), clip_denoised=clip_denoised,
+                             sample=scratch, pred_xstart=pred)
         return {'output': acc[:, 0].float(), 'pred_xstart': pred}
 
     def _prior_bpd(self, x_start, latent_mask=None):
         acc = th.zeros(x_start.shape[0], device=x_start.device, dtype=th.float64)
-        ops.prior_bpd(x_start.contiguous(), self.tables(x_start.device), self._frame_mask(latent_mask, x_start), acc)
+        with th.cuda.device(x_start.device):
+            ops.prior_bpd(x_start.contiguous(), self.tables(x_start.device), self._frame_mask(latent_mask, x_start),
+                          acc)
         return acc.float()
 
     def calc_bpd_loop_subsampled(self, model, x_start, clip_denoised=True, model_kwargs=None, latent_mask=None,
@@ -353,10 +384,10 @@ class GaussianDiffusion:
         for i, t in enumerate(t_seq):
             t_batch = th.tensor(t, device=device).long() if two_d else th.full((B,), int(t), device=device, dtype=th.long)
             noise = th.randn_like(x_start)             # one draw per t (:970)
-            ops.q_sample(x_start, noise, t_batch, tab, out=x_t)
-            with th.no_grad():
+            with th.cuda.device(device), th.no_grad():
+                ops.q_sample(x_start, noise, t_batch, tab, out=x_t)
                 eps, _ = self._eps(model, x_t, t_batch, model_kwargs)
-            ops.vb_terms(x_start, x_t, eps, noise, t_batch, tab, fmask, clip_denoised, acc[i])
+                ops.vb_terms(x_start, x_t, eps, noise, t_batch, tab, fmask, clip_denoised, acc[i])
         acc = acc.permute(1, 0, 2).float()
         prior = self._prior_bpd(x_start, latent_mask=latent_mask)
         vb = acc[:, :, 0].contiguous()

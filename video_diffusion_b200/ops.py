@@ -170,37 +170,63 @@ def attn_weights_mean(qkv, n_outer, n_inner, outer_stride, inner_stride, seq_str
         ptr(r_k), ptr(mask), int(pad_interact), ptr(out), stream()), 'vdm_attn_weights_mean'))
 
 
+_F32, _I64 = torch.float32, torch.int64
+
+
+def check_timesteps():
+    """Raise the reference's IndexError if a completed sampler-family launch saw a timestep outside its schedule
+    tables (the kernels clamp and record instead of reading out of bounds).  Asynchronous like any CUDA error:
+    called at the start of every sampler-family op and after explicit synchronisation points."""
+    if _lib.load().vdm_sampler_error():
+        raise IndexError('timestep outside [0, num_timesteps) reached a libvdm sampler kernel (pass SpacedDiffusion '
+                         'indices, not original timesteps)')
+
+
 def sampler_step(mode, x, eps, noise, t, tables, clip_denoised=True, eta=0.0, sample=None, pred_xstart=None,
                  mean=None):
+    check_timesteps()
     B = x.shape[0]
     per_batch = x.numel() // B
     if sample is None:
         sample = torch.empty_like(x)
     _timed('sampler_step', lambda: check(_lib.load().vdm_sampler_step(
-        mode, ptr(x), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B, per_batch, int(clip_denoised),
-        float(eta), ptr(sample), ptr(pred_xstart), ptr(mean), stream()), 'vdm_sampler_step'),
-           nbytes=_nbytes(x, eps, noise, sample, pred_xstart, mean))
+        mode, ptr(x, _F32), ptr(eps, _F32), ptr(noise, _F32), ptr(t, _I64), ptr(tables, _F32), tables.shape[1], B,
+        per_batch, int(clip_denoised), float(eta), ptr(sample, _F32), ptr(pred_xstart, _F32), ptr(mean, _F32), stream()),
+        'vdm_sampler_step'), nbytes=_nbytes(x, eps, noise, sample, pred_xstart, mean))
     return sample
 
 
 def q_sample(x0, noise, t, tables, out=None):
+    check_timesteps()
     B = x0.shape[0]
     if out is None:
         out = torch.empty_like(x0)
-    check(_lib.load().vdm_q_sample(ptr(x0), ptr(noise), ptr(t), ptr(tables), tables.shape[1], B, x0.numel() // B,
-                                   ptr(out), stream()), 'vdm_q_sample')
+    check(_lib.load().vdm_q_sample(ptr(x0, _F32), ptr(noise, _F32), ptr(t, _I64), ptr(tables, _F32), tables.shape[1], B,
+                                   x0.numel() // B, ptr(out, _F32), stream()), 'vdm_q_sample')
+    return out
+
+
+def lincomb(op, a, b, t, tables, row_a, row_b=0, out=None):
+    """Per-row linear combination with schedule coefficients gathered on the device (include/vdm.h: vdm_lincomb)."""
+    check_timesteps()
+    B = a.shape[0]
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.load().vdm_lincomb(op, ptr(a, _F32), ptr(b, _F32), ptr(t, _I64), ptr(tables, _F32), tables.shape[1],
+                                  row_a, row_b, B, a.numel() // B, ptr(out, _F32), stream()), 'vdm_lincomb')
     return out
 
 
 def vb_terms(x0, x_t, eps, noise, t, tables, latent_mask, clip_denoised, acc):
+    check_timesteps()
     B, F = x0.shape[0], x0.shape[1]
     per_frame = x0.numel() // (B * F)
-    check(_lib.load().vdm_vb_terms(ptr(x0), ptr(x_t), ptr(eps), ptr(noise), ptr(t), ptr(tables), tables.shape[1],
-                                   ptr(latent_mask), B, F, per_frame, int(clip_denoised), ptr(acc), stream()),
-          'vdm_vb_terms')
+    check(_lib.load().vdm_vb_terms(ptr(x0, _F32), ptr(x_t, _F32), ptr(eps, _F32), ptr(noise, _F32), ptr(t, _I64),
+                                   ptr(tables, _F32), tables.shape[1], ptr(latent_mask, _F32), B, F, per_frame,
+                                   int(clip_denoised), ptr(acc, torch.float64), stream()), 'vdm_vb_terms')
 
 
 def prior_bpd(x0, tables, latent_mask, acc):
     B, F = x0.shape[0], x0.shape[1]
-    check(_lib.load().vdm_prior_bpd(ptr(x0), ptr(tables), tables.shape[1], ptr(latent_mask), B, F,
-                                    x0.numel() // (B * F), ptr(acc), stream()), 'vdm_prior_bpd')
+    check(_lib.load().vdm_prior_bpd(ptr(x0, _F32), ptr(tables, _F32), tables.shape[1], ptr(latent_mask, _F32), B, F,
+                                    x0.numel() // (B * F), ptr(acc, torch.float64), stream()), 'vdm_prior_bpd')

@@ -12,14 +12,27 @@ import torch
 from .script_util import args_to_dict, create_video_model_and_diffusion, video_model_and_diffusion_defaults
 
 
-def load_checkpoint(checkpoint_path, device, use_ddim=False, timestep_respacing='', compute_dtype=None):
+def _load(checkpoint_path, trust_pickle=False):
+    """A checkpoint holds tensors, a plain config dict and an int: `weights_only=True` loads that without executing
+    pickled code.  Checkpoints whose config was saved as an argparse.Namespace (or anything else the safe loader
+    rejects) need the explicit `trust_pickle=True` opt-in."""
+    try:
+        return torch.load(checkpoint_path, map_location='cpu', weights_only=True)
+    except pickle.UnpicklingError:
+        if not trust_pickle:
+            raise
+        return torch.load(checkpoint_path, map_location='cpu', weights_only=False)
+
+
+def load_checkpoint(checkpoint_path, device, use_ddim=False, timestep_respacing='', compute_dtype=None,
+                    trust_pickle=False):
     """Reads a reference checkpoint `{'state_dict', 'config', 'step'}` and builds the B200 model + diffusion from its
     config (test_util.py:31-62).  Configs written before `enforce_position_invariance` / `cond_emb_type` existed get
     the reference's back-compat defaults.  Returns ((model, diffusion), model_args)."""
     default_model_configs = {'enforce_position_invariance': False, 'cond_emb_type': 'channel'}
-    data = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
+    data = _load(checkpoint_path, trust_pickle)
     state_dict = data['state_dict']
-    model_args = dict(data['config'])
+    model_args = dict(vars(data['config']) if isinstance(data['config'], argparse.Namespace) else data['config'])
     model_args.update({'use_ddim': use_ddim, 'timestep_respacing': timestep_respacing})
     for k, v in default_model_configs.items():
         model_args.setdefault(k, v)
@@ -46,7 +59,7 @@ def get_model_results_path(args, postfix=''):
     checkpoint_path = Path(args.checkpoint_path)
     name = f'{checkpoint_path.stem}'
     if name.endswith('latest'):
-        step = torch.load(args.checkpoint_path, map_location='cpu', weights_only=False)['step']
+        step = _load(args.checkpoint_path, getattr(args, 'trust_pickle', False))['step']
         name += f'_{step}'
     if postfix != '':
         name += postfix

@@ -132,6 +132,7 @@ class UNetModel(nn.Module):
         self._gn('out.0', ch)
         self._conv('out.2', model_channels, out_channels, 3, zero=True)
         self._packed = None
+        self._packed_version = -1
         self._workspaces = {}
 
     # ---- parameter registration under the reference's names ------------------------------------
@@ -188,6 +189,16 @@ class UNetModel(nn.Module):
     def _invalidate(self):
         self._packed = None
         self._workspaces = {}
+
+    def _param_version(self):
+        """Sum of the parameters' in-place version counters: any `p.data.copy_()`, EMA swap or optimiser-style update
+        after the first forward changes it, and the packed bf16 weights (and the graphs built on them) are redone."""
+        return sum(p._version for p in self.parameters())
+
+    def repack(self):
+        """Force re-packing of the kernel-side weights (also happens automatically, see _param_version)."""
+        self._invalidate()
+        return self
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -607,7 +618,7 @@ class UNetModel(nn.Module):
         if self.overlap_rpe_tables and ops.PROFILE is None:
             main = torch.cuda.current_stream()
             if ws.side is None:
-                ws.side = torch.cuda.Stream()
+                ws.side = torch.cuda.Stream(device=ws.dev)
                 ws.ev_fork, ws.ev_emb, ws.ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             ws.ev_fork.record(main)
             ws.side.wait_event(ws.ev_fork)
@@ -710,14 +721,24 @@ class UNetModel(nn.Module):
                  out_nchw=True)
         return ws.out
 
-    def _execute(self, x, x0, obs, lat, kinda, t, frame_indices, T_attn, per_frame_t=None, clone=True,
-                 attn_log=None):
+    def _execute(self, x, *args, **kwargs):
+        """Every libvdm launch goes to the current stream of the current device: make that the tensors' device."""
+        if not x.is_cuda:
+            raise RuntimeError('the B200 model needs CUDA tensors; there is no CPU fallback')
+        with torch.cuda.device(x.device):
+            return self._execute_on_device(x, *args, **kwargs)
+
+    def _execute_on_device(self, x, x0, obs, lat, kinda, t, frame_indices, T_attn, per_frame_t=None, clone=True,
+                           attn_log=None):
         if self.training:
             raise NotImplementedError('the B200 model is inference-only: call .eval()')
         if not x.is_cuda:
             raise RuntimeError('the B200 model needs CUDA tensors; there is no CPU fallback')
-        if self._packed is None:
+        ver = self._param_version()
+        if self._packed is None or ver != self._packed_version:
+            self._invalidate()
             self._pack()
+            self._packed_version = ver
         B, F, Cc, H, W = x.shape
         if Cc != 3:
             raise NotImplementedError('3-channel frames only')
