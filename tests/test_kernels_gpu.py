@@ -368,7 +368,7 @@ def test_groupnorm_channels_with_large_mean():
     o = ops()
     # temporal kernels (register-resident and general)
     for (B, T, HW, Cc) in [(2, 20, 16, 384), (2, 6, 16, 192)]:
-        x = rnd(B, T, HW, Cc, seed=1) * 0.5 + 50.0 * torch.sign(rnd(Cc, seed=9))
+        x = rnd(B, T, HW, Cc, seed=1) * 0.5 + 50.0 * torch.sign(rnd(32, seed=9)).repeat_interleave(Cc // 32)   # per GROUP
         gamma, beta = rnd(Cc, seed=2), rnd(Cc, seed=3)
         xr = x.permute(0, 2, 3, 1).reshape(B * HW, Cc, T)
         ref = F.group_norm(xr.double(), 32, gamma.double(), beta.double(), eps=1e-5).view(B, HW, Cc, T).permute(0, 3, 1, 2)
@@ -380,7 +380,7 @@ def test_groupnorm_channels_with_large_mean():
     n, H, W, C = 3, 16, 16, 128
     x = (rnd(n, C, H, W, seed=4) * 0.5).bfloat16()
     w = torch.eye(C, device='cuda').bfloat16()
-    bias = 50.0 * torch.sign(rnd(C, seed=5))
+    bias = 50.0 * torch.sign(rnd(32, seed=5)).repeat_interleave(C // 32)
     h = torch.empty(n * H * W, C, device='cuda')
     st = torch.zeros(n, 2, C, device='cuda', dtype=torch.int64)
     o.gemm(nhwc(x.float()).bfloat16(), w, C, n_img=n, H=H, W=W, taps=1, bias=bias, out_f32=h, stats_out=st)
