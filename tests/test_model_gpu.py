@@ -173,20 +173,22 @@ def test_unconditioned_video_model_matches_reference(golden, dtype):
 
 
 def test_in_place_weight_update_repacks(golden):
-    """Packed bf16 weights and CUDA graphs follow in-place parameter updates (EMA swap, p.data.copy_)."""
+    """Packed bf16 weights and CUDA graphs follow in-place parameter updates (p.mul_ / p.copy_ under no_grad: detected
+    through the version counters; writes through a `.data` alias need the documented model.repack())."""
     case = cases.UNET_CASES[0]
     model, _ = build_model(case['cfg'], golden, torch.bfloat16)
     inp = cases.unet_case_inputs(case)
     kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
     with torch.no_grad():
         a, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
-        w = model.out._modules['2'].weight
-        old = w.data.clone()
-        w.data.mul_(0.5)
-        model.out._modules['2'].bias.data.mul_(0.5)
+        w, bias = model.out._modules['2'].weight, model.out._modules['2'].bias
+        old = w.detach().clone()
+        w.mul_(0.5)
+        bias.mul_(0.5)
         b, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
-        w.data.copy_(old)
-        model.out._modules['2'].bias.data.mul_(2.0)
+        w.data.copy_(old)                     # a .data alias: invisible to the version counter
+        bias.data.mul_(2.0)
+        model.repack()
         c, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
     assert torch.allclose(b, 0.5 * a, rtol=2e-2, atol=1e-3) and not torch.allclose(b, a, rtol=1e-2, atol=1e-3)
     assert torch.equal(c, a)

@@ -191,12 +191,15 @@ class UNetModel(nn.Module):
         self._workspaces = {}
 
     def _param_version(self):
-        """Sum of the parameters' in-place version counters: any `p.data.copy_()`, EMA swap or optimiser-style update
-        after the first forward changes it, and the packed bf16 weights (and the graphs built on them) are redone."""
-        return sum(p._version for p in self.parameters())
+        """Fingerprint of the parameters: in-place version counters (`p.copy_()`, `p.mul_()`, optimiser / EMA updates
+        under no_grad bump them) and storage addresses (`p.data = new`, `vector_to_parameters`).  When it changes after
+        the first forward the packed bf16 weights and the graphs built on them are redone.  Writes through a `.data`
+        alias (`p.data.mul_()`) bypass autograd's version counter and cannot be seen: call `repack()` after those."""
+        return hash(tuple((p._version, p.data_ptr()) for p in self.parameters()))
 
     def repack(self):
-        """Force re-packing of the kernel-side weights (also happens automatically, see _param_version)."""
+        """Re-pack the kernel-side weights from the current parameters (needed only after writes through `.data`
+        aliases; every other update is detected, see _param_version)."""
         self._invalidate()
         return self
 
