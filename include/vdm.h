@@ -93,9 +93,19 @@ typedef struct {
   int32_t prob_a_cols;
   int64_t prob_w_rows;
   int64_t prob_out_stride;
+  const float* a1_coef; /* bf16 kernel, taps == 9 stride 1: GroupNorm-apply (+ scale/shift) + SiLU fused into the A1
+                           operand path (ResBlock `in_layers` / `out_layers`, unet.py:185-198, nn.py:10-17).  [n_img][C1]
+                           pairs (a, b) from vdm_gn_coef: a1 then holds the RAW (un-normalised) bf16 activation and the
+                           kernel's transform warps rewrite every activation tile in shared memory, between the TMA
+                           load and the MMA, to act(a * x + b); conv padding stays zero.  NULL = A1 used as is.
+                           Only the halo kernels take it: vdm_gemm_fused_norm_supported() tells; other shapes are an
+                           error, never a silent slow path */
+  int32_t a1_act;       /* with a1_coef: 1 = SiLU after the affine, 0 = affine only */
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
+/* 1 if vdm_gemm would run `args` (with a1_coef set) on a kernel that has the fused-normalisation transform stage */
+int vdm_gemm_fused_norm_supported(const vdm_gemm_args* args);
 
 /* ---- GroupNorm32 (+SiLU, + scale/shift), producer of GEMM A operands --------------------
  * Replaces GroupNorm32 (nn.py:15-17) + SiLU (nn.py:10-12) + `h*(1+scale)+shift`
@@ -129,6 +139,14 @@ typedef struct {
 } vdm_gn_apply_args;
 
 int vdm_gn_apply(const vdm_gn_apply_args* args, vdm_stream_t stream);
+
+/* Per-(image, channel) affine form of GroupNorm32 (+ scale/shift): coef[n][c] = (a, b) with
+ *   a = rstd_g * gamma_c * (1 + scale_nc),   b = (beta_c - mean_g * rstd_g * gamma_c) * (1 + scale_nc) + shift_nc
+ * from the same statistics tables vdm_gn_apply takes (two sources = channel concat).  A tiny launch (n_img blocks); its
+ * output feeds vdm_gemm_args.a1_coef, so the normalised activation is never written to memory. */
+int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, const void* stats2, int32_t stats2_dtype,
+                int32_t C2, int32_t n_img, int32_t HW, const float* gamma, const float* beta,
+                const float* scale_shift, int32_t ld_ss, float* coef, vdm_stream_t stream);
 
 /* GroupNorm over (C/32 channels x T frames) per (b, pixel): the temporal-attention norm
  * (unet.py:473-474 on x.reshape(B*D, C, T)).  x: [B][T][HW][C] fp32. */

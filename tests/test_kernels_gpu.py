@@ -163,6 +163,86 @@ def test_conv3x3_halo_kernel(case, monkeypatch):
     assert relerr(out_b, ref) < 6e-3
 
 
+@pytest.mark.parametrize('tmode', ['1', '2'], ids=['pair_or_t', 'transposed'])
+@pytest.mark.parametrize('case', [c for c in HALO_CASES if c[4] % 128 == 0],
+                         ids=lambda c: 'n%d_%dx%d_c%d_n%d_c2_%d_res%d' % c)
+def test_conv3x3_fused_groupnorm_silu(case, tmode, monkeypatch):
+    """GroupNorm-apply (+ scale/shift) + SiLU fused into the conv's operand path (`a1_coef`: the transform warps of the
+    halo kernels rewrite every activation slot in shared memory) against (a) the standalone gn_apply pass feeding the
+    same kernel -- BIT-EXACT, the two paths compute the same bf16 operand -- and (b) group_norm + silu + conv2d in
+    torch.  Covers the pair, transposed, wide-slot and interleaved 8x8 kernels, the fused 1x1 skip operand (passes
+    through untransformed), residuals, ragged pairs and the zero padding (must stay zero after the affine)."""
+    n, H, W, C1, N, C2, use_res = case
+    o = ops()
+    monkeypatch.setenv('VDM_GEMM_HALO', '2')
+    monkeypatch.setenv('VDM_GEMM_HALO_T', tmode)
+    h1 = (rnd(n, C1, H, W, seed=1) * 1.5 + 0.4).bfloat16()                 # raw conv1 output, bf16 only
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
+    bias = rnd(N, seed=3)
+    res = rnd(n * H * W, N, seed=4) if use_res else None
+    gamma, beta = 1 + 0.2 * rnd(C1, seed=7), 0.3 * rnd(C1, seed=8)
+    ss = rnd(n, 2 * C1, seed=9, scale=0.3)
+    wp, a2 = pack_w(w), None
+    if C2:
+        x2 = rnd(n, C2, H, W, seed=5).bfloat16().float()
+        w2 = rnd(N, C2, 1, 1, seed=6, scale=C2 ** -0.5).bfloat16().float()
+        wp = torch.cat([wp, w2.view(N, C2)], dim=1).contiguous()
+        a2 = nhwc(x2).bfloat16()
+    h1r = nhwc(h1.float()).bfloat16()
+    st = torch.zeros(n, 2, C1, device='cuda', dtype=torch.float64)
+    o.gn_stats(h1r.float(), n, H * W, st)
+    kw = dict(n_img=n, H=H, W=W, taps=9, a2=a2, bias=bias, residual=res, C1=C1)
+    out_u = torch.full((n * H * W, N), float('nan'), device='cuda')
+    st_u = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+    assert o.gemm_fused_norm_supported(h1r, wp.bfloat16(), N, out_f32=out_u, stats_out=st_u, **kw)
+    # (a) standalone normalisation pass + the same conv kernel
+    a_norm = torch.empty(n * H * W, C1, device='cuda', dtype=torch.bfloat16)
+    o.gn_apply(h1r, None, n, H, W, a_norm, stats1=st, gamma=gamma, beta=beta, scale_shift=ss, silu=True)
+    o.gemm(a_norm, wp.bfloat16(), N, out_f32=out_u, stats_out=st_u, **kw)
+    # fused: raw operand + coefficient table
+    coef = torch.empty(n, C1, 2, device='cuda')
+    o.gn_coef(st, None, n, H * W, gamma, beta, coef, scale_shift=ss)
+    out_f = torch.full((n * H * W, N), float('nan'), device='cuda')
+    st_f = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+    o.gemm(h1r, wp.bfloat16(), N, out_f32=out_f, stats_out=st_f, a1_coef=coef, a1_act=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_u), float((out_f - out_u).abs().max())
+    assert torch.equal(st_f, st_u)
+    # (b) torch
+    y = F.group_norm(h1.float(), 32, gamma, beta, eps=1e-5) * (1 + ss[:, :C1, None, None]) + ss[:, C1:, None, None]
+    ref = F.conv2d(F.silu(y).bfloat16().float(), w, bias, padding=1)
+    if C2:
+        ref = ref + F.conv2d(x2, w2)
+    ref = nhwc(ref) + (res if use_res else 0)
+    assert relerr(out_f, ref) < 6e-3          # the operand's bf16 rounding (tanh-form SiLU vs torch's) only
+    # bf16 output variant (conv1-style) and affine-only (a1_act = 0)
+    out_b = torch.empty(n * H * W, N, device='cuda', dtype=torch.bfloat16)
+    st_b = torch.zeros_like(st_f)
+    o.gemm(h1r, wp.bfloat16(), N, n_img=n, H=H, W=W, taps=9, a2=a2, bias=bias, out_bf16=out_b, stats_out=st_b,
+           a1_coef=coef, a1_act=False, C1=C1)
+    refb = F.conv2d(y.bfloat16().float(), w, bias, padding=1)
+    if C2:
+        refb = refb + F.conv2d(x2, w2)
+    assert relerr(out_b, nhwc(refb)) < 8e-3
+
+
+def test_fused_groupnorm_unsupported_shapes_raise():
+    """a1_coef on a shape / epilogue the transform-stage kernels do not cover is an error, not a silent slow path."""
+    o = ops()
+    n, H, W, C1, N = 2, 4, 4, 64, 64
+    x = rnd(n * H * W, C1, seed=1).bfloat16()
+    w = rnd(N, 9 * C1, seed=2).bfloat16()
+    coef = torch.ones(n, C1, 2, device='cuda')
+    out = torch.empty(n * H * W, N, device='cuda')
+    st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+    assert not o.gemm_fused_norm_supported(x, w, N, n_img=n, H=H, W=W, taps=9, out_f32=out)
+    with pytest.raises(RuntimeError):
+        o.gemm(x, w, N, n_img=n, H=H, W=W, taps=9, out_f32=out, a1_coef=coef)
+    with pytest.raises(RuntimeError):        # linears never take it
+        o.gemm(x, w[:, :C1].contiguous(), N, n_img=n * H * W, H=1, W=1, taps=1, out_f32=out, a1_coef=coef)
+    del st
+
+
 @pytest.mark.parametrize('halo', ['0', '2'], ids=['plain', 'halo'])
 @pytest.mark.parametrize('case', [(2, 16, 16, 128, 128), (3, 32, 32, 64, 256), (160, 8, 8, 128, 128), (5, 64, 64, 128, 256),
                                   (3, 128, 128, 64, 128), (7, 32, 64, 64, 384), (1, 16, 32, 64, 128), (3, 16, 32, 128, 256)])

@@ -17,7 +17,7 @@ TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOG
            POST_C2_DIV_C1=14, ACP_NEXT=15)
 TAB_COUNT = 16
 
-EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gn_stats', 'vdm_gn_apply',
+EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gn_stats', 'vdm_gn_apply', 'vdm_gn_coef',
            'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
            'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_error', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_lincomb',
            'vdm_vb_terms', 'vdm_prior_bpd']
@@ -31,7 +31,8 @@ class GemmArgs(C.Structure):
                 ('rowbias', _vp), ('ld_rowbias', _i32), ('residual', _vp), ('ld_res', _i32), ('out_f32', _vp),
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
                 ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp), ('n_prob', _i32),
-                ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64)]
+                ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64), ('a1_coef', _vp),
+                ('a1_act', _i32)]
 
 
 class GnApplyArgs(C.Structure):
@@ -61,6 +62,8 @@ def load():
         'vdm_gemm': [C.POINTER(GemmArgs), _vp],
         'vdm_gn_stats': [_vp, _i32, _i32, _i32, _vp, _vp],
         'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
+        'vdm_gemm_fused_norm_supported': [C.POINTER(GemmArgs)],
+        'vdm_gn_coef': [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
         'vdm_gn_temporal': [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
         'vdm_add_spatial_encoding': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
         'vdm_cond_mix': [_vp] * 6 + [_i32] * 5 + [_vp, _i32, _vp, _vp, _vp],

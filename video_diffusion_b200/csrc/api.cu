@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream);
+int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe = nullptr);
 void gemm_tc_set_trace(void* buf);
 int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream);
 
@@ -32,8 +32,16 @@ extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->a1 && a->w, "gemm: NULL operand");
   VDM_REQUIRE(a->out_f32 || a->out_bf16, "gemm: no output");
   VDM_REQUIRE(a->n_img > 0 && a->H > 0 && a->W > 0 && a->N > 0, "gemm: bad geometry");
+  VDM_REQUIRE(a->a1_coef == nullptr || a->dtype == VDM_BF16, "gemm: a1_coef (fused normalisation) is bf16-kernel only");
   if (a->dtype == VDM_BF16) return vdm::gemm_tc(a, (cudaStream_t)stream);
   if (a->dtype == VDM_F32) return vdm::gemm_simt(a, (cudaStream_t)stream);
   vdm::set_error("gemm: unknown dtype %d", a->dtype);
   return -1;
+}
+
+extern "C" int vdm_gemm_fused_norm_supported(const vdm_gemm_args* a) {
+  if (a == nullptr || a->dtype != VDM_BF16 || a->taps != 9 || a->a1_mode != 0 || a->out_nchw) return 0;
+  int ok = 0;
+  if (vdm::gemm_tc(a, nullptr, &ok) != 0) return 0;
+  return ok;
 }

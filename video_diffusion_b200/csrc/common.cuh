@@ -59,6 +59,15 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // exact-ish SiLU used where the reference computes x*sigmoid(x) in fp32
 __device__ __forceinline__ float silu_precise(float x) { return x * (1.0f / (1.0f + expf(-x))); }
 
+// x*sigmoid(x) with sigmoid(x) = 0.5 + 0.5*tanh(x/2): ONE MUFU op per element (tanh.approx, rel. error ~2^-11, well
+// below the bf16 rounding of the result) instead of ex2 + rcp.  Shared by gn_apply and the GEMM's transform warps, so
+// the fused and the standalone GroupNorm-apply produce bit-identical bf16 operands.
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
 template <typename T>
 __device__ __forceinline__ void store_elem(T* p, float v);
 template <>

@@ -54,15 +54,6 @@ struct ApplyParams {
 // of pixels, so its per-channel multiplier / offset live in registers for the whole loop.
 // dynamic smem: 2*C doubles (per-channel sums) + 64 floats (group mean / rstd)
 // MODE: 0 plain, 1 nearest-x2, 2 stride-2 parity planes; RAW / COPY: optional extra outputs.
-__device__ __forceinline__ float silu_tanh(float x) {
-  // x*sigmoid(x) with sigmoid(x) = 0.5 + 0.5*tanh(x/2): ONE MUFU op per element (tanh.approx, rel. error
-  // ~2^-11, well below the bf16 rounding of the result) instead of ex2 + rcp -- this kernel would
-  // otherwise be bound by the 16/clk/SM special-function units rather than by HBM.
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return x * fmaf(0.5f, t, 0.5f);
-}
-
 template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -217,6 +208,58 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
     float x[8];
     load8(src + (size_t)pix * ld, x);
     process(pix, x);
+  }
+}
+
+// The prologue of gn_apply_kernel as a kernel of its own: per-(image, channel) multiplier / offset of GroupNorm32
+// (+ scale/shift).  Same arithmetic in the same order, so a consumer that applies act(a*x + b) itself (the GEMM's
+// transform warps) produces bit-identical operands.  grid = n_img, dynamic smem as gn_apply_kernel.
+__global__ void __launch_bounds__(256) gn_coef_kernel(const void* st1, int st_kind, int C1, const void* st2, int st_kind2,
+                                                       int C2, int HW, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ ss,
+                                                       int ld_ss, float2* __restrict__ coef) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int C = C1 + C2, cpg = C / 32;
+  double* chs = reinterpret_cast<double*>(sm_raw);
+  double* chss = chs + C;
+  float* gmean = reinterpret_cast<float*>(chss + C);
+  float* grstd = gmean + 32;
+  const int n = blockIdx.x;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const bool first = ch < C1;
+    const void* st = first ? st1 : st2;
+    const int Cs = first ? C1 : C2, cs = first ? ch : ch - C1;
+    const size_t i0 = (size_t)n * 2 * Cs + cs;
+    if ((first ? st_kind : st_kind2) == VDM_F64) {
+      chs[ch] = reinterpret_cast<const double*>(st)[i0];
+      chss[ch] = reinterpret_cast<const double*>(st)[i0 + Cs];
+    } else {
+      chs[ch] = (double)reinterpret_cast<const long long*>(st)[i0] * (1.0 / 16777216.0);
+      chss[ch] = (double)reinterpret_cast<const long long*>(st)[i0 + Cs] * (1.0 / 16777216.0);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0, q = 0;
+    for (int j = 0; j < cpg; ++j) { s += chs[threadIdx.x * cpg + j]; q += chss[threadIdx.x * cpg + j]; }
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    gmean[threadIdx.x] = (float)mean;
+    grstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g = ch / cpg;
+    float a = grstd[g] * __ldg(gamma + ch);
+    float b = __ldg(beta + ch) - gmean[g] * a;
+    if (ss != nullptr) {
+      const float sc = 1.0f + ss[(size_t)n * ld_ss + ch];
+      a *= sc;
+      b = b * sc + ss[(size_t)n * ld_ss + C + ch];
+    }
+    coef[(size_t)n * C + ch] = make_float2(a, b);
   }
 }
 
@@ -630,6 +673,21 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
 #undef VDM_GN_BY_MODE
 #undef VDM_GN_LAUNCH
   VDM_AFTER_LAUNCH("gn_apply");
+  return 0;
+}
+
+extern "C" int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, const void* stats2, int32_t stats2_dtype,
+                           int32_t C2, int32_t n_img, int32_t HW, const float* gamma, const float* beta,
+                           const float* scale_shift, int32_t ld_ss, float* coef, vdm_stream_t stream) {
+  const int C = C1 + C2;
+  VDM_REQUIRE(stats1 && gamma && beta && coef && (C2 == 0 || stats2), "gn_coef: NULL pointer");
+  VDM_REQUIRE(C % 32 == 0 && C <= 2048 && n_img > 0 && HW > 0, "gn_coef: unsupported channels %d+%d", C1, C2);
+  VDM_REQUIRE((stats_dtype == VDM_F64 || stats_dtype == VDM_I64) && (C2 == 0 || stats2_dtype == VDM_F64 || stats2_dtype == VDM_I64),
+              "gn_coef: bad stats dtype");
+  const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);
+  gn_coef_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(stats1, stats_dtype, C1, stats2, stats2_dtype, C2, HW, gamma,
+                                                            beta, scale_shift, ld_ss, reinterpret_cast<float2*>(coef));
+  VDM_AFTER_LAUNCH("gn_coef");
   return 0;
 }
 

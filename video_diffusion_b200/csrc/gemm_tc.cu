@@ -32,6 +32,10 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+// Kernels with the fused-normalisation stage (XF) add four transform warps (threads NUM_THREADS ..): they rewrite
+// every activation slot in shared memory, between the TMA load and the MMA, to act(a * x + b).
+constexpr int XF_WARPS = 4;
+constexpr int NUM_THREADS_XF = NUM_THREADS + 32 * XF_WARPS;
 // Diagnostics build (make TRACE=1): per-role cycle counters (vdm_gemm_set_trace) and the VDM_GEMM_DEBUG timing
 // experiments.  Off by default: the single MMA-issuing thread is the critical path and must stay branch-free.
 #ifdef VDM_GEMM_TRACE
@@ -62,6 +66,8 @@ struct TcParams {
   int ld_out, ld_out_bf16;
   int out_nchw;
   int64_t* stats_out;
+  const float2* xf_coef;       // XF kernels: per-(image, A1 channel) (a, b) of the fused GroupNorm-apply
+  int xf_act;                  // XF kernels: 1 = SiLU after the affine
   int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory
   int dbg;                     // diagnostics (VDM_GEMM_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs (results are garbage)
   unsigned long long* trace;   // diagnostics (vdm_gemm_set_trace): per-CTA wait / busy cycle counters, else NULL
@@ -253,6 +259,57 @@ constexpr int tmem_cols() {   // two accumulator stages, rounded up to the power
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// ===================== transform role (XF kernels): fused GroupNorm-apply + SiLU on the A operand =====================
+// One activation slot, in place.  The slot holds `rows` pixel rows of 128 B (64 bf16 channels), 128B-swizzled exactly as
+// TMA wrote them: the 16-byte column j of row r sits at r * 128 + ((j ^ (r & 7)) << 4).  Thread tid of the 128 owns the
+// logical column j = tid & 7 (channels 8j .. 8j+7 of the chunk: its eight (a, b) pairs stay in registers) and the rows
+// r = (tid >> 3) + 16 i, for which r & 7 -- hence the physical column -- is constant.  Row r is pixel
+// (yy, xx) = (r / W, r % W) of the halo box at image position (y_first + yy, xx + x_off); pixels outside the image are
+// the convolution's zero padding (TMA out-of-bounds fill) and must stay zero, so they are skipped.
+// ILV (8x8 level): box rows are (y, image, x)-ordered, r -> (r >> 4, r & 7); a thread's rows all belong to one image.
+template <bool ILV>
+__device__ __forceinline__ void xf_transform_slot(uint8_t* slot, int rows, int log2w, int W, int H, int y_first,
+                                                  int x_off, const float (&a)[8], const float (&b)[8], int act,
+                                                  int tid) {
+  const int j = tid & 7, r0 = tid >> 3;
+  uint8_t* const base = slot + ((j ^ (r0 & 7)) << 4);
+#pragma unroll 4
+  for (int r = r0; r < rows; r += 16) {
+    const int yy = ILV ? (r >> 4) : (r >> log2w);
+    const int xx = ILV ? (r & 7) : (r & (W - 1));
+    if ((unsigned)(y_first + yy) < (unsigned)H && (unsigned)(xx + x_off) < (unsigned)W) {
+      uint4* const ptr = reinterpret_cast<uint4*>(base + r * 128);
+      const uint4 v = *ptr;
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {       // bf16 -> fp32 is a 16-bit shift
+        float y0 = fmaf(__uint_as_float(w[i] << 16), a[2 * i], b[2 * i]);
+        float y1 = fmaf(__uint_as_float(w[i] & 0xffff0000u), a[2 * i + 1], b[2 * i + 1]);
+        if (act) {
+          y0 = silu_tanh(y0);
+          y1 = silu_tanh(y1);
+        }
+        o[i] = pack_bf16x2(y0, y1);
+      }
+      *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+// the thread's eight (a, b) pairs of one 64-channel chunk: coef = table row of the image + chunk * 64 + 8 * (tid & 7)
+__device__ __forceinline__ void xf_load_coef(const float2* coef, float (&a)[8], float (&b)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(coef) + i);
+    a[2 * i] = t.x; b[2 * i] = t.y; a[2 * i + 1] = t.z; b[2 * i + 1] = t.w;
+  }
+}
+// generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrive per warp
+__device__ __forceinline__ void xf_publish_fence() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
 }
 
 template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
@@ -913,15 +970,17 @@ struct HaloLayout {
   static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
-  static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
+  static constexpr int NUM_BARS = 3 * SA + 2 * SB + 4;               // + SA "slot transformed" barriers (XF)
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
-                                                                      const __grid_constant__ CUtensorMap tm_a2,
-                                                                      const __grid_constant__ CUtensorMap tm_w,
-                                                                      const TcParams p) {
+// XF: fused GroupNorm-apply.  Each CTA's activation box then signals that CTA's OWN a_full barrier (plain TMA load), its
+// four transform warps rewrite the slot and arrive on the LEADER's a_ready barrier (2 x 4 arrivals), which is what the
+// MMA thread waits for instead of a_full.
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, bool XF = false>
+__global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
+    gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
+                        const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(!ILV || M_SUB == 1, "interleaved 8x8 tiles are 128 rows");
   constexpr int CTA_ROWS = BLOCK_M * M_SUB;
@@ -938,6 +997,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SB + 4 + s); };   // XF: slot transformed (leader's copy)
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
@@ -949,10 +1009,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
   const int halo_rows = ILV ? p.H + 2 : CTA_ROWS / p.W + 2;
   const uint32_t halo_bytes = (uint32_t)(halo_rows * (ILV ? 2 * p.W : p.W)) * (BLOCK_K * 2);
 
-  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
+  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += blockDim.x)
     reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2 * SA + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int s = 0; s < SA; ++s) mbar_init(a_ready(s), 2 * XF_WARPS);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), EPI_WARPS * 2);
@@ -997,9 +1058,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
         for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(a_empty(sa), pa ^ 1u, 0);
-            if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * halo_bytes);
-            if constexpr (ILV) tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, img, -1, 0);
-            else tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            if constexpr (XF) {   // this CTA's box signals this CTA's barrier: its transform warps go first
+              mbar_expect_tx(a_full(sa), halo_bytes);
+              if constexpr (ILV) tma_load_5d(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, img, -1, 0);
+              else tma_load_5d(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            } else {
+              if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * halo_bytes);
+              if constexpr (ILV) tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, img, -1, 0);
+              else tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_halo, a_full(sa), chunk * BLOCK_K, dx - 1, y0 - 1, 0, img);
+            }
             if (++sa == SA) {
               sa = 0;
               pa ^= 1u;
@@ -1009,14 +1076,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
         }
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
           mbar_wait(a_empty(sa), pa ^ 1u, 0);
-          if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * M_SUB * L::A_SUB_BYTES);
-          if constexpr (ILV) {   // tm_a2 is the (C2, x, image, y) view: rows land in the tile's (y, image, x) order
-            tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
-          } else {
+          if constexpr (XF) {
+            mbar_expect_tx(a_full(sa), M_SUB * L::A_SUB_BYTES);
+            if constexpr (ILV) {
+              tma_load_5d(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
+            } else {
 #pragma unroll
-            for (int sub = 0; sub < M_SUB; ++sub)
-              tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
-                               m0 + sub * BLOCK_M, 0, 0, 0);
+              for (int sub = 0; sub < M_SUB; ++sub)
+                tma_load_5d(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                            m0 + sub * BLOCK_M, 0, 0, 0);
+            }
+          } else {
+            if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * M_SUB * L::A_SUB_BYTES);
+            if constexpr (ILV) {   // tm_a2 is the (C2, x, image, y) view: rows land in the tile's (y, image, x) order
+              tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
+            } else {
+#pragma unroll
+              for (int sub = 0; sub < M_SUB; ++sub)
+                tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                                 m0 + sub * BLOCK_M, 0, 0, 0);
+            }
           }
           if (++sa == SA) {
             sa = 0;
@@ -1063,7 +1142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
         };
         const int n_units = 3 * p.c1_chunks;
         for (int u = 0; u < n_units; ++u) {
-          mbar_wait(a_full(sa), pa, 1);
+          mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);
           const uint32_t a_slot = smem_base + sa * L::A_SLOT;
           for (int dy = 0; dy < 3; ++dy) mma_block(a_slot + dy * dy_bytes);
           umma_commit_2cta(a_empty(sa));
@@ -1073,7 +1152,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
           }
         }
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
-          mbar_wait(a_full(sa), pa, 1);
+          mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);
           mma_block(smem_base + sa * L::A_SLOT);
           umma_commit_2cta(a_empty(sa));
           if (++sa == SA) {
@@ -1084,12 +1163,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_kernel(const __gr
         umma_commit_2cta(tmem_full_bar(as));
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, true, ILV>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
                                              reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
                                              L::STAT_IMGS, tmem_base,
                                              tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
                                              work_step, cta_rank, warp, lane);
+  } else if constexpr (XF) {
+    // ===================== transform warps: GroupNorm-apply (+ SiLU) on this CTA's activation slots =====================
+    const int tid = (int)threadIdx.x - NUM_THREADS;
+    const int log2w = 31 - __clz(p.W);
+    const int slot_rows = halo_rows * (ILV ? 2 * p.W : p.W);
+    const int C1 = p.c1_chunks * BLOCK_K;
+    const int n_img = p.M / p.HW;
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = work_id0; tile < n_tiles; tile += work_step) {
+      const int m0 = (tile / n_tiles_n) * TILE_M + (int)cta_rank * CTA_ROWS;
+      // ILV: the tile is two whole images and a thread's rows all lie in image (tid >> 6) & 1 of them
+      const int img = m0 / p.HW + (ILV ? ((tid >> 6) & 1) : 0);
+      const int y0 = ILV ? 0 : (m0 - (m0 / p.HW) * p.HW) / p.W;
+      const bool live = img < n_img;            // past the last image the box is zero fill: leave it
+      const float2* const crow = p.xf_coef + (size_t)(live ? img : 0) * C1 + (tid & 7) * 8;
+      for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
+        float ca[8], cb[8];
+        xf_load_coef(crow + chunk * BLOCK_K, ca, cb);
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(a_full(sa), pa, 6);
+          if (live)
+            xf_transform_slot<ILV>(smem_gen + sa * L::A_SLOT, slot_rows, log2w, p.W, p.H, y0 - 1, dx - 1, ca, cb, p.xf_act,
+                                   tid);
+          xf_publish_fence();
+          if (lane == 0) mbar_arrive_cluster(a_ready(sa), 0);
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+      }
+      for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {   // the raw 1x1 skip operand passes through untouched
+        mbar_wait(a_full(sa), pa, 6);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a_ready(sa), 0);
+        if (++sa == SA) {
+          sa = 0;
+          pa ^= 1u;
+        }
+      }
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1297,15 +1418,14 @@ struct HaloTLayout {
   static constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;              // 128 output channels x 64 k
   static constexpr int W_OFFSET = SA * A_SLOT;
   static constexpr int BAR_OFFSET = W_OFFSET + SB * W_BYTES;
-  static constexpr int NUM_BARS = 2 * SA + 2 * SB + 4;
+  static constexpr int NUM_BARS = 3 * SA + 2 * SB + 4;               // + SA "slot transformed" barriers (XF)
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int SA, int SB, int EPI, bool WIDE = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo,
-                                                                        const __grid_constant__ CUtensorMap tm_a2,
-                                                                        const __grid_constant__ CUtensorMap tm_w,
-                                                                        const TcParams p) {
+template <int SA, int SB, int EPI, bool WIDE = false, bool XF = false>
+__global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
+    gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
+                          const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   using L = HaloTLayout<SA, SB, WIDE>;
   constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
@@ -1321,6 +1441,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
   auto w_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SB + 4 + s); };   // XF: slot transformed
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
@@ -1339,6 +1460,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
       mbar_init(w_full(s), 1);
       mbar_init(w_empty(s), 2);       // both CTAs of the cluster must have consumed the tile
     }
+    for (int s = 0; s < SA; ++s) mbar_init(a_ready(s), XF_WARPS);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), EPI_WARPS);
@@ -1440,7 +1562,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
         };
         const int n_units = 3 * p.c1_chunks;
         for (int u = 0; u < n_units; ++u) {
-          mbar_wait(a_full(sa), pa, 1);
+          mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);   // XF: the transform warps hand the slot over
           const uint32_t a_slot = smem_base + sa * L::A_SLOT;
           for (int dy = 0; dy < 3; ++dy) mma_block(a_slot + dy * dy_bytes);
           umma_commit(a_empty(sa));
@@ -1450,7 +1572,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
           }
         }
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
-          mbar_wait(a_full(sa), pa, 1);
+          mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);   // XF: the transform warps hand the slot over
           mma_block(smem_base + sa * L::A_SLOT);
           umma_commit(a_empty(sa));
           if (++sa == SA) {
@@ -1461,7 +1583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
         umma_commit(tmem_full_bar(as));
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     // ===================== epilogue (warps 2..9): lane = output channel, TMEM column = pixel =====================
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter: channels q*32 .. q*32+31
@@ -1529,6 +1651,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_halo_t_kernel(const __
           unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) + (size_t)(row0 / p.HW) * 2 * p.N + c;
           atomicAdd(tab, (unsigned long long)__float2ll_rn(rsum * 16777216.0f));
           atomicAdd(tab + p.N, (unsigned long long)__float2ll_rn(rsq * 16777216.0f));
+        }
+      }
+    }
+  } else if constexpr (XF) {
+    // ===================== transform warps: GroupNorm-apply (+ SiLU) on every activation slot =====================
+    const int tid = (int)threadIdx.x - NUM_THREADS;
+    const int log2w = 31 - __clz(p.W);
+    const int slot_rows = halo_rows * p.W;
+    const int C1 = p.c1_chunks * BLOCK_K;
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = work_id0; tile < n_tiles; tile += work_step) {
+      const int m0 = (tile / n_tiles_n) * TILE_M + (int)cta_rank * PIX;
+      const int img = m0 / p.HW;
+      const int y0 = (m0 - img * p.HW) / p.W;
+      const float2* const crow = p.xf_coef + (size_t)min(img, p.M / p.HW - 1) * C1 + (tid & 7) * 8;
+      for (int chunk = 0; chunk < p.c1_chunks; ++chunk) {
+        float ca[8], cb[8];
+        xf_load_coef(crow + chunk * BLOCK_K, ca, cb);
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(a_full(sa), pa, 6);
+          xf_transform_slot<false>(smem_gen + sa * L::A_SLOT, slot_rows, log2w, p.W, p.H, y0 - 1, dx - 1, ca, cb, p.xf_act,
+                                   tid);
+          xf_publish_fence();
+          if (lane == 0) mbar_arrive(a_ready(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+      }
+      for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {   // the raw 1x1 skip operand passes through untouched
+        mbar_wait(a_full(sa), pa, 6);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready(sa));
+        if (++sa == SA) {
+          sa = 0;
+          pa ^= 1u;
         }
       }
     }
@@ -1669,14 +1829,14 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
   }
 }
 
-template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false>
+template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, bool XF = false>
 int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                      cudaStream_t stream) {
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static PerDevice<bool> configured;
   if (!configured.get()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV, XF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1689,7 +1849,7 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1699,7 +1859,7 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV>, mh, ma2, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV, XF>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (halo): launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1708,10 +1868,24 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
   return 0;
 }
 
+// fused-normalisation instances: one output + GroupNorm statistics, with or without residual (variants 4..7)
+template <int BLOCK_N, int M_SUB, int SA, int SB, bool ILV>
+int launch_halo_xf(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+                   cudaStream_t stream) {
+  switch (epilogue_variant(p, BLOCK_N)) {
+    case 4: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 4, ILV, true>(mh, ma2, mw, p, stream);
+    case 5: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 5, ILV, true>(mh, ma2, mw, p, stream);
+    case 6: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 6, ILV, true>(mh, ma2, mw, p, stream);
+    case 7: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 7, ILV, true>(mh, ma2, mw, p, stream);
+    default: set_error("gemm_tc: fused normalisation needs one output and stats_out"); return -1;
+  }
+}
+
 // interleaved 8x8 tiles: lean epilogue variants only (the caller checked epilogue_variant < 8)
 template <int BLOCK_N, int SA, int SB>
 int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                     cudaStream_t stream) {
+  if (p.xf_coef != nullptr) return launch_halo_xf<BLOCK_N, 1, SA, SB, true>(mh, ma2, mw, p, stream);
   switch (epilogue_variant(p, BLOCK_N)) {
     case 0: return launch_halo_inst<BLOCK_N, 1, SA, SB, 0, true>(mh, ma2, mw, p, stream);
     case 1: return launch_halo_inst<BLOCK_N, 1, SA, SB, 1, true>(mh, ma2, mw, p, stream);
@@ -1727,6 +1901,7 @@ int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtenso
 template <int BLOCK_N, int M_SUB, int SA, int SB>
 int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                 cudaStream_t stream) {
+  if (p.xf_coef != nullptr) return launch_halo_xf<BLOCK_N, M_SUB, SA, SB, false>(mh, ma2, mw, p, stream);
   switch (epilogue_variant(p, BLOCK_N)) {
     case 0: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 0>(mh, ma2, mw, p, stream);
     case 1: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 1>(mh, ma2, mw, p, stream);
@@ -1794,15 +1969,15 @@ int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcPar
   return launch_upfold_halo_inst<SA, SB, 8>(mh, mw, p, stream);
 }
 
-template <int SA, int SB, int EPI, bool WIDE>
+template <int SA, int SB, int EPI, bool WIDE, bool XF = false>
 int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                        cudaStream_t stream) {
   using L = HaloTLayout<SA, SB, WIDE>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static PerDevice<bool> configured;
   if (!configured.get()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE, XF>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) {
       set_error("gemm_tc (transposed halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1813,7 +1988,7 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1823,7 +1998,7 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE>, mh, ma2, mw, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE, XF>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (transposed halo): launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1832,10 +2007,24 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
   return 0;
 }
 
+// epilogue variants the fused-normalisation (XF) kernels are built for: one output + GroupNorm statistics, with or
+// without a residual -- what the ResBlock convs ask for (other combinations keep the standalone GroupNorm-apply)
+bool xf_variant_ok(int v) { return v >= 4 && v <= 7; }
+
 template <int SA, int SB, bool WIDE = false>
 int launch_halo_t(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
                   cudaStream_t stream) {
-  switch (epilogue_variant(p, 128)) {
+  const int v = epilogue_variant(p, 128);
+  if (p.xf_coef != nullptr) {
+    switch (v) {
+      case 4: return launch_halo_t_inst<SA, SB, 4, WIDE, true>(mh, ma2, mw, p, stream);
+      case 5: return launch_halo_t_inst<SA, SB, 5, WIDE, true>(mh, ma2, mw, p, stream);
+      case 6: return launch_halo_t_inst<SA, SB, 6, WIDE, true>(mh, ma2, mw, p, stream);
+      case 7: return launch_halo_t_inst<SA, SB, 7, WIDE, true>(mh, ma2, mw, p, stream);
+      default: set_error("gemm_tc: fused normalisation needs one output and stats_out"); return -1;
+    }
+  }
+  switch (v) {
     case 0: return launch_halo_t_inst<SA, SB, 0, WIDE>(mh, ma2, mw, p, stream);
     case 1: return launch_halo_t_inst<SA, SB, 1, WIDE>(mh, ma2, mw, p, stream);
     case 2: return launch_halo_t_inst<SA, SB, 2, WIDE>(mh, ma2, mw, p, stream);
@@ -1855,10 +2044,16 @@ int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream);   // conv_smal
 static unsigned long long* g_trace_buf = nullptr;
 void gemm_tc_set_trace(void* buf) { g_trace_buf = reinterpret_cast<unsigned long long*>(buf); }
 
-int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
+// probe != nullptr: do not launch; *probe = 1 if the call would run on a halo kernel with a lean epilogue, i.e. on a
+// kernel that has the fused-normalisation transform stage (vdm_gemm_fused_norm_supported)
+int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   const int64_t M = (int64_t)a->n_img * a->H * a->W;
-  if (a->a1_mode == 3) return gemm_tc_upfold(a, stream);
-  if (a->out_nchw && a->N <= 8 && !getenv("VDM_NO_SMALL_N")) {
+  if (probe) *probe = 0;
+  const bool xf = a->a1_coef != nullptr;
+  VDM_REQUIRE(!xf || (a->taps == 9 && a->a1_mode == 0 && !a->out_nchw),
+              "gemm_tc: fused normalisation (a1_coef) takes 3x3 stride-1 convolutions only");
+  if (a->a1_mode == 3) return probe ? 0 : gemm_tc_upfold(a, stream);
+  if (!probe && a->out_nchw && a->N <= 8 && !getenv("VDM_NO_SMALL_N")) {
     const int rc = conv3x3_small_n(a, stream);
     if (rc != -100) return rc;
   }
@@ -1889,6 +2084,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   p.stats_out = a->stats_out;
   p.stats_via_smem = 1;
+  p.xf_coef = reinterpret_cast<const float2*>(a->a1_coef);
+  p.xf_act = a->a1_act;
   p.w_group_tiles = a->w_group_tiles;
   p.n_par = 1;
   const int n_prob = a->n_prob > 1 ? a->n_prob : 1;
@@ -1909,6 +2106,24 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
 
   CUtensorMap ma1, ma2, mw;
   int rc;
+  const bool xf_epi = xf_variant_ok(epilogue_variant(p, 128));   // what the fused-normalisation instances exist for
+  if (probe) {
+    // mirror of the halo dispatch below, without descriptors or launches
+    const int hmode = getenv("VDM_GEMM_HALO") ? atoi(getenv("VDM_GEMM_HALO")) : 1;
+    const int tmode = getenv("VDM_GEMM_HALO_T") ? atoi(getenv("VDM_GEMM_HALO_T")) : 1;
+    const int bn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : (a->N % 128 == 0 ? 128 : 0));
+    const int rows = BLOCK_M * (bn == 128 ? 2 : 1);
+    const bool base = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 && xf_epi;
+    const bool ok8 = base && a->W == 8 && a->H == 8 && a->N % 256 == 0 &&
+                     (hmode == 2 || ((M + 255) / 256) * (a->N / 256) >= 40);
+    const bool ok = base && bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
+                    (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
+    const bool okw = base && a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 &&
+                     (hmode == 2 || ((M + 511) / 512) * (a->N / 128) >= 40);
+    (void)tmode;   // the transposed kernel is only ever chosen where the pair kernel is legal too
+    *probe = (ok8 || ok || okw) ? 1 : 0;
+    return 0;
+  }
   if (is_linear) {
     rc = encode_rows_map(&ma1, a->a1, M, a->C1 + (n_prob - 1) * (n_prob > 1 ? a->prob_a_cols : 0), a->lda1);
   } else {
@@ -2041,6 +2256,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream) {
       return launch_halo<128, 2, 3, 4>(mh, ma2, mw2, p, stream);
     }
   }
+  VDM_REQUIRE(!xf, "gemm_tc: fused normalisation (a1_coef) is not available for this shape / epilogue "
+                   "(check vdm_gemm_fused_norm_supported first)");
   int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
   // 256x128 CTA tiles (two 128-row sub-tiles sharing every weight tile) halve the L2->smem operand
   // traffic per FLOP; use them unless the layer is too small to fill the SMs that way.

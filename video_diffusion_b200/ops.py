@@ -30,11 +30,9 @@ def _nbytes(*tensors):
     return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
 
-def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
-         out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
-         w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0):
-    """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm)."""
-    lib = _lib.load()
+def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
+               out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
+               w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0, a1_coef=None, a1_act=False):
     g = GemmArgs()
     g.dtype = dt(a1.dtype)
     g.taps, g.a1_mode = taps, a1_mode
@@ -61,11 +59,40 @@ def gemm(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=
     g.out_nchw = int(out_nchw)
     g.out_silu_f32 = ptr(out_silu)
     g.stats_out = ptr(stats_out)
-    M = n_img * H * W
-    K = taps * g.C1 + g.C2
-    name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if taps == 9 else '_linear')
-    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K * n_prob,
-           meta=f'M={M} N={N} K={K} HxW={H}x{W} mode={a1_mode} res={int(residual is not None)} stats={int(stats_out is not None)}' + (f' x{n_prob}' if n_prob > 1 else ''))
+    g.a1_coef, g.a1_act = ptr(a1_coef, torch.float32), int(a1_act)
+    return g
+
+
+def gemm(a1, w, N, **kw):
+    """Implicit-GEMM conv / linear (see include/vdm.h: vdm_gemm).  `a1_coef` (from gn_coef) fuses the GroupNorm-apply
+    (+ SiLU with a1_act) of the A operand into the kernel: a1 is then the RAW bf16 activation."""
+    lib = _lib.load()
+    g = _gemm_args(a1, w, N, **kw)
+    M = g.n_img * g.H * g.W
+    K = g.taps * g.C1 + g.C2
+    name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if g.taps == 9 else '_linear')
+    _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K * g.n_prob,
+           meta=f'M={M} N={N} K={K} HxW={g.H}x{g.W} mode={g.a1_mode} res={int(bool(g.residual))} '
+                f'stats={int(bool(g.stats_out))}' + (' norm=fused' if g.a1_coef else '') +
+                (f' x{g.n_prob}' if g.n_prob > 1 else ''))
+
+
+def gemm_fused_norm_supported(a1, w, N, **kw):
+    """Would this call (with a1_coef) run on a kernel that has the fused-normalisation stage?  Same dispatch code as
+    vdm_gemm, no launch."""
+    g = _gemm_args(a1, w, N, **kw)
+    return bool(_lib.load().vdm_gemm_fused_norm_supported(C.byref(g)))
+
+
+def gn_coef(stats1, stats2, n_img, HW, gamma, beta, coef, scale_shift=None):
+    """Per-(image, channel) (a, b) of GroupNorm32 (+ scale/shift) into coef [n_img][C1+C2][2] (see vdm.h: vdm_gn_coef)."""
+    kind = lambda s: _lib.F64 if (s is not None and s.dtype == torch.float64) else _lib.I64
+    C1, C2 = stats1.shape[-1], (0 if stats2 is None else stats2.shape[-1])
+    _timed('gn_coef', lambda: check(_lib.load().vdm_gn_coef(
+        ptr(stats1), kind(stats1), C1, ptr(stats2), kind(stats2), C2, n_img, HW, ptr(gamma, torch.float32),
+        ptr(beta, torch.float32), None if scale_shift is None else scale_shift.data_ptr(),
+        0 if scale_shift is None else scale_shift.stride(0), ptr(coef, torch.float32), stream()), 'vdm_gn_coef'),
+           nbytes=_nbytes(coef))
 
 
 def gn_stats(src, n_img, HW, stats):

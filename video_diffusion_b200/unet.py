@@ -73,6 +73,7 @@ class UNetModel(nn.Module):
         self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
         self.overlap_rpe_tables = True    # RPE tables on a side stream, concurrent with the first U-Net blocks
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
+        self.fuse_norm = True             # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (halo kernels)
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
             raise NotImplementedError('model_channels must be a multiple of 64')
@@ -315,6 +316,7 @@ class UNetModel(nn.Module):
         def __init__(self, B, F, H, W, dev, stat_capacity):
             self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
             self.bufs = {}
+            self.flags = {}          # per-shape dispatch decisions (e.g. which convs take the fused normalisation)
             self.graph = None
             N = B * F
             f32 = torch.float32
@@ -410,17 +412,27 @@ class UNetModel(nn.Module):
         if ws.emb_join is not None:      # first consumer of the embedding projections: join the side branch
             torch.cuda.current_stream().wait_event(ws.emb_join)
             ws.emb_join = None
-        a2 = ws.buf(p + '.a2', (M, Cout), adt)
-        ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
-                     scale_shift=emb_out[:, off:off + 2 * Cout] if ss else None, silu=True)
         out = ws.buf(p + '.out', (M, Cout))
         st_out = self._fused_stats(ws, p + '.out', n_img, HW, Cout)
-        if node['skip']:
-            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, a2=araw, bias=P[p + '.b2'], out_f32=out,
-                     stats_out=st_out)
+        conv2 = dict(n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b2'], out_f32=out, stats_out=st_out)
+        conv2.update(dict(a2=araw) if node['skip'] else dict(residual=src1))
+        scale_shift = emb_out[:, off:off + 2 * Cout] if ss else None
+        fuse = ws.flags.get(p + '.fuse2')
+        if fuse is None:
+            # out_layers (unet.py:185-198): GroupNorm -> (1 + scale, shift) -> SiLU -> conv.  Where the conv runs on a
+            # halo kernel, its transform warps apply the first three to the raw bf16 conv1 output inside shared
+            # memory -- the normalised activation never exists in HBM; elsewhere the standalone pass produces it.
+            fuse = ws.flags[p + '.fuse2'] = bool(self.fuse_norm and h1.dtype == torch.bfloat16 and st_out is not None and
+                                        ops.gemm_fused_norm_supported(h1, P[p + '.w2'], Cout, **conv2))
+        if fuse:
+            coef = ws.buf(p + '.coef2', (n_img, Cout, 2))
+            ops.gn_coef(st_h1, None, n_img, HW, P[p + '.gn2_w'], P[p + '.gn2_b'], coef, scale_shift=scale_shift)
+            ops.gemm(h1, P[p + '.w2'], Cout, a1_coef=coef, a1_act=True, **conv2)
         else:
-            ops.gemm(a2, P[p + '.w2'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b2'], residual=src1,
-                     out_f32=out, stats_out=st_out)
+            a2 = ws.buf(p + '.a2', (M, Cout), adt)
+            ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
+                         scale_shift=scale_shift, silu=True)
+            ops.gemm(a2, P[p + '.w2'], Cout, **conv2)
         return out, st_out
 
     def _tc_temporal_ok(self, T, C, HW):
