@@ -163,8 +163,8 @@ def cpu_step(sd, batch, threads):
     noise = synth.make_noise(tuple(x.shape), seed=4)
     torch.set_num_threads(threads)
     if have_reference():
+        model, diffusion = reference_model_and_diffusion(sd)      # puts baseline/_ref on sys.path
         import improved_diffusion.gaussian_diffusion as rgd
-        model, diffusion = reference_model_and_diffusion(sd)
         kw = dict(w, x_t_minus_1=w['x0'], observed_frames='x_0')
 
         def step():

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(PIX * 32) attn_temporal_kernel(const float* __
                                                                  const float* __restrict__ mask, int pad_interact,
                                                                  int T, int HW, int heads, int hd,
                                                                  OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) float sm[];
   const int hs = hd + 4;
   const int C = heads * hd;
@@ -145,6 +147,8 @@ constexpr int QPB = 64;
 template <typename OutT>
 __global__ void __launch_bounds__(256) attn_spatial_f32_kernel(const float* __restrict__ qkv, int L, int heads,
                                                                 int hd, OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) float sm[];
   const int hs = hd + 4, C = heads * hd, hd4 = hd >> 2;
   float* Ks = sm;
@@ -247,11 +251,11 @@ extern "C" int vdm_attn_temporal(const float* qkv, const float* r_q, const float
   int rc;
   if (out_dtype == VDM_BF16) {
     if ((rc = set_smem(attn_temporal_kernel<__nv_bfloat16>, smem, "attn_temporal"))) return rc;
-    attn_temporal_kernel<__nv_bfloat16><<<grid, PIX * 32, smem, (cudaStream_t)stream>>>(
+    launch_kernel(attn_temporal_kernel<__nv_bfloat16>, grid, PIX * 32, smem, (cudaStream_t)(cudaStream_t)stream, 1, 
         qkv, r_q, r_k, r_v, mask, allow_pad_interactions, T, HW, heads, hd, (__nv_bfloat16*)out_a);
   } else {
     if ((rc = set_smem(attn_temporal_kernel<float>, smem, "attn_temporal"))) return rc;
-    attn_temporal_kernel<float><<<grid, PIX * 32, smem, (cudaStream_t)stream>>>(
+    launch_kernel(attn_temporal_kernel<float>, grid, PIX * 32, smem, (cudaStream_t)(cudaStream_t)stream, 1, 
         qkv, r_q, r_k, r_v, mask, allow_pad_interactions, T, HW, heads, hd, (float*)out_a);
   }
   VDM_AFTER_LAUNCH("attn_temporal");
@@ -270,11 +274,11 @@ extern "C" int vdm_attn_spatial(const void* qkv, int32_t qkv_dtype, int32_t n_im
   int rc;
   if (out_dtype == VDM_BF16) {
     if ((rc = set_smem(attn_spatial_f32_kernel<__nv_bfloat16>, smem, "attn_spatial"))) return rc;
-    attn_spatial_f32_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)qkv, L, heads, hd,
+    launch_kernel(attn_spatial_f32_kernel<__nv_bfloat16>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, (const float*)qkv, L, heads, hd,
                                                                                     (__nv_bfloat16*)out_a);
   } else {
     if ((rc = set_smem(attn_spatial_f32_kernel<float>, smem, "attn_spatial"))) return rc;
-    attn_spatial_f32_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)qkv, L, heads, hd,
+    launch_kernel(attn_spatial_f32_kernel<float>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, (const float*)qkv, L, heads, hd,
                                                                              (float*)out_a);
   }
   VDM_AFTER_LAUNCH("attn_spatial");
@@ -298,6 +302,8 @@ __global__ void __launch_bounds__(AW_WARPS * 32) attn_weights_mean_kernel(
     const InT* __restrict__ qkv, long long n_seq, int n_inner, long long outer_stride, long long inner_stride,
     long long seq_stride, int L, int heads, int hd, const float* __restrict__ r_q, const float* __restrict__ r_k,
     const float* __restrict__ mask, int pad_interact, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   __shared__ float qs[AW_WARPS][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wi = (long long)blockIdx.x * AW_WARPS + warp;
@@ -384,11 +390,11 @@ extern "C" int vdm_attn_weights_mean(const void* qkv, int32_t qkv_dtype, int64_t
   const long long warps = n_seq * L;
   const unsigned grid = (unsigned)((warps + AW_WARPS - 1) / AW_WARPS);
   if (qkv_dtype == VDM_BF16)
-    attn_weights_mean_kernel<__nv_bfloat16><<<grid, AW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_kernel(attn_weights_mean_kernel<__nv_bfloat16>, grid, AW_WARPS * 32, 0, (cudaStream_t)(cudaStream_t)stream, 1, 
         (const __nv_bfloat16*)qkv, n_seq, (int)n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, r_q, r_k,
         mask, allow_pad_interactions, out);
   else
-    attn_weights_mean_kernel<float><<<grid, AW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_kernel(attn_weights_mean_kernel<float>, grid, AW_WARPS * 32, 0, (cudaStream_t)(cudaStream_t)stream, 1, 
         (const float*)qkv, n_seq, (int)n_inner, outer_stride, inner_stride, seq_stride, L, heads, hd, r_q, r_k, mask,
         allow_pad_interactions, out);
   VDM_AFTER_LAUNCH("attn_weights_mean");

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) rpe_expand_kernel(const float* __restrict
                                                           __nv_bfloat16* __restrict__ bq,
                                                           __nv_bfloat16* __restrict__ bk,
                                                           __nv_bfloat16* __restrict__ bv) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   // one thread = 8 consecutive outputs (one 16-byte store)
   const int C = heads * hd, SW = 128 * gpt;
   const int which = blockIdx.z % 3;   // 0: Bk, 1: Bq, 2: Bv
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256) rpe_expand_live_kernel(const float* __res
                                                                long long qk_block_stride, int G, int T, int heads,
                                                                int hd, int gpt, float scale, __nv_bfloat16* __restrict__ bq,
                                                                __nv_bfloat16* __restrict__ bk, __nv_bfloat16* __restrict__ bv) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   __shared__ float tile[32][65];
   const int C = heads * hd, SW = 128 * gpt;
   const int which = blockIdx.z % 3, blk = blockIdx.z / 3, tg = blockIdx.y;
@@ -166,6 +170,8 @@ __global__ void __launch_bounds__(128) attn_temporal_mma_kernel(const __nv_bfloa
                                                                 int n_prob, int T, int D, int heads, int gpt,
                                                                 __nv_bfloat16* __restrict__ pm,
                                                                 float* __restrict__ pv) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   constexpr int LDS = HD + 8, CH = HD / 8, ROWS = 32;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -349,7 +355,7 @@ int launch_attn(const void* qkv, const float* sk, const float* sq, const float* 
     configured.get() = true;
   }
   const int n_prob = B * D * heads;
-  attn_temporal_mma_kernel<HD><<<(n_prob + 1) / 2, 128, smem, stream>>>(
+  launch_kernel(attn_temporal_mma_kernel<HD>, (n_prob + 1) / 2, 128, smem, (cudaStream_t)stream, 1, 
       (const __nv_bfloat16*)qkv, sk, sq, mask, pad, n_prob, T, D, heads, gpt, (__nv_bfloat16*)pm, pv);
   VDM_AFTER_LAUNCH("attn_temporal_tc");
   return 0;
@@ -376,14 +382,14 @@ extern "C" int vdm_rpe_expand(const float* r_q, const float* r_k, const float* r
   if (!zero_fill) {
     VDM_REQUIRE(T <= 32, "rpe_expand: T=%d must be <= 32", T);
     dim3 grid(gpt * ((heads * hd + 63) / 64), tgs, 3 * n_blocks);
-    rpe_expand_live_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd,
+    launch_kernel(rpe_expand_live_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd,
                                                                    gpt, 1.0f / sqrtf((float)hd), (__nv_bfloat16*)bq,
                                                                    (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
     VDM_AFTER_LAUNCH("rpe_expand");
     return 0;
   }
   dim3 grid(std::min((nvec + 255) / 256, 32), tgs, 3 * n_blocks);
-  rpe_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
+  launch_kernel(rpe_expand_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, r_q, r_k, r_v, bias, r_block_stride, tgs, qk_block_stride, G, T, heads, hd, gpt, 1.0f / sqrtf((float)hd),
                                                             (__nv_bfloat16*)bq, (__nv_bfloat16*)bk, (__nv_bfloat16*)bv);
   VDM_AFTER_LAUNCH("rpe_expand");
   return 0;

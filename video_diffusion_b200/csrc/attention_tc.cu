@@ -38,6 +38,8 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool v
 template <int HD, typename OutT>
 __global__ void __launch_bounds__(128) attn_spatial_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int L, int heads,
                                                                OutT* __restrict__ out, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   constexpr int LDS = HD + 8;  // padded row (elements): 16 B skew keeps ldmatrix conflict-free
   constexpr int CH = HD / 8;   // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -203,7 +205,7 @@ int launch(const void* qkv, int n_img, int L, int heads, void* out, cudaStream_t
   }
   dim3 grid((L + BQ - 1) / BQ, heads, n_img);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-  attn_spatial_mma_kernel<HD, OutT><<<grid, 128, smem, stream>>>((const __nv_bfloat16*)qkv, L, heads, (OutT*)out,
+  launch_kernel(attn_spatial_mma_kernel<HD, OutT>, grid, 128, smem, (cudaStream_t)stream, 1, (const __nv_bfloat16*)qkv, L, heads, (OutT*)out,
                                                                 scale_log2);
   VDM_AFTER_LAUNCH("attn_spatial_tc");
   return 0;

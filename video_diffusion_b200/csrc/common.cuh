@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/vdm.h"
 
@@ -53,6 +55,54 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute (launch_kernel below;
+// VDM_PDL=0 switches it off) and follows one protocol: `pdl_launch_dependents()` first -- the NEXT kernel in the
+// stream may then be scheduled as soon as this grid's CTAs are all resident and SM resources free up, so its launch
+// latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's tail -- and
+// `pdl_wait()` before the first access to global memory: it returns once every prerequisite grid has completed and
+// its writes are visible.  Nothing global is written before the wait, so there is no write-after-read hazard either.
+// Captured into a CUDA graph the attribute becomes a programmatic edge between the two kernel nodes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VDM_PDL");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
+}
+
+// cluster_x > 1: thread-block cluster of that many CTAs along x.  Launch errors are picked up by VDM_AFTER_LAUNCH.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
                                                                const float* __restrict__ bias, int H, int W, int TW,
                                                                int C, int N,
                                                                float* __restrict__ out /* [n_img][N][H*W] */) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) uint8_t smem[];
   // tile = R image rows x TW columns (column strips keep the halo tile small: several CTAs per SM, little re-reading)
   const int R = TILE_PIX / TW;
@@ -149,7 +151,7 @@ int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
     configured.get() = smem;
   }
   const int grid = a->n_img * (H * W / TILE_PIX);
-  conv3x3_small_n_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->a1),
+  launch_kernel(conv3x3_small_n_kernel, grid, 256, smem, (cudaStream_t)stream, 1, reinterpret_cast<const __nv_bfloat16*>(a->a1),
                                                      reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW, C, N,
                                                      a->out_f32);
   VDM_AFTER_LAUNCH("conv3x3_small_n");

@@ -14,6 +14,8 @@ namespace {
 // grid (pixel chunks, n_img); block = (C/4) x rows threads; each thread owns 4 channels.
 __global__ void gn_stats_kernel(const float* __restrict__ src, int C, int HW, int pix_per_block,
                                 double* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int C4 = C / 4;
   const int cq = threadIdx.x % C4, prow = threadIdx.x / C4, rows = blockDim.x / C4;
   const int n = blockIdx.y;
@@ -56,6 +58,8 @@ struct ApplyParams {
 // MODE: 0 plain, 1 nearest-x2, 2 stride-2 parity planes; RAW / COPY: optional extra outputs.
 template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int C = p.C1 + p.C2, cpg = C / 32, HW = p.H * p.W, C8 = C / 8;
   double* chs = reinterpret_cast<double*>(sm_raw);
@@ -218,6 +222,8 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const void* st1, int st_ki
                                                        int C2, int HW, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ ss,
                                                        int ld_ss, float2* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int C = C1 + C2, cpg = C / 32;
   double* chs = reinterpret_cast<double*>(sm_raw);
@@ -273,6 +279,8 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ out_f32,
                                                            OutT* __restrict__ out_a) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) float smt[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pix = blockIdx.x * 8 + warp;
@@ -355,6 +363,8 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
                                                                 const float* __restrict__ beta,
                                                                 float* __restrict__ out_f32, OutT* __restrict__ out_a,
                                                                 int gps, int n_slabs) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wg = (long long)blockIdx.x * 4 + warp;
   if (wg >= (long long)B * HW * n_slabs) return;
@@ -423,6 +433,8 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
 __global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* h, const float* __restrict__ enc,
                                                                     const float* __restrict__ frame_emb, float* out,
                                                                     long long total4, long long per_img4, int C4) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(h)[i];
@@ -450,6 +462,8 @@ __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__
                                                         const float* __restrict__ kinda, const float* __restrict__ t,
                                                         int B, int F, int H, int W, OutT* __restrict__ a_out,
                                                         float* __restrict__ t_frame, float* __restrict__ attn_mask) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   constexpr int CIN = MODE == 0 ? 5 : (MODE == 1 ? 6 : 3);
   const int HW = H * W;
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -510,6 +524,8 @@ __global__ void __launch_bounds__(128) cond_mix_kernel(const float* __restrict__
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, float neg_log_period,
                                           float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * half) return;
@@ -530,6 +546,8 @@ __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict
                                                           const long long* __restrict__ fi, const float* __restrict__ wd,
                                                           const float* __restrict__ bd, int B, int T, int C,
                                                           OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int C8 = C / 8;
   const int BT = B * T;
   const int total = n_nets * BT * C8;
@@ -586,6 +604,8 @@ __global__ void __launch_bounds__(256) rpe_lookup_kernel(const float* __restrict
                                                           int B, int T, int C, int n_buckets, double alpha, float alpha_f,
                                                           float beta_f, float beta_minus_alpha, float log_ratio,
                                                           float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int C4 = C / 4, rows = B * T * T;
   const long long total = (long long)3 * rows * C4;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
@@ -623,7 +643,7 @@ extern "C" int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t 
   int ppb = 256;
   while (ppb > 16 && (long long)((HW + ppb - 1) / ppb) * n_img < 2LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, n_img);
-  gn_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(src, C, HW, ppb, stats);
+  launch_kernel(gn_stats_kernel, grid, threads, 0, (cudaStream_t)(cudaStream_t)stream, 1, src, C, HW, ppb, stats);
   VDM_AFTER_LAUNCH("gn_stats");
   return 0;
 }
@@ -658,7 +678,7 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_mode == 0 || (!raw && !copy), "gn_apply: extra outputs only with the plain layout");
   VDM_REQUIRE(!(raw && copy), "gn_apply: out_raw and out_f32_copy are mutually exclusive");
 #define VDM_GN_LAUNCH(OUT, IN, MODE, RAW, COPY) \
-  gn_apply_kernel<OUT, IN, MODE, RAW, COPY><<<grid, threads, smem, (cudaStream_t)stream>>>(p)
+  launch_kernel(gn_apply_kernel<OUT, IN, MODE, RAW, COPY>, grid, threads, smem, (cudaStream_t)(cudaStream_t)stream, 1, p)
 #define VDM_GN_BY_MODE(OUT, IN)                                              \
   do {                                                                       \
     if (a->out_mode == 1) VDM_GN_LAUNCH(OUT, IN, 1, false, false);           \
@@ -685,7 +705,7 @@ extern "C" int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, 
   VDM_REQUIRE((stats_dtype == VDM_F64 || stats_dtype == VDM_I64) && (C2 == 0 || stats2_dtype == VDM_F64 || stats2_dtype == VDM_I64),
               "gn_coef: bad stats dtype");
   const size_t smem = 2 * (size_t)C * sizeof(double) + 64 * sizeof(float);
-  gn_coef_kernel<<<n_img, 256, smem, (cudaStream_t)stream>>>(stats1, stats_dtype, C1, stats2, stats2_dtype, C2, HW, gamma,
+  launch_kernel(gn_coef_kernel, n_img, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, stats1, stats_dtype, C1, stats2, stats2_dtype, C2, HW, gamma,
                                                             beta, scale_shift, ld_ss, reinterpret_cast<float2*>(coef));
   VDM_AFTER_LAUNCH("gn_coef");
   return 0;
@@ -705,10 +725,10 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
 #define VDM_GNT(TM)                                                                                                  \
   do {                                                                                                               \
     if (out_dtype == VDM_BF16)                                                                                       \
-      gn_temporal_regs_kernel<__nv_bfloat16, TM><<<grid, 128, 0, (cudaStream_t)stream>>>(                            \
+      launch_kernel(gn_temporal_regs_kernel<__nv_bfloat16, TM>, grid, 128, 0, (cudaStream_t)(cudaStream_t)stream, 1,                             \
           x, B, T, HW, C, gamma, beta, out_f32, (__nv_bfloat16*)out_a, gps, n_slabs);                                \
     else                                                                                                             \
-      gn_temporal_regs_kernel<float, TM><<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, T, HW, C, gamma, beta, out_f32, \
+      launch_kernel(gn_temporal_regs_kernel<float, TM>, grid, 128, 0, (cudaStream_t)(cudaStream_t)stream, 1, x, B, T, HW, C, gamma, beta, out_f32, \
                                                                                 (float*)out_a, gps, n_slabs);        \
   } while (0)
     if (T <= 8) VDM_GNT(8);
@@ -724,12 +744,12 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
   if (out_dtype == VDM_BF16) {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
-    gn_temporal_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32,
+    launch_kernel(gn_temporal_kernel<__nv_bfloat16>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, x, T, HW, C, gamma, beta, out_f32,
                                                                                 (__nv_bfloat16*)out_a);
   } else {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
-    gn_temporal_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, T, HW, C, gamma, beta, out_f32, (float*)out_a);
+    launch_kernel(gn_temporal_kernel<float>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, x, T, HW, C, gamma, beta, out_f32, (float*)out_a);
   }
   VDM_AFTER_LAUNCH("gn_temporal");
   return 0;
@@ -740,7 +760,7 @@ extern "C" int vdm_add_spatial_encoding(const float* h, const float* enc, const 
   VDM_REQUIRE(h && (enc || frame_emb) && out && C % 4 == 0, "add_spatial_encoding: bad arguments");
   const long long per4 = (long long)HW * C / 4, total4 = per4 * n_img;
   const int grid = (int)std::min<long long>((total4 + 255) / 256, (long long)num_sms() * 16);
-  add_spatial_encoding_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, enc, frame_emb, out, total4, per4, C / 4);
+  launch_kernel(add_spatial_encoding_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, h, enc, frame_emb, out, total4, per4, C / 4);
   VDM_AFTER_LAUNCH("add_spatial_encoding");
   return 0;
 }
@@ -752,10 +772,10 @@ static void launch_cond_mix(const float* x, const float* x0, const float* obs, c
   const long long M = (long long)B * F * H * W;
   const int grid = (int)((M + 127) / 128);
   if (out_dtype == VDM_BF16)
-    cond_mix_kernel<__nv_bfloat16, MODE><<<grid, 128, 0, stream>>>(x, x0, obs, lat, kinda, t, B, F, H, W,
+    launch_kernel(cond_mix_kernel<__nv_bfloat16, MODE>, grid, 128, 0, (cudaStream_t)stream, 1, x, x0, obs, lat, kinda, t, B, F, H, W,
                                                                   (__nv_bfloat16*)a_out, t_frame, attn_mask);
   else
-    cond_mix_kernel<float, MODE><<<grid, 128, 0, stream>>>(x, x0, obs, lat, kinda, t, B, F, H, W, (float*)a_out,
+    launch_kernel(cond_mix_kernel<float, MODE>, grid, 128, 0, (cudaStream_t)stream, 1, x, x0, obs, lat, kinda, t, B, F, H, W, (float*)a_out,
                                                           t_frame, attn_mask);
 }
 
@@ -778,7 +798,7 @@ extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t d
                                       vdm_stream_t stream) {
   VDM_REQUIRE(t_frame && out && n > 0 && dim >= 2 && max_period > 0, "timestep_embedding: bad arguments");
   const int total = n * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t_frame, n, dim,
+  launch_kernel(timestep_embedding_kernel, (total + 127) / 128, 128, 0, (cudaStream_t)(cudaStream_t)stream, 1, t_frame, n, dim,
                                                                                   (float)(-std::log(max_period)), out);
   VDM_AFTER_LAUNCH("timestep_embedding");
   return 0;
@@ -796,10 +816,10 @@ extern "C" int vdm_rpe_hidden(const float* e_t, int32_t ld_et, const int32_t* et
   VDM_REQUIRE(total < (1LL << 31), "rpe_hidden: problem too large");
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
   if (out_dtype == VDM_BF16)
-    rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices,
+    launch_kernel(rpe_hidden_kernel<__nv_bfloat16>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices,
                                                                             wd, bd, B, T, C, (__nv_bfloat16*)out);
   else
-    rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices, wd, bd,
+    launch_kernel(rpe_hidden_kernel<float>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, e_t, ld_et, et_offsets, n_nets, (const long long*)frame_indices, wd, bd,
                                                                     B, T, C, (float*)out);
   VDM_AFTER_LAUNCH("rpe_hidden");
   return 0;
@@ -813,7 +833,7 @@ extern "C" int vdm_rpe_lookup(const float* tables, const int64_t* frame_indices,
   VDM_REQUIRE(alpha > 0 && (double)n_buckets >= 2 * beta + 1, "rpe_lookup: table has %d rows, needs 2*beta+1", n_buckets);
   const long long total = (long long)3 * B * T * T * (C / 4);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
-  rpe_lookup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tables, (const long long*)frame_indices, B, T, C, n_buckets,
+  launch_kernel(rpe_lookup_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, tables, (const long long*)frame_indices, B, T, C, n_buckets,
                                                             alpha, (float)alpha, (float)beta, (float)(beta - alpha),
                                                             (float)log(gamma / alpha), out);
   VDM_AFTER_LAUNCH("rpe_lookup");

@@ -24,6 +24,8 @@ struct SimtParams {
 };
 
 __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(const SimtParams p) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -139,7 +141,7 @@ int gemm_simt(const vdm_gemm_args* a, cudaStream_t stream) {
   p.out_f32 = a->out_f32; p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.out_silu = a->out_silu_f32;
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.out_nchw = a->out_nchw;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-  gemm_simt_kernel<<<grid, THREADS, 0, stream>>>(p);
+  launch_kernel(gemm_simt_kernel, grid, THREADS, 0, (cudaStream_t)stream, 1, p);
   VDM_AFTER_LAUNCH("gemm_simt");
   return 0;
 }

@@ -700,6 +700,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tm_a2,
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const TcParams p) {
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
   constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);     // rows per work tile (CTA or CTA pair)
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader
@@ -757,6 +758,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // barriers, TMEM and shared-memory tables are set up: from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -981,6 +983,7 @@ template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, boo
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
     gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
                         const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(!ILV || M_SUB == 1, "interleaved 8x8 tiles are 128 rows");
   constexpr int CTA_ROWS = BLOCK_M * M_SUB;
@@ -1032,6 +1035,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // barriers, TMEM and shared-memory tables are set up: from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1250,6 +1254,7 @@ template <int SA, int SB, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
                                                                              const __grid_constant__ CUtensorMap tm_w,
                                                                              const TcParams p) {
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = UpfoldHaloLayout<SA, SB>;
   constexpr int BLOCK_N = L::BLOCK_N, CTA_ROWS = BLOCK_M, TILE_M = 2 * CTA_ROWS;
   const uint32_t cta_rank = cluster_ctarank();
@@ -1295,6 +1300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(con
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // barriers, TMEM and shared-memory tables are set up: from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1426,6 +1432,7 @@ template <int SA, int SB, int EPI, bool WIDE = false, bool XF = false>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
     gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
                           const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = HaloTLayout<SA, SB, WIDE>;
   constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
@@ -1479,6 +1486,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
   cluster_sync_all();       // peer barriers exist before any multicast load / commit can reach them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // barriers, TMEM and shared-memory tables are set up: from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1798,7 +1806,7 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
     }
   } else {
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2><<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma1, ma2, mw, p);
+    launch_kernel(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, grid, NUM_THREADS, L::TOTAL, (cudaStream_t)stream, 1, ma1, ma2, mw, p);
   }
   VDM_AFTER_LAUNCH("gemm_tc");
   return 0;

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(int mode, const float
                                                             long long per_batch, int clip, float eta,
                                                             float* __restrict__ sample, float* __restrict__ pred_xstart,
                                                             float* __restrict__ mean_out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int b = blockIdx.y;
   const long long tb = check_t(t[b], n_steps);
   StepConsts s;
@@ -134,6 +136,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                                         const long long* __restrict__ t, const float* __restrict__ tab,
                                                         int n_steps, long long per_batch, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int b = blockIdx.y;
   const long long tb = check_t(t[b], n_steps);
   const float a = tab[VDM_TAB_SQRT_ACP * n_steps + tb], s = tab[VDM_TAB_SQRT_1M_ACP * n_steps + tb];
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(256) lincomb_kernel(int op, const float* __res
                                                        const long long* __restrict__ t, const float* __restrict__ tab,
                                                        int n_steps, int row_a, int row_b, long long per_batch,
                                                        float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   const int bi = blockIdx.y;
   const long long tb = check_t(t[bi], n_steps);
   const float ca = tab[row_a * n_steps + tb], cb = op == 3 ? 0.f : tab[row_b * n_steps + tb];
@@ -211,6 +217,8 @@ __global__ void __launch_bounds__(256) vb_terms_kernel(const float* __restrict__
                                                         const long long* __restrict__ t, const float* __restrict__ tab,
                                                         int n_steps, const float* __restrict__ latent_mask, int F,
                                                         long long per_frame, int clip, double* __restrict__ acc) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   __shared__ float red[32];
   const int b = blockIdx.z, f = blockIdx.y;
   const float mask = latent_mask[b * F + f];
@@ -262,6 +270,8 @@ __global__ void __launch_bounds__(256) vb_terms_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) prior_bpd_kernel(const float* __restrict__ x0, const float* __restrict__ tab,
                                                          int n_steps, const float* __restrict__ latent_mask, int F,
                                                          long long per_frame, double* __restrict__ acc) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   __shared__ float red[32];
   const int b = blockIdx.z, f = blockIdx.y;
   const float mask = latent_mask[b * F + f];
@@ -332,11 +342,11 @@ extern "C" int vdm_sampler_step(int32_t mode, const float* x, const float* eps, 
                    (!mean || al(mean));
   dim3 grid(grid_x_for(vec ? per_batch / 4 : per_batch, B), B);
   if (vec)
-    sampler_step_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(mode, x, eps, noise, (const long long*)t, tables,
+    launch_kernel(sampler_step_kernel<4>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, mode, x, eps, noise, (const long long*)t, tables,
                                                                   n_steps, per_batch, clip_denoised, eta, sample,
                                                                   pred_xstart, mean);
   else
-    sampler_step_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(mode, x, eps, noise, (const long long*)t, tables,
+    launch_kernel(sampler_step_kernel<1>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, mode, x, eps, noise, (const long long*)t, tables,
                                                                   n_steps, per_batch, clip_denoised, eta, sample,
                                                                   pred_xstart, mean);
   VDM_AFTER_LAUNCH("sampler_step");
@@ -352,9 +362,9 @@ extern "C" int vdm_q_sample(const float* x0, const float* noise, const int64_t* 
   const bool vec = per_batch % 4 == 0 && al(x0) && al(noise) && al(out);
   dim3 grid(grid_x_for(vec ? per_batch / 4 : per_batch, B), B);
   if (vec)
-    q_sample_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, noise, (const long long*)t, tables, n_steps, per_batch, out);
+    launch_kernel(q_sample_kernel<4>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, x0, noise, (const long long*)t, tables, n_steps, per_batch, out);
   else
-    q_sample_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, noise, (const long long*)t, tables, n_steps, per_batch, out);
+    launch_kernel(q_sample_kernel<1>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, x0, noise, (const long long*)t, tables, n_steps, per_batch, out);
   VDM_AFTER_LAUNCH("q_sample");
   return 0;
 }
@@ -381,10 +391,10 @@ extern "C" int vdm_lincomb(int32_t op, const float* a, const float* b, const int
   const bool vec = per_batch % 4 == 0 && al(a) && (!b || al(b)) && al(out);
   dim3 grid(grid_x_for(vec ? per_batch / 4 : per_batch, B), B);
   if (vec)
-    lincomb_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
+    launch_kernel(lincomb_kernel<4>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
                                                              per_batch, out);
   else
-    lincomb_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
+    launch_kernel(lincomb_kernel<1>, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, op, a, b, (const long long*)t, tables, n_steps, row_a, row_b,
                                                              per_batch, out);
   VDM_AFTER_LAUNCH("lincomb");
   return 0;
@@ -397,7 +407,7 @@ extern "C" int vdm_vb_terms(const float* x0, const float* x_t, const float* eps,
   if (int rc = ensure_error_flag()) return rc;
   VDM_REQUIRE(B > 0 && F > 0 && per_frame > 0, "vb_terms: bad sizes");
   dim3 grid(grid_x_for(per_frame, B * F), F, B);
-  vb_terms_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x_t, eps, noise, (const long long*)t, tables, n_steps,
+  launch_kernel(vb_terms_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, x0, x_t, eps, noise, (const long long*)t, tables, n_steps,
                                                          latent_mask, F, per_frame, clip_denoised, acc);
   VDM_AFTER_LAUNCH("vb_terms");
   return 0;
@@ -407,7 +417,7 @@ extern "C" int vdm_prior_bpd(const float* x0, const float* tables, int32_t n_ste
                              int32_t F, int64_t per_frame, double* acc, vdm_stream_t stream) {
   VDM_REQUIRE(x0 && tables && latent_mask && acc, "prior_bpd: NULL pointer");
   dim3 grid(grid_x_for(per_frame, B * F), F, B);
-  prior_bpd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, tables, n_steps, latent_mask, F, per_frame, acc);
+  launch_kernel(prior_bpd_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, x0, tables, n_steps, latent_mask, F, per_frame, acc);
   VDM_AFTER_LAUNCH("prior_bpd");
   return 0;
 }

@@ -80,7 +80,11 @@ class _WrappedModel:
         key = str(timesteps.device)
         if key not in self._cache:      # the reference rebuilds this tensor on every call (:113-115)
             self._cache[key] = th.tensor(self.timestep_map, device=timesteps.device, dtype=th.long)
-        new_ts = self._cache[key][timesteps.long()]
+        # An index outside the respaced range raises IndexError in the reference (:116).  Here the lookup is clamped
+        # -- a device-side assert would poison the CUDA context -- and the sampler kernels, which receive the same
+        # unclamped t, record it: the next ops.check_timesteps() raises the IndexError.
+        tmap = self._cache[key]
+        new_ts = tmap[timesteps.long().clamp(0, tmap.numel() - 1)]
         if self.rescale_timesteps:
             new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
         return self.model(x, timesteps=new_ts, **kwargs)
