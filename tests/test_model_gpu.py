@@ -75,7 +75,7 @@ def test_forward_matches_reference_and_oracle(golden, case, dtype):
         buf, tap = tap_name(node)
         t = taps[tap]
         n, c, h, w = t.shape
-        got = ws.bufs[buf].float().cpu().view(n, h, w, c).permute(0, 3, 1, 2)
+        got = ws.tap(buf).float().cpu().view(n, h, w, c).permute(0, 3, 1, 2)
         err = max_rel(got.numpy(), t.numpy())
         worst = max(worst, err)
         if err > TOL[dtype]:
@@ -136,7 +136,7 @@ def test_full_size_models_match_reference(golden, case, dtype):
     for node in model.plan:
         buf, tap = tap_name(node)
         ref = g[f"{case['name']}/tap/{tap.rsplit('.', 1)[0]}"]
-        t = ws.bufs[buf].float()
+        t = ws.tap(buf).float()
         c = t.shape[-1]
         n = inp['x'].shape[0] * inp['x'].shape[1]
         hw = int(round((t.numel() // (n * c)) ** 0.5))
@@ -192,6 +192,52 @@ def test_in_place_weight_update_repacks(golden):
         c, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
     assert torch.allclose(b, 0.5 * a, rtol=2e-2, atol=1e-3) and not torch.allclose(b, a, rtol=1e-2, atol=1e-3)
     assert torch.equal(c, a)
+
+
+@pytest.mark.parametrize('graph', [False, True], ids=['eager', 'graph'])
+def test_micro_batches_equal_whole_batch(golden, graph):
+    """Running the U-Net body on two groups of videos in parallel streams (micro_batches = 2, the default) gives the
+    same bits as one pass over the whole batch: videos are independent, GroupNorm statistics are order-free fixed
+    point, and the RPE tables are shared through offset views."""
+    case = cases.UNET_CASES[1]                                 # ragged, B = 2
+    model, _ = build_model(case['cfg'], golden, torch.bfloat16)
+    model.use_cuda_graph = graph
+    inp = cases.unet_case_inputs(case)
+    x4 = torch.cat([inp['x'], inp['x'].flip(0) * 0.7], 0).cuda()           # B = 4: two groups of two videos
+    kw = {k: (torch.cat([v, v.flip(0)], 0).cuda() if torch.is_tensor(v) else v)
+          for k, v in cases.model_kwargs_for(inp).items()}
+    t4 = torch.cat([inp['t_model'], inp['t_model'].flip(0)]).cuda()
+    outs = {}
+    for n in (1, 2):
+        model.micro_batches = n
+        model._workspaces = {}
+        with torch.no_grad():
+            outs[n], _ = model(x4, t4, **kw)
+            again, _ = model(x4, t4, **kw)
+        assert torch.equal(again, outs[n])
+        ws = next(iter(model._workspaces.values()))
+        assert len(ws.children) == (2 if n == 2 else 0)
+    assert torch.equal(outs[1], outs[2])
+
+
+def test_fused_norm_model_equals_standalone(golden, monkeypatch):
+    """fuse_norm = True (GroupNorm-apply + scale/shift + SiLU of `out_layers` applied by the conv kernels' transform
+    warps) is an opt-in path; on the 64x64 model it must reproduce the default path bit for bit."""
+    monkeypatch.setenv('VDM_GEMM_HALO', '2')          # small batch: take the halo kernels regardless of tile count
+    case = dict(cases.FULL_CASES[0], F=4, n_obs=[1], n_lat=[3])
+    inp = cases.full_case_inputs(case)
+    kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+    outs = []
+    for fuse in (False, True):
+        model, _ = build_model(case['cfg'], golden, torch.bfloat16)
+        model.fuse_norm = fuse
+        with torch.no_grad():
+            out, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+        ws = next(iter(model._workspaces.values()))
+        n_fused = sum(bool(v) for k, v in ws.flags.items() if k.endswith('.fuse2'))
+        assert (n_fused > 10) if fuse else (n_fused == 0)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_cuda_graph_replay_equals_eager(golden):

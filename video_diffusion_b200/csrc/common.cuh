@@ -59,7 +59,7 @@ inline int num_sms() {
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute (launch_kernel below;
-// VDM_PDL=0 switches it off) and follows one protocol: `pdl_launch_dependents()` first -- the NEXT kernel in the
+// VDM_PDL=1 switches it on) and follows one protocol: `pdl_launch_dependents()` first -- the NEXT kernel in the
 // stream may then be scheduled as soon as this grid's CTAs are all resident and SM resources free up, so its launch
 // latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's tail -- and
 // `pdl_wait()` before the first access to global memory: it returns once every prerequisite grid has completed and
@@ -72,7 +72,7 @@ inline bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("VDM_PDL");
-    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    on = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // opt-in: measured slower than plain serialisation so far
   }
   return on != 0;
 }

@@ -15,6 +15,7 @@ reference-accuracy mode (fp32 SIMT kernels everywhere).
 Unsupported configurations raise NotImplementedError -- there is no PyTorch / CPU fallback.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -73,7 +74,12 @@ class UNetModel(nn.Module):
         self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
         self.overlap_rpe_tables = True    # RPE tables on a side stream, concurrent with the first U-Net blocks
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
-        self.fuse_norm = True             # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (halo kernels)
+        # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (transform warps of the halo kernels).  Correct
+        # and bit-exact against the standalone pass, but measured SLOWER on B200 (every activation element
+        # is re-transformed 4.5 times, which binds on the special-function units and shared-memory bandwidth): off.
+        self.fuse_norm = False
+        # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
+        self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
             raise NotImplementedError('model_channels must be a multiple of 64')
@@ -313,28 +319,37 @@ class UNetModel(nn.Module):
 
     # ---- execution -------------------------------------------------------------------------------
     class _Workspace:
-        def __init__(self, B, F, H, W, dev, stat_capacity):
+        def __init__(self, B, F, H, W, dev, stat_capacity, parent=None, lo=0):
+            """parent / lo: this is the workspace of one micro-batch (videos lo .. lo+B of the parent's batch): its
+            inputs and output are views of the parent's, everything else (activations, statistics) is its own."""
             self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
             self.bufs = {}
             self.flags = {}          # per-shape dispatch decisions (e.g. which convs take the fused normalisation)
             self.graph = None
             N = B * F
             f32 = torch.float32
-            self.x = torch.empty(B, F, 3, H, W, device=dev, dtype=f32)
-            self.x0 = torch.empty_like(self.x)
-            self.obs = torch.empty(B, F, device=dev, dtype=f32)
-            self.lat = torch.empty_like(self.obs)
-            self.kinda = torch.empty_like(self.obs)
-            self.t = torch.empty(B, device=dev, dtype=f32)
-            self.t_override = torch.empty(N, device=dev, dtype=f32)
-            self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
-            self.fi_float = torch.empty(B, F, device=dev, dtype=f32)
+            if parent is None:
+                self.x = torch.empty(B, F, 3, H, W, device=dev, dtype=f32)
+                self.x0 = torch.empty_like(self.x)
+                self.obs = torch.empty(B, F, device=dev, dtype=f32)
+                self.lat = torch.empty_like(self.obs)
+                self.kinda = torch.empty_like(self.obs)
+                self.t = torch.empty(B, device=dev, dtype=f32)
+                self.t_override = torch.empty(N, device=dev, dtype=f32)
+                self.fi = torch.empty(B, F, device=dev, dtype=torch.long)
+                self.fi_float = torch.empty(B, F, device=dev, dtype=f32)
+                self.out = None
+                self.stream = self.done = None
+            else:
+                self.fi, self.fi_float = parent.fi[lo:lo + B], parent.fi_float[lo:lo + B]
+                self.out = parent.out[lo:lo + B]
+                self.stream, self.done = torch.cuda.Stream(device=dev), torch.cuda.Event()
+            self.children, self.mb_fork = [], None
             self.stat_bufs = {}
             self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
             self.pool_used = 0
-            self.out = None
             self.side = self.ev_fork = self.ev_emb = self.ev_join = None
-            self.emb_join = None
+            self.emb_join = self.rpe_join = None
 
         def buf(self, name, shape, dtype=torch.float32):
             b = self.bufs.get(name)
@@ -364,6 +379,13 @@ class UNetModel(nn.Module):
         def zero_stats(self):
             if self.pool_used:
                 self.pool[:self.pool_used].zero_()
+
+        def tap(self, name):
+            """An activation buffer by name, for tests / diagnostics: with micro-batches the rows of the groups
+            (consecutive videos) are concatenated back."""
+            if name in self.bufs or not self.children:
+                return self.bufs[name]
+            return torch.cat([c.bufs[name] for c in self.children], dim=0)
 
     # GroupNorm statistics travel with the activation as (tensor, stats): in bf16 mode the producing GEMM's
     # epilogue accumulates them (deterministic fixed-point atomics); otherwise the standalone kernel does (float64).
@@ -530,9 +552,14 @@ class UNetModel(nn.Module):
             sksq = ws.buf(q + '.sksq', (2, M, SW))
             sk, sq = sksq[0], sksq[1]
             if pre is not None:
+                # tables of the FULL batch, [2][groups * SW][C] and [groups * C][SW]; a micro-batch reads its (b, t)
+                # groups through offset views (the two-problem GEMM keeps the full batch's problem stride)
                 bkq, bv = pre
-                ops.gemm(qkv[:, :C], bkq.view(2 * ntg * SW, C), SW, out_f32=sksq, w_group_tiles=tpg, C1=C, n_prob=2,
-                         prob_a_cols=C, prob_w_rows=ntg * SW, prob_out_stride=M * SW, **lin)
+                g0 = tables.get('__group0__', 0) // gpt
+                ntg_all = bkq.shape[1] // SW
+                bv = bv[g0 * C:(g0 + ntg) * C]
+                ops.gemm(qkv[:, :C], bkq.view(2 * ntg_all * SW, C)[g0 * SW:], SW, out_f32=sksq, w_group_tiles=tpg, C1=C,
+                         n_prob=2, prob_a_cols=C, prob_w_rows=ntg_all * SW, prob_out_stride=M * SW, **lin)
             else:
                 bq = ws.buf(q + '.bq', (ntg * SW, C), adt)
                 bk = ws.buf(q + '.bk', (ntg * SW, C), adt)
@@ -587,7 +614,9 @@ class UNetModel(nn.Module):
         return h3, st3
 
     def _run(self, ws, T_attn, per_frame_t, attn_log=None):
-        """The whole forward as a flat sequence of libvdm launches on the current stream."""
+        """The whole forward as a flat sequence of libvdm launches: a prologue on the full batch (conditioning mix,
+        timestep-embedding branch, RPE tables), then the U-Net body -- on the whole batch, or on `micro_batches`
+        groups of videos in parallel streams (see _body_split)."""
         P, adt = self._packed, self.compute_dtype
         B, F, H, W = ws.B, ws.F, ws.H, ws.W
         N, ch, E = B * F, self.model_channels, self.time_embed_dim
@@ -628,8 +657,7 @@ class UNetModel(nn.Module):
         # stream (a parallel branch of the CUDA graph) under the input conv and the first block, where their small
         # latency-bound launches would otherwise leave the GPU idle.  Two joins: the embedding projections before
         # the first scale/shift GroupNorm, the tables before the first attention block.
-        tables, rpe_join = None, None
-        ws.emb_join = None
+        tables, emb_join, rpe_join = None, None, None
         if self.overlap_rpe_tables and ops.PROFILE is None:
             main = torch.cuda.current_stream()
             if ws.side is None:
@@ -643,11 +671,70 @@ class UNetModel(nn.Module):
                 if T_attn == F and attn_log is None:
                     tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
                 ws.ev_join.record(ws.side)
-            ws.emb_join, rpe_join = ws.ev_emb, ws.ev_join
+            emb_join, rpe_join = ws.ev_emb, ws.ev_join
         else:
             embedding_branch()
             if T_attn == F and attn_log is None:        # the logging kernel reads the per-block fp32 tables
                 tables = self._rpe_tables(ws, rpe_et, B, F, H, W)
+
+        pro = dict(a_in=a_in, amask=amask, emb_out=emb_out, rpe_et=rpe_et, tables=tables or {})
+        if ws.out is None:
+            ws.out = torch.empty(B, F, self.out_channels, H, W, device=ws.dev)
+        n_mb = self._micro_batches_for(ws, attn_log)
+        if n_mb == 1:
+            ws.emb_join, ws.rpe_join = emb_join, rpe_join
+            self._body(ws, pro, T_attn, attn_log)
+        else:
+            self._body_split(ws, pro, T_attn, n_mb, emb_join, rpe_join)
+        return ws.out
+
+    # ---- micro-batches -----------------------------------------------------------------------------
+    def _micro_batches_for(self, ws, attn_log):
+        n = self.micro_batches
+        if (n <= 1 or self.compute_dtype != torch.bfloat16 or attn_log is not None or ops.PROFILE is not None
+                or ws.B % n or (ws.B // n * ws.F) % 2):     # (b, t) groups of the RPE tables pair up images at 8x8
+            return 1
+        return n
+
+    def _body_split(self, ws, pro, T_attn, n_mb, emb_join, rpe_join):
+        """The videos of a batch are independent (attention couples the frames of ONE video only), so the U-Net body
+        runs on `n_mb` groups of videos in parallel streams -- parallel branches of the CUDA graph.  The persistent
+        tensor-core GEMMs of the groups serialise on the SMs' shared memory, which staggers the groups by themselves:
+        while one group's GEMM holds the tensor cores, the other group's HBM-bound kernels (GroupNorm-apply, temporal
+        GroupNorm, casts) run beside it on the same SMs, instead of leaving the tensor cores idle in between."""
+        B, F, H, W = ws.B, ws.F, ws.H, ws.W
+        Bm = B // n_mb
+        if not ws.children:
+            for k in range(n_mb):
+                ws.children.append(self._Workspace(Bm, F, H, W, ws.dev, ws.pool.numel() // n_mb + 64, parent=ws,
+                                                   lo=k * Bm))
+            ws.mb_fork = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        ws.mb_fork.record(main)
+        rows_img = H * W
+        for k, child in enumerate(ws.children):
+            lo, hi = k * Bm * F, (k + 1) * Bm * F
+            sub = dict(a_in=pro['a_in'][lo * rows_img:hi * rows_img], amask=pro['amask'][lo:hi],
+                       emb_out=pro['emb_out'][lo:hi],
+                       rpe_et=None if pro['rpe_et'] is None else pro['rpe_et'][lo:hi],
+                       tables=pro['tables'], table_group0=lo)
+            child.stream.wait_event(ws.mb_fork)
+            with torch.cuda.stream(child.stream):
+                child.zero_stats()
+                child.emb_join, child.rpe_join = emb_join, rpe_join
+                self._body(child, sub, T_attn, None)
+                child.done.record(child.stream)
+        for child in ws.children:
+            main.wait_event(child.done)
+
+    def _body(self, ws, pro, T_attn, attn_log):
+        """input conv -> ... -> output head for the videos of `ws` (the whole batch or one micro-batch)."""
+        P, adt = self._packed, self.compute_dtype
+        B, F, H, W = ws.B, ws.F, ws.H, ws.W
+        N, ch = B * F, self.model_channels
+        a_in, amask, emb_out, rpe_et = pro['a_in'], pro['amask'], pro['emb_out'], pro['rpe_et']
+        tables = dict(pro['tables'])
+        tables['__group0__'] = pro.get('table_group0', 0)
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
         hs, x, cur_group, n_groups_done = [], None, None, 0
@@ -687,9 +774,9 @@ class UNetModel(nn.Module):
             elif kind == 'attn':
                 if T_attn != F:
                     raise NotImplementedError('cross_frame_attention=False')
-                if rpe_join is not None:
-                    torch.cuda.current_stream().wait_event(rpe_join)
-                    rpe_join = None
+                if ws.rpe_join is not None:
+                    torch.cuda.current_stream().wait_event(ws.rpe_join)
+                    ws.rpe_join = None
                 x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables, attn_log)
             elif kind == 'down':
                 C = node['C']
@@ -724,17 +811,16 @@ class UNetModel(nn.Module):
                     ops.gemm(x[0], P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
                              out_f32=out, C1=C)
                 x, H, W = (out, st), 2 * H, 2 * W
-        if rpe_join is not None:          # no attention block consumed the tables: still join the branch
-            torch.cuda.current_stream().wait_event(rpe_join)
+        for ev in (ws.rpe_join, ws.emb_join):       # a model without attention / scale-shift: still join the side branch
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+        ws.rpe_join = ws.emb_join = None
         h = x[0]
         st = self._stats_of(ws, 'out', h, x[1], N, H * W)
         a = ws.buf('out.a', (N * H * W, ch), adt)
         ops.gn_apply(h, None, N, H, W, a, stats1=st, gamma=P['out_gn_w'], beta=P['out_gn_b'], silu=True)
-        if ws.out is None:
-            ws.out = torch.empty(B, F, self.out_channels, H, W, device=ws.dev)
         ops.gemm(a, P['out_w'], self.out_channels, n_img=N, H=H, W=W, taps=9, bias=P['out_b'], out_f32=ws.out,
                  out_nchw=True)
-        return ws.out
 
     def _execute(self, x, *args, **kwargs):
         """Every libvdm launch goes to the current stream of the current device: make that the tensors' device."""
