@@ -226,6 +226,39 @@ def test_conv3x3_fused_groupnorm_silu(case, tmode, monkeypatch):
     assert relerr(out_b, nhwc(refb)) < 8e-3
 
 
+@pytest.mark.parametrize('M,N,K,n_prob', [(40960, 1152, 384, 1), (10240, 1536, 512, 1), (1000, 384, 384, 1),
+                                           (300, 128, 128, 1), (2560, 128, 384, 2), (777, 64, 192, 1)])
+def test_linear_tma_store_epilogue(M, N, K, n_prob, monkeypatch):
+    """The TMA-store epilogue of the plain linears (bias only; qkv, RPE score GEMMs) against the staged epilogue --
+    bit-exact -- and against torch, bf16 and fp32 outputs, ragged M, single-CTA and pair tiles, the two-problem form."""
+    o = ops()
+    a = rnd(M, K * n_prob, seed=1).bfloat16()
+    w = rnd(N * n_prob, K, seed=2, scale=K ** -0.5).bfloat16()
+    bias = rnd(N, seed=3) if n_prob == 1 else None
+    kw = dict(n_img=M, H=1, W=1, taps=1, bias=bias, C1=K)
+    if n_prob > 1:
+        kw.update(n_prob=n_prob, prob_a_cols=K, prob_w_rows=N, prob_out_stride=M * N)
+    res = {}
+    for ts in ('1', '0'):
+        monkeypatch.setenv('VDM_GEMM_TS', ts)
+        of = torch.full((n_prob, M, N), float('nan'), device='cuda')
+        o.gemm(a, w, N, out_f32=of, **kw)
+        ob = None
+        if n_prob == 1:
+            ob = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+            o.gemm(a, w, N, out_bf16=ob, **kw)
+        res[ts] = (of, ob)
+    torch.cuda.synchronize()
+    assert torch.equal(res['1'][0], res['0'][0])
+    if n_prob == 1:
+        assert torch.equal(res['1'][1], res['0'][1])
+    for i in range(n_prob):
+        ref = a[:, i * K:(i + 1) * K].float() @ w[i * N:(i + 1) * N].float().t() + (bias if bias is not None else 0)
+        assert relerr(res['1'][0][i], ref) < 2e-5
+        if n_prob == 1:
+            assert relerr(res['1'][1], ref) < 6e-3
+
+
 def test_fused_groupnorm_unsupported_shapes_raise():
     """a1_coef on a shape / epilogue the transform-stage kernels do not cover is an error, not a silent slow path."""
     o = ops()

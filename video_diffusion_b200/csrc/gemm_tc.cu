@@ -312,7 +312,9 @@ __device__ __forceinline__ void xf_publish_fence() {
   __syncwarp();
 }
 
-template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
+// TS_ESIZE > 0: the TMA-store epilogue (no statistics, no residual): the staging area holds the CTA's whole 128 x BLOCK_N
+// output tile (elements of TS_ESIZE bytes) as 128-byte-swizzled slabs of 128 rows x 128 B.
+template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false, int TS_ESIZE = 0>
 struct SmemLayout {
   static constexpr int CHUNK = (BLOCK_N < 32 || M_SUB > 1) ? 16 : 32;
   static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -323,10 +325,10 @@ struct SmemLayout {
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;                    // epilogue staging
   static constexpr int TOTAL_CHUNKS = M_SUB * (BLOCK_N / CHUNK);
   static constexpr int WARP_STG_FLOATS = 32 * (CHUNK + 4);
-  static constexpr int STG_BYTES = EPI_WARPS * WARP_STG_FLOATS * 4;
+  static constexpr int STG_BYTES = TS_ESIZE ? BLOCK_M * BLOCK_N * TS_ESIZE : EPI_WARPS * WARP_STG_FLOATS * 4;
   static constexpr int STAT_IMGS = 2;                                         // images a CTA tile may span (H*W >= 64)
   static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;                  // GroupNorm partial sums per lane quarter
-  static constexpr int STAT_BYTES = 4 * STAT_IMGS * 2 * BLOCK_N * 4;
+  static constexpr int STAT_BYTES = TS_ESIZE ? 0 : 4 * STAT_IMGS * 2 * BLOCK_N * 4;
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;         // + alignment slack
@@ -686,6 +688,107 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
   }
 }
 
+// ===================== epilogue role with TMA stores (plain linears: bias only, one output) =====================
+// The short-K linears of the attention blocks (qkv, the RPE score GEMMs) are bound by the epilogue above: per 32-column
+// chunk it stages, re-reads and issues eight row-quad stores per lane.  Here a lane keeps its accumulator ROW: it adds
+// the bias, converts and writes the row segment into a shared-memory image of the output tile (128-byte-swizzled slabs
+// of 128 rows x 128 B, the layout a SWIZZLE_128B tensor map expects; conflict-free 16-byte stores), and one elected
+// thread hands the finished tile to the TMA engine (cp.async.bulk.tensor store, fully coalesced, asynchronous: it
+// drains while the next tile's accumulator is converted).  Rows / columns beyond M / N are clipped by the tensor map.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+template <int BLOCK_N, bool BF16, bool CTA2>
+__device__ __forceinline__ void epilogue_ts_role(const TcParams& p, const CUtensorMap* tm_out, uint8_t* stg,
+                                                 uint32_t stg_addr, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                                 uint32_t tmem_empty_bar0, int n_tiles, int n_tiles_n, int work_id0,
+                                                 int work_step, uint32_t cta_rank, int warp, int lane) {
+  constexpr int TILE_M = BLOCK_M * (CTA2 ? 2 : 1);
+  constexpr int ESZ = BF16 ? 2 : 4;
+  constexpr int SLAB_COLS = 128 / ESZ;                 // output columns per 128-byte slab row
+  constexpr int N_SLABS = BLOCK_N / SLAB_COLS;
+  constexpr int SLAB_BYTES = BLOCK_M * 128;
+  constexpr int N_CHUNKS = BLOCK_N / 32;               // accumulator columns are read 32 at a time
+  const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+  const int row = q * 32 + lane;                       // tile row of this lane = its TMEM lane
+  uint8_t* const rowp = stg + row * 128;
+  const int sw = row & 7;
+  int it = 0;
+  for (int tile = work_id0; tile < n_tiles; tile += work_step, ++it) {
+    int par = 0, tl = tile;
+    if (p.tiles_per_par > 0) {
+      par = tile / p.tiles_per_par;
+      tl = tile - par * p.tiles_per_par;
+    }
+    const int n0 = (tl % n_tiles_n) * BLOCK_N;
+    const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    if (it > 0) {   // the previous tile's stores must have READ the staging area before it is overwritten
+      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    }
+    mbar_wait(tmem_full_bar0 + 8u * as, aphase, 2);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int jj = half; jj < N_CHUNKS; jj += 2) {
+      uint32_t acc[32];
+      tmem_ld_32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + jj * 32), acc);
+      float bv[32];
+      if (p.bias != nullptr) {      // the chunk's 32 bias values: uniform addresses, broadcast loads
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + jj * 32 + i));
+          bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if constexpr (BF16) {         // 32 columns = 64 B = four 16-byte pieces of slab jj / 2
+        uint8_t* const sp = rowp + (jj >> 1) * SLAB_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(acc[8 * k + 0]) + bv[8 * k + 0], __uint_as_float(acc[8 * k + 1]) + bv[8 * k + 1]);
+          v.y = pack_bf16x2(__uint_as_float(acc[8 * k + 2]) + bv[8 * k + 2], __uint_as_float(acc[8 * k + 3]) + bv[8 * k + 3]);
+          v.z = pack_bf16x2(__uint_as_float(acc[8 * k + 4]) + bv[8 * k + 4], __uint_as_float(acc[8 * k + 5]) + bv[8 * k + 5]);
+          v.w = pack_bf16x2(__uint_as_float(acc[8 * k + 6]) + bv[8 * k + 6], __uint_as_float(acc[8 * k + 7]) + bv[8 * k + 7]);
+          const int j = (jj & 1) * 4 + k;
+          *reinterpret_cast<uint4*>(sp + ((j ^ sw) << 4)) = v;
+        }
+      } else {                      // 32 columns = 128 B = the whole row of slab jj
+        uint8_t* const sp = rowp + jj * SLAB_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 v = make_float4(__uint_as_float(acc[4 * k + 0]) + bv[4 * k + 0], __uint_as_float(acc[4 * k + 1]) + bv[4 * k + 1],
+                                       __uint_as_float(acc[4 * k + 2]) + bv[4 * k + 2], __uint_as_float(acc[4 * k + 3]) + bv[4 * k + 3]);
+          *reinterpret_cast<float4*>(sp + ((k ^ sw) << 4)) = v;
+        }
+      }
+    }
+    // accumulator stage drained: hand it back to the MMA warp; then publish the tile image to the async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar0 + 8u * as, 0);
+      else mbar_arrive(tmem_empty_bar0 + 8u * as);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (ew == 0 && lane == 0) {
+#pragma unroll
+      for (int sl = 0; sl < N_SLABS; ++sl) tma_store_3d(tm_out, stg_addr + sl * SLAB_BYTES, n0 + sl * SLAB_COLS, m0, par);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+}
+
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every role loops over the CTA's
 // tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running together share A in L2).
 //   warp 0      : TMA producer (one lane), STAGES-deep smem ring
@@ -695,13 +798,17 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
 // is a runtime branch inside its row loop costs throughput): bit 0 residual add, bit 1 bf16 output (else
 // fp32), bit 2 GroupNorm statistics; bit 3 = generic path with every option decided at run time (per-image
 // bias, both outputs, NCHW store, folded-upsample row remap, ragged N).
+// bit 5 (with bit 1 = bf16): the TMA-store epilogue above (bias only, no residual / statistics), M_SUB == 1.
 template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
                                                                  const __grid_constant__ CUtensorMap tm_a2,
                                                                  const __grid_constant__ CUtensorMap tm_w,
+                                                                 const __grid_constant__ CUtensorMap tm_out,
                                                                  const TcParams p) {
   pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
-  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
+  constexpr bool TS = (EPI & 32) != 0;
+  static_assert(!TS || M_SUB == 1, "TMA-store epilogue: one 128-row sub-tile per CTA");
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2, TS ? ((EPI & 2) ? 2 : 4) : 0>;
   constexpr int TILE_M = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);     // rows per work tile (CTA or CTA pair)
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader
   const int work_id0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -924,7 +1031,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, CTA2>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
+    if constexpr (TS)
+      epilogue_ts_role<BLOCK_N, (EPI & 2) != 0, CTA2>(p, &tm_out, smem_gen + L::STG_OFFSET, smem_base + L::STG_OFFSET,
+                                                      tmem_base, tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n,
+                                                      work_id0, work_step, cta_rank, warp, lane);
+    else
+      epilogue_role<BLOCK_N, M_SUB, L::CHUNK, EPI, CTA2>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
                                              reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET),
                                              L::STAT_IMGS, tmem_base,
                                              tmem_full_bar(0), tmem_empty_bar(0), n_tiles, n_tiles_n, work_id0,
@@ -1728,7 +1840,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // bf16 tensor of up to 5 dims (innermost first), 128B swizzle, zero OOB fill.
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -1744,7 +1856,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
     estr[i] = 1;
     if (i > 0) gstrides[i - 1] = strides_bytes[i];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+  CUresult r = fn(map, dtype, rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1769,8 +1881,9 @@ int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C,
 
 template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
 int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
-                cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2>;
+                cudaStream_t stream, const CUtensorMap* mout = nullptr) {
+  constexpr bool TS = (EPI & 32) != 0;
+  using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2, TS ? ((EPI & 2) ? 2 : 4) : 0>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static PerDevice<bool> configured;
   if (!configured.get()) {
@@ -1784,29 +1897,16 @@ int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMa
   }
   constexpr int TILE_ROWS = BLOCK_M * M_SUB * (CTA2 ? 2 : 1);
   const int tiles = p.n_par * ((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + TILE_ROWS - 1) / TILE_ROWS);
+  const CUtensorMap& mo = mout ? *mout : mw;      // only read by the TMA-store epilogue
   if constexpr (CTA2) {
     // one CTA pair (a 2-CTA cluster on one TPC) per work tile; persistent over pairs
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = L::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, ma1, ma2, mw, p);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc (2-CTA): launch failed: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
+    launch_kernel(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, 2, ma1, ma2,
+                  mw, mo, p);
   } else {
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    launch_kernel(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, grid, NUM_THREADS, L::TOTAL, (cudaStream_t)stream, 1, ma1, ma2, mw, p);
+    launch_kernel(gemm_tc_kernel<BLOCK_N, M_SUB, STAGES, EPI, CTA2>, grid, NUM_THREADS, L::TOTAL, stream, 1, ma1, ma2, mw, mo,
+                  p);
   }
   VDM_AFTER_LAUNCH("gemm_tc");
   return 0;
@@ -1820,10 +1920,48 @@ int epilogue_variant(const TcParams& p, int block_n) {
   return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
 }
 
+// The TMA-store epilogue (variants 32 / 34) replaces the lean bias-only variants 0 / 2 wherever its output-tile staging
+// fits next to the operand ring; VDM_GEMM_TS=0 switches it off (tests compare the two).
+template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2, int ESZ>
+constexpr bool ts_fits() {
+  return M_SUB == 1 && BLOCK_N >= 64 && SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2, ESZ>::TOTAL <= 232448;
+}
+template <int BLOCK_N, int ESZ>
+int encode_out_map(CUtensorMap* mo, const TcParams& p) {
+  void* base = ESZ == 2 ? (void*)p.out_bf16 : (void*)p.out_f32;
+  const uint64_t ld = ESZ == 2 ? p.ld_out_bf16 : p.ld_out;
+  if (ld * ESZ % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return 1;   // not TMA-addressable
+  const uint64_t par_stride = p.n_par > 1 ? (uint64_t)p.par_out_stride : (uint64_t)p.M * ld;
+  if (par_stride * ESZ % 16 != 0) return 1;
+  uint64_t dims[3] = {(uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.n_par};
+  uint64_t st[3] = {(uint64_t)ESZ, ld * ESZ, par_stride * ESZ};
+  uint32_t box[3] = {128 / ESZ, BLOCK_M, 1};
+  return encode_map(mo, base, 3, dims, st, box, ESZ == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
 template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
 int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
            cudaStream_t stream) {
-  switch (epilogue_variant(p, BLOCK_N)) {
+  const int v = epilogue_variant(p, BLOCK_N);
+  const char* ts_env = getenv("VDM_GEMM_TS");
+  const bool ts_on = ts_env == nullptr || atoi(ts_env) != 0;
+  if (ts_on && v == 2) {
+    if constexpr (ts_fits<BLOCK_N, M_SUB, STAGES, CTA2, 2>()) {
+      CUtensorMap mo;
+      const int rc = encode_out_map<BLOCK_N, 2>(&mo, p);
+      if (rc < 0) return rc;
+      if (rc == 0) return launch_inst<BLOCK_N, M_SUB, STAGES, 34, CTA2>(ma1, ma2, mw, p, stream, &mo);
+    }
+  }
+  if (ts_on && v == 0) {
+    if constexpr (ts_fits<BLOCK_N, M_SUB, STAGES, CTA2, 4>()) {
+      CUtensorMap mo;
+      const int rc = encode_out_map<BLOCK_N, 4>(&mo, p);
+      if (rc < 0) return rc;
+      if (rc == 0) return launch_inst<BLOCK_N, M_SUB, STAGES, 32, CTA2>(ma1, ma2, mw, p, stream, &mo);
+    }
+  }
+  switch (v) {
     case 0: return launch_inst<BLOCK_N, M_SUB, STAGES, 0, CTA2>(ma1, ma2, mw, p, stream);
     case 1: return launch_inst<BLOCK_N, M_SUB, STAGES, 1, CTA2>(ma1, ma2, mw, p, stream);
     case 2: return launch_inst<BLOCK_N, M_SUB, STAGES, 2, CTA2>(ma1, ma2, mw, p, stream);
