@@ -27,7 +27,7 @@ extern "C" {
 
 typedef void* vdm_stream_t; /* cudaStream_t */
 
-enum { VDM_F32 = 0, VDM_BF16 = 1, VDM_F64 = 2, VDM_I64 = 3 };
+enum { VDM_F32 = 0, VDM_BF16 = 1, VDM_F64 = 2, VDM_I64 = 3, VDM_F16 = 4 };
 
 int vdm_version(void);
 const char* vdm_last_error_string(void);
@@ -101,6 +101,10 @@ typedef struct {
                            Only the halo kernels take it: vdm_gemm_fused_norm_supported() tells; other shapes are an
                            error, never a silent slow path */
   int32_t a1_act;       /* with a1_coef: 1 = SiLU after the affine, 0 = affine only */
+  int32_t io_dtype;     /* bf16 kernel: VDM_F32 (default) or VDM_F16 = `out_f32` and `residual` point to IEEE half tensors
+                           (same leading dimensions, in elements).  The residual stream of the bf16 model is kept in fp16
+                           (11-bit mantissa, conversions saturate): half the HBM traffic of every stream read / write;
+                           accumulation, bias / residual adds and the GroupNorm statistics stay fp32 */
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
@@ -116,6 +120,9 @@ int vdm_gemm_fused_norm_supported(const vdm_gemm_args* args);
  * whichever concat consumes it.  vdm_gn_stats fills a double-precision table (caller zeroes it); the
  * bf16 GEMM epilogue fills a 64-bit fixed-point one (vdm_gemm_args.stats_out). */
 int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t HW, double* stats, vdm_stream_t stream);
+/* the same for an fp16 (VDM_F16) or fp32 source */
+int vdm_gn_stats_t(const void* src, int32_t src_dtype, int32_t C, int32_t n_img, int32_t HW, double* stats,
+                   vdm_stream_t stream);
 
 typedef struct {
   const void* src1; int32_t C1;       /* [n_img*HW][C1], fp32 (or bf16 when src1_dtype == VDM_BF16 and C2 == 0) */
@@ -132,10 +139,11 @@ typedef struct {
   int32_t out_mode;                   /* 0 plain, 1 nearest-x2 upsampled, 2 stride-2 parity planes */
   int32_t out_dtype;                  /* VDM_F32 | VDM_BF16 */
   void* out;                          /* GEMM A operand */
-  int32_t src1_dtype;                 /* VDM_F32 | VDM_BF16 */
+  int32_t src1_dtype;                 /* VDM_F32 | VDM_F16 (src2 alike) | VDM_BF16 (single source) */
   void* out_raw;                      /* optional second output: the un-normalised input cast to out_dtype, plain
                                          layout (A operand of the 1x1 skip projection, unet.py:172-173) */
   float* out_f32_copy;                /* optional fp32 copy of the plain output (attention residual) */
+  int32_t copy_dtype;                 /* of out_f32_copy: VDM_F32 (default) | VDM_F16 */
 } vdm_gn_apply_args;
 
 int vdm_gn_apply(const vdm_gn_apply_args* args, vdm_stream_t stream);
@@ -153,6 +161,10 @@ int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, const void*
 int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C,
                     const float* gamma, const float* beta, float* out_f32,
                     void* out_a, int32_t out_dtype, vdm_stream_t stream);
+/* the same with x and the normalised residual copy `out_res` in io_dtype (VDM_F32 | VDM_F16: the fp16 stream) */
+int vdm_gn_temporal_t(const void* x, int32_t io_dtype, int32_t B, int32_t T, int32_t HW, int32_t C,
+                      const float* gamma, const float* beta, void* out_res, void* out_a, int32_t out_dtype,
+                      vdm_stream_t stream);
 
 /* out[m][c] = (h[m][c] + enc[m % HW][c]) + frame_emb[m / HW][c]: the learned spatial_encoding add
  * (unet.py:841-844) and, with use_frame_encoding, the per-frame sinusoid (unet.py:914-926; frame_emb is
@@ -160,6 +172,9 @@ int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C,
  * out may alias h. */
 int vdm_add_spatial_encoding(const float* h, const float* enc, const float* frame_emb, float* out,
                              int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream);
+/* the same with h / out in io_dtype (VDM_F32 | VDM_F16) */
+int vdm_add_spatial_encoding_t(const void* h, int32_t io_dtype, const float* enc, const float* frame_emb, void* out,
+                               int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream);
 
 /* ---- conditioning mix + input-conv im2col -----------------------------------------------
  * Replaces CondMargVideoModel.forward's masking / indicator channels / per-frame timesteps (unet.py:951-1019).

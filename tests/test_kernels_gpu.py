@@ -259,6 +259,113 @@ def test_linear_tma_store_epilogue(M, N, K, n_prob, monkeypatch):
             assert relerr(res['1'][1], ref) < 6e-3
 
 
+F16_IO_CASES = [
+    # n, H, W, C1, N, C2, residual, taps, halo mode
+    (3, 64, 64, 128, 128, 0, True, 9, '2'),       # transposed-role kernel
+    (2, 64, 64, 64, 128, 128, False, 9, '2'),
+    (5, 32, 32, 128, 256, 0, True, 9, '2'),       # pair halo kernel
+    (7, 8, 8, 64, 512, 128, False, 9, '2'),       # interleaved 8x8 tiles, fused skip operand
+    (12, 8, 8, 128, 256, 0, True, 9, '2'),
+    (3, 128, 128, 128, 128, 0, True, 9, '2'),     # wide-slot transposed kernel
+    (5, 8, 8, 128, 128, 0, True, 9, '0'),         # plain kernel, ragged tile
+    (3, 16, 16, 384, 384, 0, True, 1, '0'),       # attention proj_out: linear with residual + statistics
+    (4, 4, 4, 64, 64, 0, True, 9, '0'),           # no fused statistics (H*W % 32 != 0): variants 64 / 65
+]
+
+
+@pytest.mark.parametrize('case', F16_IO_CASES, ids=lambda c: 'n%d_%dx%d_c%d_n%d_c2_%d_res%d_t%d_h%s' % c)
+def test_gemm_fp16_stream_io(case, monkeypatch):
+    """`io_dtype` = fp16: out_f32 / residual are half tensors (the bf16 model's residual stream).  Accumulation, adds and
+    statistics are unchanged fp32, so the result is exactly the fp32-IO result rounded to half, statistics identical."""
+    n, H, W, C1, N, C2, use_res, taps, halo = case
+    o = ops()
+    monkeypatch.setenv('VDM_GEMM_HALO', halo)
+    x = nhwc(rnd(n, C1, H, W, seed=1)).bfloat16()
+    w = rnd(N, taps * C1 + C2, seed=2, scale=(taps * C1) ** -0.5).bfloat16()
+    a2 = nhwc(rnd(n, C2, H, W, seed=5)).bfloat16() if C2 else None
+    bias = rnd(N, seed=3)
+    res16 = rnd(n * H * W, N, seed=4).half() if use_res else None
+    with_stats = (H * W) % 32 == 0
+    kw = dict(n_img=n, H=H, W=W, taps=taps, a2=a2, bias=bias, C1=C1)
+    o32 = torch.full((n * H * W, N), float('nan'), device='cuda')
+    o16 = torch.full((n * H * W, N), float('nan'), device='cuda', dtype=torch.float16)
+    st32 = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64) if with_stats else None
+    st16 = torch.zeros_like(st32) if with_stats else None
+    o.gemm(x, w, N, residual=None if res16 is None else res16.float(), out_f32=o32, stats_out=st32, **kw)
+    o.gemm(x, w, N, residual=res16, out_f32=o16, stats_out=st16, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(o16, o32.half())
+    if with_stats:
+        assert torch.equal(st16, st32)
+    with pytest.raises(TypeError):           # mixed stream dtypes are refused, not reinterpreted
+        o.gemm(x, w, N, residual=rnd(n * H * W, N, seed=4), out_f32=o16, **kw)
+
+
+def test_upsample_fold_and_elementwise_fp16_stream(monkeypatch):
+    """The folded-upsample conv writing an fp16 stream, and the stream's elementwise consumers / producers
+    (gn_stats, gn_apply incl. concat + raw copy + fp16 residual copy, temporal GroupNorm, spatial-encoding add) fed
+    with fp16: same results as the fp32 forms on the same (fp16-representable) values."""
+    o = ops()
+    n, Hl, Wl, C, N = 3, 16, 16, 128, 128
+    from video_diffusion_b200.unet import fold_upsample_weights
+    x = nhwc(rnd(n, C, Hl, Wl, seed=1)).bfloat16()
+    wf = fold_upsample_weights(rnd(N, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)).bfloat16()
+    bias = rnd(N, seed=3)
+    for halo in ('2', '0'):
+        monkeypatch.setenv('VDM_GEMM_HALO', halo)
+        o32 = torch.empty(n * 4 * Hl * Wl, N, device='cuda')
+        o16 = torch.empty(n * 4 * Hl * Wl, N, device='cuda', dtype=torch.float16)
+        s32 = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+        s16 = torch.zeros_like(s32)
+        o.gemm(x, wf, N, n_img=n, H=2 * Hl, W=2 * Wl, taps=4, a1_mode=3, bias=bias, out_f32=o32, stats_out=s32, C1=C)
+        o.gemm(x, wf, N, n_img=n, H=2 * Hl, W=2 * Wl, taps=4, a1_mode=3, bias=bias, out_f32=o16, stats_out=s16, C1=C)
+        assert torch.equal(o16, o32.half()) and torch.equal(s16, s32)
+    # elementwise kernels
+    n, H, W, C1, C2 = 3, 8, 8, 128, 64
+    Cc = C1 + C2
+    h1, h2 = rnd(n * H * W, C1, seed=4).half(), rnd(n * H * W, C2, seed=5).half()
+    st = [torch.zeros(n, 2, c, device='cuda', dtype=torch.float64) for c in (C1, C2)]
+    st_f = [torch.zeros_like(t) for t in st]
+    for src, a, b in ((h1, st[0], st_f[0]), (h2, st[1], st_f[1])):
+        o.gn_stats(src, n, H * W, a)
+        o.gn_stats(src.float(), n, H * W, b)
+        assert torch.equal(a, b)
+    gamma, beta = rnd(Cc, seed=6), rnd(Cc, seed=7)
+    outs = []
+    for cast in (lambda t: t, lambda t: t.float()):
+        out = torch.empty(n * H * W, Cc, device='cuda', dtype=torch.bfloat16)
+        raw = torch.empty_like(out)
+        o.gn_apply(cast(h1), cast(h2), n, H, W, out, stats1=st[0], stats2=st[1], gamma=gamma, beta=beta, silu=True,
+                   out_raw=raw)
+        cp = torch.empty(n * H * W, C1, device='cuda', dtype=cast(h1).dtype)
+        out1 = torch.empty(n * H * W, C1, device='cuda', dtype=torch.bfloat16)
+        o.gn_apply(cast(h1), None, n, H, W, out1, stats1=st[0], gamma=gamma[:C1].contiguous(), beta=beta[:C1].contiguous(),
+                   copy=cp)
+        outs.append((out, raw, out1, cp))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][3], outs[1][3].half())
+    B, T, HW, Ct = 2, 20, 16, 384
+    xt = rnd(B, T, HW, Ct, seed=8).half()
+    g2, b2 = rnd(Ct, seed=9), rnd(Ct, seed=10)
+    r16, a16 = torch.empty_like(xt), torch.empty_like(xt, dtype=torch.bfloat16)
+    r32, a32 = torch.empty_like(xt, dtype=torch.float32), torch.empty_like(a16)
+    o.gn_temporal(xt, B, T, HW, Ct, g2, b2, r16, a16)
+    o.gn_temporal(xt.float(), B, T, HW, Ct, g2, b2, r32, a32)
+    assert torch.equal(a16, a32) and torch.equal(r16, r32.half())
+    xg = rnd(2, 7, HW, 192, seed=11).half()                      # general (two-pass) temporal kernel
+    r16, a16 = torch.empty_like(xg), torch.empty_like(xg, dtype=torch.bfloat16)
+    r32, a32 = torch.empty_like(xg, dtype=torch.float32), torch.empty_like(a16)
+    o.gn_temporal(xg, 2, 7, HW, 192, g2[:192].contiguous(), b2[:192].contiguous(), r16, a16)
+    o.gn_temporal(xg.float(), 2, 7, HW, 192, g2[:192].contiguous(), b2[:192].contiguous(), r32, a32)
+    assert torch.equal(a16, a32) and torch.equal(r16, r32.half())
+    h = rnd(B * T * HW, Ct, seed=12).half()
+    enc, femb = rnd(HW, Ct, seed=13), rnd(B * T, Ct, seed=14)
+    e16, e32 = torch.empty_like(h), torch.empty_like(h, dtype=torch.float32)
+    o.add_spatial_encoding(h, enc, e16, B * T, HW, Ct, frame_emb=femb)
+    o.add_spatial_encoding(h.float(), enc, e32, B * T, HW, Ct, frame_emb=femb)
+    assert torch.equal(e16, e32.half())
+
+
 def test_fused_groupnorm_unsupported_shapes_raise():
     """a1_coef on a shape / epilogue the transform-stage kernels do not cover is an error, not a silent slow path."""
     o = ops()

@@ -231,6 +231,7 @@ def test_fused_norm_model_equals_standalone(golden, monkeypatch):
     for fuse in (False, True):
         model, _ = build_model(case['cfg'], golden, torch.bfloat16)
         model.fuse_norm = fuse
+        model.stream_dtype = torch.float32            # the transform-stage kernels are built for the fp32 stream
         with torch.no_grad():
             out, _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
         ws = next(iter(model._workspaces.values()))

@@ -11,14 +11,14 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvdm.so')
 
-F32, BF16, F64, I64 = 0, 1, 2, 3
+F32, BF16, F64, I64, F16 = 0, 1, 2, 3, 4
 TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOGVAR=4, MODEL_VAR=5, ACP=6,
            ACP_PREV=7, POST_LOGVAR=8, SQRT_ACP=9, SQRT_1M_ACP=10, LOG_1M_ACP=11, POST_VAR=12, RECIP_POST_C1=13,
            POST_C2_DIV_C1=14, ACP_NEXT=15)
 TAB_COUNT = 16
 
-EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gn_stats', 'vdm_gn_apply', 'vdm_gn_coef',
-           'vdm_gn_temporal', 'vdm_add_spatial_encoding', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
+EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gn_stats', 'vdm_gn_stats_t', 'vdm_gn_apply', 'vdm_gn_coef',
+           'vdm_gn_temporal', 'vdm_gn_temporal_t', 'vdm_add_spatial_encoding', 'vdm_add_spatial_encoding_t', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
            'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_error', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_lincomb',
            'vdm_vb_terms', 'vdm_prior_bpd']
 
@@ -32,13 +32,13 @@ class GemmArgs(C.Structure):
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
                 ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp), ('n_prob', _i32),
                 ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64), ('a1_coef', _vp),
-                ('a1_act', _i32)]
+                ('a1_act', _i32), ('io_dtype', _i32)]
 
 
 class GnApplyArgs(C.Structure):
     _fields_ = [('src1', _vp), ('C1', _i32), ('src2', _vp), ('C2', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
                 ('stats1', _vp), ('stats2', _vp), ('stats_dtype', _i32), ('stats2_dtype', _i32), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
-                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('src1_dtype', _i32), ('out_raw', _vp), ('out_f32_copy', _vp)]
+                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('src1_dtype', _i32), ('out_raw', _vp), ('out_f32_copy', _vp), ('copy_dtype', _i32)]
 
 
 _lib = None
@@ -61,6 +61,9 @@ def load():
     sig = {
         'vdm_gemm': [C.POINTER(GemmArgs), _vp],
         'vdm_gn_stats': [_vp, _i32, _i32, _i32, _vp, _vp],
+        'vdm_gn_stats_t': [_vp, _i32, _i32, _i32, _i32, _vp, _vp],
+        'vdm_gn_temporal_t': [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
+        'vdm_add_spatial_encoding_t': [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
         'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
         'vdm_gemm_fused_norm_supported': [C.POINTER(GemmArgs)],
         'vdm_gn_coef': [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -121,5 +124,5 @@ def launch_count():
 
 def dt(code_or_dtype):
     if isinstance(code_or_dtype, int):
-        return torch.bfloat16 if code_or_dtype == BF16 else torch.float32
-    return BF16 if code_or_dtype == torch.bfloat16 else F32
+        return {BF16: torch.bfloat16, F16: torch.float16}.get(code_or_dtype, torch.float32)
+    return {torch.bfloat16: BF16, torch.float16: F16}.get(code_or_dtype, F32)

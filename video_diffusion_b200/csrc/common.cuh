@@ -1,6 +1,7 @@
 // Shared helpers for libvdm.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -124,6 +125,23 @@ template <>
 __device__ __forceinline__ void store_elem<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// fp32 pair -> packed IEEE half pair, round to nearest, SATURATING (a value beyond +-65504 clamps instead of
+// becoming inf): the residual stream of the bf16 model is stored in fp16
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ uint16_t f32_to_f16_bits(float a) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float f16_bits_to_f32(uint16_t v) { return __half2float(__ushort_as_half(v)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

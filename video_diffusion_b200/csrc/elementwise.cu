@@ -3,16 +3,41 @@
 // conditioning mix + input-conv im2col, timestep sinusoid, RPE-net hidden layer.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace vdm {
 namespace {
 
+// The residual stream is fp32 (reference-accuracy mode, tests) or fp16 (the bf16 model): IoT = float | __half.
+template <typename IoT>
+__device__ __forceinline__ float4 load4(const IoT* p) {
+  if constexpr (sizeof(IoT) == 2) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 lo = unpack_f16x2(h.x), hi = unpack_f16x2(h.y);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else {
+    return __ldg(reinterpret_cast<const float4*>(p));
+  }
+}
+template <typename IoT>
+__device__ __forceinline__ void store4(IoT* p, float4 v) {
+  if constexpr (sizeof(IoT) == 2) {
+    uint2 h;
+    h.x = pack_f16x2(v.x, v.y);
+    h.y = pack_f16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = h;
+  } else {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm statistics
 // Per-(image, channel) sum and sum of squares: stats[n][0][c], stats[n][1][c] (double).
 // grid (pixel chunks, n_img); block = (C/4) x rows threads; each thread owns 4 channels.
-__global__ void gn_stats_kernel(const float* __restrict__ src, int C, int HW, int pix_per_block,
+template <typename IoT>
+__global__ void gn_stats_kernel(const IoT* __restrict__ src, int C, int HW, int pix_per_block,
                                 double* __restrict__ stats) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
@@ -23,7 +48,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ src, int C, int HW, in
   const int p1 = min(HW, p0 + pix_per_block);
   double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   for (int p = p0 + prow; p < p1; p += rows) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(src + ((size_t)n * HW + p) * C + cq * 4));
+    const float4 t = load4(src + ((size_t)n * HW + p) * C + cq * 4);
     const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -48,7 +73,8 @@ struct ApplyParams {
   const float* gamma; const float* beta;
   const float* ss; int ld_ss;
   int silu, out_mode;
-  void* out; void* out_raw; float* copy;
+  void* out; void* out_raw; void* copy;
+  int copy_f16;
   int pix_per_block;
 };
 
@@ -56,6 +82,8 @@ struct ApplyParams {
 // of pixels, so its per-channel multiplier / offset live in registers for the whole loop.
 // dynamic smem: 2*C doubles (per-channel sums) + 64 floats (group mean / rstd)
 // MODE: 0 plain, 1 nearest-x2, 2 stride-2 parity planes; RAW / COPY: optional extra outputs.
+// InT: float, __half (fp16 residual stream; two-source concat allowed like float) or __nv_bfloat16 (conv output kept in
+// bf16, single source).
 template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   pdl_launch_dependents();
@@ -134,17 +162,26 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
     }
   }
   const bool silu = p.silu != 0;
-  // bf16 input (a conv output kept only in bf16) is single-source; fp32 input may be a two-source concat
+  // bf16 input (a conv output kept only in bf16) is single-source; fp32 / fp16 input may be a two-source concat
   const int ld = (c < p.C1) ? p.C1 : p.C2;
   const InT* src = (c < p.C1) ? reinterpret_cast<const InT*>(p.s1) + (size_t)n * HW * p.C1 + c
                               : reinterpret_cast<const InT*>(p.s2) + (size_t)n * HW * p.C2 + (c - p.C1);
   OutT* const out = reinterpret_cast<OutT*>(p.out) + c;
   OutT* const out_raw = RAW ? reinterpret_cast<OutT*>(p.out_raw) + (size_t)n * HW * C + c : nullptr;
-  float* const copy = COPY ? p.copy + (size_t)n * HW * C + c : nullptr;
+  const size_t copy_off = (size_t)n * HW * C + c;
   const int p0 = blockIdx.x * p.pix_per_block;
   const int p1 = min(HW, p0 + p.pix_per_block);
   auto load8 = [&](const InT* ptr, float (&x)[8]) {
-    if constexpr (sizeof(InT) == 2) {
+    if constexpr (std::is_same<InT, __half>::value) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(ptr));
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_f16x2(w[i]);
+        x[2 * i] = f.x;
+        x[2 * i + 1] = f.y;
+      }
+    } else if constexpr (sizeof(InT) == 2) {
       const uint4 r = __ldg(reinterpret_cast<const uint4*>(ptr));
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -178,9 +215,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
     }
     if constexpr (RAW) store8(out_raw + (size_t)pix * C, x);
     if constexpr (COPY) {
-      float* cp = copy + (size_t)pix * C;
-      *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(cp + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      const size_t o = copy_off + (size_t)pix * C;
+      if (p.copy_f16) {
+        uint4 pk;
+        pk.x = pack_f16x2(y[0], y[1]); pk.y = pack_f16x2(y[2], y[3]);
+        pk.z = pack_f16x2(y[4], y[5]); pk.w = pack_f16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.copy) + o) = pk;
+      } else {
+        float* cp = reinterpret_cast<float*>(p.copy) + o;
+        *reinterpret_cast<float4*>(cp) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(cp + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
     }
     if constexpr (MODE == 0) {
       store8(out + ((size_t)n * HW + pix) * C, y);
@@ -274,10 +319,10 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const void* st1, int st_ki
 // pass 1 streams the pixel's T x C values with coalesced float4 loads and accumulates per-channel
 // sums in shared memory, 32 lanes fold them into group statistics, pass 2 re-reads (L1/L2-hot),
 // normalises and writes the fp32 residual copy and the GEMM A operand.
-template <typename OutT>
-__global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restrict__ x, int T, int HW, int C,
+template <typename OutT, typename IoT>
+__global__ void __launch_bounds__(256) gn_temporal_kernel(const IoT* __restrict__ x, int T, int HW, int C,
                                                            const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ out_f32,
+                                                           const float* __restrict__ beta, IoT* __restrict__ out_f32,
                                                            OutT* __restrict__ out_a) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
@@ -292,15 +337,15 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
   float* gm = ga + 32;
   const int cpg = C / 32, C4 = C / 4;
   const size_t frame_stride = (size_t)HW * C;
-  const float* base = x + (size_t)b * T * frame_stride + (size_t)pix * C;
+  const IoT* base = x + (size_t)b * T * frame_stride + (size_t)pix * C;
   // Per-channel sums are taken about a pivot (the channel's value in the first frame), so channels with
   // |mean| >> std lose no precision to E[x^2] - mean^2 cancellation (the reference's GroupNorm is two-pass).
   // chs <- per-channel mean, chq <- per-channel sum of squared deviations from that mean.
   for (int q4 = lane; q4 < C4; q4 += 32) {
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + q4 * 4));
+    const float4 v0 = load4(base + q4 * 4);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     for (int t = 1; t < T; ++t) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(base + t * frame_stride + q4 * 4));
+      float4 v = load4(base + t * frame_stride + q4 * 4);
       v.x -= v0.x; v.y -= v0.y; v.z -= v0.z; v.w -= v0.w;
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
@@ -337,10 +382,10 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
     }
     for (int t = 0; t < T; ++t) {
       const size_t off = (size_t)b * T * frame_stride + t * frame_stride + (size_t)pix * C + c;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+      const float4 v = load4(x + off);
       const float y0 = fmaf(v.x - mu[0], a[0], bb[0]), y1 = fmaf(v.y - mu[1], a[1], bb[1]);
       const float y2 = fmaf(v.z - mu[2], a[2], bb[2]), y3 = fmaf(v.w - mu[3], a[3], bb[3]);
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
+      if (out_f32) store4(out_f32 + off, make_float4(y0, y1, y2, y3));
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
         pk.x = pack_bf16x2(y0, y1);
@@ -357,11 +402,11 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const float* __restric
 // its float4 column of all T frames in registers, the lanes of a group fold their sums with shuffles, and the values
 // are normalised and written without touching memory twice.  B * HW * n_slabs warps: enough parallelism for the
 // 8x8 level too (the kernel above launches only B * HW / 8 blocks there).
-template <typename OutT, int TMAX>
-__global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __restrict__ x, int B, int T, int HW, int C,
+template <typename OutT, int TMAX, typename IoT>
+__global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __restrict__ x, int B, int T, int HW, int C,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta,
-                                                                float* __restrict__ out_f32, OutT* __restrict__ out_a,
+                                                                IoT* __restrict__ out_f32, OutT* __restrict__ out_a,
                                                                 int gps, int n_slabs) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
@@ -378,11 +423,10 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
   const size_t off0 = (size_t)b * T * frame_stride + (size_t)pix * C + c;
   float4 v[TMAX];          // TMAX >= T: the frame loop is fully unrolled, every load is in flight before the first use
   float s = 0.f;
-  const float4* src = reinterpret_cast<const float4*>(x + off0);
-  const size_t stride4 = frame_stride / 4;
+  const IoT* src = x + off0;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
-    if (t < T && active) v[t] = __ldg(src + t * stride4);
+    if (t < T && active) v[t] = load4(src + t * frame_stride);
   }
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
@@ -416,7 +460,7 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
       const size_t off = off0 + t * frame_stride;
       const float y0 = fmaf(v[t].x - mean, a0, b0), y1 = fmaf(v[t].y - mean, a1, b1);
       const float y2 = fmaf(v[t].z - mean, a2, b2), y3 = fmaf(v[t].w - mean, a3, b3);
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y0, y1, y2, y3);
+      if (out_f32) store4(out_f32 + off, make_float4(y0, y1, y2, y3));
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
         pk.x = pack_bf16x2(y0, y1);
@@ -430,14 +474,22 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const float* __re
 }
 
 // out = (h + enc[pixel]) + frame_emb[image]; either addend may be absent (unet.py:841-844, 914-926)
-__global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* h, const float* __restrict__ enc,
-                                                                    const float* __restrict__ frame_emb, float* out,
+template <typename IoT>
+__global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const IoT* h, const float* __restrict__ enc,
+                                                                    const float* __restrict__ frame_emb, IoT* out,
                                                                     long long total4, long long per_img4, int C4) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(h)[i];
+    float4 v;
+    if constexpr (sizeof(IoT) == 2) {     // out may alias h: plain loads
+      const uint2 hh = reinterpret_cast<const uint2*>(h)[i];
+      const float2 lo = unpack_f16x2(hh.x), hi = unpack_f16x2(hh.y);
+      v = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      v = reinterpret_cast<const float4*>(h)[i];
+    }
     if (enc) {
       const float4 e = __ldg(reinterpret_cast<const float4*>(enc) + (i % per_img4));
       v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
@@ -446,7 +498,7 @@ __global__ void __launch_bounds__(256) add_spatial_encoding_kernel(const float* 
       const float4 e = __ldg(reinterpret_cast<const float4*>(frame_emb) + (i / per_img4) * C4 + (i % C4));
       v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
     }
-    reinterpret_cast<float4*>(out)[i] = v;
+    store4(out + 4 * i, v);
   }
 }
 
@@ -635,7 +687,13 @@ using namespace vdm;
 
 extern "C" int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t HW, double* stats,
                             vdm_stream_t stream) {
+  return vdm_gn_stats_t(src, VDM_F32, C, n_img, HW, stats, stream);
+}
+
+extern "C" int vdm_gn_stats_t(const void* src, int32_t src_dtype, int32_t C, int32_t n_img, int32_t HW, double* stats,
+                              vdm_stream_t stream) {
   VDM_REQUIRE(src && stats && C > 0, "gn_stats: NULL pointer");
+  VDM_REQUIRE(src_dtype == VDM_F32 || src_dtype == VDM_F16, "gn_stats: source must be fp32 or fp16");
   VDM_REQUIRE(C % 32 == 0 && C <= 4096, "gn_stats: unsupported channel count %d", C);
   const int C4 = C / 4;
   const int rows = C4 >= 256 ? 1 : 256 / C4;
@@ -643,7 +701,10 @@ extern "C" int vdm_gn_stats(const float* src, int32_t C, int32_t n_img, int32_t 
   int ppb = 256;
   while (ppb > 16 && (long long)((HW + ppb - 1) / ppb) * n_img < 2LL * num_sms()) ppb >>= 1;
   dim3 grid((HW + ppb - 1) / ppb, n_img);
-  launch_kernel(gn_stats_kernel, grid, threads, 0, (cudaStream_t)(cudaStream_t)stream, 1, src, C, HW, ppb, stats);
+  if (src_dtype == VDM_F16)
+    launch_kernel(gn_stats_kernel<__half>, grid, threads, 0, (cudaStream_t)stream, 1, (const __half*)src, C, HW, ppb, stats);
+  else
+    launch_kernel(gn_stats_kernel<float>, grid, threads, 0, (cudaStream_t)stream, 1, (const float*)src, C, HW, ppb, stats);
   VDM_AFTER_LAUNCH("gn_stats");
   return 0;
 }
@@ -661,7 +722,7 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_mode == 0 || a->out_f32_copy == nullptr, "gn_apply: fp32 copy only with plain output");
   ApplyParams p{a->src1, a->C1, a->src2, a->C2, a->n_img, a->H, a->W, a->stats1, a->stats2,
                 a->stats_dtype, a->stats2_dtype, a->gamma, a->beta, a->scale_shift, a->ld_ss, a->silu, a->out_mode,
-                a->out, a->out_raw, a->out_f32_copy, 0};
+                a->out, a->out_raw, a->out_f32_copy, a->copy_dtype == VDM_F16 ? 1 : 0, 0};
   const int HW = a->H * a->W;
   const int C8 = C / 8;
   const int rows = C8 >= 256 ? 1 : 256 / C8;
@@ -687,7 +748,10 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
     else if (copy) VDM_GN_LAUNCH(OUT, IN, 0, false, true);                   \
     else VDM_GN_LAUNCH(OUT, IN, 0, false, false);                            \
   } while (0)
+  VDM_REQUIRE(a->src1_dtype != VDM_F16 || a->out_dtype == VDM_BF16, "gn_apply: an fp16 stream feeds bf16 operands only");
+  VDM_REQUIRE(a->copy_dtype == VDM_F32 || a->copy_dtype == VDM_F16, "gn_apply: bad copy_dtype");
   if (a->src1_dtype == VDM_BF16) VDM_GN_BY_MODE(__nv_bfloat16, __nv_bfloat16);
+  else if (a->src1_dtype == VDM_F16) VDM_GN_BY_MODE(__nv_bfloat16, __half);
   else if (a->out_dtype == VDM_BF16) VDM_GN_BY_MODE(__nv_bfloat16, float);
   else VDM_GN_BY_MODE(float, float);
 #undef VDM_GN_BY_MODE
@@ -711,10 +775,9 @@ extern "C" int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, 
   return 0;
 }
 
-extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C, const float* gamma,
-                               const float* beta, float* out_f32, void* out_a, int32_t out_dtype, vdm_stream_t stream) {
-  VDM_REQUIRE(x && gamma && beta && out_a, "gn_temporal: NULL pointer");
-  VDM_REQUIRE(C % 32 == 0 && C <= 1024, "gn_temporal: C=%d must be a multiple of 32, <= 1024", C);
+template <typename OutT, typename IoT>
+static int gn_temporal_launch(const IoT* x, int B, int T, int HW, int C, const float* gamma, const float* beta,
+                              IoT* out_res, OutT* out_a, cudaStream_t stream) {
   if (C % 128 == 0 && T <= 32) {   // register-resident single pass
     const int l4 = C / 128;                       // float4 lanes per group
     int gps = 32 / l4;                            // groups a warp can hold ...
@@ -722,15 +785,8 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
     const int n_slabs = 32 / gps;
     const long long warps = (long long)B * HW * n_slabs;
     const unsigned grid = (unsigned)((warps + 3) / 4);
-#define VDM_GNT(TM)                                                                                                  \
-  do {                                                                                                               \
-    if (out_dtype == VDM_BF16)                                                                                       \
-      launch_kernel(gn_temporal_regs_kernel<__nv_bfloat16, TM>, grid, 128, 0, (cudaStream_t)(cudaStream_t)stream, 1,                             \
-          x, B, T, HW, C, gamma, beta, out_f32, (__nv_bfloat16*)out_a, gps, n_slabs);                                \
-    else                                                                                                             \
-      launch_kernel(gn_temporal_regs_kernel<float, TM>, grid, 128, 0, (cudaStream_t)(cudaStream_t)stream, 1, x, B, T, HW, C, gamma, beta, out_f32, \
-                                                                                (float*)out_a, gps, n_slabs);        \
-  } while (0)
+#define VDM_GNT(TM) \
+  launch_kernel(gn_temporal_regs_kernel<OutT, TM, IoT>, grid, 128, 0, stream, 1, x, B, T, HW, C, gamma, beta, out_res, out_a, gps, n_slabs)
     if (T <= 8) VDM_GNT(8);
     else if (T <= 16) VDM_GNT(16);
     else if (T <= 24) VDM_GNT(24);
@@ -741,26 +797,55 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
   }
   dim3 grid((HW + 7) / 8, B);
   const size_t smem = 8 * (2 * (size_t)C + 64) * sizeof(float);
-  if (out_dtype == VDM_BF16) {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
-    launch_kernel(gn_temporal_kernel<__nv_bfloat16>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, x, T, HW, C, gamma, beta, out_f32,
-                                                                                (__nv_bfloat16*)out_a);
-  } else {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(gn_temporal_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4); cfg = true; }
-    launch_kernel(gn_temporal_kernel<float>, grid, 256, smem, (cudaStream_t)(cudaStream_t)stream, 1, x, T, HW, C, gamma, beta, out_f32, (float*)out_a);
+  static PerDevice<bool> cfg;
+  if (!cfg.get()) {
+    cudaFuncSetAttribute(gn_temporal_kernel<OutT, IoT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * 1024 + 64) * 4);
+    cfg.get() = true;
   }
+  launch_kernel(gn_temporal_kernel<OutT, IoT>, grid, 256, smem, stream, 1, x, T, HW, C, gamma, beta, out_res, out_a);
   VDM_AFTER_LAUNCH("gn_temporal");
   return 0;
 }
 
+extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C, const float* gamma,
+                               const float* beta, float* out_f32, void* out_a, int32_t out_dtype, vdm_stream_t stream) {
+  return vdm_gn_temporal_t(x, VDM_F32, B, T, HW, C, gamma, beta, out_f32, out_a, out_dtype, stream);
+}
+
+extern "C" int vdm_gn_temporal_t(const void* x, int32_t io_dtype, int32_t B, int32_t T, int32_t HW, int32_t C,
+                                 const float* gamma, const float* beta, void* out_res, void* out_a, int32_t out_dtype,
+                                 vdm_stream_t stream) {
+  VDM_REQUIRE(x && gamma && beta && out_a, "gn_temporal: NULL pointer");
+  VDM_REQUIRE(C % 32 == 0 && C <= 1024, "gn_temporal: C=%d must be a multiple of 32, <= 1024", C);
+  VDM_REQUIRE(io_dtype == VDM_F32 || (io_dtype == VDM_F16 && out_dtype == VDM_BF16),
+              "gn_temporal: x / out_res are fp32, or fp16 with a bf16 operand output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (io_dtype == VDM_F16)
+    return gn_temporal_launch<__nv_bfloat16, __half>((const __half*)x, B, T, HW, C, gamma, beta, (__half*)out_res,
+                                                     (__nv_bfloat16*)out_a, st);
+  if (out_dtype == VDM_BF16)
+    return gn_temporal_launch<__nv_bfloat16, float>((const float*)x, B, T, HW, C, gamma, beta, (float*)out_res,
+                                                    (__nv_bfloat16*)out_a, st);
+  return gn_temporal_launch<float, float>((const float*)x, B, T, HW, C, gamma, beta, (float*)out_res, (float*)out_a, st);
+}
+
 extern "C" int vdm_add_spatial_encoding(const float* h, const float* enc, const float* frame_emb, float* out,
                                         int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream) {
+  return vdm_add_spatial_encoding_t(h, VDM_F32, enc, frame_emb, out, n_img, HW, C, stream);
+}
+
+extern "C" int vdm_add_spatial_encoding_t(const void* h, int32_t io_dtype, const float* enc, const float* frame_emb,
+                                          void* out, int32_t n_img, int32_t HW, int32_t C, vdm_stream_t stream) {
   VDM_REQUIRE(h && (enc || frame_emb) && out && C % 4 == 0, "add_spatial_encoding: bad arguments");
+  VDM_REQUIRE(io_dtype == VDM_F32 || io_dtype == VDM_F16, "add_spatial_encoding: h / out must be fp32 or fp16");
   const long long per4 = (long long)HW * C / 4, total4 = per4 * n_img;
   const int grid = (int)std::min<long long>((total4 + 255) / 256, (long long)num_sms() * 16);
-  launch_kernel(add_spatial_encoding_kernel, grid, 256, 0, (cudaStream_t)(cudaStream_t)stream, 1, h, enc, frame_emb, out, total4, per4, C / 4);
+  if (io_dtype == VDM_F16)
+    launch_kernel(add_spatial_encoding_kernel<__half>, grid, 256, 0, (cudaStream_t)stream, 1, (const __half*)h, enc, frame_emb,
+                  (__half*)out, total4, per4, C / 4);
+  else
+    launch_kernel(add_spatial_encoding_kernel<float>, grid, 256, 0, (cudaStream_t)stream, 1, (const float*)h, enc, frame_emb,
+                  (float*)out, total4, per4, C / 4);
   VDM_AFTER_LAUNCH("add_spatial_encoding");
   return 0;
 }

@@ -66,6 +66,7 @@ struct TcParams {
   int ld_out, ld_out_bf16;
   int out_nchw;
   int64_t* stats_out;
+  int io_f16;                  // out_f32 / residual point to fp16 tensors (EPI bit 6 on the lean paths)
   const float2* xf_coef;       // XF kernels: per-(image, A1 channel) (a, b) of the fused GroupNorm-apply
   int xf_act;                  // XF kernels: 1 = SiLU after the affine
   int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory
@@ -352,6 +353,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
   static_assert(!UPF || (M_SUB == 2 && (EPI & 1) == 0), "folded upsample: two parity accumulators, no residual");
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, GEN = (EPI & 8) != 0;
   constexpr bool STATS = GEN || (EPI & 4) != 0;
+  // fp16 stream: `out_f32` / `residual` are half tensors.  Compile-time on the lean paths (EPI bit 6), a uniform
+  // run-time flag on the generic one.
+  constexpr bool F16IO = (EPI & 64) != 0;
+  const bool f16io = GEN ? (p.io_f16 != 0) : F16IO;
+  const int io_shift = f16io ? 1 : 2;                 // log2 of the stream element size
   static_assert(!ILV || (!GEN && M_SUB == 1 && CHUNK == 32), "interleaved 8x8 tiles: lean epilogue, 32-column chunks");
   auto ilv_row = [](int l) { return ((l >> 3) & 1) * 64 + (l >> 4) * 8 + (l & 7); };   // tile row -> row offset
   auto tmem_full_bar = [&](int a) { return tmem_full_bar0 + 8u * a; };
@@ -412,8 +418,16 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         for (int i = 0; i < NRES; ++i) {
           const int orow = ILV ? m0 + ilv_row(q * 32 + i * RPI + r_sub) : m0 + q * 32 + i * RPI + r_sub;
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (orow < p.M && n < p.N)
-            dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
+          if (orow < p.M && n < p.N) {
+            if (f16io) {
+              const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) +
+                                                                   (size_t)orow * p.ld_res + n));
+              const float2 lo = unpack_f16x2(h.x), hi = unpack_f16x2(h.y);
+              dst[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
+            }
+          }
         }
       }
     };
@@ -421,11 +435,12 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     // flight, which made the residual read latency-bound (~1.6 TB/s).  Pull the whole tile into L2 now, while
     // this tile's MMAs are still running; the LDGs below then hit L2.
     if constexpr (HAS_RES) {
-      constexpr int LINES_PER_ROW = BLOCK_N / 32;   // 128-byte lines per tile row
-      for (int i = ew * 32 + lane; i < M_SUB * BLOCK_M * LINES_PER_ROW; i += EPI_WARPS * 32) {
-        const int row = mt0 + i / LINES_PER_ROW, n = n0 + (i % LINES_PER_ROW) * 32;
+      const int lines_per_row = (BLOCK_N << io_shift) / 128, cols_per_line = 128 >> io_shift;   // 128-byte lines
+      for (int i = ew * 32 + lane; i < M_SUB * BLOCK_M * lines_per_row; i += EPI_WARPS * 32) {
+        const int row = mt0 + i / lines_per_row, n = n0 + (i % lines_per_row) * cols_per_line;
         if (row < p.M && n < p.N)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)row * p.ld_res + n));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.residual) +
+                                                        (((size_t)row * p.ld_res + n) << io_shift)));
       }
     }
     // fetched one chunk ahead -- the first one while this tile's MMAs are still running
@@ -525,6 +540,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
             pk.x = pack_bf16x2(v.x, v.y);
             pk.y = pack_bf16x2(v.z, v.w);
             *reinterpret_cast<uint2*>(optr) = pk;
+          } else if constexpr (F16IO) {
+            uint2 pk;
+            pk.x = pack_f16x2(v.x, v.y);
+            pk.y = pack_f16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(optr) = pk;
           } else {
             *reinterpret_cast<float4*>(optr) = v;
           }
@@ -554,6 +574,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
         const int row_base = UPF ? 0 : (ILV ? m0 : row_first);
         if constexpr (BF16_OUT)
           store_rows(p.out_bf16 + par * p.par_out_stride + (size_t)row_base * p.ld_out_bf16 + n, (size_t)RPI * p.ld_out_bf16);
+        else if constexpr (F16IO)
+          store_rows(reinterpret_cast<__half*>(p.out_f32) + par * p.par_out_stride + (size_t)row_base * p.ld_out + n,
+                     (size_t)RPI * p.ld_out);
         else
           store_rows(p.out_f32 + par * p.par_out_stride + (size_t)row_base * p.ld_out + n, (size_t)RPI * p.ld_out);
       } else if (n < p.N) {  // N is a multiple of 4 on this path
@@ -582,7 +605,16 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
               const int yy = rem / p.W, xx = rem - yy * p.W;
               drow = ((size_t)img * 2 * p.H + 2 * yy + (opar >> 1)) * (2 * p.W) + 2 * xx + (opar & 1);
             }
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
+            if (p.out_f32) {
+              if (f16io) {
+                uint2 pk;
+                pk.x = pack_f16x2(v.x, v.y);
+                pk.y = pack_f16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_f32) + drow * p.ld_out + n) = pk;
+              } else {
+                *reinterpret_cast<float4*>(p.out_f32 + drow * p.ld_out + n) = v;
+              }
+            }
             if (p.out_bf16) {
               uint2 pk;
               pk.x = pack_bf16x2(v.x, v.y);
@@ -1548,6 +1580,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
   using L = HaloTLayout<SA, SB, WIDE>;
   constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
+  constexpr bool F16IO = (EPI & 64) != 0;     // out_f32 / residual are fp16 tensors (the model's residual stream)
   const uint32_t cta_rank = cluster_ctarank();
   const int work_id0 = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
   extern __shared__ uint8_t smem_raw[];
@@ -1718,7 +1751,12 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
       float rsum = 0.f, rsq = 0.f;
       float res_cur[32];
       auto load_res = [&](float (&dst)[32], int chunk) {
-        if constexpr (HAS_RES) {
+        if constexpr (HAS_RES && F16IO) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + (size_t)(row0 + chunk * 32) * p.ld_res + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            dst[i] = (row0 + chunk * 32 + i < p.M) ? f16_bits_to_f32(__ldg(rp + (size_t)i * p.ld_res)) : 0.f;
+        } else if constexpr (HAS_RES) {
           const float* rp = p.residual + (size_t)(row0 + chunk * 32) * p.ld_res + c;
 #pragma unroll
           for (int i = 0; i < 32; ++i) dst[i] = (row0 + chunk * 32 + i < p.M) ? __ldg(rp + (size_t)i * p.ld_res) : 0.f;
@@ -1728,7 +1766,9 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = row0 + j * 32 + lane;
-          if (r < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + (size_t)r * p.ld_res + c - lane));
+          if (r < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.residual) +
+                                                          ((size_t)r * p.ld_res + c - lane) * (F16IO ? 2 : 4)));
         }
       }
       load_res(res_cur, 0);
@@ -1752,6 +1792,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
               rsq = fmaf(v, v, rsq);
             }
             if constexpr (BF16_OUT) p.out_bf16[(size_t)(r + i) * p.ld_out_bf16 + c] = __float2bfloat16_rn(v);
+            else if constexpr (F16IO) reinterpret_cast<uint16_t*>(p.out_f32)[(size_t)(r + i) * p.ld_out + c] = f32_to_f16_bits(v);
             else p.out_f32[(size_t)(r + i) * p.ld_out + c] = v;
           }
         }
@@ -1917,7 +1958,13 @@ int epilogue_variant(const TcParams& p, int block_n) {
   const bool one_out = (p.out_f32 != nullptr) != (p.out_bf16 != nullptr);
   const bool fast = !p.out_nchw && !p.rowbias && p.a1_mode != 3 && one_out && p.N % block_n == 0;
   if (!fast) return 8 | (p.residual ? 1 : 0);
-  return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
+  // fp16 stream IO (bit 6): lean instances exist for the fp16-output combinations 64, 65, 68, 69
+  return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0) | (p.io_f16 ? 64 : 0);
+}
+
+int bad_variant(int v) {
+  set_error("gemm_tc: epilogue combination %d is not built (fp16 stream IO goes with an fp16 output: variants 64, 65, 68, 69)", v);
+  return -1;
 }
 
 // The TMA-store epilogue (variants 32 / 34) replaces the lean bias-only variants 0 / 2 wherever its output-tile staging
@@ -1971,7 +2018,12 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
     case 6: return launch_inst<BLOCK_N, M_SUB, STAGES, 6, CTA2>(ma1, ma2, mw, p, stream);
     case 7: return launch_inst<BLOCK_N, M_SUB, STAGES, 7, CTA2>(ma1, ma2, mw, p, stream);
     case 9: return launch_inst<BLOCK_N, M_SUB, STAGES, 9, CTA2>(ma1, ma2, mw, p, stream);
-    default: return launch_inst<BLOCK_N, M_SUB, STAGES, 8, CTA2>(ma1, ma2, mw, p, stream);
+    case 64: return launch_inst<BLOCK_N, M_SUB, STAGES, 64, CTA2>(ma1, ma2, mw, p, stream);
+    case 65: return launch_inst<BLOCK_N, M_SUB, STAGES, 65, CTA2>(ma1, ma2, mw, p, stream);
+    case 68: return launch_inst<BLOCK_N, M_SUB, STAGES, 68, CTA2>(ma1, ma2, mw, p, stream);
+    case 69: return launch_inst<BLOCK_N, M_SUB, STAGES, 69, CTA2>(ma1, ma2, mw, p, stream);
+    case 8: return launch_inst<BLOCK_N, M_SUB, STAGES, 8, CTA2>(ma1, ma2, mw, p, stream);
+    default: return bad_variant(v);
   }
 }
 
@@ -2040,7 +2092,12 @@ int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtenso
     case 4: return launch_halo_inst<BLOCK_N, 1, SA, SB, 4, true>(mh, ma2, mw, p, stream);
     case 5: return launch_halo_inst<BLOCK_N, 1, SA, SB, 5, true>(mh, ma2, mw, p, stream);
     case 6: return launch_halo_inst<BLOCK_N, 1, SA, SB, 6, true>(mh, ma2, mw, p, stream);
-    default: return launch_halo_inst<BLOCK_N, 1, SA, SB, 7, true>(mh, ma2, mw, p, stream);
+    case 7: return launch_halo_inst<BLOCK_N, 1, SA, SB, 7, true>(mh, ma2, mw, p, stream);
+    case 64: return launch_halo_inst<BLOCK_N, 1, SA, SB, 64, true>(mh, ma2, mw, p, stream);
+    case 65: return launch_halo_inst<BLOCK_N, 1, SA, SB, 65, true>(mh, ma2, mw, p, stream);
+    case 68: return launch_halo_inst<BLOCK_N, 1, SA, SB, 68, true>(mh, ma2, mw, p, stream);
+    case 69: return launch_halo_inst<BLOCK_N, 1, SA, SB, 69, true>(mh, ma2, mw, p, stream);
+    default: return bad_variant(epilogue_variant(p, BLOCK_N));
   }
 }
 
@@ -2058,7 +2115,12 @@ int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap
     case 6: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 6>(mh, ma2, mw, p, stream);
     case 7: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 7>(mh, ma2, mw, p, stream);
     case 9: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 9>(mh, ma2, mw, p, stream);
-    default: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 8>(mh, ma2, mw, p, stream);
+    case 64: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 64>(mh, ma2, mw, p, stream);
+    case 65: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 65>(mh, ma2, mw, p, stream);
+    case 68: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 68>(mh, ma2, mw, p, stream);
+    case 69: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 69>(mh, ma2, mw, p, stream);
+    case 8: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 8>(mh, ma2, mw, p, stream);
+    default: return bad_variant(epilogue_variant(p, BLOCK_N));
   }
 }
 
@@ -2104,11 +2166,13 @@ template <int SA, int SB>
 int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcParams& p, cudaStream_t stream) {
   const bool one_out = (p.out_f32 != nullptr) != (p.out_bf16 != nullptr);
   if (one_out && !p.rowbias && !p.residual) {
-    const int v = (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0);
+    const int v = (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0) | ((p.io_f16 && !p.out_bf16) ? 64 : 0);
     switch (v) {
       case 0: return launch_upfold_halo_inst<SA, SB, 0>(mh, mw, p, stream);
       case 2: return launch_upfold_halo_inst<SA, SB, 2>(mh, mw, p, stream);
       case 4: return launch_upfold_halo_inst<SA, SB, 4>(mh, mw, p, stream);
+      case 64: return launch_upfold_halo_inst<SA, SB, 64>(mh, mw, p, stream);
+      case 68: return launch_upfold_halo_inst<SA, SB, 68>(mh, mw, p, stream);
       default: return launch_upfold_halo_inst<SA, SB, 6>(mh, mw, p, stream);
     }
   }
@@ -2178,7 +2242,12 @@ int launch_halo_t(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorM
     case 4: return launch_halo_t_inst<SA, SB, 4, WIDE>(mh, ma2, mw, p, stream);
     case 5: return launch_halo_t_inst<SA, SB, 5, WIDE>(mh, ma2, mw, p, stream);
     case 6: return launch_halo_t_inst<SA, SB, 6, WIDE>(mh, ma2, mw, p, stream);
-    default: return launch_halo_t_inst<SA, SB, 7, WIDE>(mh, ma2, mw, p, stream);
+    case 7: return launch_halo_t_inst<SA, SB, 7, WIDE>(mh, ma2, mw, p, stream);
+    case 64: return launch_halo_t_inst<SA, SB, 64, WIDE>(mh, ma2, mw, p, stream);
+    case 65: return launch_halo_t_inst<SA, SB, 65, WIDE>(mh, ma2, mw, p, stream);
+    case 68: return launch_halo_t_inst<SA, SB, 68, WIDE>(mh, ma2, mw, p, stream);
+    case 69: return launch_halo_t_inst<SA, SB, 69, WIDE>(mh, ma2, mw, p, stream);
+    default: return bad_variant(v);
   }
 }
 
@@ -2232,6 +2301,9 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   p.stats_via_smem = 1;
   p.xf_coef = reinterpret_cast<const float2*>(a->a1_coef);
   p.xf_act = a->a1_act;
+  VDM_REQUIRE(a->io_dtype == VDM_F32 || a->io_dtype == VDM_F16, "gemm_tc: io_dtype must be VDM_F32 or VDM_F16");
+  p.io_f16 = (a->io_dtype == VDM_F16 && (a->out_f32 != nullptr || a->residual != nullptr)) ? 1 : 0;
+  VDM_REQUIRE(!p.io_f16 || (!a->out_nchw && a->out_f32 != nullptr), "gemm_tc: fp16 stream IO needs an fp16 `out_f32` output");
   p.w_group_tiles = a->w_group_tiles;
   p.n_par = 1;
   const int n_prob = a->n_prob > 1 ? a->n_prob : 1;
@@ -2313,7 +2385,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     const int rows = BLOCK_M * msub;
     // 8x8 level: a 128-row tile is two whole images -> interleaved halo tiles (lean epilogues, 256-wide only)
     const bool ok8 = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
-                     a->W == 8 && a->H == 8 && a->N % 256 == 0 && epilogue_variant(p, 256) < 8 &&
+                     a->W == 8 && a->H == 8 && a->N % 256 == 0 && (epilogue_variant(p, 256) & 8) == 0 &&
                      (hmode == 2 || ((M + 255) / 256) * (a->N / 256) >= 40);
     if (ok8) {
       CUtensorMap mh, mw2;
@@ -2346,7 +2418,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     // 128-pixel-wide images (the top level of the 128x128 model): a 256-pixel tile is two image rows, the slot holds
     // four -> the transposed-role kernel with 64 KB slots (two of them) for every N % 128 == 0
     const bool okw = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 &&
-                     a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 && epilogue_variant(p, 128) < 8 &&
+                     a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 && (epilogue_variant(p, 128) & 8) == 0 &&
                      (hmode == 2 || ((M + 511) / 512) * (a->N / 128) >= 40);
     if (okw) {
       CUtensorMap mh, mwt;
@@ -2369,7 +2441,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     // wide), slightly slower for 256.  VDM_GEMM_HALO_T: 0 off, 1 that rule (default), 2 every N % 128 == 0
     const int tmode = et ? atoi(et) : 1;
     if (ok && a->N % 128 == 0 && (a->N % 256 != 0 || tmode == 2) && tmode > 0 && 256 % a->W == 0 && HW % 256 == 0 &&
-        epilogue_variant(p, 128) < 8) {
+        (epilogue_variant(p, 128) & 8) == 0) {
       CUtensorMap mh, mwt;
       const uint64_t C = a->C1;
       uint64_t dims[5] = {C, (uint64_t)a->W, (uint64_t)a->H, 1, (uint64_t)a->n_img};
@@ -2478,6 +2550,7 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   p.a1_mode = 3; p.is_linear = 0; p.H = Hl; p.W = Wl; p.HW = HWl;
   p.bias = a->bias; p.out_f32 = a->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.ld_out = a->ld_out; p.ld_out_bf16 = a->ld_out_bf16; p.stats_out = a->stats_out;
+  p.io_f16 = (a->io_dtype == VDM_F16 && a->out_f32 != nullptr) ? 1 : 0;
   p.stats_via_smem = 1;
   p.n_par = 4;
   p.par_w_rows = a->N;

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
+from ._lib import BF16, F16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
 
 # Optional per-launch timing (bench.py / profiling only): when PROFILE is a list, every wrapper
 # brackets its launch with CUDA events on the current stream and appends
@@ -60,6 +60,11 @@ def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, ro
     g.out_silu_f32 = ptr(out_silu)
     g.stats_out = ptr(stats_out)
     g.a1_coef, g.a1_act = ptr(a1_coef, torch.float32), int(a1_act)
+    # `out_f32` / `residual` are the model's residual stream: fp32, or fp16 in the bf16 model (io_dtype)
+    io = {t.dtype for t in (out_f32, residual) if t is not None}
+    if len(io) > 1 or not io <= {torch.float32, torch.float16}:
+        raise TypeError(f'vdm_gemm: out_f32 / residual must both be fp32 or both fp16, got {io}')
+    g.io_dtype = dt(io.pop()) if io else F32
     return g
 
 
@@ -98,8 +103,9 @@ def gn_coef(stats1, stats2, n_img, HW, gamma, beta, coef, scale_shift=None):
 def gn_stats(src, n_img, HW, stats):
     """Per-(image, channel) sum / sum of squares of src [n_img*HW][C] into stats [n_img][2][C] (float64, zeroed)."""
     lib = _lib.load()
-    _timed('gn_stats', lambda: check(lib.vdm_gn_stats(ptr(src), src.shape[-1], n_img, HW, ptr(stats), stream()),
-                                     'vdm_gn_stats'), nbytes=_nbytes(src))
+    _timed('gn_stats', lambda: check(lib.vdm_gn_stats_t(ptr(src), dt(src.dtype), src.shape[-1], n_img, HW,
+                                                        ptr(stats, torch.float64), stream()), 'vdm_gn_stats'),
+           nbytes=_nbytes(src))
 
 
 def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=None, beta=None, scale_shift=None,
@@ -118,6 +124,9 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
     a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
     a.out, a.out_raw, a.out_f32_copy = ptr(out), ptr(out_raw), ptr(copy)
     a.src1_dtype = dt(src1.dtype)
+    a.copy_dtype = F32 if copy is None else dt(copy.dtype)
+    if src2 is not None and src2.dtype != src1.dtype:
+        raise TypeError('vdm_gn_apply: the two sources of a concat must share a dtype')
     _timed('gn_apply', lambda: check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply'),
            nbytes=_nbytes(src1, src2, out, copy, out_raw),
            meta=f'n={n_img} HxW={H}x{W} C={a.C1}+{a.C2} in={src1.dtype} norm={int(stats1 is not None)} '
@@ -126,15 +135,17 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
 
 def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):
     lib = _lib.load()
-    _timed('gn_temporal', lambda: check(lib.vdm_gn_temporal(ptr(x), B, T, HW, Cc, ptr(gamma), ptr(beta), ptr(out_f32),
-                                                            ptr(out_a), dt(out_a.dtype), stream()), 'vdm_gn_temporal'),
-           nbytes=_nbytes(x, out_f32, out_a))
+    if out_f32 is not None and out_f32.dtype != x.dtype:
+        raise TypeError('vdm_gn_temporal: the normalised residual copy has the dtype of x')
+    _timed('gn_temporal', lambda: check(lib.vdm_gn_temporal_t(ptr(x), dt(x.dtype), B, T, HW, Cc, ptr(gamma), ptr(beta),
+                                                              ptr(out_f32), ptr(out_a), dt(out_a.dtype), stream()),
+                                        'vdm_gn_temporal'), nbytes=_nbytes(x, out_f32, out_a))
 
 
 def add_spatial_encoding(h, enc, out, n_img, HW, Cc, frame_emb=None):
-    _timed('add_spatial_encoding', lambda: check(_lib.load().vdm_add_spatial_encoding(
-        ptr(h), ptr(enc), ptr(frame_emb), ptr(out), n_img, HW, Cc, stream()), 'vdm_add_spatial_encoding'),
-           nbytes=_nbytes(h, out))
+    _timed('add_spatial_encoding', lambda: check(_lib.load().vdm_add_spatial_encoding_t(
+        ptr(h), dt(h.dtype), ptr(enc, torch.float32), ptr(frame_emb, torch.float32), ptr(out, h.dtype), n_img, HW, Cc,
+        stream()), 'vdm_add_spatial_encoding'), nbytes=_nbytes(h, out))
 
 
 def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask, mode=0):

@@ -78,6 +78,11 @@ class UNetModel(nn.Module):
         # and bit-exact against the standalone pass, but measured SLOWER on B200 (every activation element
         # is re-transformed 4.5 times, which binds on the special-function units and shared-memory bandwidth): off.
         self.fuse_norm = False
+        # bf16 mode: the residual stream (every ResBlock / attention / resampling output) is stored in fp16 -- 11-bit
+        # mantissa, 4x finer than the bf16 rounding of the GEMM operands, saturating conversions -- instead of fp32:
+        # half the HBM bytes of every stream write, residual read and GroupNorm-apply read.  Accumulation, residual adds
+        # and GroupNorm statistics stay fp32.  torch.float32 restores the fp32 stream.
+        self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
         self.time_embed_dim = E = model_channels * 4
@@ -229,6 +234,11 @@ class UNetModel(nn.Module):
     @property
     def inner_dtype(self):
         return torch.float32
+
+    @property
+    def _sdt(self):
+        """dtype of the residual-stream buffers"""
+        return self.stream_dtype if self.compute_dtype == torch.bfloat16 else torch.float32
 
     # ---- weight pre-packing ----------------------------------------------------------------------
     @torch.no_grad()
@@ -434,7 +444,7 @@ class UNetModel(nn.Module):
         if ws.emb_join is not None:      # first consumer of the embedding projections: join the side branch
             torch.cuda.current_stream().wait_event(ws.emb_join)
             ws.emb_join = None
-        out = ws.buf(p + '.out', (M, Cout))
+        out = ws.buf(p + '.out', (M, Cout), self._sdt)
         st_out = self._fused_stats(ws, p + '.out', n_img, HW, Cout)
         conv2 = dict(n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b2'], out_f32=out, stats_out=st_out)
         conv2.update(dict(a2=araw) if node['skip'] else dict(residual=src1))
@@ -445,6 +455,7 @@ class UNetModel(nn.Module):
             # halo kernel, its transform warps apply the first three to the raw bf16 conv1 output inside shared
             # memory -- the normalised activation never exists in HBM; elsewhere the standalone pass produces it.
             fuse = ws.flags[p + '.fuse2'] = bool(self.fuse_norm and h1.dtype == torch.bfloat16 and st_out is not None and
+                                                 self._sdt == torch.float32 and
                                         ops.gemm_fused_norm_supported(h1, P[p + '.w2'], Cout, **conv2))
         if fuse:
             coef = ws.buf(p + '.coef2', (n_img, Cout, 2))
@@ -519,7 +530,7 @@ class UNetModel(nn.Module):
         lin = dict(n_img=M, H=1, W=1, taps=1)
         # ---- temporal attention with RPE (unet.py:246-255, 471-540)
         q = p + '.temporal_attention'
-        xn = ws.buf(q + '.xn', (M, C))
+        xn = ws.buf(q + '.xn', (M, C), self._sdt)
         xa = ws.buf(q + '.xa', (M, C), adt)
         ops.gn_temporal(h, B, T, HW, C, P[q + '.gn_w'], P[q + '.gn_b'], xn, xa)
         tc_path = self._tc_temporal_ok(T, C, HW)
@@ -584,7 +595,7 @@ class UNetModel(nn.Module):
             ops.attn_weights_mean(qkv, B, HW, T * HW * 3 * C, 3 * C, HW * 3 * C, T, heads, hd, amap, r_q=R[0], r_k=R[1],
                                   mask=amask, pad_interact=self.allow_interactions_between_padding)
             attn_log['temporal'].append(amap)
-        h2 = ws.buf(q + '.out', (M, C))
+        h2 = ws.buf(q + '.out', (M, C), self._sdt)
         st = self._fused_stats(ws, q + '.out', N, HW, C)
         # + NORMALISED x.  The rows of this GEMM are (image, pixel), so the epilogue statistics are
         # exactly the per-image GroupNorm sums the spatial attention needs next.
@@ -593,7 +604,7 @@ class UNetModel(nn.Module):
         st = self._stats_of(ws, q + '.out', h2, st, N, HW)
         # ---- spatial attention (unet.py:258-266)
         q = p + '.spatial_attention'
-        xn = ws.buf(q + '.xn', (M, C))
+        xn = ws.buf(q + '.xn', (M, C), self._sdt)
         xa = ws.buf(q + '.xa', (M, C), adt)
         ops.gn_apply(h2, None, N, H, W, xa, stats1=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
         qkv = ws.buf(q + '.qkv', (M, 3 * C), adt)       # bf16 mode: tensor-core flash kernel on bf16 q, k, v
@@ -607,7 +618,7 @@ class UNetModel(nn.Module):
             amap = torch.empty(N, HW, HW, device=h.device)
             ops.attn_weights_mean(qkv, N, 1, HW * 3 * C, 0, 3 * C, HW, heads, hd, amap)
             attn_log['spatial'].append(amap)
-        h3 = ws.buf(q + '.out', (M, C))
+        h3 = ws.buf(q + '.out', (M, C), self._sdt)
         st3 = self._fused_stats(ws, q + '.out', N, HW, C)
         ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h3,
                  stats_out=st3)
@@ -747,7 +758,7 @@ class UNetModel(nn.Module):
                 n_groups_done += 1
                 frame_enc = self.use_frame_encoding
                 if n_groups_done == self.n_blocks_before_attn and ('enc' in P or frame_enc):
-                    hn = ws.buf('h_enc', tuple(x[0].shape))
+                    hn = ws.buf('h_enc', tuple(x[0].shape), self._sdt)
                     femb = None
                     if frame_enc:     # sinusoid of the (optionally centred) frame indices, period 10 T (unet.py:914-926)
                         femb = ws.buf('frame_emb', (N, x[0].shape[1]))
@@ -764,7 +775,7 @@ class UNetModel(nn.Module):
                     in_groups = False
             kind, p = node['kind'], node['p']
             if kind == 'conv_in':
-                h = ws.buf('h_in', (N * H * W, ch))
+                h = ws.buf('h_in', (N * H * W, ch), self._sdt)
                 st = self._fused_stats(ws, 'h_in', N, H * W, ch)
                 ops.gemm(a_in, P['in_w'], ch, n_img=N, H=H, W=W, taps=1, bias=P['in_b'], out_f32=h, stats_out=st)
                 x = (h, st)
@@ -780,7 +791,7 @@ class UNetModel(nn.Module):
                 x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables, attn_log)
             elif kind == 'down':
                 C = node['C']
-                out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C))
+                out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C), self._sdt)
                 if adt == torch.bfloat16:
                     planes = ws.buf(p + '.planes', (N * H * W, C), adt)
                     ops.gn_apply(x[0], None, N, H, W, planes, out_mode=2)
@@ -793,7 +804,7 @@ class UNetModel(nn.Module):
                 x, H, W = (out, st), H // 2, W // 2
             elif kind == 'up':
                 C = node['C']
-                out = ws.buf(p + '.out', (N * 4 * H * W, C))
+                out = ws.buf(p + '.out', (N * 4 * H * W, C), self._sdt)
                 fold = adt == torch.bfloat16 and C % 128 == 0
                 st = self._fused_stats(ws, p + '.out', N, H * W if fold else 4 * H * W, C)
                 if fold:
@@ -843,7 +854,7 @@ class UNetModel(nn.Module):
         B, F, Cc, H, W = x.shape
         if Cc != 3:
             raise NotImplementedError('3-channel frames only')
-        key = (B, F, H, W, str(x.device), per_frame_t is not None)
+        key = (B, F, H, W, str(x.device), per_frame_t is not None, self._sdt, self.micro_batches, self.fuse_norm)
         ws = self._workspaces.get(key)
         if ws is None:
             chans = sum((n['cin'] + 3 * n['cout']) if n['kind'] == 'res' else 3 * n.get('C', self.model_channels)
