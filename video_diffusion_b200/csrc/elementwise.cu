@@ -248,8 +248,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   int pix = p0 + prow;
   for (; pix + (U - 1) * rows < p1; pix += U * rows) {
     float x[U][8];
+    if constexpr (std::is_same<InT, __half>::value) {   // all raw loads first, then the conversions (see gn_temporal)
+      uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) load8(src + (size_t)(pix + u * rows) * ld, x[u]);
+      for (int u = 0; u < U; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(pix + u * rows) * ld));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_f16x2(w[i]);
+          x[u][2 * i] = f.x;
+          x[u][2 * i + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) load8(src + (size_t)(pix + u * rows) * ld, x[u]);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) process(pix + u * rows, x[u]);
   }
@@ -424,9 +440,26 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
   float4 v[TMAX];          // TMAX >= T: the frame loop is fully unrolled, every load is in flight before the first use
   float s = 0.f;
   const IoT* src = x + off0;
+  if constexpr (sizeof(IoT) == 2) {
+    // raw bits first, conversions afterwards: a conversion right behind each load would stall the in-order warp on
+    // that load before the next one is issued
+    uint2 raw[TMAX];
 #pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
-    if (t < T && active) v[t] = load4(src + t * frame_stride);
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < T && active) raw[t] = __ldg(reinterpret_cast<const uint2*>(src + t * frame_stride));
+    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < T && active) {
+        const float2 lo = unpack_f16x2(raw[t].x), hi = unpack_f16x2(raw[t].y);
+        v[t] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      if (t < T && active) v[t] = load4(src + t * frame_stride);
+    }
   }
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {

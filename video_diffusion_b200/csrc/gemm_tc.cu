@@ -420,16 +420,24 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (orow < p.M && n < p.N) {
             if (f16io) {
+              // RAW bits only: a conversion right behind each load would make the in-order warp wait for that load
+              // before issuing the next one (measured: the fp16 residual read twice as slow as the fp32 one)
               const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) +
                                                                    (size_t)orow * p.ld_res + n));
-              const float2 lo = unpack_f16x2(h.x), hi = unpack_f16x2(h.y);
-              dst[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+              dst[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), 0.f, 0.f);
             } else {
               dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)orow * p.ld_res + n));
             }
           }
         }
       }
+    };
+    auto res_value = [&](const float4& raw) {     // what load_residual fetched, as fp32
+      if (f16io) {
+        const float2 lo = unpack_f16x2(__float_as_uint(raw.x)), hi = unpack_f16x2(__float_as_uint(raw.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+      return raw;
     };
     // The residual tile (up to 128 KB) is far more than the one-chunk-ahead register prefetch below keeps in
     // flight, which made the residual read latency-bound (~1.6 TB/s).  Pull the whole tile into L2 now, while
@@ -522,7 +530,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
           float4 v = vv[i];
           v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           if constexpr (HAS_RES) {
-            v.x += res_cur[i].x; v.y += res_cur[i].y; v.z += res_cur[i].z; v.w += res_cur[i].w;
+            const float4 r = res_value(res_cur[i]);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
           }
           if constexpr (STATS) {
             if (ILV && (((i * RPI) >> 3) & 1)) {   // rows 8..15, 24..31 of the warp belong to the second image
@@ -593,7 +602,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
             if constexpr (HAS_RES) {
-              const float4 r = res_cur[rr / RPI];
+              const float4 r = res_value(res_cur[rr / RPI]);
               v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
             ssum.x += v.x; ssum.y += v.y; ssum.z += v.z; ssum.w += v.w;
@@ -1754,8 +1763,8 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
         if constexpr (HAS_RES && F16IO) {
           const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + (size_t)(row0 + chunk * 32) * p.ld_res + c;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            dst[i] = (row0 + chunk * 32 + i < p.M) ? f16_bits_to_f32(__ldg(rp + (size_t)i * p.ld_res)) : 0.f;
+          for (int i = 0; i < 32; ++i)     // raw bits; converted at the use (keeps all 32 loads in flight)
+            dst[i] = __uint_as_float((row0 + chunk * 32 + i < p.M) ? (uint32_t)__ldg(rp + (size_t)i * p.ld_res) : 0u);
         } else if constexpr (HAS_RES) {
           const float* rp = p.residual + (size_t)(row0 + chunk * 32) * p.ld_res + c;
 #pragma unroll
@@ -1786,7 +1795,8 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
         for (int i = 0; i < 32; ++i) {
           if (r + i < p.M) {
             float v = __uint_as_float(acc[i]) + bias_c;
-            if constexpr (HAS_RES) v += res_cur[i];
+            if constexpr (HAS_RES && F16IO) v += f16_bits_to_f32((uint16_t)__float_as_uint(res_cur[i]));
+            else if constexpr (HAS_RES) v += res_cur[i];
             if constexpr (STATS) {
               rsum += v;
               rsq = fmaf(v, v, rsq);
