@@ -101,6 +101,14 @@ typedef struct {
                            Only the halo kernels take it: vdm_gemm_fused_norm_supported() tells; other shapes are an
                            error, never a silent slow path */
   int32_t a1_act;       /* with a1_coef: 1 = SiLU after the affine, 0 = affine only */
+  const void* a2b;      /* bf16 kernel: optional SECOND tensor of the A2 range, [M][C2b], concatenated after a2 along
+                           channels (the U-Net skip concat feeding the 1x1 skip projection, unet.py:826-828, 172-173):
+                           w then is [N][taps*C1 + C2 + C2b] */
+  int32_t C2b;
+  int32_t a2_dtype;     /* bf16 kernel: VDM_BF16 (0 / default) or VDM_F16 = a2 / a2b AND the weight columns of that range
+                           hold IEEE half.  The MMAs of the range then run with the f16 operand format, so the fp16
+                           residual stream itself is the operand of the 1x1 skip projection -- no bf16 copy of it is ever
+                           written -- and, with identity weight columns, of the residual add (`x + h`, unet.py:198) */
   int32_t io_dtype;     /* bf16 kernel: VDM_F32 (default) or VDM_F16 = `out_f32` and `residual` point to IEEE half tensors
                            (same leading dimensions, in elements).  The residual stream of the bf16 model is kept in fp16
                            (11-bit mantissa, conversions saturate): half the HBM traffic of every stream read / write;

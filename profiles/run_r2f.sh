@@ -2,7 +2,7 @@
 # round 2, call f: fp16 residual stream
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "fp16 or groupnorm or gemm or halo" > gpurun_out/r2f_k.log 2>&1; echo "rc=$?" >> gpurun_out/r2f_k.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "fp16 or groupnorm or gemm or halo or second_range" > gpurun_out/r2f_k.log 2>&1; echo "rc=$?" >> gpurun_out/r2f_k.log
 tail -12 gpurun_out/r2f_k.log
 if grep -q "rc=0" gpurun_out/r2f_k.log; then
   timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2f_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2f_tests.log

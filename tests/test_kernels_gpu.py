@@ -301,6 +301,47 @@ def test_gemm_fp16_stream_io(case, monkeypatch):
         o.gemm(x, w, N, residual=rnd(n * H * W, N, seed=4), out_f32=o16, **kw)
 
 
+A2_F16_CASES = [
+    # n, H, W, C1, N, C2a, C2b, halo
+    (2, 64, 64, 128, 128, 128, 0, '2'),      # identity residual through the MMA (transposed-role kernel)
+    (2, 64, 64, 128, 128, 128, 128, '2'),    # skip projection of a two-tensor concat
+    (5, 32, 32, 256, 256, 192, 128, '2'),    # pair halo kernel
+    (7, 8, 8, 128, 512, 256, 128, '2'),      # interleaved 8x8 tiles, odd image count
+    (3, 128, 128, 128, 128, 128, 64, '2'),   # wide-slot kernel
+    (5, 8, 8, 128, 128, 64, 64, '0'),        # plain kernel
+    (4, 4, 4, 64, 64, 64, 0, '0'),
+]
+
+
+@pytest.mark.parametrize('case', A2_F16_CASES, ids=lambda c: 'n%d_%dx%d_c%d_n%d_a%d_b%d_h%s' % c)
+def test_conv_second_range_from_fp16_stream(case, monkeypatch):
+    """The second operand range of a conv (1x1 skip projection / identity residual) read straight from fp16 tensors --
+    one or two, concatenated along channels -- against fp16 weight columns (`a2_dtype` = VDM_F16): those K blocks run
+    with the f16 MMA format inside the same accumulation as the bf16 3x3 part."""
+    n, H, W, C1, N, C2a, C2b, halo = case
+    o = ops()
+    monkeypatch.setenv('VDM_GEMM_HALO', halo)
+    x = rnd(n, C1, H, W, seed=1).bfloat16().float()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
+    sa, sb = rnd(n, C2a, H, W, seed=3).half(), (rnd(n, C2b, H, W, seed=4).half() if C2b else None)
+    identity = C2b == 0 and C2a == N
+    ws_ = torch.eye(N, device='cuda') if identity else rnd(N, C2a + C2b, seed=5, scale=(C2a + C2b) ** -0.5)
+    ws_ = ws_.half()
+    bias = rnd(N, seed=6)
+    cat = torch.cat([sa, sb], 1) if C2b else sa
+    ref = F.conv2d(x, w, bias, padding=1) + F.conv2d(cat.float(), ws_.float().view(N, -1, 1, 1))
+    wp = torch.cat([pack_w(w).bfloat16().view(torch.int16), ws_.view(torch.int16)], dim=1).contiguous().view(torch.bfloat16)
+    out = torch.full((n * H * W, N), float('nan'), device='cuda', dtype=torch.float16)
+    st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64) if (H * W) % 32 == 0 else None
+    o.gemm(nhwc(x).bfloat16(), wp, N, n_img=n, H=H, W=W, taps=9, a2=nhwc(sa.float()).half(),
+           a2b=None if sb is None else nhwc(sb.float()).half(), bias=bias, out_f32=out, stats_out=st, C1=C1)
+    torch.cuda.synchronize()
+    assert relerr(out, nhwc(ref)) < 1e-3            # fp16 output rounding (2^-11) dominates
+    if st is not None:
+        got = st.double() / 2 ** 24
+        assert relerr(got[:, 0], _chan_stats(ref)[:, 0]) < 1e-4
+
+
 def test_upsample_fold_and_elementwise_fp16_stream(monkeypatch):
     """The folded-upsample conv writing an fp16 stream, and the stream's elementwise consumers / producers
     (gn_stats, gn_apply incl. concat + raw copy + fp16 residual copy, temporal GroupNorm, spatial-encoding add) fed

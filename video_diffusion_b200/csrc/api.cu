@@ -33,6 +33,8 @@ extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_f32 || a->out_bf16, "gemm: no output");
   VDM_REQUIRE(a->n_img > 0 && a->H > 0 && a->W > 0 && a->N > 0, "gemm: bad geometry");
   VDM_REQUIRE(a->a1_coef == nullptr || a->dtype == VDM_BF16, "gemm: a1_coef (fused normalisation) is bf16-kernel only");
+  VDM_REQUIRE(a->dtype == VDM_BF16 || (a->a2b == nullptr && a->C2b == 0 && a->a2_dtype != VDM_F16 && a->io_dtype != VDM_F16),
+              "gemm: a2b / a2_dtype / io_dtype belong to the bf16 kernel");
   if (a->dtype == VDM_BF16) return vdm::gemm_tc(a, (cudaStream_t)stream);
   if (a->dtype == VDM_F32) return vdm::gemm_simt(a, (cudaStream_t)stream);
   vdm::set_error("gemm: unknown dtype %d", a->dtype);

@@ -44,9 +44,17 @@ constexpr bool kTrace = true;
 constexpr bool kTrace = false;
 #endif
 
+// The second operand range (fused 1x1 skip projection / identity residual) may come from two tensors concatenated
+// along channels (the U-Net skip concat): chunks [0, c2a_chunks) from `a`, the rest from `b`.
+struct A2Maps {
+  CUtensorMap a, b;
+};
+
 struct TcParams {
   int M, N;
   int taps, c1_chunks, c2_chunks;
+  int c2a_chunks;     // chunks of the second range that come from its first tensor (== c2_chunks for one tensor)
+  int a2_f16;         // the second range (activations AND its weight columns) is IEEE half: those MMAs use the f16 descriptor
   int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes, 3 nearest-x2 upsample folded into 2x2 taps
   int w_group_tiles;  // grouped weights: 128-row tile m reads weight rows (m / w_group_tiles) * N + n
   int tiles_per_par;  // > 0: tile index = par * tiles_per_par + ...; par = output parity (a1_mode 3) or problem of a batch
@@ -242,6 +250,9 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+
+// clears the A / B format fields (1 = bf16) of an instruction descriptor: both operands IEEE half (0)
+constexpr uint32_t kIdescF16Mask = ~((1u << 7) | (1u << 10));
 
 template <int BLOCK_N, int UMMA_M = BLOCK_M>
 constexpr uint32_t instr_desc() {
@@ -842,7 +853,7 @@ __device__ __forceinline__ void epilogue_ts_role(const TcParams& p, const CUtens
 // bit 5 (with bit 1 = bf16): the TMA-store epilogue above (bias only, no residual / statistics), M_SUB == 1.
 template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1,
-                                                                 const __grid_constant__ CUtensorMap tm_a2,
+                                                                 const __grid_constant__ A2Maps tm_a2,
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const __grid_constant__ CUtensorMap tm_out,
                                                                  const TcParams p) {
@@ -961,6 +972,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
           }
           int dy = 0, dx = 0, plane = 0, c0 = 0;
+          const CUtensorMap* a2_map = &tm_a2.a;
           const bool first_range = kb < k1;
           if (first_range) {
             const int tap = kb / p.c1_chunks;
@@ -983,16 +995,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           } else {
             c0 = (kb - k1) * BLOCK_K;
+            if (kb - k1 >= p.c2a_chunks) {     // second tensor of a concatenated second range
+              c0 -= p.c2a_chunks * BLOCK_K;
+              a2_map = &tm_a2.b;
+            }
           }
 #pragma unroll
           for (int sub = 0; sub < M_SUB; ++sub) {
             const uint32_t dst = a_dst + sub * L::A_SUB_BYTES;
             if constexpr (CTA2) {
-              if (!first_range) tma_load_5d_2cta(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              if (!first_range) tma_load_5d_2cta(dst, a2_map, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
               else if (p.is_linear) tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0 + par * p.par_a_cols, m0 + sub * BLOCK_M, 0, 0, 0);
               else tma_load_5d_2cta(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
             } else {
-              if (!first_range) tma_load_5d(dst, &tm_a2, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
+              if (!first_range) tma_load_5d(dst, a2_map, full_bar(stage), c0, m0 + sub * BLOCK_M, 0, 0, 0);
               else if (p.is_linear) tma_load_5d(dst, &tm_a1, full_bar(stage), c0 + par * p.par_a_cols, m0 + sub * BLOCK_M, 0, 0, 0);
               else tma_load_5d(dst, &tm_a1, full_bar(stage), c0, x0[sub] + dx, y0[sub] + dy, plane, img0[sub]);
             }
@@ -1013,7 +1029,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {   // 2-CTA: only the leader issues
-      constexpr uint32_t idesc = instr_desc<BLOCK_N, CTA2 ? 256 : BLOCK_M>();
+      constexpr uint32_t idesc_bf16 = instr_desc<BLOCK_N, CTA2 ? 256 : BLOCK_M>();
+      const uint32_t idesc_a2 = p.a2_f16 ? (idesc_bf16 & kIdescF16Mask) : idesc_bf16;
+      const int k1_mma = p.taps * p.c1_chunks;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -1042,6 +1060,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
           const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
+          const uint32_t idesc = kb < k1_mma ? idesc_bf16 : idesc_a2;
 #pragma unroll
           for (int sub = 0; sub < M_SUB; ++sub) {
             if (kTrace && (p.dbg & 2)) break;
@@ -1134,7 +1153,7 @@ struct HaloLayout {
 // MMA thread waits for instead of a_full.
 template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, bool XF = false>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
-    gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
+    gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ A2Maps tm_a2,
                         const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
@@ -1232,25 +1251,28 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           }
         }
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          const bool second = chunk >= p.c2a_chunks;        // second tensor of a concatenated second range
+          const CUtensorMap* a2_map = second ? &tm_a2.b : &tm_a2.a;
+          const int a2_c0 = (second ? chunk - p.c2a_chunks : chunk) * BLOCK_K;
           mbar_wait(a_empty(sa), pa ^ 1u, 0);
           if constexpr (XF) {
             mbar_expect_tx(a_full(sa), M_SUB * L::A_SUB_BYTES);
             if constexpr (ILV) {
-              tma_load_5d(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
+              tma_load_5d(smem_base + sa * L::A_SLOT, a2_map, a_full(sa), a2_c0, 0, img, 0, 0);
             } else {
 #pragma unroll
               for (int sub = 0; sub < M_SUB; ++sub)
-                tma_load_5d(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                tma_load_5d(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, a2_map, a_full(sa), a2_c0,
                             m0 + sub * BLOCK_M, 0, 0, 0);
             }
           } else {
             if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * M_SUB * L::A_SUB_BYTES);
             if constexpr (ILV) {   // tm_a2 is the (C2, x, image, y) view: rows land in the tile's (y, image, x) order
-              tma_load_5d_2cta(smem_base + sa * L::A_SLOT, &tm_a2, a_full(sa), chunk * BLOCK_K, 0, img, 0, 0);
+              tma_load_5d_2cta(smem_base + sa * L::A_SLOT, a2_map, a_full(sa), a2_c0, 0, img, 0, 0);
             } else {
 #pragma unroll
               for (int sub = 0; sub < M_SUB; ++sub)
-                tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, &tm_a2, a_full(sa), chunk * BLOCK_K,
+                tma_load_5d_2cta(smem_base + sa * L::A_SLOT + sub * L::A_SUB_BYTES, a2_map, a_full(sa), a2_c0,
                                  m0 + sub * BLOCK_M, 0, 0, 0);
             }
           }
@@ -1265,7 +1287,9 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = instr_desc<BLOCK_N, 256>();
+      constexpr uint32_t idesc_bf16 = instr_desc<BLOCK_N, 256>();
+      const uint32_t idesc_a2 = p.a2_f16 ? (idesc_bf16 & kIdescF16Mask) : idesc_bf16;   // second range in IEEE half
+      uint32_t idesc = idesc_bf16;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -1298,6 +1322,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           }
         };
         const int n_units = 3 * p.c1_chunks;
+        idesc = idesc_bf16;
         for (int u = 0; u < n_units; ++u) {
           mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);
           const uint32_t a_slot = smem_base + sa * L::A_SLOT;
@@ -1308,6 +1333,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
             pa ^= 1u;
           }
         }
+        idesc = idesc_a2;
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
           mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);
           mma_block(smem_base + sa * L::A_SLOT);
@@ -1583,7 +1609,7 @@ struct HaloTLayout {
 
 template <int SA, int SB, int EPI, bool WIDE = false, bool XF = false>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
-    gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ CUtensorMap tm_a2,
+    gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ A2Maps tm_a2,
                           const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
   pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = HaloTLayout<SA, SB, WIDE>;
@@ -1678,11 +1704,14 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           }
         }
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
+          const bool second = chunk >= p.c2a_chunks;        // second tensor of a concatenated second range
+          const CUtensorMap* a2_map = second ? &tm_a2.b : &tm_a2.a;
+          const int a2_c0 = (second ? chunk - p.c2a_chunks : chunk) * BLOCK_K;
           mbar_wait(a_empty(sa), pa ^ 1u, 0);
           mbar_expect_tx(a_full(sa), PIX * BLOCK_K * 2);
 #pragma unroll
           for (int sub = 0; sub < PIX / BLOCK_M; ++sub)
-            tma_load_5d(smem_base + sa * L::A_SLOT + sub * (BLOCK_M * BLOCK_K * 2), &tm_a2, a_full(sa), chunk * BLOCK_K,
+            tma_load_5d(smem_base + sa * L::A_SLOT + sub * (BLOCK_M * BLOCK_K * 2), a2_map, a_full(sa), a2_c0,
                         m0 + sub * BLOCK_M, 0, 0, 0);
           if (++sa == SA) {
             sa = 0;
@@ -1695,7 +1724,9 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc<PIX, BLOCK_M>();    // M = 128 output channels, N = 256 pixels
+      constexpr uint32_t idesc_bf16 = instr_desc<PIX, BLOCK_M>();    // M = 128 output channels, N = 256 pixels
+      const uint32_t idesc_a2 = p.a2_f16 ? (idesc_bf16 & kIdescF16Mask) : idesc_bf16;   // second range in IEEE half
+      uint32_t idesc = idesc_bf16;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -1723,6 +1754,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           }
         };
         const int n_units = 3 * p.c1_chunks;
+        idesc = idesc_bf16;
         for (int u = 0; u < n_units; ++u) {
           mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);   // XF: the transform warps hand the slot over
           const uint32_t a_slot = smem_base + sa * L::A_SLOT;
@@ -1733,6 +1765,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
             pa ^= 1u;
           }
         }
+        idesc = idesc_a2;
         for (int chunk = 0; chunk < p.c2_chunks; ++chunk) {
           mbar_wait(XF ? a_ready(sa) : a_full(sa), pa, 1);   // XF: the transform warps hand the slot over
           mma_block(smem_base + sa * L::A_SLOT);
@@ -1931,7 +1964,7 @@ int encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int64_t C,
 }
 
 template <int BLOCK_N, int M_SUB, int STAGES, int EPI, bool CTA2 = false>
-int launch_inst(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_inst(const CUtensorMap& ma1, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                 cudaStream_t stream, const CUtensorMap* mout = nullptr) {
   constexpr bool TS = (EPI & 32) != 0;
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2, TS ? ((EPI & 2) ? 2 : 4) : 0>;
@@ -1997,7 +2030,7 @@ int encode_out_map(CUtensorMap* mo, const TcParams& p) {
 }
 
 template <int BLOCK_N, int M_SUB, int STAGES, bool CTA2 = false>
-int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch(const CUtensorMap& ma1, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
            cudaStream_t stream) {
   const int v = epilogue_variant(p, BLOCK_N);
   const char* ts_env = getenv("VDM_GEMM_TS");
@@ -2038,7 +2071,7 @@ int launch(const CUtensorMap& ma1, const CUtensorMap& ma2, const CUtensorMap& mw
 }
 
 template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, bool XF = false>
-int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo_inst(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                      cudaStream_t stream) {
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
@@ -2078,7 +2111,7 @@ int launch_halo_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtens
 
 // fused-normalisation instances: one output + GroupNorm statistics, with or without residual (variants 4..7)
 template <int BLOCK_N, int M_SUB, int SA, int SB, bool ILV>
-int launch_halo_xf(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo_xf(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                    cudaStream_t stream) {
   switch (epilogue_variant(p, BLOCK_N)) {
     case 4: return launch_halo_inst<BLOCK_N, M_SUB, SA, SB, 4, ILV, true>(mh, ma2, mw, p, stream);
@@ -2091,7 +2124,7 @@ int launch_halo_xf(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensor
 
 // interleaved 8x8 tiles: lean epilogue variants only (the caller checked epilogue_variant < 8)
 template <int BLOCK_N, int SA, int SB>
-int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo_ilv(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                     cudaStream_t stream) {
   if (p.xf_coef != nullptr) return launch_halo_xf<BLOCK_N, 1, SA, SB, true>(mh, ma2, mw, p, stream);
   switch (epilogue_variant(p, BLOCK_N)) {
@@ -2112,7 +2145,7 @@ int launch_halo_ilv(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtenso
 }
 
 template <int BLOCK_N, int M_SUB, int SA, int SB>
-int launch_halo(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                 cudaStream_t stream) {
   if (p.xf_coef != nullptr) return launch_halo_xf<BLOCK_N, M_SUB, SA, SB, false>(mh, ma2, mw, p, stream);
   switch (epilogue_variant(p, BLOCK_N)) {
@@ -2190,7 +2223,7 @@ int launch_upfold_halo(const CUtensorMap& mh, const CUtensorMap& mw, const TcPar
 }
 
 template <int SA, int SB, int EPI, bool WIDE, bool XF = false>
-int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo_t_inst(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                        cudaStream_t stream) {
   using L = HaloTLayout<SA, SB, WIDE>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
@@ -2232,7 +2265,7 @@ int launch_halo_t_inst(const CUtensorMap& mh, const CUtensorMap& ma2, const CUte
 bool xf_variant_ok(int v) { return v >= 4 && v <= 7; }
 
 template <int SA, int SB, bool WIDE = false>
-int launch_halo_t(const CUtensorMap& mh, const CUtensorMap& ma2, const CUtensorMap& mw, const TcParams& p,
+int launch_halo_t(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap& mw, const TcParams& p,
                   cudaStream_t stream) {
   const int v = epilogue_variant(p, 128);
   if (p.xf_coef != nullptr) {
@@ -2284,7 +2317,11 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   }
   VDM_REQUIRE(a->taps == 1 || a->taps == 9, "gemm_tc: taps must be 1 or 9");
   VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
-  VDM_REQUIRE(a->C2 % BLOCK_K == 0, "gemm_tc: C2=%d must be a multiple of 64", a->C2);
+  VDM_REQUIRE(a->C2 % BLOCK_K == 0 && a->C2b % BLOCK_K == 0, "gemm_tc: C2=%d / C2b=%d must be multiples of 64", a->C2,
+              a->C2b);
+  VDM_REQUIRE(a->C2b == 0 || (a->C2 > 0 && a->a2b != nullptr), "gemm_tc: a2b needs a2 (the first tensor of the range)");
+  VDM_REQUIRE(a->a2_dtype == VDM_BF16 || a->a2_dtype == VDM_F16 || a->a2_dtype == 0,
+              "gemm_tc: a2_dtype must be VDM_BF16 or VDM_F16");
   VDM_REQUIRE(a->a1_mode == 0 || (a->a1_mode == 1 && a->taps == 9), "gemm_tc: unsupported a1_mode %d", a->a1_mode);
   VDM_REQUIRE(a->out_nchw || a->N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", a->N);
   VDM_REQUIRE(a->out_silu_f32 == nullptr, "gemm_tc: out_silu_f32 is only supported by the fp32 kernel");
@@ -2299,7 +2336,9 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   p.N = a->N;
   p.taps = a->taps;
   p.c1_chunks = a->C1 / BLOCK_K;
-  p.c2_chunks = a->C2 / BLOCK_K;
+  p.c2_chunks = (a->C2 + a->C2b) / BLOCK_K;
+  p.c2a_chunks = a->C2 / BLOCK_K;
+  p.a2_f16 = a->a2_dtype == VDM_F16 ? 1 : 0;
   p.a1_mode = a->a1_mode;
   p.is_linear = is_linear;
   p.H = a->H; p.W = a->W; p.HW = HW;
@@ -2332,7 +2371,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   VDM_REQUIRE(a->w_group_tiles == 0 || (is_linear && a->C2 == 0 && !a->out_nchw), "gemm_tc: grouped weights need taps == 1");
   VDM_REQUIRE(a->lda1 == 0 || (is_linear && a->lda1 >= a->C1 && a->lda1 % 8 == 0), "gemm_tc: bad lda1");
 
-  CUtensorMap ma1, ma2, mw;
+  CUtensorMap ma1, mw;
+  A2Maps ma2;
   int rc;
   const bool xf_epi = xf_variant_ok(epilogue_variant(p, 128));   // what the fused-normalisation instances exist for
   if (probe) {
@@ -2377,14 +2417,17 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     rc = encode_map(&ma1, a->a1, 5, dims, st, box);
   }
   if (rc) return rc;
+  ma2.a = ma2.b = ma1;
   if (a->C2 > 0) {
     VDM_REQUIRE(a->a2 != nullptr, "gemm_tc: a2 is NULL");
-    rc = encode_rows_map(&ma2, a->a2, M, a->C2);
+    rc = encode_rows_map(&ma2.a, a->a2, M, a->C2);
     if (rc) return rc;
-  } else {
-    ma2 = ma1;
+    if (a->C2b > 0) {
+      rc = encode_rows_map(&ma2.b, a->a2b, M, a->C2b);
+      if (rc) return rc;
+    }
   }
-  const int64_t K = (int64_t)a->taps * a->C1 + a->C2;
+  const int64_t K = (int64_t)a->taps * a->C1 + a->C2 + a->C2b;
   // 3x3 stride-1 layers whose CTA tile is a whole number of image rows inside one image: halo kernel (the three
   // vertical taps share one activation slot); VDM_GEMM_HALO=0 switches it off
   {
@@ -2411,13 +2454,14 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
       uint32_t wbox[2] = {BLOCK_K, 128};
       rc = encode_map(&mw2, a->w, 2, wdims, wst, wbox);
       if (rc) return rc;
-      CUtensorMap ma2p = mh;
-      if (a->C2 > 0) {   // the fused 1x1 skip operand through the same (x, image, y) view
-        const uint64_t C2 = a->C2;
+      A2Maps ma2p{mh, mh};
+      for (int src = 0; src < 2; ++src) {   // the fused 1x1 skip operand(s) through the same (x, image, y) view
+        const uint64_t C2 = src ? a->C2b : a->C2;
+        if (C2 == 0) continue;
         uint64_t d2[5] = {C2, 8, (uint64_t)a->n_img, 8, 1};
         uint64_t s2[5] = {2, C2 * 2, C2 * 2 * 64, C2 * 2 * 8, C2 * 2 * 64 * (uint64_t)a->n_img};
         uint32_t b2[5] = {BLOCK_K, 8, 2, 8, 1};
-        rc = encode_map(&ma2p, a->a2, 5, d2, s2, b2);
+        rc = encode_map(src ? &ma2p.b : &ma2p.a, src ? a->a2b : a->a2, 5, d2, s2, b2);
         if (rc) return rc;
       }
       return launch_halo_ilv<256, 3, 4>(mh, ma2p, mw2, p, stream);
@@ -2586,6 +2630,7 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   int rc = encode_map(&ma1, a->a1, 5, dims, st, box);
   if (rc) return rc;
   const int64_t K = 4 * (int64_t)a->C1;
+  const A2Maps no_a2{ma1, ma1};
   // pair tiles (256 low-res pixels x 256 / 192 channels per parity) where the layer is wide enough
   int mode = 1;
   if (const char* e = getenv("VDM_GEMM_CTA2")) mode = atoi(e);
@@ -2620,18 +2665,18 @@ int gemm_tc_upfold(const vdm_gemm_args* a, cudaStream_t stream) {
   if (rc) return rc;
   if (cta2) {
     p.tiles_per_par = (int)pair_tiles;
-    if (bn2 == 256) return launch_inst<256, 1, 5, 8, true>(ma1, ma1, mw, p, stream);
-    return launch_inst<192, 1, 6, 8, true>(ma1, ma1, mw, p, stream);
+    if (bn2 == 256) return launch_inst<256, 1, 5, 8, true>(ma1, no_a2, mw, p, stream);
+    return launch_inst<192, 1, 6, 8, true>(ma1, no_a2, mw, p, stream);
   }
   const int64_t t2 = ((M + 255) / 256) * (a->N / 128), t1 = ((M + 127) / 128) * (a->N / 128);
   const int sms = num_sms();
   const bool two = (double)((4 * t2 + sms - 1) / sms) * 2.0 <= (double)((4 * t1 + sms - 1) / sms) * 1.35;
   if (two) {
     p.tiles_per_par = (int)t2;
-    return launch_inst<128, 2, 4, 8>(ma1, ma1, mw, p, stream);
+    return launch_inst<128, 2, 4, 8>(ma1, no_a2, mw, p, stream);
   }
   p.tiles_per_par = (int)t1;
-  return launch_inst<128, 1, 5, 8>(ma1, ma1, mw, p, stream);
+  return launch_inst<128, 1, 5, 8>(ma1, no_a2, mw, p, stream);
 }
 
 }  // namespace vdm

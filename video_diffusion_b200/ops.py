@@ -32,7 +32,8 @@ def _nbytes(*tensors):
 
 def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
                out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
-               w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0, a1_coef=None, a1_act=False):
+               w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0, a1_coef=None, a1_act=False,
+               a2b=None):
     g = GemmArgs()
     g.dtype = dt(a1.dtype)
     g.taps, g.a1_mode = taps, a1_mode
@@ -45,6 +46,13 @@ def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, ro
     else:
         g.a1, g.lda1 = ptr(a1), 0
     g.a2, g.w = ptr(a2), ptr(w)
+    # second operand range: one or two tensors (channel concat), bf16 -- or fp16 (the stream itself) with fp16 weight
+    # columns for that range
+    g.a2b, g.C2b = ptr(a2b), (0 if a2b is None else a2b.shape[-1])
+    if a2 is not None:
+        if a2.dtype not in (torch.bfloat16, torch.float16, torch.float32) or (a2b is not None and a2b.dtype != a2.dtype):
+            raise TypeError('vdm_gemm: a2 / a2b must share a 16-bit dtype')
+        g.a2_dtype = dt(a2.dtype) if a2.dtype != torch.float32 else 0
     g.w_group_tiles = w_group_tiles
     g.n_prob, g.prob_a_cols, g.prob_w_rows, g.prob_out_stride = n_prob, prob_a_cols, prob_w_rows, prob_out_stride
     g.bias = ptr(bias)
@@ -74,7 +82,7 @@ def gemm(a1, w, N, **kw):
     lib = _lib.load()
     g = _gemm_args(a1, w, N, **kw)
     M = g.n_img * g.H * g.W
-    K = g.taps * g.C1 + g.C2
+    K = g.taps * g.C1 + g.C2 + g.C2b
     name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if g.taps == 9 else '_linear')
     _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K * g.n_prob,
            meta=f'M={M} N={N} K={K} HxW={g.H}x{g.W} mode={g.a1_mode} res={int(bool(g.residual))} '
