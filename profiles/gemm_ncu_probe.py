@@ -23,8 +23,9 @@ for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_256_128', 64, 64, 25
     a1 = torch.randn(M, C1, device=dev).bfloat16()
     w = (torch.randn(N, taps * C1, device=dev) * 0.02).bfloat16()
     bias = torch.randn(N, device=dev)
-    resid = torch.randn(M, N, device=dev) if use_res else None
-    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    # the residual stream of the bf16 model is fp16 (round 2): stream outputs / residuals as the model launches them
+    resid = torch.randn(M, N, device=dev).half() if use_res else None
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float16)
     st = torch.zeros(N_IMG, 2, N, device=dev, dtype=torch.int64)
     geo = dict(n_img=N_IMG, H=H, W=W)
     for _ in range(2):
@@ -37,10 +38,22 @@ for name, H, W, C1, N, taps, use_res, bf16_out in [('conv64_256_128', 64, 64, 25
 from video_diffusion_b200.unet import fold_upsample_weights  # noqa: E402
 x = torch.randn(N_IMG * 32 * 32, 256, device=dev).bfloat16()
 wf = fold_upsample_weights(torch.randn(256, 256, 3, 3) * 0.02).to(dev).bfloat16()
-out = torch.empty(N_IMG * 64 * 64, 256, device=dev)
+out = torch.empty(N_IMG * 64 * 64, 256, device=dev, dtype=torch.float16)
 st = torch.zeros(N_IMG, 2, 256, device=dev, dtype=torch.int64)
 for _ in range(2):
     ops.gemm(x, wf, 256, n_img=N_IMG, H=64, W=64, taps=4, a1_mode=3, bias=torch.zeros(256, device=dev), out_f32=out,
              stats_out=st, C1=256)
+torch.cuda.synchronize()
+# conv2 of a 64x64 ResBlock as the model runs it: bf16 3x3 part + identity residual read from the fp16 stream (f16 MMAs)
+M = N_IMG * 64 * 64
+a2n = torch.randn(M, 128, device=dev).bfloat16()
+xs = torch.randn(M, 128, device=dev).half()
+w3 = (torch.randn(128, 9 * 128, device=dev) * 0.02).bfloat16()
+wcat = torch.cat([w3.view(torch.int16), torch.eye(128, device=dev).half().view(torch.int16)], dim=1).contiguous().view(torch.bfloat16)
+out = torch.empty(M, 128, device=dev, dtype=torch.float16)
+st = torch.zeros(N_IMG, 2, 128, device=dev, dtype=torch.int64)
+for _ in range(2):
+    ops.gemm(a2n, wcat, 128, n_img=N_IMG, H=64, W=64, taps=9, a2=xs, bias=torch.zeros(128, device=dev), out_f32=out,
+             stats_out=st, C1=128)
 torch.cuda.synchronize()
 print('done')

@@ -289,7 +289,7 @@ class UNetModel(nn.Module):
                     # (vdm_gemm_args.a2_dtype = VDM_F16).  One 16-bit container; the kernel never interprets it.
                     w3 = conv_w(p + '.out_layers.3.weight')
                     tail = (sd[p + '.skip_connection.weight'].reshape(w3.shape[0], -1) if node['skip']
-                            else torch.eye(w3.shape[0]))
+                            else torch.eye(w3.shape[0], device=w3.device))
                     both = torch.cat([w3.to(torch.bfloat16).view(torch.int16), tail.to(torch.float16).view(torch.int16)],
                                      dim=1)
                     P[p + '.w2s'] = both.to(dev).contiguous().view(torch.bfloat16)
