@@ -436,6 +436,9 @@ class UNetModel(nn.Module):
         # projection as well.  Otherwise (fp32 stream, fp32 mode) gn_apply writes the raw cast next to the operand.
         stream_a2 = adt == torch.bfloat16 and self._sdt == torch.float16 and (node['skip'] or HW >= 4096)
         araw = ws.buf(p + '.araw', (M, Cin), adt) if (node['skip'] and not stream_a2) else None
+        # one pass over the block input: normalised+SiLU operand of conv1 (and the raw cast for the 1x1 skip, if needed)
+        ops.gn_apply(src1, src2, n_img, H, W, a1, stats1=st1, stats2=st2, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'],
+                     silu=True, out_raw=araw)
         off = node['emb_off']
         ss = self.use_scale_shift_norm
         st_h1 = self._fused_stats(ws, p + '.h1', n_img, HW, Cout)
