@@ -85,6 +85,7 @@ class UNetModel(nn.Module):
         self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
+        self.proj_identity = os.environ.get('VDM_PROJ_IDENTITY', '1') != '0'
         self.time_embed_dim = E = model_channels * 4
         if model_channels % 64 or (model_channels // num_heads) % 4:
             raise NotImplementedError('model_channels must be a multiple of 64')
@@ -302,6 +303,11 @@ class UNetModel(nn.Module):
                     put(q + '.gn_w', sd[q + '.norm.weight']); put(q + '.gn_b', sd[q + '.norm.bias'])
                     put(q + '.qkv_w', sd[q + '.qkv.weight'], adt); put(q + '.qkv_b', sd[q + '.qkv.bias'])
                     put(q + '.proj_w', sd[q + '.proj_out.weight'], adt); put(q + '.proj_b', sd[q + '.proj_out.bias'])
+                    if adt == torch.bfloat16:     # proj_out + identity columns (fp16): `x + proj(a)` as one GEMM, see w2s
+                        pw = sd[q + '.proj_out.weight']
+                        both = torch.cat([pw.to(torch.bfloat16).view(torch.int16),
+                                          torch.eye(pw.shape[0], device=pw.device).to(torch.float16).view(torch.int16)], dim=1)
+                        P[q + '.proj_ws'] = both.to(dev).contiguous().view(torch.bfloat16)
                 q = p + '.temporal_attention'
                 nets = ('rpe_q', 'rpe_k', 'rpe_v')
                 if not self.use_rpe_net:
@@ -619,8 +625,7 @@ class UNetModel(nn.Module):
         st = self._fused_stats(ws, q + '.out', N, HW, C)
         # + NORMALISED x.  The rows of this GEMM are (image, pixel), so the epilogue statistics are
         # exactly the per-image GroupNorm sums the spatial attention needs next.
-        ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h2,
-                 stats_out=st)
+        self._proj_out(att, q, xn, h2, st, N, H, W, C)
         st = self._stats_of(ws, q + '.out', h2, st, N, HW)
         # ---- spatial attention (unet.py:258-266)
         q = p + '.spatial_attention'
@@ -640,9 +645,20 @@ class UNetModel(nn.Module):
             attn_log['spatial'].append(amap)
         h3 = ws.buf(q + '.out', (M, C), self._sdt)
         st3 = self._fused_stats(ws, q + '.out', N, HW, C)
-        ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=h3,
-                 stats_out=st3)
+        self._proj_out(att, q, xn, h3, st3, N, H, W, C)
         return h3, st3
+
+    def _proj_out(self, att, q, xn, out, st, N, H, W, C):
+        """x + proj_out(a) (unet.py:537-538; x = the NORMALISED input).  With the fp16 stream the residual is
+        a second K range of the GEMM -- fp16 MMAs of xn against identity columns -- instead of an epilogue read:
+        this short-K linear is bound by its epilogue, not by the tensor cores."""
+        P = self._packed
+        if self.proj_identity and xn.dtype == torch.float16:
+            ops.gemm(att, P[q + '.proj_ws'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], a2=xn, out_f32=out,
+                     stats_out=st, C1=C)
+        else:
+            ops.gemm(att, P[q + '.proj_w'], C, n_img=N, H=H, W=W, taps=1, bias=P[q + '.proj_b'], residual=xn, out_f32=out,
+                     stats_out=st)
 
     def _run(self, ws, T_attn, per_frame_t, attn_log=None):
         """The whole forward as a flat sequence of libvdm launches: a prologue on the full batch (conditioning mix,
