@@ -407,6 +407,42 @@ def test_upsample_fold_and_elementwise_fp16_stream(monkeypatch):
     assert torch.equal(e16, e32.half())
 
 
+@pytest.mark.parametrize('n,HW,C,N,kind', [(160, 256, 384, 1152, 'qkv'), (160, 64, 512, 1536, 'qkv'),
+                                           (160, 256, 384, 384, 'proj'), (157, 64, 512, 512, 'proj'),
+                                           (160, 256, 384, 384, 'proj32'), (40, 256, 128, 256, 'qkv')])
+def test_linear_a_stationary_kernel(n, HW, C, N, kind, monkeypatch):
+    """The A-stationary pair kernel of the short-K attention linears (a worker keeps the whole K extent of its row tile
+    in shared memory and streams only weight tiles) against the plain kernel: same products in the same k order, so
+    outputs and GroupNorm statistics are bit-identical; plus torch."""
+    o = ops()
+    M = n * HW
+    H = W = int(HW ** 0.5)
+    a = rnd(M, C, seed=1).bfloat16()
+    w = rnd(N, C, seed=2, scale=C ** -0.5).bfloat16()
+    bias = rnd(N, seed=3)
+    outs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('VDM_GEMM_ASTAT', mode)
+        if kind == 'qkv':
+            out = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+            o.gemm(a, w, N, n_img=M, H=1, W=1, taps=1, bias=bias, out_bf16=out)
+            outs[mode] = (out, None)
+        else:
+            io = torch.float32 if kind == 'proj32' else torch.float16
+            res = rnd(M, N, seed=4).to(io)
+            out = torch.full((M, N), float('nan'), device='cuda', dtype=io)
+            st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+            o.gemm(a, w, N, n_img=n, H=H, W=W, taps=1, bias=bias, residual=res, out_f32=out, stats_out=st)
+            outs[mode] = (out, st)
+    torch.cuda.synchronize()
+    assert torch.equal(outs['1'][0], outs['0'][0])
+    ref = a.float() @ w.float().t() + bias
+    if kind != 'qkv':
+        assert torch.equal(outs['1'][1], outs['0'][1])
+        ref = ref + res.float()
+    assert relerr(outs['1'][0], ref) < 6e-3
+
+
 def test_fused_groupnorm_unsupported_shapes_raise():
     """a1_coef on a shape / epilogue the transform-stage kernels do not cover is an error, not a silent slow path."""
     o = ops()

@@ -1120,6 +1120,177 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------
+// Short-K linears (attention qkv / proj_out: K = 384 or 512, N = 3..8 tiles), "A-stationary" variant, CTA pair.
+//
+// The plain kernel re-fetches a row tile of A once per output-column tile; with six k-blocks per tile these linears
+// are bound by exactly that L2 -> shared-memory operand delivery (the TMA-store epilogue made them no faster).  Here a
+// worker (CTA pair) owns a CONTIGUOUS run of tiles with the column tile fastest, keeps the whole K extent of its
+// current row tile resident (KB_MAX x 16 KB per CTA) and streams only weight tiles through the ring: A is read once
+// per row tile instead of once per (row tile, column tile).  Roles, accumulator staging and both epilogue
+// implementations are those of gemm_tc_kernel (they only see a tile range).
+template <int BLOCK_N, int KB_MAX, int SB, int TS_ESIZE>
+struct AStatLayout {
+  static constexpr int CHUNK = 32;
+  static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_BYTES = KB_MAX * A_SUB_BYTES;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // this CTA's half of the weight tile
+  static constexpr int B_SLOT = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_OFFSET = A_BYTES;
+  static constexpr int STG_OFFSET = B_OFFSET + SB * B_SLOT;
+  static constexpr int STG_BYTES = TS_ESIZE ? BLOCK_M * BLOCK_N * TS_ESIZE : EPI_WARPS * 32 * (CHUNK + 4) * 4;
+  static constexpr int STAT_IMGS = 2;
+  static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int STAT_BYTES = TS_ESIZE ? 0 : 4 * STAT_IMGS * 2 * BLOCK_N * 4;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+  static constexpr int NUM_BARS = 2 + 2 * SB + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int KB_MAX, int SB, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __grid_constant__ CUtensorMap tm_a1,
+                                                                       const __grid_constant__ CUtensorMap tm_w,
+                                                                       const __grid_constant__ CUtensorMap tm_out,
+                                                                       const TcParams p, const int tiles_per_worker) {
+  pdl_launch_dependents();
+  constexpr bool TS = (EPI & 32) != 0;
+  using L = AStatLayout<BLOCK_N, KB_MAX, SB, TS ? ((EPI & 2) ? 2 : 4) : 0>;
+  constexpr int TILE_M = 2 * BLOCK_M;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int worker = (int)(blockIdx.x >> 1);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  const uint32_t a_full = bar_base, a_empty = bar_base + 8u;
+  auto b_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 + SB + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SB + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SB + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.c1_chunks;
+  const int n_tiles_n = p.N / BLOCK_N;
+  const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
+  const int t0 = worker * tiles_per_worker;
+  const int t_end = min(n_tiles, t0 + tiles_per_worker);
+
+  for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
+    reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), EPI_WARPS * 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(tmem_cols<BLOCK_N, 1>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      int cur_mt = -1, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = t0; tile < t_end; ++tile) {
+        const int mt = tile / n_tiles_n;
+        const int n0 = (tile - mt * n_tiles_n) * BLOCK_N;
+        const int m0 = mt * TILE_M + (int)cta_rank * BLOCK_M;
+        if (mt != cur_mt) {     // new row tile: its whole K extent, once
+          mbar_wait(a_empty, pa ^ 1u, 0);
+          if (cta_rank == 0) mbar_expect_tx(a_full, 2u * (uint32_t)num_kb * L::A_SUB_BYTES);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_5d_2cta(smem_base + kb * L::A_SUB_BYTES, &tm_a1, a_full, kb * BLOCK_K, m0, 0, 0, 0);
+          pa ^= 1u;
+          cur_mt = mt;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(b_empty(sb), pb ^ 1u, 4);
+          if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::B_BYTES);
+          tma_load_2d_2cta(smem_base + L::B_OFFSET + sb * L::B_SLOT, &tm_w, b_full(sb), kb * BLOCK_K,
+                           n0 + (int)cta_rank * (BLOCK_N / 2));
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = instr_desc<BLOCK_N, 256>();
+      int cur_mt = -1, sb = 0, it = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = t0; tile < t_end; ++tile, ++it) {
+        const int mt = tile / n_tiles_n;
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, 3);
+        if (mt != cur_mt) {
+          mbar_wait(a_full, pa, 1);
+          pa ^= 1u;
+          cur_mt = mt;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(b_full(sb), pb, 5);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t a_desc = make_smem_desc(smem_base + kb * L::A_SUB_BYTES);
+          const uint64_t b_desc = make_smem_desc(smem_base + L::B_OFFSET + sb * L::B_SLOT);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_2cta(tmem_acc, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(b_empty(sb));
+          if (++sb == SB) {
+            sb = 0;
+            pb ^= 1u;
+          }
+        }
+        umma_commit_2cta(tmem_full_bar(as));
+        // last tile of this row tile: the A region is free once these MMAs have retired
+        if (tile + 1 >= t_end || (tile + 1) / n_tiles_n != mt) umma_commit_2cta(a_empty);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9): the tile range [t0, t_end), step 1 =====================
+    if constexpr (TS)
+      epilogue_ts_role<BLOCK_N, (EPI & 2) != 0, true>(p, &tm_out, smem_gen + L::STG_OFFSET, smem_base + L::STG_OFFSET,
+                                                      tmem_base, tmem_full_bar(0), tmem_empty_bar(0), t_end, n_tiles_n, t0, 1,
+                                                      cta_rank, warp, lane);
+    else
+      epilogue_role<BLOCK_N, 1, L::CHUNK, EPI, true>(p, reinterpret_cast<float*>(smem_gen + L::STG_OFFSET),
+                                                     reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET), L::STAT_IMGS,
+                                                     tmem_base, tmem_full_bar(0), tmem_empty_bar(0), t_end, n_tiles_n, t0, 1,
+                                                     cta_rank, warp, lane);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tmem_cols<BLOCK_N, 1>())
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 3x3 stride-1 convolution, "halo" variant (always a CTA pair).
 //
 // The plain kernel fetches one shifted activation box per tap: nine L2 -> shared-memory copies of the same
@@ -2005,6 +2176,32 @@ int epilogue_variant(const TcParams& p, int block_n) {
   return (p.residual ? 1 : 0) | (p.out_bf16 ? 2 : 0) | (p.stats_out ? 4 : 0) | (p.io_f16 ? 64 : 0);
 }
 
+template <int BLOCK_N, int KB_MAX, int SB, int EPI>
+int launch_astat(const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& mo, const TcParams& p,
+                 cudaStream_t stream) {
+  constexpr bool TS = (EPI & 32) != 0;
+  using L = AStatLayout<BLOCK_N, KB_MAX, SB, TS ? ((EPI & 2) ? 2 : 4) : 0>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  static PerDevice<bool> configured;
+  if (!configured.get()) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_astat_kernel<BLOCK_N, KB_MAX, SB, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (A-stationary): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured.get() = true;
+  }
+  const int n_tiles = (p.N / BLOCK_N) * ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+  int workers = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;
+  const int tpw = (n_tiles + workers - 1) / workers;      // contiguous tiles per worker, column tile fastest
+  workers = (n_tiles + tpw - 1) / tpw;
+  launch_kernel(gemm_tc_astat_kernel<BLOCK_N, KB_MAX, SB, EPI>, 2 * workers, NUM_THREADS, L::TOTAL, stream, 2, ma1, mw, mo, p,
+                tpw);
+  VDM_AFTER_LAUNCH("gemm_tc_astat");
+  return 0;
+}
+
 int bad_variant(int v) {
   set_error("gemm_tc: epilogue combination %d is not built (fp16 stream IO goes with an fp16 output: variants 64, 65, 68, 69)", v);
   return -1;
@@ -2530,6 +2727,41 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   }
   VDM_REQUIRE(!xf, "gemm_tc: fused normalisation (a1_coef) is not available for this shape / epilogue "
                    "(check vdm_gemm_fused_norm_supported first)");
+  // short-K linears with several column tiles (attention qkv / proj_out): A-stationary pair kernel
+  {
+    const char* e = getenv("VDM_GEMM_ASTAT");
+    const bool on = e == nullptr || atoi(e) != 0;
+    const bool base = on && is_linear && a->C2 == 0 && n_prob == 1 && a->w_group_tiles == 0 && !a->out_nchw &&
+                      !a->rowbias && p.c1_chunks <= 8 && a->N % 128 == 0 && (M + 255) / 256 >= 37;
+    if (base) {
+      const int v = epilogue_variant(p, 128);
+      const char* ts_env = getenv("VDM_GEMM_TS");
+      const bool ts_on = ts_env == nullptr || atoi(ts_env) != 0;
+      CUtensorMap mo = ma1;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      if (v == 2 && ts_on && a->N / 128 >= 2) {                     // bf16 output, bias only: TMA-store epilogue
+        const bool wide = a->N % 192 == 0;
+        if (wide ? encode_out_map<192, 2>(&mo, p) == 0 : encode_out_map<128, 2>(&mo, p) == 0) {
+          uint32_t wbox[2] = {BLOCK_K, (uint32_t)(wide ? 96 : 64)};
+          rc = encode_map(&mw, a->w, 2, wdims, wst, wbox);
+          if (rc) return rc;
+          if (wide) return launch_astat<192, 8, 4, 34>(ma1, mw, mo, p, stream);
+          return launch_astat<128, 8, 6, 34>(ma1, mw, mo, p, stream);
+        }
+      } else if ((v == 4 || v == 5 || v == 68 || v == 69) && a->N / 128 >= 2) {   // stream output (+ residual) + statistics
+        uint32_t wbox[2] = {BLOCK_K, 64};
+        rc = encode_map(&mw, a->w, 2, wdims, wst, wbox);
+        if (rc) return rc;
+        switch (v) {
+          case 4: return launch_astat<128, 8, 6, 4>(ma1, mw, mo, p, stream);
+          case 5: return launch_astat<128, 8, 6, 5>(ma1, mw, mo, p, stream);
+          case 68: return launch_astat<128, 8, 6, 68>(ma1, mw, mo, p, stream);
+          default: return launch_astat<128, 8, 6, 69>(ma1, mw, mo, p, stream);
+        }
+      }
+    }
+  }
   int block_n = a->out_nchw || a->N <= 16 ? 16 : (a->N % 128 == 0 ? 128 : 64);
   // 256x128 CTA tiles (two 128-row sub-tiles sharing every weight tile) halve the L2->smem operand
   // traffic per FLOP; use them unless the layer is too small to fill the SMs that way.
