@@ -25,10 +25,13 @@ SHAPES = [  # name, H, W, C1, N, taps, C2, residual, bf16 out, stats
     ('proj16_384_384', 16, 16, 384, 384, 1, 0, True, False, True),
     ('conv8_512_512', 8, 8, 512, 512, 9, 0, True, False, True),
 ]
+SHAPES += [('qkv8_512_1536', 8, 8, 512, 1536, 1, 0, False, True, False), ('proj8_512_512', 8, 8, 512, 512, 1, 0, True, False, True)]
+if os.environ.get('TRACE_SHAPES'):          # e.g. TRACE_SHAPES=qkv16,proj16,qkv8
+    SHAPES = [s_ for s_ in SHAPES if any(s_[0].startswith(k) for k in os.environ['TRACE_SHAPES'].split(','))]
 VARIANTS = [('auto', {}), ('1cta_msub1', dict(VDM_GEMM_CTA2='0', VDM_GEMM_MSUB='1')),
             ('1cta_msub2', dict(VDM_GEMM_CTA2='0', VDM_GEMM_MSUB='2')), ('2cta', dict(VDM_GEMM_CTA2='2'))]
 if os.environ.get('TRACE_EXPERIMENTS'):     # timing experiments: VDM_GEMM_DEBUG 1 = no TMA loads, 2 = no MMAs
-    VARIANTS = [(f'{n}{sfx}', dict(e, **d)) for n, e in VARIANTS[1:] for sfx, d in
+    VARIANTS = [(f'{n}{sfx}', dict(e, **d)) for n, e in VARIANTS for sfx, d in
                 (('', {}), ('-noload', dict(VDM_GEMM_DEBUG='1')), ('-nomma', dict(VDM_GEMM_DEBUG='2')))]
 
 
@@ -56,6 +59,7 @@ def main():
         for vname, env in VARIANTS:
             for k in ('VDM_GEMM_CTA2', 'VDM_GEMM_MSUB', 'VDM_GEMM_DEBUG'):
                 os.environ.pop(k, None)
+            os.environ['VDM_GEMM_ASTAT'] = '0'      # the A-stationary kernel carries no counters
             os.environ.update(env)
             times = []
             for it in range(5):

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libvdm.so')
+LIB_PATH = os.environ.get('VDM_LIB') or os.path.join(_HERE, 'libvdm.so')    # VDM_LIB: diagnostics builds (make TRACE=1)
 
 F32, BF16, F64, I64, F16 = 0, 1, 2, 3, 4
 TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOGVAR=4, MODEL_VAR=5, ACP=6,
