@@ -421,6 +421,7 @@ def test_linear_a_stationary_kernel(n, HW, C, N, kind, monkeypatch):
     w = rnd(N, C, seed=2, scale=C ** -0.5).bfloat16()
     bias = rnd(N, seed=3)
     outs = {}
+    monkeypatch.setenv('VDM_GEMM_LINT', '0')      # (the transposed-role kernel takes these shapes by default)
     for mode in ('1', '0'):
         monkeypatch.setenv('VDM_GEMM_ASTAT', mode)
         if kind == 'qkv':
@@ -441,6 +442,54 @@ def test_linear_a_stationary_kernel(n, HW, C, N, kind, monkeypatch):
         assert torch.equal(outs['1'][1], outs['0'][1])
         ref = ref + res.float()
     assert relerr(outs['1'][0], ref) < 6e-3
+
+
+@pytest.mark.parametrize('n,HW,C,N,kind', [(160, 256, 384, 1152, 'qkv'), (160, 64, 512, 1536, 'qkv'),
+                                           (160, 256, 384, 384, 'proj'), (157, 64, 512, 512, 'proj'),
+                                           (80, 256, 384, 384, 'proj32'), (7, 128, 64, 128, 'proj'),
+                                           (33, 64, 128, 256, 'proj_nores'), (3, 256, 192, 384, 'qkv')])
+def test_linear_on_transposed_role_kernel(n, HW, C, N, kind, monkeypatch):
+    """Linears on the transposed-role kernel (weights = M operand, 256 pixels = N operand, every K block through the
+    second-range path; lean epilogue with per-lane GroupNorm statistics, incl. two 64-pixel images per warp) against
+    the generic kernel and torch.  Ragged row counts, column-block views of A, fp16 / fp32 stream IO."""
+    o = ops()
+    M = n * HW
+    H = W = int(HW ** 0.5) if int(HW ** 0.5) ** 2 == HW else 0
+    if H == 0:
+        H, W = HW // 8, 8
+    wide = rnd(M, C + 64, seed=1).bfloat16()
+    a = wide[:, 64:]                                   # a column block of a wider tensor (lda1 > C1)
+    w = rnd(N, C, seed=2, scale=C ** -0.5).bfloat16()
+    bias = rnd(N, seed=3)
+    outs = {}
+    monkeypatch.setenv('VDM_GEMM_ASTAT', '0')
+    for mode in ('2', '0'):
+        monkeypatch.setenv('VDM_GEMM_LINT', mode)
+        if kind == 'qkv':
+            out = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+            o.gemm(a, w, N, n_img=M, H=1, W=1, taps=1, bias=bias, out_bf16=out)
+            outs[mode] = (out, None)
+        else:
+            io = torch.float32 if kind == 'proj32' else torch.float16
+            res = None if kind == 'proj_nores' else rnd(M, N, seed=4).to(io)
+            out = torch.full((M, N), float('nan'), device='cuda', dtype=io)
+            st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+            o.gemm(a, w, N, n_img=n, H=H, W=W, taps=1, bias=bias, residual=res, out_f32=out, stats_out=st)
+            outs[mode] = (out, st)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    if kind != 'qkv':
+        if res is not None:
+            ref = ref + res.float()
+        got = outs['2'][1].double() / 2 ** 24
+        want = torch.stack([outs['2'][0].double().view(n, HW, N).sum(1), (outs['2'][0].double() ** 2).view(n, HW, N).sum(1)], 1)
+        # statistics of the fp32 values before the output rounding: compare with the generic kernel's and with the
+        # rounded output's own sums
+        assert relerr(got, outs['0'][1].double() / 2 ** 24) < 1e-5
+        assert relerr(got, want) < (1e-5 if kind == 'proj32' else 2e-3)
+    assert torch.isfinite(outs['2'][0].float()).all()
+    assert relerr(outs['2'][0], outs['0'][0]) < 2e-3
+    assert relerr(outs['2'][0], ref) < 6e-3
 
 
 def test_fused_groupnorm_unsupported_shapes_raise():
@@ -861,6 +910,26 @@ def test_attention_spatial_tensor_core(L, hd):
         out = torch.empty(n, L, Cc, device='cuda', dtype=odt)
         o.attn_spatial(qkv, n, L, heads, hd, out)
         assert relerr(out, ref) < (4e-3 if odt == torch.float32 else 8e-3)   # P is rounded to bf16 for the PV product
+
+
+@pytest.mark.parametrize('n,L,hd', [(160, 256, 96), (161, 64, 128), (5, 128, 64), (37, 256, 128), (9, 64, 32),
+                                    (150, 128, 96)])
+def test_attention_spatial_tcgen05(n, L, hd):
+    """The tcgen05 / TMEM kernel (bf16 in, bf16 out, L in {64, 128, 256}): several work items per CTA, two images per
+    tile at L = 64 incl. an odd image count, both softmax groups, peaky and flat rows."""
+    o = ops()
+    heads = 4
+    Cc = heads * hd
+    qkv = (rnd(n, L, 3 * Cc, seed=3) * 1.7).bfloat16()
+    qkv[0, :, :Cc] *= 4.0          # one image with sharply peaked rows
+    qkv[-1, :, :Cc] = 0            # and one with exactly uniform attention
+    ref = _attn_ref(qkv.float().view(n, 1, L, 3 * Cc), heads).view(n, L, Cc)
+    out = torch.full((n, L, Cc), float('nan'), device='cuda', dtype=torch.bfloat16)
+    o.attn_spatial(qkv, n, L, heads, hd, out)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 8e-3
+    per_img = (out.float() - ref).flatten(1).abs().amax(1) / ref.flatten(1).abs().amax(1)
+    assert float(per_img.max()) < 2e-2, per_img
 
 
 def test_rpe_hidden():

@@ -233,6 +233,8 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 
 int attn_spatial_tc(const void* qkv, int n_img, int L, int heads, int hd, void* out_a, int out_dtype,
                     cudaStream_t stream);
+bool attn_spatial_sm100_supported(int L, int heads, int hd);
+int attn_spatial_sm100(const void* qkv, int n_img, int L, int heads, int hd, void* out_a, cudaStream_t stream);
 
 }  // namespace vdm
 
@@ -266,7 +268,13 @@ extern "C" int vdm_attn_spatial(const void* qkv, int32_t qkv_dtype, int32_t n_im
                                 void* out_a, int32_t out_dtype, vdm_stream_t stream) {
   VDM_REQUIRE(qkv && out_a, "attn_spatial: NULL pointer");
   VDM_REQUIRE(hd % 4 == 0 && hd <= 128, "attn_spatial: head_dim=%d must be a multiple of 4, <= 128", hd);
-  if (qkv_dtype == VDM_BF16) return attn_spatial_tc(qkv, n_img, L, heads, hd, out_a, out_dtype, (cudaStream_t)stream);
+  if (qkv_dtype == VDM_BF16) {
+    // tcgen05 / TMEM kernel where the shape fits its envelope, else the mma.sync flash kernel
+    if (out_dtype == VDM_BF16 && attn_spatial_sm100_supported(L, heads, hd) &&
+        (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_a) & 15) == 0)
+      return attn_spatial_sm100(qkv, n_img, L, heads, hd, out_a, (cudaStream_t)stream);
+    return attn_spatial_tc(qkv, n_img, L, heads, hd, out_a, out_dtype, (cudaStream_t)stream);
+  }
   const int hs = hd + 4;
   const size_t smem = sizeof(float) * ((size_t)2 * L * hs + 8 * hs + 8 * (size_t)L);
   VDM_REQUIRE(smem <= 227 * 1024, "attn_spatial: L=%d, head_dim=%d needs %zu B of shared memory", L, hd, smem);

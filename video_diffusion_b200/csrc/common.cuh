@@ -67,7 +67,15 @@ inline int num_sms() {
 // its writes are visible.  Nothing global is written before the wait, so there is no write-after-read hazard either.
 // Captured into a CUDA graph the attribute becomes a programmatic edge between the two kernel nodes.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef VDM_PDL_LATE
+// late-trigger protocol: the trigger at the top of a kernel is dropped, the persistent GEMMs release their dependents
+// once a CTA's TMA producer has issued its last load (pdl_trigger_late), every other kernel at its exit
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_trigger_late() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger_late() {}
+#endif
 
 inline bool pdl_enabled() {
   static int on = -1;

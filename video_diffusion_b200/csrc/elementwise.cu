@@ -7,6 +7,10 @@
 
 #include "common.cuh"
 
+#ifndef GN_MIN_BLOCKS
+#define GN_MIN_BLOCKS 1
+#endif
+
 namespace vdm {
 namespace {
 
@@ -85,7 +89,7 @@ struct ApplyParams {
 // InT: float, __half (fp16 residual stream; two-source concat allowed like float) or __nv_bfloat16 (conv output kept in
 // bf16, single source).
 template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(256, GN_MIN_BLOCKS) gn_apply_kernel(const ApplyParams p) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -758,7 +762,9 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
                 a->out, a->out_raw, a->out_f32_copy, a->copy_dtype == VDM_F16 ? 1 : 0, 0};
   const int HW = a->H * a->W;
   const int C8 = C / 8;
-  const int rows = C8 >= 256 ? 1 : 256 / C8;
+  int tpb = 256;                       // VDM_GN_THREADS: block size (profiles/overlap_probe.py)
+  if (const char* e = getenv("VDM_GN_THREADS")) tpb = std::max(32, atoi(e));
+  const int rows = C8 >= tpb ? 1 : tpb / C8;
   const int threads = C8 * rows;
   int ppb = rows * 32;
   while (ppb > rows * 8 && (long long)((HW + ppb - 1) / ppb) * a->n_img < 4LL * num_sms()) ppb >>= 1;

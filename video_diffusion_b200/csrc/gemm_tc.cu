@@ -1025,6 +1025,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
       }
       if (kTrace && p.trace) p.trace[blockIdx.x * 8 + 0] = (unsigned long long)tr_wait;
+      pdl_trigger_late();   // every load of this CTA is issued: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -1230,6 +1231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
           }
         }
       }
+      pdl_trigger_late();   // every load of this CTA is issued: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -1454,6 +1456,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           load_b((9 * p.c1_chunks + chunk) * BLOCK_K, n0);
         }
       }
+      pdl_trigger_late();   // every load of this CTA is issued: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -1690,6 +1693,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(con
           }
         }
       }
+      pdl_trigger_late();   // every load of this CTA is issued: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -1891,6 +1895,7 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           load_w((9 * p.c1_chunks + chunk) * BLOCK_K);
         }
       }
+      pdl_trigger_late();   // every load of this CTA is issued: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -2016,14 +2021,27 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
             for (int i = 0; i < 32; ++i) res_cur[i] = res_next[i];
           }
         }
+        if constexpr (STATS) {
+          // 64-pixel images (8x8 level, linears only): the warp's first 64 pixels are an image of their own
+          if (chunk == 1 && p.HW == 64) {
+            if (p.stats_out != nullptr && row0 < p.M) {
+              unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) + (size_t)(row0 / 64) * 2 * p.N + c;
+              atomicAdd(tab, (unsigned long long)__float2ll_rn(rsum * 16777216.0f));
+              atomicAdd(tab + p.N, (unsigned long long)__float2ll_rn(rsq * 16777216.0f));
+            }
+            rsum = 0.f;
+            rsq = 0.f;
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));
       if constexpr (STATS) {
-        // this warp's 128 pixels lie in one image (H*W % 256 == 0): two fixed-point atomics per channel
-        if (p.stats_out != nullptr && row0 < p.M) {
-          unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) + (size_t)(row0 / p.HW) * 2 * p.N + c;
+        // this warp's 128 pixels (or, with 64-pixel images, its last 64) lie in one image: two fixed-point atomics per channel
+        const int srow = p.HW == 64 ? row0 + 64 : row0;
+        if (p.stats_out != nullptr && srow < p.M) {
+          unsigned long long* tab = reinterpret_cast<unsigned long long*>(p.stats_out) + (size_t)(srow / p.HW) * 2 * p.N + c;
           atomicAdd(tab, (unsigned long long)__float2ll_rn(rsum * 16777216.0f));
           atomicAdd(tab + p.N, (unsigned long long)__float2ll_rn(rsq * 16777216.0f));
         }
@@ -2727,6 +2745,32 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   }
   VDM_REQUIRE(!xf, "gemm_tc: fused normalisation (a1_coef) is not available for this shape / epilogue "
                    "(check vdm_gemm_fused_norm_supported first)");
+  // Linears on the transposed-role kernel (no 3x3 part: every K block is a plain [256 pixels][64] tile of A1, loaded
+  // through the kernel's second-range path): one 128 x 256 MMA per K step, weight tiles multicast across the CTA
+  // pair, and the lean epilogue (lane = channel: no staging, per-lane statistics) -- the short-K attention linears
+  // (qkv, proj_out) are bound by the staged epilogue of the generic kernel, not by the tensor cores.
+  // VDM_GEMM_LINT: 0 off, 1 heuristic (default), 2 whenever legal (tests).
+  {
+    const char* e = getenv("VDM_GEMM_LINT");
+    const int lmode = e ? atoi(e) : 1;
+    const int v = epilogue_variant(p, 128);
+    const bool stats_ok = a->stats_out == nullptr || HW % 128 == 0 || HW == 64;
+    const bool legal = lmode > 0 && is_linear && a->C2 == 0 && n_prob == 1 && a->w_group_tiles == 0 && !a->out_nchw &&
+                       a->N % 128 == 0 && ((v & ~7) == 0 || v == 64 || v == 65 || v == 68 || v == 69) && stats_ok && !xf;
+    if (legal && (lmode == 2 || (((M + 511) / 512) * (a->N / 128) >= 40 && K <= 1024))) {
+      CUtensorMap mwt;
+      uint64_t wdims[2] = {(uint64_t)K, (uint64_t)a->N};
+      uint64_t wst[2] = {2, (uint64_t)K * 2};
+      uint32_t wbox[2] = {BLOCK_K, 64};
+      rc = encode_map(&mwt, a->w, 2, wdims, wst, wbox);
+      if (rc) return rc;
+      TcParams pl = p;
+      pl.c2_chunks = pl.c2a_chunks = p.c1_chunks;     // all of K arrives as "second range" tiles of A1
+      pl.c1_chunks = 0;
+      pl.a2_f16 = 0;
+      return launch_halo_t<3, 4>(ma1, ma2, mwt, pl, stream);
+    }
+  }
   // short-K linears with several column tiles (attention qkv / proj_out): A-stationary pair kernel
   {
     const char* e = getenv("VDM_GEMM_ASTAT");
