@@ -217,38 +217,73 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t u = (uint32_t)(t >> 1) & 1u;
         mbar_wait(s_full(wg), u, 8);
         tc_fence_after();
+        // Both passes keep one TMEM load in flight while the previous chunk is consumed (two register buffers).
         // ---- pass 1: row maximum
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[32];
-          tmem_ld_32(taddr + c * 32, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          auto fold = [&](const uint32_t (&v)[32]) {
+            float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          };
+          tmem_ld_32(taddr + c_lo * 32, va);
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < c_hi) tmem_ld_32(taddr + (c + 1) * 32, vb);
+            fold(va);
+            if (c + 1 < c_hi) {
+              tmem_ld_wait();
+              if (c + 2 < c_hi) tmem_ld_32(taddr + (c + 2) * 32, va);
+              fold(vb);
+            }
+          }
         }
         const float msc = mx * scale_log2;
         // ---- pass 2: p = 2^(s * scale - max * scale), row sum, P -> TMEM as bf16 pairs (over consumed S columns)
         float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < KEYS / 32; ++c) {
-          uint32_t pk[16];
-          if (c >= c_lo && c < c_hi) {
-            uint32_t v[32];
-            tmem_ld_32(taddr + c * 32, v);
-            tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          float s0 = 0.f, s1 = 0.f;
+          auto emit = [&](const uint32_t (&v)[32], int c) {
+            uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, -msc));
               const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -msc));
-              sum += p0 + p1;
+              s0 += p0;
+              s1 += p1;
               pk[i] = pack_bf16x2(p0, p1);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            tmem_st_16(taddr + c * 16, pk);
+          };
+          tmem_ld_32(taddr + c_lo * 32, va);
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < c_hi) tmem_ld_32(taddr + (c + 1) * 32, vb);
+            emit(va, c);
+            if (c + 1 < c_hi) {
+              tmem_ld_wait();
+              if (c + 2 < c_hi) tmem_ld_32(taddr + (c + 2) * 32, va);
+              emit(vb, c + 1);
+            }
           }
-          tmem_st_16(taddr + c * 16, pk);
+          sum = s0 + s1;
+          if constexpr (L < 128) {       // keys of the other image: P = 0 (after this row's own S columns are consumed)
+            uint32_t zero[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zero[i] = 0u;
+            for (int c = 0; c < KEYS / 32; ++c)
+              if (c < c_lo || c >= c_hi) tmem_st_16(taddr + c * 16, zero);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
