@@ -113,11 +113,21 @@ typedef struct {
                            (same leading dimensions, in elements).  The residual stream of the bf16 model is kept in fp16
                            (11-bit mantissa, conversions saturate): half the HBM traffic of every stream read / write;
                            accumulation, bias / residual adds and the GroupNorm statistics stay fp32 */
+  uint32_t* img_done;   /* bf16 kernel, optional: per-image completion counters [n_img] (caller zeroes them).  Every epilogue
+                           warp adds (rows x channels it stored) once those stores AND its statistics are visible device-wide,
+                           so image n of the output -- and its GroupNorm statistics -- is complete when img_done[n] ==
+                           H*W*N.  The kernel also releases its programmatic dependents at its very top (all its CTAs are
+                           resident then), so a vdm_gn_apply launched behind it with `wait_done` runs BESIDE it on the SMs'
+                           spare registers and normalises each image as soon as the convolution has finished it, while
+                           the data is still in L2.  Only the transposed-role conv kernels take it
+                           (vdm_gemm_img_done_supported); elsewhere it is an error */
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);
 /* 1 if vdm_gemm would run `args` (with a1_coef set) on a kernel that has the fused-normalisation transform stage */
 int vdm_gemm_fused_norm_supported(const vdm_gemm_args* args);
+/* 1 if vdm_gemm would run `args` on a kernel that maintains `img_done` */
+int vdm_gemm_img_done_supported(const vdm_gemm_args* args);
 
 /* ---- GroupNorm32 (+SiLU, + scale/shift), producer of GEMM A operands --------------------
  * Replaces GroupNorm32 (nn.py:15-17) + SiLU (nn.py:10-12) + `h*(1+scale)+shift`
@@ -152,6 +162,11 @@ typedef struct {
                                          layout (A operand of the 1x1 skip projection, unet.py:172-173) */
   float* out_f32_copy;                /* optional fp32 copy of the plain output (attention residual) */
   int32_t copy_dtype;                 /* of out_f32_copy: VDM_F32 (default) | VDM_F16 */
+  const uint32_t* wait_done;          /* optional: vdm_gemm_args.img_done of the kernel launched just before on the same
+                                         stream, which produces src1 and stats1.  The launch then is a programmatic
+                                         dependent of that kernel and every block waits for wait_done[image] >= wait_count
+                                         (= H*W*C1) instead of for the whole producer grid */
+  uint32_t wait_count;
 } vdm_gn_apply_args;
 
 int vdm_gn_apply(const vdm_gn_apply_args* args, vdm_stream_t stream);

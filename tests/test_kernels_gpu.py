@@ -492,6 +492,59 @@ def test_linear_on_transposed_role_kernel(n, HW, C, N, kind, monkeypatch):
     assert relerr(outs['2'][0], ref) < 6e-3
 
 
+@pytest.mark.parametrize('n,H,W,C,N', [(160, 64, 64, 128, 128), (80, 16, 16, 384, 384), (7, 32, 32, 64, 128),
+                                       (3, 64, 64, 64, 384)])
+def test_groupnorm_apply_pipelined_behind_conv(n, H, W, C, N, monkeypatch):
+    """conv (transposed-role kernel) publishes per-image completion counters; the GroupNorm-apply launched right behind
+    it as a programmatic dependent normalises image by image while the conv still runs.  Bit-identical to the
+    serialised pair, counters end at H*W*N, repeated rounds (stale data from the previous round must never be read)."""
+    o = ops()
+    monkeypatch.setenv('VDM_GEMM_HALO', '2')
+    monkeypatch.setenv('VDM_GEMM_HALO_T', '2')
+    M = n * H * W
+    w = (rnd(N, 9 * C, seed=2) * (9 * C) ** -0.5).bfloat16()
+    bias, gam, bet = rnd(N, seed=3), rnd(N, seed=4), rnd(N, seed=5)
+    ss = rnd(n, 2 * N, seed=6) * 0.1
+    h = torch.empty(M, N, device='cuda', dtype=torch.bfloat16)
+    st = torch.zeros(n, 2, N, device='cuda', dtype=torch.int64)
+    done = torch.zeros(n, device='cuda', dtype=torch.int32)
+    conv = dict(n_img=n, H=H, W=W, taps=9, bias=bias, out_bf16=h, stats_out=st)
+    a0 = rnd(M, C, seed=1).bfloat16()
+    assert o.gemm_img_done_supported(a0, w, N, **conv)
+    for rnd_i in range(3):
+        a = (rnd(M, C, seed=10 + rnd_i)).bfloat16()
+        # serialised reference
+        st.zero_()
+        o.gemm(a, w, N, **conv)
+        ref = torch.empty(M, N, device='cuda', dtype=torch.bfloat16)
+        o.gn_apply(h, None, n, H, W, ref, stats1=st, gamma=gam, beta=bet, scale_shift=ss, silu=True)
+        st_ref = st.clone()
+        torch.cuda.synchronize()
+        # pipelined: poison the outputs, then conv + dependent apply
+        h.fill_(float('nan'))
+        st.zero_()
+        done.zero_()
+        out = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+        o.gemm(a, w, N, img_done=done, **conv)
+        o.gn_apply(h, None, n, H, W, out, stats1=st, gamma=gam, beta=bet, scale_shift=ss, silu=True, wait_done=done)
+        torch.cuda.synchronize()
+        assert torch.equal(done, torch.full_like(done, H * W * N))
+        assert torch.equal(st, st_ref)
+        assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+
+
+def test_img_done_unsupported_kernels_raise(monkeypatch):
+    o = ops()
+    a = rnd(160 * 64, 512, seed=1).bfloat16()
+    w = rnd(512, 9 * 512, seed=2).bfloat16()
+    out = torch.empty(160 * 64, 512, device='cuda', dtype=torch.bfloat16)
+    done = torch.zeros(160, device='cuda', dtype=torch.int32)
+    kw = dict(n_img=160, H=8, W=8, taps=9, out_bf16=out)
+    assert not o.gemm_img_done_supported(a, w, 512, **kw)
+    with pytest.raises(RuntimeError):
+        o.gemm(a, w, 512, img_done=done, **kw)
+
+
 def test_fused_groupnorm_unsupported_shapes_raise():
     """a1_coef on a shape / epilogue the transform-stage kernels do not cover is an error, not a silent slow path."""
     o = ops()

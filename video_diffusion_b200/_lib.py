@@ -17,7 +17,7 @@ TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOG
            POST_C2_DIV_C1=14, ACP_NEXT=15)
 TAB_COUNT = 16
 
-EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gn_stats', 'vdm_gn_stats_t', 'vdm_gn_apply', 'vdm_gn_coef',
+EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gemm_img_done_supported', 'vdm_gn_stats', 'vdm_gn_stats_t', 'vdm_gn_apply', 'vdm_gn_coef',
            'vdm_gn_temporal', 'vdm_gn_temporal_t', 'vdm_add_spatial_encoding', 'vdm_add_spatial_encoding_t', 'vdm_cond_mix', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
            'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_error', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_lincomb',
            'vdm_vb_terms', 'vdm_prior_bpd']
@@ -32,13 +32,13 @@ class GemmArgs(C.Structure):
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
                 ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp), ('n_prob', _i32),
                 ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64), ('a1_coef', _vp),
-                ('a1_act', _i32), ('a2b', _vp), ('C2b', _i32), ('a2_dtype', _i32), ('io_dtype', _i32)]
+                ('a1_act', _i32), ('a2b', _vp), ('C2b', _i32), ('a2_dtype', _i32), ('io_dtype', _i32), ('img_done', _vp)]
 
 
 class GnApplyArgs(C.Structure):
     _fields_ = [('src1', _vp), ('C1', _i32), ('src2', _vp), ('C2', _i32), ('n_img', _i32), ('H', _i32), ('W', _i32),
                 ('stats1', _vp), ('stats2', _vp), ('stats_dtype', _i32), ('stats2_dtype', _i32), ('gamma', _vp), ('beta', _vp), ('scale_shift', _vp), ('ld_ss', _i32), ('silu', _i32),
-                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('src1_dtype', _i32), ('out_raw', _vp), ('out_f32_copy', _vp), ('copy_dtype', _i32)]
+                ('out_mode', _i32), ('out_dtype', _i32), ('out', _vp), ('src1_dtype', _i32), ('out_raw', _vp), ('out_f32_copy', _vp), ('copy_dtype', _i32), ('wait_done', _vp), ('wait_count', C.c_uint32)]
 
 
 _lib = None
@@ -66,6 +66,7 @@ def load():
         'vdm_add_spatial_encoding_t': [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
         'vdm_gn_apply': [C.POINTER(GnApplyArgs), _vp],
         'vdm_gemm_fused_norm_supported': [C.POINTER(GemmArgs)],
+        'vdm_gemm_img_done_supported': [C.POINTER(GemmArgs)],
         'vdm_gn_coef': [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
         'vdm_gn_temporal': [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
         'vdm_add_spatial_encoding': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],

@@ -33,6 +33,7 @@ extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_f32 || a->out_bf16, "gemm: no output");
   VDM_REQUIRE(a->n_img > 0 && a->H > 0 && a->W > 0 && a->N > 0, "gemm: bad geometry");
   VDM_REQUIRE(a->a1_coef == nullptr || a->dtype == VDM_BF16, "gemm: a1_coef (fused normalisation) is bf16-kernel only");
+  VDM_REQUIRE(a->img_done == nullptr || a->dtype == VDM_BF16, "gemm: img_done is bf16-kernel only");
   VDM_REQUIRE(a->dtype == VDM_BF16 || (a->a2b == nullptr && a->C2b == 0 && a->a2_dtype != VDM_F16 && a->io_dtype != VDM_F16),
               "gemm: a2b / a2_dtype / io_dtype belong to the bf16 kernel");
   if (a->dtype == VDM_BF16) return vdm::gemm_tc(a, (cudaStream_t)stream);
@@ -45,5 +46,12 @@ extern "C" int vdm_gemm_fused_norm_supported(const vdm_gemm_args* a) {
   if (a == nullptr || a->dtype != VDM_BF16 || a->taps != 9 || a->a1_mode != 0 || a->out_nchw) return 0;
   int ok = 0;
   if (vdm::gemm_tc(a, nullptr, &ok) != 0) return 0;
-  return ok;
+  return ok & 1;
+}
+
+extern "C" int vdm_gemm_img_done_supported(const vdm_gemm_args* a) {
+  if (a == nullptr || a->dtype != VDM_BF16 || a->taps != 9 || a->a1_mode != 0 || a->out_nchw || a->a1_coef) return 0;
+  int ok = 0;
+  if (vdm::gemm_tc(a, nullptr, &ok) != 0) return 0;
+  return (ok >> 1) & 1;
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                               int heads, int n_items, float scale_log2) {
   using Cfg = AttnCfg<HD, L>;
   constexpr int KEYS = Cfg::KEYS, TPK = Cfg::TPK, ATOMS = Cfg::ATOMS;
-  pdl_launch_dependents();
+  pdl_launch_dependents_persistent();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_2d(smem_base + Cfg::V_OFF + a * Cfg::KV_ATOM_BYTES + kb * Cfg::BOX_BYTES, &tm_qkv, v_full,
                         2 * C + h * HD + a * 64, row0 + kb * 128);
       }
+      pdl_trigger_late();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================

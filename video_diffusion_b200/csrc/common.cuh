@@ -67,13 +67,17 @@ inline int num_sms() {
 // its writes are visible.  Nothing global is written before the wait, so there is no write-after-read hazard either.
 // Captured into a CUDA graph the attribute becomes a programmatic edge between the two kernel nodes.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #ifdef VDM_PDL_LATE
-// late-trigger protocol: the trigger at the top of a kernel is dropped, the persistent GEMMs release their dependents
-// once a CTA's TMA producer has issued its last load (pdl_trigger_late), every other kernel at its exit
-__device__ __forceinline__ void pdl_launch_dependents() {}
+// Mixed protocol (build with -DVDM_PDL_LATE): the short-block kernels trigger at their top as before -- their
+// dependent, usually a persistent GEMM, then brings up its CTAs (barriers, TMEM, descriptor fetch) as the last wave of
+// blocks drains -- but a persistent GEMM, whose CTAs are all resident from the first cycle, triggers only when a CTA's
+// TMA producer has issued its last load: triggered at the top, its dependents' blocks would sit on every SM for the
+// whole kernel and keep the other micro-batch's kernels from running beside it.
+__device__ __forceinline__ void pdl_launch_dependents_persistent() {}
 __device__ __forceinline__ void pdl_trigger_late() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #else
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents_persistent() { pdl_launch_dependents(); }
 __device__ __forceinline__ void pdl_trigger_late() {}
 #endif
 
@@ -88,8 +92,8 @@ inline bool pdl_enabled() {
 
 // cluster_x > 1: thread-block cluster of that many CTAs along x.  Launch errors are picked up by VDM_AFTER_LAUNCH.
 template <typename... KArgs, typename... Args>
-inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                          int cluster_x, Args&&... args) {
+inline void launch_kernel_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, bool programmatic, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -104,7 +108,7 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (programmatic) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -112,6 +116,11 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   cfg.attrs = attr;
   cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          int cluster_x, Args&&... args) {
+  launch_kernel_ex(kernel, grid, block, smem, stream, cluster_x, pdl_enabled(), std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

@@ -2,13 +2,17 @@
 // +scale-shift, + concat, + x2 upsample, + stride-2 parity split), temporal GroupNorm,
 // conditioning mix + input-conv im2col, timestep sinusoid, RPE-net hidden layer.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
 
 #ifndef GN_MIN_BLOCKS
-#define GN_MIN_BLOCKS 1
+#define GN_MIN_BLOCKS 7      // 128-thread blocks of <= 72 registers: three of them fit beside a persistent GEMM CTA
+#endif
+#ifndef GN_THREADS
+#define GN_THREADS 128      // default / maximum block size of gn_apply (profiles: co-residency experiments)
 #endif
 
 namespace vdm {
@@ -80,6 +84,8 @@ struct ApplyParams {
   void* out; void* out_raw; void* copy;
   int copy_f16;
   int pix_per_block;
+  const unsigned int* wait_done;   // per-image completion counters of the producer of s1 / st1 (vdm_gn_apply_args.wait_done)
+  unsigned int wait_count;
 };
 
 // grid (pixel chunks, n_img); block = (C/8) x rows threads: a thread owns 8 channels for a strided set
@@ -89,9 +95,10 @@ struct ApplyParams {
 // InT: float, __half (fp16 residual stream; two-source concat allowed like float) or __nv_bfloat16 (conv output kept in
 // bf16, single source).
 template <typename OutT, typename InT, int MODE, bool RAW, bool COPY>
-__global__ void __launch_bounds__(256, GN_MIN_BLOCKS) gn_apply_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(GN_THREADS, GN_MIN_BLOCKS) gn_apply_kernel(const ApplyParams p) {
   pdl_launch_dependents();
-  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  // polled mode (wait_done): this grid runs BESIDE its producer and waits per image, below, instead of for the whole grid
+  if (p.wait_done == nullptr) pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int C = p.C1 + p.C2, cpg = C / 32, HW = p.H * p.W, C8 = C / 8;
   double* chs = reinterpret_cast<double*>(sm_raw);
@@ -123,6 +130,25 @@ __global__ void __launch_bounds__(256, GN_MIN_BLOCKS) gn_apply_kernel(const Appl
   if (p.st1 != nullptr) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { gam[i] = __ldg(p.gamma + c + i); bet[i] = __ldg(p.beta + c + i); }
+  }
+  if (p.wait_done != nullptr) {
+    // the producer (a conv kernel whose CTAs are all resident) publishes image n with release atomics once its rows
+    // and statistics are globally visible; it can only make progress, so this wait is bounded
+    if (threadIdx.x == 0) {
+      const unsigned int* flag = p.wait_done + n;
+      const long long t0 = clock64();
+      for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= p.wait_count) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) {     // ~2 s: a protocol bug must fail loudly, never hang the box
+          printf("vdm gn_apply: image %d never completed (%u of %u)\n", n, v, p.wait_count);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
   }
   if (p.st1 != nullptr) {
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
@@ -759,11 +785,13 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_mode == 0 || a->out_f32_copy == nullptr, "gn_apply: fp32 copy only with plain output");
   ApplyParams p{a->src1, a->C1, a->src2, a->C2, a->n_img, a->H, a->W, a->stats1, a->stats2,
                 a->stats_dtype, a->stats2_dtype, a->gamma, a->beta, a->scale_shift, a->ld_ss, a->silu, a->out_mode,
-                a->out, a->out_raw, a->out_f32_copy, a->copy_dtype == VDM_F16 ? 1 : 0, 0};
+                a->out, a->out_raw, a->out_f32_copy, a->copy_dtype == VDM_F16 ? 1 : 0, 0, a->wait_done, a->wait_count};
+  VDM_REQUIRE(a->wait_done == nullptr || (a->stats1 != nullptr && a->C2 == 0),
+              "gn_apply: wait_done takes a single normalised source");
   const int HW = a->H * a->W;
   const int C8 = C / 8;
-  int tpb = 256;                       // VDM_GN_THREADS: block size (profiles/overlap_probe.py)
-  if (const char* e = getenv("VDM_GN_THREADS")) tpb = std::max(32, atoi(e));
+  int tpb = GN_THREADS;                // VDM_GN_THREADS: block size (profiles/overlap_probe.py)
+  if (const char* e = getenv("VDM_GN_THREADS")) tpb = std::min(GN_THREADS, std::max(32, atoi(e)));
   const int rows = C8 >= tpb ? 1 : tpb / C8;
   const int threads = C8 * rows;
   int ppb = rows * 32;
@@ -778,7 +806,8 @@ extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->out_mode == 0 || (!raw && !copy), "gn_apply: extra outputs only with the plain layout");
   VDM_REQUIRE(!(raw && copy), "gn_apply: out_raw and out_f32_copy are mutually exclusive");
 #define VDM_GN_LAUNCH(OUT, IN, MODE, RAW, COPY) \
-  launch_kernel(gn_apply_kernel<OUT, IN, MODE, RAW, COPY>, grid, threads, smem, (cudaStream_t)(cudaStream_t)stream, 1, p)
+  launch_kernel_ex(gn_apply_kernel<OUT, IN, MODE, RAW, COPY>, grid, threads, smem, (cudaStream_t)stream, 1, \
+                   pdl_enabled() || a->wait_done != nullptr, p)
 #define VDM_GN_BY_MODE(OUT, IN)                                              \
   do {                                                                       \
     if (a->out_mode == 1) VDM_GN_LAUNCH(OUT, IN, 1, false, false);           \

@@ -80,6 +80,7 @@ struct TcParams {
   int stats_via_smem;          // fold the GroupNorm partial sums of a tile in shared memory
   int dbg;                     // diagnostics (VDM_GEMM_DEBUG): bit 0 skip the TMA loads, bit 1 skip the MMAs (results are garbage)
   unsigned long long* trace;   // diagnostics (vdm_gemm_set_trace): per-CTA wait / busy cycle counters, else NULL
+  unsigned int* img_done;      // per-image completion counters (vdm_gemm_args.img_done), transposed-role kernels only
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tm_w,
                                                                  const __grid_constant__ CUtensorMap tm_out,
                                                                  const TcParams p) {
-  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
+  pdl_launch_dependents_persistent();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   constexpr bool TS = (EPI & 32) != 0;
   static_assert(!TS || M_SUB == 1, "TMA-store epilogue: one 128-row sub-tile per CTA");
   using L = SmemLayout<BLOCK_N, M_SUB, STAGES, CTA2, TS ? ((EPI & 2) ? 2 : 4) : 0>;
@@ -1152,7 +1153,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tm_w,
                                                                        const __grid_constant__ CUtensorMap tm_out,
                                                                        const TcParams p, const int tiles_per_worker) {
-  pdl_launch_dependents();
+  pdl_launch_dependents_persistent();
   constexpr bool TS = (EPI & 32) != 0;
   using L = AStatLayout<BLOCK_N, KB_MAX, SB, TS ? ((EPI & 2) ? 2 : 4) : 0>;
   constexpr int TILE_M = 2 * BLOCK_M;
@@ -1328,7 +1329,7 @@ template <int BLOCK_N, int M_SUB, int SA, int SB, int EPI, bool ILV = false, boo
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
     gemm_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ A2Maps tm_a2,
                         const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
-  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
+  pdl_launch_dependents_persistent();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = HaloLayout<BLOCK_N, M_SUB, SA, SB, ILV>;
   static_assert(!ILV || M_SUB == 1, "interleaved 8x8 tiles are 128 rows");
   constexpr int CTA_ROWS = BLOCK_M * M_SUB;
@@ -1607,7 +1608,7 @@ template <int SA, int SB, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_upfold_halo_kernel(const __grid_constant__ CUtensorMap tm_halo,
                                                                              const __grid_constant__ CUtensorMap tm_w,
                                                                              const TcParams p) {
-  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
+  pdl_launch_dependents_persistent();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
   using L = UpfoldHaloLayout<SA, SB>;
   constexpr int BLOCK_N = L::BLOCK_N, CTA_ROWS = BLOCK_M, TILE_M = 2 * CTA_ROWS;
   const uint32_t cta_rank = cluster_ctarank();
@@ -1786,7 +1787,10 @@ template <int SA, int SB, int EPI, bool WIDE = false, bool XF = false>
 __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
     gemm_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tm_halo, const __grid_constant__ A2Maps tm_a2,
                           const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
-  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
+  pdl_launch_dependents_persistent();   // the next kernel's prologue may overlap this kernel's tail (common.cuh)
+  // image-pipelined GroupNorm-apply: the dependent polls img_done, so it must be released now, while this grid's CTAs
+  // are all resident and can only make progress (vdm_gemm_args.img_done)
+  if (p.img_done != nullptr) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   using L = HaloTLayout<SA, SB, WIDE>;
   constexpr int PIX = L::PIX, TILE_M = 2 * PIX;
   constexpr bool HAS_RES = (EPI & 1) != 0, BF16_OUT = (EPI & 2) != 0, STATS = (EPI & 4) != 0;
@@ -2045,6 +2049,12 @@ __global__ void __launch_bounds__(XF ? NUM_THREADS_XF : NUM_THREADS, 1)
           atomicAdd(tab, (unsigned long long)__float2ll_rn(rsum * 16777216.0f));
           atomicAdd(tab + p.N, (unsigned long long)__float2ll_rn(rsq * 16777216.0f));
         }
+      }
+      if (p.img_done != nullptr && row0 < p.M) {
+        // this warp's 128 rows x 32 channels (one image: H*W % 128 == 0 here) and their statistics are out: publish
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.img_done + row0 / p.HW, (unsigned int)(min(128, p.M - row0) * 32));
       }
     }
   } else if constexpr (XF) {
@@ -2308,13 +2318,18 @@ int launch_halo_inst(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorMap
   cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {     // programmatic dependent launch (common.cuh)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_kernel<BLOCK_N, M_SUB, SA, SB, EPI, ILV, XF>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (halo): launch failed: %s", cudaGetErrorString(e));
@@ -2403,13 +2418,18 @@ int launch_upfold_halo_inst(const CUtensorMap& mh, const CUtensorMap& mw, const 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {     // programmatic dependent launch (common.cuh)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_upfold_halo_kernel<SA, SB, EPI>, mh, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (upfold halo): launch failed: %s", cudaGetErrorString(e));
@@ -2459,13 +2479,18 @@ int launch_halo_t_inst(const CUtensorMap& mh, const A2Maps& ma2, const CUtensorM
   cfg.blockDim = dim3(XF ? NUM_THREADS_XF : NUM_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {     // programmatic dependent launch (common.cuh)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_halo_t_kernel<SA, SB, EPI, WIDE, XF>, mh, ma2, mw, p);
   if (e != cudaSuccess) {
     set_error("gemm_tc (transposed halo): launch failed: %s", cudaGetErrorString(e));
@@ -2525,6 +2550,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   const bool xf = a->a1_coef != nullptr;
   VDM_REQUIRE(!xf || (a->taps == 9 && a->a1_mode == 0 && !a->out_nchw),
               "gemm_tc: fused normalisation (a1_coef) takes 3x3 stride-1 convolutions only");
+  VDM_REQUIRE(a->img_done == nullptr || (a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && !xf),
+              "gemm_tc: img_done is maintained by the transposed-role 3x3 conv kernels only");
   if (a->a1_mode == 3) return probe ? 0 : gemm_tc_upfold(a, stream);
   if (!probe && a->out_nchw && a->N <= 8 && !getenv("VDM_NO_SMALL_N")) {
     const int rc = conv3x3_small_n(a, stream);
@@ -2582,6 +2609,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     p.par_out_stride = a->prob_out_stride;
   }
   p.trace = g_trace_buf;
+  p.img_done = a->img_done;
   if (const char* e = getenv("VDM_GEMM_DEBUG")) p.dbg = atoi(e);
   VDM_REQUIRE(a->w_group_tiles == 0 || (is_linear && a->C2 == 0 && !a->out_nchw), "gemm_tc: grouped weights need taps == 1");
   VDM_REQUIRE(a->lda1 == 0 || (is_linear && a->lda1 >= a->C1 && a->lda1 % 8 == 0), "gemm_tc: bad lda1");
@@ -2603,8 +2631,19 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
     const bool okw = base && a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 &&
                      (hmode == 2 || ((M + 511) / 512) * (a->N / 128) >= 40);
-    (void)tmode;   // the transposed kernel is only ever chosen where the pair kernel is legal too
-    *probe = (ok8 || ok || okw) ? 1 : 0;
+    // bit 1: the call runs on a transposed-role kernel (which maintains img_done); mirrors the dispatch below
+    const bool lean = (epilogue_variant(p, 128) & 8) == 0;
+    const bool base_t = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 && lean;
+    const bool geo = bn != 0 && a->W >= 8 && a->W <= 64 && rows % a->W == 0 && HW % rows == 0 &&
+                     (hmode == 2 || ((M + 2 * rows - 1) / (2 * rows)) * (a->N / bn) >= 40);
+    const bool sel8 = hmode > 0 && a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && a->w_group_tiles == 0 && a->W == 8 &&
+                      a->H == 8 && a->N % 256 == 0 && (epilogue_variant(p, 256) & 8) == 0 &&
+                      (hmode == 2 || ((M + 255) / 256) * (a->N / 256) >= 40);
+    const bool sel_wide_t = base_t && a->N % 128 == 0 && a->W == 128 && HW % 256 == 0 &&
+                            (hmode == 2 || ((M + 511) / 512) * (a->N / 128) >= 40);
+    const bool sel_halo_t = base_t && geo && a->N % 128 == 0 && (a->N % 256 != 0 || tmode == 2) && tmode > 0 &&
+                            256 % a->W == 0 && HW % 256 == 0;
+    *probe = ((ok8 || ok || okw) ? 1 : 0) | ((!sel8 && !xf && (sel_wide_t || sel_halo_t)) ? 2 : 0);
     return 0;
   }
   if (is_linear) {
@@ -2656,6 +2695,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
                      a->W == 8 && a->H == 8 && a->N % 256 == 0 && (epilogue_variant(p, 256) & 8) == 0 &&
                      (hmode == 2 || ((M + 255) / 256) * (a->N / 256) >= 40);
     if (ok8) {
+      VDM_REQUIRE(a->img_done == nullptr, "gemm_tc: img_done is maintained by the transposed-role conv kernels only");
       CUtensorMap mh, mw2;
       const uint64_t C = a->C1;
       // dims (C, x, image, y): the image dimension sits between x and y, so the box lands (y, image, x)-ordered
@@ -2725,6 +2765,8 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
       if (rc) return rc;
       return launch_halo_t<3, 4>(mh, ma2, mwt, p, stream);
     }
+    VDM_REQUIRE(a->img_done == nullptr, "gemm_tc: img_done is maintained by the transposed-role conv kernels only "
+                                        "(check vdm_gemm_img_done_supported first)");
     if (ok) {
       CUtensorMap mh, mw2;
       const uint64_t C = a->C1;

@@ -33,7 +33,7 @@ def _nbytes(*tensors):
 def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, rowbias=None, residual=None,
                out_f32=None, out_bf16=None, out_nchw=False, out_silu=None, C1=None, C2=0, stats_out=None,
                w_group_tiles=0, n_prob=1, prob_a_cols=0, prob_w_rows=0, prob_out_stride=0, a1_coef=None, a1_act=False,
-               a2b=None):
+               a2b=None, img_done=None):
     g = GemmArgs()
     g.dtype = dt(a1.dtype)
     g.taps, g.a1_mode = taps, a1_mode
@@ -68,12 +68,19 @@ def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, ro
     g.out_silu_f32 = ptr(out_silu)
     g.stats_out = ptr(stats_out)
     g.a1_coef, g.a1_act = ptr(a1_coef, torch.float32), int(a1_act)
+    g.img_done = None if img_done is None else _counter_ptr(img_done, n_img)
     # `out_f32` / `residual` are the model's residual stream: fp32, or fp16 in the bf16 model (io_dtype)
     io = {t.dtype for t in (out_f32, residual) if t is not None}
     if len(io) > 1 or not io <= {torch.float32, torch.float16}:
         raise TypeError(f'vdm_gemm: out_f32 / residual must both be fp32 or both fp16, got {io}')
     g.io_dtype = dt(io.pop()) if io else F32
     return g
+
+
+def _counter_ptr(t, n_img):
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and t.numel() >= n_img):
+        raise TypeError('per-image completion counters: a contiguous int32 CUDA tensor of n_img entries')
+    return t.data_ptr()
 
 
 def gemm(a1, w, N, **kw):
@@ -97,6 +104,12 @@ def gemm_fused_norm_supported(a1, w, N, **kw):
     return bool(_lib.load().vdm_gemm_fused_norm_supported(C.byref(g)))
 
 
+def gemm_img_done_supported(a1, w, N, **kw):
+    """Would this call run on a kernel that maintains per-image completion counters (`img_done`)?  No launch."""
+    g = _gemm_args(a1, w, N, **kw)
+    return bool(_lib.load().vdm_gemm_img_done_supported(C.byref(g)))
+
+
 def gn_coef(stats1, stats2, n_img, HW, gamma, beta, coef, scale_shift=None):
     """Per-(image, channel) (a, b) of GroupNorm32 (+ scale/shift) into coef [n_img][C1+C2][2] (see vdm.h: vdm_gn_coef)."""
     kind = lambda s: _lib.F64 if (s is not None and s.dtype == torch.float64) else _lib.I64
@@ -117,7 +130,7 @@ def gn_stats(src, n_img, HW, stats):
 
 
 def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=None, beta=None, scale_shift=None,
-             silu=False, out_mode=0, copy=None, out_raw=None):
+             silu=False, out_mode=0, copy=None, out_raw=None, wait_done=None):
     lib = _lib.load()
     a = GnApplyArgs()
     a.src1, a.C1 = ptr(src1), src1.shape[-1]
@@ -133,6 +146,8 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
     a.out, a.out_raw, a.out_f32_copy = ptr(out), ptr(out_raw), ptr(copy)
     a.src1_dtype = dt(src1.dtype)
     a.copy_dtype = F32 if copy is None else dt(copy.dtype)
+    if wait_done is not None:       # launched right behind the conv that produces src1: normalise image by image
+        a.wait_done, a.wait_count = _counter_ptr(wait_done, n_img), H * W * a.C1
     if src2 is not None and src2.dtype != src1.dtype:
         raise TypeError('vdm_gn_apply: the two sources of a concat must share a dtype')
     _timed('gn_apply', lambda: check(lib.vdm_gn_apply(C.byref(a), stream()), 'vdm_gn_apply'),

@@ -85,6 +85,7 @@ class UNetModel(nn.Module):
         self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
+        self.pipeline_norm = os.environ.get('VDM_PIPELINE_NORM', '1') != '0'     # out_layers GroupNorm-apply beside conv1
         # proj_out's residual as an identity K range (like conv2 at 64x64): measured SLOWER (0.84 vs 0.71 ms for the 22
         # launches; these short-K linears are bound by operand delivery, not by the epilogue): off
         self.proj_identity = os.environ.get('VDM_PROJ_IDENTITY', '0') != '0'
@@ -405,6 +406,19 @@ class UNetModel(nn.Module):
                 self.stat_bufs[name] = b
             return b
 
+        def counters(self, name, n_img):
+            """Per-image completion counters (int32 [n_img]) of a conv whose GroupNorm-apply runs beside it; they live in
+            the statistics pool, so the memset at the start of a forward clears them too."""
+            b = self.stat_bufs.get(name)
+            if b is None:
+                n = (n_img + 1) // 2
+                if self.pool_used + n > self.pool.numel():
+                    raise RuntimeError('internal: GroupNorm statistics pool too small')
+                b = self.pool[self.pool_used:self.pool_used + n].view(torch.int32)[:n_img]
+                self.pool_used += n
+                self.stat_bufs[name] = b
+            return b
+
         def zero_stats(self):
             if self.pool_used:
                 self.pool[:self.pool_used].zero_()
@@ -454,12 +468,26 @@ class UNetModel(nn.Module):
         if rb is not None and ws.emb_join is not None:
             torch.cuda.current_stream().wait_event(ws.emb_join)
             ws.emb_join = None
+        h1_done = None
         if st_h1 is not None and self.bf16_intermediate:
             # conv1's output is only ever consumed by GroupNorm -> SiLU -> bf16: keep it in bf16 (its
             # statistics come from the fp32 accumulators in the epilogue), halving its HBM traffic
             h1 = ws.buf(p + '.h1b', (M, Cout), torch.bfloat16)
-            ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb,
-                     out_bf16=h1, stats_out=st_h1)
+            conv1 = dict(n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb, out_bf16=h1, stats_out=st_h1)
+            # Image-pipelined out_layers: where conv1 runs on a kernel that publishes per-image completion counters,
+            # the GroupNorm-apply below is launched as its programmatic dependent and normalises image n as soon as
+            # conv1 has finished it -- beside conv1 on the SMs' spare registers, reading the image from L2.
+            pipe = ws.flags.get(p + '.pipe1')
+            if pipe is None:
+                pipe = ws.flags[p + '.pipe1'] = bool(self.pipeline_norm and ops.PROFILE is None and
+                                                     ops.gemm_img_done_supported(a1, P[p + '.w1'], Cout, **conv1))
+            if pipe:
+                h1_done = ws.counters(p + '.h1.done', n_img)
+                conv1['img_done'] = h1_done
+                if ws.emb_join is not None:      # the side branch joins ahead of conv1: nothing between it and its dependent
+                    torch.cuda.current_stream().wait_event(ws.emb_join)
+                    ws.emb_join = None
+            ops.gemm(a1, P[p + '.w1'], Cout, **conv1)
         else:
             h1 = ws.buf(p + '.h1', (M, Cout))
             ops.gemm(a1, P[p + '.w1'], Cout, n_img=n_img, H=H, W=W, taps=9, bias=P[p + '.b1'], rowbias=rb,
@@ -492,7 +520,7 @@ class UNetModel(nn.Module):
         else:
             a2 = ws.buf(p + '.a2', (M, Cout), adt)
             ops.gn_apply(h1, None, n_img, H, W, a2, stats1=st_h1, gamma=P[p + '.gn2_w'], beta=P[p + '.gn2_b'],
-                         scale_shift=scale_shift, silu=True)
+                         scale_shift=scale_shift, silu=True, wait_done=h1_done)
             ops.gemm(a2, w2, Cout, **conv2)
         return out, st_out
 
@@ -892,7 +920,8 @@ class UNetModel(nn.Module):
         B, F, Cc, H, W = x.shape
         if Cc != 3:
             raise NotImplementedError('3-channel frames only')
-        key = (B, F, H, W, str(x.device), per_frame_t is not None, self._sdt, self.micro_batches, self.fuse_norm)
+        key = (B, F, H, W, str(x.device), per_frame_t is not None, self._sdt, self.micro_batches, self.fuse_norm,
+               self.pipeline_norm)
         ws = self._workspaces.get(key)
         if ws is None:
             chans = sum((n['cin'] + 3 * n['cout']) if n['kind'] == 'res' else 3 * n.get('C', self.model_channels)
