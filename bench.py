@@ -76,7 +76,7 @@ def shared_config(world):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit')
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -84,7 +84,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -108,8 +108,13 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
         busy = [v for v in sm if v > 0.5 * sm[-1]] or sm
-        return dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=int(self.rows[0][1]), reasons=reasons,
-                    samples=len(sm))
+        out = dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=int(self.rows[0][1]), reasons=reasons, samples=len(sm))
+        try:        # board power under load against the enforced limit: the step runs into the power cap
+            pw = sorted(float(r[6]) for r in self.rows if len(r) > 7 and int(r[0]) > 0.5 * sm[-1])
+            out['power_w'], out['power_limit_w'] = pw[len(pw) // 2], float(self.rows[0][7])
+        except Exception:
+            pass
+        return out
 
 
 def synth_state(cfg_name):

@@ -467,23 +467,18 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
   const int c = active ? g * cpg + (lane % l4) * 4 : 0;
   const size_t frame_stride = (size_t)HW * C;
   const size_t off0 = (size_t)b * T * frame_stride + (size_t)pix * C + c;
-  float4 v[TMAX];          // TMAX >= T: the frame loop is fully unrolled, every load is in flight before the first use
-  float s = 0.f;
+  // TMAX >= T: the frame loops are fully unrolled, every load is in flight before the first use.  fp16 input stays
+  // PACKED in registers (two per frame instead of four) and is unpacked in each of the three passes -- the
+  // conversions are exact and cheap, and the halved register count doubles the warps (= bytes in flight) per SM,
+  // which is what bounds this latency-limited kernel.
+  constexpr bool PACKED = sizeof(IoT) == 2;
+  float4 v[PACKED ? 1 : TMAX];
+  uint2 raw[PACKED ? TMAX : 1];
   const IoT* src = x + off0;
-  if constexpr (sizeof(IoT) == 2) {
-    // raw bits first, conversions afterwards: a conversion right behind each load would stall the in-order warp on
-    // that load before the next one is issued
-    uint2 raw[TMAX];
+  if constexpr (PACKED) {
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
       if (t < T && active) raw[t] = __ldg(reinterpret_cast<const uint2*>(src + t * frame_stride));
-    }
-#pragma unroll
-    for (int t = 0; t < TMAX; ++t) {
-      if (t < T && active) {
-        const float2 lo = unpack_f16x2(raw[t].x), hi = unpack_f16x2(raw[t].y);
-        v[t] = make_float4(lo.x, lo.y, hi.x, hi.y);
-      }
     }
   } else {
 #pragma unroll
@@ -491,9 +486,21 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
       if (t < T && active) v[t] = load4(src + t * frame_stride);
     }
   }
+  auto val = [&](int t) -> float4 {
+    if constexpr (PACKED) {
+      const float2 lo = unpack_f16x2(raw[t].x), hi = unpack_f16x2(raw[t].y);
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      return v[t];
+    }
+  };
+  float s = 0.f;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
-    if (t < T && active) s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+    if (t < T && active) {
+      const float4 u = val(t);
+      s += (u.x + u.y) + (u.z + u.w);
+    }
   }
   const int base = lane - lane % l4;
   float gs = 0.f;
@@ -506,7 +513,8 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
     if (t < T && active) {
-      const float dx = v[t].x - mean, dy = v[t].y - mean, dz = v[t].z - mean, dw = v[t].w - mean;
+      const float4 u = val(t);
+      const float dx = u.x - mean, dy = u.y - mean, dz = u.z - mean, dw = u.w - mean;
       q = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, q))));
     }
   }
@@ -521,8 +529,9 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
   for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
       const size_t off = off0 + t * frame_stride;
-      const float y0 = fmaf(v[t].x - mean, a0, b0), y1 = fmaf(v[t].y - mean, a1, b1);
-      const float y2 = fmaf(v[t].z - mean, a2, b2), y3 = fmaf(v[t].w - mean, a3, b3);
+      const float4 u = val(t);
+      const float y0 = fmaf(u.x - mean, a0, b0), y1 = fmaf(u.y - mean, a1, b1);
+      const float y2 = fmaf(u.z - mean, a2, b2), y3 = fmaf(u.w - mean, a3, b3);
       if (out_f32) store4(out_f32 + off, make_float4(y0, y1, y2, y3));
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;

@@ -85,7 +85,7 @@ class UNetModel(nn.Module):
         self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
-        self.pipeline_norm = os.environ.get('VDM_PIPELINE_NORM', '1') != '0'     # out_layers GroupNorm-apply beside conv1
+        self.pipeline_norm = os.environ.get('VDM_PIPELINE_NORM', '0') != '0'     # out_layers GroupNorm-apply beside conv1
         # proj_out's residual as an identity K range (like conv2 at 64x64): measured SLOWER (0.84 vs 0.71 ms for the 22
         # launches; these short-K linears are bound by operand delivery, not by the epilogue): off
         self.proj_identity = os.environ.get('VDM_PROJ_IDENTITY', '0') != '0'
