@@ -85,6 +85,7 @@ class UNetModel(nn.Module):
         self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
+        self.identity_res_min_hw = int(os.environ.get('VDM_IDENTITY_RES_MIN_HW', '4096'))   # x + h as an identity K range from this H*W on
         self.pipeline_norm = os.environ.get('VDM_PIPELINE_NORM', '0') != '0'     # out_layers GroupNorm-apply beside conv1
         # proj_out's residual as an identity K range (like conv2 at 64x64): measured SLOWER (0.84 vs 0.71 ms for the 22
         # launches; these short-K linears are bound by operand delivery, not by the epilogue): off
@@ -456,7 +457,7 @@ class UNetModel(nn.Module):
         # MMAs against fp16 weight columns): the 1x1 skip projection needs no bf16 copy of x, and on the 64x64 level
         # -- where the epilogue's residual read costs more than one extra K block -- `x + h` becomes an identity
         # projection as well.  Otherwise (fp32 stream, fp32 mode) gn_apply writes the raw cast next to the operand.
-        stream_a2 = adt == torch.bfloat16 and self._sdt == torch.float16 and (node['skip'] or HW >= 4096)
+        stream_a2 = adt == torch.bfloat16 and self._sdt == torch.float16 and (node['skip'] or HW >= self.identity_res_min_hw)
         araw = ws.buf(p + '.araw', (M, Cin), adt) if (node['skip'] and not stream_a2) else None
         # one pass over the block input: normalised+SiLU operand of conv1 (and the raw cast for the 1x1 skip, if needed)
         ops.gn_apply(src1, src2, n_img, H, W, a1, stats1=st1, stats2=st2, gamma=P[p + '.gn1_w'], beta=P[p + '.gn1_b'],
