@@ -178,6 +178,10 @@ CHAIN_CASE = dict(cfg='tiny', image_size=32, respacing='ddim10', bpd_respacing='
                   bpd_obs=[[0, 1, 2], [3, 7, 9, 11, 12, 13]], bpd_lat=[[10, 11, 12, 13, 14], [20, 21, 22, 23]])
 
 
+# scripts/video_sample_full.py schedule on the CHAIN_CASE video: 4 vertical timesteps, then 6 horizontal sweeps
+FULL_SCHEDULE_CASE = dict(vertical_steps=4, noise_seed=8000)
+
+
 def bpd_case_inputs(c):
     """run_bpd_evaluation's packing (scripts/video_nll.py:149-164) for ragged index lists."""
     obs_l, lat_l = c['bpd_obs'], c['bpd_lat']

@@ -221,6 +221,52 @@ def dump_chain():
     np.savez_compressed(os.path.join(GOLD, 'chain.npz'), **arrays)
 
 
+def dump_full_schedule():
+    """scripts/video_sample_full.py:50-323 (vertical, then horizontal diffusion) on the CHAIN_CASE video with the
+    reference's model and p_sample, replayed noise; the script itself reads `args` / `logger` globals, so its loop is
+    followed statement by statement here (observed_frames='x_0', non-adaptive mode)."""
+    from oracle.cases import FULL_SCHEDULE_CASE
+    c, f = CHAIN_CASE, FULL_SCHEDULE_CASE
+    model, diffusion = load_ref_model(c['cfg'], c['respacing'])
+    B, T = c['batch'], c['video_length']
+    video = synth.make_video((B, T, 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    samples = torch.zeros_like(video)
+    samples[:, :c['obs_length']] = video[:, :c['obs_length']]
+
+    def windows():
+        return inference_util.inference_strategies[c['mode']](video_length=T, num_obs=c['obs_length'],
+                                                              max_frames=c['max_frames'], step_size=c['step_size'])
+
+    def kwargs(x0, obs, lat):
+        fi = torch.tensor(list(obs) + list(lat)).repeat((B, 1))
+        om = torch.zeros_like(x0[:, :, :1, :1, :1])
+        om[:, :len(obs)] = 1
+        return dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+                    x_t_minus_1=x0, observed_frames='x_0')
+
+    steps = list(range(diffusion.num_timesteps))[::-1]
+    gd.th.randn_like = NoiseReplay(f['noise_seed'])
+    with torch.no_grad():
+        for obs, lat in windows():                                           # vertical diffusion (:88-203)
+            x0 = torch.cat([samples[:, obs], samples[:, lat]], dim=1).clone()
+            cur = x0.clone()
+            for step in steps[:f['vertical_steps']]:
+                cur = diffusion.p_sample(model, cur, t=torch.tensor([step] * B), clip_denoised=True,
+                                         model_kwargs=kwargs(x0, obs, lat))['sample']
+            samples[:, lat] = cur[:, -len(lat):]
+        vertical = samples.clone()
+        for step in steps[f['vertical_steps']:]:                             # horizontal diffusion (:205-313)
+            for obs, lat in windows():
+                x0 = torch.cat([samples[:, obs], samples[:, lat]], dim=1).clone()
+                cur = diffusion.p_sample(model, x0, t=torch.tensor([step] * B), clip_denoised=True,
+                                         model_kwargs=kwargs(x0, obs, lat))['sample']
+                samples[:, lat] = cur[:, -len(lat):]
+    gd.th.randn_like = torch.randn_like
+    np.savez_compressed(os.path.join(GOLD, 'chain_full.npz'), **{'full/vertical': vertical.numpy(),
+                                                                 'full/samples': samples.numpy()})
+    print('full schedule', float(samples.abs().max()), float(samples.std()))
+
+
 def dump_probe():
     """calc_bpd_loop_subsampled with a 2-D t_seq, one row of timesteps per video (gaussian_diffusion.py:960-969),
     the way scripts/video_optimal_schedule.py:97-105 calls it; stand-in network, replayed noise."""
@@ -427,6 +473,9 @@ if __name__ == '__main__':
         dump_uncond()
         dump_ddim50()
         dump_diffusion_extra()
+        sys.exit(0)
+    if sys.argv[1:] == ['full_schedule']:
+        dump_full_schedule()
         sys.exit(0)
     if sys.argv[1:] == ['attn']:
         dump_attn()

@@ -3,7 +3,8 @@
 Restates `infer_video` (scripts/video_sample.py:50-190: window assembly, chain started
 from x0.clone() -- SURVEY Q5 --, ancestral p_sample per step, write-back of the latent
 frames) and `run_bpd_evaluation` (scripts/video_nll.py:142-188) on top of the oracle
-U-Net and the oracle sampler maths.  Pinned by tests/golden/chain.npz.
+U-Net and the oracle sampler maths, plus the vertical / horizontal schedule of
+scripts/video_sample_full.py:50-323.  Pinned by tests/golden/chain.npz and chain_full.npz.
 """
 import torch
 
@@ -26,6 +27,35 @@ def infer_video(sd, cfg, sched, video, mode, max_frames, obs_length, step_size, 
             eps = U.cond_marg_forward(sd, cfg, cur, x0, om, lm, km, sched.model_time(t), fi)
             cur = D.p_sample(sched, eps, cur, t, noise_fn(tuple(cur.shape)))['sample']
         samples[:, lat] = cur[:, -len(lat):]
+    return samples
+
+
+def infer_video_full(sd, cfg, sched, video, mode, max_frames, obs_length, step_size, noise_fn, vertical_steps):
+    """scripts/video_sample_full.py:50-323 with observed_frames='x_0': `vertical_steps` timesteps window by window
+    (:88-203), then one sweep over all windows per remaining timestep (:205-313), each window restarting from the
+    video's current contents."""
+    B, T = video.shape[:2]
+    samples = torch.zeros_like(video)
+    samples[:, :obs_length] = video[:, :obs_length]
+    steps = list(reversed(range(sched.num_timesteps)))
+
+    def one(cur, x0, obs, lat, step):
+        fi, om, lm, km = (torch.from_numpy(a) for a in S.window_tensors(obs, lat, B))
+        t = torch.full((B,), step, dtype=torch.long)
+        eps = U.cond_marg_forward(sd, cfg, cur, x0, om, lm, km, sched.model_time(t), fi)
+        return D.p_sample(sched, eps, cur, t, noise_fn(tuple(cur.shape)))['sample']
+
+    if vertical_steps > 0:
+        for obs, lat in S.schedule(mode, T, obs_length, max_frames, step_size):
+            x0 = torch.cat([samples[:, obs], samples[:, lat]], dim=1).clone()
+            cur = x0.clone()
+            for step in steps[:vertical_steps]:
+                cur = one(cur, x0, obs, lat, step)
+            samples[:, lat] = cur[:, -len(lat):]
+    for step in steps[vertical_steps:]:
+        for obs, lat in S.schedule(mode, T, obs_length, max_frames, step_size):
+            x0 = torch.cat([samples[:, obs], samples[:, lat]], dim=1).clone()
+            samples[:, lat] = one(x0, x0, obs, lat, step)[:, -len(lat):]
     return samples
 
 

@@ -241,3 +241,20 @@ def test_tiny_chain_ddim_loop_and_elbo_match_reference(golden):
         raw, _ = P.run_bpd_evaluation(sd, cfg, sched4, cases.bpd_case_inputs(c), _Replay(c['noise_seed'] + 900))
         for k, v in raw.items():
             np.testing.assert_allclose(v.numpy(), g[f'bpd/{k}'], rtol=2e-4, atol=1e-6, err_msg=k)
+
+
+def test_vertical_horizontal_schedule_matches_reference(golden):
+    """scripts/video_sample_full.py:50-323 (vertical, then horizontal diffusion) -- oracle restatement vs the
+    reference's model / p_sample run through the script's loop (tests/golden/chain_full.npz)."""
+    from oracle import pipeline_oracle as P
+    g = golden.npz('chain_full')
+    c, f = cases.CHAIN_CASE, cases.FULL_SCHEDULE_CASE
+    sd = synth.make_state_dict(golden.json('spec_' + c['cfg']), seed=1)
+    cfg = U.model_config(**cases.ref_config(c['cfg']))
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    with torch.no_grad():
+        sched = D.Schedule(1000, 'linear', c['respacing'])
+        samples = P.infer_video_full(sd, cfg, sched, video, c['mode'], c['max_frames'], c['obs_length'], c['step_size'],
+                                     _Replay(f['noise_seed']), f['vertical_steps'])
+    assert np.abs(samples.numpy() - g['full/samples']).max() < 5e-4
+    assert np.abs(g['full/samples'] - g['full/vertical']).max() > 1e-2      # the horizontal sweeps did change the video

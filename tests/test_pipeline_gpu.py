@@ -1,6 +1,8 @@
 """End-to-end parity on the B200 for the two callers of the hot path, tiny config (C1):
 script-style sampling (`infer_video`), `ddim_sample_loop`, and the ELBO loop, against fixtures
 produced by the unmodified reference with the same weights and replayed noise."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -83,6 +85,54 @@ def test_infer_video_save_all_timesteps(golden, replay):
     for k in range(diffusion.num_timesteps):                             # observed prefix at every timestep
         np.testing.assert_array_equal(every[:, k, :c['obs_length']], video[:, :c['obs_length']].numpy())
     assert np.abs(every[:, 0] - every[:, -1]).max() > 1e-2               # earlier states differ
+
+
+@pytest.mark.parametrize('dtype,min_psnr,tol', [(torch.float32, 55.0, 2e-3), (torch.bfloat16, 38.0, None)],
+                         ids=['fp32', 'bf16'])
+def test_infer_video_full_vertical_horizontal_schedule(golden, replay, dtype, min_psnr, tol):
+    """scripts/video_sample_full.py:50-323: 4 vertical timesteps window by window, then one sweep over all windows per
+    remaining timestep, against the reference's model / p_sample run through that loop."""
+    from video_diffusion_b200.sampling import infer_video_full
+    c, f = cases.CHAIN_CASE, cases.FULL_SCHEDULE_CASE
+    g = golden.npz('chain_full')
+    model, diffusion = build_model(c['cfg'], golden, dtype, respacing=c['respacing'])
+    video = synth.make_video((c['batch'], c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    replay(f['noise_seed'])
+    samples, every = infer_video_full(c['mode'], model, diffusion, video, c['max_frames'], c['obs_length'],
+                                      c['step_size'], vertical_steps=f['vertical_steps'], save_all_timesteps=True)
+    ref = g['full/samples']
+    assert samples.shape == ref.shape and every.shape == (c['batch'], diffusion.num_timesteps, *video.shape[1:])
+    np.testing.assert_array_equal(samples[:, :c['obs_length']], ref[:, :c['obs_length']])
+    p = psnr(samples, ref)
+    print(f'infer_video_full {dtype}: PSNR vs reference = {p:.1f} dB, max abs diff = {np.abs(samples - ref).max():.3e}')
+    assert p >= min_psnr
+    if tol is not None:
+        assert np.abs(samples - ref).max() < tol
+        assert np.abs(every[:, f['vertical_steps'] - 1] - g['full/vertical']).max() < tol    # state after the vertical phase
+    np.testing.assert_array_equal(every[:, -1], samples)
+
+
+def test_async_sample_writer_overlaps_and_matches_save_samples(golden, replay, tmp_path):
+    """Finished frames leave the device on a copy stream while the next window runs; the files equal
+    save_samples(to_uint8(samples)) (scripts/video_sample.py:179-189, 266-272)."""
+    from video_diffusion_b200.sampling import AsyncSampleWriter, infer_video, save_samples, to_uint8
+    c = cases.CHAIN_CASE
+    model, diffusion = build_model(c['cfg'], golden, torch.float32, respacing=c['respacing'])
+    video = synth.make_video((2, c['video_length'], 3, c['image_size'], c['image_size']), seed=c['video_seed'])
+    replay(c['noise_seed'])
+    writer = AsyncSampleWriter(tuple(video.shape), 'cuda')
+    samples, _ = infer_video(c['mode'], model, diffusion, video, c['max_frames'], c['obs_length'], c['step_size'],
+                             writer=writer)
+    paths = writer.finish(str(tmp_path / 'async'), [7, 12], sample_idx=3)
+    want = save_samples(str(tmp_path / 'sync'), to_uint8(samples), [7, 12], sample_idx=3)
+    assert [os.path.basename(a) for a in paths] == [os.path.basename(b) for b in want] == ['sample_0007-3.npy',
+                                                                                          'sample_0012-3.npy']
+    for a, b in zip(paths, want):
+        x, y = np.load(a), np.load(b)
+        assert x.dtype == np.uint8 and x.shape == (c['video_length'], 3, c['image_size'], c['image_size'])
+        np.testing.assert_array_equal(x, y)
+    with pytest.raises(RuntimeError):
+        AsyncSampleWriter(tuple(video.shape), 'cuda').finish()              # nothing pushed
 
 
 @pytest.mark.parametrize('dtype,min_psnr', [(torch.float32, 55.0), (torch.bfloat16, 40.0)], ids=['fp32', 'bf16'])

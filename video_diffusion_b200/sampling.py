@@ -27,11 +27,13 @@ def get_masks(x0, num_obs):
 @torch.no_grad()
 def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size=1, optimal_schedule_path=None, *,
                 use_gradient_method=False, observed_frames='x_0', device=None, return_tensor=False,
-                save_all_timesteps=False):
+                save_all_timesteps=False, writer=None):
     """batch: (B, T, C, H, W) in [-1, 1].  Returns (samples, all_timestep_samples) as numpy arrays like
     scripts/video_sample.py:50-190; `observed_frames` and `save_all_timesteps` are script globals (`args.*`) there and
     keyword arguments here.  all_timestep_samples is (B, num_timesteps, T, C, H, W) in chain order with
-    save_all_timesteps, zeros([1]) otherwise.  Everything stays on the device until the final copy."""
+    save_all_timesteps, zeros([1]) otherwise.  Everything stays on the device until the final copy; with `writer` (an
+    AsyncSampleWriter) the finished frames of each window are converted and copied out on a side stream while the next
+    window runs."""
     if use_gradient_method:
         raise NotImplementedError('use_gradient_method needs autograd through the network')
     if 'adaptive' in mode or 'goal-directed' in mode:
@@ -49,6 +51,8 @@ def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size
         all_steps = torch.zeros(B, len(steps), *video.shape[1:], device=device)
         all_steps[:, :, :obs_length] = samples[:, :obs_length].unsqueeze(1)
     t_all = torch.arange(diffusion.num_timesteps, device=device).view(-1, 1).expand(-1, B).contiguous()
+    if writer is not None:
+        writer.push(samples, range(obs_length))
     for obs_idx, lat_idx in schedule:
         idx = torch.tensor(list(obs_idx) + list(lat_idx), device=device, dtype=torch.long)
         x0 = samples.index_select(1, idx)
@@ -64,9 +68,115 @@ def infer_video(mode, model, diffusion, batch, max_frames, obs_length, step_size
             if all_steps is not None:
                 all_steps[:, k, idx[-n_lat:]] = local[:, -n_lat:]
         samples[:, idx[-n_lat:]] = local[:, -n_lat:]
+        if writer is not None:
+            writer.push(samples, lat_idx)
     if return_tensor:
         return samples if all_steps is None else (samples, all_steps)
     return samples.cpu().numpy(), (np.zeros([1], dtype=np.float32) if all_steps is None else all_steps.cpu().numpy())
+
+
+@torch.no_grad()
+def infer_video_full(mode, model, diffusion, batch, max_frames, obs_length, step_size=1, optimal_schedule_path=None, *,
+                     vertical_steps=0, observed_frames='x_0', use_gradient_method=False, device=None,
+                     return_tensor=False, save_all_timesteps=False):
+    """The "vertical / horizontal" schedule of scripts/video_sample_full.py:50-323, an adjacent caller of the same
+    p_sample: the first `vertical_steps` timesteps run window by window like infer_video (:88-203, each window a
+    partial chain from x0.clone() with observed_frames='x_0'); every remaining timestep then sweeps ALL windows once
+    (:205-313): a window's input is whatever the video holds at that moment -- its latent frames are the partly
+    denoised state written back by the previous sweep -- one p_sample step is taken with `observed_frames` (the
+    script's args.observed_frames) and the latent frames are written back.  With vertical_steps == 0 the latent frames
+    start at zero, as in the script.  `vertical_steps`, `observed_frames`, `save_all_timesteps` are `args.*` globals
+    there.  The video stays in HBM; one device->host copy at the end."""
+    if use_gradient_method:
+        raise NotImplementedError('use_gradient_method needs autograd through the network')
+    if 'adaptive' in mode or 'goal-directed' in mode:
+        raise NotImplementedError(f'inference mode {mode!r}')
+    device = device or next(model.parameters()).device
+    B, T = batch.shape[:2]
+    video = batch.to(device, non_blocking=True).float()
+    samples = torch.zeros_like(video)
+    samples[:, :obs_length] = video[:, :obs_length]
+    n_t = diffusion.num_timesteps
+    steps = list(range(n_t))[::-1]
+    all_steps = None
+    if save_all_timesteps:                                      # scripts/video_sample_full.py:79-86
+        all_steps = torch.zeros(B, n_t, *video.shape[1:], device=device)
+        all_steps[:, :, :obs_length] = samples[:, :obs_length].unsqueeze(1)
+    t_all = torch.arange(n_t, device=device).view(-1, 1).expand(-1, B).contiguous()
+
+    def windows():
+        return iter(inference_strategies[mode](video_length=T, num_obs=obs_length, max_frames=max_frames,
+                                               step_size=step_size, optimal_schedule_path=optimal_schedule_path))
+
+    def window(obs_idx, lat_idx, observed):
+        idx = torch.tensor(list(obs_idx) + list(lat_idx), device=device, dtype=torch.long)
+        x0 = samples.index_select(1, idx)
+        obs_mask, latent_mask, kinda_marg_mask = get_masks(x0, len(obs_idx))
+        return idx, x0, dict(frame_indices=idx.view(1, -1).repeat(B, 1), x0=x0, obs_mask=obs_mask,
+                             latent_mask=latent_mask, kinda_marg_mask=kinda_marg_mask, x_t_minus_1=x0,
+                             observed_frames=observed)
+
+    if vertical_steps > 0:
+        for obs_idx, lat_idx in windows():
+            idx, x0, kwargs = window(obs_idx, lat_idx, 'x_0')
+            local, n_lat = x0.clone(), len(lat_idx)
+            for k, step in enumerate(steps[:vertical_steps]):
+                local = diffusion.p_sample(model, local, t=t_all[step], clip_denoised=True, model_kwargs=kwargs,
+                                           return_attn_weights=False)['sample']
+                if all_steps is not None:
+                    all_steps[:, k, idx[-n_lat:]] = local[:, -n_lat:]
+            samples[:, idx[-n_lat:]] = local[:, -n_lat:]
+    for k, step in enumerate(steps[vertical_steps:]):
+        for obs_idx, lat_idx in windows():
+            idx, x0, kwargs = window(obs_idx, lat_idx, observed_frames)
+            n_lat = len(lat_idx)
+            local = diffusion.p_sample(model, x0, t=t_all[step], clip_denoised=True, model_kwargs=kwargs,
+                                       return_attn_weights=False)['sample']
+            samples[:, idx[-n_lat:]] = local[:, -n_lat:]
+        if all_steps is not None:
+            all_steps[:, vertical_steps + k] = samples
+    if return_tensor:
+        return samples if all_steps is None else (samples, all_steps)
+    return samples.cpu().numpy(), (np.zeros([1], dtype=np.float32) if all_steps is None else all_steps.cpu().numpy())
+
+
+class AsyncSampleWriter:
+    """Device->host copy and .npy write of finished frames, overlapped with the next window (the reference moves every
+    window's result to the host synchronously, scripts/video_sample.py:179-189, and writes `sample_XXXX-k.npy` after
+    the whole video, :266-272).  `push` is called by infer_video after each window: on a copy stream the frames are
+    converted to uint8 exactly like `to_uint8` and copied into one pinned host buffer while the compute stream goes on
+    with the next window; `finish` waits for the copies and writes the same files as `save_samples`."""
+
+    def __init__(self, shape, device):
+        B, T, C, H, W = shape
+        self.host = torch.empty((B, T, C, H, W), dtype=torch.uint8).pin_memory()
+        self.stream = torch.cuda.Stream(device=device)
+        self.pushed = torch.zeros(T, dtype=torch.bool)
+
+    def push(self, samples, frames):
+        """samples: the (B, T, C, H, W) video on the device; frames: list of frame indices that are final now."""
+        frames = [int(f) for f in frames]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(samples.device))
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            idx = torch.tensor(frames, device=samples.device, dtype=torch.long)
+            chunk = to_uint8(samples.index_select(1, idx))
+            for j, f in enumerate(frames):
+                self.host[:, f].copy_(chunk[:, j], non_blocking=True)
+            chunk.record_stream(self.stream)
+        # the compute stream must not overwrite these frames before the copy stream has read them: infer_video never
+        # rewrites a finished frame, which is what makes the overlap safe
+        self.pushed[frames] = True
+
+    def finish(self, out_dir=None, dataset_indices=None, sample_idx=0):
+        self.stream.synchronize()
+        if not bool(self.pushed.all()):
+            raise RuntimeError(f'frames never pushed: {(~self.pushed).nonzero().flatten().tolist()}')
+        arr = self.host.numpy()
+        if out_dir is None:
+            return arr
+        return save_samples(out_dir, arr, dataset_indices, sample_idx)
 
 
 def to_uint8(samples):
