@@ -3,7 +3,7 @@
 ancestral sampler step) on BASELINE.json's config 2 -- MineRL-sized FDM U-Net, 64x64,
 max_frames=20, batch 8 per GPU, bf16 tensor-core mode, synthetic video, de-zeroed random weights.
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c2|c4|c3|c5]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c2|c2chain|c4|c3|c5]
 
 A "step" is one `diffusion.p_sample` call: conditioning mix -> U-Net forward -> fused sampler
 kernel, i.e. B*F = 160 frames denoised once.  Prints ONE JSON line (see the task contract):
@@ -354,6 +354,51 @@ def run_c3(args, model, diffusion_factory, dev, rank, world):
             'gather_ms': gather_ms, 'gathered_bytes': int(rows.numel())}))
 
 
+def run_c2chain(args, model, diffusion_factory, dev, rank, world):
+    """BASELINE configs[1] as a CHAIN: `autoreg` with step_size 7, ancestral 1000-step sampling, batch 8 -- one full window
+    (13 observed + 7 latent frames, 1000 `p_sample` steps through `infer_video`, finished frames copied out by the
+    AsyncSampleWriter) is timed; a T = 500 video with 36 observed frames is 67 such windows ("time >= 1
+    full window + extrapolate")."""
+    import torch.distributed as dist
+    from oracle import synth
+    from video_diffusion_b200.sampling import AsyncSampleWriter, infer_video
+    diffusion = diffusion_factory('')
+    obs, step, B = 36, 7, B_PER_GPU
+    T = obs + step * args.c2_windows
+    video = synth.make_video((B, T, 3, SIZE, SIZE), seed=300 + rank)
+    short = diffusion_factory('ddim10')
+    infer_video('autoreg', model, short, video[:, :obs + step], FRAMES, obs, step, return_tensor=True)    # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    writer = AsyncSampleWriter(tuple(video.shape), dev)
+    e0.record()
+    infer_video('autoreg', model, diffusion, video, FRAMES, obs, step, return_tensor=True, writer=writer)
+    frames_u8 = writer.finish()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    n_calls = args.c2_windows * diffusion.num_timesteps
+    if rank == 0:
+        per_window = ms / args.c2_windows
+        print(json.dumps({
+            'metric': 'sampled video frames/sec (full ancestral 1000-step chain, autoreg)', 'unit': 'frames/s',
+            'value': world * B * step * args.c2_windows / ms * 1e3, 'n_gpus': world, 'steps': 1, 'warmup': 1,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': f'C2 chain: 64x64 FDM U-Net, autoreg step_size 7, max_frames 20 (13 observed + 7 latent), '
+                                   f'{diffusion.num_timesteps} ancestral steps per window, {args.c2_windows} window(s) timed, '
+                                   f'{B} videos per GPU, finished frames leave on a copy stream (AsyncSampleWriter)',
+                       'network_calls': n_calls, 'denoised_frames_per_s': world * B * FRAMES * n_calls / ms * 1e3,
+                       'ms_per_window': per_window,
+                       'extrapolated_T500_video_s': per_window * 67 / 1e3,
+                       'host_uint8_bytes': int(frames_u8.size)}}))
+
+
 def run_c5(args, model, diffusion_factory, dev, rank, world):
     """BASELINE configs[4]: video_nll ELBO over all 1000 timesteps (forward-only sweep), 64x64, 20 frames, 8 videos per
     GPU; one final gather of the per-video ELBO rows.  A step = one whole `run_bpd_evaluation` call."""
@@ -405,11 +450,12 @@ def main():
     ap.add_argument('--no-stock-gpu-baseline', action='store_true')
     ap.add_argument('--stock-gpu-baseline', action='store_true', help='(default on; kept for old command lines)')
     ap.add_argument('--profile-json', default=None, help='write the per-kernel-class breakdown here')
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c4', 'c3', 'c5'],
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c2chain', 'c4', 'c3', 'c5'],
                     help="c2 (default) is the configuration BASELINE.json's metric is quoted on; c4 = the 128x128 model; "
                          'c3 / c5 = the long-video sampling job and the ELBO sweep (secondary workloads)')
     ap.add_argument('--c3-frames', type=int, default=300)
     ap.add_argument('--c5-timesteps', type=int, default=1000)
+    ap.add_argument('--c2-windows', type=int, default=1, help='c2chain: autoreg windows (1000 ancestral steps each) to time')
     args = ap.parse_args()
     if args.workload == 'c4':
         # BASELINE.json configs[3]: 128x128, channel_mult (1,1,2,3,4), 2 res blocks; SURVEY 8(d): 21.713 TFLOP per
@@ -446,9 +492,10 @@ def main():
     sd = synth_state(CFG)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
-    if args.workload in ('c3', 'c5'):
+    if args.workload in ('c3', 'c5', 'c2chain'):
         with torch.no_grad():
-            (run_c3 if args.workload == 'c3' else run_c5)(args, model, lambda r: build(r)[1], dev, rank, world)
+            {'c3': run_c3, 'c5': run_c5, 'c2chain': run_c2chain}[args.workload](args, model, lambda r: build(r)[1], dev, rank,
+                                                                                world)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -467,7 +514,7 @@ def main():
     x_pin = host['x0'].clone().pin_memory()
     out_pin = torch.empty_like(x_pin).pin_memory()
 
-    def step_e2e():
+    def step_e2e_serial():
         d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
         x = x_pin.to(dev, non_blocking=True)
         s = diffusion.p_sample(model, x, t_dev, clip_denoised=True,
@@ -475,7 +522,18 @@ def main():
         out_pin.copy_(s, non_blocking=True)
         return s
 
-    def timed(fn, steps):
+    # the public host-buffer API: uploads of step i + 1 and the download of step i ride a copy stream under the compute
+    from video_diffusion_b200.sampling import PipelinedHostStepper
+    stepper = PipelinedHostStepper(model, diffusion, dev)
+
+    def step_e2e():
+        return stepper.step(x_pin, t_dev, pinned, out_pin, clip_denoised=True)
+
+    def e2e_finish():      # inside the timed region: the last download has landed in host memory
+        stepper.drain()
+        torch.cuda.current_stream().wait_stream(stepper.copy)
+
+    def timed(fn, steps, finish=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -483,6 +541,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -525,7 +585,11 @@ def main():
             ms = timed(step_resident, args.steps)
         for _ in range(args.warmup):
             step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        e2e_finish()
+        ms_e2e = timed(step_e2e, args.steps, e2e_finish)
+        for _ in range(2):
+            step_e2e_serial()
+        ms_e2e_serial = timed(step_e2e_serial, args.steps)
 
     frames = world * B * FRAMES * args.steps
     value = frames / (ms / 1e3)
@@ -552,7 +616,10 @@ def main():
         'config': shared_config(world),
         'clocks': clk.summary(),
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
-                'd2h_bytes_per_step': int(out_pin.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': int(out_pin.numel() * 4), 'ms_per_step': ms_e2e / args.steps,
+                'api': 'sampling.PipelinedHostStepper.step (diffusion.p_sample on pinned host tensors; transfers on a '
+                       'copy stream under the neighbouring steps, all inside the timed region, last download drained)',
+                'ms_per_step_serial': ms_e2e_serial / args.steps},
         'gpu_launches': int(launches_per_step * args.steps),
         'roofline': {'bound': 'tensor',
                      'kernel': 'whole U-Net forward (SURVEY 8d algorithmic FLOPs) over the graph-replayed step; dominant '

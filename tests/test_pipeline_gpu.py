@@ -112,6 +112,38 @@ def test_infer_video_full_vertical_horizontal_schedule(golden, replay, dtype, mi
     np.testing.assert_array_equal(every[:, -1], samples)
 
 
+def test_pipelined_host_stepper_equals_direct_p_sample(golden, replay):
+    """p_sample on pinned host tensors with the transfers on a copy stream: every step's sample equals the plain call on
+    device tensors (same replayed noise), also when the two input slots are recycled."""
+    from video_diffusion_b200.sampling import PipelinedHostStepper
+    c = cases.CHAIN_CASE
+    model, diffusion = build_model(c['cfg'], golden, torch.bfloat16, respacing=c['respacing'])
+    B, F, S = 2, c['max_frames'], c['image_size']
+    steps = []
+    for i in range(5):
+        x0 = synth.make_video((B, F, 3, S, S), seed=40 + i)
+        om = torch.zeros(B, F, 1, 1, 1)
+        om[:, :3 + i] = 1
+        kw = dict(x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om),
+                  frame_indices=torch.arange(i, i + F).view(1, F).repeat(B, 1))
+        steps.append((synth.make_noise((B, F, 3, S, S), seed=60 + i), kw))
+    t = torch.tensor([7, 2]).cuda()
+    replay(900)
+    want = []
+    for x, kw in steps:
+        d = {k: v.cuda() for k, v in kw.items()}
+        want.append(diffusion.p_sample(model, x.cuda(), t, model_kwargs=dict(d, x_t_minus_1=d['x0'], observed_frames='x_0'))
+                    ['sample'].cpu())
+    replay(900)
+    stepper = PipelinedHostStepper(model, diffusion, 'cuda')
+    outs = [torch.empty(B, F, 3, S, S).pin_memory() for _ in steps]
+    for (x, kw), out in zip(steps, outs):
+        stepper.step(x.pin_memory(), t, {k: v.pin_memory() for k, v in kw.items()}, out)
+    stepper.drain()
+    for a, b in zip(outs, want):
+        assert torch.equal(a, b)
+
+
 def test_async_sample_writer_overlaps_and_matches_save_samples(golden, replay, tmp_path):
     """Finished frames leave the device on a copy stream while the next window runs; the files equal
     save_samples(to_uint8(samples)) (scripts/video_sample.py:179-189, 266-272)."""

@@ -179,6 +179,61 @@ class AsyncSampleWriter:
         return save_samples(out_dir, arr, dataset_indices, sample_idx)
 
 
+class PipelinedHostStepper:
+    """`diffusion.p_sample` for callers whose inputs and results live in (pinned) HOST memory: the inputs of step i + 1 are
+    uploaded on a copy stream while step i computes, and the sample of step i is downloaded while step i + 1 computes,
+    so the PCIe transfers (15.7 MB up + 7.9 MB down per C2 step) disappear behind the 12-13 ms of compute instead of
+    adding to them.  Two device-side input slots; a slot is rewritten only after the step that read it has been
+    enqueued past its input copy."""
+
+    def __init__(self, model, diffusion, device):
+        self.model, self.diffusion, self.device = model, diffusion, torch.device(device)
+        self.copy = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.up = [torch.cuda.Event(), torch.cuda.Event()]
+        self.used = [None, None]
+        self.i = 0
+
+    def _upload(self, slot, x_pin, kw_pin):
+        bufs = self.slots[slot]
+        if bufs is None:
+            bufs = self.slots[slot] = dict({k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                                            for k, v in kw_pin.items()}, __x=torch.empty(x_pin.shape, dtype=x_pin.dtype,
+                                                                                        device=self.device))
+        with torch.cuda.stream(self.copy):
+            if self.used[slot] is not None:
+                self.copy.wait_event(self.used[slot])
+            bufs['__x'].copy_(x_pin, non_blocking=True)
+            for k, v in kw_pin.items():
+                bufs[k].copy_(v, non_blocking=True)
+            self.up[slot].record(self.copy)
+        return bufs
+
+    def step(self, x_pin, t, kw_pin, out_pin, **p_sample_kwargs):
+        """x_pin, kw_pin (x0, masks, frame_indices ...): pinned host tensors; t: device tensor; out_pin: pinned host tensor
+        that receives the sample (valid after `drain()` or once a later step's download has completed)."""
+        slot = self.i & 1
+        self.i += 1
+        bufs = self._upload(slot, x_pin, kw_pin)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.up[slot])
+        kw = {k: v for k, v in bufs.items() if k != '__x'}
+        s = self.diffusion.p_sample(self.model, bufs['__x'], t, model_kwargs=dict(kw, x_t_minus_1=kw['x0'],
+                                                                                observed_frames='x_0'),
+                                    **p_sample_kwargs)['sample']
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.used[slot] = done
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(done)
+            out_pin.copy_(s, non_blocking=True)
+            s.record_stream(self.copy)
+        return s
+
+    def drain(self):
+        self.copy.synchronize()
+
+
 def to_uint8(samples):
     """(x+1)/2*255 clipped to uint8, as written to sample_XXXX-k.npy (scripts/video_sample.py:266-268)."""
     if torch.is_tensor(samples):
