@@ -277,6 +277,28 @@ int vdm_attn_temporal_tc(const void* qkv, const float* sk, const float* sq, cons
                          int32_t heads, int32_t hd, int32_t groups_per_tile, void* pm, float* pv,
                          vdm_stream_t stream);
 
+/* ---- temporal attention, fused block (bf16 mode, default) ------------------------------------------
+ * Replaces RPEAttention._forward between the qkv projection and proj_out (unet.py:471-536) together with
+ * RPE.forward_qk / forward_v (unet.py:357-378) in ONE kernel: per CTA (video, head, `pixels_per_cta` pixels) the
+ * RPE score terms q.Rk and k.Rq (GEMMs over the pixels of the tile), q.k^T, mask, fp32 softmax, P.V and the
+ * attn.R_v term, all on mma.sync with the intermediates in shared memory.  out: [B*T*HW][C] bf16.
+ * vdm_rpe_pack converts the fp32 R tables ([B*T*T][C] each, + optional bias [n_blocks][3][C] (q, k, v)) into the
+ * kernel's bf16 operand layouts, for `n_blocks` attention blocks per call:
+ *   rq, rk: [n_blocks][B*T][heads][t_pad][hd]   rows j >= T zero     (R[b, i, j, h, :] at group g = b*T + i)
+ *   rv    : [n_blocks][B*T][heads][hd][32]      columns s >= T zero  (transposed: the contraction runs over s)
+ * t_pad = 24 (T <= 24) or 32; T <= 32; HW a multiple of pixels_per_cta (8, or 16 for hd = 96; 0 = 8). */
+int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t n_blocks,
+                 int64_t r_block_stride /* elements between consecutive blocks' fp32 tables */, int32_t B, int32_t T,
+                 int32_t heads, int32_t hd, int32_t t_pad, void* rq, void* rk, void* rv,
+                 int64_t qk_block_stride /* elements between blocks' rq (and rk); 0 = packed */,
+                 int64_t v_block_stride /* 0 = packed */, vdm_stream_t stream);
+/* Dynamic shared memory (bytes) the fused kernel needs for this shape, or -1 if the shape is not instantiated; the
+ * launch fails above 227 KB (the host mirror falls back to the three-launch path there). */
+int64_t vdm_attn_temporal_fused_smem(int32_t T, int32_t hd, int32_t t_pad, int32_t pixels_per_cta);
+int vdm_attn_temporal_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask,
+                            int32_t allow_pad_interactions, int32_t B, int32_t T, int32_t HW, int32_t heads,
+                            int32_t hd, int32_t t_pad, int32_t pixels_per_cta, void* out, vdm_stream_t stream);
+
 /* ---- spatial attention (unet.py:258-266 -> 477-536 without RPE / mask) --------------------
  * qkv: [n_img*L][3C] (dtype qkv_dtype); softmax(q k^T / sqrt(hd)) v per (image, head).
  * qkv_dtype VDM_BF16 -> tensor-core flash kernel; VDM_F32 -> fp32 SIMT kernel. */

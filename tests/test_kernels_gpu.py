@@ -918,6 +918,73 @@ def test_attention_temporal_tensor_core_path(T, hd, HW, pad):
     assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
 
 
+@pytest.mark.parametrize('T,hd,HW,pad,pt', [(20, 96, 256, True, 8), (20, 96, 256, True, 16), (10, 32, 64, False, 8),
+                                             (7, 128, 128, True, 8), (20, 128, 64, True, 8), (32, 64, 24, False, 8),
+                                             (27, 96, 16, True, 8), (1, 96, 8, True, 8), (17, 96, 48, False, 16)])
+def test_attention_temporal_fused(T, hd, HW, pad, pt):
+    """The whole temporal attention of a block in one kernel (RPE score terms, q.k^T, mask, softmax, P.V, attn.R_v),
+    against the fp32 einsum restatement on the same bf16-rounded q, k, v and bf16-rounded (R + bias) tables."""
+    o = ops()
+    B, heads = 3, 4
+    Cc = heads * hd
+    M = B * T * HW
+    qkv = rnd(B, T, HW, 3 * Cc, seed=1).bfloat16()
+    R = [rnd(B * T * T, Cc, seed=2 + i, scale=0.5) for i in range(3)]
+    bias = rnd(3, Cc, seed=9, scale=0.2)
+    mask = torch.ones(B, T).cuda()
+    mask[0, max(T - 2, 1):] = 0
+    Rb = [(R[i] + bias[i]).bfloat16().float() for i in range(3)]
+    ref = _attn_ref(qkv.float().permute(0, 2, 1, 3), heads, mask, Rb, pad).permute(0, 2, 1, 3).reshape(M, Cc)
+    TP = 24 if T <= 24 else 32
+    nan = float('nan')
+    rq = torch.full((B * T, heads, TP, hd), nan, device='cuda', dtype=torch.bfloat16)
+    rk = torch.full_like(rq, nan)
+    rv = torch.full((B * T, heads, hd, 32), nan, device='cuda', dtype=torch.bfloat16)
+    o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rq, rk, rv, bias=bias)
+    for got, want in ((rq, Rb[0]), (rk, Rb[1])):
+        assert torch.equal(got[:, :, :T].float(), want.view(B * T, T, heads, hd).permute(0, 2, 1, 3))
+        assert float(got[:, :, T:].float().abs().sum()) == 0
+    assert torch.equal(rv[..., :T].float(), Rb[2].view(B * T, T, heads, hd).permute(0, 2, 3, 1))
+    assert float(rv[..., T:].float().abs().sum()) == 0
+    att = torch.full((M, Cc), nan, device='cuda', dtype=torch.bfloat16)
+    o.attn_temporal_fused(qkv.view(M, 3 * Cc), rq, rk, rv, mask, pad, B, T, HW, heads, hd, TP, att, pixels_per_cta=pt)
+    assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
+    # a micro-batch: videos 1.. of the same tables through offset views
+    att2 = torch.full((M, Cc), nan, device='cuda', dtype=torch.bfloat16)
+    o.attn_temporal_fused(qkv.view(M, 3 * Cc)[T * HW:], rq[T:], rk[T:], rv[T:], mask[1:], pad, B - 1, T, HW, heads, hd, TP,
+                          att2[T * HW:], pixels_per_cta=pt)
+    assert torch.equal(att2[T * HW:], att[T * HW:])
+
+
+def test_rpe_pack_batched_over_blocks_and_unsupported_shapes():
+    o = ops()
+    B, T, heads, hd, nb = 2, 20, 4, 32, 3
+    Cc, rows = heads * hd, 2 * 20 * 20
+    Rall = rnd(nb * 3 * rows, Cc, seed=3)
+    bias = rnd(nb, 3, Cc, seed=4)
+    per = B * T * heads * 24 * hd
+    rqk = torch.zeros(nb, 2, per, device='cuda', dtype=torch.bfloat16)
+    rvp = torch.zeros(nb, B * T * heads * hd * 32, device='cuda', dtype=torch.bfloat16)
+    o.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, 24, rqk[0, 0], rqk[0, 1], rvp,
+               bias=bias, n_blocks=nb, r_block_stride=3 * rows * Cc, qk_block_stride=2 * per)
+    for i in range(nb):
+        blk = Rall[i * 3 * rows:(i + 1) * 3 * rows].view(3, rows, Cc)
+        q1, k1 = torch.empty(per, device='cuda', dtype=torch.bfloat16), torch.empty(per, device='cuda', dtype=torch.bfloat16)
+        v1 = torch.empty_like(rvp[0])
+        o.rpe_pack(blk[0], blk[1], blk[2], B, T, heads, hd, 24, q1, k1, v1, bias=bias[i])
+        assert torch.equal(rqk[i, 0], q1) and torch.equal(rqk[i, 1], k1) and torch.equal(rvp[i], v1)
+    out = torch.empty(B * T * 8, Cc, device='cuda', dtype=torch.bfloat16)
+    qkv = torch.zeros(B * T * 8, 3 * Cc, device='cuda', dtype=torch.bfloat16)
+    mask = torch.ones(B, T).cuda()
+    with pytest.raises(RuntimeError, match='pixels per CTA'):
+        o.attn_temporal_fused(qkv, rqk[0, 0], rqk[0, 1], rvp[0], mask, True, B, T, 8, heads, hd, 24, out, pixels_per_cta=16)
+    with pytest.raises(RuntimeError, match='t_pad'):
+        o.attn_temporal_fused(qkv, rqk[0, 0], rqk[0, 1], rvp[0], mask, True, B, 33, 8, heads, hd, 32, out)
+    # shapes beyond the 227 KB of shared memory are reported, the model falls back to the three-launch path for them
+    assert o.attn_temporal_fused_smem(20, 96, 24, 8) == 3 * 20 * (8 * 192 + 16) + 8 * 1952
+    assert o.attn_temporal_fused_smem(32, 128, 32, 8) > 227 * 1024 and o.attn_temporal_fused_smem(20, 128, 24, 16) == -1
+
+
 @pytest.mark.parametrize('M,C,SW,tpg', [(640, 128, 128, 1), (1536, 64, 256, 1), (1024, 192, 128, 2)])
 def test_gemm_problem_batch_equals_separate_launches(M, C, SW, tpg):
     """n_prob = 2: q -> Sk and k -> Sq (column blocks of one qkv matrix, stacked grouped weights, stacked outputs) in

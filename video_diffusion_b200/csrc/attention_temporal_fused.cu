@@ -1,0 +1,534 @@
+// Temporal RPE attention of one block as ONE kernel (bf16 mode): RPE score terms, q.k^T, mask, softmax, P.V and the
+// attn.R_v term -- nothing between qkv and the attention output touches global memory (unet.py:357-378, 471-536).
+//
+//   attn[t][s] = scale * ( q_t . (k_s + Rk[t,s]) + k_s . Rq[s,t] )          (the reference scales q and k*scale)
+//   out[t]     = sum_s softmax(attn)[t][s] * (v_s + Rv[t,s])
+//
+// The R tables depend on (video, frame pair, head) but not on the pixel, q / k / v depend on the pixel: the q.k^T and
+// P.V products are per-pixel T x T GEMMs (rows = frames), the three RPE contractions are per-frame GEMMs over the
+// pixels of a tile (rows = pixels).  A CTA owns PT pixels of one (video, head); both families run on mma.sync
+// m16n8k16 (sequences of T <= 32 frames are far below a tcgen05 tile) and meet in shared memory:
+//
+//   P1a  Sk[pix][t][s]  = Q_t . Rk[t]^T      one (t, 8-key tile) unit per warp and round      -> S (fp32, smem)
+//   P1b  S[pix][t][s]  += K_s . Rq[s]^T      one (s, 8-query tile) unit per warp and round
+//   P2a  warp = pixel: Q K^T + S  -> registers
+//   P2b  mask, fp32 softmax, P -> smem (bf16, over the pixel's own S rows), P.V -> O (fp32, over the dead Q / K tiles)
+//   P3   out = O + P_t . Rv[t]               one (t, 16-channel) unit per warp and round      -> global, bf16
+//
+// The R operands are read straight from L2 as mma B fragments: vdm_rpe_pack lays the tables out so that a lane's
+// values for TWO k-steps are 16 contiguous bytes (the contraction index is permuted identically on the A side, which
+// is read from shared memory with the same 16-byte pattern), and the next unit's fragments are prefetched into
+// registers while the current unit runs.
+#include "common.cuh"
+
+#ifndef VDM_TF_G1
+#define VDM_TF_G1 4
+#endif
+#ifndef VDM_TF_G3
+#define VDM_TF_G3 8
+#endif
+
+namespace vdm {
+namespace {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp16(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// Row pitch (bytes) of a staged q / k / v row: == 64 (mod 128), so the 16-byte A-fragment reads of two adjacent
+// pixel rows (one quarter-warp) cover all 32 banks; consecutive frames of a pixel are TSTR = PT * pitch + 16 apart, so
+// the eight rows of an ldmatrix (consecutive frames, one pixel) fall into eight different 16-byte bank groups.
+template <int HD>
+struct FusedCfg {
+  static constexpr int LDSB = (HD * 2) % 128 == 64 ? HD * 2 : HD * 2 + 64;
+};
+__host__ __device__ inline int fused_region_stride(int T, int TP) {   // per-pixel S region, == 32 (mod 128)
+  const int base = T * TP * 4;
+  return base + ((32 - base % 128) + 128) % 128;
+}
+
+// ---------------------------------------------------------------- table packing
+// which 0 / 1: out[blk][g][h][j < TP][hd]   = R[blk][(g*T + j)][h*hd + f] + bias   (rows j >= T zero)
+// which 2    : out[blk][g][h][f][s < 32]    = Rv[blk][(g*T + s)][h*hd + f] + bias  (columns s >= T zero)
+__global__ void __launch_bounds__(128) rpe_pack_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
+                                                        const float* __restrict__ r_v, const float* __restrict__ bias,
+                                                        long long r_block_stride, int T, int heads, int hd, int TP,
+                                                        __nv_bfloat16* __restrict__ oq, __nv_bfloat16* __restrict__ ok,
+                                                        __nv_bfloat16* __restrict__ ov, long long qk_block_stride,
+                                                        long long v_block_stride) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  const int g = blockIdx.x, h = blockIdx.y, which = blockIdx.z % 3, blk = blockIdx.z / 3;
+  const int C = heads * hd;
+  const float* R = (which == 0 ? r_q : (which == 1 ? r_k : r_v)) + (size_t)blk * r_block_stride + (size_t)g * T * C + h * hd;
+  const float* bs = bias ? bias + ((size_t)blk * 3 + which) * C + h * hd : nullptr;
+  if (which < 2) {
+    __nv_bfloat16* out = (which == 0 ? oq : ok) + (size_t)blk * qk_block_stride + ((size_t)g * heads + h) * TP * hd;
+    const int hd8 = hd / 8;
+    for (int v = threadIdx.x; v < TP * hd8; v += blockDim.x) {
+      const int j = v / hd8, f = (v - j * hd8) * 8;
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      if (j < T) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(R + (size_t)j * C + f));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(R + (size_t)j * C + f + 4));
+        float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (bs) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] += bs[f + i];
+        }
+        pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
+        pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)j * hd + f) = pk;
+    }
+  } else {
+    __nv_bfloat16* out = ov + (size_t)blk * v_block_stride + ((size_t)g * heads + h) * hd * 32;
+    for (int f = threadIdx.x; f < hd; f += blockDim.x) {
+      const float bf = bs ? bs[f] : 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int s2 = 0; s2 < 16; ++s2) {
+        const int s = 2 * s2;
+        const float x0 = s < T ? __ldg(R + (size_t)s * C + f) + bf : 0.f;
+        const float x1 = s + 1 < T ? __ldg(R + (size_t)(s + 1) * C + f) + bf : 0.f;
+        pk[s2] = pack_bf16x2(x0, x1);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)f * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the fused block
+// grid = (HW / PT, heads, B); PT warps (warp = pixel in the per-pixel phases).
+template <int HD, int PT, int NT>
+__global__ void __launch_bounds__(PT * 32, (PT == 8 && HD <= 96) ? 2 : 1)
+attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ rq,
+                           const __nv_bfloat16* __restrict__ rk, const __nv_bfloat16* __restrict__ rv,
+                           const float* __restrict__ mask, int pad_interact, int T, int D, int heads,
+                           __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  constexpr int LDSB = FusedCfg<HD>::LDSB, KP = HD / 32, TP = NT * 8, W = PT, NTH = PT * 32;
+  constexpr int TSTR = PT * LDSB + 16;
+  constexpr int NG = HD / 16;           // 16-channel output groups of the R_v phase
+  constexpr int G1 = VDM_TF_G1, G3 = VDM_TF_G3;   // units whose R fragments are requested together
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int pix0 = blockIdx.x * PT, h = blockIdx.y, b = blockIdx.z;
+  const int C = heads * HD;
+  const uint32_t tensor_bytes = (uint32_t)T * TSTR;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t sK = sQ + tensor_bytes, sV = sK + tensor_bytes, sS = sV + tensor_bytes, sO = sQ;
+  const int RS = fused_region_stride(T, TP);
+  const float scale = rsqrtf((float)HD);
+
+  // ---- stage q, k (group 0) and v (group 1): rows (frame, pixel), HD bf16 each
+  {
+    constexpr int CH = HD / 8;
+    const int n = T * PT * CH;
+    for (int which = 0; which < 3; ++which) {
+      const uint32_t dstb = which == 0 ? sQ : (which == 1 ? sK : sV);
+      for (int idx = tid; idx < n; idx += NTH) {
+        const int r = idx / CH, c = idx - r * CH;
+        const int t = r / PT, p = r - t * PT;
+        const __nv_bfloat16* src = qkv + ((size_t)(b * T + t) * D + pix0 + p) * (3 * C) + which * C + h * HD + c * 8;
+        cp16(dstb + t * TSTR + p * LDSB + c * 16, src);
+      }
+      if (which == 1) asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // ---- P1: RPE score terms over the pixels of the tile.  Unit u = (frame i, 8-column tile nt).
+  const int n1 = T * NT;
+  auto load_b1 = [&](uint4 (&bf)[KP], const __nv_bfloat16* tab, int u) {
+    const int i = u / NT, nt = u - i * NT;
+    const __nv_bfloat16* row = tab + (((size_t)(b * T + i) * heads + h) * TP + nt * 8 + g) * HD + t4 * 8;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) bf[p] = ldg128(row + p * 32);
+  };
+  auto mma_unit1 = [&](float (&c)[4], const uint4 (&bf)[KP], uint32_t a_base) {
+    c[0] = c[1] = c[2] = c[3] = 0.f;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+      const uint4 lo = lds128(a_base + p * 64);
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+      if (PT == 16) hi = lds128(a_base + 8 * LDSB + p * 64);
+      mma16816(c, lo.x, hi.x, lo.y, hi.y, bf[p].x, bf[p].y);
+      mma16816(c, lo.z, hi.z, lo.w, hi.w, bf[p].z, bf[p].w);
+    }
+  };
+  // The fragments of G1 units are requested together (G1 * KP 16-byte loads in flight per lane): a unit is a handful
+  // of mma, so what a warp waits for is the L2 round trip, once per group instead of once per unit.
+  uint4 bf[G1][KP];
+  auto load_group1 = [&](const __nv_bfloat16* tab, int k0) {
+#pragma unroll
+    for (int j = 0; j < G1; ++j) {
+      const int u = warp + (k0 + j) * W;
+      if (u < n1) load_b1(bf[j], tab, u);
+    }
+  };
+  load_group1(rk, 0);
+  // mask values of this lane's key columns (P2b), fetched while the copies are in flight
+  float m_col[NT * 2];
+#pragma unroll
+  for (int j = 0; j < NT * 2; ++j) {
+    const int col = (j >> 1) * 8 + 2 * t4 + (j & 1);
+    m_col[j] = col < T ? __ldg(mask + b * T + col) : 0.f;
+  }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncthreads();
+  // P1a: Sk[pix][i][s] = Q_i . Rk[i][s]   (plain store: every element of S is written exactly once)
+  for (int k0 = 0; warp + k0 * W < n1; k0 += G1) {
+    if (k0) load_group1(rk, k0);
+#pragma unroll
+    for (int j = 0; j < G1; ++j) {
+      const int u = warp + (k0 + j) * W;
+      if (u < n1) {
+        const int i = u / NT, nt = u - i * NT;
+        float c[4];
+        mma_unit1(c, bf[j], sQ + i * TSTR + g * LDSB + t4 * 16);
+        const uint32_t a = sS + g * RS + (i * TP + nt * 8 + 2 * t4) * 4;
+        sts_f2(a, c[0], c[1]);
+        if (PT == 16) sts_f2(a + 8 * RS, c[2], c[3]);
+      }
+    }
+  }
+  load_group1(rq, 0);        // in flight across the barrier
+  __syncthreads();
+  // P1b: S[pix][t'][i] += K_i . Rq[i][t']
+  for (int k0 = 0; warp + k0 * W < n1; k0 += G1) {
+    if (k0) load_group1(rq, k0);
+#pragma unroll
+    for (int j = 0; j < G1; ++j) {
+      const int u = warp + (k0 + j) * W;
+      if (u < n1) {
+        const int i = u / NT, nt = u - i * NT;
+        float c[4];
+        mma_unit1(c, bf[j], sK + i * TSTR + g * LDSB + t4 * 16);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int tq = nt * 8 + 2 * t4 + e;
+          if (tq < T) {
+            const uint32_t a = sS + g * RS + (tq * TP + i) * 4;
+            sts_f(a, lds_f(a) + c[e]);
+            if (PT == 16) sts_f(a + 8 * RS, lds_f(a + 8 * RS) + c[2 + e]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- P2a: per pixel (warp), S = Q K^T + (Sk + Sq^T), both 16-frame query tiles
+  const int pix = warp;
+  float s[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt * 16 < T) {
+      const int tq = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, T - 1);
+      const uint32_t qrow = sQ + tq * TSTR + pix * LDSB + (lane >> 4) * 16;
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        uint32_t qa[4];
+        ldsm_x4(qa, qrow + kk * 32);
+#pragma unroll
+        for (int nt = 0; nt + 1 < NT; nt += 2) {
+          const int ts = min(nt * 8 + (lane & 7) + (lane >> 4) * 8, T - 1);
+          uint32_t kb[4];
+          ldsm_x4(kb, sK + ts * TSTR + pix * LDSB + kk * 32 + ((lane >> 3) & 1) * 16);
+          mma16816(s[mt][nt], qa[0], qa[1], qa[2], qa[3], kb[0], kb[1]);
+          mma16816(s[mt][nt + 1], qa[0], qa[1], qa[2], qa[3], kb[2], kb[3]);
+        }
+        if (NT & 1) {
+          const int ts = min((NT - 1) * 8 + (lane & 7), T - 1);
+          uint32_t kb[2];
+          ldsm_x2(kb, sK + ts * TSTR + pix * LDSB + kk * 32 + ((lane >> 3) & 1) * 16);
+          mma16816(s[mt][NT - 1], qa[0], qa[1], qa[2], qa[3], kb[0], kb[1]);
+        }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = mt * 16 + g + half * 8;
+        if (r < T) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const float2 v = lds_f2(sS + pix * RS + (r * TP + nt * 8 + 2 * t4) * 4);
+            s[mt][nt][half * 2] += v.x;
+            s[mt][nt][half * 2 + 1] += v.y;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();     // v has landed; nobody reads the Q / K tiles or S any more
+
+  // ---- P2b: mask, softmax, P -> smem, O = P V -> smem (fp32, over the Q / K tiles)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt * 16 < T) {
+      float inv[2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = mt * 16 + g + half * 8;
+        const bool row_ok = r < T;
+        const float m_r = row_ok ? __ldg(mask + b * T + r) : 0.f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = nt * 8 + 2 * t4 + e;
+            const float m_s = m_col[nt * 2 + e];
+            float al = m_r * m_s;
+            if (pad_interact) al += (1.f - m_r) * (1.f - m_s);
+            else if (col == r) al = 1.f;
+            const float v = (row_ok && col < T && al != 0.f) ? scale * s[mt][nt][half * 2 + e] : -INFINITY;
+            s[mt][nt][half * 2 + e] = v;
+            mx = fmaxf(mx, v);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        if (mx == -INFINITY) mx = 0.f;      // padded query rows: all keys masked
+        float sum = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pexp = __expf(s[mt][nt][half * 2 + e] - mx);
+            s[mt][nt][half * 2 + e] = pexp;
+            sum += pexp;
+          }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        inv[half] = sum > 0.f ? 1.f / sum : 0.f;
+      }
+      uint32_t pk[4][2];                     // bf16 pairs: [key tile][row half]
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          pk[nt][half] = nt < NT ? pack_bf16x2(s[mt][nt][half * 2] * inv[half], s[mt][nt][half * 2 + 1] * inv[half]) : 0u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = mt * 16 + g + half * 8;
+        if (r < T) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) sts_u32(sS + pix * RS + r * 64 + (nt * 8 + 2 * t4) * 2, pk[nt][half]);
+        }
+      }
+      float o[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (kk * 16 < T) {
+          const int ts = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, T - 1);
+          const uint32_t vrow = sV + ts * TSTR + pix * LDSB + (lane >> 4) * 16;
+#pragma unroll
+          for (int nt = 0; nt < HD / 8; nt += 2) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, vrow + nt * 16);
+            mma16816(o[nt], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], vb[0], vb[1]);
+            mma16816(o[nt + 1], pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1], vb[2], vb[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = mt * 16 + g + half * 8;
+        if (r < T) {
+          const uint32_t orow = sO + (uint32_t)(pix * T + r) * (HD * 4) + 2 * t4 * 4;
+          const int sw = (r ^ pix) & 3;
+#pragma unroll
+          for (int nt = 0; nt < HD / 8; ++nt) sts_f2(orow + ((nt ^ sw) * 8) * 4, o[nt][half * 2], o[nt][half * 2 + 1]);
+        }
+      }
+    }
+  }
+  // first R_v unit of this warp: fetched before the barrier
+  const int n3 = T * NG;
+  auto load_b3 = [&](uint4 (&bf)[2], int u) {
+    const int t = u / NG, ng = u - t * NG;
+    const __nv_bfloat16* row = rv + (((size_t)(b * T + t) * heads + h) * HD + ng * 16 + g) * 32 + t4 * 8;
+    bf[0] = ldg128(row);
+    bf[1] = ldg128(row + 8 * 32);
+  };
+  uint4 b3[G3][2];
+  auto load_group3 = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < G3; ++j) {
+      const int u = warp + (k0 + j) * W;
+      if (u < n3) load_b3(b3[j], u);
+    }
+  };
+  load_group3(0);            // in flight across the barrier
+  __syncthreads();
+
+  // ---- P3: out[pix][t][f] = O + P_t . Rv[t]   (rows = pixels)
+  for (int k0 = 0; warp + k0 * W < n3; k0 += G3) {
+    if (k0) load_group3(k0);
+#pragma unroll
+    for (int jj = 0; jj < G3; ++jj) {
+      const int u = warp + (k0 + jj) * W;
+      if (u < n3) {
+        const int t = u / NG, ng = u - t * NG;
+        const uint4 lo = lds128(sS + g * RS + t * 64 + t4 * 16);
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+        if (PT == 16) hi = lds128(sS + (g + 8) * RS + t * 64 + t4 * 16);
+        const int sw = (t ^ g) & 3;
+        __nv_bfloat16* orow = out + ((size_t)(b * T + t) * D + pix0 + g) * C + h * HD + ng * 16 + 2 * t4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(c, lo.x, hi.x, lo.y, hi.y, b3[jj][j].x, b3[jj][j].y);
+          mma16816(c, lo.z, hi.z, lo.w, hi.w, b3[jj][j].z, b3[jj][j].w);
+          const int nt = ng * 2 + j;
+          const uint32_t oa = sO + (uint32_t)(g * T + t) * (HD * 4) + ((nt ^ sw) * 8 + 2 * t4) * 4;
+          const float2 o0 = lds_f2(oa);
+          *reinterpret_cast<uint32_t*>(orow + j * 8) = pack_bf16x2(c[0] + o0.x, c[1] + o0.y);
+          if (PT == 16) {
+            const float2 o1 = lds_f2(oa + (uint32_t)8 * T * (HD * 4));
+            *reinterpret_cast<uint32_t*>(orow + (size_t)8 * C + j * 8) = pack_bf16x2(c[2] + o1.x, c[3] + o1.y);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int HD, int PT, int NT>
+int launch_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask, int pad, int B, int T,
+                 int D, int heads, void* out, cudaStream_t stream) {
+  constexpr int LDSB = FusedCfg<HD>::LDSB, TSTR = PT * LDSB + 16;
+  const size_t smem = (size_t)3 * T * TSTR + (size_t)PT * fused_region_stride(T, NT * 8);
+  if (smem > 227 * 1024) {
+    set_error("attn_temporal_fused: %zu bytes of shared memory (T=%d, head_dim=%d, %d pixels per CTA)", smem, T, HD, PT);
+    return -1;
+  }
+  static PerDevice<size_t> configured;
+  if (configured.get() < smem) {
+    cudaError_t e = cudaFuncSetAttribute(attn_temporal_fused_kernel<HD, PT, NT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("attn_temporal_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured.get() = smem;
+  }
+  launch_kernel(attn_temporal_fused_kernel<HD, PT, NT>, dim3(D / PT, heads, B), PT * 32, smem, stream, 1,
+                (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)rq, (const __nv_bfloat16*)rk, (const __nv_bfloat16*)rv,
+                mask, pad, T, D, heads, (__nv_bfloat16*)out);
+  VDM_AFTER_LAUNCH("attn_temporal_fused");
+  return 0;
+}
+
+template <int HD, int PT>
+int launch_fused_nt(int t_pad, const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask, int pad,
+                    int B, int T, int D, int heads, void* out, cudaStream_t stream) {
+  if (t_pad == 24) return launch_fused<HD, PT, 3>(qkv, rq, rk, rv, mask, pad, B, T, D, heads, out, stream);
+  return launch_fused<HD, PT, 4>(qkv, rq, rk, rv, mask, pad, B, T, D, heads, out, stream);
+}
+
+}  // namespace
+}  // namespace vdm
+
+using namespace vdm;
+
+extern "C" int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t n_blocks,
+                            int64_t r_block_stride, int32_t B, int32_t T, int32_t heads, int32_t hd, int32_t t_pad,
+                            void* rq, void* rk, void* rv, int64_t qk_block_stride, int64_t v_block_stride,
+                            vdm_stream_t stream) {
+  VDM_REQUIRE(r_q && r_k && r_v && rq && rk && rv, "rpe_pack: NULL pointer");
+  VDM_REQUIRE(T >= 1 && T <= 32 && (t_pad == 24 || t_pad == 32) && T <= t_pad, "rpe_pack: T=%d, t_pad=%d unsupported", T,
+              t_pad);
+  VDM_REQUIRE(hd % 8 == 0 && n_blocks >= 1, "rpe_pack: head_dim must be a multiple of 8");
+  const int64_t G = (int64_t)B * T;
+  if (qk_block_stride == 0) qk_block_stride = G * heads * t_pad * hd;
+  if (v_block_stride == 0) v_block_stride = G * heads * hd * 32;
+  launch_kernel(rpe_pack_kernel, dim3((unsigned)G, heads, 3 * n_blocks), 128, 0, (cudaStream_t)stream, 1, r_q, r_k, r_v,
+                bias, (long long)r_block_stride, T, heads, hd, t_pad, (__nv_bfloat16*)rq, (__nv_bfloat16*)rk,
+                (__nv_bfloat16*)rv, (long long)qk_block_stride, (long long)v_block_stride);
+  VDM_AFTER_LAUNCH("rpe_pack");
+  return 0;
+}
+
+extern "C" int64_t vdm_attn_temporal_fused_smem(int32_t T, int32_t hd, int32_t t_pad, int32_t pixels_per_cta) {
+  if (T < 1 || T > 32 || (t_pad != 24 && t_pad != 32) || T > t_pad) return -1;
+  if (hd != 32 && hd != 64 && hd != 96 && hd != 128) return -1;
+  const int pt = pixels_per_cta == 0 ? 8 : pixels_per_cta;
+  if (!(pt == 8 || (pt == 16 && hd == 96))) return -1;
+  const int ldsb = (hd * 2) % 128 == 64 ? hd * 2 : hd * 2 + 64;
+  return (int64_t)3 * T * (pt * ldsb + 16) + (int64_t)pt * fused_region_stride(T, t_pad);
+}
+
+extern "C" int vdm_attn_temporal_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask,
+                                       int32_t allow_pad_interactions, int32_t B, int32_t T, int32_t HW, int32_t heads,
+                                       int32_t hd, int32_t t_pad, int32_t pixels_per_cta, void* out,
+                                       vdm_stream_t stream) {
+  VDM_REQUIRE(qkv && rq && rk && rv && mask && out, "attn_temporal_fused: NULL pointer");
+  VDM_REQUIRE(T >= 1 && T <= 32 && (t_pad == 24 || t_pad == 32) && T <= t_pad,
+              "attn_temporal_fused: T=%d, t_pad=%d unsupported", T, t_pad);
+  int pt = pixels_per_cta;
+  if (pt == 0) pt = 8;
+  VDM_REQUIRE((pt == 8 || (pt == 16 && hd == 96)) && HW % pt == 0,
+              "attn_temporal_fused: %d pixels per CTA unsupported (HW=%d, head_dim=%d)", pt, HW, hd);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = allow_pad_interactions;
+  if (pt == 16) return launch_fused_nt<96, 16>(t_pad, qkv, rq, rk, rv, mask, pad, B, T, HW, heads, out, st);
+  switch (hd) {
+    case 32: return launch_fused_nt<32, 8>(t_pad, qkv, rq, rk, rv, mask, pad, B, T, HW, heads, out, st);
+    case 64: return launch_fused_nt<64, 8>(t_pad, qkv, rq, rk, rv, mask, pad, B, T, HW, heads, out, st);
+    case 96: return launch_fused_nt<96, 8>(t_pad, qkv, rq, rk, rv, mask, pad, B, T, HW, heads, out, st);
+    case 128: return launch_fused_nt<128, 8>(t_pad, qkv, rq, rk, rv, mask, pad, B, T, HW, heads, out, st);
+  }
+  set_error("attn_temporal_fused: head_dim=%d not in {32, 64, 96, 128}", hd);
+  return -1;
+}

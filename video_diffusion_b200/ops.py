@@ -217,6 +217,25 @@ def attn_temporal_tc(qkv, sk, sq, mask, pad_interact, B, T, HW, heads, hd, gpt, 
            nbytes=_nbytes(qkv, sk, sq, pm, pv))
 
 
+def rpe_pack(r_q, r_k, r_v, B, T, heads, hd, t_pad, rq, rk, rv, bias=None, n_blocks=1, r_block_stride=0,
+             qk_block_stride=0, v_block_stride=0):
+    _timed('rpe_pack', lambda: check(_lib.load().vdm_rpe_pack(
+        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, B, T, heads, hd, t_pad, ptr(rq), ptr(rk),
+        ptr(rv), qk_block_stride, v_block_stride, stream()), 'vdm_rpe_pack'), nbytes=_nbytes(rq, rk, rv))
+
+
+def attn_temporal_fused_smem(T, hd, t_pad, pixels_per_cta):
+    """Shared memory (bytes) of the fused temporal kernel for this shape; -1 = not instantiated."""
+    return int(_lib.load().vdm_attn_temporal_fused_smem(T, hd, t_pad, pixels_per_cta))
+
+
+def attn_temporal_fused(qkv, rq, rk, rv, mask, pad_interact, B, T, HW, heads, hd, t_pad, out, pixels_per_cta=0):
+    _timed('attn_temporal_fused', lambda: check(_lib.load().vdm_attn_temporal_fused(
+        ptr(qkv), ptr(rq), ptr(rk), ptr(rv), ptr(mask), int(pad_interact), B, T, HW, heads, hd, t_pad, pixels_per_cta,
+        ptr(out), stream()), 'vdm_attn_temporal_fused'), flops=10.0 * B * HW * heads * T * T * hd,
+           nbytes=_nbytes(qkv, out))
+
+
 def attn_spatial(qkv, n_img, L, heads, hd, out):
     _timed('attn_spatial', lambda: check(_lib.load().vdm_attn_spatial(
         ptr(qkv), dt(qkv.dtype), n_img, L, heads, hd, ptr(out), dt(out.dtype), stream()), 'vdm_attn_spatial'),

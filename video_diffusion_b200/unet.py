@@ -74,6 +74,9 @@ class UNetModel(nn.Module):
         self.bf16_intermediate = True     # bf16 mode: keep ResBlock conv1 outputs in bf16 only
         self.overlap_rpe_tables = True    # RPE tables on a side stream, concurrent with the first U-Net blocks
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
+        # bf16 mode: the whole temporal attention (RPE score terms, q.k^T, softmax, P.V, attn.R_v) as ONE kernel
+        self.fused_temporal = os.environ.get('VDM_FUSED_TEMPORAL', '1') != '0'
+        self.temporal_pixels_per_cta = int(os.environ.get('VDM_TEMPORAL_PT', '0'))   # 0 = heuristic
         # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (transform warps of the halo kernels).  Correct
         # and bit-exact against the standalone pass, but measured SLOWER on B200 (every activation element
         # is re-transformed 4.5 times, which binds on the special-function units and shared-memory bandwidth): off.
@@ -530,6 +533,21 @@ class UNetModel(nn.Module):
         return (self.compute_dtype == torch.bfloat16 and self.temporal_tensor_cores and heads * T <= 128 and T <= 32
                 and C // heads in (32, 64, 96, 128) and (HW % 128 == 0 or HW == 64))
 
+    def _temporal_pt(self, T, C, HW):
+        """Pixels per CTA of the fused temporal kernel (0 = the shape does not fit it): 16 halves the R-table traffic
+        from L2 (hd = 96 only: larger heads do not fit 16-pixel tiles of q, k, v in shared memory), else 8."""
+        if not (self.compute_dtype == torch.bfloat16 and self.fused_temporal and T <= 32):
+            return 0
+        hd, TP = C // self.num_heads, 24 if T <= 24 else 32
+        want = self.temporal_pixels_per_cta or (16 if hd == 96 else 8)
+        for pt in (want, 8):
+            if HW % pt == 0 and 0 < ops.attn_temporal_fused_smem(T, hd, TP, pt) <= 227 * 1024:
+                return pt
+        return 0
+
+    def _fused_temporal_ok(self, T, C, HW):
+        return self._temporal_pt(T, C, HW) != 0
+
     def _rpe_tables(self, ws, rpe_et, B, T, H, W):
         """RPE tables of every temporal-attention block, batched: the blocks that share (C, HW) go through ONE
         rpe_hidden launch, ONE grouped output-layer GEMM and ONE expansion into the per-(b, t) GEMM operands
@@ -546,7 +564,8 @@ class UNetModel(nn.Module):
                 h, w = h // 2, w // 2
             elif node['kind'] == 'up':
                 h, w = 2 * h, 2 * w
-            elif node['kind'] == 'attn' and self._tc_temporal_ok(T, node['C'], h * w):
+            elif node['kind'] == 'attn' and (self._tc_temporal_ok(T, node['C'], h * w)
+                                             or self._fused_temporal_ok(T, node['C'], h * w)):
                 groups.setdefault((node['C'], h * w), []).append(node)
         for (C, HW), nodes in groups.items():
             nb, key = len(nodes), f'rpe_group.{C}.{HW}'
@@ -563,6 +582,18 @@ class UNetModel(nn.Module):
             Rall = ws.buf(key + '.R', (nb * 3 * rows, C))
             ops.gemm(hid, P[key + '.out_w'], C, n_img=nb * 3 * rows, H=1, W=1, taps=1, out_f32=Rall,
                      w_group_tiles=rows // 128)
+            if self._fused_temporal_ok(T, C, HW):
+                # fused kernel: compact bf16 tables [q, k][(b, t)][head][t_pad][hd] and [(b, t)][head][hd][32]
+                TP, hd = (24 if T <= 24 else 32), C // heads
+                per = B * T * heads * TP * hd
+                rqk = ws.buf(key + '.rqk', (nb, 2, per), adt)
+                rvp = ws.buf(key + '.rvp', (nb, B * T * heads * hd * 32), adt)
+                ops.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, TP, rqk[0, 0],
+                             rqk[0, 1], rvp, bias=P[key + '.out_b'], n_blocks=nb, r_block_stride=3 * rows * C,
+                             qk_block_stride=2 * per)
+                for i, n in enumerate(nodes):
+                    tables[n['p']] = ('fused', rqk[i], rvp[i])
+                continue
             gpt = 1 if HW >= 128 else 128 // HW
             SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
             # the operands are block-diagonal over heads (~85 % structural zeros): zeroed once with the workspace,
@@ -610,7 +641,25 @@ class UNetModel(nn.Module):
                          out_f32=Rn)
                 R.append(Rn)
         att = ws.buf(q + '.att', (M, C), adt)
-        if tc_path:
+        fused = self._fused_temporal_ok(T, C, HW)
+        if fused:
+            # ONE kernel between the qkv projection and proj_out (csrc/attention_temporal_fused.cu)
+            TP = 24 if T <= 24 else 32
+            qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
+            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            if pre is not None:
+                # tables of the FULL batch; a micro-batch starts at its first (b, t) group
+                g0 = tables.get('__group0__', 0)
+                rq, rk = pre[1][0][g0 * heads * TP * hd:], pre[1][1][g0 * heads * TP * hd:]
+                rvp = pre[2][g0 * heads * hd * 32:]
+            else:
+                rqk = ws.buf(q + '.rqk', (2, N * heads * TP * hd), adt)
+                rvp = ws.buf(q + '.rvp', (N * heads * hd * 32,), adt)
+                ops.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rqk[0], rqk[1], rvp)
+                rq, rk = rqk[0], rqk[1]
+            ops.attn_temporal_fused(qkv, rq, rk, rvp, amask, self.allow_interactions_between_padding, B, T, HW, heads,
+                                    hd, TP, att, pixels_per_cta=self._temporal_pt(T, C, HW))
+        elif tc_path:
             # RPE terms as pixel-batched GEMMs with per-(b, t) weight groups, the rest on mma.sync
             gpt = 1 if HW >= 128 else 128 // HW          # (b, t) groups per 128-row tile
             tpg = max(1, HW // 128)                      # 128-row tiles per group
