@@ -295,6 +295,9 @@ int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v, const flo
 /* Dynamic shared memory (bytes) the fused kernel needs for this shape, or -1 if the shape is not instantiated; the
  * launch fails above 227 KB (the host mirror falls back to the three-launch path there). */
 int64_t vdm_attn_temporal_fused_smem(int32_t T, int32_t hd, int32_t t_pad, int32_t pixels_per_cta);
+/* Diagnostics: buf = 8 device uint64 counters (NULL = off).  Thread 0 of every CTA adds the cycles it spent in the six
+ * phases of the kernel (staging wait, P1a, P1b, P2a, P2b, P3) to buf[0..5] and 1 to buf[7]. */
+void vdm_attn_temporal_fused_set_trace(void* buf);
 int vdm_attn_temporal_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask,
                             int32_t allow_pad_interactions, int32_t B, int32_t T, int32_t HW, int32_t heads,
                             int32_t hd, int32_t t_pad, int32_t pixels_per_cta, void* out, vdm_stream_t stream);

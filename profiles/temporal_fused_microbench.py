@@ -56,6 +56,18 @@ def main():
             row[f'fused_pt{pt}_us'] = time_graph(
                 lambda i: o.attn_temporal_fused(qkvs[i], rq, rk, rv, mask, True, B, T, HW, heads, hd, TP, atts[i],
                                                 pixels_per_cta=pt), n_bufs=nb)
+        # per-phase cycles of thread 0, averaged over the CTAs of one launch (vdm_attn_temporal_fused_set_trace)
+        from video_diffusion_b200 import _lib
+        tr = torch.zeros(8, device='cuda', dtype=torch.int64)
+        _lib.load().vdm_attn_temporal_fused_set_trace(tr.data_ptr())
+        for pt in ((8, 16) if hd == 96 else (8,)):
+            tr.zero_()
+            o.attn_temporal_fused(qkvs[0], rq, rk, rv, mask, True, B, T, HW, heads, hd, TP, atts[0], pixels_per_cta=pt)
+            torch.cuda.synchronize()
+            c = tr.cpu().tolist()
+            row[f'phase_cycles_pt{pt}'] = dict(zip(('stage_wait', 'p1a', 'p1b', 'p2a', 'p2b', 'p3'),
+                                                   [round(v / max(c[7], 1)) for v in c[:6]]), ctas=c[7])
+        _lib.load().vdm_attn_temporal_fused_set_trace(None)
         row['rpe_pack_us'] = time_graph(lambda i: o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rq, rk, rv))
         # the three-launch path
         gpt, tpg = (1, HW // 128) if HW >= 128 else (128 // HW, 1)

@@ -981,7 +981,7 @@ def test_rpe_pack_batched_over_blocks_and_unsupported_shapes():
     with pytest.raises(RuntimeError, match='t_pad'):
         o.attn_temporal_fused(qkv, rqk[0, 0], rqk[0, 1], rvp[0], mask, True, B, 33, 8, heads, hd, 32, out)
     # shapes beyond the 227 KB of shared memory are reported, the model falls back to the three-launch path for them
-    assert o.attn_temporal_fused_smem(20, 96, 24, 8) == 3 * 20 * (8 * 192 + 16) + 8 * 1952
+    assert o.attn_temporal_fused_smem(20, 96, 24, 8) == 3 * 20 * (8 * 192 + 16) + 8 * 1952 + 32
     assert o.attn_temporal_fused_smem(32, 128, 32, 8) > 227 * 1024 and o.attn_temporal_fused_smem(20, 128, 24, 16) == -1
 
 

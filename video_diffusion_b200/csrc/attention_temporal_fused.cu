@@ -19,13 +19,15 @@
 // values for TWO k-steps are 16 contiguous bytes (the contraction index is permuted identically on the A side, which
 // is read from shared memory with the same 16-byte pattern), and the next unit's fragments are prefetched into
 // registers while the current unit runs.
+#include <cstdio>
+
 #include "common.cuh"
 
 #ifndef VDM_TF_G1
-#define VDM_TF_G1 4
+#define VDM_TF_G1 3
 #endif
 #ifndef VDM_TF_G3
-#define VDM_TF_G3 8
+#define VDM_TF_G3 4
 #endif
 
 namespace vdm {
@@ -50,8 +52,34 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void cp16(uint32_t smem_addr, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 2000000000LL) {   // ~1 s: a protocol bug must fail loudly, never hang the box
+      printf("vdm attn_temporal_fused: bulk copies never completed (block %d %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+      __trap();
+    }
+  }
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_copy(uint32_t smem_addr, const void* gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr),
+               "l"(gmem), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
@@ -141,13 +169,13 @@ __global__ void __launch_bounds__(128) rpe_pack_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- the fused block
-// grid = (HW / PT, heads, B); PT warps (warp = pixel in the per-pixel phases).
+// grid = (heads, HW / PT, B); PT warps (warp = pixel in the per-pixel phases).
 template <int HD, int PT, int NT>
 __global__ void __launch_bounds__(PT * 32, (PT == 8 && HD <= 96) ? 2 : 1)
 attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ rq,
                            const __nv_bfloat16* __restrict__ rk, const __nv_bfloat16* __restrict__ rv,
                            const float* __restrict__ mask, int pad_interact, int T, int D, int heads,
-                           __nv_bfloat16* __restrict__ out) {
+                           __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ trace) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
   constexpr int LDSB = FusedCfg<HD>::LDSB, KP = HD / 32, TP = NT * 8, W = PT, NTH = PT * 32;
@@ -156,29 +184,45 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
   constexpr int G1 = VDM_TF_G1, G3 = VDM_TF_G3;   // units whose R fragments are requested together
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-  const int pix0 = blockIdx.x * PT, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, pix0 = blockIdx.y * PT, b = blockIdx.z;   // the heads of a pixel tile run side by side
   const int C = heads * HD;
   const uint32_t tensor_bytes = (uint32_t)T * TSTR;
   const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t sK = sQ + tensor_bytes, sV = sK + tensor_bytes, sS = sV + tensor_bytes, sO = sQ;
   const int RS = fused_region_stride(T, TP);
   const float scale = rsqrtf((float)HD);
-
-  // ---- stage q, k (group 0) and v (group 1): rows (frame, pixel), HD bf16 each
-  {
-    constexpr int CH = HD / 8;
-    const int n = T * PT * CH;
-    for (int which = 0; which < 3; ++which) {
-      const uint32_t dstb = which == 0 ? sQ : (which == 1 ? sK : sV);
-      for (int idx = tid; idx < n; idx += NTH) {
-        const int r = idx / CH, c = idx - r * CH;
-        const int t = r / PT, p = r - t * PT;
-        const __nv_bfloat16* src = qkv + ((size_t)(b * T + t) * D + pix0 + p) * (3 * C) + which * C + h * HD + c * 8;
-        cp16(dstb + t * TSTR + p * LDSB + c * 16, src);
-      }
-      if (which == 1) asm volatile("cp.async.commit_group;" ::: "memory");
+  // diagnostics (vdm_attn_temporal_fused_set_trace): cycles per phase, summed over CTAs by thread 0; the last time stamp
+  // lives in shared memory (behind the two barriers), not in a register
+  const uint32_t tr_slot = sS + (uint32_t)PT * RS + 16;
+  auto tr_mark = [&](int slot) {
+    if (trace != nullptr && threadIdx.x == 0) {
+      const unsigned long long now = (unsigned long long)clock64();
+      unsigned long long prev;
+      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(prev) : "r"(tr_slot));
+      if (slot >= 0) atomicAdd(trace + slot, now - prev);
+      asm volatile("st.shared.u64 [%0], %1;" ::"r"(tr_slot), "l"(now) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  tr_mark(-1);
+
+  // ---- stage q, k (barrier 0) and v (barrier 1): one bulk copy per (frame, pixel) row of HD bf16
+  const uint32_t bar_qk = sS + (uint32_t)PT * RS, bar_v = bar_qk + 8;
+  if (tid == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar_qk, 2u * T * PT * HD * 2);
+    mbar_expect_tx(bar_v, (uint32_t)T * PT * HD * 2);
+  }
+  __syncthreads();
+  {
+    const int rows = T * PT;
+    for (int idx = tid; idx < 3 * rows; idx += NTH) {
+      const int which = idx / rows, r = idx - which * rows;
+      const int t = r / PT, p = r - t * PT;
+      const __nv_bfloat16* src = qkv + ((size_t)(b * T + t) * D + pix0 + p) * (3 * C) + which * C + h * HD;
+      bulk_copy(sQ + which * tensor_bytes + t * TSTR + p * LDSB, src, HD * 2, which == 2 ? bar_v : bar_qk);
+    }
   }
 
   // ---- P1: RPE score terms over the pixels of the tile.  Unit u = (frame i, 8-column tile nt).
@@ -200,66 +244,77 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       mma16816(c, lo.z, hi.z, lo.w, hi.w, bf[p].z, bf[p].w);
     }
   };
-  // The fragments of G1 units are requested together (G1 * KP 16-byte loads in flight per lane): a unit is a handful
-  // of mma, so what a warp waits for is the L2 round trip, once per group instead of once per unit.
-  uint4 bf[G1][KP];
-  auto load_group1 = [&](const __nv_bfloat16* tab, int k0) {
+  // The fragments of G1 units are requested together (G1 * KP 16-byte loads in flight per lane), and the next group's
+  // while the current one is multiplied (two register buffers): a unit is a handful of mma, what a warp would wait for
+  // is the L2 round trip.  Jobs 0 .. NG1-1 are the Sk groups, NG1 .. 2 NG1 - 1 the Sq groups; every warp runs the same
+  // number of jobs -- units past the end of its list are clamped to the last unit (loaded and multiplied like the
+  // others, so the G1 independent mma chains of a group interleave without branches; only the stores are predicated).
+  const int NG1 = (n1 + W * G1 - 1) / (W * G1);
+  uint4 bfA[G1][KP], bfB[G1][KP];
+  auto load_job1 = [&](uint4 (&bf)[G1][KP], int job) {
+    const __nv_bfloat16* tab = job < NG1 ? rk : rq;
+    const int k0 = (job < NG1 ? job : job - NG1) * G1;
+#pragma unroll
+    for (int j = 0; j < G1; ++j) load_b1(bf[j], tab, min(warp + (k0 + j) * W, n1 - 1));
+  };
+  auto run_job1 = [&](const uint4 (&bf)[G1][KP], int job) {
+    const bool second = job >= NG1;           // Sq: A = K tile, read-modify-write of the transposed element
+    const int k0 = (second ? job - NG1 : job) * G1;
+    const uint32_t a_tensor = second ? sK : sQ;
+    float c[G1][4];
+#pragma unroll
+    for (int j = 0; j < G1; ++j) {
+      const int i = min(warp + (k0 + j) * W, n1 - 1) / NT;
+      mma_unit1(c[j], bf[j], a_tensor + i * TSTR + g * LDSB + t4 * 16);
+    }
 #pragma unroll
     for (int j = 0; j < G1; ++j) {
       const int u = warp + (k0 + j) * W;
-      if (u < n1) load_b1(bf[j], tab, u);
+      if (u < n1) {
+        const int i = u / NT, nt = u - i * NT;
+        if (!second) {        // Sk[pix][i][s] = Q_i . Rk[i][s]: every element of S is written exactly once
+          const uint32_t a = sS + g * RS + (i * TP + nt * 8 + 2 * t4) * 4;
+          sts_f2(a, c[j][0], c[j][1]);
+          if (PT == 16) sts_f2(a + 8 * RS, c[j][2], c[j][3]);
+        } else {              // S[pix][t'][i] += K_i . Rq[i][t']
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tq = nt * 8 + 2 * t4 + e;
+            if (tq < T) {
+              const uint32_t a = sS + g * RS + (tq * TP + i) * 4;
+              sts_f(a, lds_f(a) + c[j][e]);
+              if (PT == 16) sts_f(a + 8 * RS, lds_f(a + 8 * RS) + c[j][2 + e]);
+            }
+          }
+        }
+      }
     }
   };
-  load_group1(rk, 0);
-  // mask values of this lane's key columns (P2b), fetched while the copies are in flight
-  float m_col[NT * 2];
+  load_job1(bfA, 0);
+  // mask values of this lane's key columns and query rows (P2b), fetched while the copies are in flight
+  float m_col[NT * 2], m_row[4];
 #pragma unroll
   for (int j = 0; j < NT * 2; ++j) {
     const int col = (j >> 1) * 8 + 2 * t4 + (j & 1);
     m_col[j] = col < T ? __ldg(mask + b * T + col) : 0.f;
   }
-  asm volatile("cp.async.wait_group 1;" ::: "memory");
-  __syncthreads();
-  // P1a: Sk[pix][i][s] = Q_i . Rk[i][s]   (plain store: every element of S is written exactly once)
-  for (int k0 = 0; warp + k0 * W < n1; k0 += G1) {
-    if (k0) load_group1(rk, k0);
 #pragma unroll
-    for (int j = 0; j < G1; ++j) {
-      const int u = warp + (k0 + j) * W;
-      if (u < n1) {
-        const int i = u / NT, nt = u - i * NT;
-        float c[4];
-        mma_unit1(c, bf[j], sQ + i * TSTR + g * LDSB + t4 * 16);
-        const uint32_t a = sS + g * RS + (i * TP + nt * 8 + 2 * t4) * 4;
-        sts_f2(a, c[0], c[1]);
-        if (PT == 16) sts_f2(a + 8 * RS, c[2], c[3]);
-      }
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int r = (j >> 1) * 16 + g + (j & 1) * 8;
+    m_row[j] = r < T ? __ldg(mask + b * T + r) : 0.f;
   }
-  load_group1(rq, 0);        // in flight across the barrier
-  __syncthreads();
-  // P1b: S[pix][t'][i] += K_i . Rq[i][t']
-  for (int k0 = 0; warp + k0 * W < n1; k0 += G1) {
-    if (k0) load_group1(rq, k0);
-#pragma unroll
-    for (int j = 0; j < G1; ++j) {
-      const int u = warp + (k0 + j) * W;
-      if (u < n1) {
-        const int i = u / NT, nt = u - i * NT;
-        float c[4];
-        mma_unit1(c, bf[j], sK + i * TSTR + g * LDSB + t4 * 16);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int tq = nt * 8 + 2 * t4 + e;
-          if (tq < T) {
-            const uint32_t a = sS + g * RS + (tq * TP + i) * 4;
-            sts_f(a, lds_f(a) + c[e]);
-            if (PT == 16) sts_f(a + 8 * RS, lds_f(a + 8 * RS) + c[2 + e]);
-          }
-        }
-      }
-    }
+  mbar_wait(bar_qk, 0);
+  tr_mark(0);
+  for (int job = 0; job < 2 * NG1; job += 2) {       // (2 NG1 jobs: always an even number)
+    load_job1(bfB, job + 1);
+    if (job == NG1) __syncthreads();                  // all of Sk is stored before the first Sq unit adds to it
+    run_job1(bfA, job);
+    if (job + 2 < 2 * NG1) load_job1(bfA, job + 2);
+    if (job + 1 == NG1) __syncthreads();
+    run_job1(bfB, job + 1);
+    if (job + 2 == NG1) tr_mark(1);
   }
+  tr_mark(2);
   __syncthreads();
 
   // ---- P2a: per pixel (warp), S = Q K^T + (Sk + Sq^T), both 16-frame query tiles
@@ -307,8 +362,9 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       }
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();     // v has landed; nobody reads the Q / K tiles or S any more
+  tr_mark(3);
+  __syncthreads();     // nobody reads the Q / K tiles or S any more
+  mbar_wait(bar_v, 0);
 
   // ---- P2b: mask, softmax, P -> smem, O = P V -> smem (fp32, over the Q / K tiles)
 #pragma unroll
@@ -319,7 +375,7 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       for (int half = 0; half < 2; ++half) {
         const int r = mt * 16 + g + half * 8;
         const bool row_ok = r < T;
-        const float m_r = row_ok ? __ldg(mask + b * T + r) : 0.f;
+        const float m_r = m_row[mt * 2 + half];
         float mx = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -401,54 +457,70 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
     bf[0] = ldg128(row);
     bf[1] = ldg128(row + 8 * 32);
   };
-  uint4 b3[G3][2];
-  auto load_group3 = [&](int k0) {
+  const int NG3 = (n3 + W * G3 - 1) / (W * G3);
+  uint4 b3A[G3][2], b3B[G3][2];
+  auto load_job3 = [&](uint4 (&bf)[G3][2], int job) {
 #pragma unroll
-    for (int j = 0; j < G3; ++j) {
-      const int u = warp + (k0 + j) * W;
-      if (u < n3) load_b3(b3[j], u);
-    }
+    for (int j = 0; j < G3; ++j) load_b3(bf[j], min(warp + (job * G3 + j) * W, n3 - 1));
   };
-  load_group3(0);            // in flight across the barrier
-  __syncthreads();
-
-  // ---- P3: out[pix][t][f] = O + P_t . Rv[t]   (rows = pixels)
-  for (int k0 = 0; warp + k0 * W < n3; k0 += G3) {
-    if (k0) load_group3(k0);
+  // out[pix][t][f] = O + P_t . Rv[t]   (rows = pixels)
+  auto run_job3 = [&](const uint4 (&bf)[G3][2], int job) {
+    float c[G3][2][4];
 #pragma unroll
     for (int jj = 0; jj < G3; ++jj) {
-      const int u = warp + (k0 + jj) * W;
+      const int t = min(warp + (job * G3 + jj) * W, n3 - 1) / NG;
+      const uint4 lo = lds128(sS + g * RS + t * 64 + t4 * 16);
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+      if (PT == 16) hi = lds128(sS + (g + 8) * RS + t * 64 + t4 * 16);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        c[jj][j][0] = c[jj][j][1] = c[jj][j][2] = c[jj][j][3] = 0.f;
+        mma16816(c[jj][j], lo.x, hi.x, lo.y, hi.y, bf[jj][j].x, bf[jj][j].y);
+        mma16816(c[jj][j], lo.z, hi.z, lo.w, hi.w, bf[jj][j].z, bf[jj][j].w);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < G3; ++jj) {
+      const int u = warp + (job * G3 + jj) * W;
       if (u < n3) {
         const int t = u / NG, ng = u - t * NG;
-        const uint4 lo = lds128(sS + g * RS + t * 64 + t4 * 16);
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-        if (PT == 16) hi = lds128(sS + (g + 8) * RS + t * 64 + t4 * 16);
         const int sw = (t ^ g) & 3;
         __nv_bfloat16* orow = out + ((size_t)(b * T + t) * D + pix0 + g) * C + h * HD + ng * 16 + 2 * t4;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c, lo.x, hi.x, lo.y, hi.y, b3[jj][j].x, b3[jj][j].y);
-          mma16816(c, lo.z, hi.z, lo.w, hi.w, b3[jj][j].z, b3[jj][j].w);
           const int nt = ng * 2 + j;
           const uint32_t oa = sO + (uint32_t)(g * T + t) * (HD * 4) + ((nt ^ sw) * 8 + 2 * t4) * 4;
           const float2 o0 = lds_f2(oa);
-          *reinterpret_cast<uint32_t*>(orow + j * 8) = pack_bf16x2(c[0] + o0.x, c[1] + o0.y);
+          *reinterpret_cast<uint32_t*>(orow + j * 8) = pack_bf16x2(c[jj][j][0] + o0.x, c[jj][j][1] + o0.y);
           if (PT == 16) {
             const float2 o1 = lds_f2(oa + (uint32_t)8 * T * (HD * 4));
-            *reinterpret_cast<uint32_t*>(orow + (size_t)8 * C + j * 8) = pack_bf16x2(c[2] + o1.x, c[3] + o1.y);
+            *reinterpret_cast<uint32_t*>(orow + (size_t)8 * C + j * 8) =
+                pack_bf16x2(c[jj][j][2] + o1.x, c[jj][j][3] + o1.y);
           }
         }
       }
     }
+  };
+  load_job3(b3A, 0);            // in flight across the barrier
+  tr_mark(4);
+  __syncthreads();
+  for (int job = 0; job < NG3; job += 2) {
+    if (job + 1 < NG3) load_job3(b3B, job + 1);
+    run_job3(b3A, job);
+    if (job + 2 < NG3) load_job3(b3A, job + 2);
+    if (job + 1 < NG3) run_job3(b3B, job + 1);
   }
+  tr_mark(5);
+  if (trace != nullptr && threadIdx.x == 0) atomicAdd(trace + 7, 1ULL);
 }
+
+static unsigned long long* g_tf_trace = nullptr;
 
 template <int HD, int PT, int NT>
 int launch_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask, int pad, int B, int T,
                  int D, int heads, void* out, cudaStream_t stream) {
   constexpr int LDSB = FusedCfg<HD>::LDSB, TSTR = PT * LDSB + 16;
-  const size_t smem = (size_t)3 * T * TSTR + (size_t)PT * fused_region_stride(T, NT * 8);
+  const size_t smem = (size_t)3 * T * TSTR + (size_t)PT * fused_region_stride(T, NT * 8) + 32;
   if (smem > 227 * 1024) {
     set_error("attn_temporal_fused: %zu bytes of shared memory (T=%d, head_dim=%d, %d pixels per CTA)", smem, T, HD, PT);
     return -1;
@@ -463,9 +535,9 @@ int launch_fused(const void* qkv, const void* rq, const void* rk, const void* rv
     }
     configured.get() = smem;
   }
-  launch_kernel(attn_temporal_fused_kernel<HD, PT, NT>, dim3(D / PT, heads, B), PT * 32, smem, stream, 1,
+  launch_kernel(attn_temporal_fused_kernel<HD, PT, NT>, dim3(heads, D / PT, B), PT * 32, smem, stream, 1,
                 (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)rq, (const __nv_bfloat16*)rk, (const __nv_bfloat16*)rv,
-                mask, pad, T, D, heads, (__nv_bfloat16*)out);
+                mask, pad, T, D, heads, (__nv_bfloat16*)out, g_tf_trace);
   VDM_AFTER_LAUNCH("attn_temporal_fused");
   return 0;
 }
@@ -500,13 +572,15 @@ extern "C" int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v
   return 0;
 }
 
+extern "C" void vdm_attn_temporal_fused_set_trace(void* buf) { g_tf_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 extern "C" int64_t vdm_attn_temporal_fused_smem(int32_t T, int32_t hd, int32_t t_pad, int32_t pixels_per_cta) {
   if (T < 1 || T > 32 || (t_pad != 24 && t_pad != 32) || T > t_pad) return -1;
   if (hd != 32 && hd != 64 && hd != 96 && hd != 128) return -1;
   const int pt = pixels_per_cta == 0 ? 8 : pixels_per_cta;
   if (!(pt == 8 || (pt == 16 && hd == 96))) return -1;
   const int ldsb = (hd * 2) % 128 == 64 ? hd * 2 : hd * 2 + 64;
-  return (int64_t)3 * T * (pt * ldsb + 16) + (int64_t)pt * fused_region_stride(T, t_pad);
+  return (int64_t)3 * T * (pt * ldsb + 16) + (int64_t)pt * fused_region_stride(T, t_pad) + 32;
 }
 
 extern "C" int vdm_attn_temporal_fused(const void* qkv, const void* rq, const void* rk, const void* rv, const float* mask,

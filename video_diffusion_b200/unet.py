@@ -88,6 +88,11 @@ class UNetModel(nn.Module):
         self.stream_dtype = torch.float16
         # bf16 mode: the U-Net body runs on this many groups of videos in parallel streams (see _body_split)
         self.micro_batches = int(os.environ.get('VDM_MICRO_BATCHES', '2'))
+        # opt-in (VDM_MB_JOIN_HW=256): micro-batches join at or below this many pixels per image -- the 16x16 / 8x8
+        # levels then run on the whole batch (their GEMMs are short: half a batch leaves the last wave of tiles nearly
+        # empty), the 64x64 / 32x32 levels per group.  Measured slower than splitting everywhere (12.75-12.83 vs
+        # 12.55-12.67 ms, profiles/bench_r3d_*): what the second stream hides at the small levels is worth more
+        self.micro_batch_join_hw = int(os.environ.get('VDM_MB_JOIN_HW', '0'))
         self.identity_res_min_hw = int(os.environ.get('VDM_IDENTITY_RES_MIN_HW', '4096'))   # x + h as an identity K range from this H*W on
         self.pipeline_norm = os.environ.get('VDM_PIPELINE_NORM', '0') != '0'     # out_layers GroupNorm-apply beside conv1
         # proj_out's residual as an identity K range (like conv2 at 64x64): measured SLOWER (0.84 vs 0.71 ms for the 22
@@ -357,6 +362,7 @@ class UNetModel(nn.Module):
             """parent / lo: this is the workspace of one micro-batch (videos lo .. lo+B of the parent's batch): its
             inputs and output are views of the parent's, everything else (activations, statistics) is its own."""
             self.B, self.F, self.H, self.W, self.dev = B, F, H, W, dev
+            self.parent, self.lo = parent, lo
             self.bufs = {}
             self.flags = {}          # per-shape dispatch decisions (e.g. which convs take the fused normalisation)
             self.graph = None
@@ -377,7 +383,7 @@ class UNetModel(nn.Module):
             else:
                 self.fi, self.fi_float = parent.fi[lo:lo + B], parent.fi_float[lo:lo + B]
                 self.out = parent.out[lo:lo + B]
-                self.stream, self.done = torch.cuda.Stream(device=dev), torch.cuda.Event()
+                self.stream, self.done, self.done2 = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
             self.children, self.mb_fork = [], None
             self.stat_bufs = {}
             self.pool = torch.zeros(stat_capacity, device=dev, dtype=torch.int64)
@@ -836,36 +842,104 @@ class UNetModel(nn.Module):
                 ws.children.append(self._Workspace(Bm, F, H, W, ws.dev, ws.pool.numel() // n_mb + 64, parent=ws,
                                                    lo=k * Bm))
             ws.mb_fork = torch.cuda.Event()
+            ws.mb_fork2 = torch.cuda.Event()
         main = torch.cuda.current_stream()
         ws.mb_fork.record(main)
         rows_img = H * W
+        first, last = self._deep_range(H, W)
+        subs = []
         for k, child in enumerate(ws.children):
             lo, hi = k * Bm * F, (k + 1) * Bm * F
-            sub = dict(a_in=pro['a_in'][lo * rows_img:hi * rows_img], amask=pro['amask'][lo:hi],
-                       emb_out=pro['emb_out'][lo:hi],
-                       rpe_et=None if pro['rpe_et'] is None else pro['rpe_et'][lo:hi],
-                       tables=pro['tables'], table_group0=lo)
+            subs.append(dict(a_in=pro['a_in'][lo * rows_img:hi * rows_img], amask=pro['amask'][lo:hi],
+                             emb_out=pro['emb_out'][lo:hi],
+                             rpe_et=None if pro['rpe_et'] is None else pro['rpe_et'][lo:hi],
+                             tables=pro['tables'], table_group0=lo))
+        if first is None:
+            for child, sub in zip(ws.children, subs):
+                child.stream.wait_event(ws.mb_fork)
+                with torch.cuda.stream(child.stream):
+                    child.zero_stats()
+                    child.emb_join, child.rpe_join = emb_join, rpe_join
+                    self._body(child, sub, T_attn, None)
+                    child.done.record(child.stream)
+            for child in ws.children:
+                main.wait_event(child.done)
+            return
+        # phase A, per group: input conv .. the downsample that enters the joined levels (its output and statistics are
+        # row ranges of the parent's buffers)
+        states = []
+        for child, sub in zip(ws.children, subs):
             child.stream.wait_event(ws.mb_fork)
             with torch.cuda.stream(child.stream):
                 child.zero_stats()
                 child.emb_join, child.rpe_join = emb_join, rpe_join
-                self._body(child, sub, T_attn, None)
+                states.append(self._body(child, sub, T_attn, None, stop=first + 1, share=first))
                 child.done.record(child.stream)
         for child in ws.children:
             main.wait_event(child.done)
+        # phase B, whole batch on the main stream: the joined levels
+        st0 = states[0]
+        full = ws.bufs[st0['shared_name']]
+        full_st = ws.stat_bufs.get(st0['shared_name'] + '.st')
+        state = dict(st0, hs=[], x=(full, full_st))
+        ws.emb_join, ws.rpe_join = emb_join, rpe_join
+        state = self._body(ws, pro, T_attn, None, start=first + 1, stop=last, state=state)
+        assert not state['hs']
+        ws.mb_fork2.record(main)
+        # phase C, per group again: from the upsample that leaves the joined levels to the output head
+        xb, hw = state['x'], state['H'] * state['W']
+        for k, (child, sub) in enumerate(zip(ws.children, subs)):
+            lo, hi = k * Bm * F, (k + 1) * Bm * F
+            st = dict(states[k], x=(xb[0][lo * hw:hi * hw], None if xb[1] is None else xb[1][lo:hi]),
+                      cur_group=state['cur_group'], in_groups=state['in_groups'],
+                      n_groups_done=state['n_groups_done'], H=state['H'], W=state['W'])
+            child.stream.wait_event(ws.mb_fork2)
+            with torch.cuda.stream(child.stream):
+                self._body(child, sub, T_attn, None, start=last, state=st)
+                child.done2.record(child.stream)
+        for child in ws.children:
+            main.wait_event(child.done2)
 
-    def _body(self, ws, pro, T_attn, attn_log):
-        """input conv -> ... -> output head for the videos of `ws` (the whole batch or one micro-batch)."""
+    def _deep_range(self, H, W):
+        """(index of the downsample whose output has <= micro_batch_join_hw pixels, index of the upsample that leaves
+        those levels), or (None, None) when the micro-batches never join."""
+        first = last = None
+        if self.micro_batch_join_hw <= 0:
+            return first, last
+        h, w = H, W
+        for i, node in enumerate(self.plan):
+            if node['kind'] == 'down':
+                h, w = h // 2, w // 2
+                if first is None and h * w <= self.micro_batch_join_hw:
+                    first = i
+            elif node['kind'] == 'up':
+                if first is not None and h * w <= self.micro_batch_join_hw < 4 * h * w:
+                    last = i
+                h, w = 2 * h, 2 * w
+        if first is None or last is None or last <= first + 1:
+            return None, None
+        return first, last
+
+    def _body(self, ws, pro, T_attn, attn_log, start=0, stop=None, state=None, share=None):
+        """input conv -> ... -> output head for the videos of `ws` (the whole batch or one micro-batch).  The plan can
+        be run in pieces (micro-batches that join for the small levels, see _body_split): nodes [start, stop), the
+        traversal state handed on as a dict; `share` = index of a downsample whose output lives in the PARENT's buffers
+        (this group's row range of them)."""
         P, adt = self._packed, self.compute_dtype
         B, F, H, W = ws.B, ws.F, ws.H, ws.W
         N, ch = B * F, self.model_channels
         a_in, amask, emb_out, rpe_et = pro['a_in'], pro['amask'], pro['emb_out'], pro['rpe_et']
         tables = dict(pro['tables'])
         tables['__group0__'] = pro.get('table_group0', 0)
+        stop = len(self.plan) if stop is None else stop
+        shared_name = None
 
         # activations travel as (tensor, per-channel GroupNorm statistics or None)
         hs, x, cur_group, n_groups_done = [], None, None, 0
         in_groups = True
+        if state is not None:
+            hs, x, cur_group, n_groups_done = state['hs'], state['x'], state['cur_group'], state['n_groups_done']
+            in_groups, H, W = state['in_groups'], state['H'], state['W']
 
         def close_group():
             nonlocal x, n_groups_done
@@ -882,7 +956,8 @@ class UNetModel(nn.Module):
                     ops.add_spatial_encoding(x[0], P.get('enc'), hn, N, H * W, x[0].shape[1], frame_emb=femb)
                     x = (hn, None)
 
-        for node in self.plan:
+        for idx in range(start, stop):
+            node = self.plan[idx]
             if node['group'] != cur_group:
                 if cur_group is not None:
                     close_group()
@@ -907,14 +982,24 @@ class UNetModel(nn.Module):
                 x = self._attention(ws, node, x, B, F, H, W, rpe_et, amask, tables, attn_log)
             elif kind == 'down':
                 C = node['C']
-                out = ws.buf(p + '.out', (N * (H // 2) * (W // 2), C), self._sdt)
+                hw2 = (H // 2) * (W // 2)
+                if idx == share:
+                    par = ws.parent
+                    shared_name = p + '.out'
+                    out = par.buf(shared_name, (par.B * F * hw2, C), self._sdt)[ws.lo * F * hw2:(ws.lo + B) * F * hw2]
+                else:
+                    out = ws.buf(p + '.out', (N * hw2, C), self._sdt)
                 if adt == torch.bfloat16:
                     planes = ws.buf(p + '.planes', (N * H * W, C), adt)
                     ops.gn_apply(x[0], None, N, H, W, planes, out_mode=2)
                     a1 = planes
                 else:
                     a1 = x[0]
-                st = self._fused_stats(ws, p + '.out', N, (H // 2) * (W // 2), C)
+                if idx == share:
+                    st = self._fused_stats(ws.parent, p + '.out', ws.parent.B * F, hw2, C)
+                    st = None if st is None else st[ws.lo * F:(ws.lo + B) * F]
+                else:
+                    st = self._fused_stats(ws, p + '.out', N, hw2, C)
                 ops.gemm(a1, P[p + '.w'], C, n_img=N, H=H // 2, W=W // 2, taps=9, a1_mode=1, bias=P[p + '.b'],
                          out_f32=out, C1=C, stats_out=st)
                 x, H, W = (out, st), H // 2, W // 2
@@ -938,6 +1023,9 @@ class UNetModel(nn.Module):
                     ops.gemm(x[0], P[p + '.w'], C, n_img=N, H=2 * H, W=2 * W, taps=9, a1_mode=2, bias=P[p + '.b'],
                              out_f32=out, C1=C)
                 x, H, W = (out, st), 2 * H, 2 * W
+        if stop < len(self.plan):
+            return dict(hs=hs, x=x, cur_group=cur_group, n_groups_done=n_groups_done, in_groups=in_groups, H=H, W=W,
+                        shared_name=shared_name)
         for ev in (ws.rpe_join, ws.emb_join):       # a model without attention / scale-shift: still join the side branch
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
