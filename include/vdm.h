@@ -121,6 +121,8 @@ typedef struct {
                            spare registers and normalises each image as soon as the convolution has finished it, while
                            the data is still in L2.  Only the transposed-role conv kernels take it
                            (vdm_gemm_img_done_supported); elsewhere it is an error */
+  int32_t a1_raw_dtype; /* output head only (out_nchw, N <= 8, with a1_coef): VDM_F16 = a1 is the RAW fp16 residual stream
+                           and GroupNorm-apply + SiLU (unet.py:745-748) happen while the conv stages its tile; 0 otherwise */
 } vdm_gemm_args;
 
 int vdm_gemm(const vdm_gemm_args* args, vdm_stream_t stream);

@@ -659,6 +659,43 @@ def test_output_head_conv_small_n(n, H, W, C1, N, monkeypatch):
         assert relerr(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3),
+                                       (2, 128, 128, 128, 3)])
+def test_output_head_conv_with_fused_groupnorm_silu(n, H, W, C1, N):
+    """The output head reading the RAW fp16 stream: GroupNorm-apply + SiLU while the tile is staged (a1_coef +
+    a1_raw_dtype), against the standalone gn_apply -> head conv pair on the same data, and against torch."""
+    o = ops()
+    x = (rnd(n, C1, H, W, seed=1) * 1.5 + 0.3).half()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16()
+    b = rnd(N, seed=3)
+    gamma, beta = 1 + 0.1 * rnd(C1, seed=4), 0.1 * rnd(C1, seed=5)
+    st = _chan_stats(x.float())
+    xs = nhwc(x)
+    coef = torch.empty(n, C1, 2, device='cuda')
+    o.gn_coef(st, None, n, H * W, gamma, beta, coef)
+    out = torch.full((n, N, H, W), float('nan'), device='cuda')
+    o.gemm(xs, pack_w(w.float()).bfloat16(), N, n_img=n, H=H, W=W, taps=9, bias=b, out_f32=out, out_nchw=True,
+           a1_coef=coef, a1_act=True)
+    a = torch.empty(n * H * W, C1, device='cuda', dtype=torch.bfloat16)
+    o.gn_apply(xs, None, n, H, W, a, stats1=st, gamma=gamma, beta=beta, silu=True)
+    two = torch.empty_like(out)
+    o.gemm(a, pack_w(w.float()).bfloat16(), N, n_img=n, H=H, W=W, taps=9, bias=b, out_f32=two, out_nchw=True)
+    assert relerr(out, two) < 1e-5          # same bf16 operand values (shared silu / affine arithmetic)
+    ref = F.conv2d(F.silu(F.group_norm(x.float(), 32, gamma, beta, eps=1e-5)), w.float(), b, padding=1)
+    assert relerr(out, ref) < 6e-3          # the activated operand is rounded to bf16
+
+
+def test_output_head_fused_groupnorm_unsupported_shape_raises():
+    o = ops()
+    n, H, W, C1, N = 4, 8, 8, 64, 3             # 8-pixel-wide images go to the tcgen05 GEMM, which has no such stage
+    x = rnd(n * H * W, C1, seed=1).half()
+    coef = torch.ones(n, C1, 2, device='cuda')
+    out = torch.empty(n, N, H, W, device='cuda')
+    with pytest.raises(RuntimeError, match='fused-normalisation'):
+        o.gemm(x, rnd(N, 9 * C1, seed=2).bfloat16(), N, n_img=n, H=H, W=W, taps=9, out_f32=out, out_nchw=True,
+               a1_coef=coef, a1_act=True)
+
+
 def _chan_stats(x, dtype=torch.float64):
     """[n][2][C] per-(image, channel) sum and sum of squares of an NCHW tensor."""
     xd = x.double()

@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
                 ('out_bf16', _vp), ('ld_out', _i32), ('ld_out_bf16', _i32), ('out_nchw', _i32),
                 ('out_silu_f32', _vp), ('lda1', _i32), ('w_group_tiles', _i32), ('stats_out', _vp), ('n_prob', _i32),
                 ('prob_a_cols', _i32), ('prob_w_rows', _i64), ('prob_out_stride', _i64), ('a1_coef', _vp),
-                ('a1_act', _i32), ('a2b', _vp), ('C2b', _i32), ('a2_dtype', _i32), ('io_dtype', _i32), ('img_done', _vp)]
+                ('a1_act', _i32), ('a2b', _vp), ('C2b', _i32), ('a2_dtype', _i32), ('io_dtype', _i32), ('img_done', _vp), ('a1_raw_dtype', _i32)]
 
 
 class GnApplyArgs(C.Structure):

@@ -6,6 +6,11 @@
 // 16 pixels x 8 channels with mma.sync m16n8k16: ldmatrix takes one address per row, so the nine taps are just
 // nine different row addresses into the same halo tile.  Output is written planar (NCHW fp32), the layout the
 // sampler consumes.
+//
+// With `coef` (vdm_gemm_args.a1_coef) the GroupNorm-apply + SiLU in front of the head (unet.py:745-748) happens while
+// the tile is staged: x is then the RAW fp16 residual stream, every staged value becomes silu(a * x + b) with the
+// per-(image, channel) pairs of vdm_gn_coef, and positions outside the image stay zero (the conv pads the ACTIVATED
+// tensor).  The standalone GroupNorm-apply pass over the 64x64 stream and its bf16 copy disappear.
 #include "common.cuh"
 
 namespace vdm {
@@ -20,10 +25,11 @@ __device__ __forceinline__ void cp16_zfill(void* smem, const void* gmem, bool va
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a), "l"(gmem), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat16* __restrict__ x,   // [n_img][H][W][C]
+template <bool XF>   // XF: x is the raw fp16 stream, normalised + activated while it is staged
+__global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const uint16_t* __restrict__ x,          // [n_img][H][W][C]
                                                                const __nv_bfloat16* __restrict__ w,   // [N][9*C]
                                                                const float* __restrict__ bias, int H, int W, int TW,
-                                                               int C, int N,
+                                                               int C, int N, const float2* __restrict__ coef, int act,
                                                                float* __restrict__ out /* [n_img][N][H*W] */) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
@@ -43,8 +49,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
   const int C8 = C / 8;
 
   // ---- stage the halo tile and the weights (index = pixel * C8 + chunk, advanced without divisions)
-  const __nv_bfloat16* ximg = x + (size_t)img * H * W * C;
-  {
+  const uint16_t* ximg = x + (size_t)img * H * W * C;
+  if constexpr (!XF) {
     const int total = (R + 2) * Wp * C8;
     const int step_pix = (int)blockDim.x / C8, step_c8 = (int)blockDim.x % C8;
     const int step_y = step_pix / Wp, step_x = step_pix % Wp;
@@ -58,6 +64,47 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const __nv_bfloat1
       if (c8 >= C8) { c8 -= C8; ++pix; ++hx; }
       if (hx >= Wp) { hx -= Wp; ++hy; }
       if (hx >= Wp) { hx -= Wp; ++hy; }
+    }
+  } else {
+    // the image's (a, b) pairs behind the weights; then batches of four 16-byte loads in flight per thread
+    float2* csm = reinterpret_cast<float2*>(wsm + (size_t)9 * 8 * Cp);
+    for (int c = tid; c < C; c += blockDim.x) csm[c] = __ldg(coef + (size_t)img * C + c);
+    __syncthreads();
+    const int total = (R + 2) * Wp * C8;
+    for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
+      uint4 v[4];
+      int pixs[4], c8s[4];
+      bool oks[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const int pix = i / C8, c8 = i - pix * C8;
+        const int hy = pix / Wp, hx = pix - hy * Wp;
+        const int xx = x0 + hx - 1, yy = y0 + hy - 1;
+        oks[u] = i < total && xx >= 0 && xx < W && yy >= 0 && yy < H;
+        pixs[u] = pix; c8s[u] = c8;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (oks[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(ximg + ((size_t)yy * W + xx) * C + c8 * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * (int)blockDim.x >= total) break;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (oks[u]) {
+          const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          uint32_t r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_f16x2(wv[q]);
+            const float4 ab = *reinterpret_cast<const float4*>(csm + c8s[u] * 8 + 2 * q);   // (a0, b0, a1, b1)
+            float y0v = fmaf(ab.x, f.x, ab.y), y1v = fmaf(ab.z, f.y, ab.w);
+            if (act) { y0v = silu_tanh(y0v); y1v = silu_tanh(y1v); }
+            r[q] = pack_bf16x2(y0v, y1v);
+          }
+          o = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+        *reinterpret_cast<uint4*>(halo + (size_t)pixs[u] * Cp + c8s[u] * 8) = o;
+      }
     }
   }
   for (int i = tid; i < 9 * 8 * C8; i += blockDim.x) {
@@ -134,26 +181,34 @@ int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
       TW = tw;
       break;
     }
+  const bool xf = a->a1_coef != nullptr;
   if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 32 == 0 && W >= 16 &&
         W % TW == 0 && TILE_PIX % TW == 0 && H % (TILE_PIX / TW) == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
-        !a->rowbias && !a->stats_out))
+        !a->rowbias && !a->stats_out && (!xf || a->a1_raw_dtype == VDM_F16) && (xf || a->a1_raw_dtype == 0)))
     return -100;
   const int R = TILE_PIX / TW;
-  const size_t smem = ((size_t)(R + 2) * (TW + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16);
+  const size_t smem = ((size_t)(R + 2) * (TW + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16) +
+                      (xf ? (size_t)C * sizeof(float2) : 0);
   if (smem > 200 * 1024) return -100;
-  static PerDevice<size_t> configured;
-  if (smem > configured.get()) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static PerDevice<size_t> configured[2];
+  if (smem > configured[xf].get()) {
+    cudaError_t e = xf ? cudaFuncSetAttribute(conv3x3_small_n_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(conv3x3_small_n_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv3x3_small_n: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured.get() = smem;
+    configured[xf].get() = smem;
   }
   const int grid = a->n_img * (H * W / TILE_PIX);
-  launch_kernel(conv3x3_small_n_kernel, grid, 256, smem, (cudaStream_t)stream, 1, reinterpret_cast<const __nv_bfloat16*>(a->a1),
-                                                     reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW, C, N,
-                                                     a->out_f32);
+  if (xf)
+    launch_kernel(conv3x3_small_n_kernel<true>, grid, 256, smem, (cudaStream_t)stream, 1,
+                  reinterpret_cast<const uint16_t*>(a->a1), reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW,
+                  C, N, reinterpret_cast<const float2*>(a->a1_coef), (int)a->a1_act, a->out_f32);
+  else
+    launch_kernel(conv3x3_small_n_kernel<false>, grid, 256, smem, (cudaStream_t)stream, 1,
+                  reinterpret_cast<const uint16_t*>(a->a1), reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW,
+                  C, N, static_cast<const float2*>(nullptr), 0, a->out_f32);
   VDM_AFTER_LAUNCH("conv3x3_small_n");
   return 0;
 }

@@ -2548,8 +2548,10 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   const int64_t M = (int64_t)a->n_img * a->H * a->W;
   if (probe) *probe = 0;
   const bool xf = a->a1_coef != nullptr;
-  VDM_REQUIRE(!xf || (a->taps == 9 && a->a1_mode == 0 && !a->out_nchw),
+  VDM_REQUIRE(!xf || (a->taps == 9 && a->a1_mode == 0 && (!a->out_nchw || a->N <= 8)),
               "gemm_tc: fused normalisation (a1_coef) takes 3x3 stride-1 convolutions only");
+  VDM_REQUIRE(a->a1_raw_dtype == 0 || (xf && a->out_nchw && a->a1_raw_dtype == VDM_F16),
+              "gemm_tc: a1_raw_dtype = VDM_F16 belongs to the small-N output head with a1_coef");
   VDM_REQUIRE(a->img_done == nullptr || (a->taps == 9 && a->a1_mode == 0 && !a->out_nchw && !xf),
               "gemm_tc: img_done is maintained by the transposed-role 3x3 conv kernels only");
   if (a->a1_mode == 3) return probe ? 0 : gemm_tc_upfold(a, stream);
@@ -2557,6 +2559,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
     const int rc = conv3x3_small_n(a, stream);
     if (rc != -100) return rc;
   }
+  VDM_REQUIRE(!(xf && a->out_nchw), "gemm_tc: this output-head shape has no fused-normalisation kernel");
   VDM_REQUIRE(a->taps == 1 || a->taps == 9, "gemm_tc: taps must be 1 or 9");
   VDM_REQUIRE(a->C1 > 0 && a->C1 % BLOCK_K == 0, "gemm_tc: C1=%d must be a multiple of 64", a->C1);
   VDM_REQUIRE(a->C2 % BLOCK_K == 0 && a->C2b % BLOCK_K == 0, "gemm_tc: C2=%d / C2b=%d must be multiples of 64", a->C2,

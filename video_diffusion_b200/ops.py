@@ -36,6 +36,9 @@ def _gemm_args(a1, w, N, *, n_img, H, W, taps, a1_mode=0, a2=None, bias=None, ro
                a2b=None, img_done=None):
     g = GemmArgs()
     g.dtype = dt(a1.dtype)
+    if a1_coef is not None and out_nchw and a1.dtype == torch.float16:
+        # output head with the GroupNorm-apply fused into its staging: a1 = the raw fp16 stream, weights bf16
+        g.dtype, g.a1_raw_dtype = BF16, F16
     g.taps, g.a1_mode = taps, a1_mode
     g.n_img, g.H, g.W = n_img, H, W
     g.C1 = a1.shape[-1] if C1 is None else C1

@@ -76,6 +76,7 @@ class UNetModel(nn.Module):
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
         # bf16 mode: the whole temporal attention (RPE score terms, q.k^T, softmax, P.V, attn.R_v) as ONE kernel
         self.fused_temporal = os.environ.get('VDM_FUSED_TEMPORAL', '1') != '0'
+        self.fuse_head_norm = os.environ.get('VDM_FUSE_HEAD', '1') != '0'   # out-head GroupNorm + SiLU inside the head conv
         self.temporal_pixels_per_cta = int(os.environ.get('VDM_TEMPORAL_PT', '0'))   # 0 = heuristic
         # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (transform warps of the halo kernels).  Correct
         # and bit-exact against the standalone pass, but measured SLOWER on B200 (every activation element
@@ -1032,6 +1033,15 @@ class UNetModel(nn.Module):
         ws.rpe_join = ws.emb_join = None
         h = x[0]
         st = self._stats_of(ws, 'out', h, x[1], N, H * W)
+        if (self.fuse_head_norm and adt == torch.bfloat16 and h.dtype == torch.float16 and self.out_channels <= 8
+                and ch % 32 == 0 and ch <= 256 and W % 16 == 0 and H % 8 == 0):
+            # GroupNorm-apply + SiLU while the head conv stages its tile (csrc/conv_small_n.cu): no bf16 copy of the
+            # top-level stream is written
+            coef = ws.buf('out.coef', (N, ch, 2))
+            ops.gn_coef(st, None, N, H * W, P['out_gn_w'], P['out_gn_b'], coef)
+            ops.gemm(h, P['out_w'], self.out_channels, n_img=N, H=H, W=W, taps=9, bias=P['out_b'], out_f32=ws.out,
+                     out_nchw=True, a1_coef=coef, a1_act=True)
+            return
         a = ws.buf('out.a', (N * H * W, ch), adt)
         ops.gn_apply(h, None, N, H, W, a, stats1=st, gamma=P['out_gn_w'], beta=P['out_gn_b'], silu=True)
         ops.gemm(a, P['out_w'], self.out_channels, n_img=N, H=H, W=W, taps=9, bias=P['out_b'], out_f32=ws.out,
