@@ -285,13 +285,18 @@ int vdm_attn_temporal_tc(const void* qkv, const float* sk, const float* sq, cons
  * RPE score terms q.Rk and k.Rq (GEMMs over the pixels of the tile), q.k^T, mask, fp32 softmax, P.V and the
  * attn.R_v term, all on mma.sync with the intermediates in shared memory.  out: [B*T*HW][C] bf16.
  * vdm_rpe_pack converts the fp32 R tables ([B*T*T][C] each, + optional bias [n_blocks][3][C] (q, k, v)) into the
- * kernel's bf16 operand layouts, for `n_blocks` attention blocks per call:
- *   rq, rk: [n_blocks][B*T][heads][t_pad][hd]   rows j >= T zero     (R[b, i, j, h, :] at group g = b*T + i)
- *   rv    : [n_blocks][B*T][heads][hd][32]      columns s >= T zero  (transposed: the contraction runs over s)
- * t_pad = 24 (T <= 24) or 32; T <= 32; HW a multiple of pixels_per_cta (8, or 16 for hd = 96; 0 = 8). */
+ * kernel's bf16 operands, for `n_blocks` attention blocks per call.  In the RPE products the table is the A operand of
+ * mma.m16n8k16 and the pixels are the n = 8 dimension, so the tables are stored FRAGMENT-MAJOR: one 16-byte vector =
+ * the four A registers of one lane for one k-step (lane = 4 g + t4; register r: row 16 mt + g + 8 (r & 1), contraction
+ * elements 8 t4 + 4 kk2 + 2 (r >> 1) + {0, 1} -- the same permutation the kernel applies to its shared-memory operand):
+ *   rq, rk: [n_blocks][B*T][heads][2][hd/32][2][32] vectors   rows = second frame index j (zero for j >= T),
+ *                                                              contraction over the channels 32 p + c of the head
+ *   rv    : [n_blocks][B*T][heads][hd/16][2][32] vectors      rows = channels, contraction over the second frame index
+ * i.e. B*T*heads*hd*32 elements per table and block.  T <= 32, hd a multiple of 32.  The kernel: t_pad = 24 (T <= 24)
+ * or 32 selects the key-tile count of the q.k^T phase; HW a multiple of pixels_per_cta (8, or 16 for hd = 96; 0 = 8). */
 int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t n_blocks,
                  int64_t r_block_stride /* elements between consecutive blocks' fp32 tables */, int32_t B, int32_t T,
-                 int32_t heads, int32_t hd, int32_t t_pad, void* rq, void* rk, void* rv,
+                 int32_t heads, int32_t hd, void* rq, void* rk, void* rv,
                  int64_t qk_block_stride /* elements between blocks' rq (and rk); 0 = packed */,
                  int64_t v_block_stride /* 0 = packed */, vdm_stream_t stream);
 /* Dynamic shared memory (bytes) the fused kernel needs for this shape, or -1 if the shape is not instantiated; the

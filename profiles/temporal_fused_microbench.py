@@ -46,10 +46,9 @@ def main():
         qkvs = [rnd(M, 3 * Cc, seed=10 + i).bfloat16() for i in range(nb)]
         R = [rnd(B * T * T, Cc, seed=2 + i, scale=0.5) for i in range(3)]
         mask = torch.ones(B, T).cuda()
-        rq = torch.empty(B * T, heads, TP, hd, device='cuda', dtype=torch.bfloat16)
-        rk = torch.empty_like(rq)
-        rv = torch.empty(B * T, heads, hd, 32, device='cuda', dtype=torch.bfloat16)
-        o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rq, rk, rv)
+        rq = torch.empty(B * T, heads, hd * 32, device='cuda', dtype=torch.bfloat16)
+        rk, rv = torch.empty_like(rq), torch.empty_like(rq)
+        o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, rq, rk, rv)
         atts = [torch.empty(M, Cc, device='cuda', dtype=torch.bfloat16) for _ in range(nb)]
         row = dict(HW=HW, hd=hd, M=M)
         for pt in ((8, 16) if hd == 96 else (8,)):
@@ -68,7 +67,7 @@ def main():
             row[f'phase_cycles_pt{pt}'] = dict(zip(('stage_wait', 'p1a', 'p1b', 'p2a', 'p2b', 'p3'),
                                                    [round(v / max(c[7], 1)) for v in c[:6]]), ctas=c[7])
         _lib.load().vdm_attn_temporal_fused_set_trace(None)
-        row['rpe_pack_us'] = time_graph(lambda i: o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rq, rk, rv))
+        row['rpe_pack_us'] = time_graph(lambda i: o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, rq, rk, rv))
         # the three-launch path
         gpt, tpg = (1, HW // 128) if HW >= 128 else (128 // HW, 1)
         SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt

@@ -955,6 +955,28 @@ def test_attention_temporal_tensor_core_path(T, hd, HW, pad):
     assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
 
 
+def _rpe_fragment_major(Rb, B, T, heads, hd, which):
+    """Expected vdm_rpe_pack output (see vdm.h): 16-byte vectors = the four A registers of an mma lane.  Rb: [B*T*T][C]
+    bf16-rounded (R + bias) as fp32.  which 'qk': [G][heads][2][hd/32][2][32][4][2]; 'v': [G][heads][hd/16][2][32][4][2]."""
+    G = B * T
+    R5 = Rb.view(G, T, heads, hd).cpu()
+    ar = torch.arange
+    if which == 'qk':
+        mt, p, kk2, lane, r, e = torch.meshgrid(ar(2), ar(hd // 32), ar(2), ar(32), ar(4), ar(2), indexing='ij')
+        row = 16 * mt + lane // 4 + 8 * (r & 1)                                  # second frame index j
+        con = 32 * p + 8 * (lane % 4) + 4 * kk2 + 2 * (r >> 1) + e              # channel f
+        vals = R5[:, row.clamp(max=T - 1), :, con]                              # index dims first, then (G, heads)
+        vals = vals * (row < T)[..., None, None]
+    else:
+        mt, kk2, lane, r, e = torch.meshgrid(ar(hd // 16), ar(2), ar(32), ar(4), ar(2), indexing='ij')
+        row = 16 * mt + lane // 4 + 8 * (r & 1)                                  # channel f
+        con = 8 * (lane % 4) + 4 * kk2 + 2 * (r >> 1) + e                       # second frame index s
+        vals = R5[:, con.clamp(max=T - 1), :, row]
+        vals = vals * (con < T)[..., None, None]
+    nd = vals.dim()
+    return vals.permute(nd - 2, nd - 1, *range(nd - 2)).contiguous()
+
+
 @pytest.mark.parametrize('T,hd,HW,pad,pt', [(20, 96, 256, True, 8), (20, 96, 256, True, 16), (10, 32, 64, False, 8),
                                              (7, 128, 128, True, 8), (20, 128, 64, True, 8), (32, 64, 24, False, 8),
                                              (27, 96, 16, True, 8), (1, 96, 8, True, 8), (17, 96, 48, False, 16)])
@@ -974,15 +996,13 @@ def test_attention_temporal_fused(T, hd, HW, pad, pt):
     ref = _attn_ref(qkv.float().permute(0, 2, 1, 3), heads, mask, Rb, pad).permute(0, 2, 1, 3).reshape(M, Cc)
     TP = 24 if T <= 24 else 32
     nan = float('nan')
-    rq = torch.full((B * T, heads, TP, hd), nan, device='cuda', dtype=torch.bfloat16)
-    rk = torch.full_like(rq, nan)
-    rv = torch.full((B * T, heads, hd, 32), nan, device='cuda', dtype=torch.bfloat16)
-    o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rq, rk, rv, bias=bias)
-    for got, want in ((rq, Rb[0]), (rk, Rb[1])):
-        assert torch.equal(got[:, :, :T].float(), want.view(B * T, T, heads, hd).permute(0, 2, 1, 3))
-        assert float(got[:, :, T:].float().abs().sum()) == 0
-    assert torch.equal(rv[..., :T].float(), Rb[2].view(B * T, T, heads, hd).permute(0, 2, 3, 1))
-    assert float(rv[..., T:].float().abs().sum()) == 0
+    per = heads * hd * 32                         # elements per (b, t) group and table
+    rq = torch.full((B * T, per), nan, device='cuda', dtype=torch.bfloat16)
+    rk, rv = torch.full_like(rq, nan), torch.full_like(rq, nan)
+    o.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, rq, rk, rv, bias=bias)
+    assert torch.equal(rq.float().cpu().view(-1), _rpe_fragment_major(Rb[0], B, T, heads, hd, 'qk').view(-1))
+    assert torch.equal(rk.float().cpu().view(-1), _rpe_fragment_major(Rb[1], B, T, heads, hd, 'qk').view(-1))
+    assert torch.equal(rv.float().cpu().view(-1), _rpe_fragment_major(Rb[2], B, T, heads, hd, 'v').view(-1))
     att = torch.full((M, Cc), nan, device='cuda', dtype=torch.bfloat16)
     o.attn_temporal_fused(qkv.view(M, 3 * Cc), rq, rk, rv, mask, pad, B, T, HW, heads, hd, TP, att, pixels_per_cta=pt)
     assert relerr(att, ref) < 1.2e-2        # P and the attention output are rounded to bf16
@@ -999,16 +1019,16 @@ def test_rpe_pack_batched_over_blocks_and_unsupported_shapes():
     Cc, rows = heads * hd, 2 * 20 * 20
     Rall = rnd(nb * 3 * rows, Cc, seed=3)
     bias = rnd(nb, 3, Cc, seed=4)
-    per = B * T * heads * 24 * hd
+    per = B * T * heads * hd * 32
     rqk = torch.zeros(nb, 2, per, device='cuda', dtype=torch.bfloat16)
-    rvp = torch.zeros(nb, B * T * heads * hd * 32, device='cuda', dtype=torch.bfloat16)
-    o.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, 24, rqk[0, 0], rqk[0, 1], rvp,
+    rvp = torch.zeros(nb, per, device='cuda', dtype=torch.bfloat16)
+    o.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, rqk[0, 0], rqk[0, 1], rvp,
                bias=bias, n_blocks=nb, r_block_stride=3 * rows * Cc, qk_block_stride=2 * per)
     for i in range(nb):
         blk = Rall[i * 3 * rows:(i + 1) * 3 * rows].view(3, rows, Cc)
         q1, k1 = torch.empty(per, device='cuda', dtype=torch.bfloat16), torch.empty(per, device='cuda', dtype=torch.bfloat16)
         v1 = torch.empty_like(rvp[0])
-        o.rpe_pack(blk[0], blk[1], blk[2], B, T, heads, hd, 24, q1, k1, v1, bias=bias[i])
+        o.rpe_pack(blk[0], blk[1], blk[2], B, T, heads, hd, q1, k1, v1, bias=bias[i])
         assert torch.equal(rqk[i, 0], q1) and torch.equal(rqk[i, 1], k1) and torch.equal(rvp[i], v1)
     out = torch.empty(B * T * 8, Cc, device='cuda', dtype=torch.bfloat16)
     qkv = torch.zeros(B * T * 8, 3 * Cc, device='cuda', dtype=torch.bfloat16)

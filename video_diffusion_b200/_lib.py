@@ -79,7 +79,7 @@ def load():
         'vdm_rpe_lookup': [_vp, _vp, _i32, _i32, _i32, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp],
         'vdm_rpe_expand': [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
         'vdm_attn_temporal_tc': [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
-        'vdm_rpe_pack': [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp],
+        'vdm_rpe_pack': [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp],
         'vdm_attn_temporal_fused_smem': [_i32, _i32, _i32, _i32],
         'vdm_attn_temporal_fused_set_trace': [_vp],
         'vdm_attn_temporal_fused': [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],

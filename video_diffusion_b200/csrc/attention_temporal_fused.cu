@@ -9,16 +9,18 @@
 // pixels of a tile (rows = pixels).  A CTA owns PT pixels of one (video, head); both families run on mma.sync
 // m16n8k16 (sequences of T <= 32 frames are far below a tcgen05 tile) and meet in shared memory:
 //
-//   P1a  Sk[pix][t][s]  = Q_t . Rk[t]^T      one (t, 8-key tile) unit per warp and round      -> S (fp32, smem)
-//   P1b  S[pix][t][s]  += K_s . Rq[s]^T      one (s, 8-query tile) unit per warp and round
+//   P1a  Sk^T[s][pix]  = Rk[t] . Q_t^T      one (t, 16 keys) unit per warp and round             -> S (fp32, smem)
+//   P1b  Sq^T[t][pix]  = Rq[s] . K_s^T      one (s, 16 queries) unit per warp and round          -> S +=
 //   P2a  warp = pixel: Q K^T + S  -> registers
 //   P2b  mask, fp32 softmax, P -> smem (bf16, over the pixel's own S rows), P.V -> O (fp32, over the dead Q / K tiles)
-//   P3   out = O + P_t . Rv[t]               one (t, 16-channel) unit per warp and round      -> global, bf16
+//   P3   out^T[f][pix] = Rv[t]^T . P_t^T + O   one (t, 16 channels) unit per warp and round       -> global, bf16
 //
-// The R operands are read straight from L2 as mma B fragments: vdm_rpe_pack lays the tables out so that a lane's
-// values for TWO k-steps are 16 contiguous bytes (the contraction index is permuted identically on the A side, which
-// is read from shared memory with the same 16-byte pattern), and the next unit's fragments are prefetched into
-// registers while the current unit runs.
+// In the RPE products the R table is the A operand (m = 16 table rows) and the pixels are the n = 8 dimension, so a
+// tile of 8 pixels wastes nothing.  vdm_rpe_pack writes the tables FRAGMENT-MAJOR: the four A registers of a lane for
+// one k-step are 16 contiguous bytes and a warp's load is 512 contiguous bytes of L2; the B fragments of two k-steps
+// are one 16-byte shared-memory load from the q / k / P row of the lane's pixel (the contraction index is permuted
+// identically on both sides).  No register shuffling between the loads and the mma, and the fragments of several
+// units are requested together so that a warp waits for the L2 round trip once per group.
 #include <cstdio>
 
 #include "common.cuh"
@@ -27,7 +29,7 @@
 #define VDM_TF_G1 3
 #endif
 #ifndef VDM_TF_G3
-#define VDM_TF_G3 4
+#define VDM_TF_G3 8
 #endif
 
 namespace vdm {
@@ -116,55 +118,53 @@ __host__ __device__ inline int fused_region_stride(int T, int TP) {   // per-pix
 }
 
 // ---------------------------------------------------------------- table packing
-// which 0 / 1: out[blk][g][h][j < TP][hd]   = R[blk][(g*T + j)][h*hd + f] + bias   (rows j >= T zero)
-// which 2    : out[blk][g][h][f][s < 32]    = Rv[blk][(g*T + s)][h*hd + f] + bias  (columns s >= T zero)
+// Fragment-major A operands of mma.m16n8k16 (16-byte vectors v = 4 registers of one lane for one k-step; lane = 4 g + t4;
+// register r: table row 16 mt + g + 8 (r & 1), contraction elements c(kk2, r, e) = 8 t4 + 4 kk2 + 2 (r >> 1) + e):
+//   which 0 / 1 (Rq / Rk): out[blk][grp][h][mt < 2][p < hd/32][kk2 < 2][lane]   row = second frame index j (zero for
+//                          j >= T), contraction over channels f = 32 p + c:  R[blk][(grp*T + j)][h*hd + f] + bias
+//   which 2 (Rv)         : out[blk][grp][h][mt < hd/16][kk2 < 2][lane]          row = channel f, contraction over the
+//                          second frame index s = c (zero for s >= T):       Rv[blk][(grp*T + s)][h*hd + f] + bias
 __global__ void __launch_bounds__(128) rpe_pack_kernel(const float* __restrict__ r_q, const float* __restrict__ r_k,
                                                         const float* __restrict__ r_v, const float* __restrict__ bias,
-                                                        long long r_block_stride, int T, int heads, int hd, int TP,
-                                                        __nv_bfloat16* __restrict__ oq, __nv_bfloat16* __restrict__ ok,
-                                                        __nv_bfloat16* __restrict__ ov, long long qk_block_stride,
+                                                        long long r_block_stride, int T, int heads, int hd,
+                                                        uint4* __restrict__ oq, uint4* __restrict__ ok,
+                                                        uint4* __restrict__ ov, long long qk_block_stride,
                                                         long long v_block_stride) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
-  const int g = blockIdx.x, h = blockIdx.y, which = blockIdx.z % 3, blk = blockIdx.z / 3;
-  const int C = heads * hd;
-  const float* R = (which == 0 ? r_q : (which == 1 ? r_k : r_v)) + (size_t)blk * r_block_stride + (size_t)g * T * C + h * hd;
+  const int grp = blockIdx.x, h = blockIdx.y, which = blockIdx.z % 3, blk = blockIdx.z / 3;
+  const int C = heads * hd, KP = hd / 32, MV = hd / 16;
+  const float* R = (which == 0 ? r_q : (which == 1 ? r_k : r_v)) + (size_t)blk * r_block_stride + (size_t)grp * T * C + h * hd;
   const float* bs = bias ? bias + ((size_t)blk * 3 + which) * C + h * hd : nullptr;
-  if (which < 2) {
-    __nv_bfloat16* out = (which == 0 ? oq : ok) + (size_t)blk * qk_block_stride + ((size_t)g * heads + h) * TP * hd;
-    const int hd8 = hd / 8;
-    for (int v = threadIdx.x; v < TP * hd8; v += blockDim.x) {
-      const int j = v / hd8, f = (v - j * hd8) * 8;
-      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-      if (j < T) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(R + (size_t)j * C + f));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(R + (size_t)j * C + f + 4));
-        float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (bs) {
+  const int nvec = (which < 2 ? 2 * KP : MV) * 64;
+  uint4* out = which < 2 ? (which == 0 ? oq : ok) + (size_t)blk * (qk_block_stride / 8) + ((size_t)grp * heads + h) * nvec
+                         : ov + (size_t)blk * (v_block_stride / 8) + ((size_t)grp * heads + h) * nvec;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int lane = v & 31, kk2 = (v >> 5) & 1, g = lane >> 2, t4 = lane & 3;
+    uint32_t reg[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] += bs[f + i];
+    for (int r = 0; r < 4; ++r) {
+      const int c0 = 8 * t4 + 4 * kk2 + 2 * (r >> 1);
+      float x[2] = {0.f, 0.f};
+      if (which < 2) {
+        const int mp = v >> 6, mt = mp / KP, p = mp - mt * KP;
+        const int j = 16 * mt + g + 8 * (r & 1), f = 32 * p + c0;
+        if (j < T) {
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(R + (size_t)j * C + f));
+          x[0] = t2.x + (bs ? bs[f] : 0.f);
+          x[1] = t2.y + (bs ? bs[f + 1] : 0.f);
         }
-        pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
-        pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
-      }
-      *reinterpret_cast<uint4*>(out + (size_t)j * hd + f) = pk;
-    }
-  } else {
-    __nv_bfloat16* out = ov + (size_t)blk * v_block_stride + ((size_t)g * heads + h) * hd * 32;
-    for (int f = threadIdx.x; f < hd; f += blockDim.x) {
-      const float bf = bs ? bs[f] : 0.f;
-      uint32_t pk[16];
+      } else {
+        const int mt = v >> 6;
+        const int f = 16 * mt + g + 8 * (r & 1);
+        const float bf = bs ? bs[f] : 0.f;
 #pragma unroll
-      for (int s2 = 0; s2 < 16; ++s2) {
-        const int s = 2 * s2;
-        const float x0 = s < T ? __ldg(R + (size_t)s * C + f) + bf : 0.f;
-        const float x1 = s + 1 < T ? __ldg(R + (size_t)(s + 1) * C + f) + bf : 0.f;
-        pk[s2] = pack_bf16x2(x0, x1);
+        for (int e = 0; e < 2; ++e)
+          if (c0 + e < T) x[e] = __ldg(R + (size_t)(c0 + e) * C + f) + bf;
       }
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)f * 32);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      reg[r] = pack_bf16x2(x[0], x[1]);
     }
+    out[v] = make_uint4(reg[0], reg[1], reg[2], reg[3]);
   }
 }
 
@@ -181,7 +181,7 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
   constexpr int LDSB = FusedCfg<HD>::LDSB, KP = HD / 32, TP = NT * 8, W = PT, NTH = PT * 32;
   constexpr int TSTR = PT * LDSB + 16;
   constexpr int NG = HD / 16;           // 16-channel output groups of the R_v phase
-  constexpr int G1 = VDM_TF_G1, G3 = VDM_TF_G3;   // units whose R fragments are requested together
+  constexpr int G1 = VDM_TF_G1, G3 = PT == 8 ? VDM_TF_G3 : VDM_TF_G3 / 2;   // units whose R fragments are requested together
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.x, pix0 = blockIdx.y * PT, b = blockIdx.z;   // the heads of a pixel tile run side by side
@@ -225,72 +225,78 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
     }
   }
 
-  // ---- P1: RPE score terms over the pixels of the tile.  Unit u = (frame i, 8-column tile nt).
-  const int n1 = T * NT;
-  auto load_b1 = [&](uint4 (&bf)[KP], const __nv_bfloat16* tab, int u) {
-    const int i = u / NT, nt = u - i * NT;
-    const __nv_bfloat16* row = tab + (((size_t)(b * T + i) * heads + h) * TP + nt * 8 + g) * HD + t4 * 8;
-#pragma unroll
-    for (int p = 0; p < KP; ++p) bf[p] = ldg128(row + p * 32);
-  };
-  auto mma_unit1 = [&](float (&c)[4], const uint4 (&bf)[KP], uint32_t a_base) {
-    c[0] = c[1] = c[2] = c[3] = 0.f;
+  // ---- P1: RPE score terms.  Unit u = (frame i, 16-row tile mt of the table): S^T tile [16 frames][pixels].
+  constexpr int NPT = PT / 8;                    // 8-pixel column tiles
+  const int MT1 = (T + 15) >> 4;                 // 16-row tiles of a table that hold live rows
+  const int n1 = T * MT1;
+  const uint4* rq4 = reinterpret_cast<const uint4*>(rq);
+  const uint4* rk4 = reinterpret_cast<const uint4*>(rk);
+  const uint4* rv4 = reinterpret_cast<const uint4*>(rv);
+  auto load_a1 = [&](uint4 (&af)[KP][2], const uint4* tab, int u) {
+    const int i = u / MT1, mt = u - i * MT1;
+    const uint4* src = tab + ((((size_t)(b * T + i) * heads + h) * 2 + mt) * KP) * 64 + lane;
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
-      const uint4 lo = lds128(a_base + p * 64);
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-      if (PT == 16) hi = lds128(a_base + 8 * LDSB + p * 64);
-      mma16816(c, lo.x, hi.x, lo.y, hi.y, bf[p].x, bf[p].y);
-      mma16816(c, lo.z, hi.z, lo.w, hi.w, bf[p].z, bf[p].w);
+      af[p][0] = __ldg(src + p * 64);
+      af[p][1] = __ldg(src + p * 64 + 32);
     }
   };
-  // The fragments of G1 units are requested together (G1 * KP 16-byte loads in flight per lane), and the next group's
-  // while the current one is multiplied (two register buffers): a unit is a handful of mma, what a warp would wait for
-  // is the L2 round trip.  Jobs 0 .. NG1-1 are the Sk groups, NG1 .. 2 NG1 - 1 the Sq groups; every warp runs the same
-  // number of jobs -- units past the end of its list are clamped to the last unit (loaded and multiplied like the
-  // others, so the G1 independent mma chains of a group interleave without branches; only the stores are predicated).
+  // Jobs 0 .. NG1-1 are the Sk groups, NG1 .. 2 NG1 - 1 the Sq groups; every warp runs the same number of jobs -- units
+  // past the end of its list are clamped to the last unit (loaded and multiplied like the others, so the independent
+  // mma chains of a group interleave without branches; only the stores are predicated).
   const int NG1 = (n1 + W * G1 - 1) / (W * G1);
-  uint4 bfA[G1][KP], bfB[G1][KP];
-  auto load_job1 = [&](uint4 (&bf)[G1][KP], int job) {
-    const __nv_bfloat16* tab = job < NG1 ? rk : rq;
+  uint4 afA[G1][KP][2];
+  auto load_job1 = [&](uint4 (&af)[G1][KP][2], int job) {
+    const uint4* tab = job < NG1 ? rk4 : rq4;
     const int k0 = (job < NG1 ? job : job - NG1) * G1;
 #pragma unroll
-    for (int j = 0; j < G1; ++j) load_b1(bf[j], tab, min(warp + (k0 + j) * W, n1 - 1));
+    for (int j = 0; j < G1; ++j) load_a1(af[j], tab, min(warp + (k0 + j) * W, n1 - 1));
   };
-  auto run_job1 = [&](const uint4 (&bf)[G1][KP], int job) {
-    const bool second = job >= NG1;           // Sq: A = K tile, read-modify-write of the transposed element
+  auto run_job1 = [&](const uint4 (&af)[G1][KP][2], int job) {
+    const bool second = job >= NG1;           // Sq: B = K tile, read-modify-write of the transposed element
     const int k0 = (second ? job - NG1 : job) * G1;
-    const uint32_t a_tensor = second ? sK : sQ;
-    float c[G1][4];
+    const uint32_t b_tensor = second ? sK : sQ;
+    float c[G1][NPT][4];
 #pragma unroll
     for (int j = 0; j < G1; ++j) {
-      const int i = min(warp + (k0 + j) * W, n1 - 1) / NT;
-      mma_unit1(c[j], bf[j], a_tensor + i * TSTR + g * LDSB + t4 * 16);
+      const int i = min(warp + (k0 + j) * W, n1 - 1) / MT1;
+      const uint32_t brow = b_tensor + i * TSTR + g * LDSB + t4 * 16;       // row of pixel g (the n index of B)
+#pragma unroll
+      for (int np = 0; np < NPT; ++np) c[j][np][0] = c[j][np][1] = c[j][np][2] = c[j][np][3] = 0.f;
+#pragma unroll
+      for (int p = 0; p < KP; ++p) {
+#pragma unroll
+        for (int np = 0; np < NPT; ++np) {
+          const uint4 bv = lds128(brow + np * 8 * LDSB + p * 64);
+          mma16816(c[j][np], af[j][p][0].x, af[j][p][0].y, af[j][p][0].z, af[j][p][0].w, bv.x, bv.y);
+          mma16816(c[j][np], af[j][p][1].x, af[j][p][1].y, af[j][p][1].z, af[j][p][1].w, bv.z, bv.w);
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < G1; ++j) {
       const int u = warp + (k0 + j) * W;
       if (u < n1) {
-        const int i = u / NT, nt = u - i * NT;
-        if (!second) {        // Sk[pix][i][s] = Q_i . Rk[i][s]: every element of S is written exactly once
-          const uint32_t a = sS + g * RS + (i * TP + nt * 8 + 2 * t4) * 4;
-          sts_f2(a, c[j][0], c[j][1]);
-          if (PT == 16) sts_f2(a + 8 * RS, c[j][2], c[j][3]);
-        } else {              // S[pix][t'][i] += K_i . Rq[i][t']
+        const int i = u / MT1, mt = u - i * MT1;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int tq = nt * 8 + 2 * t4 + e;
-            if (tq < T) {
-              const uint32_t a = sS + g * RS + (tq * TP + i) * 4;
-              sts_f(a, lds_f(a) + c[j][e]);
-              if (PT == 16) sts_f(a + 8 * RS, lds_f(a + 8 * RS) + c[j][2 + e]);
+        for (int np = 0; np < NPT; ++np)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = mt * 16 + g + (r >> 1) * 8;          // key s (Sk) / query t' (Sq)
+            const int pix = np * 8 + 2 * t4 + (r & 1);
+            if (row < T) {
+              if (!second) {      // Sk[pix][i][s]: every element of S is written exactly once
+                sts_f(sS + pix * RS + (i * TP + row) * 4, c[j][np][r]);
+              } else {            // S[pix][t'][i] += K_i . Rq[i][t']
+                const uint32_t a = sS + pix * RS + (row * TP + i) * 4;
+                sts_f(a, lds_f(a) + c[j][np][r]);
+              }
             }
           }
-        }
       }
     }
   };
-  load_job1(bfA, 0);
+  load_job1(afA, 0);
   // mask values of this lane's key columns and query rows (P2b), fetched while the copies are in flight
   float m_col[NT * 2], m_row[4];
 #pragma unroll
@@ -305,14 +311,13 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
   }
   mbar_wait(bar_qk, 0);
   tr_mark(0);
-  for (int job = 0; job < 2 * NG1; job += 2) {       // (2 NG1 jobs: always an even number)
-    load_job1(bfB, job + 1);
-    if (job == NG1) __syncthreads();                  // all of Sk is stored before the first Sq unit adds to it
-    run_job1(bfA, job);
-    if (job + 2 < 2 * NG1) load_job1(bfA, job + 2);
-    if (job + 1 == NG1) __syncthreads();
-    run_job1(bfB, job + 1);
-    if (job + 2 == NG1) tr_mark(1);
+  for (int job = 0; job < 2 * NG1; ++job) {
+    if (job) load_job1(afA, job);
+    if (job == NG1) {
+      tr_mark(1);
+      __syncthreads();                                // all of Sk is stored before the first Sq unit adds to it
+    }
+    run_job1(afA, job);
   }
   tr_mark(2);
   __syncthreads();
@@ -449,66 +454,65 @@ attn_temporal_fused_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       }
     }
   }
-  // first R_v unit of this warp: fetched before the barrier
+  // ---- P3: out^T[f][pix] = Rv[t]^T . P_t^T + O.  Unit u = (frame t, 16 channels mt)
   const int n3 = T * NG;
-  auto load_b3 = [&](uint4 (&bf)[2], int u) {
-    const int t = u / NG, ng = u - t * NG;
-    const __nv_bfloat16* row = rv + (((size_t)(b * T + t) * heads + h) * HD + ng * 16 + g) * 32 + t4 * 8;
-    bf[0] = ldg128(row);
-    bf[1] = ldg128(row + 8 * 32);
-  };
   const int NG3 = (n3 + W * G3 - 1) / (W * G3);
-  uint4 b3A[G3][2], b3B[G3][2];
-  auto load_job3 = [&](uint4 (&bf)[G3][2], int job) {
+  uint4 a3[G3][2];
+  auto load_job3 = [&](int job) {
 #pragma unroll
-    for (int j = 0; j < G3; ++j) load_b3(bf[j], min(warp + (job * G3 + j) * W, n3 - 1));
+    for (int j = 0; j < G3; ++j) {
+      const int u = min(warp + (job * G3 + j) * W, n3 - 1);
+      const int t = u / NG, mt = u - t * NG;
+      const uint4* src = rv4 + (((size_t)(b * T + t) * heads + h) * NG + mt) * 64 + lane;
+      a3[j][0] = __ldg(src);
+      a3[j][1] = __ldg(src + 32);
+    }
   };
-  // out[pix][t][f] = O + P_t . Rv[t]   (rows = pixels)
-  auto run_job3 = [&](const uint4 (&bf)[G3][2], int job) {
-    float c[G3][2][4];
+  load_job3(0);            // in flight across the barrier
+  tr_mark(4);
+  __syncthreads();
+  const bool even = (g & 1) == 0;
+  for (int job = 0; job < NG3; ++job) {
+    if (job) load_job3(job);
+    float c[G3][NPT][4];
 #pragma unroll
-    for (int jj = 0; jj < G3; ++jj) {
-      const int t = min(warp + (job * G3 + jj) * W, n3 - 1) / NG;
-      const uint4 lo = lds128(sS + g * RS + t * 64 + t4 * 16);
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-      if (PT == 16) hi = lds128(sS + (g + 8) * RS + t * 64 + t4 * 16);
+    for (int j = 0; j < G3; ++j) {
+      const int t = min(warp + (job * G3 + j) * W, n3 - 1) / NG;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        c[jj][j][0] = c[jj][j][1] = c[jj][j][2] = c[jj][j][3] = 0.f;
-        mma16816(c[jj][j], lo.x, hi.x, lo.y, hi.y, bf[jj][j].x, bf[jj][j].y);
-        mma16816(c[jj][j], lo.z, hi.z, lo.w, hi.w, bf[jj][j].z, bf[jj][j].w);
+      for (int np = 0; np < NPT; ++np) {
+        const uint4 bv = lds128(sS + (np * 8 + g) * RS + t * 64 + t4 * 16);     // P row of pixel g, frame t
+        c[j][np][0] = c[j][np][1] = c[j][np][2] = c[j][np][3] = 0.f;
+        mma16816(c[j][np], a3[j][0].x, a3[j][0].y, a3[j][0].z, a3[j][0].w, bv.x, bv.y);
+        mma16816(c[j][np], a3[j][1].x, a3[j][1].y, a3[j][1].z, a3[j][1].w, bv.z, bv.w);
       }
     }
 #pragma unroll
-    for (int jj = 0; jj < G3; ++jj) {
-      const int u = warp + (job * G3 + jj) * W;
-      if (u < n3) {
-        const int t = u / NG, ng = u - t * NG;
-        const int sw = (t ^ g) & 3;
-        __nv_bfloat16* orow = out + ((size_t)(b * T + t) * D + pix0 + g) * C + h * HD + ng * 16 + 2 * t4;
+    for (int j = 0; j < G3; ++j) {
+      const int u = warp + (job * G3 + j) * W;
+      const bool live = u < n3;
+      const int uu = min(u, n3 - 1);
+      const int t = uu / NG, mt = uu - t * NG;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int nt = ng * 2 + j;
-          const uint32_t oa = sO + (uint32_t)(g * T + t) * (HD * 4) + ((nt ^ sw) * 8 + 2 * t4) * 4;
-          const float2 o0 = lds_f2(oa);
-          *reinterpret_cast<uint32_t*>(orow + j * 8) = pack_bf16x2(c[jj][j][0] + o0.x, c[jj][j][1] + o0.y);
-          if (PT == 16) {
-            const float2 o1 = lds_f2(oa + (uint32_t)8 * T * (HD * 4));
-            *reinterpret_cast<uint32_t*>(orow + (size_t)8 * C + j * 8) =
-                pack_bf16x2(c[jj][j][2] + o1.x, c[jj][j][3] + o1.y);
-          }
+      for (int np = 0; np < NPT; ++np) {
+        // accumulator: (channel 16 mt + g [+ 8], pixel 2 t4 [+ 1]).  Lanes g and g ^ 1 swap halves, so each ends up with
+        // two CHANNEL pairs of one pixel: 4-byte stores, and the addend O comes as two 8-byte shared-memory loads.
+        const float v1 = __shfl_xor_sync(0xffffffffu, even ? c[j][np][1] : c[j][np][0], 4);
+        const float v2 = __shfl_xor_sync(0xffffffffu, even ? c[j][np][3] : c[j][np][2], 4);
+        const int pix = np * 8 + 2 * t4 + (even ? 0 : 1);
+        const int fa = mt * 16 + g - (even ? 0 : 1);
+        const float lo0 = even ? c[j][np][0] : v1, lo1 = even ? v1 : c[j][np][1];
+        const float hi0 = even ? c[j][np][2] : v2, hi1 = even ? v2 : c[j][np][3];
+        if (live) {
+          const int sw = (t ^ pix) & 3;
+          const uint32_t orow = sO + (uint32_t)(pix * T + t) * (HD * 4);
+          const float2 o0 = lds_f2(orow + ((((fa >> 3) ^ sw) << 3) + (fa & 7)) * 4);
+          const float2 o1 = lds_f2(orow + (((((fa >> 3) + 1) ^ sw) << 3) + (fa & 7)) * 4);
+          __nv_bfloat16* dst = out + ((size_t)(b * T + t) * D + pix0 + pix) * C + h * HD + fa;
+          *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(lo0 + o0.x, lo1 + o0.y);
+          *reinterpret_cast<uint32_t*>(dst + 8) = pack_bf16x2(hi0 + o1.x, hi1 + o1.y);
         }
       }
     }
-  };
-  load_job3(b3A, 0);            // in flight across the barrier
-  tr_mark(4);
-  __syncthreads();
-  for (int job = 0; job < NG3; job += 2) {
-    if (job + 1 < NG3) load_job3(b3B, job + 1);
-    run_job3(b3A, job);
-    if (job + 2 < NG3) load_job3(b3A, job + 2);
-    if (job + 1 < NG3) run_job3(b3B, job + 1);
   }
   tr_mark(5);
   if (trace != nullptr && threadIdx.x == 0) atomicAdd(trace + 7, 1ULL);
@@ -555,19 +559,18 @@ int launch_fused_nt(int t_pad, const void* qkv, const void* rq, const void* rk, 
 using namespace vdm;
 
 extern "C" int vdm_rpe_pack(const float* r_q, const float* r_k, const float* r_v, const float* bias, int32_t n_blocks,
-                            int64_t r_block_stride, int32_t B, int32_t T, int32_t heads, int32_t hd, int32_t t_pad,
-                            void* rq, void* rk, void* rv, int64_t qk_block_stride, int64_t v_block_stride,
-                            vdm_stream_t stream) {
+                            int64_t r_block_stride, int32_t B, int32_t T, int32_t heads, int32_t hd, void* rq, void* rk,
+                            void* rv, int64_t qk_block_stride, int64_t v_block_stride, vdm_stream_t stream) {
   VDM_REQUIRE(r_q && r_k && r_v && rq && rk && rv, "rpe_pack: NULL pointer");
-  VDM_REQUIRE(T >= 1 && T <= 32 && (t_pad == 24 || t_pad == 32) && T <= t_pad, "rpe_pack: T=%d, t_pad=%d unsupported", T,
-              t_pad);
-  VDM_REQUIRE(hd % 8 == 0 && n_blocks >= 1, "rpe_pack: head_dim must be a multiple of 8");
+  VDM_REQUIRE(T >= 1 && T <= 32, "rpe_pack: T=%d unsupported", T);
+  VDM_REQUIRE(hd % 32 == 0 && n_blocks >= 1, "rpe_pack: head_dim must be a multiple of 32");
   const int64_t G = (int64_t)B * T;
-  if (qk_block_stride == 0) qk_block_stride = G * heads * t_pad * hd;
-  if (v_block_stride == 0) v_block_stride = G * heads * hd * 32;
+  if (qk_block_stride == 0) qk_block_stride = G * heads * hd * 32;     // 2 row tiles x hd/32 x 2 k-steps x 32 lanes x 8
+  if (v_block_stride == 0) v_block_stride = G * heads * hd * 32;       // hd/16 row tiles x 2 k-steps x 32 lanes x 8
+  VDM_REQUIRE(qk_block_stride % 8 == 0 && v_block_stride % 8 == 0, "rpe_pack: block strides are multiples of 8 elements");
   launch_kernel(rpe_pack_kernel, dim3((unsigned)G, heads, 3 * n_blocks), 128, 0, (cudaStream_t)stream, 1, r_q, r_k, r_v,
-                bias, (long long)r_block_stride, T, heads, hd, t_pad, (__nv_bfloat16*)rq, (__nv_bfloat16*)rk,
-                (__nv_bfloat16*)rv, (long long)qk_block_stride, (long long)v_block_stride);
+                bias, (long long)r_block_stride, T, heads, hd, (uint4*)rq, (uint4*)rk, (uint4*)rv,
+                (long long)qk_block_stride, (long long)v_block_stride);
   VDM_AFTER_LAUNCH("rpe_pack");
   return 0;
 }

@@ -220,10 +220,11 @@ def attn_temporal_tc(qkv, sk, sq, mask, pad_interact, B, T, HW, heads, hd, gpt, 
            nbytes=_nbytes(qkv, sk, sq, pm, pv))
 
 
-def rpe_pack(r_q, r_k, r_v, B, T, heads, hd, t_pad, rq, rk, rv, bias=None, n_blocks=1, r_block_stride=0,
+def rpe_pack(r_q, r_k, r_v, B, T, heads, hd, rq, rk, rv, bias=None, n_blocks=1, r_block_stride=0,
              qk_block_stride=0, v_block_stride=0):
+    """fp32 R tables -> the fused temporal kernel's fragment-major bf16 operands (B*T*heads*hd*32 elements per table)."""
     _timed('rpe_pack', lambda: check(_lib.load().vdm_rpe_pack(
-        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, B, T, heads, hd, t_pad, ptr(rq), ptr(rk),
+        ptr(r_q), ptr(r_k), ptr(r_v), ptr(bias), n_blocks, r_block_stride, B, T, heads, hd, ptr(rq), ptr(rk),
         ptr(rv), qk_block_stride, v_block_stride, stream()), 'vdm_rpe_pack'), nbytes=_nbytes(rq, rk, rv))
 
 

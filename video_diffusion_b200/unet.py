@@ -590,12 +590,12 @@ class UNetModel(nn.Module):
             ops.gemm(hid, P[key + '.out_w'], C, n_img=nb * 3 * rows, H=1, W=1, taps=1, out_f32=Rall,
                      w_group_tiles=rows // 128)
             if self._fused_temporal_ok(T, C, HW):
-                # fused kernel: compact bf16 tables [q, k][(b, t)][head][t_pad][hd] and [(b, t)][head][hd][32]
-                TP, hd = (24 if T <= 24 else 32), C // heads
-                per = B * T * heads * TP * hd
+                # fused kernel: fragment-major bf16 tables, B*T*heads*hd*32 elements each (vdm_rpe_pack)
+                hd = C // heads
+                per = B * T * heads * hd * 32
                 rqk = ws.buf(key + '.rqk', (nb, 2, per), adt)
-                rvp = ws.buf(key + '.rvp', (nb, B * T * heads * hd * 32), adt)
-                ops.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, TP, rqk[0, 0],
+                rvp = ws.buf(key + '.rvp', (nb, per), adt)
+                ops.rpe_pack(Rall[:rows], Rall[rows:2 * rows], Rall[2 * rows:3 * rows], B, T, heads, hd, rqk[0, 0],
                              rqk[0, 1], rvp, bias=P[key + '.out_b'], n_blocks=nb, r_block_stride=3 * rows * C,
                              qk_block_stride=2 * per)
                 for i, n in enumerate(nodes):
@@ -656,13 +656,12 @@ class UNetModel(nn.Module):
             ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
             if pre is not None:
                 # tables of the FULL batch; a micro-batch starts at its first (b, t) group
-                g0 = tables.get('__group0__', 0)
-                rq, rk = pre[1][0][g0 * heads * TP * hd:], pre[1][1][g0 * heads * TP * hd:]
-                rvp = pre[2][g0 * heads * hd * 32:]
+                g0 = tables.get('__group0__', 0) * heads * hd * 32
+                rq, rk, rvp = pre[1][0][g0:], pre[1][1][g0:], pre[2][g0:]
             else:
-                rqk = ws.buf(q + '.rqk', (2, N * heads * TP * hd), adt)
+                rqk = ws.buf(q + '.rqk', (2, N * heads * hd * 32), adt)
                 rvp = ws.buf(q + '.rvp', (N * heads * hd * 32,), adt)
-                ops.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, TP, rqk[0], rqk[1], rvp)
+                ops.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, rqk[0], rqk[1], rvp)
                 rq, rk = rqk[0], rqk[1]
             ops.attn_temporal_fused(qkv, rq, rk, rvp, amask, self.allow_interactions_between_padding, B, T, HW, heads,
                                     hd, TP, att, pixels_per_cta=self._temporal_pt(T, C, HW))
