@@ -59,6 +59,15 @@ for C, HW in ((384, 256), (512, 64)):
         lambda: ops.attn_temporal_tc(qkv, sk, sq, mask, True, B, T, HW, heads, hd, gpt, pm, pv),
         nbytes=qkv.numel() * 2 + 2 * sk.numel() * 4 + pm.numel() * 2 + pv.numel() * 4,
         flops=4.0 * B * HW * heads * T * T * hd)
+    # the whole temporal block in one kernel (default path)
+    R = [torch.randn(B * T * T, C, device=dev) * 0.5 for _ in range(3)]
+    rq = torch.empty(B * T * heads * hd * 32, device=dev, dtype=torch.bfloat16)
+    rk, rv = torch.empty_like(rq), torch.empty_like(rq)
+    ops.rpe_pack(R[0], R[1], R[2], B, T, heads, hd, rq, rk, rv)
+    pt = 16 if hd == 96 else 8
+    run(f'attn_temporal_fused C={C} HW={HW} pt={pt}',
+        lambda: ops.attn_temporal_fused(qkv, rq, rk, rv, mask, True, B, T, HW, heads, hd, 24, att, pixels_per_cta=pt),
+        nbytes=qkv.numel() * 2 + att.numel() * 2, flops=10.0 * B * HW * heads * T * T * hd)
 
 for (HWs, C, in_dtype) in ((64, 128, torch.float32), (32, 256, torch.bfloat16)):
     n = B * T

@@ -6,7 +6,7 @@
 //
 // The R tables depend on (video, frame pair, head) but not on the pixel, q / k / v depend on the pixel: the q.k^T and
 // P.V products are per-pixel T x T GEMMs (rows = frames), the three RPE contractions are per-frame GEMMs over the
-// pixels of a tile (rows = pixels).  A CTA owns PT pixels of one (video, head); both families run on mma.sync
+// pixels of a tile (table rows x pixels).  A CTA owns PT pixels of one (video, head); both families run on mma.sync
 // m16n8k16 (sequences of T <= 32 frames are far below a tcgen05 tile) and meet in shared memory:
 //
 //   P1a  Sk^T[s][pix]  = Rk[t] . Q_t^T      one (t, 16 keys) unit per warp and round             -> S (fp32, smem)
@@ -103,7 +103,6 @@ __device__ __forceinline__ float lds_f(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
-__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // Row pitch (bytes) of a staged q / k / v row: == 64 (mod 128), so the 16-byte A-fragment reads of two adjacent
 // pixel rows (one quarter-warp) cover all 32 banks; consecutive frames of a pixel are TSTR = PT * pitch + 16 apart, so
