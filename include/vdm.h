@@ -50,9 +50,11 @@ void vdm_gemm_set_trace(void* buf);
  *
  * dtype VDM_BF16: A1/A2/W are bf16, the kernel is the tcgen05/TMEM/TMA one (fp32 accumulate).
  * dtype VDM_F32 : A1/A2/W are fp32, SIMT fp32 kernel (reference-accuracy mode).
+ * dtype VDM_F16 : plain linears only (taps 1, no A2): A1 and W are IEEE half, same tcgen05 kernels with the f16 operand
+ *                 format -- the normalised fp16 stream itself is the operand of the attention qkv projection.
  */
 typedef struct {
-  int32_t dtype;        /* VDM_F32 | VDM_BF16: type of a1, a2, w */
+  int32_t dtype;        /* VDM_F32 | VDM_BF16 | VDM_F16 (plain linears): type of a1, a2, w */
   int32_t taps;         /* 1 (linear / 1x1), 9 (3x3, pad 1) or 4 (a1_mode 3) */
   int32_t a1_mode;      /* 0: A1 is [n][H][W][C1] at output resolution (stride 1)
                            1: stride-2 conv.  bf16: A1 is parity planes [n][py][px][H][W][C1] of the
@@ -158,7 +160,8 @@ typedef struct {
   int32_t silu;
   int32_t out_mode;                   /* 0 plain, 1 nearest-x2 upsampled, 2 stride-2 parity planes */
   int32_t out_dtype;                  /* VDM_F32 | VDM_BF16 */
-  void* out;                          /* GEMM A operand */
+  void* out;                          /* GEMM A operand; may be NULL with out_f32_copy (plain layout): only the copy is
+                                         written -- in fp16 it is itself the operand of the qkv projection (VDM_F16) */
   int32_t src1_dtype;                 /* VDM_F32 | VDM_F16 (src2 alike) | VDM_BF16 (single source) */
   void* out_raw;                      /* optional second output: the un-normalised input cast to out_dtype, plain
                                          layout (A operand of the 1x1 skip projection, unet.py:172-173) */
@@ -186,7 +189,8 @@ int vdm_gn_coef(const void* stats1, int32_t stats_dtype, int32_t C1, const void*
 int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW, int32_t C,
                     const float* gamma, const float* beta, float* out_f32,
                     void* out_a, int32_t out_dtype, vdm_stream_t stream);
-/* the same with x and the normalised residual copy `out_res` in io_dtype (VDM_F32 | VDM_F16: the fp16 stream) */
+/* the same with x and the normalised residual copy `out_res` in io_dtype (VDM_F32 | VDM_F16: the fp16 stream);
+ * out_a may be NULL when out_res is given (the fp16 copy then feeds the qkv projection directly, vdm_gemm dtype VDM_F16) */
 int vdm_gn_temporal_t(const void* x, int32_t io_dtype, int32_t B, int32_t T, int32_t HW, int32_t C,
                       const float* gamma, const float* beta, void* out_res, void* out_a, int32_t out_dtype,
                       vdm_stream_t stream);

@@ -444,6 +444,59 @@ def test_linear_a_stationary_kernel(n, HW, C, N, kind, monkeypatch):
     assert relerr(outs['1'][0], ref) < 6e-3
 
 
+@pytest.mark.parametrize('M,C,N', [(40960, 384, 1152), (10240, 512, 1536), (2560, 128, 256), (1000, 64, 24)])
+def test_linear_fp16_operands(M, C, N, monkeypatch):
+    """dtype VDM_F16: a plain linear whose activations AND weights are IEEE half (the normalised fp16 stream feeding the
+    attention qkv projection), on the A-stationary pair kernel, the plain kernel and the transposed-role kernel --
+    bit-identical to each other (same products, same k order), and against torch on the same fp16 values."""
+    o = ops()
+    a = rnd(M, C, seed=1).half()
+    w = rnd(N, C, seed=2, scale=C ** -0.5).half()
+    bias = rnd(N, seed=3)
+    outs = []
+    for astat, lint in (('1', '0'), ('0', '0'), ('0', '2')):
+        monkeypatch.setenv('VDM_GEMM_ASTAT', astat)
+        monkeypatch.setenv('VDM_GEMM_LINT', lint)
+        out = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16)
+        o.gemm(a, w, N, n_img=M, H=1, W=1, taps=1, bias=bias, out_bf16=out)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = a.float() @ w.float().t() + bias
+    assert relerr(outs[0], ref) < 5e-3            # bf16 rounding of the output only
+    # the same values as bf16 operands lose three significand bits
+    out_b = torch.empty_like(outs[0])
+    o.gemm(a.bfloat16(), w.bfloat16(), N, n_img=M, H=1, W=1, taps=1, bias=bias, out_bf16=out_b)
+    assert relerr(outs[0], ref) <= relerr(out_b, ref) + 1e-4
+    with pytest.raises(RuntimeError, match='plain linears'):          # convolutions keep bf16 operands
+        o.gemm(rnd(2 * 64, 64, seed=5).half(), rnd(64, 9 * 64, seed=6).half(), 64, n_img=2, H=8, W=8, taps=9,
+               out_bf16=torch.empty(128, 64, device='cuda', dtype=torch.bfloat16))
+
+
+def test_groupnorm_kernels_with_the_stream_copy_as_only_output():
+    """gn_temporal with out_a = None and gn_apply with out = None + copy: only the normalised fp16 stream copy is
+    written (it feeds the qkv projection directly); bit-identical to the copy of the two-output call."""
+    o = ops()
+    B, T, HW, Cc = 2, 20, 64, 384
+    x = (rnd(B, T, HW, Cc, seed=1) * 2 + 0.5).half()
+    g, b = 1 + 0.1 * rnd(Cc, seed=2), 0.1 * rnd(Cc, seed=3)
+    both_r, both_a = torch.empty_like(x), torch.empty(B, T, HW, Cc, device='cuda', dtype=torch.bfloat16)
+    o.gn_temporal(x, B, T, HW, Cc, g, b, both_r, both_a)
+    only = torch.full_like(x, float('nan'))
+    o.gn_temporal(x, B, T, HW, Cc, g, b, only, None)
+    assert torch.equal(only, both_r)
+    n = B * T
+    xs = x.view(n * HW, Cc)
+    st = _chan_stats(xs.view(n, 8, 8, Cc).permute(0, 3, 1, 2).float())
+    c2, a2 = torch.empty_like(xs), torch.empty(n * HW, Cc, device='cuda', dtype=torch.bfloat16)
+    o.gn_apply(xs, None, n, 8, 8, a2, stats1=st, gamma=g, beta=b, copy=c2)
+    c1 = torch.full_like(xs, float('nan'))
+    o.gn_apply(xs, None, n, 8, 8, None, stats1=st, gamma=g, beta=b, copy=c1)
+    assert torch.equal(c1, c2)
+    with pytest.raises(RuntimeError, match='NULL'):
+        o.gn_apply(xs, None, n, 8, 8, None, stats1=st, gamma=g, beta=b)
+
+
 @pytest.mark.parametrize('n,HW,C,N,kind', [(160, 256, 384, 1152, 'qkv'), (160, 64, 512, 1536, 'qkv'),
                                            (160, 256, 384, 384, 'proj'), (157, 64, 512, 512, 'proj'),
                                            (80, 256, 384, 384, 'proj32'), (7, 128, 64, 128, 'proj'),

@@ -34,9 +34,12 @@ extern "C" int vdm_gemm(const vdm_gemm_args* a, vdm_stream_t stream) {
   VDM_REQUIRE(a->n_img > 0 && a->H > 0 && a->W > 0 && a->N > 0, "gemm: bad geometry");
   VDM_REQUIRE(a->a1_coef == nullptr || a->dtype == VDM_BF16, "gemm: a1_coef (fused normalisation) is bf16-kernel only");
   VDM_REQUIRE(a->img_done == nullptr || a->dtype == VDM_BF16, "gemm: img_done is bf16-kernel only");
-  VDM_REQUIRE(a->dtype == VDM_BF16 || (a->a2b == nullptr && a->C2b == 0 && a->a2_dtype != VDM_F16 && a->io_dtype != VDM_F16),
+  VDM_REQUIRE(a->dtype == VDM_BF16 || a->dtype == VDM_F16 ||
+                  (a->a2b == nullptr && a->C2b == 0 && a->a2_dtype != VDM_F16 && a->io_dtype != VDM_F16),
               "gemm: a2b / a2_dtype / io_dtype belong to the bf16 kernel");
-  if (a->dtype == VDM_BF16) return vdm::gemm_tc(a, (cudaStream_t)stream);
+  // VDM_F16: a plain linear whose activations AND weights are IEEE half (the normalised fp16 stream itself feeding the
+  // attention qkv projection): the tcgen05 kernels with the f16 operand format
+  if (a->dtype == VDM_BF16 || a->dtype == VDM_F16) return vdm::gemm_tc(a, (cudaStream_t)stream);
   if (a->dtype == VDM_F32) return vdm::gemm_simt(a, (cudaStream_t)stream);
   vdm::set_error("gemm: unknown dtype %d", a->dtype);
   return -1;

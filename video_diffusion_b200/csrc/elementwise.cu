@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(GN_THREADS, GN_MIN_BLOCKS) gn_apply_kernel(con
       }
     }
     if constexpr (MODE == 0) {
-      store8(out + ((size_t)n * HW + pix) * C, y);
+      if (!COPY || p.out != nullptr) store8(out + ((size_t)n * HW + pix) * C, y);   // (COPY alone: `out` may be NULL)
     } else {
       const int yy = pix / p.W, xx = pix - yy * p.W;
       if constexpr (MODE == 1) {  // nearest x2
@@ -432,7 +432,9 @@ __global__ void __launch_bounds__(256) gn_temporal_kernel(const IoT* __restrict_
       const float y0 = fmaf(v.x - mu[0], a[0], bb[0]), y1 = fmaf(v.y - mu[1], a[1], bb[1]);
       const float y2 = fmaf(v.z - mu[2], a[2], bb[2]), y3 = fmaf(v.w - mu[3], a[3], bb[3]);
       if (out_f32) store4(out_f32 + off, make_float4(y0, y1, y2, y3));
-      if constexpr (sizeof(OutT) == 2) {
+      if (out_a == nullptr) {
+        // the normalised copy alone (fp16 stream: it is itself the A operand of the qkv projection)
+      } else if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
         pk.x = pack_bf16x2(y0, y1);
         pk.y = pack_bf16x2(y2, y3);
@@ -533,7 +535,9 @@ __global__ void __launch_bounds__(128) gn_temporal_regs_kernel(const IoT* __rest
       const float y0 = fmaf(u.x - mean, a0, b0), y1 = fmaf(u.y - mean, a1, b1);
       const float y2 = fmaf(u.z - mean, a2, b2), y3 = fmaf(u.w - mean, a3, b3);
       if (out_f32) store4(out_f32 + off, make_float4(y0, y1, y2, y3));
-      if constexpr (sizeof(OutT) == 2) {
+      if (out_a == nullptr) {
+        // the normalised copy alone (fp16 stream: it is itself the A operand of the qkv projection)
+      } else if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
         pk.x = pack_bf16x2(y0, y1);
         pk.y = pack_bf16x2(y2, y3);
@@ -783,7 +787,7 @@ extern "C" int vdm_gn_stats_t(const void* src, int32_t src_dtype, int32_t C, int
 
 extern "C" int vdm_gn_apply(const vdm_gn_apply_args* a, vdm_stream_t stream) {
   const int C = a->C1 + a->C2;
-  VDM_REQUIRE(a->src1 && a->out && (a->C2 == 0 || a->src2), "gn_apply: NULL pointer");
+  VDM_REQUIRE(a->src1 && (a->out || (a->out_f32_copy && a->out_mode == 0)) && (a->C2 == 0 || a->src2), "gn_apply: NULL pointer");
   VDM_REQUIRE(C % 32 == 0 && a->C1 % 8 == 0 && a->C2 % 8 == 0 && C <= 2048, "gn_apply: unsupported channels %d+%d",
               a->C1, a->C2);
   VDM_REQUIRE(!a->stats1 || (a->gamma && a->beta), "gn_apply: gamma/beta missing");
@@ -892,7 +896,7 @@ extern "C" int vdm_gn_temporal(const float* x, int32_t B, int32_t T, int32_t HW,
 extern "C" int vdm_gn_temporal_t(const void* x, int32_t io_dtype, int32_t B, int32_t T, int32_t HW, int32_t C,
                                  const float* gamma, const float* beta, void* out_res, void* out_a, int32_t out_dtype,
                                  vdm_stream_t stream) {
-  VDM_REQUIRE(x && gamma && beta && out_a, "gn_temporal: NULL pointer");
+  VDM_REQUIRE(x && gamma && beta && (out_a || out_res), "gn_temporal: NULL pointer");
   VDM_REQUIRE(C % 32 == 0 && C <= 1024, "gn_temporal: C=%d must be a multiple of 32, <= 1024", C);
   VDM_REQUIRE(io_dtype == VDM_F32 || (io_dtype == VDM_F16 && out_dtype == VDM_BF16),
               "gn_temporal: x / out_res are fp32, or fp16 with a bf16 operand output");

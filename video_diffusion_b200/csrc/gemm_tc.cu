@@ -54,6 +54,7 @@ struct TcParams {
   int M, N;
   int taps, c1_chunks, c2_chunks;
   int c2a_chunks;     // chunks of the second range that come from its first tensor (== c2_chunks for one tensor)
+  int a1_f16;         // the first range (activations AND its weight columns) is IEEE half (linears: vdm_gemm dtype VDM_F16)
   int a2_f16;         // the second range (activations AND its weight columns) is IEEE half: those MMAs use the f16 descriptor
   int a1_mode;    // 0 stride-1 / linear, 1 stride-2 parity planes, 3 nearest-x2 upsample folded into 2x2 taps
   int w_group_tiles;  // grouped weights: 128-row tile m reads weight rows (m / w_group_tiles) * N + n
@@ -1031,8 +1032,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {   // 2-CTA: only the leader issues
-      constexpr uint32_t idesc_bf16 = instr_desc<BLOCK_N, CTA2 ? 256 : BLOCK_M>();
-      const uint32_t idesc_a2 = p.a2_f16 ? (idesc_bf16 & kIdescF16Mask) : idesc_bf16;
+      constexpr uint32_t idesc_c = instr_desc<BLOCK_N, CTA2 ? 256 : BLOCK_M>();
+      const uint32_t idesc_bf16 = p.a1_f16 ? (idesc_c & kIdescF16Mask) : idesc_c;     // descriptor of the first range
+      const uint32_t idesc_a2 = p.a2_f16 ? (idesc_c & kIdescF16Mask) : idesc_c;
       const int k1_mma = p.taps * p.c1_chunks;
       int stage = 0;
       uint32_t phase = 0;
@@ -1237,7 +1239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = instr_desc<BLOCK_N, 256>();
+      const uint32_t idesc = p.a1_f16 ? (instr_desc<BLOCK_N, 256>() & kIdescF16Mask) : instr_desc<BLOCK_N, 256>();
       int cur_mt = -1, sb = 0, it = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = t0; tile < t_end; ++tile, ++it) {
@@ -2584,6 +2586,9 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
   p.c2_chunks = (a->C2 + a->C2b) / BLOCK_K;
   p.c2a_chunks = a->C2 / BLOCK_K;
   p.a2_f16 = a->a2_dtype == VDM_F16 ? 1 : 0;
+  p.a1_f16 = a->dtype == VDM_F16 ? 1 : 0;
+  VDM_REQUIRE(!p.a1_f16 || (a->taps == 1 && a->C2 == 0 && !xf && a->w_group_tiles == 0 && !a->out_nchw),
+              "gemm_tc: dtype VDM_F16 (fp16 activations and weights) takes plain linears only");
   p.a1_mode = a->a1_mode;
   p.is_linear = is_linear;
   p.H = a->H; p.W = a->W; p.HW = HW;
@@ -2814,7 +2819,7 @@ int gemm_tc(const vdm_gemm_args* a, cudaStream_t stream, int* probe) {
       TcParams pl = p;
       pl.c2_chunks = pl.c2a_chunks = p.c1_chunks;     // all of K arrives as "second range" tiles of A1
       pl.c1_chunks = 0;
-      pl.a2_f16 = 0;
+      pl.a2_f16 = p.a1_f16;                           // (an fp16 linear: those tiles are IEEE half)
       return launch_halo_t<3, 4>(ma1, ma2, mwt, pl, stream);
     }
   }

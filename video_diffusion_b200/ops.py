@@ -93,7 +93,7 @@ def gemm(a1, w, N, **kw):
     g = _gemm_args(a1, w, N, **kw)
     M = g.n_img * g.H * g.W
     K = g.taps * g.C1 + g.C2 + g.C2b
-    name = ('gemm_tc' if g.dtype == BF16 else 'gemm_simt') + ('_conv3x3' if g.taps == 9 else '_linear')
+    name = ('gemm_tc' if g.dtype in (BF16, F16) else 'gemm_simt') + ('_conv3x3' if g.taps == 9 else '_linear')
     _timed(name, lambda: check(lib.vdm_gemm(C.byref(g), stream()), 'vdm_gemm'), flops=2.0 * M * N * K * g.n_prob,
            meta=f'M={M} N={N} K={K} HxW={g.H}x{g.W} mode={g.a1_mode} res={int(bool(g.residual))} '
                 f'stats={int(bool(g.stats_out))}' + (' norm=fused' if g.a1_coef else '') +
@@ -145,7 +145,8 @@ def gn_apply(src1, src2, n_img, H, W, out, *, stats1=None, stats2=None, gamma=No
     a.gamma, a.beta = ptr(gamma), ptr(beta)
     a.scale_shift = None if scale_shift is None else scale_shift.data_ptr()
     a.ld_ss = 0 if scale_shift is None else scale_shift.stride(0)
-    a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, dt(out.dtype)
+    # `out` may be None when only the `copy` output is wanted (the fp16 stream copy that feeds the qkv projection)
+    a.silu, a.out_mode, a.out_dtype = int(silu), out_mode, (BF16 if out is None else dt(out.dtype))
     a.out, a.out_raw, a.out_f32_copy = ptr(out), ptr(out_raw), ptr(copy)
     a.src1_dtype = dt(src1.dtype)
     a.copy_dtype = F32 if copy is None else dt(copy.dtype)
@@ -163,8 +164,9 @@ def gn_temporal(x, B, T, HW, Cc, gamma, beta, out_f32, out_a):
     lib = _lib.load()
     if out_f32 is not None and out_f32.dtype != x.dtype:
         raise TypeError('vdm_gn_temporal: the normalised residual copy has the dtype of x')
+    out_dt = BF16 if out_a is None else dt(out_a.dtype)        # out_a None: the normalised copy alone
     _timed('gn_temporal', lambda: check(lib.vdm_gn_temporal_t(ptr(x), dt(x.dtype), B, T, HW, Cc, ptr(gamma), ptr(beta),
-                                                              ptr(out_f32), ptr(out_a), dt(out_a.dtype), stream()),
+                                                              ptr(out_f32), ptr(out_a), out_dt, stream()),
                                         'vdm_gn_temporal'), nbytes=_nbytes(x, out_f32, out_a))
 
 

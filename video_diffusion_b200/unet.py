@@ -76,6 +76,8 @@ class UNetModel(nn.Module):
         self.temporal_tensor_cores = True # bf16 mode: RPE terms as grouped GEMMs + mma.sync attention core
         # bf16 mode: the whole temporal attention (RPE score terms, q.k^T, softmax, P.V, attn.R_v) as ONE kernel
         self.fused_temporal = os.environ.get('VDM_FUSED_TEMPORAL', '1') != '0'
+        # fp16 stream: the attention qkv projections read the normalised fp16 copy directly (no bf16 operand copy)
+        self.qkv_from_stream = os.environ.get('VDM_QKV_F16', '1') != '0'
         self.fuse_head_norm = os.environ.get('VDM_FUSE_HEAD', '1') != '0'   # out-head GroupNorm + SiLU inside the head conv
         self.temporal_pixels_per_cta = int(os.environ.get('VDM_TEMPORAL_PT', '0'))   # 0 = heuristic
         # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (transform warps of the halo kernels).  Correct
@@ -315,6 +317,8 @@ class UNetModel(nn.Module):
                     q = f'{p}.{which}'
                     put(q + '.gn_w', sd[q + '.norm.weight']); put(q + '.gn_b', sd[q + '.norm.bias'])
                     put(q + '.qkv_w', sd[q + '.qkv.weight'], adt); put(q + '.qkv_b', sd[q + '.qkv.bias'])
+                    if adt == torch.bfloat16:     # fp16 stream: the normalised copy xn is itself the qkv operand (VDM_F16)
+                        put(q + '.qkv_w16', sd[q + '.qkv.weight'], torch.float16)
                     put(q + '.proj_w', sd[q + '.proj_out.weight'], adt); put(q + '.proj_b', sd[q + '.proj_out.bias'])
                     if adt == torch.bfloat16:     # proj_out + identity columns (fp16): `x + proj(a)` as one GEMM, see w2s
                         pw = sd[q + '.proj_out.weight']
@@ -626,8 +630,14 @@ class UNetModel(nn.Module):
         # ---- temporal attention with RPE (unet.py:246-255, 471-540)
         q = p + '.temporal_attention'
         xn = ws.buf(q + '.xn', (M, C), self._sdt)
-        xa = ws.buf(q + '.xa', (M, C), adt)
+        # fp16 stream: xn (the normalised residual) doubles as the A operand of the qkv projection, in IEEE half
+        # with half weights -- 11 instead of 8 significand bits, and no bf16 copy `xa` written and read back
+        f16_qkv = self.qkv_from_stream and adt == torch.bfloat16 and xn.dtype == torch.float16
+        qkv_a, qkv_w = (xn, P[q + '.qkv_w16']) if f16_qkv else (None, P[q + '.qkv_w'])
+        xa = None if f16_qkv else ws.buf(q + '.xa', (M, C), adt)
         ops.gn_temporal(h, B, T, HW, C, P[q + '.gn_w'], P[q + '.gn_b'], xn, xa)
+        if qkv_a is None:
+            qkv_a = xa
         tc_path = self._tc_temporal_ok(T, C, HW)
         rows = B * T * T
         pre = tables.get(p) if tables else None
@@ -653,7 +663,7 @@ class UNetModel(nn.Module):
             # ONE kernel between the qkv projection and proj_out (csrc/attention_temporal_fused.cu)
             TP = 24 if T <= 24 else 32
             qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
-            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            ops.gemm(qkv_a, qkv_w, 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
             if pre is not None:
                 # tables of the FULL batch; a micro-batch starts at its first (b, t) group
                 g0 = tables.get('__group0__', 0) * heads * hd * 32
@@ -671,7 +681,7 @@ class UNetModel(nn.Module):
             tpg = max(1, HW // 128)                      # 128-row tiles per group
             SW, ntg = 128 * gpt, (B * T + gpt - 1) // gpt
             qkv = ws.buf(q + '.qkvb', (M, 3 * C), adt)
-            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            ops.gemm(qkv_a, qkv_w, 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
             sksq = ws.buf(q + '.sksq', (2, M, SW))
             sk, sq = sksq[0], sksq[1]
             if pre is not None:
@@ -697,7 +707,7 @@ class UNetModel(nn.Module):
             ops.gemm(pm, bv, C, residual=pv, out_bf16=att, w_group_tiles=tpg, **lin)
         else:
             qkv = ws.buf(q + '.qkv', (M, 3 * C))
-            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+            ops.gemm(qkv_a, qkv_w, 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
             ops.attn_temporal(qkv, R[0], R[1], R[2], amask, self.allow_interactions_between_padding, B, T, HW, heads,
                               hd, att)
         if attn_log is not None:
@@ -716,13 +726,16 @@ class UNetModel(nn.Module):
         # ---- spatial attention (unet.py:258-266)
         q = p + '.spatial_attention'
         xn = ws.buf(q + '.xn', (M, C), self._sdt)
-        xa = ws.buf(q + '.xa', (M, C), adt)
+        qkv_a, qkv_w = (xn, P[q + '.qkv_w16']) if f16_qkv else (None, P[q + '.qkv_w'])
+        xa = None if f16_qkv else ws.buf(q + '.xa', (M, C), adt)
         ops.gn_apply(h2, None, N, H, W, xa, stats1=st, gamma=P[q + '.gn_w'], beta=P[q + '.gn_b'], copy=xn)
+        if qkv_a is None:
+            qkv_a = xa
         qkv = ws.buf(q + '.qkv', (M, 3 * C), adt)       # bf16 mode: tensor-core flash kernel on bf16 q, k, v
         if adt == torch.bfloat16:
-            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
+            ops.gemm(qkv_a, qkv_w, 3 * C, bias=P[q + '.qkv_b'], out_bf16=qkv, **lin)
         else:
-            ops.gemm(xa, P[q + '.qkv_w'], 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
+            ops.gemm(qkv_a, qkv_w, 3 * C, bias=P[q + '.qkv_b'], out_f32=qkv, **lin)
         att = ws.buf(q + '.att', (M, C), adt)
         ops.attn_spatial(qkv, N, HW, heads, hd, att)
         if attn_log is not None:
