@@ -208,16 +208,43 @@ def test_micro_batches_equal_whole_batch(golden, graph):
           for k, v in cases.model_kwargs_for(inp).items()}
     t4 = torch.cat([inp['t_model'], inp['t_model'].flip(0)]).cuda()
     outs = {}
-    for n in (1, 2):
-        model.micro_batches = n
+    # (micro-batches, join threshold): the groups may also meet for the small levels (micro_batch_join_hw, opt-in) --
+    # 256: the 16x16 level and below run on the whole batch, 64: only the 8x8 level and below
+    for n, join in ((1, 0), (2, 0), (2, 256), (2, 64)):
+        model.micro_batches, model.micro_batch_join_hw = n, join
         model._workspaces = {}
         with torch.no_grad():
-            outs[n], _ = model(x4, t4, **kw)
+            outs[n, join], _ = model(x4, t4, **kw)
             again, _ = model(x4, t4, **kw)
-        assert torch.equal(again, outs[n])
+        assert torch.equal(again, outs[n, join])
         ws = next(iter(model._workspaces.values()))
         assert len(ws.children) == (2 if n == 2 else 0)
-    assert torch.equal(outs[1], outs[2])
+        if join:
+            assert model._deep_range(ws.H, ws.W)[0] is not None           # the plan really was run in three pieces
+    assert all(torch.equal(outs[1, 0], o) for o in outs.values())
+
+
+def test_session3_paths_against_the_paths_they_replace(golden):
+    """The defaults added in round 2, session 3 -- temporal attention as one kernel, the output head with its
+    GroupNorm-apply fused in, qkv projections reading the fp16 stream copy -- against the launches they replace, on the
+    tiny and on the full-size C2 architecture: same eps to well inside the bf16 tolerance (the fused head is
+    bit-identical by construction, the other two change rounding points)."""
+    for case, inp in ((cases.UNET_CASES[1], None), (dict(cases.FULL_CASES[0], F=8, n_obs=[3], n_lat=[5]), 'full')):
+        inp = cases.unet_case_inputs(case) if inp is None else cases.full_case_inputs(case)
+        kw = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cases.model_kwargs_for(inp).items()}
+        outs = {}
+        for name, flags in (('default', {}), ('three_launch', dict(fused_temporal=False)),
+                            ('head_unfused', dict(fuse_head_norm=False)), ('qkv_bf16', dict(qkv_from_stream=False))):
+            model, _ = build_model(case['cfg'], golden, torch.bfloat16)
+            for k, v in flags.items():
+                setattr(model, k, v)
+            with torch.no_grad():
+                outs[name], _ = model(inp['x'].cuda(), inp['t_model'].cuda(), **kw)
+        ref = outs['default'].float()
+        scale = float(ref.abs().max())
+        assert torch.equal(outs['head_unfused'], outs['default'])
+        for name in ('three_launch', 'qkv_bf16'):
+            assert float((outs[name].float() - ref).abs().max()) / scale < 1e-2, name
 
 
 def test_fused_norm_model_equals_standalone(golden, monkeypatch):

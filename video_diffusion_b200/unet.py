@@ -1081,7 +1081,7 @@ class UNetModel(nn.Module):
         if Cc != 3:
             raise NotImplementedError('3-channel frames only')
         key = (B, F, H, W, str(x.device), per_frame_t is not None, self._sdt, self.micro_batches, self.fuse_norm,
-               self.pipeline_norm)
+               self.pipeline_norm, self.micro_batch_join_hw, self.fused_temporal, self.fuse_head_norm, self.qkv_from_stream)
         ws = self._workspaces.get(key)
         if ws is None:
             chans = sum((n['cin'] + 3 * n['cout']) if n['kind'] == 'res' else 3 * n.get('C', self.model_channels)
