@@ -583,7 +583,9 @@ def main():
             step_resident()
         with ClockSampler(local) as clk:
             ms = timed(step_resident, args.steps)
-        for _ in range(args.warmup):
+        # (the pipelined stepper hands its results to a copy stream -- record_stream -- so the caching allocator needs a
+        # few more steps than the resident loop before it stops growing: at least 8 untimed steps for this leg)
+        for _ in range(max(args.warmup, 8)):
             step_e2e()
         e2e_finish()
         ms_e2e = timed(step_e2e, args.steps, e2e_finish)
@@ -619,7 +621,7 @@ def main():
                 'd2h_bytes_per_step': int(out_pin.numel() * 4), 'ms_per_step': ms_e2e / args.steps,
                 'api': 'sampling.PipelinedHostStepper.step (diffusion.p_sample on pinned host tensors; transfers on a '
                        'copy stream under the neighbouring steps, all inside the timed region, last download drained)',
-                'ms_per_step_serial': ms_e2e_serial / args.steps},
+                'ms_per_step_serial': ms_e2e_serial / args.steps, 'warmup_steps': max(args.warmup, 8)},
         'gpu_launches': int(launches_per_step * args.steps),
         'roofline': {'bound': 'tensor',
                      'kernel': 'whole U-Net forward (SURVEY 8d algorithmic FLOPs) over the graph-replayed step; dominant '
