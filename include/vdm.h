@@ -217,6 +217,15 @@ int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const f
                  int32_t W, int32_t mode, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
                  vdm_stream_t stream);
 
+/* The inputs of one forward (the caller's x, x0, per-frame masks, per-video timesteps, frame indices) into the
+ * address-stable workspace tensors the captured CUDA graph reads -- ONE launch instead of seven device-to-device copies
+ * around every graph replay (the host side of UNetModel.forward's argument handling, unet.py:949-1013).  All tensors
+ * contiguous; x / x0: `elems` fp32 each (a multiple of 4); masks [B*F] fp32; t [B] fp32; frame_indices [B*F] int64 or NULL. */
+int vdm_stage_inputs(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
+                     const float* kinda_marg_mask, const float* t, const int64_t* frame_indices, int32_t B, int32_t F,
+                     int64_t elems, float* ws_x, float* ws_x0, float* ws_obs, float* ws_lat, float* ws_kinda, float* ws_t,
+                     int64_t* ws_fi, vdm_stream_t stream);
+
 /* sinusoidal embedding (nn.py:89-107, 110-122): out[n] = [cos(t*f_i) | sin(t*f_i)], f_i = exp(-ln(max_period) i / half);
  * max_period = 10000 for diffusion time, 10 T for frame indices */
 int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, double max_period, float* out,

@@ -144,6 +144,43 @@ def test_pipelined_host_stepper_equals_direct_p_sample(golden, replay):
         assert torch.equal(a, b)
 
 
+def test_staged_inputs_and_borrowed_output_keep_the_api_semantics(golden, replay):
+    """The host side of a step: the per-call input copies as one launch (vdm_stage_inputs) and eps handed to the sampler
+    without a copy.  Same samples as the seven-copy path bit for bit; a direct model call still returns a tensor of its
+    own (the next forward must not change it); non-contiguous / expanded inputs take the copy path."""
+    c = cases.CHAIN_CASE
+    model, diffusion = build_model(c['cfg'], golden, torch.bfloat16, respacing=c['respacing'])
+    B, F, S = 2, c['max_frames'], c['image_size']
+    x0 = synth.make_video((B, F, 3, S, S), seed=40).cuda()
+    om = torch.zeros(B, F, 1, 1, 1, device='cuda')
+    om[:, :4] = 1
+    fi = torch.arange(F, device='cuda').view(1, F).repeat(B, 1)
+    kw = dict(x0=x0, obs_mask=om, latent_mask=1 - om, kinda_marg_mask=torch.zeros_like(om), frame_indices=fi,
+              x_t_minus_1=x0, observed_frames='x_0')
+    x = synth.make_noise((B, F, 3, S, S), seed=61).cuda()
+    t = torch.tensor([7, 2]).cuda()
+    outs = {}
+    for fused in (True, False):
+        model.stage_inputs_fused = fused
+        replay(901)
+        outs[fused] = diffusion.p_sample(model, x, t, model_kwargs=kw)['sample'].clone()
+    assert torch.equal(outs[True], outs[False])
+    model.stage_inputs_fused = True
+    # expanded frame indices (the reference's default arange(F).expand) and a non-contiguous x0 take the copy path
+    kw2 = dict(kw, frame_indices=torch.arange(F, device='cuda').view(1, F).expand(B, F),
+               x0=x0.transpose(0, 1).contiguous().transpose(0, 1))
+    kw2['x_t_minus_1'] = kw2['x0']
+    replay(901)
+    assert torch.equal(diffusion.p_sample(model, x, t, model_kwargs=kw2)['sample'], outs[True])
+    # a direct call owns its result
+    wrapped = diffusion._wrap_model(model) if hasattr(diffusion, '_wrap_model') else model
+    with torch.no_grad():
+        e1, _ = wrapped(x, t, **kw)
+        keep = e1.clone()
+        e2, _ = wrapped(x * 0.5, t, **kw)
+    assert torch.equal(e1, keep) and e1.data_ptr() != e2.data_ptr()
+
+
 def test_async_sample_writer_overlaps_and_matches_save_samples(golden, replay, tmp_path):
     """Finished frames leave the device on a copy stream while the next window runs; the files equal
     save_samples(to_uint8(samples)) (scripts/video_sample.py:179-189, 266-272)."""

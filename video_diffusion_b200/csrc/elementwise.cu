@@ -960,6 +960,54 @@ extern "C" int vdm_cond_mix(const float* x, const float* x0, const float* obs_ma
   return 0;
 }
 
+// One launch for the inputs of a forward: the caller's tensors into the address-stable workspace the CUDA graph reads
+// (two big fp32 tensors through float4 copies, the per-frame masks / timesteps / frame indices by the first block).
+__global__ void __launch_bounds__(256) stage_inputs_kernel(const float4* __restrict__ x, const float4* __restrict__ x0,
+                                                            float4* __restrict__ wx, float4* __restrict__ wx0,
+                                                            long long n4, const float* __restrict__ obs,
+                                                            const float* __restrict__ lat, const float* __restrict__ kinda,
+                                                            float* __restrict__ wobs, float* __restrict__ wlat,
+                                                            float* __restrict__ wkinda, int BF, const float* __restrict__ t,
+                                                            float* __restrict__ wt, int B, const long long* __restrict__ fi,
+                                                            long long* __restrict__ wfi) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(x + i), b = __ldg(x0 + i);
+    wx[i] = a;
+    wx0[i] = b;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < BF; i += blockDim.x) {
+      wobs[i] = obs[i];
+      wlat[i] = lat[i];
+      wkinda[i] = kinda[i];
+      if (fi != nullptr) wfi[i] = fi[i];
+    }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) wt[i] = t[i];
+  }
+}
+
+extern "C" int vdm_stage_inputs(const float* x, const float* x0, const float* obs_mask, const float* latent_mask,
+                                const float* kinda_marg_mask, const float* t, const int64_t* frame_indices, int32_t B,
+                                int32_t F, int64_t elems, float* ws_x, float* ws_x0, float* ws_obs, float* ws_lat,
+                                float* ws_kinda, float* ws_t, int64_t* ws_fi, vdm_stream_t stream) {
+  VDM_REQUIRE(x && x0 && obs_mask && latent_mask && kinda_marg_mask && t && ws_x && ws_x0 && ws_obs && ws_lat &&
+                  ws_kinda && ws_t && (frame_indices == nullptr || ws_fi),
+              "stage_inputs: NULL pointer");
+  VDM_REQUIRE(elems > 0 && elems % 4 == 0 && B > 0 && F > 0, "stage_inputs: elems=%lld must be a positive multiple of 4",
+              (long long)elems);
+  const long long n4 = elems / 4;
+  const int grid = (int)std::min<long long>((n4 + 255) / 256, 4LL * num_sms());
+  launch_kernel(stage_inputs_kernel, grid, 256, 0, (cudaStream_t)stream, 1, reinterpret_cast<const float4*>(x),
+                reinterpret_cast<const float4*>(x0), reinterpret_cast<float4*>(ws_x), reinterpret_cast<float4*>(ws_x0), n4,
+                obs_mask, latent_mask, kinda_marg_mask, ws_obs, ws_lat, ws_kinda, B * F, t, ws_t, B,
+                reinterpret_cast<const long long*>(frame_indices), reinterpret_cast<long long*>(ws_fi));
+  VDM_AFTER_LAUNCH("stage_inputs");
+  return 0;
+}
+
 extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, double max_period, float* out,
                                       vdm_stream_t stream) {
   VDM_REQUIRE(t_frame && out && n > 0 && dim >= 2 && max_period > 0, "timestep_embedding: bad arguments");

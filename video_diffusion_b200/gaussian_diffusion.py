@@ -143,7 +143,18 @@ class GaussianDiffusion:
         return t
 
     def _eps(self, model, x, t, model_kwargs, return_attn_weights=False):
-        out, attn = model(x, self._scale_timesteps(t), return_attn_weights=return_attn_weights, **(model_kwargs or {}))
+        # every caller feeds eps to a libvdm kernel before the next forward: let the B200 model hand out its workspace
+        # tensor instead of a copy (a stand-in network has no such flag and is called as is)
+        inner = getattr(model, 'model', model)
+        borrow = hasattr(inner, '_borrow_output')
+        if borrow:
+            inner._borrow_output = True
+        try:
+            out, attn = model(x, self._scale_timesteps(t), return_attn_weights=return_attn_weights,
+                              **(model_kwargs or {}))
+        finally:
+            if borrow:
+                inner._borrow_output = False
         if out.shape != x.shape:
             raise NotImplementedError('model output shape %s != input shape %s (learned sigma?)'
                                       % (tuple(out.shape), tuple(x.shape)))

@@ -182,6 +182,16 @@ def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask, m
         ptr(attn_mask), stream()), 'vdm_cond_mix'), nbytes=_nbytes(x, x0, a_out))
 
 
+def stage_inputs(x, x0, obs, lat, kinda, t, fi, ws):
+    """The inputs of a forward into the workspace tensors of `ws`, one launch (vdm_stage_inputs); fi may be None."""
+    B, F = ws.B, ws.F
+    _timed('stage_inputs', lambda: check(_lib.load().vdm_stage_inputs(
+        ptr(x, torch.float32), ptr(x0, torch.float32), ptr(obs, torch.float32), ptr(lat, torch.float32),
+        ptr(kinda, torch.float32), ptr(t, torch.float32), ptr(fi, torch.long), B, F, x.numel(), ptr(ws.x), ptr(ws.x0),
+        ptr(ws.obs), ptr(ws.lat), ptr(ws.kinda), ptr(ws.t), ptr(ws.fi), stream()), 'vdm_stage_inputs'),
+           nbytes=4.0 * x.numel() * 4)
+
+
 def timestep_embedding(t_frame, dim, out, max_period=10000.0):
     _timed('timestep_embedding', lambda: check(_lib.load().vdm_timestep_embedding(
         ptr(t_frame), t_frame.numel(), dim, float(max_period), ptr(out), stream()), 'vdm_timestep_embedding'))

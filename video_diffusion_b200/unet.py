@@ -78,6 +78,8 @@ class UNetModel(nn.Module):
         self.fused_temporal = os.environ.get('VDM_FUSED_TEMPORAL', '1') != '0'
         # fp16 stream: the attention qkv projections read the normalised fp16 copy directly (no bf16 operand copy)
         self.qkv_from_stream = os.environ.get('VDM_QKV_F16', '1') != '0'
+        self.stage_inputs_fused = os.environ.get('VDM_STAGE_INPUTS', '1') != '0'   # one launch for the per-call input copies
+        self._borrow_output = False
         self.fuse_head_norm = os.environ.get('VDM_FUSE_HEAD', '1') != '0'   # out-head GroupNorm + SiLU inside the head conv
         self.temporal_pixels_per_cta = int(os.environ.get('VDM_TEMPORAL_PT', '0'))   # 0 = heuristic
         # bf16 mode: GroupNorm-apply + SiLU inside the conv's operand path (transform warps of the halo kernels).  Correct
@@ -1087,13 +1089,23 @@ class UNetModel(nn.Module):
             chans = sum((n['cin'] + 3 * n['cout']) if n['kind'] == 'res' else 3 * n.get('C', self.model_channels)
                         for n in self.plan) + 2 * self.model_channels
             ws = self._workspaces[key] = self._Workspace(B, F, H, W, x.device, 2 * B * F * chans)
-        ws.x.copy_(x)
-        ws.x0.copy_(x0)
-        ws.obs.copy_(obs.reshape(B, F))
-        ws.lat.copy_(lat.reshape(B, F))
-        ws.kinda.copy_(kinda.reshape(B, F))
-        ws.t.copy_(t.reshape(B))
-        ws.fi.copy_(frame_indices.reshape(B, F))
+        def plain(v, n, dtype=torch.float32):
+            return torch.is_tensor(v) and v.is_cuda and v.dtype == dtype and v.is_contiguous() and v.numel() == n
+        if (self.stage_inputs_fused and plain(x, ws.x.numel()) and plain(x0, ws.x.numel()) and x.numel() % 4 == 0
+                and plain(obs, B * F) and plain(lat, B * F) and plain(kinda, B * F) and plain(t, B)):
+            # one launch instead of seven device-to-device copies around every graph replay
+            fi_ok = plain(frame_indices, B * F, torch.long)
+            ops.stage_inputs(x, x0, obs, lat, kinda, t, frame_indices if fi_ok else None, ws)
+            if not fi_ok:
+                ws.fi.copy_(frame_indices.reshape(B, F))
+        else:
+            ws.x.copy_(x)
+            ws.x0.copy_(x0)
+            ws.obs.copy_(obs.reshape(B, F))
+            ws.lat.copy_(lat.reshape(B, F))
+            ws.kinda.copy_(kinda.reshape(B, F))
+            ws.t.copy_(t.reshape(B))
+            ws.fi.copy_(frame_indices.reshape(B, F))
         if self.use_frame_encoding:
             fi = frame_indices.reshape(B, F).float()
             ws.fi_float.copy_(fi - fi.mean(dim=1, keepdim=True) if self.enforce_position_invariance else fi)
@@ -1113,7 +1125,10 @@ class UNetModel(nn.Module):
             out = ws.out
         else:
             out = self._run(ws, T_attn, per_frame_t is not None)
-        return out.clone() if clone else out
+        # gaussian_diffusion._eps consumes eps in the next kernel of the same stream: it borrows the workspace tensor
+        # (one flag, cleared by the call it applies to) instead of paying for a copy per step
+        borrow, self._borrow_output = self._borrow_output, False
+        return out.clone() if (clone and not borrow) else out
 
     def forward(self, x, timesteps, y=None, attn_mask=None, T=1, return_attn_weights=False, frame_indices=None,
                 **kwargs):
