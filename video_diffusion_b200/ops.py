@@ -14,6 +14,9 @@ from ._lib import BF16, F16, F32, GemmArgs, GnApplyArgs, check, dt, ptr, stream
 # brackets its launch with CUDA events on the current stream and appends
 # (kernel name, start event, end event, algorithmic flops, algorithmic bytes).
 PROFILE = None
+# Timeline mode (profiles/step_timeline.py): with PROFILE_STREAMS a list as well, the model keeps its micro-batch and
+# side streams while profiling, and every record's stream handle is appended here (same index as in PROFILE).
+PROFILE_STREAMS = None
 
 
 def _timed(name, fn, flops=0.0, nbytes=0.0, meta=''):
@@ -24,6 +27,8 @@ def _timed(name, fn, flops=0.0, nbytes=0.0, meta=''):
     fn()
     e1.record()
     PROFILE.append((name, e0, e1, flops, nbytes, meta))
+    if PROFILE_STREAMS is not None:
+        PROFILE_STREAMS.append(torch.cuda.current_stream().cuda_stream)
 
 
 def _nbytes(*tensors):

@@ -806,7 +806,7 @@ class UNetModel(nn.Module):
         # latency-bound launches would otherwise leave the GPU idle.  Two joins: the embedding projections before
         # the first scale/shift GroupNorm, the tables before the first attention block.
         tables, emb_join, rpe_join = None, None, None
-        if self.overlap_rpe_tables and ops.PROFILE is None:
+        if self.overlap_rpe_tables and (ops.PROFILE is None or ops.PROFILE_STREAMS is not None):
             main = torch.cuda.current_stream()
             if ws.side is None:
                 ws.side = torch.cuda.Stream(device=ws.dev)
@@ -839,7 +839,8 @@ class UNetModel(nn.Module):
     # ---- micro-batches -----------------------------------------------------------------------------
     def _micro_batches_for(self, ws, attn_log):
         n = self.micro_batches
-        if (n <= 1 or self.compute_dtype != torch.bfloat16 or attn_log is not None or ops.PROFILE is not None
+        if (n <= 1 or self.compute_dtype != torch.bfloat16 or attn_log is not None
+                or (ops.PROFILE is not None and ops.PROFILE_STREAMS is None)
                 or ws.B % n or (ws.B // n * ws.F) % 2):     # (b, t) groups of the RPE tables pair up images at 8x8
             return 1
         return n
