@@ -211,6 +211,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       : "memory");
 }
 
+// The same without release semantics: handing a drained TMEM accumulator stage back to the leader's MMA thread publishes
+// no generic-proxy data (the tcgen05.ld's are complete -- tcgen05.wait::ld -- and ordered by
+// tcgen05.fence::before_thread_sync), and the release form costs a MEMBAR.ALL.CTA + ERRBAR per warp and tile that waits for
+// the lane's staging stores (ncu: 17 % of the samples of the short-K linears sat on it).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+
 // ---- cluster multicast forms used by the transposed halo kernel (two independent cta_group::1 CTAs that share
 // every weight tile): a TMA load lands at the same shared-memory offset in every CTA of the mask and signals the
 // mbarrier at the same offset there; a commit arrives on the barrier of every CTA of the mask.
@@ -712,7 +725,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, float* stg_base
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-      if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
+      if constexpr (CTA2) mbar_arrive_cluster_relaxed(tmem_empty_bar(as), 0);   // the leader's MMA thread owns the wait
       else mbar_arrive(tmem_empty_bar(as));
     }
     if (use_tab) {
@@ -781,10 +794,6 @@ __device__ __forceinline__ void epilogue_ts_role(const TcParams& p, const CUtens
     const int m0 = (tl / n_tiles_n) * TILE_M + (int)cta_rank * BLOCK_M;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-    if (it > 0) {   // the previous tile's stores must have READ the staging area before it is overwritten
-      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    }
     mbar_wait(tmem_full_bar0 + 8u * as, aphase, 2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -801,6 +810,12 @@ __device__ __forceinline__ void epilogue_ts_role(const TcParams& p, const CUtens
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+      }
+      if (jj == half && it > 0) {
+        // the previous tile's stores must have READ the staging area before it is overwritten -- waited for here, under
+        // the TMEM and bias loads of this warp's first chunk, not in front of them
+        if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if constexpr (BF16) {         // 32 columns = 64 B = four 16-byte pieces of slab jj / 2
@@ -829,7 +844,7 @@ __device__ __forceinline__ void epilogue_ts_role(const TcParams& p, const CUtens
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-      if constexpr (CTA2) mbar_arrive_cluster(tmem_empty_bar0 + 8u * as, 0);
+      if constexpr (CTA2) mbar_arrive_cluster_relaxed(tmem_empty_bar0 + 8u * as, 0);
       else mbar_arrive(tmem_empty_bar0 + 8u * as);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
