@@ -26,3 +26,17 @@ for _ in range(3):
     ops.gemm(att, wp, C, n_img=160, H=16, W=16, taps=1, bias=bias, residual=res, out_f32=out, stats_out=st)
 torch.cuda.synchronize()
 print('ok')
+
+# (--convs) two convolutions of the step as well: 8x8 512->512 (interleaved halo pair kernel, 80 pair tiles on 74 pairs)
+# and 64x64 128->128 (transposed-role kernel, the epilogue-heavy K = 1152 shape)
+if '--convs' in sys.argv:
+    for (n, H, Cc, N) in ((160, 8, 512, 512), (160, 64, 128, 128)):
+        x = torch.randn(n * H * H, Cc, device=dev).bfloat16()
+        w = (torch.randn(N, 9 * Cc, device=dev) * 0.02).bfloat16()
+        b = torch.zeros(N, device=dev)
+        o16 = torch.empty(n * H * H, N, device=dev, dtype=torch.float16)
+        stc = torch.zeros(n, 2, N, device=dev, dtype=torch.int64)
+        for _ in range(2):
+            ops.gemm(x, w, N, n_img=n, H=H, W=H, taps=9, bias=b, out_f32=o16, stats_out=stc)
+    torch.cuda.synchronize()
+    print('convs ok')
