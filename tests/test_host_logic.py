@@ -180,3 +180,29 @@ def test_checkpoint_loader_and_elbo_pickles(golden, tmp_path):
     assert [p.name for p in paths] == ['elbo_7_s.pkl', 'elbo_8_s.pkl', 'elbo_11_s.pkl']
     d = pickle.load(open(paths[1], 'rb'))
     assert d['total_bpd'].shape == (2,) and d['vb'].shape == (2, 5) and d['total_bpd'][1] == 2.0
+
+
+def test_micro_batch_join_range_of_the_launch_plan():
+    """micro_batch_join_hw (opt-in): the plan pieces between which the two groups of videos meet -- from the downsample
+    whose output has at most that many pixels to the upsample that leaves those levels.  Pure host logic."""
+    from video_diffusion_b200 import create_video_model_and_diffusion, video_model_and_diffusion_defaults
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config('c2'))
+    model, _ = create_video_model_and_diffusion(**kw)
+    want = {0: (None, None), 4096: (None, None),           # off / no downsample lands at 64x64
+            64: ('input_blocks.9.0.op', 'output_blocks.2.2.conv'),        # the 8x8 level only
+            256: ('input_blocks.6.0.op', 'output_blocks.5.2.conv'),       # 16x16 and 8x8
+            1024: ('input_blocks.3.0.op', 'output_blocks.8.1.conv')}      # 32x32 and below
+    for hw, (p_first, p_last) in want.items():
+        model.micro_batch_join_hw = hw
+        first, last = model._deep_range(64, 64)
+        if p_first is None:
+            assert first is None and last is None
+            continue
+        assert (model.plan[first]['kind'], model.plan[first]['p']) == ('down', p_first)
+        assert (model.plan[last]['kind'], model.plan[last]['p']) == ('up', p_last)
+        # between them the pushes and pops of the skip stack balance: one push per input block, one pop per res block
+        # of the output path
+        pushes = len({n['group'] for n in model.plan[first:last] if n['group'].startswith('input')})
+        pops = sum(1 for n in model.plan[first + 1:last] if n['kind'] == 'res' and n.get('cat'))
+        assert pushes == pops
