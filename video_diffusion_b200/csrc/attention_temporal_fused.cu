@@ -104,9 +104,10 @@ __device__ __forceinline__ float lds_f(uint32_t a) {
 __device__ __forceinline__ void sts_f(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 
-// Row pitch (bytes) of a staged q / k / v row: == 64 (mod 128), so the 16-byte A-fragment reads of two adjacent
-// pixel rows (one quarter-warp) cover all 32 banks; consecutive frames of a pixel are TSTR = PT * pitch + 16 apart, so
-// the eight rows of an ldmatrix (consecutive frames, one pixel) fall into eight different 16-byte bank groups.
+// Row pitch (bytes) of a staged q / k / v row: == 64 (mod 128), so the 16-byte B-fragment reads of two adjacent
+// pixel rows (one quarter-warp of the RPE phases) cover all 32 banks; consecutive frames of a pixel are
+// TSTR = PT * pitch + 16 apart, so the eight rows of an ldmatrix of the per-pixel phases (consecutive frames, one pixel)
+// fall into eight different 16-byte bank groups.
 template <int HD>
 struct FusedCfg {
   static constexpr int LDSB = (HD * 2) % 128 == 64 ? HD * 2 : HD * 2 + 64;
