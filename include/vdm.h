@@ -217,6 +217,12 @@ int vdm_cond_mix(const float* x, const float* x0, const float* obs_mask, const f
                  int32_t W, int32_t mode, void* a_out, int32_t out_dtype, float* t_frame, float* attn_mask,
                  vdm_stream_t stream);
 
+/* `_WrappedModel.__call__` (respace.py:113-119) as one launch: out[i] = (float)timestep_map[clamp(t[i], 0, n_map-1)] * scale
+ * (scale = 1000 / original_num_steps when rescale_timesteps, else 1).  An index outside the map is clamped here and
+ * reported by the sampler kernels that receive the same t (vdm_sampler_error). */
+int vdm_map_timesteps(const int64_t* t, const int64_t* timestep_map, int32_t n_map, float scale, float* out, int32_t B,
+                      vdm_stream_t stream);
+
 /* The inputs of one forward (the caller's x, x0, per-frame masks, per-video timesteps, frame indices) into the
  * address-stable workspace tensors the captured CUDA graph reads -- ONE launch instead of seven device-to-device copies
  * around every graph replay (the host side of UNetModel.forward's argument handling, unet.py:949-1013).  All tensors

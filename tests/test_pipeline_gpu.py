@@ -181,6 +181,29 @@ def test_staged_inputs_and_borrowed_output_keep_the_api_semantics(golden, replay
     assert torch.equal(e1, keep) and e1.data_ptr() != e2.data_ptr()
 
 
+def test_wrapped_model_timestep_map_in_one_launch():
+    """respace.py:113-119: the timestep-map gather + rescale of `_WrappedModel` as one libvdm launch gives the bits of
+    the torch expression; tensors the kernel does not take (2-D per-frame timesteps, no rescale) keep the torch path."""
+    from video_diffusion_b200 import create_gaussian_diffusion
+    seen = {}
+
+    class Probe(torch.nn.Module):
+        def forward(self, x, timesteps=None, **kw):
+            seen['t'] = timesteps
+            return x, None
+
+    for respacing, steps in (('ddim10', 1000), ('10,15,20', 300), ('', 1000)):
+        d = create_gaussian_diffusion(steps=steps, rescale_timesteps=True, timestep_respacing=respacing)
+        wrapped = d._wrap_model(Probe())
+        t = torch.tensor([0, 3, d.num_timesteps - 1], device='cuda')
+        wrapped(torch.zeros(3, 1, device='cuda'), t)
+        tmap = torch.tensor(d.timestep_map, device='cuda')
+        want = tmap[t].float() * (1000.0 / steps)
+        assert seen['t'].dtype == torch.float32 and torch.equal(seen['t'], want)
+        wrapped(torch.zeros(3, 1, device='cuda'), t.view(3, 1).expand(3, 2))          # per-frame timesteps: torch path
+        assert torch.equal(seen['t'], (tmap[t].float() * (1000.0 / steps)).view(3, 1).expand(3, 2))
+
+
 def test_async_sample_writer_overlaps_and_matches_save_samples(golden, replay, tmp_path):
     """Finished frames leave the device on a copy stream while the next window runs; the files equal
     save_samples(to_uint8(samples)) (scripts/video_sample.py:179-189, 266-272)."""

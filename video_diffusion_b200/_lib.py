@@ -18,7 +18,7 @@ TAB = dict(SQRT_RECIP_ACP=0, SQRT_RECIPM1_ACP=1, POST_C1=2, POST_C2=3, MODEL_LOG
 TAB_COUNT = 16
 
 EXPORTS = ['vdm_version', 'vdm_last_error_string', 'vdm_launch_count', 'vdm_gemm_set_trace', 'vdm_gemm', 'vdm_gemm_fused_norm_supported', 'vdm_gemm_img_done_supported', 'vdm_gn_stats', 'vdm_gn_stats_t', 'vdm_gn_apply', 'vdm_gn_coef',
-           'vdm_gn_temporal', 'vdm_gn_temporal_t', 'vdm_add_spatial_encoding', 'vdm_add_spatial_encoding_t', 'vdm_cond_mix', 'vdm_stage_inputs', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
+           'vdm_gn_temporal', 'vdm_gn_temporal_t', 'vdm_add_spatial_encoding', 'vdm_add_spatial_encoding_t', 'vdm_cond_mix', 'vdm_stage_inputs', 'vdm_map_timesteps', 'vdm_timestep_embedding', 'vdm_rpe_hidden',
            'vdm_attn_temporal', 'vdm_rpe_lookup', 'vdm_rpe_expand', 'vdm_attn_temporal_tc', 'vdm_rpe_pack', 'vdm_attn_temporal_fused', 'vdm_attn_temporal_fused_smem', 'vdm_attn_temporal_fused_set_trace', 'vdm_attn_spatial', 'vdm_attn_weights_mean', 'vdm_sampler_error', 'vdm_sampler_step', 'vdm_q_sample', 'vdm_lincomb',
            'vdm_vb_terms', 'vdm_prior_bpd']
 
@@ -83,6 +83,7 @@ def load():
         'vdm_attn_temporal_fused_smem': [_i32, _i32, _i32, _i32],
         'vdm_attn_temporal_fused_set_trace': [_vp],
         'vdm_attn_temporal_fused': [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+        'vdm_map_timesteps': [_vp, _vp, _i32, _f32, _vp, _i32, _vp],
         'vdm_stage_inputs': [_vp] * 7 + [_i32, _i32, _i64] + [_vp] * 8,
         'vdm_sampler_step': [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp],
         'vdm_q_sample': [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp],

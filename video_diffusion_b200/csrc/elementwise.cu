@@ -1008,6 +1008,28 @@ extern "C" int vdm_stage_inputs(const float* x, const float* x0, const float* ob
   return 0;
 }
 
+// respace.py:113-119 as one launch: new_ts = timestep_map[clamp(t)] (optionally * 1000 / original_num_steps, fp32).
+__global__ void map_timesteps_kernel(const long long* __restrict__ t, const long long* __restrict__ tmap, int n_map,
+                                     float scale, float* __restrict__ out, int B) {
+  pdl_launch_dependents();
+  pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    long long k = t[i];
+    k = k < 0 ? 0 : (k >= n_map ? n_map - 1 : k);
+    out[i] = (float)tmap[k] * scale;
+  }
+}
+
+extern "C" int vdm_map_timesteps(const int64_t* t, const int64_t* timestep_map, int32_t n_map, float scale, float* out,
+                                 int32_t B, vdm_stream_t stream) {
+  VDM_REQUIRE(t && timestep_map && out && n_map > 0 && B > 0, "map_timesteps: bad arguments");
+  launch_kernel(map_timesteps_kernel, (B + 127) / 128, 128, 0, (cudaStream_t)stream, 1,
+                reinterpret_cast<const long long*>(t), reinterpret_cast<const long long*>(timestep_map), n_map, scale, out, B);
+  VDM_AFTER_LAUNCH("map_timesteps");
+  return 0;
+}
+
 extern "C" int vdm_timestep_embedding(const float* t_frame, int32_t n, int32_t dim, double max_period, float* out,
                                       vdm_stream_t stream) {
   VDM_REQUIRE(t_frame && out && n > 0 && dim >= 2 && max_period > 0, "timestep_embedding: bad arguments");

@@ -187,6 +187,15 @@ def cond_mix(x, x0, obs, lat, kinda, t, B, F, H, W, a_out, t_frame, attn_mask, m
         ptr(attn_mask), stream()), 'vdm_cond_mix'), nbytes=_nbytes(x, x0, a_out))
 
 
+def map_timesteps(t, tmap, scale):
+    """respace.py:113-119 in one launch: float32 (timestep_map[clamp(t)] * scale)."""
+    out = torch.empty(t.shape, device=t.device, dtype=torch.float32)
+    _timed('map_timesteps', lambda: check(_lib.load().vdm_map_timesteps(
+        ptr(t, torch.long), ptr(tmap, torch.long), tmap.numel(), float(scale), ptr(out), t.numel(), stream()),
+        'vdm_map_timesteps'))
+    return out
+
+
 def stage_inputs(x, x0, obs, lat, kinda, t, fi, ws):
     """The inputs of a forward into the workspace tensors of `ws`, one launch (vdm_stage_inputs); fi may be None."""
     B, F = ws.B, ws.F

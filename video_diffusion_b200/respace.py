@@ -84,6 +84,13 @@ class _WrappedModel:
         # -- a device-side assert would poison the CUDA context -- and the sampler kernels, which receive the same
         # unclamped t, record it: the next ops.check_timesteps() raises the IndexError.
         tmap = self._cache[key]
+        if (self.rescale_timesteps and timesteps.is_cuda and timesteps.dtype == th.long and timesteps.dim() == 1
+                and timesteps.is_contiguous()):
+            # gather + rescale as one launch (the same fp32 product as below)
+            from . import ops
+            with th.cuda.device(timesteps.device):
+                new_ts = ops.map_timesteps(timesteps, tmap, 1000.0 / self.original_num_steps)
+            return self.model(x, timesteps=new_ts, **kwargs)
         new_ts = tmap[timesteps.long().clamp(0, tmap.numel() - 1)]
         if self.rescale_timesteps:
             new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
