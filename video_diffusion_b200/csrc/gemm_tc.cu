@@ -1161,7 +1161,8 @@ struct AStatLayout {
   static constexpr int STAT_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int STAT_BYTES = TS_ESIZE ? 0 : 4 * STAT_IMGS * 2 * BLOCK_N * 4;
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
-  static constexpr int NUM_BARS = 2 + 2 * SB + 4;
+  static constexpr int SBX = SB + 4;                 // weight-ring slots incl. those carved from unused A slots (K < 64 KB_MAX)
+  static constexpr int NUM_BARS = 2 + 2 * SBX + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 
@@ -1181,15 +1182,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   const uint32_t a_full = bar_base, a_empty = bar_base + 8u;
+  constexpr int SBX = L::SBX;
   auto b_full = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 + SB + s); };
-  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SB + a); };
-  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SB + 2 + a); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 + SBX + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SBX + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 + 2 * SBX + 2 + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + L::NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = p.c1_chunks;
+  // K shorter than the reserved A region (KB_MAX k-blocks): the unused A slots become extra weight-ring slots -- the
+  // ring depth, not the tensor core, is what the MMA thread of these short-K linears waits for
+  const int sb_n = SB + min(SBX - SB, ((KB_MAX - num_kb) * L::A_SUB_BYTES) / L::B_SLOT);
+  auto b_slot = [&](int s) {
+    return s < SB ? smem_base + L::B_OFFSET + s * L::B_SLOT
+                  : smem_base + (uint32_t)num_kb * L::A_SUB_BYTES + (uint32_t)(s - SB) * L::B_SLOT;
+  };
   const int n_tiles_n = p.N / BLOCK_N;
   const int n_tiles = n_tiles_n * ((p.M + TILE_M - 1) / TILE_M);
   const int t0 = worker * tiles_per_worker;
@@ -1198,7 +1207,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
   for (int i = threadIdx.x; i < L::STAT_BYTES / 4; i += NUM_THREADS)
     reinterpret_cast<float*>(smem_gen + L::STAT_OFFSET)[i] = 0.f;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 + 2 * SB; ++s) mbar_init(bar_base + 8u * s, 1);
+    for (int s = 0; s < 2 + 2 * SBX; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), EPI_WARPS * 2);
@@ -1241,9 +1250,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(b_empty(sb), pb ^ 1u, 4);
           if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::B_BYTES);
-          tma_load_2d_2cta(smem_base + L::B_OFFSET + sb * L::B_SLOT, &tm_w, b_full(sb), kb * BLOCK_K,
-                           n0 + (int)cta_rank * (BLOCK_N / 2));
-          if (++sb == SB) {
+          tma_load_2d_2cta(b_slot(sb), &tm_w, b_full(sb), kb * BLOCK_K, n0 + (int)cta_rank * (BLOCK_N / 2));
+          if (++sb == sb_n) {
             sb = 0;
             pb ^= 1u;
           }
@@ -1273,12 +1281,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_astat_kernel(const __g
           mbar_wait(b_full(sb), pb, 5);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t a_desc = make_smem_desc(smem_base + kb * L::A_SUB_BYTES);
-          const uint64_t b_desc = make_smem_desc(smem_base + L::B_OFFSET + sb * L::B_SLOT);
+          const uint64_t b_desc = make_smem_desc(b_slot(sb));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16_2cta(tmem_acc, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
           umma_commit_2cta(b_empty(sb));
-          if (++sb == SB) {
+          if (++sb == sb_n) {
             sb = 0;
             pb ^= 1u;
           }
