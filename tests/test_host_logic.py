@@ -206,3 +206,26 @@ def test_micro_batch_join_range_of_the_launch_plan():
         pushes = len({n['group'] for n in model.plan[first:last] if n['group'].startswith('input')})
         pops = sum(1 for n in model.plan[first + 1:last] if n['kind'] == 'res' and n.get('cat'))
         assert pushes == pops
+
+
+def test_fused_temporal_kernel_is_chosen_where_it_fits():
+    """Host-side dispatch of the temporal attention block: the fused kernel (16 pixels per CTA for 96-wide heads, else 8)
+    wherever its shared memory fits, the three-launch path elsewhere.  vdm_attn_temporal_fused_smem is a pure host
+    function of the C ABI: no GPU needed."""
+    from video_diffusion_b200 import create_video_model_and_diffusion, ops, video_model_and_diffusion_defaults
+    assert ops.attn_temporal_fused_smem(20, 96, 24, 8) <= 113 * 1024            # two CTAs per SM
+    assert ops.attn_temporal_fused_smem(20, 96, 24, 16) <= 227 * 1024
+    assert ops.attn_temporal_fused_smem(32, 128, 32, 8) > 227 * 1024            # too large: fallback
+    assert ops.attn_temporal_fused_smem(20, 48, 24, 8) == -1                    # head width not instantiated
+    kw = video_model_and_diffusion_defaults()
+    kw.update(cases.ref_config('c2'))
+    model, _ = create_video_model_and_diffusion(**kw)
+    assert model._temporal_pt(20, 384, 256) == 16 and model._temporal_pt(20, 512, 64) == 8
+    assert model._temporal_pt(20, 384, 8) == 8                                  # 8 pixels per image: one tile of 8
+    assert model._temporal_pt(32, 512, 64) == 0 and model._temporal_pt(33, 384, 256) == 0
+    assert model._temporal_pt(20, 64, 256) == 0                                 # 16-wide heads (the tiny model)
+    model.fused_temporal = False
+    assert model._temporal_pt(20, 384, 256) == 0
+    import torch
+    model2, _ = create_video_model_and_diffusion(compute_dtype=torch.float32, **kw)
+    assert model2._temporal_pt(20, 384, 256) == 0                               # fp32 mode keeps the SIMT kernels
