@@ -694,10 +694,10 @@ def test_linear_rowbias_nchw_and_silu(dtype):
 
 
 @pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3), (2, 128, 128, 128, 3), (1, 6, 128, 64, 6),
-                                       (4, 8, 8, 64, 3)])
+                                       (4, 8, 8, 64, 3), (2, 32, 32, 256, 8), (1, 16, 16, 64, 1)])
 def test_output_head_conv_small_n(n, H, W, C1, N, monkeypatch):
-    """C -> 3 / 6 channel 3x3 conv with a planar (NCHW) store: the halo-tile mma.sync kernel and, for shapes it does
-    not take (8x8 here) or when switched off, the tcgen05 GEMM; both against conv2d on the same bf16-rounded data."""
+    """C -> 3 / 6 channel 3x3 conv with a planar (NCHW) store: the streaming mma.sync kernel (conv_small_n.cu; ragged row tiles, 1 to 8
+    output channels) and, for shapes it does not take (8x8 here) or when switched off, the tcgen05 GEMM; both against conv2d on the same bf16-rounded data."""
     o = ops()
     x = rnd(n, C1, H, W, seed=1).bfloat16().float()
     w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
@@ -712,8 +712,21 @@ def test_output_head_conv_small_n(n, H, W, C1, N, monkeypatch):
         assert relerr(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('n,H,W,C1,N', [(1, 37, 64, 128, 3), (1, 20, 16, 64, 1), (2, 24, 48, 64, 2), (1, 5, 80, 192, 8)])
+def test_output_head_conv_ragged_shapes(n, H, W, C1, N):
+    """Image heights that are no multiple of the row tile, widths that are no power of two (any multiple of 16):
+    shapes only the streaming kernel takes (the tcgen05 GEMM wants H*W in multiples of 128)."""
+    o = ops()
+    x = rnd(n, C1, H, W, seed=1).bfloat16().float()
+    w = rnd(N, C1, 3, 3, seed=2, scale=(9 * C1) ** -0.5).bfloat16().float()
+    b = rnd(N, seed=3)
+    out = torch.full((n, N, H, W), float('nan'), device='cuda')
+    o.gemm(nhwc(x).bfloat16(), pack_w(w).bfloat16(), N, n_img=n, H=H, W=W, taps=9, bias=b, out_f32=out, out_nchw=True)
+    assert relerr(out, F.conv2d(x, w, b, padding=1)) < 2e-5
+
+
 @pytest.mark.parametrize('n,H,W,C1,N', [(2, 64, 64, 128, 3), (3, 32, 32, 64, 6), (2, 16, 16, 192, 3), (1, 8, 128, 64, 3),
-                                       (2, 128, 128, 128, 3)])
+                                       (2, 128, 128, 128, 3), (2, 32, 32, 256, 6)])
 def test_output_head_conv_with_fused_groupnorm_silu(n, H, W, C1, N):
     """The output head reading the RAW fp16 stream: GroupNorm-apply + SiLU while the tile is staged (a1_coef +
     a1_raw_dtype), against the standalone gn_apply -> head conv pair on the same data, and against torch."""

@@ -1,169 +1,245 @@
 // 3x3 convolution with a handful of output channels (the U-Net's `out` head, unet.py:745-749: C -> 3 or 6).
 //
 // On the tcgen05 GEMM this layer wastes the tensor core (a 128 x 16 tile keeps 3 columns) and re-reads its
-// activation tile from L2 once per tap.  Here a CTA stages the 128-pixel tile WITH its one-pixel halo in shared
-// memory once (cp.async, zero fill outside the image = the conv padding), and each of its 8 warps computes
-// 16 pixels x 8 channels with mma.sync m16n8k16: ldmatrix takes one address per row, so the nine taps are just
-// nine different row addresses into the same halo tile.  Output is written planar (NCHW fp32), the layout the
-// sampler consumes.
+// activation tile from L2 once per tap.  With so few output channels the layer is a pure streaming problem (one read
+// of the activations, 2 bytes per element; the output is 1 % of that), so the kernel is built around reading every
+// activation ONCE, straight from global memory into mma.sync fragments -- no shared-memory staging of the activations:
 //
-// With `coef` (vdm_gemm_args.a1_coef) the GroupNorm-apply + SiLU in front of the head (unet.py:745-748) happens while
-// the tile is staged: x is then the RAW fp16 residual stream, every staged value becomes silu(a * x + b) with the
-// per-(image, channel) pairs of vdm_gn_coef, and positions outside the image stay zero (the conv pads the ACTIVATED
-// tensor).  The standalone GroupNorm-apply pass over the 64x64 stream and its bf16 copy disappear.
+//   1. per-pixel products for all nine taps at once:  Y[pixel][tap * N + n] = sum_c x[pixel][c] * w[n][tap][c]
+//      -- a plain GEMM over the tile's pixels (its rows plus one row above and below), 9 N <= 72 columns, K = C.
+//      mma.sync m16n8k16 leaves the K order free as long as both operands agree, so within a 32-channel block lane
+//      (g, q) takes channels q*8 .. q*8+7 of rows g and g+8 as its A fragments of two k-steps: one 16-byte global
+//      load per row and block, and the matching B fragment is one 16-byte piece of a weight row (fragment-major copy
+//      in shared memory, one LDS.128 per block and column tile).
+//   2. Y (fp32, column-major so that both the fragment stores and the gather are bank-conflict free) goes to shared
+//      memory; out[n][y][x] = bias[n] + sum_tap Y[(y + dy, x + dx)][tap * N + n], taps outside the image skipped
+//      (= the conv's zero padding), written planar (NCHW fp32), the layout the sampler consumes.
+//
+// A tile is R full image rows, so the only re-read is the two halo rows ((R + 2) / R, mostly L2 hits).
+//
+// With `coef` (vdm_gemm_args.a1_coef) the GroupNorm-apply + SiLU in front of the head (unet.py:745-748) happens in
+// registers between the global load and the mma: x is then the RAW fp16 residual stream and every value becomes
+// silu(a * x + b) with the per-(image, channel) pairs of vdm_gn_coef (same arithmetic as gn_apply, so the bf16
+// operands are the ones the two-launch path would produce).  The standalone GroupNorm-apply pass over the 64x64
+// stream and its bf16 copy disappear.
 #include "common.cuh"
 
 namespace vdm {
 namespace {
 
-constexpr int TILE_PIX = 128;
-constexpr int PAD = 8;   // bf16 elements of padding per pixel / weight row: 16 B shifts keep ldmatrix conflict-free
+constexpr int HEAD_THREADS = 256;
+// coefficient pairs of 8 channels sit 80 bytes apart: the four 16-byte pieces a quarter warp reads (q = 0..3) then
+// fall into different banks
+constexpr int CSTRIDE = 10;
 
-__device__ __forceinline__ void cp16_zfill(void* smem, const void* gmem, bool valid) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
-  const int bytes = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a), "l"(gmem), "r"(bytes) : "memory");
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 
-template <bool XF>   // XF: x is the raw fp16 stream, normalised + activated while it is staged
-__global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const uint16_t* __restrict__ x,          // [n_img][H][W][C]
-                                                               const __nv_bfloat16* __restrict__ w,   // [N][9*C]
-                                                               const float* __restrict__ bias, int H, int W, int TW,
-                                                               int C, int N, const float2* __restrict__ coef, int act,
-                                                               float* __restrict__ out /* [n_img][N][H*W] */) {
+// act(a * x + b) of eight fp16 values -> four bf16 pairs; csm8 = the eight staged coefficient pairs of these channels.
+// With ACT the staged pairs are (a / 2, b / 2), so h = fma(a / 2, x, b / 2) is EXACTLY half of gn_apply's
+// v = fma(a, x, b), and h * (tanh(h) + 1) rounds exactly like its silu_tanh(v) = v * fma(0.5, tanh(v / 2), 0.5)
+// (scaling by two commutes with rounding): bit-identical operands for four instructions per value instead of five.
+template <bool ACT>
+__device__ __forceinline__ uint4 norm_act8(const uint4 v, const float2* csm8) {
+  const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_f16x2(wv[i]);
+    const float4 ab = *reinterpret_cast<const float4*>(csm8 + 2 * i);   // (a0, b0, a1, b1)
+    float y0 = fmaf(ab.x, f.x, ab.y), y1 = fmaf(ab.z, f.y, ab.w);
+    if (ACT) {
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(y0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(y1));
+      y0 = y0 * (t0 + 1.0f);
+      y1 = y1 * (t1 + 1.0f);
+    }
+    r[i] = pack_bf16x2(y0, y1);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+// XF: x is the raw fp16 stream, normalised + activated in registers.  KB = C / 32, NT = column tiles of 8 (>= 9 N / 8).
+// (Keeping a warp's next pass in flight under the current one -- 32 more registers at C = 128 -- and the maximum
+// shared-memory carveout were measured: 74.6 vs 78.2 us / slower for the pre-activated operand, and 89 vs 78 us.)
+template <bool XF, int KB, int NT>
+__global__ void __launch_bounds__(HEAD_THREADS, 2)
+conv3x3_head_kernel(const uint16_t* __restrict__ x,          // [n_img][H][W][C]  bf16 (or raw fp16 with XF)
+                    const __nv_bfloat16* __restrict__ w,     // [N][9 * C]
+                    const float* __restrict__ bias, int H, int W, int R, int N, int P,
+                    const float2* __restrict__ coef, int act, float* __restrict__ out /* [n_img][N][H*W] */) {
   pdl_launch_dependents();
   pdl_wait();   // PDL protocol (common.cuh): nothing global is touched before this line
+  constexpr int C = KB * 32;
   extern __shared__ __align__(16) uint8_t smem[];
-  // tile = R image rows x TW columns (column strips keep the halo tile small: several CTAs per SM, little re-reading)
-  const int R = TILE_PIX / TW;
-  const int Wp = TW + 2, Cp = C + PAD;
-  __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem);                 // [(R+2)][Wp][Cp]
-  __nv_bfloat16* wsm = halo + (size_t)(R + 2) * Wp * Cp;                        // [9][8][Cp]
-  const int strips = W / TW;
-  const int tiles_per_img = H * W / TILE_PIX;
+  float* ysm = reinterpret_cast<float*>(smem);                                   // [9 N][P]
+  uint4* bsm = reinterpret_cast<uint4*>(ysm + (size_t)9 * N * P);                // [KB][NT][32 lanes]
+  float2* csm = reinterpret_cast<float2*>(bsm + KB * NT * 32);                   // [C / 8][CSTRIDE] (XF only)
+  const int tiles_per_img = (H + R - 1) / R;
   const int img = blockIdx.x / tiles_per_img;
-  const int t_in_img = blockIdx.x - img * tiles_per_img;
-  const int y0 = (t_in_img / strips) * R;
-  const int x0 = (t_in_img % strips) * TW;
+  const int y0 = (blockIdx.x - img * tiles_per_img) * R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C8 = C / 8;
+  const int g = lane >> 2, q = lane & 3;
 
-  // ---- stage the halo tile and the weights (index = pixel * C8 + chunk, advanced without divisions)
+  // ---- the tile's passes: 16 consecutive pixels of a row each; rows outside the image are never gathered, so the
+  //      valid passes are one contiguous range
   const uint16_t* ximg = x + (size_t)img * H * W * C;
-  if constexpr (!XF) {
-    const int total = (R + 2) * Wp * C8;
-    const int step_pix = (int)blockDim.x / C8, step_c8 = (int)blockDim.x % C8;
-    const int step_y = step_pix / Wp, step_x = step_pix % Wp;
-    int c8 = tid % C8, pix = tid / C8;
-    int hy = pix / Wp, hx = pix % Wp;
-    for (int i = tid; i < total; i += blockDim.x) {
-      const int xx = x0 + hx - 1, yy = y0 + hy - 1;
-      const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;
-      cp16_zfill(halo + (size_t)pix * Cp + c8 * 8, ok ? ximg + ((size_t)yy * W + xx) * C + c8 * 8 : ximg, ok);
-      c8 += step_c8; pix += step_pix; hx += step_x; hy += step_y;
-      if (c8 >= C8) { c8 -= C8; ++pix; ++hx; }
-      if (hx >= Wp) { hx -= Wp; ++hy; }
-      if (hx >= Wp) { hx -= Wp; ++hy; }
+  const int hr_lo = y0 == 0 ? 1 : 0, hr_hi = min(R + 2, H - y0 + 1);
+  const int mt_hi = hr_hi * W / 16;
+  int mt = hr_lo * W / 16 + warp;
+  uint4 alo[KB], ahi[KB];
+  auto load_pass = [&](int m) {
+    const int hp = m * 16, hr = hp / W;
+    const uint16_t* row_lo = ximg + ((size_t)(y0 - 1 + hr) * W + (hp - hr * W) + g) * C + q * 8;
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      alo[kb] = ldg_stream16(row_lo + kb * 32);
+      ahi[kb] = ldg_stream16(row_lo + (size_t)8 * C + kb * 32);
     }
-  } else {
-    // the image's (a, b) pairs behind the weights; then batches of four 16-byte loads in flight per thread
-    float2* csm = reinterpret_cast<float2*>(wsm + (size_t)9 * 8 * Cp);
-    for (int c = tid; c < C; c += blockDim.x) csm[c] = __ldg(coef + (size_t)img * C + c);
-    __syncthreads();
-    const int total = (R + 2) * Wp * C8;
-    for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
-      uint4 v[4];
-      int pixs[4], c8s[4];
-      bool oks[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * blockDim.x;
-        const int pix = i / C8, c8 = i - pix * C8;
-        const int hy = pix / Wp, hx = pix - hy * Wp;
-        const int xx = x0 + hx - 1, yy = y0 + hy - 1;
-        oks[u] = i < total && xx >= 0 && xx < W && yy >= 0 && yy < H;
-        pixs[u] = pix; c8s[u] = c8;
-        v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (oks[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(ximg + ((size_t)yy * W + xx) * C + c8 * 8));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * (int)blockDim.x >= total) break;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (oks[u]) {
-          const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          uint32_t r[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = unpack_f16x2(wv[q]);
-            const float4 ab = *reinterpret_cast<const float4*>(csm + c8s[u] * 8 + 2 * q);   // (a0, b0, a1, b1)
-            float y0v = fmaf(ab.x, f.x, ab.y), y1v = fmaf(ab.z, f.y, ab.w);
-            if (act) { y0v = silu_tanh(y0v); y1v = silu_tanh(y1v); }
-            r[q] = pack_bf16x2(y0v, y1v);
-          }
-          o = make_uint4(r[0], r[1], r[2], r[3]);
-        }
-        *reinterpret_cast<uint4*>(halo + (size_t)pixs[u] * Cp + c8s[u] * 8) = o;
-      }
+  };
+
+  // ---- weights as B fragments: lane (g, q) of column tile j holds channels q*8..q*8+7 of column 8 j + g
+  for (int i = tid; i < KB * NT * 32; i += HEAD_THREADS) {
+    const int l = i & 31, j = (i >> 5) % NT, kb = i / (32 * NT);
+    const int col = 8 * j + (l >> 2);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (col < 9 * N) {
+      const int tap = col / N, n = col - tap * N;
+      v = __ldg(reinterpret_cast<const uint4*>(w + ((size_t)n * 9 + tap) * C + kb * 32 + (l & 3) * 8));
     }
+    bsm[i] = v;
   }
-  for (int i = tid; i < 9 * 8 * C8; i += blockDim.x) {
-    const int c8 = i % C8, n = (i / C8) % 8, tap = i / (8 * C8);
-    cp16_zfill(wsm + (size_t)(tap * 8 + n) * Cp + c8 * 8, n < N ? w + ((size_t)n * 9 + tap) * C + c8 * 8 : w, n < N);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if constexpr (XF)
+    for (int c = tid; c < C; c += HEAD_THREADS) {
+      float2 ab = __ldg(coef + (size_t)img * C + c);
+      if (act) { ab.x *= 0.5f; ab.y *= 0.5f; }   // see norm_act8
+      csm[(c >> 3) * CSTRIDE + (c & 7)] = ab;
+    }
   __syncthreads();
 
-  // ---- warp = 16 consecutive pixels of one image row
-  const int p0 = warp * 16;
-  const int ry = p0 / TW, rx = p0 - ry * TW;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two chains: even / odd k-steps
-  const int a_row = lane & 15, a_k = (lane >> 4) * 8;       // ldmatrix.x4 row / k-half supplied by this lane
-  const int b_n = lane >> 2, b_k = (lane & 3) * 2;
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3, dx = tap - dy * 3;              // halo coordinates already include the -1
-    const __nv_bfloat16* arow = halo + ((size_t)(ry + dy) * Wp + rx + dx + a_row) * Cp + a_k;
-    const __nv_bfloat16* brow = wsm + (size_t)(tap * 8 + b_n) * Cp + b_k;
-#pragma unroll 2
-    for (int k0 = 0; k0 < C; k0 += 32) {
-      uint32_t a[4], a2[4];
-      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(arow + k0);
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(a2[0]), "=r"(a2[1]), "=r"(a2[2]), "=r"(a2[3]) : "r"(addr + 32u));
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + k0);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + k0 + 8);
-      const uint32_t b2 = *reinterpret_cast<const uint32_t*>(brow + k0 + 16);
-      const uint32_t b3 = *reinterpret_cast<const uint32_t*>(brow + k0 + 24);
-      asm volatile(
-          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-          "{%0, %1, %2, %3};"
-          : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
-          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-      asm volatile(
-          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-          "{%0, %1, %2, %3};"
-          : "+f"(acc2[0]), "+f"(acc2[1]), "+f"(acc2[2]), "+f"(acc2[3])
-          : "r"(a2[0]), "r"(a2[1]), "r"(a2[2]), "r"(a2[3]), "r"(b2), "r"(b3));
+  // ---- Y = x W^T over the tile's rows and its halo rows
+  for (; mt < mt_hi; mt += HEAD_THREADS / 32) {
+    const int hp = mt * 16;                       // first pixel of the pass, halo-tile numbering ((R + 2) x W)
+    uint4 clo[KB], chi[KB];
+    load_pass(mt);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) { clo[kb] = alo[kb]; chi[kb] = ahi[kb]; }
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      uint4 lo = clo[kb], hi = chi[kb];
+      if constexpr (XF) {
+        const float2* c8 = csm + (kb * 4 + q) * CSTRIDE;
+        if (act) { lo = norm_act8<true>(lo, c8); hi = norm_act8<true>(hi, c8); }
+        else { lo = norm_act8<false>(lo, c8); hi = norm_act8<false>(hi, c8); }
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const uint4 b = bsm[(kb * NT + j) * 32 + lane];
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+            "{%0, %1, %2, %3};"
+            : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+            : "r"(lo.x), "r"(hi.x), "r"(lo.y), "r"(hi.y), "r"(b.x), "r"(b.y));
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+            "{%0, %1, %2, %3};"
+            : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+            : "r"(lo.z), "r"(hi.z), "r"(lo.w), "r"(hi.w), "r"(b.z), "r"(b.w));
+      }
+    }
+    // accumulator layout: acc[.][0,1] = (row g, cols 2 q + {0,1}); acc[.][2,3] = row g + 8
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * j + 2 * q + e;
+        if (col < 9 * N) {
+          float* yc = ysm + (size_t)col * P + hp + g;
+          yc[0] = acc[j][e];
+          yc[8] = acc[j][2 + e];
+        }
+      }
+  }
+  __syncthreads();
+
+  // ---- gather the nine taps (fixed order), planar store: a thread keeps its image column and walks rows / channels
+  const int groups = HEAD_THREADS / W;
+  const int grp = tid / W, xx = tid - grp * W;
+  if (grp < groups) {
+    const bool okl = xx > 0, okr = xx < W - 1;
+    const size_t tap_stride = (size_t)N * P;
+    for (int r = grp; r < R && y0 + r < H; r += groups) {
+      const int y = y0 + r;
+      const bool oku = y > 0, okd = y < H - 1;
+      const float* yb = ysm + r * W + xx;          // halo row r = image row y - 1
+      float* orow = out + (size_t)img * N * H * W + (size_t)y * W + xx;
+      for (int n = 0; n < N; ++n) {
+        float v[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const bool ok = (dy == 0 ? oku : (dy == 2 ? okd : true)) && (dx == 0 ? okl : (dx == 2 ? okr : true));
+          v[tap] = 0.f;
+          if (ok) v[tap] = yb[tap * tap_stride + (size_t)n * P + dy * W + dx - 1];
+        }
+        float s = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) s += v[tap];
+        orow[(size_t)n * H * W] = s;
+      }
     }
   }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
-  // accumulator layout: acc[0,1] = (row lane/4, cols 2*(lane%4) + {0,1}); acc[2,3] = row + 8
-  const int HW = H * W;
-  const int pix = (y0 + ry) * W + x0 + rx + (lane >> 2);
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int n = (lane & 3) * 2 + e;
-    if (n < N) {
-      const float bv = bias ? bias[n] : 0.f;
-      float* o = out + ((size_t)img * N + n) * HW + pix;
-      o[0] = acc[e] + bv;
-      o[8] = acc[2 + e] + bv;
+}
+
+struct HeadCfg {
+  int H, W, R, N, P;
+  size_t smem;
+  int grid;
+};
+
+template <bool XF, int KB, int NT>
+int launch_head(const vdm_gemm_args* a, const HeadCfg& c, cudaStream_t stream) {
+  static PerDevice<size_t> configured;
+  auto* kernel = conv3x3_head_kernel<XF, KB, NT>;
+  if (c.smem > configured.get()) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) {
+      set_error("conv3x3_small_n: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
     }
+    configured.get() = c.smem;
+  }
+  launch_kernel(kernel, c.grid, HEAD_THREADS, c.smem, stream, 1, reinterpret_cast<const uint16_t*>(a->a1),
+                reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, c.H, c.W, c.R, c.N, c.P,
+                reinterpret_cast<const float2*>(a->a1_coef), (int)a->a1_act, a->out_f32);
+  return 0;
+}
+
+template <bool XF, int KB>
+int launch_head_nt(const vdm_gemm_args* a, const HeadCfg& c, int nt, cudaStream_t stream) {
+  switch (nt) {
+    case 4: return launch_head<XF, KB, 4>(a, c, stream);
+    case 7: return launch_head<XF, KB, 7>(a, c, stream);
+    default: return launch_head<XF, KB, 9>(a, c, stream);
+  }
+}
+
+template <bool XF>
+int launch_head_kb(const vdm_gemm_args* a, const HeadCfg& c, int kb, int nt, cudaStream_t stream) {
+  switch (kb) {
+    case 2: return launch_head_nt<XF, 2>(a, c, nt, stream);
+    case 4: return launch_head_nt<XF, 4>(a, c, nt, stream);
+    case 6: return launch_head_nt<XF, 6>(a, c, nt, stream);
+    case 8: return launch_head_nt<XF, 8>(a, c, nt, stream);
+    default: return -100;
   }
 }
 
@@ -173,42 +249,28 @@ __global__ void __launch_bounds__(256) conv3x3_small_n_kernel(const uint16_t* __
 // GEMM), 0 on success.
 int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   const int W = a->W, H = a->H, C = a->C1, N = a->N;
-  // tile = (128 / TW) rows x TW columns: narrow strips of many rows re-read the least halo (TW 16: 1.41x, 32: 1.59x,
-  // 64: 2.06x; measured 0.124 / 0.130 / 0.161 ms on 160 x 64 x 64 x 128) -- the narrowest strip the image height allows
-  int TW = W;
-  for (int tw = 16; tw <= 64; tw *= 2)
-    if (W % tw == 0 && H % (TILE_PIX / tw) == 0) {
-      TW = tw;
-      break;
-    }
   const bool xf = a->a1_coef != nullptr;
-  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N <= 8 && C % 32 == 0 && W >= 16 &&
-        W % TW == 0 && TILE_PIX % TW == 0 && H % (TILE_PIX / TW) == 0 && a->out_f32 && !a->out_bf16 && !a->residual &&
-        !a->rowbias && !a->stats_out && (!xf || a->a1_raw_dtype == VDM_F16) && (xf || a->a1_raw_dtype == 0)))
+  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N >= 1 && N <= 8 && C % 64 == 0 && C <= 256 &&
+        W % 16 == 0 && W <= HEAD_THREADS && a->out_f32 && !a->out_bf16 && !a->residual && !a->rowbias && !a->stats_out &&
+        (!xf || a->a1_raw_dtype == VDM_F16) && (xf || a->a1_raw_dtype == 0)))
     return -100;
-  const int R = TILE_PIX / TW;
-  const size_t smem = ((size_t)(R + 2) * (TW + 2) + 9 * 8) * (C + PAD) * sizeof(__nv_bfloat16) +
-                      (xf ? (size_t)C * sizeof(float2) : 0);
-  if (smem > 200 * 1024) return -100;
-  static PerDevice<size_t> configured[2];
-  if (smem > configured[xf].get()) {
-    cudaError_t e = xf ? cudaFuncSetAttribute(conv3x3_small_n_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                       : cudaFuncSetAttribute(conv3x3_small_n_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("conv3x3_small_n: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured[xf].get() = smem;
-  }
-  const int grid = a->n_img * (H * W / TILE_PIX);
-  if (xf)
-    launch_kernel(conv3x3_small_n_kernel<true>, grid, 256, smem, (cudaStream_t)stream, 1,
-                  reinterpret_cast<const uint16_t*>(a->a1), reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW,
-                  C, N, reinterpret_cast<const float2*>(a->a1_coef), (int)a->a1_act, a->out_f32);
-  else
-    launch_kernel(conv3x3_small_n_kernel<false>, grid, 256, smem, (cudaStream_t)stream, 1,
-                  reinterpret_cast<const uint16_t*>(a->a1), reinterpret_cast<const __nv_bfloat16*>(a->w), a->bias, H, W, TW,
-                  C, N, static_cast<const float2*>(nullptr), 0, a->out_f32);
+  // R image rows per CTA: as many as keep the fp32 product tile (9 N columns of (R + 2) W pixels) near 70 KB -- two
+  // CTAs per SM -- and at most 16; fewer rows re-read more halo ((R + 2) / R)
+  HeadCfg c{};
+  c.H = H; c.W = W; c.N = N;
+  int R = (int)(70 * 1024 / ((size_t)36 * N * W)) - 2;
+  R = R < 1 ? 1 : (R > 16 ? 16 : R);
+  if (R > H) R = H;
+  c.R = R;
+  c.P = (R + 2) * W;
+  c.P += (36 - c.P % 32) % 32;            // P = 4 (mod 32): the fragment stores of a warp hit 32 different banks
+  const int nt = 9 * N <= 32 ? 4 : (9 * N <= 56 ? 7 : 9);
+  c.smem = (size_t)9 * N * c.P * sizeof(float) + (size_t)(C / 32) * nt * 32 * sizeof(uint4) +
+           (xf ? (size_t)(C / 8) * CSTRIDE * sizeof(float2) : 0);
+  if (c.smem > 200 * 1024) return -100;
+  c.grid = a->n_img * ((H + R - 1) / R);
+  const int rc = xf ? launch_head_kb<true>(a, c, C / 32, nt, stream) : launch_head_kb<false>(a, c, C / 32, nt, stream);
+  if (rc != 0) return rc;
   VDM_AFTER_LAUNCH("conv3x3_small_n");
   return 0;
 }
