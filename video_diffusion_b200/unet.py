@@ -809,7 +809,11 @@ class UNetModel(nn.Module):
         if self.overlap_rpe_tables and (ops.PROFILE is None or ops.PROFILE_STREAMS is not None):
             main = torch.cuda.current_stream()
             if ws.side is None:
-                ws.side = torch.cuda.Stream(device=ws.dev)
+                # high priority: the branch is a chain of small launches that the U-Net body waits for (first scale/shift
+                # GroupNorm, first attention block); without it they queue behind the body's persistent GEMM grids
+                # (VDM_SIDE_PRIORITY=0: default priority, for A/B runs)
+                prio = 0 if os.environ.get('VDM_SIDE_PRIORITY') == '0' else -1
+                ws.side = torch.cuda.Stream(device=ws.dev, priority=prio)
                 ws.ev_fork, ws.ev_emb, ws.ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             ws.ev_fork.record(main)
             ws.side.wait_event(ws.ev_fork)
