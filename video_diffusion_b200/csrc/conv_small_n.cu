@@ -250,7 +250,7 @@ int launch_head_kb(const vdm_gemm_args* a, const HeadCfg& c, int kb, int nt, cud
 int conv3x3_small_n(const vdm_gemm_args* a, cudaStream_t stream) {
   const int W = a->W, H = a->H, C = a->C1, N = a->N;
   const bool xf = a->a1_coef != nullptr;
-  if (!(a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N >= 1 && N <= 8 && C % 64 == 0 && C <= 256 &&
+  if (!(a->dtype == VDM_BF16 && a->io_dtype != VDM_F16 && a->taps == 9 && a->a1_mode == 0 && a->C2 == 0 && a->out_nchw && N >= 1 && N <= 8 && C % 64 == 0 && C <= 256 &&
         W % 16 == 0 && W <= HEAD_THREADS && a->out_f32 && !a->out_bf16 && !a->residual && !a->rowbias && !a->stats_out &&
         (!xf || a->a1_raw_dtype == VDM_F16) && (xf || a->a1_raw_dtype == 0)))
     return -100;
