@@ -183,12 +183,16 @@ class PipelinedHostStepper:
     """`diffusion.p_sample` for callers whose inputs and results live in (pinned) HOST memory: the inputs of step i + 1 are
     uploaded on a copy stream while step i computes, and the sample of step i is downloaded while step i + 1 computes,
     so the PCIe transfers (15.7 MB up + 7.9 MB down per C2 step) disappear behind the 12-13 ms of compute instead of
-    adding to them.  Two device-side input slots; a slot is rewritten only after the step that read it has been
-    enqueued past its input copy."""
+    adding to them.  Uploads and downloads have a stream each (`up_stream`, `copy`): on ONE stream the upload of step
+    i + 1 queues behind the download of step i, which waits for step i's compute -- the upload then starts only after
+    the step it was meant to hide under.  Two device-side input slots; a slot is rewritten only after the step that
+    read it has been enqueued past its input copy."""
 
     def __init__(self, model, diffusion, device):
         self.model, self.diffusion, self.device = model, diffusion, torch.device(device)
-        self.copy = torch.cuda.Stream(device=self.device)
+        self.copy = torch.cuda.Stream(device=self.device)           # downloads
+        # uploads (VDM_STEPPER_ONE_STREAM=1: share the download stream, for A/B runs)
+        self.up_stream = self.copy if os.environ.get('VDM_STEPPER_ONE_STREAM') == '1' else torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
         self.up = [torch.cuda.Event(), torch.cuda.Event()]
         self.used = [None, None]
@@ -200,13 +204,13 @@ class PipelinedHostStepper:
             bufs = self.slots[slot] = dict({k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
                                             for k, v in kw_pin.items()}, __x=torch.empty(x_pin.shape, dtype=x_pin.dtype,
                                                                                         device=self.device))
-        with torch.cuda.stream(self.copy):
+        with torch.cuda.stream(self.up_stream):
             if self.used[slot] is not None:
-                self.copy.wait_event(self.used[slot])
+                self.up_stream.wait_event(self.used[slot])
             bufs['__x'].copy_(x_pin, non_blocking=True)
             for k, v in kw_pin.items():
                 bufs[k].copy_(v, non_blocking=True)
-            self.up[slot].record(self.copy)
+            self.up[slot].record(self.up_stream)
         return bufs
 
     def step(self, x_pin, t, kw_pin, out_pin, **p_sample_kwargs):
@@ -231,6 +235,7 @@ class PipelinedHostStepper:
         return s
 
     def drain(self):
+        self.up_stream.synchronize()
         self.copy.synchronize()
 
 
